@@ -1,0 +1,209 @@
+/*
+ * mbpo_b200.h -- C ABI of the B200-native iCEM planning hot path.
+ *
+ * Drop-in boundary for lasgroup/Model-based-policy-optimizers (reference paths below are
+ * relative to the reference repository root).  The reference has no FFI of its own (it
+ * is pure JAX); every entry point here replaces one jitted Python function, and the
+ * Python host package (model-based-policy-optimizers_b200/mbpo_b200) binds them with
+ * ctypes behind the reference's unchanged call signatures.  See INTEGRATION.md.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless the name ends in _host.
+ *   - All arrays are dense row-major with the shapes in the comments; float = IEEE
+ *     binary32, keys = uint32[2] (JAX threefry key data).
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that
+ *     stream, never synchronises the device, and allocates no device memory.
+ *   - Return value: 0 (MBPO_OK) or a negative MBPO_E* code; the message is available
+ *     from mbpo_last_error() (thread local).  There is NO CPU fallback.
+ */
+#ifndef MBPO_B200_H_
+#define MBPO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MBPO_ABI_VERSION 1
+#define MBPO_MAX_HORIZON 128
+#define MBPO_MAX_FREQ (MBPO_MAX_HORIZON / 2 + 1)
+
+enum {
+  MBPO_OK = 0,
+  MBPO_EINVAL = -1,      /* bad shape / null pointer / inconsistent config */
+  MBPO_EUNSUPPORTED = -2,/* unsupported system_kind / horizon / action_dim for this kernel */
+  MBPO_ECUDA = -3,       /* CUDA runtime error (launch, attribute)          */
+  MBPO_EWORKSPACE = -4   /* caller workspace too small                      */
+};
+
+enum { MBPO_PRNG_LEGACY = 0, MBPO_PRNG_PARTITIONABLE = 1 }; /* jax_threefry_partitionable */
+enum { MBPO_SUMMARIZE_MEAN = 0, MBPO_SUMMARIZE_MAX = 1 };   /* icem_optimizer.py:112-115 */
+enum { MBPO_SYSTEM_PENDULUM = 0, MBPO_SYSTEM_MLP_ENSEMBLE = 1 };
+/* MBPO_MATH_REFERENCE follows pendulum_dynamics.py:35,43 literally (theta re-derived with
+ * atan2 from [cos, sin] every step).  MBPO_MATH_THETA_CARRY keeps theta in a register and
+ * wraps it to (-pi, pi]; mathematically identical, rounding differs. */
+enum { MBPO_MATH_REFERENCE = 0, MBPO_MATH_THETA_CARRY = 1 };
+
+/* PendulumDynamicsParams (mbpo/systems/dynamics/pendulum_dynamics.py:12-19) followed by
+ * PendulumRewardParams (mbpo/systems/rewards/pendulum_reward.py:12-16), same order. */
+typedef struct MbpoPendulumParams {
+  float max_speed, max_torque, dt, g, m, l;
+  float control_cost, angle_cost, target_angle;
+} MbpoPendulumParams;
+
+/* Learned MLP-ensemble System (template: mbpo/utils/network_utils.py:5-17, swish).
+ * E members of [x_dim+u_dim -> hidden -> hidden -> hidden -> x_dim], predicting delta-x.
+ * w_in  float[E, x_dim+u_dim, hidden]   b_in  float[E, hidden]
+ * w_h   bf16 [E, 2, hidden(out), hidden(in)]  (K-major, i.e. transposed Dense kernels)
+ * b_h   float[E, 2, hidden]
+ * w_out float[E, hidden, x_dim]         b_out float[E, x_dim]
+ * The reward is the pendulum reward on the current state. */
+typedef struct MbpoMlpEnsembleParams {
+  int32_t num_members, hidden, x_dim, u_dim;
+  const float* w_in;
+  const float* b_in;
+  const uint16_t* w_h;
+  const float* b_h;
+  const float* w_out;
+  const float* b_out;
+  MbpoPendulumParams reward;
+} MbpoMlpEnsembleParams;
+
+/* iCemParams (mbpo/optimizers/trajectory_optimizers/icem_optimizer.py:25-50) plus the
+ * static shapes jit closes over.  Fill with mbpo_icem_cfg_init(). */
+typedef struct MbpoIcemCfg {
+  int32_t horizon;          /* H */
+  int32_t action_dim;       /* A */
+  int32_t x_dim;            /* X */
+  int32_t num_samples;      /* N  :40 */
+  int32_t num_elites;       /* K  :41 */
+  int32_t num_prev_elites;  /* Np = max(int(elite_set_fraction*K),1)  :170 */
+  int32_t num_particles;    /* P  :39 */
+  int32_t num_steps;        /* S  :44 */
+  int32_t warm_start;       /* :49 */
+  int32_t prng_mode;        /* MBPO_PRNG_* */
+  int32_t summarize;        /* MBPO_SUMMARIZE_* (use_optimism) */
+  int32_t system_kind;      /* MBPO_SYSTEM_* */
+  int32_t math_mode;        /* MBPO_MATH_* */
+  float init_std;           /* :42 */
+  float alpha;              /* :43 */
+  float exponent;           /* :45 */
+  float u_min, u_max;       /* :47-48 (scalar form) */
+  float lambda_constraint;  /* :50 (unused without cost_fn) */
+  /* trace-time constants of powerlaw_psd_gaussian (general_utils.py:143-178) */
+  float sigma;
+  float s_scale[MBPO_MAX_FREQ];
+} MbpoIcemCfg;
+
+/* Optional per-iteration dumps of mbpo_icem_plan for parity tests (any pointer may be
+ * NULL).  M = N + Np. */
+typedef struct MbpoIcemTrace {
+  float* actions;      /* [S, B, M, H*A]  clipped samples + zero rows  (:190-192) */
+  float* values;       /* [S, B, M]       objective values             (:195)     */
+  int32_t* elite_idx;  /* [S, B, K]       argsort(values)[-K:]         (:199)     */
+  float* mean;         /* [S, B, H*A]     refit mean after iteration   (:210)     */
+  float* std;          /* [S, B, H*A]     refit std after iteration    (:214)     */
+  float* best_value;   /* [S, B]          best-so-far value            (:217-226) */
+} MbpoIcemTrace;
+
+int mbpo_abi_version(void);
+const char* mbpo_last_error(void);
+/* sizeof() of the ABI structs, so that a foreign binding can verify its own layout:
+ * which = 0 MbpoIcemCfg, 1 MbpoPendulumParams, 2 MbpoMlpEnsembleParams, 3 MbpoIcemTrace;
+ * anything else returns 0. */
+size_t mbpo_struct_size(int which);
+
+/* Host helper: fills every field from iCemParams + shapes and computes s_scale/sigma
+ * exactly as general_utils.py:143-178 does at trace time (float32 arithmetic). */
+int mbpo_icem_cfg_init(MbpoIcemCfg* cfg_host, int horizon, int action_dim, int x_dim,
+                       int num_particles, int num_samples, int num_elites, float init_std,
+                       float alpha, int num_steps, float exponent, float elite_set_fraction,
+                       float u_min, float u_max, int warm_start, float lambda_constraint);
+
+/* ---- JAX PRNG (jax.random.split / random_bits / uniform / normal), vmapped over M keys --- */
+int mbpo_prng_split(const uint32_t* keys /*[M,2]*/, int M, int num, int prng_mode,
+                    uint32_t* keys_out /*[M,num,2]*/, void* stream);
+int mbpo_prng_random_bits(const uint32_t* keys /*[M,2]*/, int M, int n, int prng_mode,
+                          uint32_t* bits_out /*[M,n]*/, void* stream);
+int mbpo_prng_uniform(const uint32_t* keys, int M, int n, int prng_mode, float lo, float hi,
+                      float* out /*[M,n]*/, void* stream);
+int mbpo_prng_normal(const uint32_t* keys, int M, int n, int prng_mode, float* out /*[M,n]*/,
+                     void* stream);
+
+/* ---- stage 1: colored-noise action sampling ------------------------------------------- */
+/* vmap(powerlaw_psd_gaussian(exponent, H, key)) (general_utils.py:81-208).
+ * bits_out (optional) receives the raw uint32 words behind sr and si: [M, 2, H/2+1]. */
+int mbpo_powerlaw_noise(const MbpoIcemCfg* cfg_host, const uint32_t* keys /*[M,2]*/, int M,
+                        float* noise_out /*[M,H]*/, uint32_t* bits_out, void* stream);
+/* One iCEM iteration of key plumbing + sampling (icem_optimizer.py:174-192) for B problems. */
+int mbpo_icem_sample_actions(const MbpoIcemCfg* cfg_host, const uint32_t* carry_key /*[B,2]*/,
+                             const float* mean /*[B,H,A]*/, const float* std /*[B,H,A]*/, int B,
+                             float* actions_out /*[B,N+Np,H,A]*/, uint32_t* next_key_out /*[B,2]*/,
+                             uint32_t* particle_keys_out /*[B,N+Np,2] or NULL*/, void* stream);
+
+/* ---- stage 2: rollouts ------------------------------------------------------------------ */
+/* vmap(System.step) (base_systems.py:40-52; pendulum_system.py:18-39). */
+int mbpo_system_step(int system_kind, const void* sys_params_host, int math_mode,
+                     const float* x /*[R,X]*/, const float* u /*[R,A]*/, int R,
+                     float* x_next /*[R,X]*/, float* reward /*[R]*/, void* stream);
+/* vmap(vmap(rollout_actions)) (optimizer_utils.py:11-59) + horizon mean (icem :160).
+ * x0 [B,X]; actions [B,M,H,A]; returns_out [B,M] (NULL to skip).  The Transition buffers
+ * obs_out/next_obs_out [B,M,H,X] and reward_out [B,M,H] are optional (NULL to skip). */
+int mbpo_rollout_actions(int system_kind, const void* sys_params_host, int math_mode,
+                         int horizon, int action_dim, int x_dim, const float* x0,
+                         const float* actions, int B, int M, float* returns_out, float* obs_out,
+                         float* reward_out, float* next_obs_out, void* stream);
+
+/* ---- stage 3: elite selection + refit + best tracking (icem_optimizer.py:199-226) ------- */
+int mbpo_icem_elite_refit(const MbpoIcemCfg* cfg_host, const float* actions /*[B,M,H*A]*/,
+                          const float* values /*[B,M]*/, const float* mean_in /*[B,H*A]*/,
+                          const float* std_in, const float* best_value_in /*[B]*/,
+                          const float* best_seq_in /*[B,H*A]*/, int B, float* mean_out,
+                          float* std_out, float* best_value_out, float* best_seq_out,
+                          int32_t* elite_idx_out /*[B,K] or NULL*/, void* stream);
+
+/* ---- fused plan: iCemTO.optimize (icem_optimizer.py:134-252) vmapped over B problems ---- */
+int mbpo_icem_plan(const MbpoIcemCfg* cfg_host, const void* sys_params_host,
+                   const float* x0 /*[B,X]*/, const uint32_t* key_in /*[B,2]*/,
+                   const float* best_seq_in /*[B,H,A]*/, int B, float* best_seq_out /*[B,H,A]*/,
+                   float* best_value_out /*[B]*/, uint32_t* key_out /*[B,2]*/,
+                   const MbpoIcemTrace* trace_host /*NULL = no dumps*/, void* stream);
+/* 1 if mbpo_icem_plan runs this configuration as the single fused kernel, 0 if it composes
+ * the staged kernels through `workspace`. */
+int mbpo_icem_plan_is_fused(const MbpoIcemCfg* cfg_host);
+size_t mbpo_icem_workspace_bytes(const MbpoIcemCfg* cfg_host, int B);
+int mbpo_icem_plan_staged(const MbpoIcemCfg* cfg_host, const void* sys_params_host,
+                          const float* x0, const uint32_t* key_in, const float* best_seq_in, int B,
+                          float* best_seq_out, float* best_value_out, uint32_t* key_out,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- closed-loop MPC (tests/test_icemopt.py:19-32): plan -> system.step -> warm start ---- */
+int mbpo_icem_mpc_closed_loop(const MbpoIcemCfg* cfg_host, const void* sys_params_host,
+                              const float* x0 /*[B,X]*/, const uint32_t* key_in /*[B,2]*/,
+                              const float* best_seq_in /*[B,H,A]*/, int B, int num_mpc_steps,
+                              float* states_out /*[T,B,X]*/, float* rewards_out /*[T,B]*/,
+                              float* actions_out /*[T,B,A]*/, float* best_seq_out /*[B,H,A]*/,
+                              uint32_t* key_out /*[B,2]*/, void* stream);
+
+/* ---- vmapped env rollouts for SAC/PPO collection ---------------------------------------- */
+/* brax_wrapper.py:40-50 + brax_utils/training.py:71-74,91-107,119-137 + sac/acting.py:35-55.
+ * In/out env state: obs [E,X], steps [E], done [E] (float, as brax), first_obs [E,X].
+ * actions [T,E,A].  Transition outputs are time-major: observation/next_observation
+ * [T,E,X], reward/discount/truncation [T,E].  Any output pointer may be NULL. */
+int mbpo_env_rollout(int system_kind, const void* sys_params_host, int math_mode, int x_dim,
+                     int action_dim, int episode_length, int action_repeat, float* obs,
+                     float* steps, float* done, const float* first_obs, const float* actions,
+                     int E, int T, float* observation_out, float* reward_out, float* discount_out,
+                     float* next_observation_out, float* truncation_out, void* stream);
+
+/* ---- stage 4: learned MLP-ensemble dynamics, batched forward on tcgen05 ------------------ */
+/* inp [R, x_dim+u_dim], member [R] (int32 ensemble member per row) -> delta [R, x_dim]. */
+int mbpo_mlp_dynamics_forward(const MbpoMlpEnsembleParams* params_host, const float* inp,
+                              const int32_t* member, int R, float* delta_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MBPO_B200_H_ */

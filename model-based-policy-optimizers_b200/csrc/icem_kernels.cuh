@@ -1,0 +1,382 @@
+// iCEM kernels: fused plan (sample -> rollout -> select -> refit, all S iterations in one
+// launch, one CTA per planning problem) and the staged kernels behind the per-stage C ABI.
+//
+// Reference: mbpo/optimizers/trajectory_optimizers/icem_optimizer.py:134-252 (optimize),
+// mbpo/utils/optimizer_utils.py:11-59 (rollout_actions), pendulum_*.py (System.step).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "noise.cuh"
+#include "pendulum.cuh"
+#include "select.cuh"
+
+namespace mbpo {
+
+// ------------------------------------------------------------------------------------------
+// Rollout of one action row held in shared/global memory; returns the horizon-mean reward
+// (icem_optimizer.py:160 inner jnp.mean over rollout_actions(...).reward).
+// ------------------------------------------------------------------------------------------
+template <int MATH, typename ActFn>
+__device__ __forceinline__ float rollout_return(const PendulumConsts& pc, float c0, float s0, float w0, int H,
+                                                ActFn act) {
+  float acc = 0.0f;
+  if (MATH == MBPO_MATH_REFERENCE) {
+    float c = c0, s = s0, w = w0;
+#pragma unroll 2
+    for (int t = 0; t < H; ++t) {
+      float r;
+      pendulum_step_ref(pc, c, s, w, act(t), r);
+      acc = __fadd_rn(acc, r);
+    }
+  } else {
+    float th = atan2f(s0, c0), w = w0;
+#pragma unroll 2
+    for (int t = 0; t < H; ++t) {
+      float r;
+      pendulum_step_theta(pc, th, w, act(t), r);
+      acc = __fadd_rn(acc, r);
+    }
+  }
+  return __fdiv_rn(acc, static_cast<float>(H));
+}
+
+// summarize over P identical particles (deterministic System): jnp.mean / jnp.max  (:160)
+__device__ __forceinline__ float summarize_particles(float ret, int P, int summarize) {
+  if (summarize == MBPO_SUMMARIZE_MAX || P == 1) return ret;
+  float acc = 0.0f;
+  for (int p = 0; p < P; ++p) acc = __fadd_rn(acc, ret);
+  return __fdiv_rn(acc, static_cast<float>(P));
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused plan kernel
+// ------------------------------------------------------------------------------------------
+struct PlanArgs {
+  // shapes / hyper-parameters
+  int B, N, Np, K, P, S;
+  int warm_start, summarize;
+  float init_std, alpha, one_minus_alpha, u_min, u_max;
+  MbpoPendulumParams sys;
+  float scale[MBPO_MAX_FREQ];  // fill_noise_scale()
+  // I/O
+  const float* x0;           // [B,3]
+  const uint32_t* key_in;    // [B,2]
+  const float* best_seq_in;  // [B,H]
+  float* best_seq_out;       // [B,H]
+  float* best_value_out;     // [B]
+  uint32_t* key_out;         // [B,2]
+  MbpoIcemTrace trace;       // optional dumps
+};
+
+template <int H>
+struct PlanSmem {
+  static constexpr int HS = H | 1;  // odd row stride: conflict-free per-thread rows
+  static size_t bytes(int N, int Np, int K) {
+    size_t words = static_cast<size_t>(N) * HS  // action rows
+                   + (N + Np)                   // sort keys
+                   + 2 * (N + 1)                // legacy split words
+                   + 3 * H                      // mean, std, best_seq
+                   + 2 * K                      // elite_idx, scratch
+                   + 8;                         // best_value, carry key, state key, pad
+    return words * 4;
+  }
+};
+
+// Shared-memory carve-up of one planning CTA.
+template <int H>
+struct PlanCtaSmem {
+  float* act;          // [N][HS] action rows of the sampled candidates
+  uint32_t* skey;      // [M]     total-order keys of the objective values
+  uint32_t* flat;      // [2(N+1)] legacy split(sampling_rng, N+1) words
+  float* mean;         // [H]
+  float* std_;         // [H]
+  float* best_seq;     // [H]
+  int* elite_idx;      // [K]
+  int* scratch;        // [K]
+  float* best_value;   // [1]
+  uint32_t* carry;     // [2] carry.key
+  uint32_t* state_key; // [2] opt_state.key (closed loop)
+  __device__ __forceinline__ PlanCtaSmem(uint32_t* base, int N, int Np, int K) {
+    constexpr int HS = PlanSmem<H>::HS;
+    act = reinterpret_cast<float*>(base);
+    skey = base + static_cast<size_t>(N) * HS;
+    flat = skey + (N + Np);
+    mean = reinterpret_cast<float*>(flat + 2 * (N + 1));
+    std_ = mean + H;
+    best_seq = std_ + H;
+    elite_idx = reinterpret_cast<int*>(best_seq + H);
+    scratch = elite_idx + K;
+    best_value = reinterpret_cast<float*>(scratch + K);
+    carry = reinterpret_cast<uint32_t*>(best_value + 1);
+    state_key = carry + 2;
+  }
+};
+
+// iCemTO.optimize for ONE problem, executed by the whole CTA (icem_optimizer.py:134-252).
+// Thread n owns samples n, n+THREADS, ...: it derives the sample's key, generates the
+// colored-noise row straight into its shared-memory action row, rolls the row out with the
+// state in registers and publishes the total-order key of the objective.  Warp 0 then selects
+// and refits.  `prev_best` ([H], global or this CTA's own sm.best_seq) is the previous plan's
+// best sequence for the warm start; `key_in` is opt_state.key; the new opt_state.key is
+// returned through key_new (valid in thread 0 only).  `slot` indexes the optional trace
+// dumps ([S, B, ...] with problem slot `slot` of `slots`).
+template <int H, int PRNG, int MATH, int THREADS>
+__device__ __forceinline__ void plan_problem(const PlanArgs& a, const PlanCtaSmem<H>& sm, const PendulumConsts& pc,
+                                             const RefitScalars& rs, const float* prev_best, Key2 key_in,
+                                             Key2& key_new, float x_c, float x_s, float x_w, int slot, int slots) {
+  constexpr int HS = PlanSmem<H>::HS;
+  const int N = a.N, M = a.N + a.Np, K = a.K;
+  const int tid = threadIdx.x;
+  float* act = sm.act;
+  uint32_t* skey = sm.skey;
+  uint32_t* flat = sm.flat;
+  float* mean = sm.mean;
+  float* std_ = sm.std_;
+  float* best_seq = sm.best_seq;
+
+  // ---- prologue: warm start, key split (icem_optimizer.py:235-249) ------------------------
+  float m0 = 0.0f;
+  if (tid < H && a.warm_start) m0 = prev_best[tid + 1 < H ? tid + 1 : H - 1];
+  __syncthreads();  // prev_best may alias best_seq
+  if (tid < H) {
+    mean[tid] = m0;
+    std_[tid] = a.init_std;
+    best_seq[tid] = m0;
+  }
+  if (tid == 0) {
+    *sm.best_value = __int_as_float(0xFF800000);  // -inf
+    Key2 k_opt;
+    split2<PRNG>(key_in, k_opt, key_new);         // optimizer_key, key = split(opt_state.key, 2)
+    sm.carry[0] = k_opt.k0;
+    sm.carry[1] = k_opt.k1;
+  }
+  __syncthreads();
+
+  for (int it = 0; it < a.S; ++it) {
+    const size_t tslot = static_cast<size_t>(it) * slots + slot;
+    // ---- key plumbing (:174-180) -----------------------------------------------------------
+    Key2 ck{sm.carry[0], sm.carry[1]}, sampling_rng, particles_rng;
+    split2<PRNG>(ck, sampling_rng, particles_rng);  // particles_rng is dead for a deterministic System
+    if (PRNG == MBPO_PRNG_LEGACY) {
+      // split(sampling_rng, N+1): block j -> flat[j], flat[N+1+j]
+      for (int j = tid; j < N + 1; j += THREADS) {
+        uint32_t y0 = static_cast<uint32_t>(j), y1 = static_cast<uint32_t>(N + 1 + j);
+        threefry2x32(sampling_rng.k0, sampling_rng.k1, y0, y1);
+        flat[j] = y0;
+        flat[N + 1 + j] = y1;
+      }
+    }
+    __syncthreads();  // flat complete; every thread has read carry
+    if (tid == 0) {
+      Key2 nk;
+      if (PRNG == MBPO_PRNG_LEGACY) { nk.k0 = flat[0]; nk.k1 = flat[1]; }
+      else nk = split_at<1>(sampling_rng, static_cast<uint32_t>(N + 1), 0u);
+      sm.carry[0] = nk.k0; sm.carry[1] = nk.k1;   // key = sampling_rng[0]  (:176)
+    }
+
+    // ---- sample + rollout, one row per thread pass -----------------------------------------
+    for (int n = tid; n < N; n += THREADS) {
+      Key2 skey_n;
+      if (PRNG == MBPO_PRNG_LEGACY) { skey_n.k0 = flat[2 * (n + 1)]; skey_n.k1 = flat[2 * (n + 1) + 1]; }
+      else skey_n = split_at<1>(sampling_rng, static_cast<uint32_t>(N + 1), static_cast<uint32_t>(n + 1));
+      const Key2 dim_key = split_at<PRNG>(skey_n, 1u, 0u);   // vmap(split(x, action_dim)), A == 1  (:180)
+      float* row = act + static_cast<size_t>(n) * HS;
+      colored_noise_row<H, PRNG>(dim_key, a.scale, nullptr, [&](int t, float y) {
+        const float v = __fadd_rn(mean[t], __fmul_rn(y, std_[t]));           // :190
+        row[t] = fminf(fmaxf(v, a.u_min), a.u_max);                          // :191
+      });
+      const float ret = rollout_return<MATH>(pc, x_c, x_s, x_w, H, [&](int t) { return row[t]; });
+      const float val = summarize_particles(ret, a.P, a.summarize);
+      skey[n] = total_order_key(val);
+      if (a.trace.values) a.trace.values[tslot * M + n] = val;
+      if (a.trace.actions) {
+        float* dst = a.trace.actions + (tslot * M + n) * H;
+        for (int t = 0; t < H; ++t) dst[t] = row[t];
+      }
+    }
+    // kept-elite rows are the closure's all-zero sequences (:192,:245): one rollout serves
+    // all Np rows and all iterations (deterministic System).
+    if (tid == THREADS - 1) {
+      if (it == 0) {
+        const float ret = rollout_return<MATH>(pc, x_c, x_s, x_w, H, [](int) { return 0.0f; });
+        const uint32_t zk = total_order_key(summarize_particles(ret, a.P, a.summarize));
+        for (int j = N; j < M; ++j) skey[j] = zk;
+      }
+      if (a.trace.values || a.trace.actions) {
+        const uint32_t zk = skey[N];
+        const float zv = __uint_as_float((zk & 0x80000000u) ? (zk & 0x7FFFFFFFu) : ~zk);
+        for (int j = N; j < M; ++j) {
+          if (a.trace.values) a.trace.values[tslot * M + j] = zv;
+          if (a.trace.actions) {
+            float* dst = a.trace.actions + (tslot * M + j) * H;
+            for (int t = 0; t < H; ++t) dst[t] = 0.0f;
+          }
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- select + refit + best tracking (:199-226), warp 0 ---------------------------------
+    if (tid < 32) {
+      warp_select_refit(rs, skey, sm.elite_idx, sm.scratch,
+                        [&](int i, int d) { return i < N ? act[static_cast<size_t>(i) * HS + d] : 0.0f; }, mean,
+                        std_, best_seq, sm.best_value);
+      if (a.trace.elite_idx)
+        for (int e = tid; e < K; e += 32) a.trace.elite_idx[tslot * K + e] = sm.elite_idx[e];
+      for (int d = tid; d < H; d += 32) {
+        if (a.trace.mean) a.trace.mean[tslot * H + d] = mean[d];
+        if (a.trace.std) a.trace.std[tslot * H + d] = std_[d];
+      }
+      if (a.trace.best_value && tid == 0) a.trace.best_value[tslot] = *sm.best_value;
+    }
+    __syncthreads();
+  }
+}
+
+// Fused plan: one CTA plans one problem at a time (grid-stride over problems).
+template <int H, int PRNG, int MATH, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) icem_plan_pendulum_kernel(const __grid_constant__ PlanArgs a) {
+  extern __shared__ __align__(16) uint32_t smem_u32[];
+  const PlanCtaSmem<H> sm(smem_u32, a.N, a.Np, a.K);
+  const int tid = threadIdx.x;
+  const PendulumConsts pc(a.sys);
+  RefitScalars rs;
+  rs.M = a.N + a.Np; rs.K = a.K; rs.D = H; rs.alpha = a.alpha; rs.one_minus_alpha = a.one_minus_alpha;
+
+  for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+    const float x_c = a.x0[3 * b], x_s = a.x0[3 * b + 1], x_w = a.x0[3 * b + 2];
+    Key2 k_in{a.key_in[2 * b], a.key_in[2 * b + 1]}, k_new;
+    plan_problem<H, PRNG, MATH, THREADS>(a, sm, pc, rs, a.best_seq_in + static_cast<size_t>(b) * H, k_in, k_new, x_c,
+                                         x_s, x_w, b, a.B);
+    // ---- epilogue (:251) -----------------------------------------------------------------
+    if (tid < H) a.best_seq_out[static_cast<size_t>(b) * H + tid] = sm.best_seq[tid];
+    if (tid == 0) {
+      a.best_value_out[b] = *sm.best_value;
+      a.key_out[2 * b] = k_new.k0;
+      a.key_out[2 * b + 1] = k_new.k1;
+    }
+    __syncthreads();
+  }
+}
+
+// Closed-loop MPC (tests/test_icemopt.py:19-32): T times { act = optimize(x)[0]; x = true
+// system.step(x, act); warm start from the previous best sequence }, one CTA per problem,
+// the whole loop in one launch (the reference runs it as one lax.scan).
+struct MpcArgs {
+  int T;
+  float* states_out;   // [T,B,3]
+  float* rewards_out;  // [T,B]
+  float* actions_out;  // [T,B,1]
+};
+
+template <int H, int PRNG, int MATH, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+    icem_mpc_pendulum_kernel(const __grid_constant__ PlanArgs a, const __grid_constant__ MpcArgs m) {
+  extern __shared__ __align__(16) uint32_t smem_u32[];
+  const PlanCtaSmem<H> sm(smem_u32, a.N, a.Np, a.K);
+  __shared__ float xs[4];
+  const int tid = threadIdx.x;
+  const PendulumConsts pc(a.sys);
+  RefitScalars rs;
+  rs.M = a.N + a.Np; rs.K = a.K; rs.D = H; rs.alpha = a.alpha; rs.one_minus_alpha = a.one_minus_alpha;
+
+  for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+    if (tid < H) sm.best_seq[tid] = a.best_seq_in[static_cast<size_t>(b) * H + tid];
+    if (tid < 3) xs[tid] = a.x0[3 * b + tid];
+    if (tid == 0) { sm.state_key[0] = a.key_in[2 * b]; sm.state_key[1] = a.key_in[2 * b + 1]; }
+    __syncthreads();
+    for (int t = 0; t < m.T; ++t) {
+      const float x_c = xs[0], x_s = xs[1], x_w = xs[2];
+      Key2 k_in{sm.state_key[0], sm.state_key[1]}, k_new;
+      plan_problem<H, PRNG, MATH, THREADS>(a, sm, pc, rs, sm.best_seq, k_in, k_new, x_c, x_s, x_w, 0, 1);
+      if (tid == 0) {
+        sm.state_key[0] = k_new.k0; sm.state_key[1] = k_new.k1;
+        const float u = sm.best_seq[0];                       // opt_state.action (:67-69)
+        float c = x_c, s = x_s, w = x_w, r;
+        if (MATH == MBPO_MATH_REFERENCE) {
+          pendulum_step_ref(pc, c, s, w, u, r);
+        } else {
+          float th = atan2f(s, c);
+          pendulum_step_theta(pc, th, w, u, r);
+          sincosf(th, &s, &c);
+        }
+        xs[0] = c; xs[1] = s; xs[2] = w;
+        const size_t o = static_cast<size_t>(t) * a.B + b;
+        if (m.states_out) { m.states_out[o * 3] = c; m.states_out[o * 3 + 1] = s; m.states_out[o * 3 + 2] = w; }
+        if (m.rewards_out) m.rewards_out[o] = r;
+        if (m.actions_out) m.actions_out[o] = u;
+      }
+      __syncthreads();
+    }
+    if (tid < H) a.best_seq_out[static_cast<size_t>(b) * H + tid] = sm.best_seq[tid];
+    if (tid == 0) {
+      a.best_value_out ? (void)(a.best_value_out[b] = *sm.best_value) : (void)0;
+      a.key_out[2 * b] = sm.state_key[0];
+      a.key_out[2 * b + 1] = sm.state_key[1];
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Staged kernels
+// ------------------------------------------------------------------------------------------
+
+// Per-bin noise multipliers (fill_noise_scale) passed by value: the staged kernels need no
+// device allocation and the table is read straight from the constant bank.
+struct ScaleTable {
+  float v[MBPO_MAX_FREQ];
+};
+
+// vmap(powerlaw_psd_gaussian): one thread per key.
+template <int H, int PRNG>
+__global__ void powerlaw_noise_kernel(const __grid_constant__ ScaleTable tbl, const uint32_t* __restrict__ keys, int M,
+                                      float* __restrict__ out, uint32_t* __restrict__ bits_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  Key2 k{keys[2 * i], keys[2 * i + 1]};
+  float* row = out + static_cast<size_t>(i) * H;
+  colored_noise_row<H, PRNG>(k, tbl.v, bits_out ? bits_out + static_cast<size_t>(i) * 2 * NoiseShape<H>::F : nullptr,
+                             [&](int t, float y) { row[t] = y; });
+}
+
+// One iCEM iteration of key plumbing + sampling for B problems (icem_optimizer.py:174-192).
+// grid = (ceil((N+Np)*A / blockDim), B); thread = (candidate n, action dim a).
+template <int H, int PRNG>
+__global__ void sample_actions_kernel(const __grid_constant__ ScaleTable tbl, const uint32_t* __restrict__ carry_key,
+                                      const float* __restrict__ mean, const float* __restrict__ std_, int N, int Np,
+                                      int A, float u_min, float u_max, float* __restrict__ actions,
+                                      uint32_t* __restrict__ next_key, uint32_t* __restrict__ particle_keys) {
+  const int b = blockIdx.y;
+  const int M = N + Np;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * A) return;
+  const int n = idx / A, ad = idx % A;
+  Key2 ck{carry_key[2 * b], carry_key[2 * b + 1]}, sampling_rng, particles_rng;
+  split2<PRNG>(ck, sampling_rng, particles_rng);                                                          // :174
+  if (ad == 0 && particle_keys) {
+    const Key2 pk = split_at<PRNG>(particles_rng, static_cast<uint32_t>(M), static_cast<uint32_t>(n));   // :177
+    particle_keys[(static_cast<size_t>(b) * M + n) * 2] = pk.k0;
+    particle_keys[(static_cast<size_t>(b) * M + n) * 2 + 1] = pk.k1;
+  }
+  if (idx == 0) {
+    const Key2 nk = split_at<PRNG>(sampling_rng, static_cast<uint32_t>(N + 1), 0u);                       // :176
+    next_key[2 * b] = nk.k0;
+    next_key[2 * b + 1] = nk.k1;
+  }
+  float* row = actions + (static_cast<size_t>(b) * M + n) * H * A + ad;  // element t at row[t*A]
+  if (n >= N) {  // kept-elite rows: closure zeros (:192,:245)
+    for (int t = 0; t < H; ++t) row[static_cast<size_t>(t) * A] = 0.0f;
+    return;
+  }
+  const Key2 sk = split_at<PRNG>(sampling_rng, static_cast<uint32_t>(N + 1), static_cast<uint32_t>(n + 1));
+  const Key2 dk = split_at<PRNG>(sk, static_cast<uint32_t>(A), static_cast<uint32_t>(ad));                // :180
+  const float* mrow = mean + static_cast<size_t>(b) * H * A + ad;
+  const float* srow = std_ + static_cast<size_t>(b) * H * A + ad;
+  colored_noise_row<H, PRNG>(dk, tbl.v, nullptr, [&](int t, float y) {
+    const float v = __fadd_rn(mrow[static_cast<size_t>(t) * A], __fmul_rn(y, srow[static_cast<size_t>(t) * A]));
+    row[static_cast<size_t>(t) * A] = fminf(fmaxf(v, u_min), u_max);
+  });
+}
+
+}  // namespace mbpo

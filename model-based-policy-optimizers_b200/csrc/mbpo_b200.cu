@@ -1,0 +1,547 @@
+// C ABI of the B200-native iCEM planning hot path (declared in include/mbpo_b200.h).
+//
+// Host side only validates arguments, fills kernel argument structs and launches on the
+// caller's stream.  No allocation, no synchronisation, no CPU fallback: an unsupported
+// configuration is an error (MBPO_EUNSUPPORTED), never a slow path.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+
+#include "../../include/mbpo_b200.h"
+#include "env_kernels.cuh"
+#include "host_util.h"
+#include "mlp_kernels.cuh"
+#include "plan_dispatch.h"
+#include "staged_kernels.cuh"
+
+namespace mbpo {
+thread_local char g_err[512] = "";
+}
+
+using namespace mbpo;
+
+namespace {
+
+bool horizon_supported(int H) {
+  switch (H) {
+#define X(h) case h:
+    MBPO_FOR_EACH_H(X)
+#undef X
+    return true;
+    default:
+      return false;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// PRNG primitive kernels (runtime mode; one thread per output word / key)
+// ------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void prng_split_kernel(const uint32_t* __restrict__ keys, long long total, int num,
+                                  uint32_t* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long m = i / num;
+  const uint32_t j = static_cast<uint32_t>(i % num);
+  const Key2 k{keys[2 * m], keys[2 * m + 1]};
+  const Key2 o = split_at<MODE>(k, static_cast<uint32_t>(num), j);
+  out[2 * i] = o.k0;
+  out[2 * i + 1] = o.k1;
+}
+
+// what: 0 bits, 1 uniform(lo,hi), 2 normal
+template <int MODE>
+__global__ void prng_draw_kernel(const uint32_t* __restrict__ keys, long long total, int n, int what, float lo,
+                                 float hi, void* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long m = i / n;
+  const uint32_t w = static_cast<uint32_t>(i % n);
+  const Key2 k{keys[2 * m], keys[2 * m + 1]};
+  const uint32_t bits = random_bits_at<MODE>(k, static_cast<uint32_t>(n), w);
+  if (what == 0) static_cast<uint32_t*>(out)[i] = bits;
+  else if (what == 1) static_cast<float*>(out)[i] = bits_to_uniform(bits, lo, hi);
+  else static_cast<float*>(out)[i] = bits_to_normal(bits);
+}
+
+int prng_draw(const uint32_t* keys, int M, int n, int prng_mode, int what, float lo, float hi, void* out,
+              void* stream) {
+  MBPO_REQUIRE(keys && out, "prng: null pointer");
+  MBPO_REQUIRE(M >= 0 && n >= 0, "prng: negative size");
+  MBPO_REQUIRE(prng_mode == 0 || prng_mode == 1, "prng: bad prng_mode %d", prng_mode);
+  const long long total = static_cast<long long>(M) * n;
+  if (total == 0) return MBPO_OK;
+  const int threads = 256;
+  const unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);
+  if (prng_mode == 0)
+    prng_draw_kernel<0><<<blocks, threads, 0, as_stream(stream)>>>(keys, total, n, what, lo, hi, out);
+  else
+    prng_draw_kernel<1><<<blocks, threads, 0, as_stream(stream)>>>(keys, total, n, what, lo, hi, out);
+  return check_launch("prng_draw_kernel");
+}
+
+int validate_cfg(const MbpoIcemCfg* c) {
+  MBPO_REQUIRE(c != nullptr, "cfg is null");
+  MBPO_REQUIRE(c->horizon >= 2 && c->horizon <= MBPO_MAX_HORIZON, "horizon %d outside [2, %d]", c->horizon,
+               MBPO_MAX_HORIZON);
+  MBPO_REQUIRE(c->action_dim >= 1, "action_dim %d < 1", c->action_dim);
+  MBPO_REQUIRE(c->x_dim >= 1, "x_dim %d < 1", c->x_dim);
+  MBPO_REQUIRE(c->num_samples >= 1, "num_samples %d < 1", c->num_samples);
+  MBPO_REQUIRE(c->num_prev_elites >= 1, "num_prev_elites %d < 1", c->num_prev_elites);
+  MBPO_REQUIRE(c->num_elites >= 1 && c->num_elites <= c->num_samples + c->num_prev_elites,
+               "num_elites %d outside [1, num_samples + num_prev_elites = %d]", c->num_elites,
+               c->num_samples + c->num_prev_elites);
+  MBPO_REQUIRE(c->num_particles >= 1, "num_particles %d < 1", c->num_particles);
+  MBPO_REQUIRE(c->num_steps >= 1, "num_steps %d < 1", c->num_steps);
+  MBPO_REQUIRE(c->prng_mode == 0 || c->prng_mode == 1, "bad prng_mode %d", c->prng_mode);
+  MBPO_REQUIRE(c->summarize == 0 || c->summarize == 1, "bad summarize %d", c->summarize);
+  MBPO_REQUIRE(c->math_mode == 0 || c->math_mode == 1, "bad math_mode %d", c->math_mode);
+  MBPO_REQUIRE(c->sigma > 0.0f && std::isfinite(c->sigma), "sigma must be positive and finite");
+  return MBPO_OK;
+}
+
+ScaleTable make_scale_table(const MbpoIcemCfg* c) {
+  ScaleTable t;
+  std::memset(&t, 0, sizeof(t));
+  fill_noise_scale(c->s_scale, c->sigma, c->horizon, t.v);
+  return t;
+}
+
+// ---- fused plan --------------------------------------------------------------------------
+void fill_plan_args(PlanArgs& a, const MbpoIcemCfg* c, const MbpoPendulumParams* sys, const float* x0,
+                    const uint32_t* key_in, const float* best_seq_in, int B, float* best_seq_out,
+                    float* best_value_out, uint32_t* key_out, const MbpoIcemTrace* trace) {
+  std::memset(&a, 0, sizeof(a));
+  a.B = B; a.N = c->num_samples; a.Np = c->num_prev_elites; a.K = c->num_elites; a.P = c->num_particles;
+  a.S = c->num_steps; a.warm_start = c->warm_start; a.summarize = c->summarize;
+  a.init_std = c->init_std; a.alpha = c->alpha; a.one_minus_alpha = static_cast<float>(1.0 - static_cast<double>(c->alpha));
+  a.u_min = c->u_min; a.u_max = c->u_max;
+  a.sys = *sys;
+  fill_noise_scale(c->s_scale, c->sigma, c->horizon, a.scale);
+  a.x0 = x0; a.key_in = key_in; a.best_seq_in = best_seq_in; a.best_seq_out = best_seq_out;
+  a.best_value_out = best_value_out; a.key_out = key_out;
+  if (trace) a.trace = *trace;
+}
+
+int plan_fusable(const MbpoIcemCfg* c, bool set_error) {
+  const char* why = nullptr;
+  if (c->system_kind != MBPO_SYSTEM_PENDULUM) why = "fused plan supports system_kind == MBPO_SYSTEM_PENDULUM only";
+  else if (c->action_dim != 1 || c->x_dim != 3) why = "fused plan requires action_dim == 1 and x_dim == 3";
+  else if (!horizon_supported(c->horizon)) why = "fused plan: horizon has no compiled kernel (" MBPO_H_LIST_STR ")";
+  else {
+    const int HS = c->horizon | 1;
+    const size_t words = static_cast<size_t>(c->num_samples) * HS + (c->num_samples + c->num_prev_elites) +
+                         2 * (c->num_samples + 1) + 3 * c->horizon + 2 * c->num_elites + 8;
+    if (words * 4 > 227 * 1024) why = "fused plan: population does not fit 227 KB of shared memory";
+  }
+  if (why && set_error) fail(MBPO_EUNSUPPORTED, "%s", why);
+  return why == nullptr;
+}
+
+int run_plan(const MbpoIcemCfg* c, const void* sys_params_host, const float* x0, const uint32_t* key_in,
+             const float* best_seq_in, int B, float* best_seq_out, float* best_value_out, uint32_t* key_out,
+             const MbpoIcemTrace* trace, const MpcArgs* mpc, void* stream) {
+  int rc = validate_cfg(c);
+  if (rc != MBPO_OK) return rc;
+  MBPO_REQUIRE(sys_params_host && x0 && key_in && best_seq_in && best_seq_out && key_out, "plan: null pointer");
+  MBPO_REQUIRE(mpc != nullptr || best_value_out != nullptr, "plan: best_value_out is null");
+  MBPO_REQUIRE(B >= 0, "plan: B < 0");
+  if (!plan_fusable(c, true)) return MBPO_EUNSUPPORTED;
+  if (B == 0) return MBPO_OK;
+  PlanArgs a;
+  fill_plan_args(a, c, static_cast<const MbpoPendulumParams*>(sys_params_host), x0, key_in, best_seq_in, B,
+                 best_seq_out, best_value_out, key_out, trace);
+  switch (c->horizon) {
+#define X(h) \
+  case h:    \
+    return plan_entry<h>(c->prng_mode, c->math_mode, a, mpc, as_stream(stream));
+    MBPO_FOR_EACH_H(X)
+#undef X
+    default:
+      return fail(MBPO_EUNSUPPORTED, "horizon %d has no compiled kernel", c->horizon);
+  }
+}
+
+}  // namespace
+
+// ============================================================================================
+// extern "C"
+// ============================================================================================
+extern "C" {
+
+int mbpo_abi_version(void) { return MBPO_ABI_VERSION; }
+
+const char* mbpo_last_error(void) { return g_err; }
+
+size_t mbpo_struct_size(int which) {
+  switch (which) {
+    case 0: return sizeof(MbpoIcemCfg);
+    case 1: return sizeof(MbpoPendulumParams);
+    case 2: return sizeof(MbpoMlpEnsembleParams);
+    case 3: return sizeof(MbpoIcemTrace);
+    default: return 0;
+  }
+}
+
+int mbpo_icem_cfg_init(MbpoIcemCfg* cfg, int horizon, int action_dim, int x_dim, int num_particles, int num_samples,
+                       int num_elites, float init_std, float alpha, int num_steps, float exponent,
+                       float elite_set_fraction, float u_min, float u_max, int warm_start, float lambda_constraint) {
+  MBPO_REQUIRE(cfg != nullptr, "cfg is null");
+  MBPO_REQUIRE(horizon >= 2 && horizon <= MBPO_MAX_HORIZON, "horizon %d outside [2, %d]", horizon, MBPO_MAX_HORIZON);
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->horizon = horizon;
+  cfg->action_dim = action_dim;
+  cfg->x_dim = x_dim;
+  cfg->num_samples = num_samples;
+  cfg->num_elites = num_elites;
+  // num_prev_elites_per_iter = max(int(elite_set_fraction * num_elites), 1): python float (double) product
+  const int npe = static_cast<int>(static_cast<double>(elite_set_fraction) * num_elites);
+  cfg->num_prev_elites = npe > 1 ? npe : 1;
+  cfg->num_particles = num_particles;
+  cfg->num_steps = num_steps;
+  cfg->warm_start = warm_start ? 1 : 0;
+  cfg->prng_mode = MBPO_PRNG_LEGACY;
+  cfg->summarize = MBPO_SUMMARIZE_MEAN;
+  cfg->system_kind = MBPO_SYSTEM_PENDULUM;
+  cfg->math_mode = MBPO_MATH_REFERENCE;
+  cfg->init_std = init_std;
+  cfg->alpha = alpha;
+  cfg->exponent = exponent;
+  cfg->u_min = u_min;
+  cfg->u_max = u_max;
+  cfg->lambda_constraint = lambda_constraint;
+  // general_utils.py:143-178 in float32: f = rfftfreq(H); s_scale[:ix] = s_scale[ix] with
+  // ix = sum(f < 1/H) = 1; s_scale **= -exponent/2; w = s_scale[1:]; w[-1] *= (1 + H%2)/2;
+  // sigma = 2*sqrt(sum(w^2))/H.
+  const int F = horizon / 2 + 1;
+  const float fmin = static_cast<float>(1.0 / horizon);
+  float f[MBPO_MAX_FREQ];
+  for (int i = 0; i < F; ++i) f[i] = static_cast<float>(i) / static_cast<float>(horizon);
+  int ix = 0;
+  for (int i = 0; i < F; ++i) ix += (f[i] < fmin) ? 1 : 0;
+  if (ix && ix < F)
+    for (int i = 0; i < ix; ++i) f[i] = f[ix];
+  const float pw = static_cast<float>(-static_cast<double>(exponent) / 2.0);
+  float sumsq = 0.0f;
+  for (int i = 0; i < F; ++i) {
+    cfg->s_scale[i] = powf(f[i], pw);
+    if (i >= 1) {
+      float w = cfg->s_scale[i];
+      if (i == F - 1) w = w * static_cast<float>((1 + (horizon % 2)) / 2.0);
+      sumsq += w * w;
+    }
+  }
+  cfg->sigma = 2.0f * sqrtf(sumsq) / static_cast<float>(horizon);
+  return MBPO_OK;
+}
+
+// ---- PRNG ------------------------------------------------------------------------------------
+int mbpo_prng_split(const uint32_t* keys, int M, int num, int prng_mode, uint32_t* keys_out, void* stream) {
+  MBPO_REQUIRE(keys && keys_out, "prng_split: null pointer");
+  MBPO_REQUIRE(M >= 0 && num >= 0, "prng_split: negative size");
+  MBPO_REQUIRE(prng_mode == 0 || prng_mode == 1, "prng_split: bad prng_mode %d", prng_mode);
+  const long long total = static_cast<long long>(M) * num;
+  if (total == 0) return MBPO_OK;
+  const int threads = 256;
+  const unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);
+  if (prng_mode == 0) prng_split_kernel<0><<<blocks, threads, 0, as_stream(stream)>>>(keys, total, num, keys_out);
+  else prng_split_kernel<1><<<blocks, threads, 0, as_stream(stream)>>>(keys, total, num, keys_out);
+  return check_launch("prng_split_kernel");
+}
+
+int mbpo_prng_random_bits(const uint32_t* keys, int M, int n, int prng_mode, uint32_t* bits_out, void* stream) {
+  return prng_draw(keys, M, n, prng_mode, 0, 0.0f, 0.0f, bits_out, stream);
+}
+
+int mbpo_prng_uniform(const uint32_t* keys, int M, int n, int prng_mode, float lo, float hi, float* out,
+                      void* stream) {
+  return prng_draw(keys, M, n, prng_mode, 1, lo, hi, out, stream);
+}
+
+int mbpo_prng_normal(const uint32_t* keys, int M, int n, int prng_mode, float* out, void* stream) {
+  return prng_draw(keys, M, n, prng_mode, 2, 0.0f, 0.0f, out, stream);
+}
+
+// ---- stage 1 -----------------------------------------------------------------------------------
+int mbpo_powerlaw_noise(const MbpoIcemCfg* cfg, const uint32_t* keys, int M, float* noise_out, uint32_t* bits_out,
+                        void* stream) {
+  const int rc = validate_cfg(cfg);
+  if (rc != MBPO_OK) return rc;
+  MBPO_REQUIRE(keys && noise_out, "powerlaw_noise: null pointer");
+  MBPO_REQUIRE(M >= 0, "powerlaw_noise: M < 0");
+  if (!horizon_supported(cfg->horizon))
+    return fail(MBPO_EUNSUPPORTED, "horizon %d has no compiled sampling kernel (" MBPO_H_LIST_STR ")", cfg->horizon);
+  if (M == 0) return MBPO_OK;
+  const ScaleTable tbl = make_scale_table(cfg);
+  switch (cfg->horizon) {
+#define X(h) \
+  case h:    \
+    return noise_entry<h>(cfg->prng_mode, tbl, keys, M, noise_out, bits_out, as_stream(stream));
+    MBPO_FOR_EACH_H(X)
+#undef X
+  }
+  return MBPO_EUNSUPPORTED;
+}
+
+int mbpo_icem_sample_actions(const MbpoIcemCfg* cfg, const uint32_t* carry_key, const float* mean, const float* std_,
+                             int B, float* actions_out, uint32_t* next_key_out, uint32_t* particle_keys_out,
+                             void* stream) {
+  const int rc = validate_cfg(cfg);
+  if (rc != MBPO_OK) return rc;
+  MBPO_REQUIRE(carry_key && mean && std_ && actions_out && next_key_out, "sample_actions: null pointer");
+  MBPO_REQUIRE(B >= 0 && B <= 65535, "sample_actions: B %d outside [0, 65535]", B);
+  if (!horizon_supported(cfg->horizon))
+    return fail(MBPO_EUNSUPPORTED, "horizon %d has no compiled sampling kernel (" MBPO_H_LIST_STR ")", cfg->horizon);
+  if (B == 0) return MBPO_OK;
+  const ScaleTable tbl = make_scale_table(cfg);
+  switch (cfg->horizon) {
+#define X(h)                                                                                                    \
+  case h:                                                                                                       \
+    return sample_entry<h>(cfg->prng_mode, tbl, carry_key, mean, std_, cfg->num_samples, cfg->num_prev_elites, \
+                           cfg->action_dim, cfg->u_min, cfg->u_max, B, actions_out, next_key_out,               \
+                           particle_keys_out, as_stream(stream));
+    MBPO_FOR_EACH_H(X)
+#undef X
+  }
+  return MBPO_EUNSUPPORTED;
+}
+
+// ---- stage 2 -----------------------------------------------------------------------------------
+int mbpo_system_step(int system_kind, const void* sys_params_host, int math_mode, const float* x, const float* u,
+                     int R, float* x_next, float* reward, void* stream) {
+  MBPO_REQUIRE(system_kind == MBPO_SYSTEM_PENDULUM || system_kind == MBPO_SYSTEM_MLP_ENSEMBLE,
+               "system_step: unknown system_kind %d", system_kind);
+  if (system_kind != MBPO_SYSTEM_PENDULUM)
+    return fail(MBPO_EUNSUPPORTED, "system_step: only MBPO_SYSTEM_PENDULUM has an inlined step");
+  MBPO_REQUIRE(sys_params_host && x && u && x_next && reward, "system_step: null pointer");
+  MBPO_REQUIRE(math_mode == 0 || math_mode == 1, "system_step: bad math_mode %d", math_mode);
+  MBPO_REQUIRE(R >= 0, "system_step: R < 0");
+  if (R == 0) return MBPO_OK;
+  const MbpoPendulumParams sys = *static_cast<const MbpoPendulumParams*>(sys_params_host);
+  const int threads = 128;
+  const unsigned blocks = static_cast<unsigned>((R + threads - 1) / threads);
+  if (math_mode == 0)
+    system_step_pendulum_kernel<0><<<blocks, threads, 0, as_stream(stream)>>>(sys, x, u, R, x_next, reward);
+  else
+    system_step_pendulum_kernel<1><<<blocks, threads, 0, as_stream(stream)>>>(sys, x, u, R, x_next, reward);
+  return check_launch("system_step_pendulum_kernel");
+}
+
+int mbpo_rollout_actions(int system_kind, const void* sys_params_host, int math_mode, int horizon, int action_dim,
+                         int x_dim, const float* x0, const float* actions, int B, int M, float* returns_out,
+                         float* obs_out, float* reward_out, float* next_obs_out, void* stream) {
+  if (system_kind != MBPO_SYSTEM_PENDULUM)
+    return fail(MBPO_EUNSUPPORTED, "rollout_actions: only MBPO_SYSTEM_PENDULUM has an inlined step");
+  MBPO_REQUIRE(sys_params_host && x0 && actions, "rollout_actions: null pointer");
+  MBPO_REQUIRE(action_dim == 1 && x_dim == 3, "rollout_actions: pendulum needs action_dim == 1, x_dim == 3");
+  MBPO_REQUIRE(horizon >= 1 && horizon <= 4096, "rollout_actions: horizon %d outside [1, 4096]", horizon);
+  MBPO_REQUIRE(math_mode == 0 || math_mode == 1, "rollout_actions: bad math_mode %d", math_mode);
+  MBPO_REQUIRE(B >= 0 && M >= 0, "rollout_actions: negative size");
+  const long long total = static_cast<long long>(B) * M;
+  if (total == 0) return MBPO_OK;
+  const MbpoPendulumParams sys = *static_cast<const MbpoPendulumParams*>(sys_params_host);
+  const int threads = 128;
+  const int HS = horizon | 1;
+  const size_t smem = static_cast<size_t>(threads / 32) * 32 * HS * sizeof(float);
+  if (smem > 227 * 1024) return fail(MBPO_EUNSUPPORTED, "rollout_actions: horizon %d too long to stage", horizon);
+  const long long warps = (total + 31) / 32;
+  const unsigned blocks = static_cast<unsigned>((warps + threads / 32 - 1) / (threads / 32));
+  cudaError_t e;
+  if (math_mode == 0) {
+    e = cudaFuncSetAttribute(rollout_actions_pendulum_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(smem));
+    if (e != cudaSuccess) return fail(MBPO_ECUDA, "rollout_actions smem attr: %s", cudaGetErrorString(e));
+    rollout_actions_pendulum_kernel<0><<<blocks, threads, smem, as_stream(stream)>>>(
+        sys, horizon, x0, actions, B, M, returns_out, obs_out, reward_out, next_obs_out);
+  } else {
+    e = cudaFuncSetAttribute(rollout_actions_pendulum_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(smem));
+    if (e != cudaSuccess) return fail(MBPO_ECUDA, "rollout_actions smem attr: %s", cudaGetErrorString(e));
+    rollout_actions_pendulum_kernel<1><<<blocks, threads, smem, as_stream(stream)>>>(
+        sys, horizon, x0, actions, B, M, returns_out, obs_out, reward_out, next_obs_out);
+  }
+  return check_launch("rollout_actions_pendulum_kernel");
+}
+
+// ---- stage 3 -----------------------------------------------------------------------------------
+int mbpo_icem_elite_refit(const MbpoIcemCfg* cfg, const float* actions, const float* values, const float* mean_in,
+                          const float* std_in, const float* best_value_in, const float* best_seq_in, int B,
+                          float* mean_out, float* std_out, float* best_value_out, float* best_seq_out,
+                          int32_t* elite_idx_out, void* stream) {
+  const int rc = validate_cfg(cfg);
+  if (rc != MBPO_OK) return rc;
+  MBPO_REQUIRE(actions && values && mean_in && std_in && best_value_in && best_seq_in && mean_out && std_out &&
+                   best_value_out && best_seq_out,
+               "elite_refit: null pointer");
+  MBPO_REQUIRE(B >= 0, "elite_refit: B < 0");
+  if (B == 0) return MBPO_OK;
+  RefitScalars rs;
+  rs.M = cfg->num_samples + cfg->num_prev_elites;
+  rs.K = cfg->num_elites;
+  rs.D = cfg->horizon * cfg->action_dim;
+  rs.alpha = cfg->alpha;
+  rs.one_minus_alpha = static_cast<float>(1.0 - static_cast<double>(cfg->alpha));
+  const size_t smem = (static_cast<size_t>(rs.M) + 2 * rs.K + 3 * rs.D + 4) * 4;
+  if (smem > 227 * 1024) return fail(MBPO_EUNSUPPORTED, "elite_refit: population too large for shared memory");
+  const cudaError_t e =
+      cudaFuncSetAttribute(elite_refit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return fail(MBPO_ECUDA, "elite_refit smem attr: %s", cudaGetErrorString(e));
+  elite_refit_kernel<<<B, 32, smem, as_stream(stream)>>>(rs, actions, values, mean_in, std_in, best_value_in,
+                                                          best_seq_in, mean_out, std_out, best_value_out, best_seq_out,
+                                                          elite_idx_out);
+  return check_launch("elite_refit_kernel");
+}
+
+// ---- fused plan ----------------------------------------------------------------------------------
+int mbpo_icem_plan_is_fused(const MbpoIcemCfg* cfg) {
+  if (validate_cfg(cfg) != MBPO_OK) return 0;
+  return plan_fusable(cfg, false);
+}
+
+int mbpo_icem_plan(const MbpoIcemCfg* cfg, const void* sys_params_host, const float* x0, const uint32_t* key_in,
+                   const float* best_seq_in, int B, float* best_seq_out, float* best_value_out, uint32_t* key_out,
+                   const MbpoIcemTrace* trace_host, void* stream) {
+  return run_plan(cfg, sys_params_host, x0, key_in, best_seq_in, B, best_seq_out, best_value_out, key_out,
+                  trace_host, nullptr, stream);
+}
+
+// Staged plan workspace layout (floats unless noted), all [B, ...]:
+//   actions [B,M,D] | values [B,M] | mean [B,D] | std [B,D] | mean2 [B,D] | std2 [B,D] | best_seq2 [B,D]
+//   | best_value [B] | best_value2 [B] | carry_key u32[B,2] | carry_key2 u32[B,2]
+size_t mbpo_icem_workspace_bytes(const MbpoIcemCfg* cfg, int B) {
+  if (validate_cfg(cfg) != MBPO_OK || B < 0) return 0;
+  const size_t M = static_cast<size_t>(cfg->num_samples) + cfg->num_prev_elites;
+  const size_t D = static_cast<size_t>(cfg->horizon) * cfg->action_dim;
+  const size_t b = static_cast<size_t>(B);
+  const size_t words = b * M * D + b * M + 5 * b * D + 2 * b + 4 * b;
+  return words * 4 + 256;
+}
+
+int mbpo_icem_plan_staged(const MbpoIcemCfg* cfg, const void* sys_params_host, const float* x0,
+                          const uint32_t* key_in, const float* best_seq_in, int B, float* best_seq_out,
+                          float* best_value_out, uint32_t* key_out, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+  int rc = validate_cfg(cfg);
+  if (rc != MBPO_OK) return rc;
+  MBPO_REQUIRE(sys_params_host && x0 && key_in && best_seq_in && best_seq_out && best_value_out && key_out &&
+                   workspace,
+               "plan_staged: null pointer");
+  MBPO_REQUIRE(B >= 0 && B <= 65535, "plan_staged: B %d outside [0, 65535]", B);
+  if (cfg->system_kind != MBPO_SYSTEM_PENDULUM)
+    return fail(MBPO_EUNSUPPORTED, "plan_staged: only MBPO_SYSTEM_PENDULUM has an inlined step");
+  if (workspace_bytes < mbpo_icem_workspace_bytes(cfg, B))
+    return fail(MBPO_EWORKSPACE, "plan_staged: workspace %zu B < required %zu B", workspace_bytes,
+                mbpo_icem_workspace_bytes(cfg, B));
+  if (B == 0) return MBPO_OK;
+  const size_t M = static_cast<size_t>(cfg->num_samples) + cfg->num_prev_elites;
+  const size_t D = static_cast<size_t>(cfg->horizon) * cfg->action_dim;
+  const size_t b = static_cast<size_t>(B);
+  uintptr_t p = reinterpret_cast<uintptr_t>(workspace);
+  p = (p + 255) & ~static_cast<uintptr_t>(255);
+  float* w = reinterpret_cast<float*>(p);
+  float* actions = w;            w += b * M * D;
+  float* values = w;             w += b * M;
+  float* mean[2];  float* std_[2];
+  mean[0] = w; w += b * D;  std_[0] = w; w += b * D;
+  mean[1] = w; w += b * D;  std_[1] = w; w += b * D;
+  float* bseq[2];  bseq[0] = best_seq_out;  bseq[1] = w;  w += b * D;
+  float* bval[2];  bval[0] = w; w += b;  bval[1] = w; w += b;
+  uint32_t* ckey[2];
+  ckey[0] = reinterpret_cast<uint32_t*>(w); w += 2 * b;
+  ckey[1] = reinterpret_cast<uint32_t*>(w); w += 2 * b;
+  cudaStream_t st = as_stream(stream);
+
+  // ping-pong so that after S iterations the results land in slot 0 (= the caller's buffers)
+  int cur = (cfg->num_steps % 2 == 0) ? 0 : 1;
+  if (cfg->prng_mode == 0)
+    plan_prologue_kernel<0><<<B, 64, 0, st>>>(B, static_cast<int>(D), cfg->action_dim, cfg->warm_start, cfg->init_std,
+                                              key_in, best_seq_in, ckey[cur], key_out, mean[cur], std_[cur], bseq[cur],
+                                              bval[cur]);
+  else
+    plan_prologue_kernel<1><<<B, 64, 0, st>>>(B, static_cast<int>(D), cfg->action_dim, cfg->warm_start, cfg->init_std,
+                                              key_in, best_seq_in, ckey[cur], key_out, mean[cur], std_[cur], bseq[cur],
+                                              bval[cur]);
+  rc = check_launch("plan_prologue_kernel");
+  if (rc != MBPO_OK) return rc;
+  for (int it = 0; it < cfg->num_steps; ++it) {
+    const int nxt = cur ^ 1;
+    rc = mbpo_icem_sample_actions(cfg, ckey[cur], mean[cur], std_[cur], B, actions, ckey[nxt], nullptr, stream);
+    if (rc != MBPO_OK) return rc;
+    rc = mbpo_rollout_actions(cfg->system_kind, sys_params_host, cfg->math_mode, cfg->horizon, cfg->action_dim,
+                              cfg->x_dim, x0, actions, B, static_cast<int>(M), values, nullptr, nullptr, nullptr,
+                              stream);
+    if (rc != MBPO_OK) return rc;
+    if (cfg->num_particles > 1 && cfg->summarize == MBPO_SUMMARIZE_MEAN) {
+      const long long n = static_cast<long long>(b * M);
+      summarize_particles_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(values, n, cfg->num_particles,
+                                                                                         cfg->summarize);
+      rc = check_launch("summarize_particles_kernel");
+      if (rc != MBPO_OK) return rc;
+    }
+    rc = mbpo_icem_elite_refit(cfg, actions, values, mean[cur], std_[cur], bval[cur], bseq[cur], B, mean[nxt],
+                               std_[nxt], bval[nxt], bseq[nxt], nullptr, stream);
+    if (rc != MBPO_OK) return rc;
+    cur = nxt;
+  }
+  // cur == 0 here; best value lives in the workspace, copy it out
+  const cudaError_t e = cudaMemcpyAsync(best_value_out, bval[cur], b * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) return fail(MBPO_ECUDA, "plan_staged copy: %s", cudaGetErrorString(e));
+  return MBPO_OK;
+}
+
+// ---- closed-loop MPC -------------------------------------------------------------------------------
+int mbpo_icem_mpc_closed_loop(const MbpoIcemCfg* cfg, const void* sys_params_host, const float* x0,
+                              const uint32_t* key_in, const float* best_seq_in, int B, int num_mpc_steps,
+                              float* states_out, float* rewards_out, float* actions_out, float* best_seq_out,
+                              uint32_t* key_out, void* stream) {
+  MBPO_REQUIRE(num_mpc_steps >= 0, "mpc_closed_loop: num_mpc_steps < 0");
+  MpcArgs m;
+  m.T = num_mpc_steps;
+  m.states_out = states_out;
+  m.rewards_out = rewards_out;
+  m.actions_out = actions_out;
+  return run_plan(cfg, sys_params_host, x0, key_in, best_seq_in, B, best_seq_out, nullptr, key_out, nullptr, &m,
+                  stream);
+}
+
+// ---- env rollouts ----------------------------------------------------------------------------------
+int mbpo_env_rollout(int system_kind, const void* sys_params_host, int math_mode, int x_dim, int action_dim,
+                     int episode_length, int action_repeat, float* obs, float* steps, float* done,
+                     const float* first_obs, const float* actions, int E, int T, float* observation_out,
+                     float* reward_out, float* discount_out, float* next_observation_out, float* truncation_out,
+                     void* stream) {
+  if (system_kind != MBPO_SYSTEM_PENDULUM)
+    return fail(MBPO_EUNSUPPORTED, "env_rollout: only MBPO_SYSTEM_PENDULUM has an inlined step");
+  MBPO_REQUIRE(sys_params_host && obs && steps && done && first_obs && actions, "env_rollout: null pointer");
+  MBPO_REQUIRE(action_dim == 1 && x_dim == 3, "env_rollout: pendulum needs action_dim == 1, x_dim == 3");
+  MBPO_REQUIRE(math_mode == 0 || math_mode == 1, "env_rollout: bad math_mode %d", math_mode);
+  MBPO_REQUIRE(episode_length >= 1 && action_repeat >= 1, "env_rollout: episode_length/action_repeat < 1");
+  MBPO_REQUIRE(E >= 0 && T >= 0, "env_rollout: negative size");
+  if (E == 0 || T == 0) return MBPO_OK;
+  EnvArgs a;
+  a.sys = *static_cast<const MbpoPendulumParams*>(sys_params_host);
+  a.E = E; a.T = T; a.episode_length = episode_length; a.action_repeat = action_repeat;
+  a.obs = obs; a.steps = steps; a.done = done; a.first_obs = first_obs; a.actions = actions;
+  a.observation_out = observation_out; a.reward_out = reward_out; a.discount_out = discount_out;
+  a.next_observation_out = next_observation_out; a.truncation_out = truncation_out;
+  const int threads = 128;
+  const unsigned blocks = static_cast<unsigned>((E + threads - 1) / threads);
+  if (math_mode == 0) env_rollout_pendulum_kernel<0><<<blocks, threads, 0, as_stream(stream)>>>(a);
+  else env_rollout_pendulum_kernel<1><<<blocks, threads, 0, as_stream(stream)>>>(a);
+  return check_launch("env_rollout_pendulum_kernel");
+}
+
+// ---- stage 4 ---------------------------------------------------------------------------------------
+int mbpo_mlp_dynamics_forward(const MbpoMlpEnsembleParams* p, const float* inp, const int32_t* member, int R,
+                              float* delta_out, void* stream) {
+  MBPO_REQUIRE(p && inp && member && delta_out, "mlp_dynamics_forward: null pointer");
+  MBPO_REQUIRE(R >= 0, "mlp_dynamics_forward: R < 0");
+  MBPO_REQUIRE(p->w_in && p->b_in && p->w_h && p->b_h && p->w_out && p->b_out, "mlp_dynamics_forward: null weights");
+  if (R == 0) return MBPO_OK;
+  const int rc = launch_mlp_forward(*p, inp, member, R, delta_out, as_stream(stream), g_err, sizeof(g_err));
+  if (rc != MBPO_OK) return rc;
+  return check_launch("mlp_dynamics_forward");
+}
+
+}  // extern "C"

@@ -1,0 +1,96 @@
+"""Vmapped env rollouts for SAC/PPO data collection (BASELINE config 3).
+
+One object stands for the reference's wrapper stack AutoResetWrapper(VmapWrapper(
+EpisodeWrapper(BraxWrapper(system)))) (mbpo/systems/brax_wrapper.py:40-50;
+mbpo/optimizers/policy_optimizers/brax_utils/training.py:29-47,50-137) and ``unroll`` emits
+the Transition that sac/acting.py:35-55 ``actor_step`` builds, for T steps in one launch.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict
+
+import torch
+
+from . import _lib
+from .config import config
+from .systems.base_systems import System, SystemParams, _Replaceable
+from .utils.optimizer_utils import Transition
+
+
+@dataclass
+class EnvState(_Replaceable):
+    """brax_utils/base.py:12-23 State, restricted to what the System path uses.  info holds
+    'steps', 'truncation' and 'first_obs' like the Episode/AutoReset wrappers' info dict."""
+    obs: torch.Tensor = None          # [E, X]
+    reward: torch.Tensor = None       # [E]
+    done: torch.Tensor = None         # [E] float, as brax
+    system_params: SystemParams = None
+    info: Dict[str, torch.Tensor] = None
+
+
+class VmappedSystemEnv:
+    def __init__(self, system: System, system_params: SystemParams, episode_length: int = 1000,
+                 action_repeat: int = 1):
+        self.system = system
+        self.init_system_params = system_params
+        self.episode_length = int(episode_length)
+        self.action_repeat = int(action_repeat)
+
+    @property
+    def action_size(self) -> int:
+        return self.system.u_dim
+
+    @property
+    def observation_size(self) -> int:
+        return self.system.x_dim
+
+    def reset(self, first_obs: torch.Tensor) -> EnvState:
+        """The reference samples first observations from the true replay buffer
+        (brax_wrapper.py:25-38); here the caller supplies them: first_obs [E, X]."""
+        obs = first_obs.to(torch.float32).contiguous().clone()
+        e = obs.shape[0]
+        zeros = torch.zeros(e, dtype=torch.float32, device=obs.device)
+        return EnvState(obs=obs, reward=zeros.clone(), done=zeros.clone(), system_params=self.init_system_params,
+                        info=dict(steps=zeros.clone(), truncation=zeros.clone(), first_obs=obs.clone()))
+
+    def unroll(self, state: EnvState, actions: torch.Tensor):
+        """actions [T, E, A] -> (final EnvState, Transition with fields [T, E, ...]); extras
+        carries state_extras.truncation like actor_step (acting.py:46-55)."""
+        acts = actions.to(torch.float32).contiguous()
+        T, E, A = acts.shape
+        X = self.system.x_dim
+        dev = acts.device
+        obs = state.obs.clone()
+        steps = state.info["steps"].clone()
+        done = state.done.clone()
+        first = state.info["first_obs"].contiguous()
+        o = torch.empty((T, E, X), dtype=torch.float32, device=dev)
+        n = torch.empty((T, E, X), dtype=torch.float32, device=dev)
+        r = torch.empty((T, E), dtype=torch.float32, device=dev)
+        d = torch.empty((T, E), dtype=torch.float32, device=dev)
+        tr = torch.empty((T, E), dtype=torch.float32, device=dev)
+        params = self.system.pack_params(state.system_params)
+        with _lib.cuda_guard(acts):
+            _lib.check(_lib.lib.mbpo_env_rollout(
+                self.system.system_kind, _lib.C.addressof(params), config.math_mode_id, X, A, self.episode_length,
+                self.action_repeat, _lib.ptr(obs), _lib.ptr(steps), _lib.ptr(done), _lib.ptr(first), _lib.ptr(acts),
+                E, T, _lib.ptr(o), _lib.ptr(r), _lib.ptr(d), _lib.ptr(n), _lib.ptr(tr), _lib.stream_ptr(dev)))
+        new_state = EnvState(obs=obs, reward=r[-1] if T else state.reward, done=done,
+                             system_params=state.system_params,
+                             info=dict(steps=steps, truncation=tr[-1] if T else state.info["truncation"],
+                                       first_obs=first))
+        transition = Transition(observation=o, action=acts, reward=r, discount=d, next_observation=n,
+                                extras={"state_extras": {"truncation": tr}})
+        return new_state, transition
+
+    def step(self, state: EnvState, action: torch.Tensor) -> EnvState:
+        """One wrapped env step: action [E, A]."""
+        new_state, _ = self.unroll(state, action.reshape(1, *action.shape))
+        return new_state
+
+
+def wrap(system: System, system_params: SystemParams, episode_length: int = 1000,
+         action_repeat: int = 1) -> VmappedSystemEnv:
+    """training.py:29-47 ``wrap`` applied to BraxWrapper(system, ...)."""
+    return VmappedSystemEnv(system, system_params, episode_length, action_repeat)

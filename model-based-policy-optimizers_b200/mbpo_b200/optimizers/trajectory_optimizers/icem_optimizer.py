@@ -1,0 +1,267 @@
+"""iCEM trajectory optimizer behind the reference's call signatures.
+
+Mirrors mbpo/optimizers/trajectory_optimizers/icem_optimizer.py: iCemParams :25-50,
+iCemOptimizerState :62-69, AbstractCost :78-90, iCemTO :93-257, iCEMOptimizer :260-319.
+``optimize`` is one launch of the fused CUDA plan kernel (mbpo_icem_plan): sampling, rollouts,
+elite selection and refit for all num_steps iterations run on the GPU; nothing is computed on
+the host.
+
+Additive to the reference: every method also accepts a leading problem axis -- initial_state
+[B, X] with an opt_state whose key is [B, 2] and best_sequence [B, H, A] -- which is
+``jax.vmap(optimize)`` with per-problem keys, and ``closed_loop`` runs the plan -> true
+System.step -> warm start loop of tests/test_icemopt.py:19-32 in a single launch.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Any, List, NamedTuple, Optional, Tuple
+
+import torch
+
+from ... import _lib
+from ... import random as jr
+from ...config import config
+from ...systems.base_systems import System
+from ...utils.type_aliases import OptimizerState, OptimizerTrainingOutPut
+from ..base_optimizer import BaseOptimizer
+
+
+class iCemParams(NamedTuple):
+    """icem_optimizer.py:25-50."""
+    num_particles: int = 10
+    num_samples: int = 500
+    num_elites: int = 50
+    init_std: float = 0.5
+    alpha: float = 0.0
+    num_steps: int = 5
+    exponent: float = 0.0
+    elite_set_fraction: float = 0.3
+    u_min: Any = -1.0
+    u_max: Any = 1.0
+    warm_start: bool = True
+    lambda_constraint: float = 1e4
+
+
+@dataclass
+class iCemOptimizerState(OptimizerState):
+    """icem_optimizer.py:62-69."""
+    best_sequence: torch.Tensor = None
+    best_reward: torch.Tensor = None
+
+    @property
+    def action(self):
+        # best_sequence[0]; with a leading problem axis: the first action of every problem
+        return self.best_sequence[..., 0, :]
+
+
+@dataclass
+class iCemTrainingOutput(OptimizerTrainingOutPut):
+    summary: List = None
+
+
+class AbstractCost:
+    """icem_optimizer.py:78-90.  Constraint costs are a 'next' row: the CUDA
+    path has no kernel for an arbitrary Python cost and refuses it rather than falling back."""
+
+    def __init__(self, horizon: int):
+        self.horizon = horizon
+
+    def __call__(self, states, actions):
+        raise NotImplementedError
+
+
+def _scalar_bound(v, name: str) -> float:
+    if isinstance(v, torch.Tensor):
+        if v.numel() == 1 or bool((v == v.reshape(-1)[0]).all()):
+            return float(v.reshape(-1)[0])
+        raise _lib.MbpoUnsupported(_lib.MBPO_EUNSUPPORTED, "array-valued %s is not supported by the CUDA path" % name)
+    try:
+        return float(v)
+    except TypeError:
+        import numpy as np
+        a = np.asarray(v, dtype=np.float32)
+        if (a == a.reshape(-1)[0]).all():
+            return float(a.reshape(-1)[0])
+        raise _lib.MbpoUnsupported(_lib.MBPO_EUNSUPPORTED, "array-valued %s is not supported by the CUDA path" % name)
+
+
+class iCemTO(BaseOptimizer):
+    def __init__(self, horizon: int, action_dim: int, key: Optional[torch.Tensor] = None,
+                 opt_params: iCemParams = iCemParams(), cost_fn: AbstractCost | None = None,
+                 use_optimism: bool = False, use_pessimism: bool = False, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.horizon = horizon
+        self.opt_params = opt_params
+        self.key = key
+        self.opt_dim = (horizon,) + (action_dim,)
+        self.action_dim = action_dim
+        self.cost_fn = cost_fn
+        self.use_optimism = use_optimism
+        self.use_pessimism = use_pessimism
+        if cost_fn is not None:
+            raise _lib.MbpoUnsupported(_lib.MBPO_EUNSUPPORTED,
+                                       "cost_fn constraints have no CUDA kernel yet (no fallback path exists)")
+
+    # ---- C-ABI configuration -----------------------------------------------------------------
+    def _cfg(self) -> _lib.IcemCfgC:
+        assert self.system is not None, "iCem optimizer requires system to be defined."
+        p = self.opt_params
+        cfg = _lib.IcemCfgC()
+        _lib.check(_lib.lib.mbpo_icem_cfg_init(
+            _lib.C.byref(cfg), self.horizon, self.action_dim, self.system.x_dim, p.num_particles, p.num_samples,
+            p.num_elites, p.init_std, p.alpha, p.num_steps, p.exponent, p.elite_set_fraction,
+            _scalar_bound(p.u_min, "u_min"), _scalar_bound(p.u_max, "u_max"), int(bool(p.warm_start)),
+            p.lambda_constraint))
+        cfg.prng_mode = config.prng_mode
+        cfg.summarize = _lib.SUMMARIZE_MAX if self.use_optimism else _lib.SUMMARIZE_MEAN   # :112-115
+        cfg.system_kind = self.system.system_kind
+        cfg.math_mode = config.math_mode_id
+        return cfg
+
+    # ---- reference API -------------------------------------------------------------------------
+    def init(self, key: torch.Tensor, true_buffer_state=None) -> iCemOptimizerState:
+        """icem_optimizer.py:121-132.  key [2] -> single-problem state; key [B, 2] -> B problems."""
+        assert self.system is not None, "iCem optimizer requires system to be defined."
+        ks = jr.split(key, 3)                                   # init_key, dummy_buffer_key, key
+        init_key, dummy_buffer_key, new_key = ks[..., 0, :], ks[..., 1, :], ks[..., 2, :]
+        system_params = self.system.init_params(init_key)
+        batch = tuple(key.shape[:-1])
+        return iCemOptimizerState(
+            true_buffer_state=self.dummy_true_buffer_state(dummy_buffer_key),
+            system_params=system_params,
+            best_sequence=torch.zeros(batch + self.opt_dim, dtype=torch.float32, device=key.device),
+            best_reward=torch.zeros(batch, dtype=torch.float32, device=key.device),
+            key=new_key.contiguous(),
+        )
+
+    def _plan_raw(self, x0: torch.Tensor, key: torch.Tensor, best_seq: torch.Tensor, system_params,
+                  trace: bool = False):
+        """x0 [B,X], key [B,2], best_seq [B,H,A] -> (best_seq', best_value, key', trace dict|None)."""
+        cfg = self._cfg()
+        B = x0.shape[0]
+        dev = x0.device
+        H, A = self.opt_dim
+        out_seq = torch.empty((B, H, A), dtype=torch.float32, device=dev)
+        out_val = torch.empty((B,), dtype=torch.float32, device=dev)
+        out_key = torch.empty((B, 2), dtype=torch.uint32, device=dev)
+        params = self.system.pack_params(system_params)
+        tr_c, tr = None, None
+        fused = bool(_lib.lib.mbpo_icem_plan_is_fused(_lib.C.byref(cfg)))
+        with _lib.cuda_guard(x0):
+            if fused:
+                if trace:
+                    S, M, K = cfg.num_steps, cfg.num_samples + cfg.num_prev_elites, cfg.num_elites
+                    tr = dict(actions=torch.empty((S, B, M, H * A), dtype=torch.float32, device=dev),
+                              values=torch.empty((S, B, M), dtype=torch.float32, device=dev),
+                              elite_idx=torch.empty((S, B, K), dtype=torch.int32, device=dev),
+                              mean=torch.empty((S, B, H * A), dtype=torch.float32, device=dev),
+                              std=torch.empty((S, B, H * A), dtype=torch.float32, device=dev),
+                              best_value=torch.empty((S, B), dtype=torch.float32, device=dev))
+                    tr_c = _lib.IcemTraceC(*(_lib.ptr(tr[n]) for n in ("actions", "values", "elite_idx", "mean",
+                                                                        "std", "best_value")))
+                _lib.check(_lib.lib.mbpo_icem_plan(_lib.C.byref(cfg), _lib.C.addressof(params), _lib.ptr(x0),
+                                                   _lib.ptr(key), _lib.ptr(best_seq), B, _lib.ptr(out_seq),
+                                                   _lib.ptr(out_val), _lib.ptr(out_key),
+                                                   _lib.C.byref(tr_c) if tr_c is not None else None,
+                                                   _lib.stream_ptr(dev)))
+            else:
+                if trace:
+                    raise _lib.MbpoUnsupported(_lib.MBPO_EUNSUPPORTED, "trace dumps exist for the fused plan only")
+                nbytes = _lib.lib.mbpo_icem_workspace_bytes(_lib.C.byref(cfg), B)
+                ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+                _lib.check(_lib.lib.mbpo_icem_plan_staged(_lib.C.byref(cfg), _lib.C.addressof(params), _lib.ptr(x0),
+                                                          _lib.ptr(key), _lib.ptr(best_seq), B, _lib.ptr(out_seq),
+                                                          _lib.ptr(out_val), _lib.ptr(out_key), _lib.ptr(ws), nbytes,
+                                                          _lib.stream_ptr(dev)))
+        return out_seq, out_val, out_key, tr
+
+    def _canon(self, initial_state: torch.Tensor, opt_state: iCemOptimizerState):
+        single = initial_state.dim() == 1
+        x0 = initial_state.reshape(1, -1) if single else initial_state
+        x0 = x0.to(torch.float32).contiguous()
+        B = x0.shape[0]
+        H, A = self.opt_dim
+        key = opt_state.key.reshape(-1, 2).contiguous()
+        seq = opt_state.best_sequence.reshape(-1, H, A).to(torch.float32).contiguous()
+        if key.shape[0] != B or seq.shape[0] != B:
+            raise ValueError("optimize: %d initial states but opt_state holds %d keys / %d sequences" % (
+                B, key.shape[0], seq.shape[0]))
+        return single, x0, key, seq
+
+    def optimize(self, initial_state: torch.Tensor, opt_state: iCemOptimizerState) -> iCemOptimizerState:
+        """icem_optimizer.py:134-252."""
+        assert self.system is not None, "iCem optimizer requires system to be defined."
+        single, x0, key, seq = self._canon(initial_state, opt_state)
+        out_seq, out_val, out_key, _ = self._plan_raw(x0, key, seq, opt_state.system_params)
+        if single:
+            out_seq, out_val, out_key = out_seq[0], out_val[0], out_key[0]
+        return opt_state.replace(key=out_key, best_sequence=out_seq, best_reward=out_val)
+
+    def act(self, obs: torch.Tensor, opt_state: iCemOptimizerState, evaluate: bool = True):
+        """icem_optimizer.py:254-257."""
+        new_opt_state = self.optimize(initial_state=obs, opt_state=opt_state)
+        return new_opt_state.action, new_opt_state
+
+    # ---- additive: closed loop in one launch (tests/test_icemopt.py:19-32) ---------------------
+    def closed_loop(self, initial_state: torch.Tensor, opt_state: iCemOptimizerState, num_steps: int):
+        """Returns (states [T, (B,) X], rewards [T, (B)], actions [T, (B,) A], new opt_state)."""
+        assert self.system is not None, "iCem optimizer requires system to be defined."
+        single, x0, key, seq = self._canon(initial_state, opt_state)
+        cfg = self._cfg()
+        B, dev = x0.shape[0], x0.device
+        H, A = self.opt_dim
+        states = torch.empty((num_steps, B, x0.shape[1]), dtype=torch.float32, device=dev)
+        rewards = torch.empty((num_steps, B), dtype=torch.float32, device=dev)
+        actions = torch.empty((num_steps, B, A), dtype=torch.float32, device=dev)
+        out_seq = torch.empty((B, H, A), dtype=torch.float32, device=dev)
+        out_key = torch.empty((B, 2), dtype=torch.uint32, device=dev)
+        params = self.system.pack_params(opt_state.system_params)
+        with _lib.cuda_guard(x0):
+            _lib.check(_lib.lib.mbpo_icem_mpc_closed_loop(
+                _lib.C.byref(cfg), _lib.C.addressof(params), _lib.ptr(x0), _lib.ptr(key), _lib.ptr(seq), B, num_steps,
+                _lib.ptr(states), _lib.ptr(rewards), _lib.ptr(actions), _lib.ptr(out_seq), _lib.ptr(out_key),
+                _lib.stream_ptr(dev)))
+        if single:
+            states, rewards, actions, out_seq, out_key = states[:, 0], rewards[:, 0], actions[:, 0], out_seq[0], out_key[0]
+        return states, rewards, actions, opt_state.replace(key=out_key, best_sequence=out_seq)
+
+
+class iCEMOptimizer(BaseOptimizer):
+    """icem_optimizer.py:260-319: wrapper for consistency with the SAC / PPO optimizers."""
+
+    def __init__(self, horizon: int, opt_params: iCemParams = iCemParams(), system: System | None = None,
+                 key: Optional[torch.Tensor] = None, **agent_kwargs):
+        super().__init__(system, key)
+        self.horizon = horizon
+        self.key = key
+        self.opt_params = opt_params
+        self.agent_class = iCemTO
+        self.agent_kwargs = agent_kwargs
+        if system is not None:
+            self.set_system(system)
+
+    @property
+    def can_act_in_batches(self):
+        return False
+
+    def init(self, key: torch.Tensor, true_buffer_state=None) -> iCemOptimizerState:
+        assert self.system is not None, "iCEM optimizer requires system to be defined."
+        self.agent = self.agent_class(horizon=self.horizon, action_dim=self.system.u_dim, key=self.key,
+                                      opt_params=self.opt_params, **self.agent_kwargs)
+        self.agent.set_system(self.system)
+        if true_buffer_state is None:
+            ks = jr.split(key, 2)
+            dummy_buffer_key, key = ks[0], ks[1]
+            true_buffer_state = self.dummy_true_buffer_state(dummy_buffer_key)
+        agent_state = self.agent.init(key)
+        agent_state.true_buffer_state = true_buffer_state
+        return agent_state
+
+    def act(self, obs: torch.Tensor, opt_state: iCemOptimizerState, evaluate: bool = True) -> Tuple[torch.Tensor, iCemOptimizerState]:
+        assert self.system is not None, "iCEM optimizer requires system to be defined."
+        action, opt_state = self.agent.act(obs.reshape(-1), opt_state, evaluate)
+        return action.reshape(1, -1), opt_state
+
+    def train(self, opt_state: iCemOptimizerState) -> iCemTrainingOutput:
+        training_output = super().train(opt_state)
+        return iCemTrainingOutput(optimizer_state=training_output.optimizer_state, summary=[])

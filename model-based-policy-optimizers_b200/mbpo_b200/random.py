@@ -1,0 +1,70 @@
+"""jax.random work-alikes on CUDA tensors (threefry2x32, bit-identical to JAX).
+
+Replaces the reference's calls at mbpo/optimizers/trajectory_optimizers/icem_optimizer.py:
+123,155,174-180,246 and mbpo/utils/general_utils.py:189-191.  Keys are uint32[..., 2] CUDA
+tensors; every function accepts a batch of keys (leading dims) = ``jax.vmap`` of the scalar call.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .config import config
+
+
+def PRNGKey(seed: int, device=None) -> torch.Tensor:
+    """jax.random.PRNGKey for a 64-bit seed: uint32[2] = [seed >> 32, seed & 0xffffffff]."""
+    dev = _lib.require_cuda(device)
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    hi, lo = seed >> 32, seed & 0xFFFFFFFF
+    # torch has no uint32 constructor from python ints > 2^31 on all versions: go through int64
+    return torch.tensor([hi, lo], dtype=torch.int64).to(torch.uint32).to(dev)
+
+
+def _as_keys(key: torch.Tensor) -> torch.Tensor:
+    if key.dtype not in (torch.uint32, torch.int32):
+        raise TypeError("PRNG keys must be uint32 (or int32 bit patterns), got %s" % key.dtype)
+    if key.shape[-1] != 2:
+        raise ValueError("PRNG keys must have shape [..., 2], got %s" % (tuple(key.shape),))
+    return key.contiguous()
+
+
+def split(key: torch.Tensor, num: int = 2) -> torch.Tensor:
+    """jax.random.split: uint32[..., 2] -> uint32[..., num, 2]."""
+    key = _as_keys(key)
+    m = key.numel() // 2
+    out = torch.empty(key.shape[:-1] + (num, 2), dtype=torch.uint32, device=key.device)
+    with _lib.cuda_guard(key):
+        _lib.check(_lib.lib.mbpo_prng_split(_lib.ptr(key), m, num, config.prng_mode, _lib.ptr(out),
+                                            _lib.stream_ptr(key.device)))
+    return out
+
+
+def random_bits(key: torch.Tensor, n: int) -> torch.Tensor:
+    """jax.random.bits(key, (n,)) : uint32[..., 2] -> uint32[..., n]."""
+    key = _as_keys(key)
+    out = torch.empty(key.shape[:-1] + (n,), dtype=torch.uint32, device=key.device)
+    with _lib.cuda_guard(key):
+        _lib.check(_lib.lib.mbpo_prng_random_bits(_lib.ptr(key), key.numel() // 2, n, config.prng_mode,
+                                                  _lib.ptr(out), _lib.stream_ptr(key.device)))
+    return out
+
+
+def uniform(key: torch.Tensor, n: int, minval: float = 0.0, maxval: float = 1.0) -> torch.Tensor:
+    """jax.random.uniform(key, (n,), minval, maxval) in float32."""
+    key = _as_keys(key)
+    out = torch.empty(key.shape[:-1] + (n,), dtype=torch.float32, device=key.device)
+    with _lib.cuda_guard(key):
+        _lib.check(_lib.lib.mbpo_prng_uniform(_lib.ptr(key), key.numel() // 2, n, config.prng_mode, minval, maxval,
+                                              _lib.ptr(out), _lib.stream_ptr(key.device)))
+    return out
+
+
+def normal(key: torch.Tensor, n: int) -> torch.Tensor:
+    """jax.random.normal(key, (n,)) in float32."""
+    key = _as_keys(key)
+    out = torch.empty(key.shape[:-1] + (n,), dtype=torch.float32, device=key.device)
+    with _lib.cuda_guard(key):
+        _lib.check(_lib.lib.mbpo_prng_normal(_lib.ptr(key), key.numel() // 2, n, config.prng_mode, _lib.ptr(out),
+                                             _lib.stream_ptr(key.device)))
+    return out

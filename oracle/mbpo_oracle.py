@@ -1,0 +1,557 @@
+"""ORACLE (test infrastructure, NOT product code) -- NumPy restatement of the mbpo
+iCEM planning hot path, following the reference line by line.
+
+Reference files restated here (paths relative to /root/reference):
+  mbpo/utils/general_utils.py:81-208                       powerlaw_psd_gaussian
+  mbpo/systems/dynamics/pendulum_dynamics.py:12-63         PendulumDynamics.next_state / ode
+  mbpo/systems/rewards/pendulum_reward.py:12-42            PendulumReward.__call__
+  mbpo/systems/pendulum_system.py:18-46                    PendulumSystem.step / reset
+  mbpo/utils/optimizer_utils.py:11-59                      rollout_actions
+  mbpo/optimizers/trajectory_optimizers/icem_optimizer.py:121-257   iCemTO.init/optimize/act
+  mbpo/systems/brax_wrapper.py:40-50, mbpo/optimizers/policy_optimizers/brax_utils/
+  training.py:71-137, .../sac/acting.py:35-55              vmapped env step + wrappers
+  mbpo/utils/network_utils.py:5-17                         MLP template (learned dynamics)
+
+PARITY PINNING: the reference is pure JAX, JAX cannot be installed here, and the
+reference's tests hold no golden vectors (tests/test_icemopt.py:37-38 is the threshold
+sum(rewards) >= -400).  This restatement is therefore pinned by (i) the JAX PRNG
+known-answer vectors (oracle/jax_prng.py), (ii) the reference's behavioural threshold,
+(iii) an independent plain-C twin (oracle/c/mbpo_oracle.c).  Float parity against a
+real JAX/XLA run is UNPINNED.
+
+Summation orders that XLA leaves unspecified (mean over the horizon, mean over elites)
+are fixed here as plain left-to-right float32 sums.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline/reference legs may
+import this module.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field, replace
+from typing import Optional
+
+import numpy as np
+
+from . import jax_prng as jr
+
+F32 = np.float32
+U32 = np.uint32
+
+
+# ----------------------------------------------------------------------------------
+# iCemParams  (icem_optimizer.py:25-50)
+# ----------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class ICemParams:
+    num_particles: int = 10
+    num_samples: int = 500
+    num_elites: int = 50
+    init_std: float = 0.5
+    alpha: float = 0.0
+    num_steps: int = 5
+    exponent: float = 0.0
+    elite_set_fraction: float = 0.3
+    u_min: float = -1.0
+    u_max: float = 1.0
+    warm_start: bool = True
+    lambda_constraint: float = 1e4
+
+    @property
+    def num_prev_elites(self) -> int:  # icem_optimizer.py:170
+        return max(int(self.elite_set_fraction * self.num_elites), 1)
+
+
+# ----------------------------------------------------------------------------------
+# Pendulum parameters  (pendulum_dynamics.py:12-19, pendulum_reward.py:12-16)
+# ----------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class PendulumParams:
+    max_speed: float = 8.0
+    max_torque: float = 2.0
+    dt: float = 0.05
+    g: float = 9.81
+    m: float = 1.0
+    l: float = 1.0
+    control_cost: float = 0.02
+    angle_cost: float = 1.0
+    target_angle: float = 0.0
+
+    def packed(self) -> np.ndarray:
+        return np.array([self.max_speed, self.max_torque, self.dt, self.g, self.m, self.l,
+                         self.control_cost, self.angle_cost, self.target_angle], dtype=F32)
+
+
+# ----------------------------------------------------------------------------------
+# powerlaw_psd_gaussian  (general_utils.py:81-208)
+# ----------------------------------------------------------------------------------
+def powerlaw_tables(exponent: float, samples: int, dtype=F32):
+    """Static (trace-time) part: s_scale[F] and sigma  (general_utils.py:143-178)."""
+    dt = dtype
+    nfreq = samples // 2 + 1
+    f = np.arange(nfreq, dtype=dt) / dt(samples)                     # rfftfreq, :143
+    fmin = max(0.0, 1.0 / samples)                                    # :146-147
+    s_scale = f.copy()
+    ix = int(np.sum(s_scale < dt(fmin)))                              # :153
+    if ix and ix < len(s_scale):                                      # :166-172
+        s_scale[:ix] = s_scale[ix]
+    s_scale = np.power(s_scale, dt(-exponent / 2.0)).astype(dt)       # :173
+    w = s_scale[1:].copy()                                            # :176
+    w[-1] = w[-1] * dt((1 + (samples % 2)) / 2.0)                     # :177
+    sigma = dt(2) * np.sqrt(np.sum(w ** 2, dtype=dt)) / dt(samples)   # :178
+    return s_scale.astype(dt), dt(sigma)
+
+
+def irfft_direct(sr, si, n, dtype=F32):
+    """Direct real inverse DFT of the half spectrum (jnp.fft.irfft semantics: the
+    imaginary parts of the DC and, for even n, the Nyquist bins are ignored)."""
+    nfreq = n // 2 + 1
+    t = np.arange(n)
+    k = np.arange(nfreq)
+    ang = 2.0 * np.pi * ((np.outer(k, t)) % n) / n
+    c = np.cos(ang)
+    s = np.sin(ang)
+    wgt = np.full(nfreq, 2.0)
+    wgt[0] = 1.0
+    if n % 2 == 0:
+        wgt[-1] = 1.0
+    cr = (wgt[:, None] * c / n).astype(dtype)
+    ci = (-wgt[:, None] * s / n).astype(dtype)
+    ci[0] = 0
+    if n % 2 == 0:
+        ci[-1] = 0
+    return (sr.astype(dtype) @ cr + si.astype(dtype) @ ci).astype(dtype)
+
+
+def powerlaw_psd_gaussian_keys(exponent: float, size: int, keys: np.ndarray,
+                               partitionable: bool = False, dtype=F32,
+                               return_bits: bool = False):
+    """vmap(powerlaw_psd_gaussian) over keys uint32[M,2] -> float[M, size].
+
+    Per key (general_utils.py:189-207): key_sr, key_si, _ = split(rng, 3);
+    sr = normal(key_sr,(F,))*s_scale; si likewise; Nyquist/DC fix; irfft(n=size)/sigma.
+    """
+    keys = np.asarray(keys, dtype=U32).reshape(-1, 2)
+    m = keys.shape[0]
+    nfreq = size // 2 + 1
+    s_scale, sigma = powerlaw_tables(exponent, size, dtype)
+    sr = np.empty((m, nfreq), dtype=F32)
+    si = np.empty((m, nfreq), dtype=F32)
+    bits_r = np.empty((m, nfreq), dtype=U32)
+    bits_i = np.empty((m, nfreq), dtype=U32)
+    sub = split_keys(keys, 3, partitionable)                          # :189
+    for out, bits_out, kk in ((sr, bits_r, sub[:, 0]), (si, bits_i, sub[:, 1])):
+        b = random_bits_keys(kk, nfreq, partitionable)
+        bits_out[:] = b
+        out[:] = jr.bits_to_normal(b)                                 # :190-191
+    sr = sr.astype(dtype) * s_scale
+    si = si.astype(dtype) * s_scale
+    if size % 2 == 0:                                                 # :195-197
+        si[:, -1] = 0
+        sr[:, -1] = sr[:, -1] * dtype(np.sqrt(2))
+    si[:, 0] = 0                                                      # :200-201
+    sr[:, 0] = sr[:, 0] * dtype(np.sqrt(2))
+    y = np.fft.irfft(sr + 1j * si, n=size, axis=-1).astype(dtype) / sigma   # :207
+    if return_bits:
+        return y.astype(dtype), bits_r, bits_i
+    return y.astype(dtype)
+
+
+def powerlaw_psd_gaussian(exponent: float, size: int, rng, partitionable: bool = False, dtype=F32):
+    return powerlaw_psd_gaussian_keys(exponent, size, np.asarray(rng).reshape(1, 2),
+                                      partitionable, dtype)[0]
+
+
+# -- vmapped PRNG helpers ----------------------------------------------------------
+def split_keys(keys: np.ndarray, num: int, partitionable: bool = False) -> np.ndarray:
+    """vmap(lambda k: split(k, num))(keys): uint32[M,2] -> uint32[M,num,2]."""
+    keys = np.asarray(keys, dtype=U32).reshape(-1, 2)
+    k0 = keys[:, 0:1]
+    k1 = keys[:, 1:2]
+    if partitionable:
+        y0, y1 = jr.threefry2x32(k0, k1, np.zeros((1, num), dtype=U32), np.arange(num, dtype=U32)[None])
+        return np.stack([y0, y1], axis=-1)
+    c = np.arange(2 * num, dtype=U32)
+    y0, y1 = jr.threefry2x32(k0, k1, c[None, :num], c[None, num:])
+    return np.concatenate([y0, y1], axis=1).reshape(-1, num, 2)
+
+
+def random_bits_keys(keys: np.ndarray, n: int, partitionable: bool = False) -> np.ndarray:
+    """vmap(lambda k: random_bits(k,(n,)))(keys): uint32[M,2] -> uint32[M,n]."""
+    keys = np.asarray(keys, dtype=U32).reshape(-1, 2)
+    k0 = keys[:, 0:1]
+    k1 = keys[:, 1:2]
+    if partitionable:
+        y0, y1 = jr.threefry2x32(k0, k1, np.zeros((1, n), dtype=U32), np.arange(n, dtype=U32)[None])
+        return y0 ^ y1
+    npad = n + (n % 2)
+    c = np.arange(npad, dtype=U32)
+    if n % 2:
+        c[-1] = 0
+    h = npad // 2
+    y0, y1 = jr.threefry2x32(k0, k1, c[None, :h], c[None, h:])
+    return np.concatenate([y0, y1], axis=1)[:, :n]
+
+
+# ----------------------------------------------------------------------------------
+# Pendulum System.step  (pendulum_system.py:18-39; batched over leading axis)
+# ----------------------------------------------------------------------------------
+def pendulum_step(x: np.ndarray, u: np.ndarray, p: PendulumParams = PendulumParams(), dtype=F32):
+    """x[...,3], u[...] (scalar action per row) -> (x_next[...,3], reward[...])."""
+    d = dtype
+    x = np.asarray(x, dtype=d)
+    u = np.asarray(u, dtype=d)
+    max_speed, max_torque, dt, g, m, l = (d(p.max_speed), d(p.max_torque), d(p.dt), d(p.g), d(p.m), d(p.l))
+    th = np.arctan2(x[..., 1], x[..., 0]).astype(d)                   # dynamics :35
+    thdot = x[..., 2]
+    uu = (np.clip(u, d(-1), d(1)) * max_torque).astype(d)             # :59
+    c_g = d(d(d(3) * g) / d(d(2) * l))                                # 3*g/(2*l)
+    c_u = d(d(3.0) / d(m * d(l * l)))                                 # 3.0/(m*l**2)
+    thdd = (c_g * np.sin(th).astype(d) + c_u * uu).astype(d)          # :60
+    nthd_ode = np.clip((thdot + thdd * dt).astype(d), -max_speed, max_speed)   # :61-62
+    newth = (th + nthd_ode * dt).astype(d)                            # :40
+    nthd = np.clip((thdot + thdd * dt).astype(d), -max_speed, max_speed)       # :41-42
+    x_next = np.stack([np.cos(newth), np.sin(newth), nthd], axis=-1).astype(d)  # :43
+    # reward on the CURRENT state and the raw action  (pendulum_reward.py:32-40)
+    pi = d(np.pi)
+    two_pi = d(2 * np.pi)
+    diff = (th - d(p.target_angle)).astype(d)
+    diff = (np.remainder((diff + pi).astype(d), two_pi).astype(d) - pi).astype(d)   # :35 floored mod
+    reward = (-(d(p.angle_cost) * (diff * diff) + d(0.1) * (thdot * thdot))
+              - d(p.control_cost) * (u * u)).astype(d)                # :38-39
+    return x_next, reward
+
+
+def pendulum_reset(dtype=F32):
+    """PendulumSystem.reset (pendulum_system.py:41-46)."""
+    return np.array([-1.0, 0.0, 0.0], dtype=dtype), dtype(0.0)
+
+
+# ----------------------------------------------------------------------------------
+# Learned MLP-ensemble System (config 4; template network_utils.py:5-17, swish)
+# ----------------------------------------------------------------------------------
+@dataclass
+class MlpEnsembleParams:
+    """E members of [X+A -> hidden.. -> X] with swish; predicts delta-x.  Weights are
+    stored [E, in, out] (flax Dense kernel layout), biases [E, out]."""
+    weights: list
+    biases: list
+    reward: PendulumParams = field(default_factory=PendulumParams)
+
+    @property
+    def num_members(self) -> int:
+        return self.weights[0].shape[0]
+
+
+def make_mlp_ensemble(seed: int = 3, members: int = 5, x_dim: int = 3, u_dim: int = 1,
+                      hidden=(256, 256, 256), scale: float = 1.0) -> MlpEnsembleParams:
+    rng = np.random.default_rng(seed)
+    dims = (x_dim + u_dim,) + tuple(hidden) + (x_dim,)
+    ws, bs = [], []
+    for i in range(len(dims) - 1):
+        ws.append((rng.standard_normal((members, dims[i], dims[i + 1])) * scale / np.sqrt(dims[i])).astype(F32))
+        bs.append((0.01 * rng.standard_normal((members, dims[i + 1]))).astype(F32))
+    # keep the predicted delta small so rollouts stay bounded
+    ws[-1] = (ws[-1] * F32(0.1)).astype(F32)
+    return MlpEnsembleParams(ws, bs)
+
+
+def _bf16_round(a: np.ndarray) -> np.ndarray:
+    """Round-to-nearest-even float32 -> bfloat16 -> float32."""
+    a = np.ascontiguousarray(a, dtype=F32)
+    b = a.view(U32)
+    rounded = ((b + U32(0x7FFF) + ((b >> U32(16)) & U32(1))) & U32(0xFFFF0000)).astype(U32)
+    return rounded.view(F32)
+
+
+def swish(x):
+    return x / (1.0 + np.exp(-x))
+
+
+def mlp_member_forward(params: MlpEnsembleParams, member: np.ndarray, inp: np.ndarray,
+                       bf16: bool = False) -> np.ndarray:
+    """inp[M, X+A], member[M] (which ensemble member serves each row) -> delta[M, X].
+
+    bf16=True applies the same operand rounding as the tensor-core path: activations and
+    hidden-layer weights rounded to bfloat16, products accumulated in float32; the first
+    layer (K = X+A) and the last layer (N = X) stay float32.
+    """
+    h = np.asarray(inp, dtype=F32)
+    nl = len(params.weights)
+    out = np.empty((h.shape[0], params.weights[-1].shape[-1]), dtype=F32)
+    for e in range(params.num_members):
+        rows = np.nonzero(member == e)[0]
+        if rows.size == 0:
+            continue
+        a = h[rows]
+        for li in range(nl):
+            w = params.weights[li][e]
+            b = params.biases[li][e]
+            hidden_gemm = 0 < li < nl - 1
+            if bf16 and hidden_gemm:
+                a = (_bf16_round(a).astype(np.float64) @ _bf16_round(w).astype(np.float64)).astype(F32) + b
+            else:
+                a = (a.astype(np.float64) @ w.astype(np.float64)).astype(F32) + b
+            if li < nl - 1:
+                a = swish(a.astype(F32)).astype(F32)
+        out[rows] = a
+    return out
+
+
+def mlp_ensemble_step(x, u, member, params: MlpEnsembleParams, bf16: bool = False):
+    """System.step for the learned ensemble: x_next = x + MLP_member([x,u]); the reward is
+    the pendulum reward (pendulum_reward.py:27-42) on the current state."""
+    x = np.asarray(x, dtype=F32)
+    u = np.asarray(u, dtype=F32)
+    inp = np.concatenate([x, u[..., None]], axis=-1).astype(F32)
+    dx = mlp_member_forward(params, member, inp, bf16)
+    x_next = (x + dx).astype(F32)
+    _, reward = pendulum_step(x, u, params.reward)
+    return x_next, reward
+
+
+# ----------------------------------------------------------------------------------
+# rollout_actions  (optimizer_utils.py:11-59), batched over rows
+# ----------------------------------------------------------------------------------
+def rollout_actions(x0: np.ndarray, actions: np.ndarray, p: PendulumParams = PendulumParams(),
+                    dtype=F32, full: bool = False):
+    """x0[R,3] (or [3]), actions[R,H] -> mean-over-horizon reward[R]  (icem :160 inner mean).
+
+    full=True also returns the brax Transition fields (observation, reward,
+    next_observation) as arrays [R,H,3], [R,H], [R,H,3]  (optimizer_utils.py:47-58).
+    """
+    actions = np.asarray(actions, dtype=dtype)
+    r, h = actions.shape
+    x = np.broadcast_to(np.asarray(x0, dtype=dtype), (r, 3)).copy()
+    acc = np.zeros(r, dtype=dtype)
+    if full:
+        obs = np.empty((r, h, 3), dtype=dtype)
+        nxt = np.empty((r, h, 3), dtype=dtype)
+        rew = np.empty((r, h), dtype=dtype)
+    for t in range(h):                                                # lax.scan :46
+        xn, rw = pendulum_step(x, actions[:, t], p, dtype)
+        if full:
+            obs[:, t] = x
+            nxt[:, t] = xn
+            rew[:, t] = rw
+        acc = (acc + rw).astype(dtype)                                # left-to-right f32 sum
+        x = xn
+    ret = (acc / dtype(h)).astype(dtype)                              # jnp.mean over horizon
+    if full:
+        return ret, obs, rew, nxt
+    return ret
+
+
+# ----------------------------------------------------------------------------------
+# iCEM  (icem_optimizer.py:121-257)
+# ----------------------------------------------------------------------------------
+@dataclass
+class ICemState:
+    """iCemOptimizerState (icem_optimizer.py:62-69) minus the opaque replay buffer."""
+    key: np.ndarray
+    best_sequence: np.ndarray
+    best_reward: np.ndarray
+
+    @property
+    def action(self):
+        return self.best_sequence[0]
+
+    def replace(self, **kw):
+        return replace(self, **kw)
+
+
+def icem_init(key, horizon: int, action_dim: int = 1, partitionable: bool = False) -> ICemState:
+    """iCemTO.init (icem_optimizer.py:121-132): init_key, dummy_buffer_key, key = split(key, 3)."""
+    ks = jr.split(key, 3, partitionable)
+    return ICemState(key=ks[2], best_sequence=np.zeros((horizon, action_dim), dtype=F32),
+                     best_reward=F32(0.0))
+
+
+def total_order_key(v: np.ndarray) -> np.ndarray:
+    """Monotone uint32 image of float32 under JAX's sort order (jax/_src/lax/lax.py
+    _float_to_int_for_sort): IEEE total order with -0.0 == +0.0 and all NaNs equal, last."""
+    v = np.asarray(v, dtype=F32)
+    b = v.view(U32).copy()
+    b[v == 0] = U32(0)
+    b[np.isnan(v)] = U32(0x7FC00000)
+    neg = (b >> U32(31)).astype(bool)
+    return np.where(neg, ~b, b | U32(0x80000000)).astype(U32)
+
+
+def stable_argsort(values: np.ndarray) -> np.ndarray:
+    """jnp argsort: stable ascending under the total order (icem_optimizer.py:199)."""
+    return np.argsort(total_order_key(values), kind="stable")
+
+
+def icem_sample_actions(carry_key, mean, std, params: ICemParams, horizon: int, action_dim: int = 1,
+                        partitionable: bool = False, dtype=F32, return_bits: bool = False):
+    """One iteration of key plumbing + colored sampling  (icem_optimizer.py:174-192).
+
+    Returns (next_key, actions[N+Np, H, A], particle_keys[N+Np, 2]) (+ bit streams)."""
+    n = params.num_samples
+    npe = params.num_prev_elites
+    ks = jr.split(carry_key, 2, partitionable)                        # :174
+    sampling_rng, particles_rng = ks[0], ks[1]
+    srs = jr.split(sampling_rng, n + 1, partitionable)                # :175
+    next_key, sample_keys = srs[0], srs[1:]                           # :176
+    particle_keys = jr.split(particles_rng, n + npe, partitionable)   # :177
+    dim_keys = split_keys(sample_keys, action_dim, partitionable)     # :180  [N, A, 2]
+    res = powerlaw_psd_gaussian_keys(params.exponent, horizon, dim_keys.reshape(-1, 2),
+                                     partitionable, dtype, return_bits=return_bits)
+    noise = res[0] if return_bits else res
+    colored = noise.reshape(n, action_dim, horizon).transpose(0, 2, 1)   # out_axes=1, :185-187
+    mean = np.asarray(mean, dtype=dtype)
+    std = np.asarray(std, dtype=dtype)
+    acts = (mean[None] + colored * std[None]).astype(dtype)           # :190
+    acts = np.clip(acts, dtype(params.u_min), dtype(params.u_max))    # :191
+    prev_elites = np.zeros((npe, horizon, action_dim), dtype=dtype)   # closure zeros, :192,:245
+    acts = np.concatenate([acts, prev_elites], axis=0)
+    if return_bits:
+        return next_key, acts, particle_keys, res[1], res[2]
+    return next_key, acts, particle_keys
+
+
+def particle_mean(value_per_particle: np.ndarray, dtype=F32) -> np.ndarray:
+    """jnp.mean over the particle axis (last), left-to-right."""
+    p = value_per_particle.shape[-1]
+    acc = np.zeros(value_per_particle.shape[:-1], dtype=dtype)
+    for i in range(p):
+        acc = (acc + value_per_particle[..., i]).astype(dtype)
+    return (acc / dtype(p)).astype(dtype)
+
+
+def icem_objective(x0, acts, params: ICemParams, sys_params: PendulumParams, use_optimism=False, dtype=F32):
+    """vmap(objective) (icem_optimizer.py:144-166,195) for the deterministic pendulum: every
+    particle sees the same trajectory, so mean/max over particles is over P identical values."""
+    ret = rollout_actions(np.asarray(x0, dtype=dtype), acts[:, :, 0], sys_params, dtype)
+    if use_optimism or params.num_particles == 1:
+        return ret
+    return particle_mean(np.repeat(ret[:, None], params.num_particles, axis=1), dtype)
+
+
+def icem_refit(acts, values, mean, std, best_value, best_seq, params: ICemParams, dtype=F32):
+    """Elite select + refit + best tracking  (icem_optimizer.py:199-226)."""
+    k = params.num_elites
+    idx = stable_argsort(values)[-k:]                                 # :199
+    elites = acts[idx]                                                # :202
+    elite_values = values[idx]                                        # :203
+    acc = np.zeros(elites.shape[1:], dtype=dtype)
+    for e in range(k):
+        acc = (acc + elites[e]).astype(dtype)
+    elite_mean = (acc / dtype(k)).astype(dtype)                       # :206
+    acc = np.zeros(elites.shape[1:], dtype=dtype)
+    for e in range(k):
+        dlt = (elites[e] - elite_mean).astype(dtype)
+        acc = (acc + dlt * dlt).astype(dtype)
+    elite_var = (acc / dtype(k)).astype(dtype)                        # :207 (ddof=0, two-pass)
+    a = dtype(params.alpha)
+    one_m = dtype(1 - params.alpha)
+    new_mean = (mean * a + one_m * elite_mean).astype(dtype)          # :210
+    var = ((std * std) * a + one_m * elite_var).astype(dtype)         # :211
+    new_std = np.sqrt(var).astype(dtype)                              # :214
+    if best_value <= elite_values[-1]:                                # :217-226
+        best_value, best_seq = elite_values[-1], elites[-1]
+    return new_mean, new_std, best_value, best_seq, idx
+
+
+def icem_optimize(x0, state: ICemState, params: ICemParams, horizon: int, action_dim: int = 1,
+                  sys_params: PendulumParams = PendulumParams(), use_optimism: bool = False,
+                  partitionable: bool = False, dtype=F32, trace: Optional[list] = None) -> ICemState:
+    """iCemTO.optimize (icem_optimizer.py:134-252) for one problem."""
+    mean = np.zeros((horizon, action_dim), dtype=dtype)
+    if params.warm_start:                                             # :239-241
+        mean[:-1] = state.best_sequence[1:]
+        mean[-1] = state.best_sequence[-1]
+    std = np.full((horizon, action_dim), params.init_std, dtype=dtype)   # :243
+    best_seq = mean.copy()                                            # :244
+    best_value = dtype(-np.inf)                                       # :235
+    ks = jr.split(state.key, 2, partitionable)                        # :246
+    carry_key, new_state_key = ks[0], ks[1]
+    for it in range(params.num_steps):                                # lax.scan :250
+        in_key, in_mean, in_std = carry_key, mean, std
+        carry_key, acts, _ = icem_sample_actions(carry_key, mean, std, params, horizon, action_dim,
+                                                 partitionable, dtype)
+        values = icem_objective(x0, acts, params, sys_params, use_optimism, dtype)    # :195
+        mean, std, best_value, best_seq, idx = icem_refit(acts, values, mean, std, best_value,
+                                                          best_seq, params, dtype)
+        if trace is not None:
+            trace.append(dict(key=in_key, mean_in=in_mean, std_in=in_std, actions=acts, values=values,
+                              elite_idx=idx, mean=mean, std=std, best_value=best_value,
+                              best_seq=best_seq))
+    return ICemState(key=new_state_key, best_sequence=np.asarray(best_seq, dtype=F32),
+                     best_reward=F32(best_value))                     # :251
+
+
+def icem_act(x0, state: ICemState, params: ICemParams, horizon: int, **kw):
+    """iCemTO.act (icem_optimizer.py:254-257)."""
+    new_state = icem_optimize(x0, state, params, horizon, **kw)
+    return new_state.action, new_state
+
+
+def closed_loop_mpc(num_steps: int = 200, horizon: int = 20, params: ICemParams = ICemParams(),
+                    seed: int = 0, partitionable: bool = False, collapse_particles: bool = True):
+    """tests/test_icemopt.py:6-32 -- returns (states[T,3], rewards[T], actions[T])."""
+    key = jr.PRNGKey(seed)
+    ks = jr.split(key, 3, partitionable)                              # optimizer_key, init_key, key
+    init_key = ks[1]
+    x, _ = pendulum_reset()
+    st = icem_init(init_key, horizon, 1, partitionable)
+    p = replace(params, num_particles=1) if collapse_particles else params
+    xs, rs, us = [], [], []
+    for _ in range(num_steps):
+        a, st = icem_act(x, st, p, horizon, partitionable=partitionable)
+        xn, r = pendulum_step(x[None], a, PendulumParams())
+        x = xn[0]
+        xs.append(x)
+        rs.append(r[0])
+        us.append(a[0])
+    return np.array(xs), np.array(rs), np.array(us)
+
+
+# ----------------------------------------------------------------------------------
+# Vmapped env step with Episode/AutoReset wrappers and actor_step Transition
+#   brax_wrapper.py:40-50; brax_utils/training.py:71-74,91-107,119-137; sac/acting.py:35-55
+# ----------------------------------------------------------------------------------
+def env_rollout(x0: np.ndarray, actions: np.ndarray, episode_length: int,
+                p: PendulumParams = PendulumParams(), action_repeat: int = 1,
+                steps0: Optional[np.ndarray] = None, done0: Optional[np.ndarray] = None,
+                first_obs: Optional[np.ndarray] = None, dtype=F32):
+    """x0[E,3], actions[T,E] -> dict of Transition fields, time-major [T,E,...].
+
+    Per env and step: (1) AutoReset: steps = where(done, 0, steps); done = 0
+    (training.py:120-124); (2) Episode: action_repeat x system.step with the same action,
+    rewards summed (:92-97); (3) steps += action_repeat; done = where(steps >= L, 1, done);
+    truncation = where(steps >= L, 1 - done_sys, 0) (:98-107); (4) obs = where(done,
+    first_obs, obs) (:136); (5) Transition(observation=previous obs, action, reward,
+    discount = 1 - done, next_observation = post-reset obs, truncation) (acting.py:46-55).
+    """
+    t_len, e = actions.shape
+    obs = np.asarray(x0, dtype=dtype).copy()
+    first = obs.copy() if first_obs is None else np.asarray(first_obs, dtype=dtype)
+    steps = np.zeros(e, dtype=dtype) if steps0 is None else np.asarray(steps0, dtype=dtype).copy()
+    done = np.zeros(e, dtype=dtype) if done0 is None else np.asarray(done0, dtype=dtype).copy()
+    out = dict(observation=np.empty((t_len, e, 3), dtype), action=np.asarray(actions, dtype=dtype)[..., None],
+               reward=np.empty((t_len, e), dtype), discount=np.empty((t_len, e), dtype),
+               next_observation=np.empty((t_len, e, 3), dtype), truncation=np.empty((t_len, e), dtype))
+    for t in range(t_len):
+        steps = np.where(done != 0, dtype(0), steps)
+        done = np.zeros(e, dtype=dtype)                               # system done is always 0.0
+        prev = obs
+        rew = np.zeros(e, dtype=dtype)
+        x = obs
+        for _ in range(action_repeat):
+            x, r = pendulum_step(x, actions[t], p, dtype)
+            rew = (rew + r).astype(dtype)
+        steps = (steps + dtype(action_repeat)).astype(dtype)
+        over = steps >= dtype(episode_length)
+        trunc = np.where(over, dtype(1) - done, dtype(0)).astype(dtype)
+        done = np.where(over, dtype(1), done).astype(dtype)
+        obs = np.where(done[:, None] != 0, first, x).astype(dtype)
+        out["observation"][t] = prev
+        out["reward"][t] = rew
+        out["discount"][t] = dtype(1) - done
+        out["next_observation"][t] = obs
+        out["truncation"][t] = trunc
+    out["final_obs"] = obs
+    out["final_steps"] = steps
+    out["final_done"] = done
+    return out

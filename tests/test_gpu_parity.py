@@ -1,0 +1,538 @@
+"""GPU parity tests: the CUDA path (through the C ABI / the host mirror) against the CPU oracle.
+
+Bars (BASELINE.json north_star): uint32 PRNG words and elite indices bit-exact; states,
+returns and refit mean/std within rel 1e-5 (fp32).  Floats that depend on libm
+(log1p/atan2/sin/cos) differ from the NumPy oracle by a few ulp, so tolerances are stated per
+test.  Chaotic amplification over long open-loop rollouts is handled by teacher forcing
+(SURVEY.md section 7).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import jax_prng as ojr
+from oracle import mbpo_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def mb(cuda_device):
+    import mbpo_b200
+    return mbpo_b200
+
+
+def _keys(n, seed=0):
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, 2 ** 32, size=(n, 2), dtype=np.uint64).astype(np.uint32)
+
+
+def _dev(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+@pytest.fixture(params=[False, True], ids=["legacy", "partitionable"])
+def prng_mode(request, mb):
+    mb.config.threefry_partitionable = request.param
+    yield request.param
+    mb.config.threefry_partitionable = False
+
+
+@pytest.fixture(params=["reference", "theta_carry"])
+def math_mode(request, mb):
+    mb.config.math_mode = request.param
+    yield request.param
+    mb.config.math_mode = "reference"
+
+
+# ---------------------------------------------------------------------------------------------
+# PRNG: bit-exact
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("num", [1, 2, 3, 7, 501])
+def test_split_bit_exact(mb, cuda_device, prng_mode, num):
+    keys = _keys(33, seed=num)
+    got = mb.random.split(_dev(keys, cuda_device), num).cpu().numpy()
+    want = orc.split_keys(keys, num, prng_mode)
+    assert got.dtype == np.uint32 and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("n", [1, 2, 11, 16, 26, 1000])
+def test_random_bits_bit_exact(mb, cuda_device, prng_mode, n):
+    keys = _keys(17, seed=n)
+    got = mb.random.random_bits(_dev(keys, cuda_device), n).cpu().numpy()
+    assert np.array_equal(got, orc.random_bits_keys(keys, n, prng_mode))
+
+
+def test_prngkey_and_known_answers(mb, cuda_device):
+    k0 = mb.random.PRNGKey(0, cuda_device)
+    assert k0.cpu().numpy().tolist() == [0, 0]
+    assert mb.random.split(k0).cpu().numpy().tolist() == [[4146024105, 967050713], [2718843009, 1272950319]]
+    assert abs(float(mb.random.normal(k0, 1)[0]) - (-0.20584226)) < 1e-6
+    assert abs(float(mb.random.uniform(k0, 1)[0]) - 0.41845703) < 1e-7
+    assert abs(float(mb.random.normal(mb.random.PRNGKey(42, cuda_device), 1)[0]) - (-0.18471177)) < 1e-6
+
+
+def test_uniform_normal_vs_oracle(mb, cuda_device, prng_mode):
+    keys = _keys(64, seed=5)
+    n = 257
+    bits = orc.random_bits_keys(keys, n, prng_mode)
+    u = mb.random.uniform(_dev(keys, cuda_device), n, -2.0, 3.0).cpu().numpy()
+    assert np.array_equal(u, ojr.bits_to_uniform(bits, -2.0, 3.0))          # pure bit ops + one fma-free affine
+    z = mb.random.normal(_dev(keys, cuda_device), n).cpu().numpy()
+    np.testing.assert_allclose(z, ojr.bits_to_normal(bits), rtol=2e-6, atol=1e-7)   # log1pf/sqrtf: few ulp
+
+
+# ---------------------------------------------------------------------------------------------
+# stage 1: colored noise and action sampling
+# ---------------------------------------------------------------------------------------------
+def _cfg(mb, horizon, params, action_dim=1):
+    from mbpo_b200.optimizers import iCemTO, iCemParams
+    from mbpo_b200.systems import PendulumSystem
+    opt = iCemTO(horizon=horizon, action_dim=action_dim, opt_params=iCemParams(**params))
+    opt.set_system(PendulumSystem())
+    return opt, opt._cfg()
+
+
+@pytest.mark.parametrize("horizon", [5, 8, 15, 20, 30, 50])
+@pytest.mark.parametrize("exponent", [0.0, 2.0])
+def test_powerlaw_noise(mb, cuda_device, prng_mode, horizon, exponent):
+    L = mb._lib
+    _, cfg = _cfg(mb, horizon, dict(exponent=exponent))
+    keys = _keys(300, seed=horizon)
+    F = horizon // 2 + 1
+    dkeys = _dev(keys, cuda_device)
+    out = torch.empty((300, horizon), dtype=torch.float32, device=cuda_device)
+    bits = torch.empty((300, 2, F), dtype=torch.uint32, device=cuda_device)
+    L.check(L.lib.mbpo_powerlaw_noise(L.C.byref(cfg), L.ptr(dkeys), 300, L.ptr(out), L.ptr(bits),
+                                      L.stream_ptr(cuda_device)))
+    want, br, bi = orc.powerlaw_psd_gaussian_keys(exponent, horizon, keys, prng_mode, return_bits=True)
+    got_bits = bits.cpu().numpy()
+    assert np.array_equal(got_bits[:, 0], br) and np.array_equal(got_bits[:, 1], bi)      # bit-exact words
+    # s_scale / sigma computed by the C host helper match the oracle's float32 tables
+    s_scale, sigma = orc.powerlaw_tables(exponent, horizon)
+    np.testing.assert_allclose(np.array(cfg.s_scale[:F]), s_scale, rtol=2e-7)
+    np.testing.assert_allclose(cfg.sigma, sigma, rtol=3e-7)
+    # direct f32 DFT vs the oracle's double-precision irfft: unit-variance rows, abs error ~1e-6
+    np.testing.assert_allclose(out.cpu().numpy(), want, rtol=RTOL, atol=5e-6)
+
+
+@pytest.mark.parametrize("horizon,action_dim", [(20, 1), (30, 1), (8, 3)])
+def test_sample_actions(mb, cuda_device, prng_mode, horizon, action_dim):
+    L = mb._lib
+    params = dict(num_samples=64, num_elites=10, exponent=1.0)
+    _, cfg = _cfg(mb, horizon, params, action_dim)
+    B, N, Np = 5, 64, cfg.num_prev_elites
+    assert Np == 3
+    rng = np.random.default_rng(1)
+    keys = _keys(B, seed=9)
+    mean = rng.uniform(-0.5, 0.5, (B, horizon, action_dim)).astype(np.float32)
+    std = rng.uniform(0.1, 0.8, (B, horizon, action_dim)).astype(np.float32)
+    acts = torch.empty((B, N + Np, horizon, action_dim), dtype=torch.float32, device=cuda_device)
+    nk = torch.empty((B, 2), dtype=torch.uint32, device=cuda_device)
+    pk = torch.empty((B, N + Np, 2), dtype=torch.uint32, device=cuda_device)
+    dk, dm, ds = _dev(keys, cuda_device), _dev(mean, cuda_device), _dev(std, cuda_device)
+    L.check(L.lib.mbpo_icem_sample_actions(L.C.byref(cfg), L.ptr(dk), L.ptr(dm), L.ptr(ds), B, L.ptr(acts), L.ptr(nk),
+                                           L.ptr(pk), L.stream_ptr(cuda_device)))
+    p = orc.ICemParams(**params)
+    for b in range(B):
+        want_key, want_acts, want_pk = orc.icem_sample_actions(keys[b], mean[b], std[b], p, horizon, action_dim,
+                                                               prng_mode)
+        assert np.array_equal(nk[b].cpu().numpy(), want_key)
+        assert np.array_equal(pk[b].cpu().numpy(), want_pk)
+        np.testing.assert_allclose(acts[b].cpu().numpy(), want_acts, rtol=RTOL, atol=5e-6)
+        assert np.all(acts[b, N:].cpu().numpy() == 0.0)          # closure prev_elites quirk: zero rows
+
+
+# ---------------------------------------------------------------------------------------------
+# stage 2: System.step and rollouts
+# ---------------------------------------------------------------------------------------------
+def _random_states(n, seed):
+    rng = np.random.default_rng(seed)
+    th = rng.uniform(-np.pi, np.pi, n)
+    w = rng.uniform(-8, 8, n)
+    return np.stack([np.cos(th), np.sin(th), w], axis=-1).astype(np.float32)
+
+
+def test_system_step(mb, cuda_device, math_mode):
+    from mbpo_b200.systems import PendulumSystem
+    sys_ = PendulumSystem()
+    st = sys_.reset(mb.random.split(mb.random.PRNGKey(0, cuda_device), 20))      # tests/test_sys_pendulum.py
+    assert st.x_next.shape == (20, 3)
+    x = _random_states(4096, 0)
+    u = np.random.default_rng(1).uniform(-1.5, 1.5, (4096, 1)).astype(np.float32)   # beyond the torque clip too
+    out = sys_.step(_dev(x, cuda_device), _dev(u, cuda_device), st.system_params)
+    assert out.x_next.shape == (4096, 3) and out.reward.shape == (4096,)
+    assert out.system_params.key is None                                           # key dropped (:38)
+    xn, r = orc.pendulum_step(x, u[:, 0])
+    np.testing.assert_allclose(out.x_next.cpu().numpy(), xn, rtol=RTOL, atol=2e-6)
+    np.testing.assert_allclose(out.reward.cpu().numpy(), r, rtol=RTOL, atol=2e-6)
+
+
+@pytest.mark.parametrize("horizon", [1, 7, 20, 30, 50])
+def test_rollout_actions_vs_oracle(mb, cuda_device, math_mode, horizon):
+    from mbpo_b200.systems import PendulumSystem
+    from mbpo_b200.utils import rollout_actions, rollout_returns
+    sys_ = PendulumSystem()
+    sp = sys_.reset(device=cuda_device).system_params
+    B, M = 7, 45                                       # ragged: 315 rows, not a multiple of 32
+    x0 = _random_states(B, 3)
+    acts = np.clip(np.random.default_rng(4).normal(0, 0.5, (B, M, horizon, 1)), -1, 1).astype(np.float32)
+    tr = rollout_actions(sys_, sp, _dev(x0, cuda_device), _dev(acts, cuda_device), horizon)
+    ret = rollout_returns(sys_, sp, _dev(x0, cuda_device), _dev(acts, cuda_device)).cpu().numpy()
+    want_ret, obs, rew, nxt = orc.rollout_actions(np.repeat(x0, M, axis=0), acts.reshape(B * M, horizon), full=True)
+    # teacher-forced per-step parity: step the oracle from the GPU's own observations
+    g_obs = tr.observation.cpu().numpy().reshape(-1, 3)
+    g_nxt = tr.next_observation.cpu().numpy().reshape(-1, 3)
+    g_rew = tr.reward.cpu().numpy().reshape(-1)
+    xn, r = orc.pendulum_step(g_obs, acts.reshape(-1))
+    np.testing.assert_allclose(g_nxt, xn, rtol=RTOL, atol=3e-6)
+    np.testing.assert_allclose(g_rew, r, rtol=RTOL, atol=3e-6)
+    # observation[t] is next_observation[t-1], observation[0] is the initial state (optimizer_utils.py:47-50)
+    o = tr.observation.cpu().numpy()
+    assert np.array_equal(o[:, :, 1:], tr.next_observation.cpu().numpy()[:, :, :-1])
+    assert np.array_equal(o[:, :, 0], np.broadcast_to(x0[:, None], (B, M, 3)))
+    assert bool((tr.discount == 1).all())
+    # returns: mean reward; open-loop, so the tolerance grows with the horizon (chaotic amplification)
+    np.testing.assert_allclose(ret.reshape(-1), g_rew.reshape(B * M, horizon).astype(np.float64).mean(1), rtol=2e-6)
+    tol = 1e-5 if horizon <= 30 else 1e-4
+    bad = np.abs(ret.reshape(-1) - want_ret) > tol * np.abs(want_ret) + 1e-6
+    assert bad.mean() <= 0.01, "more than 1%% of open-loop returns off by > %g" % tol
+    # single-sequence form
+    tr1 = rollout_actions(sys_, sp, _dev(x0[0], cuda_device), _dev(acts[0, 0], cuda_device), horizon)
+    assert tr1.observation.shape == (horizon, 3) and tr1.reward.shape == (horizon,)
+    assert np.array_equal(tr1.reward.cpu().numpy(), tr.reward[0, 0].cpu().numpy())
+
+
+# ---------------------------------------------------------------------------------------------
+# stage 3: elite selection + refit (bit-exact given identical inputs)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("alpha", [0.0, 0.1])
+@pytest.mark.parametrize("ties", [False, True])
+def test_elite_refit_bit_exact(mb, cuda_device, alpha, ties):
+    L = mb._lib
+    horizon, N, K = 20, 500, 50
+    params = dict(num_samples=N, num_elites=K, alpha=alpha)
+    _, cfg = _cfg(mb, horizon, params)
+    M = N + cfg.num_prev_elites
+    B = 6
+    rng = np.random.default_rng(7)
+    acts = rng.uniform(-1, 1, (B, M, horizon)).astype(np.float32)
+    acts[:, N:] = 0
+    vals = rng.normal(-5, 2, (B, M)).astype(np.float32)
+    if ties:
+        vals = np.round(vals)                      # many exact ties across the K-th boundary
+        vals[0, :7] = np.nan                       # NaN sorts last (= best) under the total order
+        vals[1, 3] = -0.0
+        vals[1, 4] = 0.0
+    mean = rng.uniform(-0.3, 0.3, (B, horizon)).astype(np.float32)
+    std = rng.uniform(0.2, 0.6, (B, horizon)).astype(np.float32)
+    bval = np.array([-np.inf, -1.0, 100.0, -np.inf, -3.0, 0.0], dtype=np.float32)
+    bseq = rng.uniform(-1, 1, (B, horizon)).astype(np.float32)
+    d = lambda a: _dev(a, cuda_device)
+    o_mean, o_std, o_bseq = (torch.empty((B, horizon), dtype=torch.float32, device=cuda_device) for _ in range(3))
+    o_bval = torch.empty((B,), dtype=torch.float32, device=cuda_device)
+    o_idx = torch.empty((B, K), dtype=torch.int32, device=cuda_device)
+    ta, tv, tm, ts, tb, tq = d(acts), d(vals), d(mean), d(std), d(bval), d(bseq)
+    L.check(L.lib.mbpo_icem_elite_refit(L.C.byref(cfg), L.ptr(ta), L.ptr(tv), L.ptr(tm), L.ptr(ts), L.ptr(tb),
+                                        L.ptr(tq), B, L.ptr(o_mean), L.ptr(o_std), L.ptr(o_bval), L.ptr(o_bseq),
+                                        L.ptr(o_idx), L.stream_ptr(cuda_device)))
+    p = orc.ICemParams(**params)
+    for b in range(B):
+        m, s, bv, bs, idx = orc.icem_refit(acts[b][..., None], vals[b], mean[b][:, None], std[b][:, None], bval[b],
+                                           bseq[b][:, None], p)
+        assert np.array_equal(o_idx[b].cpu().numpy(), idx), "elite indices differ (problem %d)" % b
+        assert np.array_equal(o_mean[b].cpu().numpy(), m[:, 0])
+        assert np.array_equal(o_std[b].cpu().numpy(), s[:, 0])
+        got_bv = o_bval[b].cpu().numpy()
+        assert (np.isnan(got_bv) and np.isnan(bv)) or got_bv == bv
+        assert np.array_equal(o_bseq[b].cpu().numpy(), np.asarray(bs)[:, 0])
+
+
+# ---------------------------------------------------------------------------------------------
+# fused plan, teacher-forced against the oracle iteration by iteration
+# ---------------------------------------------------------------------------------------------
+def _check_plan_trace(mb, cuda_device, horizon, params, B, prng_mode, exact_refit=True):
+    from mbpo_b200.systems import PendulumSystem
+    opt, cfg = _cfg(mb, horizon, params)
+    sys_ = PendulumSystem()
+    sp = sys_.reset(device=cuda_device).system_params
+    x0 = _random_states(B, 11)
+    keys = _keys(B, seed=12)
+    seq = np.random.default_rng(13).uniform(-1, 1, (B, horizon, 1)).astype(np.float32)
+    out_seq, out_val, out_key, tr = opt._plan_raw(_dev(x0, cuda_device), _dev(keys, cuda_device),
+                                                  _dev(seq, cuda_device), sp, trace=True)
+    tr = {k: v.cpu().numpy() for k, v in tr.items()}
+    p = orc.ICemParams(**params)
+    N, K = p.num_samples, p.num_elites
+    assert mb._lib.lib.mbpo_icem_plan_is_fused(mb._lib.C.byref(cfg)) == 1
+    for b in range(B):
+        ks = ojr.split(keys[b], 2, prng_mode)
+        assert np.array_equal(out_key[b].cpu().numpy(), ks[1])                    # new opt_state.key (:246-247)
+        carry = ks[0]
+        mean = np.zeros((horizon, 1), np.float32)
+        if p.warm_start:
+            mean[:-1] = seq[b, 1:]
+            mean[-1] = seq[b, -1]
+        std = np.full((horizon, 1), p.init_std, np.float32)
+        bval, bseq = np.float32(-np.inf), mean.copy()
+        for it in range(p.num_steps):
+            carry, acts, _ = orc.icem_sample_actions(carry, mean, std, p, horizon, 1, prng_mode)
+            g_acts = tr["actions"][it, b].reshape(N + p.num_prev_elites, horizon, 1)
+            np.testing.assert_allclose(g_acts, acts, rtol=RTOL, atol=5e-6)        # sampling from the GPU's own mean/std
+            vals = orc.icem_objective(x0[b], g_acts, p, orc.PendulumParams())      # oracle rollout of the GPU's actions
+            g_vals = tr["values"][it, b]
+            tol = 1e-5 if horizon <= 30 else 1e-4
+            bad = np.abs(g_vals - vals) > tol * np.abs(vals) + 1e-6
+            assert bad.mean() <= 0.01
+            # selection + refit are exact functions of (actions, values): feed the GPU's own
+            mean, std, bval, bseq, idx = orc.icem_refit(g_acts, g_vals, mean, std, bval, bseq, p)
+            assert np.array_equal(tr["elite_idx"][it, b], idx)
+            if exact_refit:
+                assert np.array_equal(tr["mean"][it, b], mean[:, 0])
+                assert np.array_equal(tr["std"][it, b], std[:, 0])
+            assert tr["best_value"][it, b] == bval
+            mean, std = tr["mean"][it, b][:, None].copy(), tr["std"][it, b][:, None].copy()
+        assert np.array_equal(out_seq[b].cpu().numpy(), np.asarray(bseq))
+        assert out_val[b].cpu().numpy() == bval
+
+
+@pytest.mark.parametrize("horizon,params", [
+    (20, dict()),                                                            # iCemParams() defaults = config 1
+    (30, dict(num_samples=512, num_particles=1)),                            # config 2
+    (30, dict(num_samples=512, num_particles=1, exponent=2.0, alpha=0.1)),   # spectral + momentum paths
+    (8, dict(num_samples=40, num_elites=7, num_steps=3, warm_start=False)),
+    (15, dict(num_samples=100, num_elites=20, num_steps=2, exponent=1.0)),   # odd horizon
+    (50, dict(num_samples=1024, num_particles=1)),                           # config 4 population
+])
+def test_fused_plan_teacher_forced(mb, cuda_device, prng_mode, horizon, params):
+    _check_plan_trace(mb, cuda_device, horizon, params, B=3, prng_mode=prng_mode)
+
+
+def test_fused_plan_theta_carry(mb, cuda_device):
+    mb.config.math_mode = "theta_carry"
+    try:
+        _check_plan_trace(mb, cuda_device, 30, dict(num_samples=512, num_particles=1), B=3, prng_mode=False)
+    finally:
+        mb.config.math_mode = "reference"
+
+
+def test_plan_end_to_end_vs_oracle(mb, cuda_device):
+    """Free-running (not teacher-forced) comparison: most problems agree end to end; the rest
+    differ only through elite flips at return gaps below tolerance."""
+    from mbpo_b200.optimizers import iCemTO, iCemParams
+    from mbpo_b200.systems import PendulumSystem
+    horizon, B = 20, 8
+    params = dict(num_samples=200, num_elites=20, num_particles=1, num_steps=3)
+    opt = iCemTO(horizon=horizon, action_dim=1, opt_params=iCemParams(**params))
+    opt.set_system(PendulumSystem())
+    keys = _keys(B, seed=21)
+    st = opt.init(_dev(keys, cuda_device))
+    x0 = _random_states(B, 22)
+    action, new = opt.act(_dev(x0, cuda_device), st)
+    assert action.shape == (B, 1) and new.best_sequence.shape == (B, horizon, 1)
+    agree = 0
+    for b in range(B):
+        ost = orc.icem_init(keys[b], horizon)
+        onew = orc.icem_optimize(x0[b], ost, orc.ICemParams(**params), horizon)
+        assert np.array_equal(new.key[b].cpu().numpy(), onew.key)
+        if np.allclose(new.best_sequence[b].cpu().numpy(), onew.best_sequence, rtol=RTOL, atol=5e-6):
+            agree += 1
+            np.testing.assert_allclose(float(new.best_reward[b]), float(onew.best_reward), rtol=1e-5, atol=1e-6)
+    assert agree >= B - 2
+
+
+def test_staged_plan_matches_fused(mb, cuda_device):
+    L = mb._lib
+    from mbpo_b200.systems import PendulumSystem
+    horizon, B = 20, 4
+    params = dict(num_samples=128, num_elites=16, num_particles=10, num_steps=4, alpha=0.1)
+    opt, cfg = _cfg(mb, horizon, params)
+    sp = PendulumSystem().reset(device=cuda_device).system_params
+    x0, keys = _dev(_random_states(B, 31), cuda_device), _dev(_keys(B, 32), cuda_device)
+    seq = torch.zeros((B, horizon, 1), device=cuda_device)
+    f_seq, f_val, f_key, _ = opt._plan_raw(x0, keys, seq, sp)
+    nbytes = L.lib.mbpo_icem_workspace_bytes(L.C.byref(cfg), B)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=cuda_device)
+    s_seq, s_val = torch.empty_like(f_seq), torch.empty_like(f_val)
+    s_key = torch.empty_like(f_key)
+    pp = PendulumSystem().pack_params(sp)
+    L.check(L.lib.mbpo_icem_plan_staged(L.C.byref(cfg), L.C.addressof(pp), L.ptr(x0), L.ptr(keys), L.ptr(seq), B,
+                                        L.ptr(s_seq), L.ptr(s_val), L.ptr(s_key), L.ptr(ws), nbytes,
+                                        L.stream_ptr(cuda_device)))
+    assert torch.equal(f_key, s_key)
+    assert torch.equal(f_seq, s_seq) and torch.equal(f_val, s_val)     # same device math in both paths
+    with pytest.raises(mb.MbpoError):
+        L.check(L.lib.mbpo_icem_plan_staged(L.C.byref(cfg), L.C.addressof(pp), L.ptr(x0), L.ptr(keys), L.ptr(seq), B,
+                                            L.ptr(s_seq), L.ptr(s_val), L.ptr(s_key), L.ptr(ws), 16,
+                                            L.stream_ptr(cuda_device)))
+
+
+# ---------------------------------------------------------------------------------------------
+# config 1: the reference's own test (tests/test_icemopt.py), closed loop, threshold -400
+# ---------------------------------------------------------------------------------------------
+def _icemopt_setup(mb, cuda_device):
+    from mbpo_b200.optimizers import iCemTO, iCemParams
+    from mbpo_b200.systems import PendulumSystem
+    jr = mb.random
+    key = jr.PRNGKey(0, cuda_device)
+    ks = jr.split(key, 3)
+    optimizer_key, init_key, key = ks[0], ks[1], ks[2]
+    system = PendulumSystem()
+    system_state = system.reset(key)
+    cem = iCemTO(horizon=20, action_dim=1, system=None, opt_params=iCemParams(), key=optimizer_key)
+    cem.set_system(system)
+    return system, system_state, cem, cem.init(init_key)
+
+
+def test_icemopt_reference_test_python_loop(mb, cuda_device):
+    system, system_state, cem, st = _icemopt_setup(mb, cuda_device)
+    rewards = []
+    for _ in range(200):
+        action, st = cem.act(obs=system_state.x_next, opt_state=st)
+        system_state = system.step(x=system_state.x_next, u=action, system_params=system_state.system_params)
+        st = st.replace(system_params=system_state.system_params)
+        rewards.append(system_state.reward)
+    total = float(torch.stack(rewards).sum())
+    assert total >= -400, total                                            # tests/test_icemopt.py:37-38
+
+
+def test_icemopt_closed_loop_kernel_matches_python_loop(mb, cuda_device, prng_mode):
+    system, system_state, cem, st = _icemopt_setup(mb, cuda_device)
+    states, rewards, actions, new = cem.closed_loop(system_state.x_next, st, 200)
+    assert states.shape == (200, 3) and rewards.shape == (200,) and actions.shape == (200, 1)
+    assert float(rewards.sum()) >= -400
+    s2, st2 = system_state, st
+    for t in range(25):                                                    # same kernels, same bits
+        a, st2 = cem.act(obs=s2.x_next, opt_state=st2)
+        s2 = system.step(x=s2.x_next, u=a, system_params=s2.system_params)
+        assert torch.equal(a, actions[t]) and torch.equal(s2.x_next, states[t]) and torch.equal(s2.reward, rewards[t])
+
+
+# ---------------------------------------------------------------------------------------------
+# config 3: vmapped env rollouts with Episode / AutoReset bookkeeping
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("E,T,episode_length,action_repeat", [(1000, 57, 20, 1), (77, 40, 7, 2), (4096, 16, 200, 1)])
+def test_env_rollout(mb, cuda_device, math_mode, E, T, episode_length, action_repeat):
+    from mbpo_b200.envs import wrap
+    from mbpo_b200.systems import PendulumSystem
+    sys_ = PendulumSystem()
+    sp = sys_.reset(device=cuda_device).system_params
+    env = wrap(sys_, sp, episode_length=episode_length, action_repeat=action_repeat)
+    x0 = _random_states(E, 41)
+    acts = np.random.default_rng(42).uniform(-1, 1, (T, E, 1)).astype(np.float32)
+    st = env.reset(_dev(x0, cuda_device))
+    new, tr = env.unroll(st, _dev(acts, cuda_device))
+    want = orc.env_rollout(x0, acts[..., 0], episode_length, action_repeat=action_repeat)
+    # bookkeeping is exact
+    for name in ("discount", "truncation"):
+        got = tr.discount if name == "discount" else tr.extras["state_extras"]["truncation"]
+        assert np.array_equal(got.cpu().numpy(), want[name]), name
+    assert np.array_equal(new.info["steps"].cpu().numpy(), want["final_steps"])
+    assert np.array_equal(new.done.cpu().numpy(), want["final_done"])
+    # teacher-forced float parity: step the oracle from the GPU's recorded observations
+    o = tr.observation.cpu().numpy()
+    x, rew = o.reshape(-1, 3), np.zeros(T * E, np.float32)
+    for _ in range(action_repeat):
+        x, r = orc.pendulum_step(x, acts.reshape(-1))
+        rew = rew + r
+    done = (1.0 - want["discount"]).reshape(-1, 1)
+    nxt = np.where(done != 0, np.broadcast_to(x0[None], (T, E, 3)).reshape(-1, 3), x)
+    tol = dict(rtol=RTOL * (4 if action_repeat > 1 else 1), atol=4e-6)
+    np.testing.assert_allclose(tr.next_observation.cpu().numpy().reshape(-1, 3), nxt, **tol)
+    np.testing.assert_allclose(tr.reward.cpu().numpy().reshape(-1), rew, **tol)
+    assert np.array_equal(o[1:], tr.next_observation.cpu().numpy()[:-1])       # obs[t+1] = next_obs[t]
+    assert np.array_equal(o[0], x0)
+    # chunked unroll == one unroll (state carried in EnvState)
+    mid = T // 3
+    s1, t1 = env.unroll(st, _dev(acts[:mid], cuda_device))
+    s2, t2 = env.unroll(s1, _dev(acts[mid:], cuda_device))
+    assert torch.equal(torch.cat([t1.next_observation, t2.next_observation]), tr.next_observation)
+    assert torch.equal(s2.obs, new.obs) and torch.equal(s2.info["steps"], new.info["steps"])
+
+
+# ---------------------------------------------------------------------------------------------
+# stage 4: learned MLP-ensemble dynamics forward
+# ---------------------------------------------------------------------------------------------
+def test_mlp_dynamics_forward(mb, cuda_device):
+    L = mb._lib
+    ens = orc.make_mlp_ensemble(seed=3, members=5)
+    R = 1000
+    rng = np.random.default_rng(50)
+    inp = rng.uniform(-1, 1, (R, 4)).astype(np.float32)
+    member = rng.integers(0, 5, R).astype(np.int32)
+    d = lambda a: _dev(a, cuda_device)
+    w_in, b_in = d(ens.weights[0]), d(ens.biases[0])
+    w_h = torch.stack([d(ens.weights[1]), d(ens.weights[2])], dim=1)              # [E, 2, in, out]
+    w_h = w_h.transpose(-1, -2).contiguous().to(torch.bfloat16)                   # K-major [E, 2, out, in]
+    b_h = torch.stack([d(ens.biases[1]), d(ens.biases[2])], dim=1).contiguous()
+    w_out, b_out = d(ens.weights[3]), d(ens.biases[3])
+    p = L.MlpEnsembleParamsC(5, 256, 3, 1, L.ptr(w_in), L.ptr(b_in), L.ptr(w_h), L.ptr(b_h), L.ptr(w_out),
+                             L.ptr(b_out), L.PendulumParamsC(8, 2, .05, 9.81, 1, 1, .02, 1, 0))
+    out = torch.empty((R, 3), dtype=torch.float32, device=cuda_device)
+    ti, tm = d(inp), d(member)
+    L.check(L.lib.mbpo_mlp_dynamics_forward(L.C.byref(p), L.ptr(ti), L.ptr(tm), R, L.ptr(out),
+                                            L.stream_ptr(cuda_device)))
+    want = orc.mlp_member_forward(ens, member, inp, bf16=True)
+    # identical bf16 operand rounding, fp32 accumulate; swish via __expf: a flipped bf16 rounding of one
+    # activation moves an output by ~1e-4 relative
+    np.testing.assert_allclose(out.cpu().numpy(), want, rtol=2e-3, atol=2e-4)
+    full = orc.mlp_member_forward(ens, member, inp, bf16=False)
+    assert np.abs(out.cpu().numpy() - full).max() < 5e-2                            # bf16 vs fp32 network
+
+
+# ---------------------------------------------------------------------------------------------
+# error behaviour: no fallback, loud failures
+# ---------------------------------------------------------------------------------------------
+def test_errors(mb, cuda_device):
+    from mbpo_b200.optimizers import iCemTO, iCemParams, AbstractCost
+    from mbpo_b200.systems import PendulumSystem, System
+    with pytest.raises(NotImplementedError):
+        iCemTO(horizon=20, action_dim=1, cost_fn=AbstractCost(20))
+    opt = iCemTO(horizon=21, action_dim=1, opt_params=iCemParams(num_particles=1))   # no compiled kernel for H=21
+    opt.set_system(PendulumSystem())
+    st = opt.init(mb.random.PRNGKey(0, cuda_device))
+    with pytest.raises(mb.MbpoUnsupported):
+        opt.act(torch.tensor([-1.0, 0.0, 0.0], device=cuda_device), st)
+    with pytest.raises(mb.MbpoError):                                                # CPU tensors are refused
+        PendulumSystem().step(torch.zeros(3), torch.zeros(1), st.system_params)
+
+    class Other(System):
+        system_kind = 7
+    o = iCemTO(horizon=20, action_dim=1)
+    o.set_system(Other(x_dim=3, u_dim=1))
+    with pytest.raises(mb.MbpoUnsupported):
+        o.optimize(torch.zeros(3, device=cuda_device), st)
+
+
+# ---------------------------------------------------------------------------------------------
+# full-size properties (BASELINE config 2 / 3 sizes): size-independent invariants
+# ---------------------------------------------------------------------------------------------
+def test_full_size_config2_properties(mb, cuda_device):
+    from mbpo_b200.optimizers import iCemTO, iCemParams
+    from mbpo_b200.systems import PendulumSystem
+    B, H = 4096, 30
+    opt = iCemTO(horizon=H, action_dim=1, opt_params=iCemParams(num_samples=512, num_particles=1))
+    sys_ = PendulumSystem()
+    opt.set_system(sys_)
+    keys = mb.random.split(mb.random.PRNGKey(0, cuda_device), B)
+    st = opt.init(keys)
+    x0 = _dev(_random_states(B, 0), cuda_device)
+    a1, n1 = opt.act(x0, st)
+    a2, n2 = opt.act(x0, st)
+    assert torch.equal(a1, a2) and torch.equal(n1.best_sequence, n2.best_sequence)       # deterministic
+    assert bool(((n1.best_sequence >= -1) & (n1.best_sequence <= 1)).all())               # clipped actions
+    # best_reward is the return of best_sequence: re-roll it out through the staged kernel
+    from mbpo_b200.utils import rollout_returns
+    ret = rollout_returns(sys_, st.system_params, x0, n1.best_sequence.reshape(B, 1, H, 1))[:, 0]
+    assert torch.equal(ret, n1.best_reward)
+    # sharding invariance: planning a slice alone gives the same bits as inside the batch
+    sl = slice(1000, 1100)
+    st_sl = st.replace(key=st.key[sl].contiguous(), best_sequence=st.best_sequence[sl].contiguous(),
+                       best_reward=st.best_reward[sl].contiguous())
+    a3, n3 = opt.act(x0[sl].contiguous(), st_sl)
+    assert torch.equal(a3, a1[sl]) and torch.equal(n3.key, n1.key[sl])
+    # planning beats the zero sequence (which is always among the candidates)
+    zero = rollout_returns(sys_, st.system_params, x0, torch.zeros((B, 1, H, 1), device=cuda_device))[:, 0]
+    assert bool((n1.best_reward >= zero).all())
