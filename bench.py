@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- iCEM model-rollout transitions/sec on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU restatement of the reference
+
+A "step" is one batched plan call (iCemTO.optimize over B independent problems): S CEM
+iterations of sample -> rollout -> score -> elite-select -> refit.  Workload (default) is
+BASELINE.json configs[1]: 4,096 initial states, pop=512 (+15 kept rows), horizon=30,
+5 iterations, analytic pendulum, num_particles=1.  With N GPUs every rank plans its own 4,096
+problems (weak scaling; problems are independent, no data-path collective; the first actions
+are all-gathered over NCCL only in the end-to-end leg).
+
+transitions per step = B * S * (N_samples + Np) * P * H = 4096*5*527*1*30 = 323,788,800 per GPU.
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "model-based-policy-optimizers_b200"))
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (B per GPU, horizon, iCemParams overrides)
+    "config2_batched_icem": dict(B=4096, horizon=30, params=dict(num_samples=512, num_particles=1)),
+    "config1_single_state": dict(B=1, horizon=20, params=dict(num_particles=1)),
+    "config2_colored": dict(B=4096, horizon=30, params=dict(num_samples=512, num_particles=1, exponent=2.0, alpha=0.1)),
+    "config4_population": dict(B=1024, horizon=50, params=dict(num_samples=1024, num_particles=1)),
+}
+METRIC = "iCEM model-rollout transitions/sec (pop x horizon x problems x CEM iterations)"
+UNIT = "transitions/s"
+
+# Thread-level instructions the fused plan kernel executes per transition on the default
+# workload, measured with ncu (smsp__thread_inst_executed.sum / transitions; profiles/).  Used
+# for roofline.achieved = executed lane-instructions per second; see DESIGN.md.
+LANE_INSTR_PER_TRANSITION = {"config2_batched_icem": None}
+
+
+def transitions_per_step(B, horizon, p):
+    npe = max(int(p.elite_set_fraction * p.num_elites), 1)
+    return B * p.num_steps * (p.num_samples + npe) * p.num_particles * horizon
+
+
+def random_states(n, seed):
+    rng = np.random.default_rng(seed)
+    th, w = rng.uniform(-np.pi, np.pi, n), rng.uniform(-8, 8, n)
+    return np.stack([np.cos(th), np.sin(th), w], -1).astype(np.float32)
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def host_info():
+    model = ""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return os.cpu_count() or 1, model
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's plain-C twin (OpenMP over problems) on a bounded sample of the workload
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step(wl, steps: int, warmup: int, sample_B: int | None = None):
+    """Times `steps` plan calls of the CPU restatement on a bounded sample; returns dict."""
+    from oracle import c_twin, jax_prng as jr, mbpo_oracle as orc
+    lib = c_twin.load(native=True)
+    p = orc.ICemParams(**wl["params"])
+    cores = lib.orc_max_threads()
+    B = sample_B or max(cores * 32, 64)
+    B = min(B, wl["B"]) if wl["B"] > 1 else 1
+    cfg = c_twin.make_cfg(p, wl["horizon"])
+    p9 = orc.PendulumParams().packed()
+    x0 = random_states(wl["B"], 0)[:B]
+    keys = orc.split_keys(jr.PRNGKey(0).reshape(1, 2), wl["B"])[0][:B]
+    seq = np.zeros((B, wl["horizon"]), np.float32)
+    used = cores
+    for _ in range(max(warmup, 1)):
+        c_twin.optimize_batch(lib, cfg, p9, x0[: max(B // 8, 1)], keys[: max(B // 8, 1)], seq[: max(B // 8, 1)])
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        _, _, _, used = c_twin.optimize_batch(lib, cfg, p9, x0, keys, seq)
+    dt = (time.perf_counter() - t0) / steps
+    tr = transitions_per_step(B, wl["horizon"], p)
+    return dict(value=tr / dt, ms_per_step=dt * 1e3, cores=used, sample_B=B,
+                sample="%d of %d problems per step (same keys/states as the GPU arm), C restatement + OpenMP" % (
+                    B, wl["B"]))
+
+
+def run_reference(args, wl_name, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ncores, model = host_info()
+    r = cpu_reference_step(wl, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(wl_name, wl, args.gpus, l2="n/a (CPU)"),
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                         "sample": r["sample"], "host_cpu": model, "host_logical_cpus": ncores,
+                         "note": "CPU restatement of the reference semantics (oracle/c) -- the reference's JAX "
+                                 "stack is not installable in this image, so this is not XLA"},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(name, wl, gpus, l2):
+    p = dict(num_particles=10, num_samples=500, num_elites=50, num_steps=5, exponent=0.0, alpha=0.0)
+    p.update(wl["params"])
+    return {"workload": name, "problems_per_gpu": wl["B"], "problems_total": wl["B"] * gpus, "horizon": wl["horizon"],
+            "num_samples": p["num_samples"], "num_elites": p["num_elites"], "num_prev_elites": 15,
+            "num_particles": p["num_particles"], "cem_iterations": p["num_steps"], "exponent": p["exponent"],
+            "alpha": p["alpha"], "system": "analytic pendulum", "parallelism": "problems sharded x%d" % gpus,
+            "l2": l2}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, wl_name, wl):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU restatement)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import mbpo_b200
+    from mbpo_b200.optimizers import iCemTO, iCemParams
+    from mbpo_b200.systems import PendulumSystem
+    from mbpo_b200.parallel import all_gather_blocks, shard_bounds
+
+    mbpo_b200.config.math_mode = args.math
+    p = iCemParams(**wl["params"])
+    B, H = wl["B"], wl["horizon"]
+    total_B = B * world
+    opt = iCemTO(horizon=H, action_dim=1, opt_params=p)
+    system = PendulumSystem()
+    opt.set_system(system)
+    lo, hi = shard_bounds(total_B, rank, world)
+    keys_all = mbpo_b200.random.split(mbpo_b200.random.PRNGKey(0, dev), total_B)
+    state = opt.init(keys_all[lo:hi].contiguous())
+    x0_host = torch.from_numpy(random_states(total_B, 0)[lo:hi].copy()).pin_memory()
+    x0 = x0_host.to(dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+    tr_step = transitions_per_step(B, H, p)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing ---------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        opt.optimize(x0, state)
+    barrier()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        for k in range(args.steps):
+            flush.zero_()                     # evict L2 between timed iterations (untimed)
+            starts[k].record()
+            new_state = opt.optimize(x0, state)
+            ends[k].record()
+        barrier()
+    ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = tr_step * world / (ms_per_step * 1e-3)
+    clocks = clk.summary()
+
+    # ---- end to end through the public API with host buffers ------------------------------------
+    act_host = torch.empty((B, 1), dtype=torch.float32).pin_memory()
+    gathered = None
+    for _ in range(3):
+        a, _ = opt.act(x0_host.to(dev, non_blocking=True), state)
+        act_host.copy_(a, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        xd = x0_host.to(dev, non_blocking=True)            # h2d: this step's initial states
+        a, st2 = opt.act(xd, state)
+        if world > 1:
+            gathered = all_gather_blocks(a.contiguous(), total_B)   # NCCL gather of the chosen first actions
+        act_host.copy_(a, non_blocking=True)               # d2h: the step's result
+        torch.cuda.synchronize(dev)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = tr_step * world / e2e_s
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+        issue_peak = 148 * 4 * 32 * sm_max * 1e6 / 1e12          # T lane-instr/s
+        ipt = LANE_INSTR_PER_TRANSITION.get(wl_name)
+        kernel_ms = ms_per_step                                   # one fused kernel per step: event time = launch time
+        roofline = {
+            "bound": "issue", "kernel": "icem_plan_pendulum_kernel",
+            "achieved": (tr_step * ipt / (kernel_ms * 1e-3) / 1e12) if ipt else None,
+            "peak": issue_peak, "unit": "T lane-instr/s",
+            "frac": (tr_step * ipt / (kernel_ms * 1e-3) / 1e12 / issue_peak) if ipt else None,
+            "traffic": None,
+            "lane_instr_per_transition": ipt,
+            "peak_source": "148 SMs x 4 SMSPs x 32 lanes x sm_max_mhz (MEASURED_PEAKS.json)",
+            "note": "the fused plan keeps actions in shared memory: HBM traffic is ~0 B/transition, so the "
+                    "limiting roofline is the SM issue rate, not HBM or the tensor pipe (DESIGN.md)",
+        }
+        cpu = None
+        if not args.no_cpu_baseline:
+            r = cpu_reference_step(wl, steps=1, warmup=1)
+            ncores, model = host_info()
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
+                   "host_cpu": model, "host_logical_cpus": ncores}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(wl_name, wl, world, l2="flushed (256 MiB memset) before every timed step"),
+            "math_mode": args.math,
+            "ms_per_plan_call": ms_per_step,
+            "pop_x_horizon_x_problems_per_s": B * world * p.num_samples * H / (ms_per_step * 1e-3),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
+                    "h2d_bytes_per_step": int(x0_host.numel() * 4), "d2h_bytes_per_step": int(act_host.numel() * 4),
+                    "api": "iCemTO.act(obs[B,3] from pinned host) -> first actions[B,1] to pinned host"
+                           + ("; NCCL all_gather of first actions" if world > 1 else "")},
+            "gpu_launches": args.steps,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="config2_batched_icem")
+    ap.add_argument("--math", choices=["reference", "theta_carry"], default="reference")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, args.workload, wl)
+    else:
+        run_ours(args, args.workload, wl)
+
+
+if __name__ == "__main__":
+    main()

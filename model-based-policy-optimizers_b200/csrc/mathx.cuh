@@ -9,7 +9,7 @@ namespace mbpo {
 // uniform in [lo, hi): mantissa trick, then max(lo, f*(hi-lo)+lo)
 __device__ __forceinline__ float bits_to_uniform(uint32_t bits, float lo, float hi) {
   const float f = __uint_as_float((bits >> 9) | 0x3F800000u) - 1.0f;
-  return fmaxf(lo, f * (hi - lo) + lo);
+  return fmaxf(lo, __fadd_rn(__fmul_rn(f, hi - lo), lo));  // unfused, as the oracle
 }
 
 // XLA ErfInv32: w = -log1p(-x*x); w < 5 ? poly(w-2.5) : poly(sqrt(w)-3); result p*x.

@@ -20,3 +20,16 @@ def cuda_device():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda", 0)
+
+
+@pytest.fixture(scope="session")
+def c_oracle():
+    """The oracle's plain-C twin (oracle/c), built on demand with the committed Makefile."""
+    import ctypes
+    import subprocess
+    cdir = os.path.join(ROOT, "oracle", "c")
+    lib = os.path.join(cdir, "libmbpo_oracle.so")
+    src = os.path.join(cdir, "mbpo_oracle.c")
+    if not os.path.exists(lib) or os.path.getmtime(lib) < os.path.getmtime(src):
+        subprocess.run(["make", "-s", "-C", cdir], check=True)
+    return ctypes.CDLL(lib)

@@ -501,9 +501,11 @@ def test_errors(mb, cuda_device):
     class Other(System):
         system_kind = 7
     o = iCemTO(horizon=20, action_dim=1)
+    o.set_system(PendulumSystem())
+    st20 = o.init(mb.random.PRNGKey(0, cuda_device))
     o.set_system(Other(x_dim=3, u_dim=1))
-    with pytest.raises(mb.MbpoUnsupported):
-        o.optimize(torch.zeros(3, device=cuda_device), st)
+    with pytest.raises(mb.MbpoUnsupported):                                         # a System without a CUDA step
+        o.optimize(torch.zeros(3, device=cuda_device), st20)
 
 
 # ---------------------------------------------------------------------------------------------
