@@ -100,9 +100,9 @@ __global__ void __launch_bounds__(128) env_rollout_pendulum_kernel(const __grid_
         if (MATH == MBPO_MATH_REFERENCE) {
           pendulum_step_ref(pc, c, s, w, u_cur[k], rr);
         } else {
-          float th = atan2f(s, c);
+          float th = atan2_bounded(s, c);
           pendulum_step_theta(pc, th, w, u_cur[k], rr);
-          sincosf(th, &s, &c);
+          sincos_bounded(th, s, c);
         }
         rew = __fadd_rn(rew, rr);
       }

@@ -29,7 +29,7 @@ __device__ __forceinline__ float rollout_return(const PendulumConsts& pc, float 
       acc = __fadd_rn(acc, r);
     }
   } else {
-    float th = atan2f(s0, c0), w = w0;
+    float th = atan2_bounded(s0, c0), w = w0;
 #pragma unroll 2
     for (int t = 0; t < H; ++t) {
       float r;
@@ -76,7 +76,8 @@ struct PlanSmem {
                    + (N + Np)                   // sort keys
                    + 2 * (N + 1)                // legacy split words
                    + 3 * H                      // mean, std, best_seq
-                   + 2 * K                      // elite_idx, scratch
+                   + 2 * K                      // elite_idx, sel_idx
+                   + select_scratch_words(K)    // selection counters + selected keys
                    + 8;                         // best_value, carry key, state key, pad
     return words * 4;
   }
@@ -92,7 +93,8 @@ struct PlanCtaSmem {
   float* std_;         // [H]
   float* best_seq;     // [H]
   int* elite_idx;      // [K]
-  int* scratch;        // [K]
+  int* sel_idx;        // [K]
+  uint32_t* sel_scratch;  // [select_scratch_words(K)]
   float* best_value;   // [1]
   uint32_t* carry;     // [2] carry.key
   uint32_t* state_key; // [2] opt_state.key (closed loop)
@@ -105,8 +107,9 @@ struct PlanCtaSmem {
     std_ = mean + H;
     best_seq = std_ + H;
     elite_idx = reinterpret_cast<int*>(best_seq + H);
-    scratch = elite_idx + K;
-    best_value = reinterpret_cast<float*>(scratch + K);
+    sel_idx = elite_idx + K;
+    sel_scratch = reinterpret_cast<uint32_t*>(sel_idx + K);
+    best_value = reinterpret_cast<float*>(sel_scratch + select_scratch_words(K));
     carry = reinterpret_cast<uint32_t*>(best_value + 1);
     state_key = carry + 2;
   }
@@ -115,8 +118,8 @@ struct PlanCtaSmem {
 // iCemTO.optimize for ONE problem, executed by the whole CTA (icem_optimizer.py:134-252).
 // Thread n owns samples n, n+THREADS, ...: it derives the sample's key, generates the
 // colored-noise row straight into its shared-memory action row, rolls the row out with the
-// state in registers and publishes the total-order key of the objective.  Warp 0 then selects
-// and refits.  `prev_best` ([H], global or this CTA's own sm.best_seq) is the previous plan's
+// state in registers and publishes the total-order key of the objective.  The CTA then selects
+// and refits together (select.cuh).  `prev_best` ([H], global or this CTA's own sm.best_seq) is the previous plan's
 // best sequence for the warm start; `key_in` is opt_state.key; the new opt_state.key is
 // returned through key_new (valid in thread 0 only).  `slot` indexes the optional trace
 // dumps ([S, B, ...] with problem slot `slot` of `slots`).
@@ -181,7 +184,7 @@ __device__ __forceinline__ void plan_problem(const PlanArgs& a, const PlanCtaSme
       else skey_n = split_at<1>(sampling_rng, static_cast<uint32_t>(N + 1), static_cast<uint32_t>(n + 1));
       const Key2 dim_key = split_at<PRNG>(skey_n, 1u, 0u);   // vmap(split(x, action_dim)), A == 1  (:180)
       float* row = act + static_cast<size_t>(n) * HS;
-      colored_noise_row<H, PRNG>(dim_key, a.scale, nullptr, [&](int t, float y) {
+      colored_noise_row<H, PRNG>(dim_key, a.scale, row, nullptr, [&](int t, float y) {
         const float v = __fadd_rn(mean[t], __fmul_rn(y, std_[t]));           // :190
         row[t] = fminf(fmaxf(v, a.u_min), a.u_max);                          // :191
       });
@@ -216,19 +219,17 @@ __device__ __forceinline__ void plan_problem(const PlanArgs& a, const PlanCtaSme
     }
     __syncthreads();
 
-    // ---- select + refit + best tracking (:199-226), warp 0 ---------------------------------
-    if (tid < 32) {
-      warp_select_refit(rs, skey, sm.elite_idx, sm.scratch,
-                        [&](int i, int d) { return i < N ? act[static_cast<size_t>(i) * HS + d] : 0.0f; }, mean,
-                        std_, best_seq, sm.best_value);
-      if (a.trace.elite_idx)
-        for (int e = tid; e < K; e += 32) a.trace.elite_idx[tslot * K + e] = sm.elite_idx[e];
-      for (int d = tid; d < H; d += 32) {
-        if (a.trace.mean) a.trace.mean[tslot * H + d] = mean[d];
-        if (a.trace.std) a.trace.std[tslot * H + d] = std_[d];
-      }
-      if (a.trace.best_value && tid == 0) a.trace.best_value[tslot] = *sm.best_value;
+    // ---- select + refit + best tracking (:199-226), whole CTA --------------------------------
+    cta_select_refit<THREADS>(rs, skey, sm.elite_idx, sm.sel_idx, sm.sel_scratch,
+                              [&](int i, int d) { return i < N ? act[static_cast<size_t>(i) * HS + d] : 0.0f; },
+                              mean, std_, best_seq, sm.best_value);
+    if (a.trace.elite_idx)
+      for (int e = tid; e < K; e += THREADS) a.trace.elite_idx[tslot * K + e] = sm.elite_idx[e];
+    for (int d = tid; d < H; d += THREADS) {
+      if (a.trace.mean) a.trace.mean[tslot * H + d] = mean[d];
+      if (a.trace.std) a.trace.std[tslot * H + d] = std_[d];
     }
+    if (a.trace.best_value && tid == 0) a.trace.best_value[tslot] = *sm.best_value;
     __syncthreads();
   }
 }
@@ -296,9 +297,9 @@ __global__ void __launch_bounds__(THREADS, MINB)
         if (MATH == MBPO_MATH_REFERENCE) {
           pendulum_step_ref(pc, c, s, w, u, r);
         } else {
-          float th = atan2f(s, c);
+          float th = atan2_bounded(s, c);
           pendulum_step_theta(pc, th, w, u, r);
-          sincosf(th, &s, &c);
+          sincos_bounded(th, s, c);
         }
         xs[0] = c; xs[1] = s; xs[2] = w;
         const size_t o = static_cast<size_t>(t) * a.B + b;
@@ -328,25 +329,30 @@ struct ScaleTable {
   float v[MBPO_MAX_FREQ];
 };
 
+constexpr int STAGED_THREADS = 128;  // block size of the staged sampling kernels
+
 // vmap(powerlaw_psd_gaussian): one thread per key.
 template <int H, int PRNG>
-__global__ void powerlaw_noise_kernel(const __grid_constant__ ScaleTable tbl, const uint32_t* __restrict__ keys, int M,
+__global__ void __launch_bounds__(STAGED_THREADS) powerlaw_noise_kernel(const __grid_constant__ ScaleTable tbl, const uint32_t* __restrict__ keys, int M,
                                       float* __restrict__ out, uint32_t* __restrict__ bits_out) {
+  __shared__ float stage[STAGED_THREADS][H | 1];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M) return;
   Key2 k{keys[2 * i], keys[2 * i + 1]};
   float* row = out + static_cast<size_t>(i) * H;
-  colored_noise_row<H, PRNG>(k, tbl.v, bits_out ? bits_out + static_cast<size_t>(i) * 2 * NoiseShape<H>::F : nullptr,
+  colored_noise_row<H, PRNG>(k, tbl.v, stage[threadIdx.x],
+                             bits_out ? bits_out + static_cast<size_t>(i) * 2 * NoiseShape<H>::F : nullptr,
                              [&](int t, float y) { row[t] = y; });
 }
 
 // One iCEM iteration of key plumbing + sampling for B problems (icem_optimizer.py:174-192).
 // grid = (ceil((N+Np)*A / blockDim), B); thread = (candidate n, action dim a).
 template <int H, int PRNG>
-__global__ void sample_actions_kernel(const __grid_constant__ ScaleTable tbl, const uint32_t* __restrict__ carry_key,
+__global__ void __launch_bounds__(STAGED_THREADS) sample_actions_kernel(const __grid_constant__ ScaleTable tbl, const uint32_t* __restrict__ carry_key,
                                       const float* __restrict__ mean, const float* __restrict__ std_, int N, int Np,
                                       int A, float u_min, float u_max, float* __restrict__ actions,
                                       uint32_t* __restrict__ next_key, uint32_t* __restrict__ particle_keys) {
+  __shared__ float stage[STAGED_THREADS][H | 1];
   const int b = blockIdx.y;
   const int M = N + Np;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -373,7 +379,7 @@ __global__ void sample_actions_kernel(const __grid_constant__ ScaleTable tbl, co
   const Key2 dk = split_at<PRNG>(sk, static_cast<uint32_t>(A), static_cast<uint32_t>(ad));                // :180
   const float* mrow = mean + static_cast<size_t>(b) * H * A + ad;
   const float* srow = std_ + static_cast<size_t>(b) * H * A + ad;
-  colored_noise_row<H, PRNG>(dk, tbl.v, nullptr, [&](int t, float y) {
+  colored_noise_row<H, PRNG>(dk, tbl.v, stage[threadIdx.x], nullptr, [&](int t, float y) {
     const float v = __fadd_rn(mrow[static_cast<size_t>(t) * A], __fmul_rn(y, srow[static_cast<size_t>(t) * A]));
     row[static_cast<size_t>(t) * A] = fminf(fmaxf(v, u_min), u_max);
   });

@@ -13,8 +13,14 @@ __device__ __forceinline__ float bits_to_uniform(uint32_t bits, float lo, float 
 }
 
 // XLA ErfInv32: w = -log1p(-x*x); w < 5 ? poly(w-2.5) : poly(sqrt(w)-3); result p*x.
+// Like the reference formula, x*x is rounded to float32 first (this rounding dominates the
+// tail: for |x| -> 1 it is a several-percent perturbation of 1 - x*x, so a "more accurate"
+// (1-x)(1+x) would NOT match JAX).  log1p(-t) is then evaluated as log(1 - t) with the hardware
+// log2 (MUFU.LG2): 1 - t is exact for t >= 0.5 (Sterbenz) and otherwise perturbs w by <= 6e-8
+// absolute, i.e. the result by <= ~2e-8 relative (|p'(w)| <= 0.25) -- below the 1-2 ulp spread
+// between log1p implementations (XLA's own is a polynomial), ~20 instructions cheaper.
 __device__ __forceinline__ float erf_inv_f32(float x) {
-  float w = -log1pf(-(x * x));
+  float w = -__logf(1.0f - __fmul_rn(x, x));
   float p;
   if (w < 5.0f) {
     w = w - 2.5f;
@@ -59,6 +65,62 @@ __device__ __forceinline__ uint32_t total_order_key(float v) {
   if (v == 0.0f) b = 0u;
   if (v != v) b = 0x7FC00000u;
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+// ---- bounded-range trigonometry for the pendulum (|angle| <= ~4 rad) ------------------------
+// Branch-free float32 sin/cos/atan2 with 1-2 ulp accuracy (the same accuracy class as libm /
+// XLA's own polynomial implementations; the parity bar is rel 1e-5).  No large-argument
+// slow path: the callers' angles are bounded by pi + max_speed*dt.
+
+// sin and cos of x, |x| < 2^20.  Cody-Waite reduction by pi/2 in three terms, Cephes minimax
+// polynomials on [-pi/4, pi/4].
+__device__ __forceinline__ void sincos_bounded(float x, float& s, float& c) {
+  const float m = fmaf(x, 0.636619747f, 12582912.0f);  // round(x * 2/pi) in the low mantissa bits
+  const int q = __float_as_int(m);
+  const float fq = m - 12582912.0f;
+  float r = fmaf(fq, -1.57079601e+00f, x);
+  r = fmaf(fq, -3.13916473e-07f, r);
+  r = fmaf(fq, -5.39030253e-15f, r);
+  const float r2 = r * r;
+  float sp = fmaf(-1.9515295891e-4f, r2, 8.3321608736e-3f);
+  sp = fmaf(sp, r2, -1.6666654611e-1f);
+  const float sr = fmaf(sp * r2, r, r);
+  float cp = fmaf(2.443315711809948e-5f, r2, -1.388731625493765e-3f);
+  cp = fmaf(cp, r2, 4.166664568298827e-2f);
+  const float cr = fmaf(cp * r2, r2, fmaf(-0.5f, r2, 1.0f));
+  const bool odd = q & 1;
+  const float s0 = odd ? cr : sr;
+  const float c0 = odd ? sr : cr;
+  s = __int_as_float(__float_as_int(s0) ^ ((q & 2) << 30));
+  c = __int_as_float(__float_as_int(c0) ^ (((q + 1) & 2) << 30));
+}
+
+__device__ __forceinline__ float sin_bounded(float x) {
+  float s, c;
+  sincos_bounded(x, s, c);
+  return s;
+}
+
+// atan2(y, x) for finite inputs: atan(min/max) by a degree-17 odd minimax polynomial
+// (max abs error 7e-8 on [0, 1]) and quadrant fix-ups; atan2(+-0, +-0) = +-0 like NumPy/XLA
+// for (0, +0).
+__device__ __forceinline__ float atan2_bounded(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  const float t = (mx > 0.0f) ? __fdividef(mn, mx) : 0.0f;
+  const float u = t * t;
+  float q = 2.974586547e-03f;
+  q = fmaf(q, u, -1.658116880e-02f);
+  q = fmaf(q, u, 4.355351503e-02f);
+  q = fmaf(q, u, -7.580576113e-02f);
+  q = fmaf(q, u, 1.067893936e-01f);
+  q = fmaf(q, u, -1.421420891e-01f);
+  q = fmaf(q, u, 1.999413718e-01f);
+  q = fmaf(q, u, -3.333316696e-01f);
+  float r = fmaf(t * u, q, t);
+  if (ay > ax) r = 1.57079637f - r;
+  if (x < 0.0f) r = 3.14159274f - r;
+  return copysignf(r, y);
 }
 
 }  // namespace mbpo

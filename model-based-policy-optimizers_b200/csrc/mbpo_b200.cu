@@ -132,7 +132,8 @@ int plan_fusable(const MbpoIcemCfg* c, bool set_error) {
   else {
     const int HS = c->horizon | 1;
     const size_t words = static_cast<size_t>(c->num_samples) * HS + (c->num_samples + c->num_prev_elites) +
-                         2 * (c->num_samples + 1) + 3 * c->horizon + 2 * c->num_elites + 8;
+                         2 * (c->num_samples + 1) + 3 * c->horizon + 2 * c->num_elites +
+                         select_scratch_words(c->num_elites) + 8;
     if (words * 4 > 227 * 1024) why = "fused plan: population does not fit 227 KB of shared memory";
   }
   if (why && set_error) fail(MBPO_EUNSUPPORTED, "%s", why);
@@ -382,12 +383,12 @@ int mbpo_icem_elite_refit(const MbpoIcemCfg* cfg, const float* actions, const fl
   rs.D = cfg->horizon * cfg->action_dim;
   rs.alpha = cfg->alpha;
   rs.one_minus_alpha = static_cast<float>(1.0 - static_cast<double>(cfg->alpha));
-  const size_t smem = (static_cast<size_t>(rs.M) + 2 * rs.K + 3 * rs.D + 4) * 4;
+  const size_t smem = (static_cast<size_t>(rs.M) + 2 * rs.K + select_scratch_words(rs.K) + 3 * rs.D + 4) * 4;
   if (smem > 227 * 1024) return fail(MBPO_EUNSUPPORTED, "elite_refit: population too large for shared memory");
   const cudaError_t e =
       cudaFuncSetAttribute(elite_refit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return fail(MBPO_ECUDA, "elite_refit smem attr: %s", cudaGetErrorString(e));
-  elite_refit_kernel<<<B, 32, smem, as_stream(stream)>>>(rs, actions, values, mean_in, std_in, best_value_in,
+  elite_refit_kernel<<<B, REFIT_THREADS, smem, as_stream(stream)>>>(rs, actions, values, mean_in, std_in, best_value_in,
                                                           best_seq_in, mean_out, std_out, best_value_out, best_seq_out,
                                                           elite_idx_out);
   return check_launch("elite_refit_kernel");

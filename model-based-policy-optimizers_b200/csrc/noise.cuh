@@ -1,5 +1,5 @@
 // Colored (power-law) Gaussian noise row: powerlaw_psd_gaussian(exponent, H, rng)
-// (mbpo/utils/general_utils.py:81-208), one row per thread, everything in registers.
+// (mbpo/utils/general_utils.py:81-208), one row per thread.
 //
 //   key_sr, key_si, _ = split(rng, 3)                         :189
 //   sr = normal(key_sr, (F,)) * s_scale ; si likewise         :190-191
@@ -55,51 +55,66 @@ struct NoiseShape {
   static constexpr bool EVEN = (H % 2) == 0;
 };
 
-// F normals scaled by scale[f] (scale already holds s_scale[f] / sigma * sqrt(2)-fixes).
-// bits_out (optional, global) receives the F raw words.
-template <int H, int MODE>
-__device__ __forceinline__ void scaled_normals(Key2 key, const float* __restrict__ scale, float (&v)[NoiseShape<H>::F],
-                                               uint32_t* bits_out) {
+// Stages the scaled normals of one spectrum half (real or imaginary part) into `stage`:
+//   stage[k]         = sr[k]            k in [0, F)
+//   stage[F + k - 1] = si[k]            k in [1, LASTK)   (DC and, for even H, Nyquist have no
+//                                                           imaginary part: general_utils.py:195-201)
+// so the H needed values fill exactly the H floats of the caller's row.  The threefry blocks run
+// in a rolled loop (small code: the instruction cache matters more than the last bit of ILP);
+// `scale` is indexed dynamically (constant bank / shared memory).
+template <int H, int MODE, bool IMAG>
+__device__ __forceinline__ void stage_normals(Key2 key, const float* __restrict__ scale, float* stage,
+                                              uint32_t* bits_out) {
   using S = NoiseShape<H>;
+  constexpr int LASTK = S::EVEN ? S::F - 1 : S::F;
+  auto put = [&](int k, uint32_t word) {
+    if (bits_out) bits_out[k] = word;
+    if (!IMAG) {
+      stage[k] = bits_to_normal(word) * scale[k];
+    } else if (k >= 1 && k < LASTK) {
+      stage[S::F + k - 1] = bits_to_normal(word) * scale[k];
+    }
+  };
   if (MODE == 1) {
-#pragma unroll
+#pragma unroll 2
     for (int f = 0; f < S::F; ++f) {
       uint32_t x0 = 0u, x1 = static_cast<uint32_t>(f);
       threefry2x32(key.k0, key.k1, x0, x1);
-      const uint32_t b = x0 ^ x1;
-      if (bits_out) bits_out[f] = b;
-      v[f] = bits_to_normal(b) * scale[f];
+      put(f, x0 ^ x1);
     }
   } else {
-#pragma unroll
+#pragma unroll 2
     for (int j = 0; j < S::HALF; ++j) {
       uint32_t x0 = static_cast<uint32_t>(j);
       uint32_t x1 = (S::HALF + j < S::F) ? static_cast<uint32_t>(S::HALF + j) : 0u;
       threefry2x32(key.k0, key.k1, x0, x1);
-      if (bits_out) bits_out[j] = x0;
-      v[j] = bits_to_normal(x0) * scale[j];
-      if (S::HALF + j < S::F) {
-        if (bits_out) bits_out[S::HALF + j] = x1;
-        v[S::HALF + j] = bits_to_normal(x1) * scale[S::HALF + j];
-      }
+      put(j, x0);
+      if (S::HALF + j < S::F) put(S::HALF + j, x1);
     }
   }
 }
 
-// Emits y[t] for every t in [0, H) through emit(t, value).  `scale` may live in shared or
-// constant memory (F floats).
+// Emits y[t] for every t in [0, H) through emit(t, value).  `stage` is H floats private to the
+// calling thread (its own shared-memory action row: emit may overwrite it, every staged value is
+// in a register by then).  `scale` may live in shared or constant memory (F floats).
 template <int H, int MODE, typename Emit>
-__device__ __forceinline__ void colored_noise_row(Key2 rng, const float* __restrict__ scale, uint32_t* bits_out,
-                                                  Emit emit) {
+__device__ __forceinline__ void colored_noise_row(Key2 rng, const float* __restrict__ scale, float* stage,
+                                                  uint32_t* bits_out, Emit emit) {
   using S = NoiseShape<H>;
   constexpr detail::Twiddle<H> tw{};
+  constexpr int LASTK = S::EVEN ? S::F - 1 : S::F;  // bins [1, LASTK) have weight 2
   Key2 key_sr, key_si;
   split3_first2<MODE>(rng, key_sr, key_si);
-  float sr[S::F], si[S::F];
-  scaled_normals<H, MODE>(key_sr, scale, sr, bits_out);
-  scaled_normals<H, MODE>(key_si, scale, si, bits_out ? bits_out + S::F : nullptr);
+  stage_normals<H, MODE, false>(key_sr, scale, stage, bits_out);
+  stage_normals<H, MODE, true>(key_si, scale, stage, bits_out ? bits_out + S::F : nullptr);
 
-  constexpr int LASTK = S::EVEN ? S::F - 1 : S::F;  // bins [1, LASTK) have weight 2
+  float sr[S::F], si[S::F];
+#pragma unroll
+  for (int k = 0; k < S::F; ++k) sr[k] = stage[k];
+  si[0] = 0.0f;
+#pragma unroll
+  for (int k = 1; k < S::F; ++k) si[k] = (k < LASTK) ? stage[S::F + k - 1] : 0.0f;
+
   // t = 0
   {
     float a = sr[0] * tw.c[0];

@@ -5,6 +5,7 @@
 //         mbpo/systems/rewards/pendulum_reward.py:27-42 (reward on the CURRENT state).
 #pragma once
 #include "../../include/mbpo_b200.h"
+#include "mathx.cuh"
 
 namespace mbpo {
 
@@ -57,13 +58,13 @@ __device__ __forceinline__ float reward_from(const PendulumConsts& p, float th, 
 // One reference-literal step on the [cos, sin, thdot] state.
 __device__ __forceinline__ void pendulum_step_ref(const PendulumConsts& p, float& c, float& s, float& w,
                                                   float u, float& reward) {
-  const float th = atan2f(s, c);                                    // dynamics :35 / reward :32
+  const float th = atan2_bounded(s, c);                             // dynamics :35 / reward :32
   reward = reward_from(p, th, w, u);                                // reward uses x, raw u
   const float uu = fminf(fmaxf(u, -1.0f), 1.0f) * p.max_torque;     // :59
-  const float thdd = p.c_g * sinf(th) + p.c_u * uu;                 // :60
+  const float thdd = p.c_g * sin_bounded(th) + p.c_u * uu;          // :60
   const float nw = fminf(fmaxf(w + thdd * p.dt, -p.max_speed), p.max_speed);   // :61-62 (=:41-42)
   const float nth = th + nw * p.dt;                                 // :40
-  sincosf(nth, &s, &c);                                             // :43
+  sincos_bounded(nth, s, c);                                        // :43
   w = nw;
 }
 
@@ -73,7 +74,7 @@ __device__ __forceinline__ void pendulum_step_theta(const PendulumConsts& p, flo
                                                     float& reward) {
   reward = reward_from(p, th, w, u);
   const float uu = fminf(fmaxf(u, -1.0f), 1.0f) * p.max_torque;
-  const float thdd = p.c_g * sinf(th) + p.c_u * uu;
+  const float thdd = p.c_g * sin_bounded(th) + p.c_u * uu;
   const float nw = fminf(fmaxf(w + thdd * p.dt, -p.max_speed), p.max_speed);
   float nth = th + nw * p.dt;
   if (nth > MBPO_PI_F) nth -= MBPO_TWO_PI_F;

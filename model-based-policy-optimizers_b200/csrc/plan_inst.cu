@@ -59,7 +59,7 @@ int plan_entry<MBPO_INST_H>(int prng_mode, int math_mode, const PlanArgs& a, con
 template <>
 int noise_entry<MBPO_INST_H>(int prng_mode, const ScaleTable& tbl, const uint32_t* keys, int M, float* noise_out,
                              uint32_t* bits_out, cudaStream_t st) {
-  const int threads = 128;
+  const int threads = STAGED_THREADS;
   const unsigned blocks = static_cast<unsigned>((M + threads - 1) / threads);
   if (prng_mode == 0) powerlaw_noise_kernel<kH, 0><<<blocks, threads, 0, st>>>(tbl, keys, M, noise_out, bits_out);
   else powerlaw_noise_kernel<kH, 1><<<blocks, threads, 0, st>>>(tbl, keys, M, noise_out, bits_out);
@@ -70,7 +70,7 @@ template <>
 int sample_entry<MBPO_INST_H>(int prng_mode, const ScaleTable& tbl, const uint32_t* carry_key, const float* mean,
                               const float* std_, int N, int Np, int A, float u_min, float u_max, int B,
                               float* actions, uint32_t* next_key, uint32_t* particle_keys, cudaStream_t st) {
-  const int threads = 128;
+  const int threads = STAGED_THREADS;
   const dim3 grid(static_cast<unsigned>(((N + Np) * A + threads - 1) / threads), static_cast<unsigned>(B));
   if (prng_mode == 0)
     sample_actions_kernel<kH, 0><<<grid, threads, 0, st>>>(tbl, carry_key, mean, std_, N, Np, A, u_min, u_max,

@@ -20,9 +20,9 @@ __global__ void system_step_pendulum_kernel(const MbpoPendulumParams sys, const 
   if (MATH == MBPO_MATH_REFERENCE) {
     pendulum_step_ref(pc, c, s, w, u[i], r);
   } else {
-    float th = atan2f(s, c);
+    float th = atan2_bounded(s, c);
     pendulum_step_theta(pc, th, w, u[i], r);
-    sincosf(th, &s, &c);
+    sincos_bounded(th, s, c);
   }
   x_next[3 * i] = c; x_next[3 * i + 1] = s; x_next[3 * i + 2] = w;
   reward[i] = r;
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(128) rollout_actions_pendulum_kernel(
     return;
   }
   float acc = 0.0f;
-  float th = (MATH == MBPO_MATH_REFERENCE) ? 0.0f : atan2f(s, c);
+  float th = (MATH == MBPO_MATH_REFERENCE) ? 0.0f : atan2_bounded(s, c);
   for (int t = 0; t < H; ++t) {
     const size_t o = (static_cast<size_t>(r) * H + t);
     if (obs_out) { obs_out[o * 3] = c; obs_out[o * 3 + 1] = s; obs_out[o * 3 + 2] = w; }
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(128) rollout_actions_pendulum_kernel(
       pendulum_step_ref(pc, c, s, w, row[t], rew);
     } else {
       pendulum_step_theta(pc, th, w, row[t], rew);
-      sincosf(th, &s, &c);
+      sincos_bounded(th, s, c);
     }
     if (reward_out) reward_out[o] = rew;
     if (next_obs_out) { next_obs_out[o * 3] = c; next_obs_out[o * 3 + 1] = s; next_obs_out[o * 3 + 2] = w; }
@@ -98,44 +98,44 @@ __global__ void __launch_bounds__(128) rollout_actions_pendulum_kernel(
   if (returns_out) returns_out[r] = __fdiv_rn(acc, static_cast<float>(H));
 }
 
-// Stage 3 standalone: one warp per problem; keys staged in shared memory, rows read from HBM.
-__global__ void __launch_bounds__(32) elite_refit_kernel(RefitScalars rs, const float* __restrict__ actions,
-                                                         const float* __restrict__ values,
-                                                         const float* __restrict__ mean_in,
-                                                         const float* __restrict__ std_in,
-                                                         const float* __restrict__ best_value_in,
-                                                         const float* __restrict__ best_seq_in, float* mean_out,
-                                                         float* std_out, float* best_value_out, float* best_seq_out,
-                                                         int* elite_idx_out) {
+// Stage 3 standalone: one CTA per problem; keys staged in shared memory, rows read from HBM.
+constexpr int REFIT_THREADS = 128;
+
+__global__ void __launch_bounds__(REFIT_THREADS) elite_refit_kernel(
+    RefitScalars rs, const float* __restrict__ actions, const float* __restrict__ values,
+    const float* __restrict__ mean_in, const float* __restrict__ std_in, const float* __restrict__ best_value_in,
+    const float* __restrict__ best_seq_in, float* mean_out, float* std_out, float* best_value_out,
+    float* best_seq_out, int* elite_idx_out) {
   extern __shared__ __align__(16) uint32_t refit_sm[];
-  const int b = blockIdx.x, lane = threadIdx.x;
-  uint32_t* keys = refit_sm;                                  // [M]
+  const int b = blockIdx.x, tid = threadIdx.x;
+  uint32_t* keys = refit_sm;                             // [M]
   int* elite_idx = reinterpret_cast<int*>(keys + rs.M);  // [K]
-  int* scratch = elite_idx + rs.K;                       // [K]
-  float* mean = reinterpret_cast<float*>(scratch + rs.K);
+  int* sel_idx = elite_idx + rs.K;                       // [K]
+  uint32_t* scratch = reinterpret_cast<uint32_t*>(sel_idx + rs.K);
+  float* mean = reinterpret_cast<float*>(scratch + select_scratch_words(rs.K));
   float* std_ = mean + rs.D;
   float* best_seq = std_ + rs.D;
   float* best_value = best_seq + rs.D;
-  for (int i = lane; i < rs.M; i += 32) keys[i] = total_order_key(values[static_cast<size_t>(b) * rs.M + i]);
-  for (int d = lane; d < rs.D; d += 32) {
+  for (int i = tid; i < rs.M; i += REFIT_THREADS) keys[i] = total_order_key(values[static_cast<size_t>(b) * rs.M + i]);
+  for (int d = tid; d < rs.D; d += REFIT_THREADS) {
     mean[d] = mean_in[static_cast<size_t>(b) * rs.D + d];
     std_[d] = std_in[static_cast<size_t>(b) * rs.D + d];
     best_seq[d] = best_seq_in[static_cast<size_t>(b) * rs.D + d];
   }
-  if (lane == 0) *best_value = best_value_in[b];
-  __syncwarp();
+  if (tid == 0) *best_value = best_value_in[b];
+  __syncthreads();
   const float* rows = actions + static_cast<size_t>(b) * rs.M * rs.D;
-  warp_select_refit(rs, keys, elite_idx, scratch,
-                    [&](int i, int d) { return __ldg(rows + static_cast<size_t>(i) * rs.D + d); }, mean, std_, best_seq,
-                    best_value);
-  for (int d = lane; d < rs.D; d += 32) {
+  cta_select_refit<REFIT_THREADS>(rs, keys, elite_idx, sel_idx, scratch,
+                                  [&](int i, int d) { return __ldg(rows + static_cast<size_t>(i) * rs.D + d); }, mean,
+                                  std_, best_seq, best_value);
+  for (int d = tid; d < rs.D; d += REFIT_THREADS) {
     mean_out[static_cast<size_t>(b) * rs.D + d] = mean[d];
     std_out[static_cast<size_t>(b) * rs.D + d] = std_[d];
     best_seq_out[static_cast<size_t>(b) * rs.D + d] = best_seq[d];
   }
-  if (lane == 0) best_value_out[b] = *best_value;
+  if (tid == 0) best_value_out[b] = *best_value;
   if (elite_idx_out)
-    for (int e = lane; e < rs.K; e += 32) elite_idx_out[static_cast<size_t>(b) * rs.K + e] = elite_idx[e];
+    for (int e = tid; e < rs.K; e += REFIT_THREADS) elite_idx_out[static_cast<size_t>(b) * rs.K + e] = elite_idx[e];
 }
 
 // Warm-start prologue of optimize (:235-249) for the staged plan.
