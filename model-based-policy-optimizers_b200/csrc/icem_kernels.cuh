@@ -40,6 +40,39 @@ __device__ __forceinline__ float rollout_return(const PendulumConsts& pc, float 
   return __fdiv_rn(acc, static_cast<float>(H));
 }
 
+// Two independent rollouts from the same initial state, interleaved step by step: the horizon
+// recurrence is a serial dependency chain, so a second chain in the same thread doubles the
+// instruction-level parallelism at a cost of ~8 registers.
+template <int MATH>
+__device__ __forceinline__ void rollout_return2(const PendulumConsts& pc, float c0, float s0, float w0, int H,
+                                                const float* __restrict__ row_a, const float* __restrict__ row_b,
+                                                float& ret_a, float& ret_b) {
+  float acc_a = 0.0f, acc_b = 0.0f;
+  if (MATH == MBPO_MATH_REFERENCE) {
+    float ca = c0, sa = s0, wa = w0, cb = c0, sb = s0, wb = w0;
+#pragma unroll 1
+    for (int t = 0; t < H; ++t) {
+      float ra, rb;
+      pendulum_step_ref(pc, ca, sa, wa, row_a[t], ra);
+      pendulum_step_ref(pc, cb, sb, wb, row_b[t], rb);
+      acc_a = __fadd_rn(acc_a, ra);
+      acc_b = __fadd_rn(acc_b, rb);
+    }
+  } else {
+    float tha = atan2_bounded(s0, c0), wa = w0, thb = tha, wb = w0;
+#pragma unroll 1
+    for (int t = 0; t < H; ++t) {
+      float ra, rb;
+      pendulum_step_theta(pc, tha, wa, row_a[t], ra);
+      pendulum_step_theta(pc, thb, wb, row_b[t], rb);
+      acc_a = __fadd_rn(acc_a, ra);
+      acc_b = __fadd_rn(acc_b, rb);
+    }
+  }
+  ret_a = __fdiv_rn(acc_a, static_cast<float>(H));
+  ret_b = __fdiv_rn(acc_b, static_cast<float>(H));
+}
+
 // summarize over P identical particles (deterministic System): jnp.mean / jnp.max  (:160)
 __device__ __forceinline__ float summarize_particles(float ret, int P, int summarize) {
   if (summarize == MBPO_SUMMARIZE_MAX || P == 1) return ret;
@@ -72,12 +105,12 @@ template <int H>
 struct PlanSmem {
   static constexpr int HS = H | 1;  // odd row stride: conflict-free per-thread rows
   static size_t bytes(int N, int Np, int K) {
-    size_t words = static_cast<size_t>(N) * HS  // action rows
+    size_t words = static_cast<size_t>(N + 1) * HS  // action rows + one all-zero row
                    + (N + Np)                   // sort keys
                    + 2 * (N + 1)                // legacy split words
                    + 3 * H                      // mean, std, best_seq
                    + 2 * K                      // elite_idx, sel_idx
-                   + select_scratch_words(K)    // selection counters + selected keys
+                   + select_scratch_words(K, N + Np)  // selection histogram + lists
                    + 8;                         // best_value, carry key, state key, pad
     return words * 4;
   }
@@ -86,7 +119,7 @@ struct PlanSmem {
 // Shared-memory carve-up of one planning CTA.
 template <int H>
 struct PlanCtaSmem {
-  float* act;          // [N][HS] action rows of the sampled candidates
+  float* act;          // [N + 1][HS] action rows of the sampled candidates; row N is all zeros
   uint32_t* skey;      // [M]     total-order keys of the objective values
   uint32_t* flat;      // [2(N+1)] legacy split(sampling_rng, N+1) words
   float* mean;         // [H]
@@ -94,14 +127,14 @@ struct PlanCtaSmem {
   float* best_seq;     // [H]
   int* elite_idx;      // [K]
   int* sel_idx;        // [K]
-  uint32_t* sel_scratch;  // [select_scratch_words(K)]
+  uint32_t* sel_scratch;  // [select_scratch_words(K, M)]
   float* best_value;   // [1]
   uint32_t* carry;     // [2] carry.key
   uint32_t* state_key; // [2] opt_state.key (closed loop)
   __device__ __forceinline__ PlanCtaSmem(uint32_t* base, int N, int Np, int K) {
     constexpr int HS = PlanSmem<H>::HS;
     act = reinterpret_cast<float*>(base);
-    skey = base + static_cast<size_t>(N) * HS;
+    skey = base + static_cast<size_t>(N + 1) * HS;
     flat = skey + (N + Np);
     mean = reinterpret_cast<float*>(flat + 2 * (N + 1));
     std_ = mean + H;
@@ -109,7 +142,7 @@ struct PlanCtaSmem {
     elite_idx = reinterpret_cast<int*>(best_seq + H);
     sel_idx = elite_idx + K;
     sel_scratch = reinterpret_cast<uint32_t*>(sel_idx + K);
-    best_value = reinterpret_cast<float*>(sel_scratch + select_scratch_words(K));
+    best_value = reinterpret_cast<float*>(sel_scratch + select_scratch_words(K, N + Np));
     carry = reinterpret_cast<uint32_t*>(best_value + 1);
     state_key = carry + 2;
   }
@@ -146,6 +179,7 @@ __device__ __forceinline__ void plan_problem(const PlanArgs& a, const PlanCtaSme
     std_[tid] = a.init_std;
     best_seq[tid] = m0;
   }
+  if (tid < HS) act[static_cast<size_t>(N) * HS + tid] = 0.0f;   // the all-zero row
   if (tid == 0) {
     *sm.best_value = __int_as_float(0xFF800000);  // -inf
     Key2 k_opt;
@@ -177,47 +211,62 @@ __device__ __forceinline__ void plan_problem(const PlanArgs& a, const PlanCtaSme
       sm.carry[0] = nk.k0; sm.carry[1] = nk.k1;   // key = sampling_rng[0]  (:176)
     }
 
-    // ---- sample + rollout, one row per thread pass -----------------------------------------
-    for (int n = tid; n < N; n += THREADS) {
-      Key2 skey_n;
-      if (PRNG == MBPO_PRNG_LEGACY) { skey_n.k0 = flat[2 * (n + 1)]; skey_n.k1 = flat[2 * (n + 1) + 1]; }
-      else skey_n = split_at<1>(sampling_rng, static_cast<uint32_t>(N + 1), static_cast<uint32_t>(n + 1));
-      const Key2 dim_key = split_at<PRNG>(skey_n, 1u, 0u);   // vmap(split(x, action_dim)), A == 1  (:180)
-      float* row = act + static_cast<size_t>(n) * HS;
-      colored_noise_row<H, PRNG>(dim_key, a.scale, row, nullptr, [&](int t, float y) {
-        const float v = __fadd_rn(mean[t], __fmul_rn(y, std_[t]));           // :190
-        row[t] = fminf(fmaxf(v, a.u_min), a.u_max);                          // :191
-      });
-      const float ret = rollout_return<MATH>(pc, x_c, x_s, x_w, H, [&](int t) { return row[t]; });
-      const float val = summarize_particles(ret, a.P, a.summarize);
-      skey[n] = total_order_key(val);
-      if (a.trace.values) a.trace.values[tslot * M + n] = val;
-      if (a.trace.actions) {
-        float* dst = a.trace.actions + (tslot * M + n) * H;
-        for (int t = 0; t < H; ++t) dst[t] = row[t];
+    // ---- sample + rollout ----------------------------------------------------------------------
+    // Jobs 0..N-1 are the sampled candidates, job N is the closure's all-zero kept-elite row
+    // (:192,:245; deterministic System: one rollout serves all Np rows and all iterations, so it
+    // is only a job in iteration 0).  A thread takes jobs tid, tid + THREADS, ... two at a time:
+    // both rows are sampled first, then rolled out together (rollout_return2).
+    const int jobs = (it == 0) ? N + 1 : N;
+    for (int n0 = tid; n0 < jobs; n0 += 2 * THREADS) {
+      const int n1 = n0 + THREADS;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int n = h ? n1 : n0;
+        if (n >= N) continue;
+        Key2 skey_n;
+        if (PRNG == MBPO_PRNG_LEGACY) { skey_n.k0 = flat[2 * (n + 1)]; skey_n.k1 = flat[2 * (n + 1) + 1]; }
+        else skey_n = split_at<1>(sampling_rng, static_cast<uint32_t>(N + 1), static_cast<uint32_t>(n + 1));
+        const Key2 dim_key = split_at<PRNG>(skey_n, 1u, 0u);   // vmap(split(x, action_dim)), A == 1  (:180)
+        float* row = act + static_cast<size_t>(n) * HS;
+        colored_noise_row<H, PRNG>(dim_key, a.scale, row, nullptr, [&](int t, float y) {
+          const float v = __fadd_rn(mean[t], __fmul_rn(y, std_[t]));           // :190
+          row[t] = fminf(fmaxf(v, a.u_min), a.u_max);                          // :191
+        });
       }
-    }
-    // kept-elite rows are the closure's all-zero sequences (:192,:245): one rollout serves
-    // all Np rows and all iterations (deterministic System).
-    if (tid == THREADS - 1) {
-      if (it == 0) {
-        const float ret = rollout_return<MATH>(pc, x_c, x_s, x_w, H, [](int) { return 0.0f; });
-        const uint32_t zk = total_order_key(summarize_particles(ret, a.P, a.summarize));
-        for (int j = N; j < M; ++j) skey[j] = zk;
-      }
-      if (a.trace.values || a.trace.actions) {
-        const uint32_t zk = skey[N];
-        const float zv = __uint_as_float((zk & 0x80000000u) ? (zk & 0x7FFFFFFFu) : ~zk);
-        for (int j = N; j < M; ++j) {
-          if (a.trace.values) a.trace.values[tslot * M + j] = zv;
+      const int r0 = n0 < N ? n0 : N, r1 = n1 < N ? n1 : N;   // idle slots roll out the zero row
+      float ret0, ret1;
+      rollout_return2<MATH>(pc, x_c, x_s, x_w, H, act + static_cast<size_t>(r0) * HS,
+                            act + static_cast<size_t>(r1) * HS, ret0, ret1);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int n = h ? n1 : n0;
+        const float val = summarize_particles(h ? ret1 : ret0, a.P, a.summarize);
+        if (n < N) {
+          skey[n] = total_order_key(val);
+          if (a.trace.values) a.trace.values[tslot * M + n] = val;
           if (a.trace.actions) {
-            float* dst = a.trace.actions + (tslot * M + j) * H;
-            for (int t = 0; t < H; ++t) dst[t] = 0.0f;
+            const float* row = act + static_cast<size_t>(n) * HS;
+            float* dst = a.trace.actions + (tslot * M + n) * H;
+            for (int t = 0; t < H; ++t) dst[t] = row[t];
           }
+        } else if (n == N && it == 0) {
+          const uint32_t zk = total_order_key(val);
+          for (int j = N; j < M; ++j) skey[j] = zk;
         }
       }
     }
     __syncthreads();
+    if (a.trace.values || a.trace.actions) {
+      const uint32_t zk = skey[N];
+      const float zv = __uint_as_float((zk & 0x80000000u) ? (zk & 0x7FFFFFFFu) : ~zk);
+      for (int j = N + tid; j < M; j += THREADS) {
+        if (a.trace.values) a.trace.values[tslot * M + j] = zv;
+        if (a.trace.actions) {
+          float* dst = a.trace.actions + (tslot * M + j) * H;
+          for (int t = 0; t < H; ++t) dst[t] = 0.0f;
+        }
+      }
+    }
 
     // ---- select + refit + best tracking (:199-226), whole CTA --------------------------------
     cta_select_refit<THREADS>(rs, skey, sm.elite_idx, sm.sel_idx, sm.sel_scratch,

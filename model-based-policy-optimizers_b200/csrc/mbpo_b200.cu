@@ -131,9 +131,9 @@ int plan_fusable(const MbpoIcemCfg* c, bool set_error) {
   else if (!horizon_supported(c->horizon)) why = "fused plan: horizon has no compiled kernel (" MBPO_H_LIST_STR ")";
   else {
     const int HS = c->horizon | 1;
-    const size_t words = static_cast<size_t>(c->num_samples) * HS + (c->num_samples + c->num_prev_elites) +
+    const size_t words = static_cast<size_t>(c->num_samples + 1) * HS + (c->num_samples + c->num_prev_elites) +
                          2 * (c->num_samples + 1) + 3 * c->horizon + 2 * c->num_elites +
-                         select_scratch_words(c->num_elites) + 8;
+                         select_scratch_words(c->num_elites, c->num_samples + c->num_prev_elites) + 8;
     if (words * 4 > 227 * 1024) why = "fused plan: population does not fit 227 KB of shared memory";
   }
   if (why && set_error) fail(MBPO_EUNSUPPORTED, "%s", why);
@@ -383,7 +383,7 @@ int mbpo_icem_elite_refit(const MbpoIcemCfg* cfg, const float* actions, const fl
   rs.D = cfg->horizon * cfg->action_dim;
   rs.alpha = cfg->alpha;
   rs.one_minus_alpha = static_cast<float>(1.0 - static_cast<double>(cfg->alpha));
-  const size_t smem = (static_cast<size_t>(rs.M) + 2 * rs.K + select_scratch_words(rs.K) + 3 * rs.D + 4) * 4;
+  const size_t smem = (static_cast<size_t>(rs.M) + 2 * rs.K + select_scratch_words(rs.K, rs.M) + 3 * rs.D + 4) * 4;
   if (smem > 227 * 1024) return fail(MBPO_EUNSUPPORTED, "elite_refit: population too large for shared memory");
   const cudaError_t e =
       cudaFuncSetAttribute(elite_refit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));

@@ -8,13 +8,13 @@
 //   if best_value <= elite_values[-1]: best = (elite_values[-1], elites[-1])        :217-226
 //
 // The sort key of element i is the pair (total_order_key(value_i), i); pairs are unique, so
-// "top K of a stable ascending sort" is exactly "the K largest pairs".  The K-th largest
-// 32-bit key is found by a bitwise binary search in which every thread counts its own
-// candidates and the CTA sums the counts (one barrier per differing bit); ties at the
-// threshold keep the largest indices.  The K elites are then ranked among themselves (K
-// compares each) so that every float sum below runs in the reference's rank order with
-// unfused float32 operations: given identical inputs the refit is bit-identical to the
-// NumPy oracle.
+// "top K of a stable ascending sort" is exactly "the K largest pairs".  Selection is one
+// radix pass: a 256-bin shared-memory histogram over the 8 most significant bits in which the
+// keys differ locates the bin holding the K-th largest key; everything in higher bins is an
+// elite, and the (few) candidates inside the boundary bin are ranked exactly by brute force.
+// The K elites are then ranked among themselves (K compares each) so that every float sum
+// below runs in the reference's rank order with unfused float32 operations: given identical
+// inputs the refit is bit-identical to the NumPy oracle.
 #pragma once
 #include "mathx.cuh"
 
@@ -28,17 +28,19 @@ struct RefitScalars {
   float one_minus_alpha;  // float32(1 - alpha), rounded on the host like the weak python scalar
 };
 
-// Scratch words the selection needs besides keys/elite_idx: counters + K selected keys.
-__host__ __device__ constexpr int select_scratch_words(int K) { return 40 + K; }
+// Scratch words the selection needs besides keys / elite_idx / sel_idx:
+// histogram [256] + misc [8] + selected keys [K] + boundary-bin candidates [M].
+__host__ __device__ constexpr int select_scratch_words(int K, int M) { return 264 + K + M; }
 
 // keys      : shared, uint32[M]  total-order keys of the objective values
 // elite_idx : shared, int32[K]   out: argsort(values)[-K:]  (ascending rank)
 // sel_idx   : shared, int32[K]   temporary (unordered selection)
-// scratch   : shared, uint32[select_scratch_words(K)]  temporary
+// scratch   : shared, uint32[select_scratch_words(K, M)]  temporary
 // row(i, d) : action element d of candidate i
 // mean/std/best_seq : shared float[D], updated in place; best_value: shared float*
-// Must be called by all THREADS threads of the CTA (contains barriers); on return the
-// outputs are visible to every thread.
+// Must be called by all THREADS threads of the CTA (contains barriers; THREADS a multiple of
+// 32); keys must be visible (barrier) before the call; on return the outputs are visible to
+// every thread.
 template <int THREADS, typename RowFn>
 __device__ __forceinline__ void cta_select_refit(const RefitScalars rs, const uint32_t* keys, int* elite_idx,
                                                  int* sel_idx, uint32_t* scratch, RowFn row, float* mean,
@@ -47,12 +49,13 @@ __device__ __forceinline__ void cta_select_refit(const RefitScalars rs, const ui
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int M = rs.M, K = rs.K;
-  // scratch layout: [0] or, [1] and, [2] n_gt, [3] n_eq, [4] selection cursor, [8..40) per-bit counts, [40..) keys
-  uint32_t* cnt = scratch + 8;
-  uint32_t* sel_key = scratch + 40;
+  uint32_t* hist = scratch;              // [256]
+  uint32_t* misc = scratch + 256;        // [0] or, [1] and, [2] selection cursor, [3] candidate cursor
+  uint32_t* sel_key = scratch + 264;     // [K]
+  int* cand = reinterpret_cast<int*>(scratch + 264 + K);  // [M]
 
-  // ---- 0. reset counters; OR / AND of all keys -------------------------------------------
-  for (int i = tid; i < 40; i += THREADS) scratch[i] = (i == 1) ? 0xFFFFFFFFu : 0u;
+  // ---- 0. reset; OR / AND of all keys (which bits differ at all) -----------------------------
+  for (int i = tid; i < 264; i += THREADS) scratch[i] = (i == 257) ? 0xFFFFFFFFu : 0u;
   __syncthreads();
   {
     uint32_t o = 0u, a = 0xFFFFFFFFu;
@@ -64,65 +67,90 @@ __device__ __forceinline__ void cta_select_refit(const RefitScalars rs, const ui
     o = __reduce_or_sync(full, o);
     a = __reduce_and_sync(full, a);
     if (lane == 0) {
-      atomicOr(&scratch[0], o);
-      atomicAnd(&scratch[1], a);
+      atomicOr(&misc[0], o);
+      atomicAnd(&misc[1], a);
     }
   }
   __syncthreads();
-  const uint32_t all_and = scratch[1];
-  const uint32_t diff = scratch[0] ^ all_and;
+  const uint32_t diff = misc[0] ^ misc[1];
+  const int hb = 31 - __clz(diff | 1u);        // highest differing bit (0 if all keys are equal)
+  const int shift = hb > 7 ? hb - 7 : 0;       // digit = bits [shift, shift + 8); higher bits are common
 
-  // ---- 1. K-th largest key: bitwise binary search over the bits that differ ----------------
-  uint32_t thr = all_and;  // common bits
-  for (int bit = 31 - __clz(diff | 1u); bit >= 0; --bit) {
-    if (!((diff >> bit) & 1u)) continue;  // CTA-uniform
-    const uint32_t cand = thr | (1u << bit);
-    int c = 0;
-    for (int i = tid; i < M; i += THREADS) c += (keys[i] >= cand) ? 1 : 0;
-    c = __reduce_add_sync(full, c);
-    if (lane == 0 && c) atomicAdd(&cnt[bit], static_cast<uint32_t>(c));
-    __syncthreads();
-    if (static_cast<int>(cnt[bit]) >= K) thr = cand;
-  }
-  // thr is now the K-th largest key (bits below the lowest differing bit are common).
+  // ---- 1. histogram of the leading digit ---------------------------------------------------
+  for (int i = tid; i < M; i += THREADS) atomicAdd(&hist[(keys[i] >> shift) & 255u], 1u);
+  __syncthreads();
+
+  // ---- 2. boundary bin: the largest bin bb with count(bins >= bb) >= K (every warp redundantly)
+  int bb, n_above;
   {
-    int n_gt = 0, n_eq = 0;
-    for (int i = tid; i < M; i += THREADS) {
-      const uint32_t k = keys[i];
-      n_gt += (k > thr) ? 1 : 0;
-      n_eq += (k == thr) ? 1 : 0;
+    uint32_t h8[8];
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      h8[j] = hist[lane * 8 + j];
+      s += h8[j];
     }
-    n_gt = __reduce_add_sync(full, n_gt);
-    n_eq = __reduce_add_sync(full, n_eq);
-    if (lane == 0) {
-      if (n_gt) atomicAdd(&scratch[2], static_cast<uint32_t>(n_gt));
-      if (n_eq) atomicAdd(&scratch[3], static_cast<uint32_t>(n_eq));
+    uint32_t suf = s;  // inclusive suffix sum over lanes (lanes >= mine)
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t v = __shfl_down_sync(full, suf, off);
+      if (lane + off < 32) suf += v;
     }
+    const unsigned ok = __ballot_sync(full, static_cast<int>(suf) >= K);  // lane 0 always qualifies (suf = M >= K)
+    const int L = 31 - __clz(ok);
+    int my_bb = 0, my_above = 0;
+    if (lane == L) {
+      uint32_t above = suf - s;  // keys in bins above this lane's eight
+      my_bb = lane * 8;
+#pragma unroll
+      for (int j = 7; j >= 0; --j) {
+        if (static_cast<int>(above + h8[j]) >= K) {
+          my_bb = lane * 8 + j;
+          break;
+        }
+        above += h8[j];
+      }
+      my_above = static_cast<int>(above);
+    }
+    bb = __shfl_sync(full, my_bb, L);
+    n_above = __shfl_sync(full, my_above, L);
   }
-  __syncthreads();
-  const int skip = static_cast<int>(scratch[3]) - (K - static_cast<int>(scratch[2]));  // ties that do NOT make the cut
+  const int need = K - n_above;  // elites still to be taken from the boundary bin (>= 1)
 
-  // ---- 2. selection (unordered): k > thr, or a tie whose ascending-index rank is >= skip ---
+  // ---- 3. classify: above the boundary bin -> elite; inside it -> candidate ------------------
   for (int i = tid; i < M; i += THREADS) {
     const uint32_t k = keys[i];
-    bool sel = k > thr;
-    if (k == thr) {
-      sel = true;
-      if (skip > 0) {  // rare: the cut falls inside a group of equal values
-        int tie_rank = 0;
-        for (int j = 0; j < i; ++j) tie_rank += (keys[j] == thr) ? 1 : 0;
-        sel = tie_rank >= skip;
-      }
-    }
-    if (sel) {
-      const uint32_t pos = atomicAdd(&scratch[4], 1u);
+    const int d = static_cast<int>((k >> shift) & 255u);
+    if (d > bb) {
+      const uint32_t pos = atomicAdd(&misc[2], 1u);
       sel_idx[pos] = i;
       sel_key[pos] = k;
+    } else if (d == bb) {
+      cand[atomicAdd(&misc[3], 1u)] = i;
     }
   }
   __syncthreads();
 
-  // ---- 3. rank the K elites by (key, index) ascending --------------------------------------
+  // ---- 4. exact choice inside the boundary bin: the `need` largest (key, index) pairs ---------
+  const int nc = static_cast<int>(misc[3]);
+  for (int e = tid; e < nc; e += THREADS) {
+    const int ie = cand[e];
+    const uint32_t ke = keys[ie];
+    int larger = 0;
+    for (int f = 0; f < nc; ++f) {
+      const int jf = cand[f];
+      const uint32_t kf = keys[jf];
+      larger += (kf > ke || (kf == ke && jf > ie)) ? 1 : 0;
+    }
+    if (larger < need) {
+      const uint32_t pos = atomicAdd(&misc[2], 1u);
+      sel_idx[pos] = ie;
+      sel_key[pos] = ke;
+    }
+  }
+  __syncthreads();
+
+  // ---- 5. rank the K elites by (key, index) ascending --------------------------------------
   for (int e = tid; e < K; e += THREADS) {
     const int ie = sel_idx[e];
     const uint32_t ke = sel_key[e];
@@ -136,7 +164,7 @@ __device__ __forceinline__ void cta_select_refit(const RefitScalars rs, const ui
   }
   __syncthreads();
 
-  // ---- 4. refit, column-parallel, rank-ordered unfused float32 sums ------------------------
+  // ---- 6. refit, column-parallel, rank-ordered unfused float32 sums ------------------------
   const float kf = static_cast<float>(K);
   const int best_i = elite_idx[K - 1];
   const uint32_t best_key = keys[best_i];

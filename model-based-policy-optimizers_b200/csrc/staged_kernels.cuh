@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(REFIT_THREADS) elite_refit_kernel(
   int* elite_idx = reinterpret_cast<int*>(keys + rs.M);  // [K]
   int* sel_idx = elite_idx + rs.K;                       // [K]
   uint32_t* scratch = reinterpret_cast<uint32_t*>(sel_idx + rs.K);
-  float* mean = reinterpret_cast<float*>(scratch + select_scratch_words(rs.K));
+  float* mean = reinterpret_cast<float*>(scratch + select_scratch_words(rs.K, rs.M));
   float* std_ = mean + rs.D;
   float* best_seq = std_ + rs.D;
   float* best_value = best_seq + rs.D;
