@@ -22,7 +22,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -59,39 +58,40 @@ def random_states(n, seed):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Streams nvidia-smi clocks / throttle reasons (one sample every 20 ms) while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index = index
-        self.rows = []
-        self._stop = threading.Event()
-        self._t = threading.Thread(target=self._run, daemon=True)
-
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.1)
+        self.proc = None
+        self.out = ""
 
     def __enter__(self):
-        self._t.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.15)        # let the first samples arrive before the timed region starts
+        except Exception:
+            self.proc = None
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+        if self.proc is not None:
+            time.sleep(0.05)
+            self.proc.terminate()
+            try:
+                self.out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill()
 
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for line in self.out.splitlines():
+            r = [c.strip() for c in line.split(",")]
             if len(r) < 7:
                 continue
             try:
@@ -308,7 +308,7 @@ def run_ours(args, wl_name, wl):
                     "h2d_bytes_per_step": int(x0_host.numel() * 4), "d2h_bytes_per_step": int(act_host.numel() * 4),
                     "api": "iCemTO.act(obs[B,3] from pinned host) -> first actions[B,1] to pinned host"
                            + ("; NCCL all_gather of first actions" if world > 1 else "")},
-            "gpu_launches": args.steps,
+            "gpu_launches": 2 * args.steps,   # zero_row_value_kernel + icem_plan_pendulum_kernel per step
             "roofline": roofline,
             "cpu_baseline": cpu,
         }
@@ -320,7 +320,7 @@ def run_ours(args, wl_name, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="config2_batched_icem")

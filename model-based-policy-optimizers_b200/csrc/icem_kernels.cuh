@@ -99,6 +99,9 @@ struct PlanArgs {
   float* best_value_out;     // [B]
   uint32_t* key_out;         // [B,2]
   MbpoIcemTrace trace;       // optional dumps
+  // 1: best_value_out[b] holds, on entry, the objective of the all-zero action row of problem b
+  // (zero_row_value_kernel) -- the kept-elite rows are then no rollout job inside the plan.
+  int zero_value_precomputed;
 };
 
 template <int H>
@@ -216,7 +219,11 @@ __device__ __forceinline__ void plan_problem(const PlanArgs& a, const PlanCtaSme
     // (:192,:245; deterministic System: one rollout serves all Np rows and all iterations, so it
     // is only a job in iteration 0).  A thread takes jobs tid, tid + THREADS, ... two at a time:
     // both rows are sampled first, then rolled out together (rollout_return2).
-    const int jobs = (it == 0) ? N + 1 : N;
+    const int jobs = (it == 0 && !a.zero_value_precomputed) ? N + 1 : N;
+    if (it == 0 && a.zero_value_precomputed && tid == THREADS - 1) {
+      const uint32_t zk = total_order_key(a.best_value_out[slot]);
+      for (int j = N; j < M; ++j) skey[j] = zk;
+    }
     for (int n0 = tid; n0 < jobs; n0 += 2 * THREADS) {
       const int n1 = n0 + THREADS;
 #pragma unroll 1
@@ -281,6 +288,18 @@ __device__ __forceinline__ void plan_problem(const PlanArgs& a, const PlanCtaSme
     if (a.trace.best_value && tid == 0) a.trace.best_value[tslot] = *sm.best_value;
     __syncthreads();
   }
+}
+
+// Objective of the all-zero action row (the closure's kept-elite rows, :192,:245) for every
+// problem, one thread per problem: keeps a one-lane rollout out of the plan kernel's CTAs.
+template <int MATH>
+__global__ void zero_row_value_kernel(const MbpoPendulumParams sys, int H, int P, int summarize,
+                                      const float* __restrict__ x0, int B, float* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const PendulumConsts pc(sys);
+  const float ret = rollout_return<MATH>(pc, x0[3 * b], x0[3 * b + 1], x0[3 * b + 2], H, [](int) { return 0.0f; });
+  out[b] = summarize_particles(ret, P, summarize);
 }
 
 // Fused plan: one CTA plans one problem at a time (grid-stride over problems).

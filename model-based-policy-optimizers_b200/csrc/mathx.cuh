@@ -19,6 +19,9 @@ __device__ __forceinline__ float bits_to_uniform(uint32_t bits, float lo, float 
 // log2 (MUFU.LG2): 1 - t is exact for t >= 0.5 (Sterbenz) and otherwise perturbs w by <= 6e-8
 // absolute, i.e. the result by <= ~2e-8 relative (|p'(w)| <= 0.25) -- below the 1-2 ulp spread
 // between log1p implementations (XLA's own is a polynomial), ~20 instructions cheaper.
+// GUARD = false drops the |x| == 1 -> +-inf special case for callers whose argument is provably
+// inside (-1, 1).
+template <bool GUARD = true>
 __device__ __forceinline__ float erf_inv_f32(float x) {
   float w = -__logf(1.0f - __fmul_rn(x, x));
   float p;
@@ -45,16 +48,17 @@ __device__ __forceinline__ float erf_inv_f32(float x) {
     p = fmaf(p, w, 1.00167406f);
     p = fmaf(p, w, 2.83297682f);
   }
-  return (fabsf(x) == 1.0f) ? __int_as_float(0x7F800000) * x : p * x;
+  return GUARD ? ((fabsf(x) == 1.0f) ? __int_as_float(0x7F800000) * x : p * x) : p * x;
 }
 
 // jax.random.normal for one 32-bit word: sqrt(2) * erf_inv(uniform(nextafter(-1,0), 1)).
-// hi - lo = 1 - (-0.99999994) rounds to exactly 2.0f in float32.
+// hi - lo = 1 - (-0.99999994) rounds to exactly 2.0f in float32, so f * 2 is exact and
+// u = f * 2 + lo lies in [lo, 0.99999982]: jax's max(lo, u) is the identity and |u| < 1.
 __device__ __forceinline__ float bits_to_normal(uint32_t bits) {
   const float lo = -0.99999994f;  // nextafter(-1, 0)
   const float f = __uint_as_float((bits >> 9) | 0x3F800000u) - 1.0f;
-  const float u = fmaxf(lo, f * 2.0f + lo);
-  return 1.41421356f * erf_inv_f32(u);
+  const float u = f * 2.0f + lo;
+  return 1.41421356f * erf_inv_f32<false>(u);
 }
 
 // Sort key of jnp.argsort (stable, ascending; icem_optimizer.py:199): monotone uint32 image

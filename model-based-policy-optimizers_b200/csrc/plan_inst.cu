@@ -34,7 +34,13 @@ int launch(const PlanArgs& a, const MpcArgs* mpc, cudaStream_t st) {
     auto kernel = icem_plan_pendulum_kernel<kH, PRNG, MATH, kPlanThreads, kMinBlocks>;
     const int rc = prepare_plan_kernel(kernel, smem, a.B, &grid);
     if (rc != MBPO_OK) return rc;
-    kernel<<<grid, kPlanThreads, smem, st>>>(a);
+    PlanArgs b = a;
+    b.zero_value_precomputed = 1;   // best_value_out doubles as the hand-over buffer
+    zero_row_value_kernel<MATH><<<(a.B + 127) / 128, 128, 0, st>>>(a.sys, kH, a.P, a.summarize, a.x0, a.B,
+                                                                  a.best_value_out);
+    const int rc2 = check_launch("zero_row_value_kernel");
+    if (rc2 != MBPO_OK) return rc2;
+    kernel<<<grid, kPlanThreads, smem, st>>>(b);
     return check_launch("icem_plan_pendulum_kernel");
   }
   auto kernel = icem_mpc_pendulum_kernel<kH, PRNG, MATH, kPlanThreads, kMinBlocks>;
