@@ -1,0 +1,146 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads without a GPU, exports every symbol
+include/mbpo_b200.h declares, agrees with the ctypes struct layouts, and fails loudly (error
+codes, no fallback) when asked to compute without a CUDA device.  No kernels run here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mbpo_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "mbpo_b200.h")
+
+
+@pytest.fixture(scope="module")
+def mb():
+    import mbpo_b200
+    return mbpo_b200
+
+
+def _declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mbpo_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(mb):
+    names = _declared_symbols()
+    assert len(names) >= 20
+    lib = C.CDLL(mb._lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), "libmbpo_b200.so does not export %s" % n
+    assert set(names) == set(mb._lib.SIGNATURES), "ctypes binding and header disagree"
+
+
+def test_abi_version_and_struct_layout(mb):
+    L = mb._lib
+    assert L.lib.mbpo_abi_version() == L.MBPO_ABI_VERSION == 1
+    for which, st in enumerate((L.IcemCfgC, L.PendulumParamsC, L.MlpEnsembleParamsC, L.IcemTraceC)):
+        assert L.lib.mbpo_struct_size(which) == C.sizeof(st)
+    assert L.lib.mbpo_struct_size(99) == 0
+    assert C.sizeof(L.PendulumParamsC) == 36
+
+
+@pytest.mark.parametrize("horizon,exponent", [(20, 0.0), (30, 2.0), (15, 1.0), (50, 0.5), (5, 3.0)])
+def test_cfg_init_matches_reference_trace_time_constants(mb, horizon, exponent):
+    """mbpo_icem_cfg_init runs on the host: s_scale / sigma (general_utils.py:143-178) and
+    num_prev_elites (icem_optimizer.py:170) against the oracle."""
+    L = mb._lib
+    cfg = L.IcemCfgC()
+    L.check(L.lib.mbpo_icem_cfg_init(C.byref(cfg), horizon, 1, 3, 10, 500, 50, 0.5, 0.0, 5, exponent, 0.3, -1.0, 1.0,
+                                     1, 1e4))
+    s_scale, sigma = orc.powerlaw_tables(exponent, horizon)
+    F = horizon // 2 + 1
+    np.testing.assert_allclose(np.array(cfg.s_scale[:F]), s_scale, rtol=3e-7)
+    assert cfg.sigma == pytest.approx(float(sigma), rel=5e-7)
+    assert cfg.num_prev_elites == orc.ICemParams().num_prev_elites == 15
+    assert (cfg.horizon, cfg.num_samples, cfg.num_elites, cfg.num_steps, cfg.warm_start) == (horizon, 500, 50, 5, 1)
+    assert cfg.prng_mode == L.PRNG_LEGACY and cfg.math_mode == L.MATH_REFERENCE
+    for frac, k, want in ((0.3, 50, 15), (0.01, 50, 1), (0.5, 7, 3), (0.3, 10, 3)):
+        L.check(L.lib.mbpo_icem_cfg_init(C.byref(cfg), horizon, 1, 3, 1, 64, k, 0.5, 0.0, 5, 0.0, frac, -1.0, 1.0, 1, 1e4))
+        assert cfg.num_prev_elites == want == max(int(frac * k), 1)
+
+
+def test_error_codes_without_gpu(mb):
+    L = mb._lib
+    cfg = L.IcemCfgC()
+    assert L.lib.mbpo_icem_cfg_init(C.byref(cfg), 1000, 1, 3, 1, 64, 8, 0.5, 0.0, 5, 0.0, 0.3, -1.0, 1.0, 1, 1e4) == L.MBPO_EINVAL
+    assert b"horizon" in L.lib.mbpo_last_error()
+    L.check(L.lib.mbpo_icem_cfg_init(C.byref(cfg), 30, 1, 3, 1, 512, 50, 0.5, 0.0, 5, 0.0, 0.3, -1.0, 1.0, 1, 1e4))
+    assert L.lib.mbpo_icem_plan_is_fused(C.byref(cfg)) == 1
+    assert L.lib.mbpo_icem_workspace_bytes(C.byref(cfg), 16) > 16 * 527 * 30 * 4
+    cfg.horizon = 21                                   # no compiled kernel for H=21
+    assert L.lib.mbpo_icem_plan_is_fused(C.byref(cfg)) == 0
+    cfg.horizon = 30
+    cfg.num_samples = 4000                             # 4000 x 31 floats do not fit 227 KB of shared memory
+    assert L.lib.mbpo_icem_plan_is_fused(C.byref(cfg)) == 0
+    cfg.num_samples, cfg.num_elites = 8, 100           # K > N + Np
+    assert L.lib.mbpo_icem_plan_is_fused(C.byref(cfg)) == 0
+    # null pointers are EINVAL, never a crash
+    assert L.lib.mbpo_prng_split(None, 4, 2, 0, None, None) == L.MBPO_EINVAL
+    assert L.lib.mbpo_system_step(0, None, 0, None, None, 4, None, None, None) == L.MBPO_EINVAL
+    assert L.lib.mbpo_system_step(9, None, 0, None, None, 4, None, None, None) == L.MBPO_EINVAL
+    with pytest.raises(mb.MbpoError):
+        L.check(L.MBPO_EINVAL)
+    with pytest.raises(NotImplementedError):
+        L.check(L.MBPO_EUNSUPPORTED)
+
+
+def test_no_cpu_fallback(mb):
+    """Without a GPU the product path refuses to run (the oracle is never consulted)."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from mbpo_b200.optimizers import iCemTO, iCemParams
+    from mbpo_b200.systems import PendulumSystem, SystemParams
+    with pytest.raises(mb.MbpoError):
+        mb.random.PRNGKey(0)
+    with pytest.raises(mb.MbpoError):
+        PendulumSystem().step(torch.zeros(3), torch.zeros(1), SystemParams())
+    with pytest.raises(mb.MbpoError):
+        mb.random.split(torch.zeros(2, dtype=torch.uint32))
+    opt = iCemTO(horizon=20, action_dim=1, opt_params=iCemParams())
+    opt.set_system(PendulumSystem())
+    cfg = opt._cfg()                                   # host-only: allowed
+    assert cfg.num_prev_elites == 15 and cfg.system_kind == mb._lib.SYSTEM_PENDULUM
+    import sys
+    assert not any(m.startswith("oracle") for m in sys.modules if "mbpo_b200" in m)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "model-based-policy-optimizers_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "from oracle" not in text and "import oracle" not in text, os.path.join(dirpath, f)
+
+
+def test_api_surface_matches_reference(mb):
+    """Names and argument order of the reference interface."""
+    import inspect
+    from mbpo_b200.optimizers import BaseOptimizer, iCEMOptimizer, iCemParams, iCemTO
+    from mbpo_b200.systems import PendulumSystem, System, SystemParams, SystemState
+    from mbpo_b200.utils import rollout_actions
+    assert iCemParams._fields == ("num_particles", "num_samples", "num_elites", "init_std", "alpha", "num_steps",
+                                  "exponent", "elite_set_fraction", "u_min", "u_max", "warm_start", "lambda_constraint")
+    assert iCemParams() == (10, 500, 50, 0.5, 0.0, 5, 0.0, 0.3, -1.0, 1.0, True, 1e4)
+    assert list(inspect.signature(iCemTO.__init__).parameters)[:8] == [
+        "self", "horizon", "action_dim", "key", "opt_params", "cost_fn", "use_optimism", "use_pessimism"]
+    assert list(inspect.signature(iCemTO.optimize).parameters) == ["self", "initial_state", "opt_state"]
+    assert list(inspect.signature(iCemTO.act).parameters) == ["self", "obs", "opt_state", "evaluate"]
+    assert list(inspect.signature(iCemTO.init).parameters) == ["self", "key", "true_buffer_state"]
+    assert list(inspect.signature(iCEMOptimizer.__init__).parameters)[:5] == ["self", "horizon", "opt_params", "system", "key"]
+    assert list(inspect.signature(System.step).parameters) == ["self", "x", "u", "system_params"]
+    assert list(inspect.signature(rollout_actions).parameters) == ["system", "system_params", "init_state", "actions", "horizon"]
+    assert issubclass(iCemTO, BaseOptimizer) and issubclass(PendulumSystem, System)
+    assert iCEMOptimizer(horizon=20).can_act_in_batches is False
+    s = PendulumSystem()
+    assert (s.x_dim, s.u_dim, s.min_action, s.max_action) == (3, 1, -1.0, 1.0)
+    sp = System.system_params_vmap_axes(0)
+    assert sp.key == 0 and sp.dynamics_params is None
+    st = SystemState(x_next=1, reward=2, system_params=SystemParams())
+    assert st.done == 0.0 and st.replace(reward=3).reward == 3
