@@ -37,6 +37,7 @@ WORKLOADS = {
     "config2_colored": dict(B=4096, horizon=30, params=dict(num_samples=512, num_particles=1, exponent=2.0, alpha=0.1)),
     "config4_population": dict(B=1024, horizon=50, params=dict(num_samples=1024, num_particles=1)),
 }
+GUARD = None
 METRIC = "iCEM model-rollout transitions/sec (pop x horizon x problems x CEM iterations)"
 UNIT = "transitions/s"
 
@@ -166,7 +167,7 @@ def run_reference(args, wl_name, wl):
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line, GUARD)
 
 
 def workload_config(name, wl, gpus, l2):
@@ -312,9 +313,171 @@ def run_ours(args, wl_name, wl):
             "roofline": roofline,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit_json(line, GUARD)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# config 3: vmapped System.step rollouts for SAC/PPO data collection (HBM-bound stream)
+# ------------------------------------------------------------------------------------------------
+ENV_E, ENV_T, ENV_EPISODE = 65536, 1000, 200
+ENV_BYTES_PER_TRANSITION = 4 + 36    # action read; obs 12 + next_obs 12 + reward/discount/truncation 12 written
+
+
+def run_env(args):
+    """65,536 envs x 1,000 wrapped env steps per call, envs sharded over the ranks (strong scaling)."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import c_twin, mbpo_oracle as orc
+        lib = c_twin.load(native=True)
+        E, T = 4096, 250                       # bounded sample of the same workload
+        x0 = random_states(ENV_E, 1)[:E]
+        acts = np.random.default_rng(2).uniform(-1, 1, (T, E)).astype(np.float32)
+        p9 = orc.PendulumParams().packed()
+        c_twin.env_rollout(lib, p9, x0[:256], acts[:, :256].copy(), ENV_EPISODE)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            out = c_twin.env_rollout(lib, p9, x0, acts, ENV_EPISODE)
+        dt = (time.perf_counter() - t0) / args.steps
+        ncores, model = host_info()
+        v = E * T / dt
+        emit_json({"impl": "reference", "metric": "vmapped System.step env-steps/sec", "value": v,
+                          "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                          "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "config3_env_rollouts", "envs": ENV_E, "steps_per_call": ENV_T},
+                          "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": out["threads"], "kind": "port",
+                                           "sample": "%d envs x %d steps of 65536 x 1000" % (E, T), "host_cpu": model},
+                          "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
+                  GUARD)
+        return
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import mbpo_b200
+    from mbpo_b200.envs import wrap
+    from mbpo_b200.parallel import shard_bounds
+    from mbpo_b200.systems import PendulumSystem
+    mbpo_b200.config.math_mode = args.math
+    lo, hi = shard_bounds(ENV_E, rank, world)
+    E, T = hi - lo, ENV_T
+    system = PendulumSystem()
+    sp = system.reset(device=dev).system_params
+    env = wrap(system, sp, episode_length=ENV_EPISODE)
+    x0 = torch.from_numpy(random_states(ENV_E, 1)[lo:hi].copy()).to(dev)
+    acts_host = torch.from_numpy(np.random.default_rng(2).uniform(-1, 1, (T, ENV_E, 1)).astype(np.float32)[:, lo:hi].copy())
+    acts_host = acts_host.pin_memory()
+    acts = acts_host.to(dev)
+    st = env.reset(x0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # raw C-ABI launches into preallocated Transition buffers (no allocator traffic in the timed region)
+    L = mbpo_b200._lib
+    o = torch.empty((T, E, 3), device=dev); n = torch.empty((T, E, 3), device=dev)
+    r = torch.empty((T, E), device=dev); d = torch.empty((T, E), device=dev); tr = torch.empty((T, E), device=dev)
+    params = system.pack_params(sp)
+    obs, steps, done, first = st.obs.clone(), st.info["steps"].clone(), st.done.clone(), st.info["first_obs"]
+
+    def launch():
+        L.check(L.lib.mbpo_env_rollout(system.system_kind, L.C.addressof(params), mbpo_b200.config.math_mode_id, 3, 1,
+                                       ENV_EPISODE, 1, L.ptr(obs), L.ptr(steps), L.ptr(done), L.ptr(first),
+                                       L.ptr(acts), E, T, L.ptr(o), L.ptr(r), L.ptr(d), L.ptr(n), L.ptr(tr),
+                                       L.stream_ptr(dev)))
+    for _ in range(max(args.warmup, 3)):
+        launch()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        for k in range(args.steps):
+            starts[k].record()
+            launch()
+            ends[k].record()
+        barrier()
+    ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends)) / args.steps
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = ENV_E * T / (ms * 1e-3)
+    # end to end: actions from pinned host memory, rewards back to the host
+    rew_host = torch.empty((T, E), dtype=torch.float32).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        a_dev = acts_host.to(dev, non_blocking=True)
+        st2, trn = env.unroll(st, a_dev)
+        rew_host.copy_(trn.reward, non_blocking=True)
+        torch.cuda.synchronize(dev)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = E * T * ENV_BYTES_PER_TRANSITION / (ms * 1e-3) / 1e9     # this rank's kernel
+        emit_json({
+            "metric": "vmapped System.step env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config3_env_rollouts", "envs": ENV_E, "steps_per_call": T,
+                       "episode_length": ENV_EPISODE, "action_repeat": 1, "parallelism": "envs sharded x%d" % world,
+                       "l2": "inputs+outputs %.2f GB per call >> 126 MB L2" % (E * T * ENV_BYTES_PER_TRANSITION / 1e9)},
+            "math_mode": args.math, "clocks": clk.summary(),
+            "e2e": {"value": ENV_E * T / e2e_s, "unit": "env-steps/s", "ms_per_step": e2e_s * 1e3,
+                    "h2d_bytes_per_step": int(acts_host.numel() * 4), "d2h_bytes_per_step": int(rew_host.numel() * 4),
+                    "api": "VmappedSystemEnv.unroll(actions[T,E,1] from pinned host) -> Transition; rewards to host"},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "hbm", "kernel": "env_rollout_pendulum_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "algorithmic_bytes_per_transition": ENV_BYTES_PER_TRANSITION,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
+            "cpu_baseline": None}, GUARD)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+class _StdoutGuard:
+    """Everything the libraries print (e.g. the NCCL version banner) goes to stderr; only the final
+    JSON line reaches the real stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+_real_print = print
+
+
+def emit_json(obj, guard):
+    sys.stdout.flush()
+    os.write(guard.saved, (json.dumps(obj) + "\n").encode())
 
 
 def main():
@@ -323,15 +486,19 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="config2_batched_icem")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["config3_env_rollouts"], default="config2_batched_icem")
     ap.add_argument("--math", choices=["reference", "theta_carry"], default="reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
-    if args.impl == "reference":
-        run_reference(args, args.workload, wl)
-    else:
-        run_ours(args, args.workload, wl)
+    global GUARD
+    with _StdoutGuard() as GUARD:
+        if args.workload == "config3_env_rollouts":
+            return run_env(args)
+        wl = WORKLOADS[args.workload]
+        if args.impl == "reference":
+            run_reference(args, args.workload, wl)
+        else:
+            run_ours(args, args.workload, wl)
 
 
 if __name__ == "__main__":

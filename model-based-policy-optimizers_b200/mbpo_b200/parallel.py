@@ -36,6 +36,10 @@ def all_gather_blocks(local: torch.Tensor, total: int) -> torch.Tensor:
         return local
     sizes = [shard_bounds(total, r, ws) for r in range(ws)]
     max_rows = max(hi - lo for lo, hi in sizes)
+    if total % ws == 0:                       # equal blocks: gather straight into the result
+        out = torch.empty((total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous())
+        return out
     pad = torch.zeros((max_rows,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     pad[: local.shape[0]] = local
     out = torch.empty((ws * max_rows,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
