@@ -322,7 +322,7 @@ def run_ours(args, wl_name, wl):
 # config 3: vmapped System.step rollouts for SAC/PPO data collection (HBM-bound stream)
 # ------------------------------------------------------------------------------------------------
 ENV_E, ENV_T, ENV_EPISODE = 65536, 1000, 200
-ENV_BYTES_PER_TRANSITION = 4 + 36    # action read; obs 12 + next_obs 12 + reward/discount/truncation 12 written
+ENV_BYTES_PER_TRANSITION = 4 + 24    # action read; next_obs 12 (observation aliases it) + reward/discount/truncation 12 written
 
 
 def run_env(args):
@@ -385,7 +385,8 @@ def run_env(args):
 
     # raw C-ABI launches into preallocated Transition buffers (no allocator traffic in the timed region)
     L = mbpo_b200._lib
-    o = torch.empty((T, E, 3), device=dev); n = torch.empty((T, E, 3), device=dev)
+    buf = torch.empty((T + 1, E, 3), device=dev)      # observation = buf[:T], next_observation = buf[1:]
+    n = buf[1:]
     r = torch.empty((T, E), device=dev); d = torch.empty((T, E), device=dev); tr = torch.empty((T, E), device=dev)
     params = system.pack_params(sp)
     obs, steps, done, first = st.obs.clone(), st.info["steps"].clone(), st.done.clone(), st.info["first_obs"]
@@ -393,7 +394,7 @@ def run_env(args):
     def launch():
         L.check(L.lib.mbpo_env_rollout(system.system_kind, L.C.addressof(params), mbpo_b200.config.math_mode_id, 3, 1,
                                        ENV_EPISODE, 1, L.ptr(obs), L.ptr(steps), L.ptr(done), L.ptr(first),
-                                       L.ptr(acts), E, T, L.ptr(o), L.ptr(r), L.ptr(d), L.ptr(n), L.ptr(tr),
+                                       L.ptr(acts), E, T, None, L.ptr(r), L.ptr(d), L.ptr(n), L.ptr(tr),
                                        L.stream_ptr(dev)))
     for _ in range(max(args.warmup, 3)):
         launch()

@@ -191,7 +191,11 @@ int mbpo_icem_mpc_closed_loop(const MbpoIcemCfg* cfg_host, const void* sys_param
 /* brax_wrapper.py:40-50 + brax_utils/training.py:71-74,91-107,119-137 + sac/acting.py:35-55.
  * In/out env state: obs [E,X], steps [E], done [E] (float, as brax), first_obs [E,X].
  * actions [T,E,A].  Transition outputs are time-major: observation/next_observation
- * [T,E,X], reward/discount/truncation [T,E].  Any output pointer may be NULL. */
+ * [T,E,X], reward/discount/truncation [T,E].  Any output pointer may be NULL.
+ * observation[t] equals next_observation[t-1] (the post-reset state) and observation[0] is the
+ * incoming obs, so a caller that lays both out as overlapping views of one [T+1,E,X] buffer
+ * passes observation_out = NULL and next_observation_out = buffer + E*X (12 B/transition less
+ * HBM traffic for the pendulum); the kernel never reads its outputs. */
 int mbpo_env_rollout(int system_kind, const void* sys_params_host, int math_mode, int x_dim,
                      int action_dim, int episode_length, int action_repeat, float* obs,
                      float* steps, float* done, const float* first_obs, const float* actions,

@@ -10,8 +10,11 @@
 //   BraxWrapper.step        systems/brax_wrapper.py:40-50   system.step(obs, action, params)
 //   actor_step              sac/acting.py:35-55             Transition(obs_prev, action, reward,
 //                                                           1 - done, obs_after_reset, truncation)
-// HBM traffic per transition (pendulum): 4 B action read + 36 B written (obs 12, next_obs 12,
-// reward 4, discount 4, truncation 4); the Transition's `action` field aliases the input.
+// HBM traffic per transition (pendulum): 4 B action read + 24 B written (next_obs 12, reward 4,
+// discount 4, truncation 4).  observation[t] is next_observation[t-1] (the post-reset state), so
+// the host side passes observation_out = NULL and exposes both fields as overlapping views of
+// one [T+1, E, 3] buffer; a separate observation buffer (+12 B) is written only when the caller
+// asks for one.  The Transition's `action` field aliases the caller's input.
 #pragma once
 #include "pendulum.cuh"
 
@@ -25,41 +28,41 @@ struct EnvArgs {
   float* done;           // [E]   in/out
   const float* first_obs;  // [E,3]
   const float* actions;  // [T,E]
-  float* observation_out;       // [T,E,3]
-  float* reward_out;            // [T,E]
-  float* discount_out;          // [T,E]
-  float* next_observation_out;  // [T,E,3]
-  float* truncation_out;        // [T,E]
+  float* observation_out;       // [T,E,3] or NULL
+  float* reward_out;            // [T,E]   or NULL
+  float* discount_out;          // [T,E]   or NULL
+  float* next_observation_out;  // [T,E,3] or NULL
+  float* truncation_out;        // [T,E]   or NULL
 };
 
-constexpr int ENV_CHUNK = 8;   // actions prefetched per thread (registers)
+constexpr int ENV_CHUNK = 8;     // actions prefetched per thread (registers)
+constexpr int ENV_THREADS = 64;   // 1,024 CTAs for 65,536 envs: 6.9 per SM, 1% imbalance (128 threads: 14%)
 
 // Transposes a warp's 32 x 3 floats through shared memory so the [E,3] rows leave as three
-// fully coalesced 128-byte stores.
-__device__ __forceinline__ void warp_store3(float* tile, float* dst_warp, int lane, int valid_rows, float a, float b,
-                                            float c) {
+// fully coalesced 128-byte stores.  dst already points at this lane's first element.
+__device__ __forceinline__ void warp_store3(float* tile, float* dst, int lane, int n_valid, float a, float b, float c) {
   tile[lane * 3] = a;
   tile[lane * 3 + 1] = b;
   tile[lane * 3 + 2] = c;
   __syncwarp();
-  const int n = valid_rows * 3;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const int i = lane + 32 * k;
-    if (i < n) dst_warp[i] = tile[i];
-  }
+  const float v0 = tile[lane], v1 = tile[lane + 32], v2 = tile[lane + 64];
   __syncwarp();
+  if (lane < n_valid) dst[0] = v0;
+  if (lane + 32 < n_valid) dst[32] = v1;
+  if (lane + 64 < n_valid) dst[64] = v2;
 }
 
-template <int MATH>
-__global__ void __launch_bounds__(128) env_rollout_pendulum_kernel(const __grid_constant__ EnvArgs a) {
-  __shared__ float tiles[4][96];
+// OBS: also write the separate observation buffer.  OUT: write next_obs / reward / discount /
+// truncation (all four non-NULL; the C ABI falls back to the checked kernel otherwise).
+template <int MATH, bool OBS>
+__global__ void __launch_bounds__(ENV_THREADS) env_rollout_pendulum_kernel(const __grid_constant__ EnvArgs a) {
+  __shared__ float tiles[ENV_THREADS / 32][96];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = blockIdx.x * ENV_THREADS + threadIdx.x;
   const int warp_e0 = e - lane;
   if (warp_e0 >= a.E) return;
   const bool live = e < a.E;
-  const int valid_rows = (a.E - warp_e0) < 32 ? (a.E - warp_e0) : 32;
+  const int n_valid = ((a.E - warp_e0) < 32 ? (a.E - warp_e0) : 32) * 3;
   const int ee = live ? e : a.E - 1;  // dead lanes shadow the last env, their stores are masked
   const PendulumConsts pc(a.sys);
   float* tile = tiles[warp];
@@ -69,10 +72,23 @@ __global__ void __launch_bounds__(128) env_rollout_pendulum_kernel(const __grid_
   float steps = a.steps[ee], done = a.done[ee];
   const float ep_len = static_cast<float>(a.episode_length);
   const float rep = static_cast<float>(a.action_repeat);
+  const size_t E = static_cast<size_t>(a.E);
+  // theta-carry: the angle lives in a register across steps; [cos, sin] are only outputs
+  float th = (MATH == MBPO_MATH_REFERENCE) ? 0.0f : atan2_bounded(s, c);
+  const float f_th = (MATH == MBPO_MATH_REFERENCE) ? 0.0f : atan2_bounded(f_s, f_c);
+
+  // running pointers, advanced by one time step per iteration
+  const float* p_act = a.actions + ee;
+  float* p_rew = a.reward_out + ee;
+  float* p_dis = a.discount_out + ee;
+  float* p_tru = a.truncation_out + ee;
+  float* p_nxt = a.next_observation_out + static_cast<size_t>(warp_e0) * 3 + lane;
+  float* p_obs = OBS ? a.observation_out + static_cast<size_t>(warp_e0) * 3 + lane : nullptr;
 
   float u_buf[ENV_CHUNK];
 #pragma unroll
-  for (int k = 0; k < ENV_CHUNK; ++k) u_buf[k] = (k < a.T) ? __ldg(a.actions + static_cast<size_t>(k) * a.E + ee) : 0.0f;
+  for (int k = 0; k < ENV_CHUNK; ++k) u_buf[k] = (k < a.T) ? __ldg(p_act + k * E) : 0.0f;
+  p_act += ENV_CHUNK * E;
 
   for (int t0 = 0; t0 < a.T; t0 += ENV_CHUNK) {
     float u_cur[ENV_CHUNK];
@@ -80,44 +96,98 @@ __global__ void __launch_bounds__(128) env_rollout_pendulum_kernel(const __grid_
     for (int k = 0; k < ENV_CHUNK; ++k) u_cur[k] = u_buf[k];
     // prefetch the next chunk while this one computes
 #pragma unroll
-    for (int k = 0; k < ENV_CHUNK; ++k) {
-      const int t = t0 + ENV_CHUNK + k;
-      u_buf[k] = (t < a.T) ? __ldg(a.actions + static_cast<size_t>(t) * a.E + ee) : 0.0f;
-    }
+    for (int k = 0; k < ENV_CHUNK; ++k) u_buf[k] = (t0 + ENV_CHUNK + k < a.T) ? __ldg(p_act + k * E) : 0.0f;
+    p_act += ENV_CHUNK * E;
+    const int kmax = (a.T - t0) < ENV_CHUNK ? (a.T - t0) : ENV_CHUNK;
 #pragma unroll
     for (int k = 0; k < ENV_CHUNK; ++k) {
-      const int t = t0 + k;
-      if (t >= a.T) break;
-      const size_t row = static_cast<size_t>(t) * a.E;
-      // AutoReset pre-step (training.py:120-124)
-      steps = (done != 0.0f) ? 0.0f : steps;
-      done = 0.0f;
-      if (a.observation_out) warp_store3(tile, a.observation_out + (row + warp_e0) * 3, lane, valid_rows, c, s, w);
-      // Episode: action_repeat x system.step with the same action (training.py:92-97)
-      float rew = 0.0f;
-      for (int r = 0; r < a.action_repeat; ++r) {
-        float rr;
-        if (MATH == MBPO_MATH_REFERENCE) {
-          pendulum_step_ref(pc, c, s, w, u_cur[k], rr);
-        } else {
-          float th = atan2_bounded(s, c);
-          pendulum_step_theta(pc, th, w, u_cur[k], rr);
-          sincos_bounded(th, s, c);
+      if (k < kmax) {
+        // AutoReset pre-step (training.py:120-124)
+        steps = (done != 0.0f) ? 0.0f : steps;
+        done = 0.0f;
+        if (OBS) {
+          warp_store3(tile, p_obs, lane, n_valid, c, s, w);
+          p_obs += 3 * E;
         }
-        rew = __fadd_rn(rew, rr);
+        // Episode: action_repeat x system.step with the same action (training.py:92-97)
+        float rew = 0.0f;
+        for (int r = 0; r < a.action_repeat; ++r) {
+          float rr;
+          if (MATH == MBPO_MATH_REFERENCE) pendulum_step_ref(pc, c, s, w, u_cur[k], rr);
+          else pendulum_step_theta(pc, th, w, u_cur[k], rr);
+          rew = __fadd_rn(rew, rr);
+        }
+        if (MATH != MBPO_MATH_REFERENCE) sincos_bounded(th, s, c);
+        steps = __fadd_rn(steps, rep);
+        const bool over = steps >= ep_len;                   // training.py:98-107
+        const float trunc = over ? (1.0f - done) : 0.0f;     // system done is always 0.0
+        done = over ? 1.0f : done;
+        if (over) { c = f_c; s = f_s; w = f_w; th = f_th; }  // training.py:136
+        warp_store3(tile, p_nxt, lane, n_valid, c, s, w);
+        p_nxt += 3 * E;
+        if (live) {
+          *p_rew = rew;
+          *p_dis = 1.0f - done;
+          *p_tru = trunc;
+        }
+        p_rew += E; p_dis += E; p_tru += E;
       }
-      steps = __fadd_rn(steps, rep);
-      const bool over = steps >= ep_len;                   // training.py:98-107
-      const float trunc = over ? (1.0f - done) : 0.0f;     // system done is always 0.0
-      done = over ? 1.0f : done;
-      if (done != 0.0f) { c = f_c; s = f_s; w = f_w; }     // training.py:136
-      if (a.next_observation_out)
-        warp_store3(tile, a.next_observation_out + (row + warp_e0) * 3, lane, valid_rows, c, s, w);
-      if (live) {
-        if (a.reward_out) a.reward_out[row + e] = rew;
-        if (a.discount_out) a.discount_out[row + e] = 1.0f - done;
-        if (a.truncation_out) a.truncation_out[row + e] = trunc;
+    }
+  }
+  if (live) {
+    a.obs[3 * e] = c; a.obs[3 * e + 1] = s; a.obs[3 * e + 2] = w;
+    a.steps[e] = steps;
+    a.done[e] = done;
+  }
+}
+
+// Fully checked variant: any output pointer may be NULL.
+template <int MATH>
+__global__ void __launch_bounds__(ENV_THREADS) env_rollout_pendulum_checked_kernel(const __grid_constant__ EnvArgs a) {
+  __shared__ float tiles[ENV_THREADS / 32][96];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int e = blockIdx.x * ENV_THREADS + threadIdx.x;
+  const int warp_e0 = e - lane;
+  if (warp_e0 >= a.E) return;
+  const bool live = e < a.E;
+  const int n_valid = ((a.E - warp_e0) < 32 ? (a.E - warp_e0) : 32) * 3;
+  const int ee = live ? e : a.E - 1;
+  const PendulumConsts pc(a.sys);
+  float* tile = tiles[warp];
+  float c = a.obs[3 * ee], s = a.obs[3 * ee + 1], w = a.obs[3 * ee + 2];
+  const float f_c = a.first_obs[3 * ee], f_s = a.first_obs[3 * ee + 1], f_w = a.first_obs[3 * ee + 2];
+  float steps = a.steps[ee], done = a.done[ee];
+  const float ep_len = static_cast<float>(a.episode_length);
+  const float rep = static_cast<float>(a.action_repeat);
+  for (int t = 0; t < a.T; ++t) {
+    const size_t row = static_cast<size_t>(t) * a.E;
+    const float u = __ldg(a.actions + row + ee);
+    steps = (done != 0.0f) ? 0.0f : steps;
+    done = 0.0f;
+    if (a.observation_out) warp_store3(tile, a.observation_out + (row + warp_e0) * 3 + lane, lane, n_valid, c, s, w);
+    float rew = 0.0f;
+    for (int r = 0; r < a.action_repeat; ++r) {
+      float rr;
+      if (MATH == MBPO_MATH_REFERENCE) {
+        pendulum_step_ref(pc, c, s, w, u, rr);
+      } else {
+        float th = atan2_bounded(s, c);
+        pendulum_step_theta(pc, th, w, u, rr);
+        sincos_bounded(th, s, c);
       }
+      rew = __fadd_rn(rew, rr);
+    }
+    steps = __fadd_rn(steps, rep);
+    const bool over = steps >= ep_len;
+    const float trunc = over ? (1.0f - done) : 0.0f;
+    done = over ? 1.0f : done;
+    if (over) { c = f_c; s = f_s; w = f_w; }
+    if (a.next_observation_out)
+      warp_store3(tile, a.next_observation_out + (row + warp_e0) * 3 + lane, lane, n_valid, c, s, w);
+    if (live) {
+      if (a.reward_out) a.reward_out[row + e] = rew;
+      if (a.discount_out) a.discount_out[row + e] = 1.0f - done;
+      if (a.truncation_out) a.truncation_out[row + e] = trunc;
     }
   }
   if (live) {

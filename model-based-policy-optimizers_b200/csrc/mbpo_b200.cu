@@ -526,10 +526,18 @@ int mbpo_env_rollout(int system_kind, const void* sys_params_host, int math_mode
   a.obs = obs; a.steps = steps; a.done = done; a.first_obs = first_obs; a.actions = actions;
   a.observation_out = observation_out; a.reward_out = reward_out; a.discount_out = discount_out;
   a.next_observation_out = next_observation_out; a.truncation_out = truncation_out;
-  const int threads = 128;
-  const unsigned blocks = static_cast<unsigned>((E + threads - 1) / threads);
-  if (math_mode == 0) env_rollout_pendulum_kernel<0><<<blocks, threads, 0, as_stream(stream)>>>(a);
-  else env_rollout_pendulum_kernel<1><<<blocks, threads, 0, as_stream(stream)>>>(a);
+  const unsigned blocks = static_cast<unsigned>((E + ENV_THREADS - 1) / ENV_THREADS);
+  cudaStream_t st = as_stream(stream);
+  const bool all_out = reward_out && discount_out && next_observation_out && truncation_out;
+  const int sel = (all_out ? (observation_out ? 2 : 1) : 0) * 2 + math_mode;
+  switch (sel) {
+    case 0: env_rollout_pendulum_checked_kernel<0><<<blocks, ENV_THREADS, 0, st>>>(a); break;
+    case 1: env_rollout_pendulum_checked_kernel<1><<<blocks, ENV_THREADS, 0, st>>>(a); break;
+    case 2: env_rollout_pendulum_kernel<0, false><<<blocks, ENV_THREADS, 0, st>>>(a); break;
+    case 3: env_rollout_pendulum_kernel<1, false><<<blocks, ENV_THREADS, 0, st>>>(a); break;
+    case 4: env_rollout_pendulum_kernel<0, true><<<blocks, ENV_THREADS, 0, st>>>(a); break;
+    default: env_rollout_pendulum_kernel<1, true><<<blocks, ENV_THREADS, 0, st>>>(a); break;
+  }
   return check_launch("env_rollout_pendulum_kernel");
 }
 

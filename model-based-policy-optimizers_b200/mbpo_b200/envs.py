@@ -56,7 +56,8 @@ class VmappedSystemEnv:
 
     def unroll(self, state: EnvState, actions: torch.Tensor):
         """actions [T, E, A] -> (final EnvState, Transition with fields [T, E, ...]); extras
-        carries state_extras.truncation like actor_step (acting.py:46-55)."""
+        carries state_extras.truncation like actor_step (acting.py:46-55).  observation and
+        next_observation are overlapping views of one buffer (treat them as read-only)."""
         acts = actions.to(torch.float32).contiguous()
         T, E, A = acts.shape
         X = self.system.x_dim
@@ -65,8 +66,10 @@ class VmappedSystemEnv:
         steps = state.info["steps"].clone()
         done = state.done.clone()
         first = state.info["first_obs"].contiguous()
-        o = torch.empty((T, E, X), dtype=torch.float32, device=dev)
-        n = torch.empty((T, E, X), dtype=torch.float32, device=dev)
+        # observation[t] = next_observation[t-1]: both are views of one [T+1, E, X] buffer
+        buf = torch.empty((T + 1, E, X), dtype=torch.float32, device=dev)
+        buf[0].copy_(obs)
+        o, n = buf[:T], buf[1:]
         r = torch.empty((T, E), dtype=torch.float32, device=dev)
         d = torch.empty((T, E), dtype=torch.float32, device=dev)
         tr = torch.empty((T, E), dtype=torch.float32, device=dev)
@@ -75,7 +78,7 @@ class VmappedSystemEnv:
             _lib.check(_lib.lib.mbpo_env_rollout(
                 self.system.system_kind, _lib.C.addressof(params), config.math_mode_id, X, A, self.episode_length,
                 self.action_repeat, _lib.ptr(obs), _lib.ptr(steps), _lib.ptr(done), _lib.ptr(first), _lib.ptr(acts),
-                E, T, _lib.ptr(o), _lib.ptr(r), _lib.ptr(d), _lib.ptr(n), _lib.ptr(tr), _lib.stream_ptr(dev)))
+                E, T, None, _lib.ptr(r), _lib.ptr(d), _lib.ptr(n), _lib.ptr(tr), _lib.stream_ptr(dev)))
         new_state = EnvState(obs=obs, reward=r[-1] if T else state.reward, done=done,
                              system_params=state.system_params,
                              info=dict(steps=steps, truncation=tr[-1] if T else state.info["truncation"],
