@@ -44,7 +44,8 @@ UNIT = "transitions/s"
 # Thread-level instructions the fused plan kernel executes per transition on the default
 # workload, measured with ncu (smsp__thread_inst_executed.sum / transitions; profiles/).  Used
 # for roofline.achieved = executed lane-instructions per second; see DESIGN.md.
-LANE_INSTR_PER_TRANSITION = {"config2_batched_icem": None}
+LANE_INSTR_PER_TRANSITION = {("config2_batched_icem", "reference"): 229.7,
+                             ("config2_batched_icem", "theta_carry"): 185.1}
 
 
 def transitions_per_step(B, horizon, p):
@@ -277,7 +278,7 @@ def run_ours(args, wl_name, wl):
             pass
         sm_max = float(peaks.get("sm_max_mhz", 1965.0))
         issue_peak = 148 * 4 * 32 * sm_max * 1e6 / 1e12          # T lane-instr/s
-        ipt = LANE_INSTR_PER_TRANSITION.get(wl_name)
+        ipt = LANE_INSTR_PER_TRANSITION.get((wl_name, args.math))
         kernel_ms = ms_per_step                                   # one fused kernel per step: event time = launch time
         roofline = {
             "bound": "issue", "kernel": "icem_plan_pendulum_kernel",
