@@ -207,6 +207,14 @@ int mbpo_env_rollout(int system_kind, const void* sys_params_host, int math_mode
 int mbpo_mlp_dynamics_forward(const MbpoMlpEnsembleParams* params_host, const float* inp,
                               const int32_t* member, int R, float* delta_out, void* stream);
 
+/* vmap(vmap(rollout_actions)) + the particle summary of iCemTO.objective (icem_optimizer.py:155-160)
+ * through the learned ensemble System: particle p is rolled through ensemble member p
+ * (num_particles == num_members), x_next = x + MLP_p([x, u]), reward = pendulum reward on (x, u).
+ * x0 [B,X]; actions [B,M,H,A]; returns_out [B,M] = mean (MBPO_SUMMARIZE_MEAN) or max over members of
+ * the horizon-mean reward.  One fused tcgen05 kernel (CTA pairs, weights resident in shared memory). */
+int mbpo_ensemble_rollout(const MbpoMlpEnsembleParams* params_host, int horizon, const float* x0,
+                          const float* actions, int B, int M, int summarize, float* returns_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,7 @@
 #include "host_util.h"
 #include "mlp_kernels.cuh"
 #include "mlp_tc_kernels.cuh"
+#include "ensemble_kernels.cuh"
 #include "plan_dispatch.h"
 #include "staged_kernels.cuh"
 
@@ -334,8 +335,15 @@ int mbpo_system_step(int system_kind, const void* sys_params_host, int math_mode
 int mbpo_rollout_actions(int system_kind, const void* sys_params_host, int math_mode, int horizon, int action_dim,
                          int x_dim, const float* x0, const float* actions, int B, int M, float* returns_out,
                          float* obs_out, float* reward_out, float* next_obs_out, void* stream) {
+  if (system_kind == MBPO_SYSTEM_MLP_ENSEMBLE) {
+    if (obs_out || reward_out || next_obs_out)
+      return fail(MBPO_EUNSUPPORTED, "rollout_actions: the ensemble System returns objectives only (no Transition buffers)");
+    MBPO_REQUIRE(action_dim == 1 && x_dim == 3, "rollout_actions: ensemble System needs action_dim == 1, x_dim == 3");
+    return mbpo_ensemble_rollout(static_cast<const MbpoMlpEnsembleParams*>(sys_params_host), horizon, x0, actions, B, M,
+                                 MBPO_SUMMARIZE_MEAN, returns_out, stream);
+  }
   if (system_kind != MBPO_SYSTEM_PENDULUM)
-    return fail(MBPO_EUNSUPPORTED, "rollout_actions: only MBPO_SYSTEM_PENDULUM has an inlined step");
+    return fail(MBPO_EUNSUPPORTED, "rollout_actions: unknown system_kind %d", system_kind);
   MBPO_REQUIRE(sys_params_host && x0 && actions, "rollout_actions: null pointer");
   MBPO_REQUIRE(action_dim == 1 && x_dim == 3, "rollout_actions: pendulum needs action_dim == 1, x_dim == 3");
   MBPO_REQUIRE(horizon >= 1 && horizon <= 4096, "rollout_actions: horizon %d outside [1, 4096]", horizon);
@@ -558,6 +566,19 @@ int mbpo_mlp_dynamics_forward(const MbpoMlpEnsembleParams* p, const float* inp, 
                                                  sizeof(g_err));
   if (rc != MBPO_OK) return rc;
   return check_launch("mlp_dynamics_forward");
+}
+
+int mbpo_ensemble_rollout(const MbpoMlpEnsembleParams* p, int horizon, const float* x0, const float* actions, int B,
+                          int M, int summarize, float* returns_out, void* stream) {
+  MBPO_REQUIRE(p && x0 && actions && returns_out, "ensemble_rollout: null pointer");
+  MBPO_REQUIRE(p->w_in && p->b_in && p->w_h && p->b_h && p->w_out && p->b_out, "ensemble_rollout: null weights");
+  MBPO_REQUIRE(horizon >= 1 && B >= 0 && M >= 0, "ensemble_rollout: bad sizes");
+  MBPO_REQUIRE(summarize == 0 || summarize == 1, "ensemble_rollout: bad summarize %d", summarize);
+  if (static_cast<long long>(B) * M == 0) return MBPO_OK;
+  const int rc = ens::launch_ensemble_rollout(*p, horizon, x0, actions, B, M, summarize, returns_out,
+                                              as_stream(stream), g_err, sizeof(g_err));
+  if (rc != MBPO_OK) return rc;
+  return check_launch("ensemble_rollout_kernel");
 }
 
 }  // extern "C"

@@ -1,7 +1,8 @@
 """mbpo.systems work-alike (mbpo/systems/__init__.py:1-4)."""
 from .base_systems import System, SystemParams, SystemState
+from .mlp_ensemble_system import MLPEnsembleSystem, MlpEnsembleDynamicsParams
 from .pendulum_system import (PendulumDynamics, PendulumDynamicsParams, PendulumReward, PendulumRewardParams,
                               PendulumSystem)
 
-__all__ = ["System", "SystemParams", "SystemState", "PendulumSystem", "PendulumDynamics", "PendulumDynamicsParams",
+__all__ = ["MLPEnsembleSystem", "MlpEnsembleDynamicsParams", "System", "SystemParams", "SystemState", "PendulumSystem", "PendulumDynamics", "PendulumDynamicsParams",
            "PendulumReward", "PendulumRewardParams"]

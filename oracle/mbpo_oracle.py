@@ -309,6 +309,37 @@ def mlp_ensemble_step(x, u, member, params: MlpEnsembleParams, bf16: bool = Fals
     return x_next, reward
 
 
+def ensemble_rollout_returns(x0, actions, params: MlpEnsembleParams, bf16: bool = True, use_max: bool = False):
+    """vmap(objective) through the learned ensemble (icem_optimizer.py:144-160): x0[B,3],
+    actions[B,M,H] -> [B,M].  Particle p is rolled through member p; the objective is the
+    mean (or max) over members of the horizon-mean reward (left-to-right float32 sums)."""
+    x0 = np.asarray(x0, dtype=F32)
+    actions = np.asarray(actions, dtype=F32)
+    b, m, h = actions.shape
+    rows = b * m
+    acts = actions.reshape(rows, h)
+    per_member = []
+    for e in range(params.num_members):
+        x = np.repeat(x0, m, axis=0).copy()
+        member = np.full(rows, e, dtype=np.int32)
+        acc = np.zeros(rows, dtype=F32)
+        for t in range(h):
+            xn, r = mlp_ensemble_step(x, acts[:, t], member, params, bf16)
+            acc = (acc + r).astype(F32)
+            x = xn
+        per_member.append((acc / F32(h)).astype(F32))
+    if use_max:
+        out = per_member[0]
+        for r in per_member[1:]:
+            out = np.maximum(out, r)
+    else:
+        out = np.zeros(rows, dtype=F32)
+        for r in per_member:
+            out = (out + r).astype(F32)
+        out = (out / F32(params.num_members)).astype(F32)
+    return out.reshape(b, m)
+
+
 # ----------------------------------------------------------------------------------
 # rollout_actions  (optimizer_utils.py:11-59), batched over rows
 # ----------------------------------------------------------------------------------

@@ -522,6 +522,49 @@ def test_mlp_dynamics_forward(mb, cuda_device):
     assert np.abs(out.cpu().numpy() - full).max() < 5e-2                            # bf16 vs fp32 network
 
 
+def _ensemble_on_device(mb, cuda_device, ens):
+    from mbpo_b200.systems import MLPEnsembleSystem, MlpEnsembleDynamicsParams, SystemParams, PendulumRewardParams
+    d = lambda a: _dev(a, cuda_device)
+    dyn = MlpEnsembleDynamicsParams(weights=[d(w) for w in ens.weights], biases=[d(b) for b in ens.biases])
+    return MLPEnsembleSystem(), SystemParams(dynamics_params=dyn, reward_params=PendulumRewardParams())
+
+
+@pytest.mark.parametrize("B,M,H", [(1, 256, 5), (3, 139, 12), (2, 527, 8)])
+def test_ensemble_rollout_fused_tcgen05(mb, cuda_device, B, M, H):
+    """Fused cta_group::2 rollout kernel against the oracle (same bf16 operand rounding, fp32 accumulate)."""
+    ens = orc.make_mlp_ensemble(seed=3, members=5)
+    sys_, sp = _ensemble_on_device(mb, cuda_device, ens)
+    x0 = _random_states(B, 71)
+    acts = np.clip(np.random.default_rng(72).normal(0, 0.5, (B, M, H, 1)), -1, 1).astype(np.float32)
+    got = sys_.ensemble_returns(sp, _dev(x0, cuda_device), _dev(acts, cuda_device)).cpu().numpy()
+    want = orc.ensemble_rollout_returns(x0, acts[..., 0], ens, bf16=True)
+    # a flipped bf16 rounding of one activation moves a step's delta by ~1e-4 relative; errors accumulate over H
+    np.testing.assert_allclose(got, want, rtol=5e-3, atol=5e-3)
+    assert np.abs(got - want).mean() < 5e-4
+    got_max = sys_.ensemble_returns(sp, _dev(x0, cuda_device), _dev(acts, cuda_device), use_optimism=True).cpu().numpy()
+    want_max = orc.ensemble_rollout_returns(x0, acts[..., 0], ens, bf16=True, use_max=True)
+    np.testing.assert_allclose(got_max, want_max, rtol=5e-3, atol=5e-3)
+    assert np.all(got_max >= got - 1e-6)
+    # the rollout_actions ABI routes the ensemble System to the same kernel
+    from mbpo_b200.utils import rollout_returns
+    again = rollout_returns(sys_, sp, _dev(x0, cuda_device), _dev(acts, cuda_device)).cpu().numpy()
+    assert np.array_equal(again, got)
+
+
+def test_ensemble_system_step_matches_forward_kernel(mb, cuda_device):
+    ens = orc.make_mlp_ensemble(seed=3, members=5)
+    sys_, sp = _ensemble_on_device(mb, cuda_device, ens)
+    R = 700
+    x = _random_states(R, 73)
+    u = np.random.default_rng(74).uniform(-1, 1, (R, 1)).astype(np.float32)
+    member = (np.arange(R) // 128 % 5).astype(np.int32)                       # homogeneous tiles
+    sp2 = sp.replace(dynamics_params=sp.dynamics_params.replace(member=_dev(member, cuda_device)))
+    st = sys_.step(_dev(x, cuda_device), _dev(u, cuda_device), sp2)
+    xn, r = orc.mlp_ensemble_step(x, u[:, 0], member, ens, bf16=True)
+    np.testing.assert_allclose(st.x_next.cpu().numpy(), xn, rtol=2e-3, atol=2e-4)
+    np.testing.assert_allclose(st.reward.cpu().numpy(), r, rtol=1e-5, atol=3e-6)
+
+
 # ---------------------------------------------------------------------------------------------
 # error behaviour: no fallback, loud failures
 # ---------------------------------------------------------------------------------------------
