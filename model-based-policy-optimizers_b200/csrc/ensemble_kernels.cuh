@@ -7,7 +7,7 @@
 // with particle p rolled through ensemble member p (num_particles == num_members).
 //
 // A CTA PAIR (thread-block cluster of 2, tcgen05 cta_group::2) owns 256 candidate rows; each
-// CTA's 128 threads own 128 rows = its 128 TMEM lanes.  For every member e the pair keeps BOTH
+// CTA owns 128 rows = its 128 TMEM lanes, four threads per row (one per quarter of the hidden units).  For every member e the pair keeps BOTH
 // hidden-layer weight matrices resident in shared memory for the whole horizon, split along N
 // across the pair (each CTA holds W[e,l][128 rows of N, 256 K] = 64 KB per layer, fetched by TMA as
 // 32 K-chunk slabs), so the only per-step traffic is the action stream.  Per horizon step:
@@ -29,6 +29,8 @@ namespace ens {
 
 using namespace tc;
 
+constexpr int ENS_THREADS = 512;              // four threads per row: warps 4q..4q+3 own accumulator columns [64q, 64q+64)
+constexpr int ENS_SPLIT = ENS_THREADS / 128;  // threads per row
 constexpr uint32_t WH_BYTES = 128 * HID * 2;  // one layer's N-half: 65536
 constexpr uint32_t WH_LBO = 128 * 16;         // 2048: next K-chunk of a weight half
 
@@ -41,7 +43,8 @@ struct Smem {
   static constexpr uint32_t B_H = B_IN + HID * 4;         // float [2][256]
   static constexpr uint32_t W_OUT = B_H + 2 * HID * 4;    // float [256][4]
   static constexpr uint32_t B_OUT = W_OUT + HID * 4 * 4;  // float [4]
-  static constexpr uint32_t BARS = B_OUT + 16;            // bar_w, bar_mma, bar_a
+  static constexpr uint32_t DELTA = B_OUT + 16;           // float4 [ENS_SPLIT][128]: partial output-layer sums
+  static constexpr uint32_t BARS = DELTA + ENS_SPLIT * TILE_M * 16;  // bar_w, bar_mma, bar_a
   static constexpr uint32_t TMEM_PTR = BARS + 32;
   static constexpr uint32_t TOTAL = TMEM_PTR + 16;
 };
@@ -59,6 +62,15 @@ struct EnsArgs {
   float* returns_out;   // [R]
   MbpoPendulumParams reward;
 };
+
+// swish(z) = z * sigmoid(z) with sigmoid(z) = 0.5 + 0.5 * tanh(z / 2): one MUFU (tanh.approx) instead of
+// two (ex2 + rcp); the activation pipeline is MUFU-throughput bound.  |error| <= ~2.5e-4 * |z|, well
+// inside the bf16 rounding (2^-9 relative) the activations receive next.
+__device__ __forceinline__ float swish_tanh(float z) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z));
+  return z * fmaf(t, 0.5f, 0.5f);
+}
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -108,10 +120,12 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
       : "memory");
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TILE_M, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ENS_THREADS, 1)
     ensemble_rollout_kernel(const __grid_constant__ EnsArgs a, const __grid_constant__ CUtensorMap w_map) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int lrow = tid & (TILE_M - 1);   // row within the CTA's tile = TMEM lane
+  const int half = tid >> 7;             // which 256 / ENS_SPLIT hidden units / accumulator columns this thread owns
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   float* s_w_in = reinterpret_cast<float*>(smem + Smem::W_IN);
@@ -119,6 +133,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TILE_M, 1)
   float* s_b_h = reinterpret_cast<float*>(smem + Smem::B_H);
   float* s_w_out = reinterpret_cast<float*>(smem + Smem::W_OUT);
   float* s_b_out = reinterpret_cast<float*>(smem + Smem::B_OUT);
+  float4* s_delta = reinterpret_cast<float4*>(smem + Smem::DELTA);
   uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + Smem::BARS);  // weights landed (this CTA)
   uint64_t* bar_mma = bar_w + 1;                                     // accumulator complete (multicast commit)
   uint64_t* bar_a = bar_w + 2;                                       // leader only: both CTAs' A tiles written
@@ -141,7 +156,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TILE_M, 1)
   cluster_sync();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + half * (HID / ENS_SPLIT);
   const uint32_t a_addr = smem_u32(smem + Smem::A);
   const uint32_t w_addr[2] = {smem_u32(smem + Smem::W1), smem_u32(smem + Smem::W2)};
   const uint32_t bar_a_leader = map_to_cta(smem_u32(bar_a), 0);
@@ -153,7 +168,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TILE_M, 1)
 
   const int num_groups = (a.R + 2 * TILE_M - 1) / (2 * TILE_M);
   for (int group = blockIdx.x >> 1; group < num_groups; group += gridDim.x >> 1) {
-    const int row = group * 2 * TILE_M + static_cast<int>(rank) * TILE_M + tid;
+    const int row = group * 2 * TILE_M + static_cast<int>(rank) * TILE_M + lrow;
     const bool valid = row < a.R;
     const int rr = valid ? row : a.R - 1;
     const int b = rr / a.M;
@@ -171,10 +186,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TILE_M, 1)
             tma_load_2d(smem + (l ? Smem::W2 : Smem::W1) + kc * WH_LBO, &w_map, kc * 8,
                         (e * 2 + l) * HID + static_cast<int>(rank) * 128, bar_w);
       }
-      for (int i = tid; i < 4 * HID; i += TILE_M) s_w_in[i] = a.w_in[static_cast<size_t>(e) * 4 * HID + i];
-      for (int i = tid; i < HID; i += TILE_M) s_b_in[i] = a.b_in[e * HID + i];
-      for (int i = tid; i < 2 * HID; i += TILE_M) s_b_h[i] = a.b_h[e * 2 * HID + i];
-      for (int i = tid; i < HID * 3; i += TILE_M) s_w_out[(i / 3) * 4 + (i % 3)] = a.w_out[static_cast<size_t>(e) * HID * 3 + i];
+      for (int i = tid; i < 4 * HID; i += ENS_THREADS) s_w_in[i] = a.w_in[static_cast<size_t>(e) * 4 * HID + i];
+      for (int i = tid; i < HID; i += ENS_THREADS) s_b_in[i] = a.b_in[e * HID + i];
+      for (int i = tid; i < 2 * HID; i += ENS_THREADS) s_b_h[i] = a.b_h[e * 2 * HID + i];
+      for (int i = tid; i < HID * 3; i += ENS_THREADS) s_w_out[(i / 3) * 4 + (i % 3)] = a.w_out[static_cast<size_t>(e) * HID * 3 + i];
       if (tid < 3) s_b_out[tid] = a.b_out[e * 3 + tid];
       mbar_wait(bar_w, phase_w);  // every thread observes the TMA completion (async-proxy writes visible)
       phase_w ^= 1;
@@ -189,7 +204,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TILE_M, 1)
         acc = __fadd_rn(acc, reward_from(pc, atan2_bounded(x[1], x[0]), x[2], u));
         // ---- layer 0 on CUDA cores ---------------------------------------------------------------
 #pragma unroll 2
-        for (int kc = 0; kc < KCHUNKS; ++kc) {
+        for (int kc = half * (KCHUNKS / ENS_SPLIT); kc < (half + 1) * (KCHUNKS / ENS_SPLIT); ++kc) {
           float h[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -199,12 +214,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TILE_M, 1)
             v = fmaf(x[1], s_w_in[HID + n], v);
             v = fmaf(x[2], s_w_in[2 * HID + n], v);
             v = fmaf(u, s_w_in[3 * HID + n], v);
-            h[j] = swish_f(v);
+            h[j] = swish_tanh(v);
           }
           uint4 pk;
           pk.x = pack_bf16(h[0], h[1]); pk.y = pack_bf16(h[2], h[3]);
           pk.z = pack_bf16(h[4], h[5]); pk.w = pack_bf16(h[6], h[7]);
-          *reinterpret_cast<uint4*>(smem + Smem::A + kc * A_LBO + tid * 16) = pk;
+          *reinterpret_cast<uint4*>(smem + Smem::A + kc * A_LBO + lrow * 16) = pk;
         }
         float delta[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll 1
@@ -232,24 +247,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TILE_M, 1)
           // ---- epilogue ---------------------------------------------------------------------------------
           const float* bias = s_b_h + layer * HID;
 #pragma unroll 1
-          for (int c = 0; c < HID / 32; ++c) {
+          for (int c = 0; c < HID / 32 / ENS_SPLIT; ++c) {
+            const int cg = half * (HID / 32 / ENS_SPLIT) + c;        // global 32-column chunk
             uint32_t v[32];
             tmem_ld32(tmem_row + c * 32, v);
             float h[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) h[j] = swish_f(__uint_as_float(v[j]) + bias[c * 32 + j]);
+            for (int j = 0; j < 32; ++j) h[j] = swish_tanh(__uint_as_float(v[j]) + bias[cg * 32 + j]);
             if (layer == 0) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 uint4 pk;
                 pk.x = pack_bf16(h[q * 8 + 0], h[q * 8 + 1]); pk.y = pack_bf16(h[q * 8 + 2], h[q * 8 + 3]);
                 pk.z = pack_bf16(h[q * 8 + 4], h[q * 8 + 5]); pk.w = pack_bf16(h[q * 8 + 6], h[q * 8 + 7]);
-                *reinterpret_cast<uint4*>(smem + Smem::A + (c * 4 + q) * A_LBO + tid * 16) = pk;
+                *reinterpret_cast<uint4*>(smem + Smem::A + (cg * 4 + q) * A_LBO + lrow * 16) = pk;
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                const float4 wo = *reinterpret_cast<const float4*>(s_w_out + (c * 32 + j) * 4);
+                const float4 wo = *reinterpret_cast<const float4*>(s_w_out + (cg * 32 + j) * 4);
                 delta[0] = fmaf(h[j], wo.x, delta[0]);
                 delta[1] = fmaf(h[j], wo.y, delta[1]);
                 delta[2] = fmaf(h[j], wo.z, delta[2]);
@@ -260,16 +276,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TILE_M, 1)
         // the next step's layer 0 overwrites A only after this CTA's MMA reads completed (bar_mma) and
         // tcgen05.ld of D completed (tcgen05.wait::ld inside tmem_ld32); D is rewritten only after the
         // next "A ready" handshake, which every thread precedes with tcgen05.fence::before_thread_sync.
-        x[0] = __fadd_rn(x[0], delta[0] + s_b_out[0]);
-        x[1] = __fadd_rn(x[1], delta[1] + s_b_out[1]);
-        x[2] = __fadd_rn(x[2], delta[2] + s_b_out[2]);
+        // combine the column quarters of the output layer (fixed order: q0 + q1 + ... + bias)
+        s_delta[half * TILE_M + lrow] = make_float4(delta[0], delta[1], delta[2], 0.0f);
+        __syncthreads();
+        float4 d = s_delta[lrow];
+#pragma unroll
+        for (int q = 1; q < ENS_SPLIT; ++q) {
+          const float4 dq = s_delta[q * TILE_M + lrow];
+          d.x += dq.x; d.y += dq.y; d.z += dq.z;
+        }
+        x[0] = __fadd_rn(x[0], d.x + s_b_out[0]);
+        x[1] = __fadd_rn(x[1], d.y + s_b_out[1]);
+        x[2] = __fadd_rn(x[2], d.z + s_b_out[2]);
       }
       const float ret = __fdiv_rn(acc, static_cast<float>(a.H));
       if (a.summarize == MBPO_SUMMARIZE_MAX) summary = (e == 0) ? ret : fmaxf(summary, ret);
       else summary = __fadd_rn(summary, ret);
     }
     if (a.summarize != MBPO_SUMMARIZE_MAX) summary = __fdiv_rn(summary, static_cast<float>(a.num_members));
-    if (valid) a.returns_out[row] = summary;
+    if (valid && half == 0) a.returns_out[row] = summary;
   }
 
   // ---- teardown --------------------------------------------------------------------------------------
@@ -322,7 +347,7 @@ inline int launch_ensemble_rollout(const MbpoMlpEnsembleParams& p, int horizon, 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int groups = (a.R + 2 * TILE_M - 1) / (2 * TILE_M);
   const int pairs = groups < sms / 2 ? groups : sms / 2;
-  ensemble_rollout_kernel<<<2 * pairs, TILE_M, Smem::TOTAL, st>>>(a, map);
+  ensemble_rollout_kernel<<<2 * pairs, ENS_THREADS, Smem::TOTAL, st>>>(a, map);
   return MBPO_OK;
 }
 

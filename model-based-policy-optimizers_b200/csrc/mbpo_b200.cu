@@ -439,8 +439,15 @@ int mbpo_icem_plan_staged(const MbpoIcemCfg* cfg, const void* sys_params_host, c
                    workspace,
                "plan_staged: null pointer");
   MBPO_REQUIRE(B >= 0 && B <= 65535, "plan_staged: B %d outside [0, 65535]", B);
-  if (cfg->system_kind != MBPO_SYSTEM_PENDULUM)
-    return fail(MBPO_EUNSUPPORTED, "plan_staged: only MBPO_SYSTEM_PENDULUM has an inlined step");
+  if (cfg->system_kind != MBPO_SYSTEM_PENDULUM && cfg->system_kind != MBPO_SYSTEM_MLP_ENSEMBLE)
+    return fail(MBPO_EUNSUPPORTED, "plan_staged: unknown system_kind %d", cfg->system_kind);
+  if (cfg->system_kind == MBPO_SYSTEM_MLP_ENSEMBLE) {
+    const MbpoMlpEnsembleParams* ep = static_cast<const MbpoMlpEnsembleParams*>(sys_params_host);
+    if (cfg->num_particles != ep->num_members)
+      return fail(MBPO_EUNSUPPORTED, "plan_staged: the ensemble System rolls particle p through member p; "
+                  "num_particles (%d) must equal num_members (%d)", cfg->num_particles, ep->num_members);
+    MBPO_REQUIRE(cfg->action_dim == 1 && cfg->x_dim == 3, "plan_staged: ensemble System needs action_dim == 1, x_dim == 3");
+  }
   if (workspace_bytes < mbpo_icem_workspace_bytes(cfg, B))
     return fail(MBPO_EWORKSPACE, "plan_staged: workspace %zu B < required %zu B", workspace_bytes,
                 mbpo_icem_workspace_bytes(cfg, B));
@@ -479,16 +486,24 @@ int mbpo_icem_plan_staged(const MbpoIcemCfg* cfg, const void* sys_params_host, c
     const int nxt = cur ^ 1;
     rc = mbpo_icem_sample_actions(cfg, ckey[cur], mean[cur], std_[cur], B, actions, ckey[nxt], nullptr, stream);
     if (rc != MBPO_OK) return rc;
-    rc = mbpo_rollout_actions(cfg->system_kind, sys_params_host, cfg->math_mode, cfg->horizon, cfg->action_dim,
-                              cfg->x_dim, x0, actions, B, static_cast<int>(M), values, nullptr, nullptr, nullptr,
-                              stream);
-    if (rc != MBPO_OK) return rc;
-    if (cfg->num_particles > 1 && cfg->summarize == MBPO_SUMMARIZE_MEAN) {
-      const long long n = static_cast<long long>(b * M);
-      summarize_particles_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(values, n, cfg->num_particles,
-                                                                                         cfg->summarize);
-      rc = check_launch("summarize_particles_kernel");
+    if (cfg->system_kind == MBPO_SYSTEM_MLP_ENSEMBLE) {
+      // particles = ensemble members; the kernel summarises over them itself (:160)
+      rc = mbpo_ensemble_rollout(static_cast<const MbpoMlpEnsembleParams*>(sys_params_host), cfg->horizon, x0, actions,
+                                 B, static_cast<int>(M), cfg->summarize, values, stream);
       if (rc != MBPO_OK) return rc;
+    } else {
+      rc = mbpo_rollout_actions(cfg->system_kind, sys_params_host, cfg->math_mode, cfg->horizon, cfg->action_dim,
+                                cfg->x_dim, x0, actions, B, static_cast<int>(M), values, nullptr, nullptr, nullptr,
+                                stream);
+      if (rc != MBPO_OK) return rc;
+      if (cfg->num_particles > 1 && cfg->summarize == MBPO_SUMMARIZE_MEAN) {
+        const long long n = static_cast<long long>(b * M);
+        summarize_particles_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(values, n,
+                                                                                           cfg->num_particles,
+                                                                                           cfg->summarize);
+        rc = check_launch("summarize_particles_kernel");
+        if (rc != MBPO_OK) return rc;
+      }
     }
     rc = mbpo_icem_elite_refit(cfg, actions, values, mean[cur], std_[cur], bval[cur], bseq[cur], B, mean[nxt],
                                std_[nxt], bval[nxt], bseq[nxt], nullptr, stream);

@@ -56,9 +56,34 @@ class _Packed:
 class MLPEnsembleSystem(System):
     system_kind = _lib.SYSTEM_MLP_ENSEMBLE
 
-    def __init__(self, x_dim: int = 3, u_dim: int = 1):
+    def __init__(self, x_dim: int = 3, u_dim: int = 1, num_members: int = 5, hidden: int = 256,
+                 dynamics_params: Optional[MlpEnsembleDynamicsParams] = None,
+                 reward_params: Optional[PendulumRewardParams] = None):
         super().__init__(x_dim=x_dim, u_dim=u_dim)
+        self.num_members = num_members
+        self.hidden = hidden
+        self.dynamics_params = dynamics_params
+        self.reward_params = reward_params or PendulumRewardParams()
         self._cache = None
+
+    def init_params(self, key: torch.Tensor) -> SystemParams:
+        """System.init_params (base_systems.py:54-60): keys = split(key, 3).  The dynamics parameters are
+        the ones given to the constructor, or a random initialisation (N(0, 1/fan_in)) drawn from keys[0]."""
+        from .. import random as jr
+        keys = jr.split(key, 3)
+        k_dyn = keys[..., 0, :].reshape(-1, 2)[0]
+        dyn = self.dynamics_params
+        if dyn is None:
+            dims = (self.x_dim + self.u_dim, self.hidden, self.hidden, self.hidden, self.x_dim)
+            lk = jr.split(k_dyn, 4)
+            ws, bs = [], []
+            for i in range(4):
+                n = self.num_members * dims[i] * dims[i + 1]
+                w = jr.normal(lk[i], n).reshape(self.num_members, dims[i], dims[i + 1]) / (dims[i] ** 0.5)
+                ws.append(w * (0.1 if i == 3 else 1.0))
+                bs.append(torch.zeros((self.num_members, dims[i + 1]), dtype=torch.float32, device=key.device))
+            dyn = MlpEnsembleDynamicsParams(weights=ws, biases=bs)
+        return SystemParams(dynamics_params=dyn, reward_params=self.reward_params, key=keys[..., 2, :].contiguous())
 
     def packed(self, system_params: SystemParams) -> _Packed:
         dyn = system_params.dynamics_params

@@ -565,6 +565,35 @@ def test_ensemble_system_step_matches_forward_kernel(mb, cuda_device):
     np.testing.assert_allclose(st.reward.cpu().numpy(), r, rtol=1e-5, atol=3e-6)
 
 
+def test_icem_plan_with_ensemble_system(mb, cuda_device):
+    """iCemTO over the learned-ensemble System through the unchanged API (staged plan)."""
+    from mbpo_b200.optimizers import iCemTO, iCemParams
+    ens = orc.make_mlp_ensemble(seed=3, members=5)
+    sys_, sp = _ensemble_on_device(mb, cuda_device, ens)
+    H, B = 20, 3
+    params = dict(num_samples=200, num_elites=20, num_particles=5, num_steps=3)
+    opt = iCemTO(horizon=H, action_dim=1, opt_params=iCemParams(**params))
+    opt.set_system(sys_)
+    keys = _keys(B, seed=81)
+    st = opt.init(_dev(keys, cuda_device)).replace(system_params=sp)
+    x0 = _random_states(B, 82)
+    action, new = opt.act(_dev(x0, cuda_device), st)
+    assert action.shape == (B, 1) and new.best_sequence.shape == (B, H, 1)
+    for b in range(B):                                                            # integer path is exact
+        assert np.array_equal(new.key[b].cpu().numpy(), ojr.split(ojr.split(keys[b], 3)[2], 2)[1])
+    # best_reward is the ensemble objective of best_sequence (same kernel, same bits)
+    again = sys_.ensemble_returns(sp, _dev(x0, cuda_device), new.best_sequence.reshape(B, 1, H, 1))[:, 0]
+    assert torch.equal(again, new.best_reward)
+    zero = sys_.ensemble_returns(sp, _dev(x0, cuda_device), torch.zeros((B, 1, H, 1), device=cuda_device))[:, 0]
+    assert bool((new.best_reward >= zero).all())
+    want = orc.ensemble_rollout_returns(x0, new.best_sequence.cpu().numpy().reshape(B, 1, H), ens)[:, 0]
+    np.testing.assert_allclose(new.best_reward.cpu().numpy(), want, rtol=5e-3, atol=5e-3)
+    with pytest.raises(mb.MbpoUnsupported):                                       # particles must be the members
+        o2 = iCemTO(horizon=H, action_dim=1, opt_params=iCemParams(num_samples=64, num_particles=3))
+        o2.set_system(sys_)
+        o2.act(_dev(x0, cuda_device), st)
+
+
 # ---------------------------------------------------------------------------------------------
 # error behaviour: no fallback, loud failures
 # ---------------------------------------------------------------------------------------------
