@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(HERE, "mbpo_b200", "libmbpo_b200.so")
 HORIZONS = (5, 8, 15, 20, 30, 50)          # keep in sync with MBPO_FOR_EACH_H (csrc/host_util.h)
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-I", INCLUDE]
+              "-Xcompiler", "-fPIC", "-I", INCLUDE] + os.environ.get("MBPO_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _nvcc() -> str:

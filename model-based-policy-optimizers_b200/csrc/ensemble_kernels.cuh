@@ -6,19 +6,32 @@
 //     reward = pendulum reward on (x, u)   (rewards/pendulum_reward.py:27-42)
 // with particle p rolled through ensemble member p (num_particles == num_members).
 //
-// A CTA PAIR (thread-block cluster of 2, tcgen05 cta_group::2) owns 256 candidate rows; each
-// CTA owns 128 rows = its 128 TMEM lanes, four threads per row (one per quarter of the hidden units).  For every member e the pair keeps BOTH
-// hidden-layer weight matrices resident in shared memory for the whole horizon, split along N
-// across the pair (each CTA holds W[e,l][128 rows of N, 256 K] = 64 KB per layer, fetched by TMA as
-// 32 K-chunk slabs), so the only per-step traffic is the action stream.  Per horizon step:
-//   layer 0 (K = 4) on CUDA cores -> bf16 activations into the canonical K-major A tile in smem
-//   16 x tcgen05.mma.cta_group::2 (M256 N256 K16), issued by one thread of the leader CTA;
-//        completion multicast to both CTAs' mbarriers by tcgen05.commit
-//   epilogue 1: tcgen05.ld accumulator rows, bias + swish, bf16 -> A tile (next layer's operand)
-//   16 x tcgen05.mma with W[e,1]
-//   epilogue 2: bias + swish, output layer (N = 3) on CUDA cores, x += delta, reward accumulated
-// The state never leaves registers; returns are averaged (or maxed) over members in registers in
-// member order, so the result is deterministic and needs no workspace.
+// A CTA PAIR (thread-block cluster of 2, tcgen05 cta_group::2) owns 256 candidate rows; each CTA
+// owns 128 rows = its 128 TMEM lanes.  ALL FOUR layers run on the tensor cores, and the MMAs of
+// layer l+1 are issued K-chunk by K-chunk while the CUDA cores are still producing layer l's
+// activations (software pipeline through mbarriers; no __syncthreads inside the horizon loop):
+//
+//   warps 0-15  "epilogue" warps.  Warp w owns TMEM lanes 32*(w%4).. (rows) and, in every
+//               64-column round, the 16 accumulator columns 64*r + 16*(w/4)..: tcgen05.ld -> bias +
+//               swish -> bf16 -> the canonical K-major A chunk in shared memory -> mbarrier arrive.
+//   warp 16     one elected thread of the leader CTA issues every tcgen05.mma (M256, 2-SM) as soon
+//               as the chunk it consumes has been published by both CTAs, and tcgen05.commit
+//               (multicast to both CTAs) when a layer's accumulator is complete.
+//
+//   layer 0  (K = 4 inputs)  one UMMA with K = 16: the fp32 inputs are split into bf16 hi + lo parts
+//            and the fp32 weights / bias into hi + lo (+ lo2) parts, slots carry the cross products
+//            hi*wh + hi*wl + lo*wh (+ bias against a column of ones): ~2^-16 relative, far inside
+//            the bf16 rounding the activations receive next.  Weights are pre-scaled by 0.5.
+//   layer 1,2 (256 x 256)    16 UMMAs (M256 N256 K16) each, weights resident in shared memory for the
+//            whole horizon, split along N across the pair (64 KB per layer per CTA, by TMA).
+//   layer 3  (N = 3 outputs) 16 UMMAs with N = 16: columns 0-2 hold the hi parts of w_out, 3-5 the
+//            lo parts; delta = (c_j + c_{3+j}) + b_out.
+//   swish(v) = h + h * tanh(h) with h = v / 2: one FFMA (0.5 * acc + 0.5 * bias, exact scaling), one
+//            MUFU.TANH, one FFMA per activation.
+// Two 256-column accumulators alternate (layer l writes D[l & 1]), so layer l+1's MMAs never touch
+// the accumulator the epilogue of layer l is still reading.  The state never leaves registers;
+// returns are averaged (or maxed) over members in registers in member order: deterministic, no
+// workspace.
 #pragma once
 #include "mathx.cuh"
 #include "mlp_tc_kernels.cuh"
@@ -29,23 +42,26 @@ namespace ens {
 
 using namespace tc;
 
-constexpr int ENS_THREADS = 512;              // four threads per row: warps 4q..4q+3 own accumulator columns [64q, 64q+64)
-constexpr int ENS_SPLIT = ENS_THREADS / 128;  // threads per row
-constexpr uint32_t WH_BYTES = 128 * HID * 2;  // one layer's N-half: 65536
-constexpr uint32_t WH_LBO = 128 * 16;         // 2048: next K-chunk of a weight half
+constexpr int EPI_WARPS = 16;
+constexpr int MMA_WARP = EPI_WARPS;                 // warp index of the MMA issuer
+constexpr int ENS_THREADS = (EPI_WARPS + 1) * 32;   // 544
+constexpr uint32_t WH_BYTES = 128 * HID * 2;        // one hidden layer's N-half: 65536
+constexpr uint32_t WH_LBO = 128 * 16;               // 2048: next K-chunk of a weight half
+constexpr uint32_t W3_LBO = 8 * 16;                 // 128: next K-chunk of the 8-row output-layer tile
+constexpr int ENS_TMEM_COLS = 512;                  // two 256-column accumulators
+constexpr int ROUNDS = 4;                           // 64-column rounds per layer
 
 struct Smem {
-  static constexpr uint32_t A = 0;                        // 128 x 256 bf16 activations
+  static constexpr uint32_t A = 0;                        // 128 x 256 bf16 activations (4 chunks of 16 KB)
   static constexpr uint32_t W1 = A + A_BYTES;             // W[e,0] rows [128*rank, +128)
   static constexpr uint32_t W2 = W1 + WH_BYTES;           // W[e,1] rows [128*rank, +128)
-  static constexpr uint32_t W_IN = W2 + WH_BYTES;         // float [4][256]
-  static constexpr uint32_t B_IN = W_IN + 4 * HID * 4;    // float [256]
-  static constexpr uint32_t B_H = B_IN + HID * 4;         // float [2][256]
-  static constexpr uint32_t W_OUT = B_H + 2 * HID * 4;    // float [256][4]
-  static constexpr uint32_t B_OUT = W_OUT + HID * 4 * 4;  // float [4]
-  static constexpr uint32_t DELTA = B_OUT + 16;           // float4 [ENS_SPLIT][128]: partial output-layer sums
-  static constexpr uint32_t BARS = DELTA + ENS_SPLIT * TILE_M * 16;  // bar_w, bar_mma, bar_a
-  static constexpr uint32_t TMEM_PTR = BARS + 32;
+  static constexpr uint32_t A0 = W2 + WH_BYTES;           // 128 x 16 bf16: split inputs (layer 0 A operand)
+  static constexpr uint32_t W0 = A0 + TILE_M * 32;        // 128 x 16 bf16: split layer-0 weights (N-half)
+  static constexpr uint32_t W3 = W0 + 128 * 32;           // 8 x 256 bf16: output layer hi/lo rows
+  static constexpr uint32_t HB = W3 + 8 * HID * 2;        // float [2][256]: 0.5 * b_h
+  static constexpr uint32_t B_OUT = HB + 2 * HID * 4;     // float [4]
+  static constexpr uint32_t BARS = B_OUT + 16;            // full[4], full_a0, bar_mma, bar_out, bar_w
+  static constexpr uint32_t TMEM_PTR = BARS + 8 * 8;
   static constexpr uint32_t TOTAL = TMEM_PTR + 16;
 };
 static_assert(Smem::TOTAL <= 227 * 1024, "ensemble rollout shared memory plan exceeds 227 KB");
@@ -63,14 +79,15 @@ struct EnsArgs {
   MbpoPendulumParams reward;
 };
 
-// swish(z) = z * sigmoid(z) with sigmoid(z) = 0.5 + 0.5 * tanh(z / 2): one MUFU (tanh.approx) instead of
-// two (ex2 + rcp); the activation pipeline is MUFU-throughput bound.  |error| <= ~2.5e-4 * |z|, well
-// inside the bf16 rounding (2^-9 relative) the activations receive next.
-__device__ __forceinline__ float swish_tanh(float z) {
+__device__ __forceinline__ float tanh_approx(float z) {
   float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z));
-  return z * fmaf(t, 0.5f, 0.5f);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(z));
+  return t;
 }
+// swish(2h) = 2h * sigmoid(2h) = h + h * tanh(h)
+__device__ __forceinline__ float swish_half(float h) { return fmaf(h, tanh_approx(h), h); }
+
+__device__ __forceinline__ float bf16_hi(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -87,14 +104,17 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t ran
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // default semantics (.release.cta): the data this arrive publishes stays in the arriving CTA's own shared
+  // memory (each SM's tensor core reads its own half of A), made visible to the async proxy by the
+  // fence.proxy.async before it; a cluster-scope release would cost a full memory barrier per round.
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred P1;\n\t"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
       "@P1 bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t"
@@ -119,52 +139,147 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
       "h"(static_cast<uint16_t>(3))
       : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// tcgen05.ld without the wait, so that the next round's load overlaps this round's arithmetic
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
+// The wait names the destination registers so that no use of them can be scheduled above it.
+__device__ __forceinline__ void tmem_wait_ld16(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld8(uint32_t (&v)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7])
+               :
+               : "memory");
+}
+
+// One epilogue round: 16 accumulator values of this thread's row -> 16 bf16 activations in the A tile.
+template <bool HAS_BIAS>
+__device__ __forceinline__ void epilogue_round(const uint32_t (&v)[16], const float* hb, uint8_t* a_dst) {
+  float s[16];
+#pragma unroll
+  for (int j4 = 0; j4 < 4; ++j4) {
+    float4 b = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (HAS_BIAS) b = *reinterpret_cast<const float4*>(hb + j4 * 4);
+    const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float acc = __uint_as_float(v[j4 * 4 + j]);
+      const float h = HAS_BIAS ? fmaf(acc, 0.5f, bb[j]) : acc;
+      s[j4 * 4 + j] = swish_half(h);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    uint4 pk;
+    pk.x = pack_bf16(s[q * 8 + 0], s[q * 8 + 1]); pk.y = pack_bf16(s[q * 8 + 2], s[q * 8 + 3]);
+    pk.z = pack_bf16(s[q * 8 + 4], s[q * 8 + 5]); pk.w = pack_bf16(s[q * 8 + 6], s[q * 8 + 7]);
+    *reinterpret_cast<uint4*>(a_dst + q * A_LBO) = pk;
+  }
+}
+
+// The split-input row of the layer-0 A operand: per input [hi, hi, lo], then [1, 1, 1, 0].
+__device__ __forceinline__ void build_a0_row(uint8_t* a0_row, float x0, float x1, float x2, float u) {
+  const float v[4] = {x0, x1, x2, u};
+  float hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    hi[i] = bf16_hi(v[i]);
+    lo[i] = v[i] - hi[i];
+  }
+  uint4 p0, p1;
+  p0.x = pack_bf16(hi[0], hi[0]); p0.y = pack_bf16(lo[0], hi[1]);
+  p0.z = pack_bf16(hi[1], lo[1]); p0.w = pack_bf16(hi[2], hi[2]);
+  p1.x = pack_bf16(lo[2], hi[3]); p1.y = pack_bf16(hi[3], lo[3]);
+  p1.z = pack_bf16(1.0f, 1.0f);   p1.w = pack_bf16(1.0f, 0.0f);
+  *reinterpret_cast<uint4*>(a0_row) = p0;
+  *reinterpret_cast<uint4*>(a0_row + A_LBO) = p1;
+}
+
+#ifdef MBPO_ENS_TRACE
+__device__ long long g_ens_trace[256];
+#define ENS_TRACE(cond, slot) do { if ((cond) && blockIdx.x == 0 && e == 0 && t == 10) g_ens_trace[slot] = clock64(); } while (0)
+#else
+#define ENS_TRACE(cond, slot) do { } while (0)
+#endif
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ENS_THREADS, 1)
     ensemble_rollout_kernel(const __grid_constant__ EnsArgs a, const __grid_constant__ CUtensorMap w_map) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int lrow = tid & (TILE_M - 1);   // row within the CTA's tile = TMEM lane
-  const int half = tid >> 7;             // which 256 / ENS_SPLIT hidden units / accumulator columns this thread owns
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quarter = warp >> 2;                       // which 16 of a round's 64 columns (epilogue warps)
+  const int lrow = ((warp & 3) << 5) | lane;           // row within the CTA's tile = TMEM lane
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  float* s_w_in = reinterpret_cast<float*>(smem + Smem::W_IN);
-  float* s_b_in = reinterpret_cast<float*>(smem + Smem::B_IN);
-  float* s_b_h = reinterpret_cast<float*>(smem + Smem::B_H);
-  float* s_w_out = reinterpret_cast<float*>(smem + Smem::W_OUT);
+  const bool row_owner = warp < 4;                     // the thread that carries the row's state
+  float* s_hb = reinterpret_cast<float*>(smem + Smem::HB);
   float* s_b_out = reinterpret_cast<float*>(smem + Smem::B_OUT);
-  float4* s_delta = reinterpret_cast<float4*>(smem + Smem::DELTA);
-  uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + Smem::BARS);  // weights landed (this CTA)
-  uint64_t* bar_mma = bar_w + 1;                                     // accumulator complete (multicast commit)
-  uint64_t* bar_a = bar_w + 2;                                       // leader only: both CTAs' A tiles written
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + Smem::BARS);  // [4] leader: chunk r of A published by both CTAs
+  uint64_t* bar_a0 = bar_full + 4;                                      // leader: A0 rows published by both CTAs
+  uint64_t* bar_mma = bar_full + 5;                                     // accumulator of layer 0/1/2 complete (multicast)
+  uint64_t* bar_out = bar_full + 6;                                     // output-layer accumulator complete (multicast)
+  uint64_t* bar_w = bar_full + 7;                                       // this CTA's weight halves landed
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + Smem::TMEM_PTR);
 
   // ---- one-time setup --------------------------------------------------------------------------
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
-                 "r"(TMEM_COLS));
+                 "r"(ENS_TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
   }
   if (tid == 0) {
-    mbar_init(bar_w, 1);
+    for (int r = 0; r < ROUNDS; ++r) mbar_init(bar_full + r, 2 * EPI_WARPS);
+    mbar_init(bar_a0, 2 * 4);
     mbar_init(bar_mma, 1);
-    mbar_init(bar_a, 2);
+    mbar_init(bar_out, 1);
+    mbar_init(bar_w, 1);
     fence_barrier_init();
   }
+  // the output-layer tile of the non-leader CTA stays all zero (its 8 rows are columns 8-15 of D3)
+  for (int i = tid; i < 8 * HID * 2 / 16; i += ENS_THREADS)
+    reinterpret_cast<uint4*>(smem + Smem::W3)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   cluster_sync();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + half * (HID / ENS_SPLIT);
+  const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
   const uint32_t a_addr = smem_u32(smem + Smem::A);
-  const uint32_t w_addr[2] = {smem_u32(smem + Smem::W1), smem_u32(smem + Smem::W2)};
-  const uint32_t bar_a_leader = map_to_cta(smem_u32(bar_a), 0);
+  const uint32_t bar_full_leader = map_to_cta(smem_u32(bar_full), 0);
+  const uint32_t bar_a0_leader = map_to_cta(smem_u32(bar_a0), 0);
   constexpr uint32_t IDESC = umma_idesc_bf16(2 * TILE_M, HID);
-  uint32_t phase_w = 0, phase_mma = 0, phase_a = 0;
+  constexpr uint32_t IDESC_OUT = umma_idesc_bf16(2 * TILE_M, 16);
+  uint32_t phase_w = 0;
+  uint32_t ph_mma = 0, ph_out = 0;       // epilogue warps
+  uint32_t ph_full = 0, ph_a0 = 0;       // MMA thread
   const PendulumConsts pc(a.reward);
-  const float inv_h = 1.0f;  // (mean over the horizon taken with __fdiv_rn below)
-  (void)inv_h;
 
   const int num_groups = (a.R + 2 * TILE_M - 1) / (2 * TILE_M);
   for (int group = blockIdx.x >> 1; group < num_groups; group += gridDim.x >> 1) {
@@ -177,8 +292,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ENS_THREADS, 1)
     float summary = 0.0f;
 
     for (int e = 0; e < a.num_members; ++e) {
-      // ---- member e: both weight halves by TMA, small fp32 parameters by the threads ------------
-      __syncthreads();  // previous member's parameters / A tile no longer in use by this CTA
+      // ---- member e: hidden weight halves by TMA; the small layers are split into bf16 parts here ----
+      __syncthreads();  // every MMA of the previous member has completed (row owners waited bar_out)
       if (tid == 0) {
         mbar_expect_tx(bar_w, 2 * WH_BYTES);
         for (int l = 0; l < 2; ++l)
@@ -186,115 +301,174 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ENS_THREADS, 1)
             tma_load_2d(smem + (l ? Smem::W2 : Smem::W1) + kc * WH_LBO, &w_map, kc * 8,
                         (e * 2 + l) * HID + static_cast<int>(rank) * 128, bar_w);
       }
-      for (int i = tid; i < 4 * HID; i += ENS_THREADS) s_w_in[i] = a.w_in[static_cast<size_t>(e) * 4 * HID + i];
-      for (int i = tid; i < HID; i += ENS_THREADS) s_b_in[i] = a.b_in[e * HID + i];
-      for (int i = tid; i < 2 * HID; i += ENS_THREADS) s_b_h[i] = a.b_h[e * 2 * HID + i];
-      for (int i = tid; i < HID * 3; i += ENS_THREADS) s_w_out[(i / 3) * 4 + (i % 3)] = a.w_out[static_cast<size_t>(e) * HID * 3 + i];
+      if (tid < 128) {
+        // layer 0, this CTA's 128 output units: per input [wh, wl, wh], then the bias [bh, bm, bl, 0]; all * 0.5
+        const int n = static_cast<int>(rank) * 128 + tid;
+        float wh[4], wl[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float w = 0.5f * a.w_in[(static_cast<size_t>(e) * 4 + i) * HID + n];
+          wh[i] = bf16_hi(w);
+          wl[i] = w - wh[i];
+        }
+        const float bias = 0.5f * a.b_in[e * HID + n];
+        const float bh = bf16_hi(bias), bm = bf16_hi(bias - bh), bl = (bias - bh) - bm;
+        uint4 p0, p1;
+        p0.x = pack_bf16(wh[0], wl[0]); p0.y = pack_bf16(wh[0], wh[1]);
+        p0.z = pack_bf16(wl[1], wh[1]); p0.w = pack_bf16(wh[2], wl[2]);
+        p1.x = pack_bf16(wh[2], wh[3]); p1.y = pack_bf16(wl[3], wh[3]);
+        p1.z = pack_bf16(bh, bm);       p1.w = pack_bf16(bl, 0.0f);
+        *reinterpret_cast<uint4*>(smem + Smem::W0 + tid * 16) = p0;
+        *reinterpret_cast<uint4*>(smem + Smem::W0 + WH_LBO + tid * 16) = p1;
+      } else if (tid < 128 + HID && leader) {
+        // output layer: row j (j < 3) = hi part of w_out[:, j], row 3 + j = lo part; rows 6, 7 stay zero
+        const int k = tid - 128;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const float w = a.w_out[(static_cast<size_t>(e) * HID + k) * 3 + j];
+          const __nv_bfloat16 h = __float2bfloat16_rn(w);
+          const __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
+          uint8_t* base = smem + Smem::W3 + (k >> 3) * W3_LBO + (k & 7) * 2;
+          *reinterpret_cast<__nv_bfloat16*>(base + j * 16) = h;
+          *reinterpret_cast<__nv_bfloat16*>(base + (3 + j) * 16) = l;
+        }
+      }
+      for (int i = tid; i < 2 * HID; i += ENS_THREADS) s_hb[i] = 0.5f * a.b_h[e * 2 * HID + i];
       if (tid < 3) s_b_out[tid] = a.b_out[e * 3 + tid];
-      mbar_wait(bar_w, phase_w);  // every thread observes the TMA completion (async-proxy writes visible)
+      fence_proxy_async();        // generic-proxy writes of W0 / W3 -> visible to the tensor core
+      mbar_wait(bar_w, phase_w);  // every thread observes the TMA completion
       phase_w ^= 1;
       __syncthreads();
 
-      float x[3] = {x_init[0], x_init[1], x_init[2]};
-      float acc = 0.0f;
+      if (warp == MMA_WARP) {
+        // ================= MMA issuer: warp 16 of the leader CTA =====================================
+        // The whole warp runs the (warp-uniform) waits; one elected lane issues.  Every operand below is
+        // derived from warp-uniform values and compile-time offsets, so the descriptors live in uniform
+        // registers and each tcgen05.mma costs a handful of instructions.
+        if (leader) {
+          const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+          const bool elected = elect_one();
+          const uint64_t desc_a = umma_desc(a_addr, A_LBO, SBO);
+          const uint64_t desc_a0 = umma_desc(smem_u32(smem + Smem::A0), A_LBO, SBO);
+          const uint64_t desc_w0 = umma_desc(smem_u32(smem + Smem::W0), WH_LBO, SBO);
+          const uint64_t desc_w1 = umma_desc(smem_u32(smem + Smem::W1), WH_LBO, SBO);
+          const uint64_t desc_w2 = umma_desc(smem_u32(smem + Smem::W2), WH_LBO, SBO);
+          const uint64_t desc_w3 = umma_desc(smem_u32(smem + Smem::W3), W3_LBO, SBO);
 #pragma unroll 1
-      for (int t = 0; t < a.H; ++t) {
-        const float u = __ldg(act + t);
-        // reward on the current state and the raw action (pendulum_reward.py:32-40)
-        acc = __fadd_rn(acc, reward_from(pc, atan2_bounded(x[1], x[0]), x[2], u));
-        // ---- layer 0 on CUDA cores ---------------------------------------------------------------
-#pragma unroll 2
-        for (int kc = half * (KCHUNKS / ENS_SPLIT); kc < (half + 1) * (KCHUNKS / ENS_SPLIT); ++kc) {
-          float h[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int n = kc * 8 + j;
-            float v = s_b_in[n];
-            v = fmaf(x[0], s_w_in[n], v);
-            v = fmaf(x[1], s_w_in[HID + n], v);
-            v = fmaf(x[2], s_w_in[2 * HID + n], v);
-            v = fmaf(u, s_w_in[3 * HID + n], v);
-            h[j] = swish_tanh(v);
-          }
-          uint4 pk;
-          pk.x = pack_bf16(h[0], h[1]); pk.y = pack_bf16(h[2], h[3]);
-          pk.z = pack_bf16(h[4], h[5]); pk.w = pack_bf16(h[6], h[7]);
-          *reinterpret_cast<uint4*>(smem + Smem::A + kc * A_LBO + lrow * 16) = pk;
-        }
-        float delta[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll 1
-        for (int layer = 0; layer < 2; ++layer) {
-          // ---- publish this CTA's A tile to the tensor core, tell the leader -----------------------
-          tc_fence_before();
-          fence_proxy_async();
-          __syncthreads();
-          if (tid == 0) mbar_arrive_cluster(bar_a_leader);
-          if (leader && tid == 0) {
-            mbar_wait_cluster(bar_a, phase_a);
+          for (int t = 0; t < a.H; ++t) {
+            mbar_wait(bar_a0, ph_a0);
+            ph_a0 ^= 1;
             tc_fence_after();
-#pragma unroll
-            for (int s = 0; s < HID / 16; ++s) {
-              const uint64_t da = umma_desc(a_addr + s * 2 * A_LBO, A_LBO, SBO);
-              const uint64_t db = umma_desc(w_addr[layer] + s * 2 * WH_LBO, WH_LBO, SBO);
-              umma_bf16_ss_2sm(tmem_base, da, db, IDESC, s > 0 ? 1u : 0u);
+            ENS_TRACE(lane == 0, 0);
+            if (elected) {
+              umma_bf16_ss_2sm(tmem_u, desc_a0, desc_w0, IDESC, 0u);
+              umma_commit_2sm(bar_mma);
             }
-            umma_commit_2sm(bar_mma);
+            ENS_TRACE(lane == 0, 1);
+#pragma unroll
+            for (int layer = 1; layer <= 3; ++layer) {
+              const uint32_t d = tmem_u + (layer & 1) * HID;
+              const uint64_t desc_w = layer == 1 ? desc_w1 : (layer == 2 ? desc_w2 : desc_w3);
+              constexpr uint32_t A_STEP = (2 * A_LBO) >> 4;      // one K = 16 step, in descriptor units
+              const uint32_t w_step = (layer < 3 ? 2 * WH_LBO : 2 * W3_LBO) >> 4;
+#pragma unroll
+              for (int r = 0; r < ROUNDS; ++r) {
+                mbar_wait(bar_full + r, ph_full);
+                tc_fence_after();
+                ENS_TRACE(lane == 0, 2 + (layer - 1) * 8 + r * 2);
+                if (elected) {
+#pragma unroll
+                  for (int s = 4 * r; s < 4 * r + 4; ++s)
+                    umma_bf16_ss_2sm(d, desc_a + static_cast<uint64_t>(s * A_STEP),
+                                     desc_w + static_cast<uint64_t>(s * w_step), layer < 3 ? IDESC : IDESC_OUT,
+                                     s > 0 ? 1u : 0u);
+                  if (r == ROUNDS - 1) umma_commit_2sm(layer < 3 ? bar_mma : bar_out);
+                }
+                ENS_TRACE(lane == 0, 3 + (layer - 1) * 8 + r * 2);
+              }
+              ph_full ^= 1;
+            }
           }
-          phase_a ^= 1;
-          mbar_wait(bar_mma, phase_mma);
-          phase_mma ^= 1;
-          tc_fence_after();
-          // ---- epilogue ---------------------------------------------------------------------------------
-          const float* bias = s_b_h + layer * HID;
+        }
+      } else {
+        // ================= epilogue warps ============================================================
+        float x[3] = {x_init[0], x_init[1], x_init[2]};
+        float acc = 0.0f;
+        float u = 0.0f;
+        if (row_owner) {
+          u = __ldg(act);
+          build_a0_row(smem + Smem::A0 + lrow * 16, x[0], x[1], x[2], u);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(bar_a0_leader);
+        }
 #pragma unroll 1
-          for (int c = 0; c < HID / 32 / ENS_SPLIT; ++c) {
-            const int cg = half * (HID / 32 / ENS_SPLIT) + c;        // global 32-column chunk
-            uint32_t v[32];
-            tmem_ld32(tmem_row + c * 32, v);
-            float h[32];
+        for (int t = 0; t < a.H; ++t) {
+          float u_next = 0.0f;
+          if (row_owner) {
+            // reward on the current state and the raw action (pendulum_reward.py:32-40); runs under MMA 0
+            acc = __fadd_rn(acc, reward_from(pc, atan2_bounded(x[1], x[0]), x[2], u));
+            if (t + 1 < a.H) u_next = __ldg(act + t + 1);
+          }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) h[j] = swish_tanh(__uint_as_float(v[j]) + bias[cg * 32 + j]);
-            if (layer == 0) {
+          for (int layer = 0; layer < 3; ++layer) {
+            mbar_wait(bar_mma, ph_mma);   // accumulator of this layer complete; the A tile is free again
+            ph_mma ^= 1;
+            tc_fence_after();
+            ENS_TRACE(tid == 0, 32 + layer * 8);
+            ENS_TRACE(tid == 480, 64 + layer * 8);
+            const uint32_t d_src = tmem_lane + (layer & 1) * HID + quarter * 16;
+            const float* hb = s_hb + (layer > 0 ? layer - 1 : 0) * HID + quarter * 16;   // layers 1, 2 (layer 0's bias is in the MMA)
+            uint32_t v[2][16];
+            tmem_ld16_nowait(d_src, v[0]);
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                uint4 pk;
-                pk.x = pack_bf16(h[q * 8 + 0], h[q * 8 + 1]); pk.y = pack_bf16(h[q * 8 + 2], h[q * 8 + 3]);
-                pk.z = pack_bf16(h[q * 8 + 4], h[q * 8 + 5]); pk.w = pack_bf16(h[q * 8 + 6], h[q * 8 + 7]);
-                *reinterpret_cast<uint4*>(smem + Smem::A + (cg * 4 + q) * A_LBO + lrow * 16) = pk;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float4 wo = *reinterpret_cast<const float4*>(s_w_out + (cg * 32 + j) * 4);
-                delta[0] = fmaf(h[j], wo.x, delta[0]);
-                delta[1] = fmaf(h[j], wo.y, delta[1]);
-                delta[2] = fmaf(h[j], wo.z, delta[2]);
-              }
+            for (int r = 0; r < ROUNDS; ++r) {
+              tmem_wait_ld16(v[r & 1]);
+              if (r + 1 < ROUNDS) tmem_ld16_nowait(d_src + (r + 1) * 64, v[(r + 1) & 1]);
+              uint8_t* dst = smem + Smem::A + (8 * r + 2 * quarter) * A_LBO + lrow * 16;
+              if (layer == 0) epilogue_round<false>(v[r & 1], nullptr, dst);
+              else epilogue_round<true>(v[r & 1], hb + r * 64, dst);
+              fence_proxy_async();   // generic-proxy writes of A -> async proxy (tensor core)
+              tc_fence_before();     // this thread's tcgen05.ld before the MMAs that follow the arrive
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(bar_full_leader + r * 8);
+              ENS_TRACE(tid == 0, 33 + layer * 8 + r);
+              ENS_TRACE(tid == 480, 65 + layer * 8 + r);
+            }
+          }
+          if (row_owner) {
+            mbar_wait(bar_out, ph_out);
+            ph_out ^= 1;
+            tc_fence_after();
+            ENS_TRACE(tid == 0, 56);
+            uint32_t o[8];
+            tmem_ld8_nowait(tmem_lane + HID, o);
+            tmem_wait_ld8(o);
+            tc_fence_before();
+            x[0] = __fadd_rn(x[0], (__uint_as_float(o[0]) + __uint_as_float(o[3])) + s_b_out[0]);
+            x[1] = __fadd_rn(x[1], (__uint_as_float(o[1]) + __uint_as_float(o[4])) + s_b_out[1]);
+            x[2] = __fadd_rn(x[2], (__uint_as_float(o[2]) + __uint_as_float(o[5])) + s_b_out[2]);
+            if (t + 1 < a.H) {
+              u = u_next;
+              build_a0_row(smem + Smem::A0 + lrow * 16, x[0], x[1], x[2], u);
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(bar_a0_leader);
+              ENS_TRACE(tid == 0, 57);
             }
           }
         }
-        // the next step's layer 0 overwrites A only after this CTA's MMA reads completed (bar_mma) and
-        // tcgen05.ld of D completed (tcgen05.wait::ld inside tmem_ld32); D is rewritten only after the
-        // next "A ready" handshake, which every thread precedes with tcgen05.fence::before_thread_sync.
-        // combine the column quarters of the output layer (fixed order: q0 + q1 + ... + bias)
-        s_delta[half * TILE_M + lrow] = make_float4(delta[0], delta[1], delta[2], 0.0f);
-        __syncthreads();
-        float4 d = s_delta[lrow];
-#pragma unroll
-        for (int q = 1; q < ENS_SPLIT; ++q) {
-          const float4 dq = s_delta[q * TILE_M + lrow];
-          d.x += dq.x; d.y += dq.y; d.z += dq.z;
+        if (row_owner) {
+          const float ret = __fdiv_rn(acc, static_cast<float>(a.H));
+          if (a.summarize == MBPO_SUMMARIZE_MAX) summary = (e == 0) ? ret : fmaxf(summary, ret);
+          else summary = __fadd_rn(summary, ret);
         }
-        x[0] = __fadd_rn(x[0], d.x + s_b_out[0]);
-        x[1] = __fadd_rn(x[1], d.y + s_b_out[1]);
-        x[2] = __fadd_rn(x[2], d.z + s_b_out[2]);
       }
-      const float ret = __fdiv_rn(acc, static_cast<float>(a.H));
-      if (a.summarize == MBPO_SUMMARIZE_MAX) summary = (e == 0) ? ret : fmaxf(summary, ret);
-      else summary = __fadd_rn(summary, ret);
     }
-    if (a.summarize != MBPO_SUMMARIZE_MAX) summary = __fdiv_rn(summary, static_cast<float>(a.num_members));
-    if (valid && half == 0) a.returns_out[row] = summary;
+    if (row_owner && warp != MMA_WARP) {
+      if (a.summarize != MBPO_SUMMARIZE_MAX) summary = __fdiv_rn(summary, static_cast<float>(a.num_members));
+      if (valid) a.returns_out[row] = summary;
+    }
   }
 
   // ---- teardown --------------------------------------------------------------------------------------
@@ -302,7 +476,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ENS_THREADS, 1)
   __syncthreads();
   cluster_sync();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ENS_TMEM_COLS));
   }
 }
 

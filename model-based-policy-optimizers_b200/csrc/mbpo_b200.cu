@@ -597,3 +597,9 @@ int mbpo_ensemble_rollout(const MbpoMlpEnsembleParams* p, int horizon, const flo
 }
 
 }  // extern "C"
+
+#ifdef MBPO_ENS_TRACE
+extern "C" int mbpo_debug_ens_trace(long long* out_host) {
+  return cudaMemcpyFromSymbol(out_host, mbpo::ens::g_ens_trace, sizeof(long long) * 256) == cudaSuccess ? 0 : -3;
+}
+#endif

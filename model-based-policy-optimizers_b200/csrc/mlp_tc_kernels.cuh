@@ -3,7 +3,7 @@
 //   h0 = swish(inp @ w_in[e] + b_in[e])                 CUDA cores, float32   (K = x_dim + u_dim = 4)
 //   h1 = swish(bf16(h0) @ bf16(w_h[e,0]) + b_h[e,0])    tcgen05.mma kind::f16 (bf16 x bf16 -> fp32 in TMEM)
 //   h2 = swish(bf16(h1) @ bf16(w_h[e,1]) + b_h[e,1])    tcgen05.mma
-//   delta = h2 @ w_out[e] + b_out[e]                    CUDA cores, float32   (N = x_dim = 3)
+//   delta = bf16(h2) @ w_out[e] + b_out[e]              CUDA cores, float32   (N = x_dim = 3)
 //
 // One CTA (128 threads = 128 TMEM lanes) owns a tile of 128 rows; thread r owns row r.
 //   * A operand (activations, 128 x 256 bf16) lives in shared memory in the canonical K-major
@@ -279,10 +279,13 @@ __global__ void __launch_bounds__(TILE_M, 1)
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const float4 wo = *reinterpret_cast<const float4*>(s_w_out + (c * 32 + j) * 4);
-              out[0] = fmaf(h[j], wo.x, out[0]);
-              out[1] = fmaf(h[j], wo.y, out[1]);
-              out[2] = fmaf(h[j], wo.z, out[2]);
-              out[3] = fmaf(h[j], wo.w, out[3]);
+              // the activations entering the output layer are bf16 too (the fused rollout kernel runs
+              // that layer on the tensor cores as well); the weights stay float32
+              const float hj = __bfloat162float(__float2bfloat16_rn(h[j]));
+              out[0] = fmaf(hj, wo.x, out[0]);
+              out[1] = fmaf(hj, wo.y, out[1]);
+              out[2] = fmaf(hj, wo.z, out[2]);
+              out[3] = fmaf(hj, wo.w, out[3]);
             }
           }
         }

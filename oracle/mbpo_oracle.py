@@ -273,7 +273,8 @@ def mlp_member_forward(params: MlpEnsembleParams, member: np.ndarray, inp: np.nd
 
     bf16=True applies the same operand rounding as the tensor-core path: activations and
     hidden-layer weights rounded to bfloat16, products accumulated in float32; the first
-    layer (K = X+A) and the last layer (N = X) stay float32.
+    layer (K = X+A) stays float32 and the last layer (N = X) takes bfloat16 activations against
+    float32 weights.
     """
     h = np.asarray(inp, dtype=F32)
     nl = len(params.weights)
@@ -289,6 +290,10 @@ def mlp_member_forward(params: MlpEnsembleParams, member: np.ndarray, inp: np.nd
             hidden_gemm = 0 < li < nl - 1
             if bf16 and hidden_gemm:
                 a = (_bf16_round(a).astype(np.float64) @ _bf16_round(w).astype(np.float64)).astype(F32) + b
+            elif bf16 and li == nl - 1:
+                # output layer: bf16 activations against the float32 weights (the fused kernel feeds the
+                # tensor core w = bf16(w) + bf16(w - bf16(w)), i.e. w to 2^-17)
+                a = (_bf16_round(a).astype(np.float64) @ w.astype(np.float64)).astype(F32) + b
             else:
                 a = (a.astype(np.float64) @ w.astype(np.float64)).astype(F32) + b
             if li < nl - 1:
