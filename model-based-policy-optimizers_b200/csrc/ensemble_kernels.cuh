@@ -49,7 +49,13 @@ constexpr uint32_t WH_BYTES = 128 * HID * 2;        // one hidden layer's N-half
 constexpr uint32_t WH_LBO = 128 * 16;               // 2048: next K-chunk of a weight half
 constexpr uint32_t W3_LBO = 8 * 16;                 // 128: next K-chunk of the 8-row output-layer tile
 constexpr int ENS_TMEM_COLS = 512;                  // two 256-column accumulators
-constexpr int ROUNDS = 4;                           // 64-column rounds per layer
+// A layer's 256 activation columns are published to the MMA issuer in rounds of 64, 64, 64, 32, 16, 16
+// columns (4, 4, 4, 2, 1, 1 UMMA K-steps): the rounds shrink towards the end so that the MMA work that is
+// still outstanding when the last round is published -- the only part the next epilogue has to wait for --
+// is a single K-step.
+constexpr int ROUNDS = 6;
+__host__ __device__ constexpr int round_cols(int r) { return r < 3 ? 64 : (r == 3 ? 32 : 16); }
+__host__ __device__ constexpr int round_first_col(int r) { return r < 3 ? 64 * r : (r == 3 ? 192 : (r == 4 ? 224 : 240)); }
 
 struct Smem {
   static constexpr uint32_t A = 0;                        // 128 x 256 bf16 activations (4 chunks of 16 KB)
@@ -60,8 +66,8 @@ struct Smem {
   static constexpr uint32_t W3 = W0 + 128 * 32;           // 8 x 256 bf16: output layer hi/lo rows
   static constexpr uint32_t HB = W3 + 8 * HID * 2;        // float [2][256]: 0.5 * b_h
   static constexpr uint32_t B_OUT = HB + 2 * HID * 4;     // float [4]
-  static constexpr uint32_t BARS = B_OUT + 16;            // full[4], full_a0, bar_mma, bar_out, bar_w
-  static constexpr uint32_t TMEM_PTR = BARS + 8 * 8;
+  static constexpr uint32_t BARS = B_OUT + 16;            // full[ROUNDS], full_a0, bar_mma, bar_out, bar_w
+  static constexpr uint32_t TMEM_PTR = BARS + (ROUNDS + 4) * 8;
   static constexpr uint32_t TOTAL = TMEM_PTR + 16;
 };
 static_assert(Smem::TOTAL <= 227 * 1024, "ensemble rollout shared memory plan exceeds 227 KB");
@@ -164,6 +170,14 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&v)[8]
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, uint32_t (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld4(uint32_t (&v)[4]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]) : : "memory");
+}
 // The wait names the destination registers so that no use of them can be scheduled above it.
 __device__ __forceinline__ void tmem_wait_ld16(uint32_t (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
@@ -179,12 +193,13 @@ __device__ __forceinline__ void tmem_wait_ld8(uint32_t (&v)[8]) {
                : "memory");
 }
 
-// One epilogue round: 16 accumulator values of this thread's row -> 16 bf16 activations in the A tile.
-template <bool HAS_BIAS>
-__device__ __forceinline__ void epilogue_round(const uint32_t (&v)[16], const float* hb, uint8_t* a_dst) {
-  float s[16];
+// One epilogue round: NC accumulator values of this thread's row -> NC bf16 activations in the A tile
+// (a_dst points at the first of them).  NC = 16: two 16-byte K-chunks; 8: one; 4: half of one.
+template <int NC, bool HAS_BIAS>
+__device__ __forceinline__ void epilogue_round(const uint32_t (&v)[NC], const float* hb, uint8_t* a_dst) {
+  float s[NC];
 #pragma unroll
-  for (int j4 = 0; j4 < 4; ++j4) {
+  for (int j4 = 0; j4 < NC / 4; ++j4) {
     float4 b = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     if (HAS_BIAS) b = *reinterpret_cast<const float4*>(hb + j4 * 4);
     const float bb[4] = {b.x, b.y, b.z, b.w};
@@ -195,13 +210,28 @@ __device__ __forceinline__ void epilogue_round(const uint32_t (&v)[16], const fl
       s[j4 * 4 + j] = swish_half(h);
     }
   }
+  if (NC == 4) {
+    uint2 pk;
+    pk.x = pack_bf16(s[0], s[1]); pk.y = pack_bf16(s[2], s[3]);
+    *reinterpret_cast<uint2*>(a_dst) = pk;
+  } else {
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    uint4 pk;
-    pk.x = pack_bf16(s[q * 8 + 0], s[q * 8 + 1]); pk.y = pack_bf16(s[q * 8 + 2], s[q * 8 + 3]);
-    pk.z = pack_bf16(s[q * 8 + 4], s[q * 8 + 5]); pk.w = pack_bf16(s[q * 8 + 6], s[q * 8 + 7]);
-    *reinterpret_cast<uint4*>(a_dst + q * A_LBO) = pk;
+    for (int q = 0; q < NC / 8; ++q) {
+      uint4 pk;
+      pk.x = pack_bf16(s[q * 8 + 0], s[q * 8 + 1]); pk.y = pack_bf16(s[q * 8 + 2], s[q * 8 + 3]);
+      pk.z = pack_bf16(s[q * 8 + 4], s[q * 8 + 5]); pk.w = pack_bf16(s[q * 8 + 6], s[q * 8 + 7]);
+      *reinterpret_cast<uint4*>(a_dst + q * A_LBO) = pk;
+    }
   }
+}
+
+// Publish a finished round: generic-proxy writes of A -> async proxy (tensor core); this thread's tcgen05.ld
+// ordered before the MMAs that follow the arrive; one arrive per warp on the leader's barrier.
+__device__ __forceinline__ void publish_round(uint32_t bar_cluster_addr, int lane) {
+  fence_proxy_async();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive_cluster(bar_cluster_addr);
 }
 
 // The split-input row of the layer-0 A operand: per input [hi, hi, lo], then [1, 1, 1, 0].
@@ -240,11 +270,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ENS_THREADS, 1)
   const bool row_owner = warp < 4;                     // the thread that carries the row's state
   float* s_hb = reinterpret_cast<float*>(smem + Smem::HB);
   float* s_b_out = reinterpret_cast<float*>(smem + Smem::B_OUT);
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + Smem::BARS);  // [4] leader: chunk r of A published by both CTAs
-  uint64_t* bar_a0 = bar_full + 4;                                      // leader: A0 rows published by both CTAs
-  uint64_t* bar_mma = bar_full + 5;                                     // accumulator of layer 0/1/2 complete (multicast)
-  uint64_t* bar_out = bar_full + 6;                                     // output-layer accumulator complete (multicast)
-  uint64_t* bar_w = bar_full + 7;                                       // this CTA's weight halves landed
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + Smem::BARS);  // [ROUNDS] leader: round r of A published by both CTAs
+  uint64_t* bar_a0 = bar_full + ROUNDS;                                 // leader: A0 rows published by both CTAs
+  uint64_t* bar_mma = bar_full + ROUNDS + 1;                            // accumulator of layer 0/1/2 complete (multicast)
+  uint64_t* bar_out = bar_full + ROUNDS + 2;                            // output-layer accumulator complete (multicast)
+  uint64_t* bar_w = bar_full + ROUNDS + 3;                              // this CTA's weight halves landed
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + Smem::TMEM_PTR);
 
   // ---- one-time setup --------------------------------------------------------------------------
@@ -375,16 +405,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ENS_THREADS, 1)
               for (int r = 0; r < ROUNDS; ++r) {
                 mbar_wait(bar_full + r, ph_full);
                 tc_fence_after();
-                ENS_TRACE(lane == 0, 2 + (layer - 1) * 8 + r * 2);
+                ENS_TRACE(lane == 0, 2 + (layer - 1) * 12 + r * 2);
                 if (elected) {
 #pragma unroll
-                  for (int s = 4 * r; s < 4 * r + 4; ++s)
+                  for (int s = round_first_col(r) / 16; s < (round_first_col(r) + round_cols(r)) / 16; ++s)
                     umma_bf16_ss_2sm(d, desc_a + static_cast<uint64_t>(s * A_STEP),
                                      desc_w + static_cast<uint64_t>(s * w_step), layer < 3 ? IDESC : IDESC_OUT,
                                      s > 0 ? 1u : 0u);
                   if (r == ROUNDS - 1) umma_commit_2sm(layer < 3 ? bar_mma : bar_out);
                 }
-                ENS_TRACE(lane == 0, 3 + (layer - 1) * 8 + r * 2);
+                ENS_TRACE(lane == 0, 3 + (layer - 1) * 12 + r * 2);
               }
               ph_full ^= 1;
             }
@@ -415,32 +445,54 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ENS_THREADS, 1)
             mbar_wait(bar_mma, ph_mma);   // accumulator of this layer complete; the A tile is free again
             ph_mma ^= 1;
             tc_fence_after();
-            ENS_TRACE(tid == 0, 32 + layer * 8);
-            ENS_TRACE(tid == 480, 64 + layer * 8);
-            const uint32_t d_src = tmem_lane + (layer & 1) * HID + quarter * 16;
-            const float* hb = s_hb + (layer > 0 ? layer - 1 : 0) * HID + quarter * 16;   // layers 1, 2 (layer 0's bias is in the MMA)
+            ENS_TRACE(tid == 0, 39 + layer * 8);
+            ENS_TRACE(tid == 480, 71 + layer * 8);
+            const uint32_t d_src = tmem_lane + (layer & 1) * HID;
+            const float* hb = s_hb + (layer > 0 ? layer - 1 : 0) * HID;   // layers 1, 2 (layer 0's bias is in the MMA)
+            uint8_t* a_row = smem + Smem::A + lrow * 16;
+            // rounds 0-2: 16 columns per thread (K-step 4r + quarter); the loads run one round ahead
             uint32_t v[2][16];
-            tmem_ld16_nowait(d_src, v[0]);
+            tmem_ld16_nowait(d_src + quarter * 16, v[0]);
 #pragma unroll
-            for (int r = 0; r < ROUNDS; ++r) {
+            for (int r = 0; r < 3; ++r) {
               tmem_wait_ld16(v[r & 1]);
-              if (r + 1 < ROUNDS) tmem_ld16_nowait(d_src + (r + 1) * 64, v[(r + 1) & 1]);
-              uint8_t* dst = smem + Smem::A + (8 * r + 2 * quarter) * A_LBO + lrow * 16;
-              if (layer == 0) epilogue_round<false>(v[r & 1], nullptr, dst);
-              else epilogue_round<true>(v[r & 1], hb + r * 64, dst);
-              fence_proxy_async();   // generic-proxy writes of A -> async proxy (tensor core)
-              tc_fence_before();     // this thread's tcgen05.ld before the MMAs that follow the arrive
-              __syncwarp();
-              if (lane == 0) mbar_arrive_cluster(bar_full_leader + r * 8);
-              ENS_TRACE(tid == 0, 33 + layer * 8 + r);
-              ENS_TRACE(tid == 480, 65 + layer * 8 + r);
+              if (r + 1 < 3) tmem_ld16_nowait(d_src + (r + 1) * 64 + quarter * 16, v[(r + 1) & 1]);
+              uint8_t* dst = a_row + (8 * r + 2 * quarter) * A_LBO;
+              if (layer == 0) epilogue_round<16, false>(v[r & 1], nullptr, dst);
+              else epilogue_round<16, true>(v[r & 1], hb + r * 64 + quarter * 16, dst);
+              publish_round(bar_full_leader + r * 8, lane);
+              ENS_TRACE(tid == 0, 40 + layer * 8 + r);
+              ENS_TRACE(tid == 480, 72 + layer * 8 + r);
+            }
+            {  // round 3: 8 columns per thread (K-chunk 24 + quarter)
+              uint32_t w8[8];
+              tmem_ld8_nowait(d_src + 192 + quarter * 8, w8);
+              tmem_wait_ld8(w8);
+              uint8_t* dst = a_row + (24 + quarter) * A_LBO;
+              if (layer == 0) epilogue_round<8, false>(w8, nullptr, dst);
+              else epilogue_round<8, true>(w8, hb + 192 + quarter * 8, dst);
+              publish_round(bar_full_leader + 3 * 8, lane);
+              ENS_TRACE(tid == 0, 40 + layer * 8 + 3);
+            }
+#pragma unroll
+            for (int r = 4; r < 6; ++r) {  // rounds 4, 5: 4 columns per thread (half of K-chunk 28 / 30 + quarter / 2)
+              uint32_t w4[4];
+              const int col = round_first_col(r) + quarter * 4;
+              tmem_ld4_nowait(d_src + col, w4);
+              tmem_wait_ld4(w4);
+              uint8_t* dst = a_row + (col >> 3) * A_LBO + (col & 7) * 2;
+              if (layer == 0) epilogue_round<4, false>(w4, nullptr, dst);
+              else epilogue_round<4, true>(w4, hb + col, dst);
+              publish_round(bar_full_leader + r * 8, lane);
+              ENS_TRACE(tid == 0, 40 + layer * 8 + r);
+              ENS_TRACE(tid == 480, 72 + layer * 8 + r);
             }
           }
           if (row_owner) {
             mbar_wait(bar_out, ph_out);
             ph_out ^= 1;
             tc_fence_after();
-            ENS_TRACE(tid == 0, 56);
+            ENS_TRACE(tid == 0, 100);
             uint32_t o[8];
             tmem_ld8_nowait(tmem_lane + HID, o);
             tmem_wait_ld8(o);
@@ -454,7 +506,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ENS_THREADS, 1)
               fence_proxy_async();
               __syncwarp();
               if (lane == 0) mbar_arrive_cluster(bar_a0_leader);
-              ENS_TRACE(tid == 0, 57);
+              ENS_TRACE(tid == 0, 101);
             }
           }
         }
