@@ -179,6 +179,19 @@ int mbpo_icem_plan_staged(const MbpoIcemCfg* cfg_host, const void* sys_params_ho
                           float* best_seq_out, float* best_value_out, uint32_t* key_out,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- objective tail + array-valued bounds: pieces of the general staged plan ---------------- */
+/* iCemTO.objective's tail (icem_optimizer.py:158-166) for a deterministic System (P identical
+ * particles): values[i] <- summarize_reward(values[i]) - lambda * relu(summarize_cost(cost[i])).
+ * values [n] holds the horizon-mean reward of one particle; cost [n] (NULL = no cost_fn) the
+ * trajectory cost AbstractCost.__call__ returned (:78-90).  summarize_* are MBPO_SUMMARIZE_*
+ * (use_optimism :112-115, use_pessimism :116-119). */
+int mbpo_icem_penalize(float* values, const float* cost, long long n, int num_particles,
+                       int summarize_reward, int summarize_cost, float lambda_constraint, void* stream);
+/* jnp.clip(actions, u_min, u_max) with bounds broadcast to [H, A] (icem_optimizer.py:47-48,191):
+ * clips the N sampled rows of every problem of actions [B, M, D], D = H*A; u_min/u_max [D]. */
+int mbpo_icem_clip_actions(float* actions, const float* u_min, const float* u_max, int B, int M, int N,
+                           int D, void* stream);
+
 /* ---- closed-loop MPC (tests/test_icemopt.py:19-32): plan -> system.step -> warm start ---- */
 int mbpo_icem_mpc_closed_loop(const MbpoIcemCfg* cfg_host, const void* sys_params_host,
                               const float* x0 /*[B,X]*/, const uint32_t* key_in /*[B,2]*/,

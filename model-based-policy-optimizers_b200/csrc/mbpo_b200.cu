@@ -516,6 +516,30 @@ int mbpo_icem_plan_staged(const MbpoIcemCfg* cfg, const void* sys_params_host, c
   return MBPO_OK;
 }
 
+// ---- objective tail and array-valued bounds (the general staged plan composes these) -----------------
+int mbpo_icem_penalize(float* values, const float* cost, long long n, int num_particles, int summarize_reward,
+                       int summarize_cost, float lambda_constraint, void* stream) {
+  MBPO_REQUIRE(values, "penalize: null values");
+  MBPO_REQUIRE(n >= 0 && num_particles >= 1, "penalize: bad sizes");
+  MBPO_REQUIRE((summarize_reward == 0 || summarize_reward == 1) && (summarize_cost == 0 || summarize_cost == 1),
+               "penalize: bad summarize");
+  if (n == 0) return MBPO_OK;
+  penalize_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream)>>>(
+      values, cost, n, num_particles, summarize_reward, summarize_cost, lambda_constraint);
+  return check_launch("penalize_kernel");
+}
+
+int mbpo_icem_clip_actions(float* actions, const float* u_min, const float* u_max, int B, int M, int N, int D,
+                           void* stream) {
+  MBPO_REQUIRE(actions && u_min && u_max, "clip_actions: null pointer");
+  MBPO_REQUIRE(B >= 0 && M >= 0 && N >= 0 && N <= M && D >= 1, "clip_actions: bad sizes");
+  const long long total = static_cast<long long>(B) * M * D;
+  if (total == 0) return MBPO_OK;
+  clip_actions_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, as_stream(stream)>>>(actions, u_min, u_max,
+                                                                                                 total, M, N, D);
+  return check_launch("clip_actions_kernel");
+}
+
 // ---- closed-loop MPC -------------------------------------------------------------------------------
 int mbpo_icem_mpc_closed_loop(const MbpoIcemCfg* cfg, const void* sys_params_host, const float* x0,
                               const uint32_t* key_in, const float* best_seq_in, int B, int num_mpc_steps,

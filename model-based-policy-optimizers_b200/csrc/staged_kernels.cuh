@@ -170,4 +170,29 @@ __global__ void summarize_particles_kernel(float* values, long long n, int P, in
   if (i < n) values[i] = summarize_particles(values[i], P, summarize);
 }
 
+// iCemTO.objective's tail (icem_optimizer.py:158-166) for a deterministic System, whose P particles are
+// identical: values[i] = summarize(reward_i) - lambda * relu(summarize_cost(cost_i)).  cost may be null.
+__global__ void penalize_kernel(float* values, const float* __restrict__ cost, long long n, int P,
+                                int summarize_reward, int summarize_cost, float lambda) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = summarize_particles(values[i], P, summarize_reward);
+  if (cost) {
+    const float c = summarize_particles(cost[i], P, summarize_cost);
+    v = __fsub_rn(v, __fmul_rn(lambda, fmaxf(c, 0.0f)));
+  }
+  values[i] = v;
+}
+
+// jnp.clip(actions, u_min, u_max) with bounds broadcast to [H, A] (icem_optimizer.py:47-48,191): the N
+// sampled rows of every problem; the kept-elite rows (n >= N) are not clipped (:192).
+__global__ void clip_actions_kernel(float* actions, const float* __restrict__ u_min, const float* __restrict__ u_max,
+                                    long long total, int M, int N, int D) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int d = static_cast<int>(i % D);
+  const int m = static_cast<int>((i / D) % M);
+  if (m < N) actions[i] = fminf(fmaxf(actions[i], u_min[d]), u_max[d]);
+}
+
 }  // namespace mbpo

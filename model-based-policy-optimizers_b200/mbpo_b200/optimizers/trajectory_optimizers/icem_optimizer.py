@@ -60,8 +60,11 @@ class iCemTrainingOutput(OptimizerTrainingOutPut):
 
 
 class AbstractCost:
-    """icem_optimizer.py:78-90.  Constraint costs are a 'next' row: the CUDA
-    path has no kernel for an arbitrary Python cost and refuses it rather than falling back."""
+    """icem_optimizer.py:78-90: ``cost(states [H, X], actions [H, A]) -> scalar`` with the constraint
+    E[sum_t c(x_t, u_t)] <= 0.  Here the cost is a torch function of CUDA tensors; like the reference
+    (``vmap(self.cost_fn)``, :162) it is written for ONE trajectory and vmapped over problems and
+    candidates by the optimizer (torch.vmap).  The rollouts that feed it, the particle summaries and the
+    penalty ``reward - lambda * relu(cost)`` (:166) run in the CUDA library (staged plan)."""
 
     def __init__(self, horizon: int):
         self.horizon = horizon
@@ -70,11 +73,12 @@ class AbstractCost:
         raise NotImplementedError
 
 
-def _scalar_bound(v, name: str) -> float:
+def _scalar_bound(v):
+    """float(v) if the bound is a scalar (or an array of one repeated value), else None."""
     if isinstance(v, torch.Tensor):
         if v.numel() == 1 or bool((v == v.reshape(-1)[0]).all()):
             return float(v.reshape(-1)[0])
-        raise _lib.MbpoUnsupported(_lib.MBPO_EUNSUPPORTED, "array-valued %s is not supported by the CUDA path" % name)
+        return None
     try:
         return float(v)
     except TypeError:
@@ -82,7 +86,13 @@ def _scalar_bound(v, name: str) -> float:
         a = np.asarray(v, dtype=np.float32)
         if (a == a.reshape(-1)[0]).all():
             return float(a.reshape(-1)[0])
-        raise _lib.MbpoUnsupported(_lib.MBPO_EUNSUPPORTED, "array-valued %s is not supported by the CUDA path" % name)
+        return None
+
+
+def _array_bound(v, opt_dim, device) -> torch.Tensor:
+    """A bound broadcastable to (H, A) (icem_optimizer.py:47-48) as a contiguous float32 [H*A] device tensor."""
+    t = torch.as_tensor(v, dtype=torch.float32, device=device)
+    return torch.broadcast_to(t, opt_dim).reshape(-1).contiguous()
 
 
 class iCemTO(BaseOptimizer):
@@ -98,20 +108,23 @@ class iCemTO(BaseOptimizer):
         self.cost_fn = cost_fn
         self.use_optimism = use_optimism
         self.use_pessimism = use_pessimism
-        if cost_fn is not None:
-            raise _lib.MbpoUnsupported(_lib.MBPO_EUNSUPPORTED,
-                                       "cost_fn constraints have no CUDA kernel yet (no fallback path exists)")
 
     # ---- C-ABI configuration -----------------------------------------------------------------
+    def _array_bounds(self) -> bool:
+        p = self.opt_params
+        return _scalar_bound(p.u_min) is None or _scalar_bound(p.u_max) is None
+
     def _cfg(self) -> _lib.IcemCfgC:
         assert self.system is not None, "iCem optimizer requires system to be defined."
         p = self.opt_params
         cfg = _lib.IcemCfgC()
+        # array-valued bounds: the sampling kernel runs unclipped and mbpo_icem_clip_actions applies them
+        lo, hi = (float("-inf"), float("inf")) if self._array_bounds() else (_scalar_bound(p.u_min),
+                                                                           _scalar_bound(p.u_max))
         _lib.check(_lib.lib.mbpo_icem_cfg_init(
             _lib.C.byref(cfg), self.horizon, self.action_dim, self.system.x_dim, p.num_particles, p.num_samples,
             p.num_elites, p.init_std, p.alpha, p.num_steps, p.exponent, p.elite_set_fraction,
-            _scalar_bound(p.u_min, "u_min"), _scalar_bound(p.u_max, "u_max"), int(bool(p.warm_start)),
-            p.lambda_constraint))
+            lo, hi, int(bool(p.warm_start)), p.lambda_constraint))
         cfg.prng_mode = config.prng_mode
         cfg.summarize = _lib.SUMMARIZE_MAX if self.use_optimism else _lib.SUMMARIZE_MEAN   # :112-115
         cfg.system_kind = self.system.system_kind
@@ -137,6 +150,10 @@ class iCemTO(BaseOptimizer):
     def _plan_raw(self, x0: torch.Tensor, key: torch.Tensor, best_seq: torch.Tensor, system_params,
                   trace: bool = False):
         """x0 [B,X], key [B,2], best_seq [B,H,A] -> (best_seq', best_value, key', trace dict|None)."""
+        if self.cost_fn is not None or self._array_bounds():
+            if trace:
+                raise _lib.MbpoUnsupported(_lib.MBPO_EUNSUPPORTED, "trace dumps exist for the fused plan only")
+            return self._plan_general(x0, key, best_seq, system_params) + (None,)
         cfg = self._cfg()
         B = x0.shape[0]
         dev = x0.device
@@ -175,6 +192,71 @@ class iCemTO(BaseOptimizer):
                                                           _lib.stream_ptr(dev)))
         return out_seq, out_val, out_key, tr
 
+    def _plan_general(self, x0: torch.Tensor, key: torch.Tensor, best_seq: torch.Tensor, system_params):
+        """iCemTO.optimize with a constraint cost (:161-166) and / or array-valued bounds (:47-48): the
+        per-stage C-ABI kernels composed on the caller's stream.  Every number is produced by the CUDA
+        library except the user's own cost function, which is vmapped torch code on the same device."""
+        from ...systems.pendulum_system import PendulumSystem
+        cfg = self._cfg()
+        L = _lib
+        dev = x0.device
+        B, X = x0.shape
+        H, A = self.opt_dim
+        N, Np, S = cfg.num_samples, cfg.num_prev_elites, cfg.num_steps
+        M, D = N + Np, H * A
+        p = self.opt_params
+        if self.cost_fn is not None and not isinstance(self.system, PendulumSystem):
+            raise L.MbpoUnsupported(L.MBPO_EUNSUPPORTED, "cost_fn needs a System whose rollout kernel writes the "
+                                    "Transition observations (PendulumSystem)")
+        params = self.system.pack_params(system_params)
+        lo = hi = None
+        if self._array_bounds():
+            lo, hi = _array_bound(p.u_min, self.opt_dim, dev), _array_bound(p.u_max, self.opt_dim, dev)
+        cost_batched = None
+        if self.cost_fn is not None:
+            cost_batched = torch.vmap(torch.vmap(self.cost_fn))          # over problems, then candidates (:162)
+        st = L.stream_ptr(dev)
+        ks = jr.split(key, 2)                                             # optimizer_key, key  (:246)
+        carry, out_key = ks[:, 0].contiguous(), ks[:, 1].contiguous()
+        mean = torch.zeros((B, H, A), dtype=torch.float32, device=dev)
+        if p.warm_start:                                                  # :239-241
+            mean[:, :-1] = best_seq[:, 1:]
+            mean[:, -1] = best_seq[:, -1]
+        std = torch.full((B, H, A), float(p.init_std), dtype=torch.float32, device=dev)       # :243
+        bseq, bval = mean.clone(), torch.full((B,), float("-inf"), dtype=torch.float32, device=dev)   # :244,:235
+        actions = torch.empty((B, M, H, A), dtype=torch.float32, device=dev)
+        values = torch.empty((B, M), dtype=torch.float32, device=dev)
+        obs = torch.empty((B, M, H, X), dtype=torch.float32, device=dev) if cost_batched is not None else None
+        s_rew = L.SUMMARIZE_MAX if self.use_optimism else L.SUMMARIZE_MEAN    # :112-115
+        s_cost = L.SUMMARIZE_MAX if self.use_pessimism else L.SUMMARIZE_MEAN  # :116-119
+        with L.cuda_guard(x0):
+            for _ in range(S):
+                nxt_carry = torch.empty_like(carry)
+                L.check(L.lib.mbpo_icem_sample_actions(L.C.byref(cfg), L.ptr(carry), L.ptr(mean), L.ptr(std), B,
+                                                       L.ptr(actions), L.ptr(nxt_carry), None, st))
+                if lo is not None:
+                    L.check(L.lib.mbpo_icem_clip_actions(L.ptr(actions), L.ptr(lo), L.ptr(hi), B, M, N, D, st))
+                if self.system.system_kind == L.SYSTEM_MLP_ENSEMBLE:
+                    # particles = members; the rollout kernel summarises over them itself (:160)
+                    L.check(L.lib.mbpo_ensemble_rollout(L.C.addressof(params), H, L.ptr(x0), L.ptr(actions), B, M,
+                                                        s_rew, L.ptr(values), st))
+                else:
+                    L.check(L.lib.mbpo_rollout_actions(self.system.system_kind, L.C.addressof(params),
+                                                       config.math_mode_id, H, A, X, L.ptr(x0), L.ptr(actions), B, M,
+                                                       L.ptr(values), L.ptr(obs), None, None, st))
+                    cost = None
+                    if cost_batched is not None:
+                        cost = cost_batched(obs, actions).to(torch.float32).reshape(B, M).contiguous()
+                    L.check(L.lib.mbpo_icem_penalize(L.ptr(values), L.ptr(cost), B * M, cfg.num_particles, s_rew,
+                                                     s_cost, float(p.lambda_constraint), st))
+                n_mean, n_std = torch.empty_like(mean), torch.empty_like(std)
+                n_bval, n_bseq = torch.empty_like(bval), torch.empty_like(bseq)
+                L.check(L.lib.mbpo_icem_elite_refit(L.C.byref(cfg), L.ptr(actions), L.ptr(values), L.ptr(mean),
+                                                    L.ptr(std), L.ptr(bval), L.ptr(bseq), B, L.ptr(n_mean),
+                                                    L.ptr(n_std), L.ptr(n_bval), L.ptr(n_bseq), None, st))
+                carry, mean, std, bval, bseq = nxt_carry, n_mean, n_std, n_bval, n_bseq
+        return bseq, bval, out_key
+
     def _canon(self, initial_state: torch.Tensor, opt_state: iCemOptimizerState):
         single = initial_state.dim() == 1
         x0 = initial_state.reshape(1, -1) if single else initial_state
@@ -206,6 +288,9 @@ class iCemTO(BaseOptimizer):
     def closed_loop(self, initial_state: torch.Tensor, opt_state: iCemOptimizerState, num_steps: int):
         """Returns (states [T, (B,) X], rewards [T, (B)], actions [T, (B,) A], new opt_state)."""
         assert self.system is not None, "iCem optimizer requires system to be defined."
+        if self.cost_fn is not None or self._array_bounds():
+            raise _lib.MbpoUnsupported(_lib.MBPO_EUNSUPPORTED, "closed_loop runs the fused plan kernel, which has no "
+                                       "cost_fn / array-valued bounds; loop over act() instead")
         single, x0, key, seq = self._canon(initial_state, opt_state)
         cfg = self._cfg()
         B, dev = x0.shape[0], x0.device

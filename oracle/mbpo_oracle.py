@@ -438,7 +438,7 @@ def icem_sample_actions(carry_key, mean, std, params: ICemParams, horizon: int, 
     mean = np.asarray(mean, dtype=dtype)
     std = np.asarray(std, dtype=dtype)
     acts = (mean[None] + colored * std[None]).astype(dtype)           # :190
-    acts = np.clip(acts, dtype(params.u_min), dtype(params.u_max))    # :191
+    acts = np.clip(acts, np.asarray(params.u_min, dtype=dtype), np.asarray(params.u_max, dtype=dtype))   # :191
     prev_elites = np.zeros((npe, horizon, action_dim), dtype=dtype)   # closure zeros, :192,:245
     acts = np.concatenate([acts, prev_elites], axis=0)
     if return_bits:
@@ -455,13 +455,23 @@ def particle_mean(value_per_particle: np.ndarray, dtype=F32) -> np.ndarray:
     return (acc / dtype(p)).astype(dtype)
 
 
-def icem_objective(x0, acts, params: ICemParams, sys_params: PendulumParams, use_optimism=False, dtype=F32):
+def icem_objective(x0, acts, params: ICemParams, sys_params: PendulumParams, use_optimism=False, dtype=F32,
+                   cost_fn=None, use_pessimism=False):
     """vmap(objective) (icem_optimizer.py:144-166,195) for the deterministic pendulum: every
-    particle sees the same trajectory, so mean/max over particles is over P identical values."""
-    ret = rollout_actions(np.asarray(x0, dtype=dtype), acts[:, :, 0], sys_params, dtype)
-    if use_optimism or params.num_particles == 1:
-        return ret
-    return particle_mean(np.repeat(ret[:, None], params.num_particles, axis=1), dtype)
+    particle sees the same trajectory, so mean/max over particles is over P identical values.
+    cost_fn(states [M,H,X], actions [M,H,A]) -> [M] is the (already vmapped) AbstractCost (:161-166)."""
+    def summarize(v, use_max):
+        if use_max or params.num_particles == 1:
+            return v
+        return particle_mean(np.repeat(v[:, None], params.num_particles, axis=1), dtype)
+    if cost_fn is None:
+        ret = rollout_actions(np.asarray(x0, dtype=dtype), acts[:, :, 0], sys_params, dtype)
+        return summarize(ret, use_optimism)
+    ret, obs, _, _ = rollout_actions(np.asarray(x0, dtype=dtype), acts[:, :, 0], sys_params, dtype, full=True)
+    cost = np.asarray(cost_fn(obs, acts), dtype=dtype)
+    cost = summarize(cost, use_pessimism)
+    pen = (dtype(params.lambda_constraint) * np.maximum(cost, dtype(0))).astype(dtype)         # :166
+    return (summarize(ret, use_optimism) - pen).astype(dtype)
 
 
 def icem_refit(acts, values, mean, std, best_value, best_seq, params: ICemParams, dtype=F32):
@@ -491,7 +501,8 @@ def icem_refit(acts, values, mean, std, best_value, best_seq, params: ICemParams
 
 def icem_optimize(x0, state: ICemState, params: ICemParams, horizon: int, action_dim: int = 1,
                   sys_params: PendulumParams = PendulumParams(), use_optimism: bool = False,
-                  partitionable: bool = False, dtype=F32, trace: Optional[list] = None) -> ICemState:
+                  partitionable: bool = False, dtype=F32, trace: Optional[list] = None,
+                  cost_fn=None, use_pessimism: bool = False) -> ICemState:
     """iCemTO.optimize (icem_optimizer.py:134-252) for one problem."""
     mean = np.zeros((horizon, action_dim), dtype=dtype)
     if params.warm_start:                                             # :239-241
@@ -506,7 +517,7 @@ def icem_optimize(x0, state: ICemState, params: ICemParams, horizon: int, action
         in_key, in_mean, in_std = carry_key, mean, std
         carry_key, acts, _ = icem_sample_actions(carry_key, mean, std, params, horizon, action_dim,
                                                  partitionable, dtype)
-        values = icem_objective(x0, acts, params, sys_params, use_optimism, dtype)    # :195
+        values = icem_objective(x0, acts, params, sys_params, use_optimism, dtype, cost_fn, use_pessimism)   # :195
         mean, std, best_value, best_seq, idx = icem_refit(acts, values, mean, std, best_value,
                                                           best_seq, params, dtype)
         if trace is not None:

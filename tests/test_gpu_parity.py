@@ -343,6 +343,126 @@ def test_plan_end_to_end_vs_oracle(mb, cuda_device):
     assert agree >= B - 2
 
 
+class _SpeedLimit:
+    """AbstractCost: the largest |thdot| along the trajectory must stay below `limit` (max is exact in
+    float32, so the GPU and the oracle see bit-identical costs for bit-identical observations)."""
+
+    def __init__(self, limit):
+        self.limit = limit
+
+    def __call__(self, states, actions):                       # one trajectory: [H, 3], [H, 1] -> scalar
+        return states[:, 2].abs().max() - self.limit
+
+    def numpy(self, obs, acts):                                # vmapped: [M, H, 3] -> [M]
+        return (np.abs(obs[:, :, 2]).max(axis=1) - np.float32(self.limit)).astype(np.float32)
+
+
+@pytest.mark.parametrize("use_pessimism", [False, True])
+def test_plan_with_cost_fn_vs_oracle(mb, cuda_device, use_pessimism):
+    """iCemTO with a constraint cost (icem_optimizer.py:161-166): staged CUDA plan against the oracle."""
+    from mbpo_b200.optimizers import iCemTO, iCemParams
+    from mbpo_b200.systems import PendulumSystem
+    from mbpo_b200.utils import rollout_actions
+    horizon, B = 20, 8
+    params = dict(num_samples=200, num_elites=20, num_particles=3, num_steps=3, lambda_constraint=10.0)
+    cost = _SpeedLimit(5.0)
+    opt = iCemTO(horizon=horizon, action_dim=1, opt_params=iCemParams(**params), cost_fn=cost,
+                 use_pessimism=use_pessimism)
+    system = PendulumSystem()
+    opt.set_system(system)
+    keys = _keys(B, seed=23)
+    st = opt.init(_dev(keys, cuda_device))
+    x0 = _random_states(B, 24)
+    action, new = opt.act(_dev(x0, cuda_device), st)
+    assert action.shape == (B, 1) and new.best_sequence.shape == (B, horizon, 1)
+    agree = 0
+    for b in range(B):
+        ost = orc.icem_init(keys[b], horizon)
+        onew = orc.icem_optimize(x0[b], ost, orc.ICemParams(**params), horizon, cost_fn=cost.numpy,
+                                 use_pessimism=use_pessimism)
+        assert np.array_equal(new.key[b].cpu().numpy(), onew.key)
+        if np.allclose(new.best_sequence[b].cpu().numpy(), onew.best_sequence, rtol=RTOL, atol=5e-6):
+            agree += 1
+            np.testing.assert_allclose(float(new.best_reward[b]), float(onew.best_reward), rtol=1e-4, atol=1e-4)
+    assert agree >= B - 2
+    # best_reward is the penalised objective of best_sequence: recompute it from the Transition
+    tr = rollout_actions(system, st.system_params, _dev(x0, cuda_device), new.best_sequence.reshape(B, 1, horizon, 1),
+                         horizon)
+    ret = tr.reward[:, 0].cpu().numpy()
+    obs = tr.observation[:, 0].cpu().numpy()
+    acc = np.zeros(B, np.float32)
+    for t in range(horizon):
+        acc = (acc + ret[:, t]).astype(np.float32)
+    rew = (acc / np.float32(horizon)).astype(np.float32)
+    c = cost.numpy(obs, None)
+    p3 = lambda v: ((v + v + v) / np.float32(3)).astype(np.float32)                 # mean over 3 identical particles
+    c_s = c if use_pessimism else p3(c)
+    want = (p3(rew) - np.float32(10.0) * np.maximum(c_s, np.float32(0))).astype(np.float32)
+    np.testing.assert_allclose(new.best_reward.cpu().numpy(), want, rtol=1e-6, atol=1e-6)
+    # the constraint binds for fast initial states: penalised value below the plain return there
+    assert np.all(new.best_reward.cpu().numpy() <= p3(rew) + 1e-6)
+    with pytest.raises(mb.MbpoUnsupported):                                       # closed loop is the fused kernel only
+        opt.closed_loop(_dev(x0, cuda_device), st, 2)
+
+
+def test_plan_with_array_bounds_vs_oracle(mb, cuda_device):
+    """u_min / u_max broadcastable to (H, A) (icem_optimizer.py:47-48,191)."""
+    from mbpo_b200.optimizers import iCemTO, iCemParams
+    from mbpo_b200.systems import PendulumSystem
+    horizon, B = 20, 6
+    u_min = -np.linspace(0.2, 1.0, horizon, dtype=np.float32).reshape(horizon, 1)
+    u_max = np.linspace(1.0, 0.3, horizon, dtype=np.float32).reshape(horizon, 1)
+    params = dict(num_samples=200, num_elites=20, num_particles=1, num_steps=3, u_min=u_min, u_max=u_max)
+    opt = iCemTO(horizon=horizon, action_dim=1, opt_params=iCemParams(**params))
+    opt.set_system(PendulumSystem())
+    keys = _keys(B, seed=25)
+    st = opt.init(_dev(keys, cuda_device))
+    x0 = _random_states(B, 26)
+    action, new = opt.act(_dev(x0, cuda_device), st)
+    seq = new.best_sequence.cpu().numpy()
+    assert np.all(seq >= u_min[None] - 1e-7) and np.all(seq <= u_max[None] + 1e-7)
+    agree = 0
+    for b in range(B):
+        onew = orc.icem_optimize(x0[b], orc.icem_init(keys[b], horizon), orc.ICemParams(**params), horizon)
+        assert np.array_equal(new.key[b].cpu().numpy(), onew.key)
+        if np.allclose(seq[b], onew.best_sequence, rtol=RTOL, atol=5e-6):
+            agree += 1
+            np.testing.assert_allclose(float(new.best_reward[b]), float(onew.best_reward), rtol=1e-5, atol=1e-6)
+    assert agree >= B - 2
+    # scalar bounds given as arrays take the fused path and agree with plain scalars bit for bit
+    o1 = iCemTO(horizon=horizon, action_dim=1, opt_params=iCemParams(num_samples=128, num_particles=1,
+                                                                     u_min=np.full((horizon, 1), -0.5, np.float32),
+                                                                     u_max=0.5))
+    o2 = iCemTO(horizon=horizon, action_dim=1, opt_params=iCemParams(num_samples=128, num_particles=1, u_min=-0.5,
+                                                                     u_max=0.5))
+    o1.set_system(PendulumSystem()); o2.set_system(PendulumSystem())
+    n1 = o1.optimize(_dev(x0, cuda_device), st)
+    n2 = o2.optimize(_dev(x0, cuda_device), st)
+    assert torch.equal(n1.best_sequence, n2.best_sequence) and torch.equal(n1.best_reward, n2.best_reward)
+
+
+def test_general_staged_plan_matches_fused(mb, cuda_device):
+    """The Python-composed staged plan (cost / array-bounds route) with a never-binding cost reproduces the
+    fused kernel bit for bit: same kernels' arithmetic, x - lambda * relu(negative) = x."""
+    from mbpo_b200.optimizers import iCemTO, iCemParams
+    from mbpo_b200.systems import PendulumSystem
+    horizon, B = 20, 5
+    params = dict(num_samples=128, num_elites=16, num_particles=10, num_steps=4, alpha=0.1)
+    free = _SpeedLimit(1e6)
+    for optimism in (False, True):
+        fused = iCemTO(horizon=horizon, action_dim=1, opt_params=iCemParams(**params), use_optimism=optimism)
+        staged = iCemTO(horizon=horizon, action_dim=1, opt_params=iCemParams(**params), cost_fn=free,
+                        use_optimism=optimism)
+        fused.set_system(PendulumSystem()); staged.set_system(PendulumSystem())
+        keys = _dev(_keys(B, seed=27), cuda_device)
+        st = fused.init(keys)
+        st = st.replace(best_sequence=torch.rand_like(st.best_sequence) - 0.5)    # exercise the warm start
+        x0 = _dev(_random_states(B, 28), cuda_device)
+        a, b_ = fused.optimize(x0, st), staged.optimize(x0, st)
+        assert torch.equal(a.key, b_.key)
+        assert torch.equal(a.best_sequence, b_.best_sequence) and torch.equal(a.best_reward, b_.best_reward)
+
+
 def test_staged_plan_matches_fused(mb, cuda_device):
     L = mb._lib
     from mbpo_b200.systems import PendulumSystem

@@ -203,3 +203,34 @@ def test_mlp_oracle_bf16_rounding():
     assert a.shape == (64, 3) and np.abs(a - b).max() < 5e-2 and np.abs(a - b).max() > 0
     r = orc._bf16_round(np.array([1.0, 1.00390625, 1.0058594, -2.5], np.float32))
     assert r.tolist() == [1.0, 1.0, 1.0078125, -2.5]                              # round to nearest even
+
+
+def test_oracle_cost_fn_penalty_and_array_bounds():
+    """icem_optimizer.py:161-166 (reward - lambda * relu(cost), mean / max over identical particles) and
+    :47-48,191 (bounds broadcastable to (H, A)) in the oracle."""
+    horizon = 12
+    p = orc.ICemParams(num_samples=64, num_elites=8, num_particles=3, num_steps=2, lambda_constraint=10.0)
+    x0 = np.array([np.cos(2.0), np.sin(2.0), 6.5], np.float32)
+    key = jr.PRNGKey(5)
+    mean = np.zeros((horizon, 1), np.float32)
+    std = np.full((horizon, 1), 0.5, np.float32)
+    _, acts, _ = orc.icem_sample_actions(key, mean, std, p, horizon)
+    plain = orc.icem_objective(x0, acts, p, orc.PendulumParams())
+    never = lambda obs, a: (np.abs(obs[:, :, 2]).max(axis=1) - np.float32(1e6)).astype(np.float32)
+    binds = lambda obs, a: (np.abs(obs[:, :, 2]).max(axis=1) - np.float32(5.0)).astype(np.float32)
+    assert np.array_equal(orc.icem_objective(x0, acts, p, orc.PendulumParams(), cost_fn=never), plain)
+    pen = orc.icem_objective(x0, acts, p, orc.PendulumParams(), cost_fn=binds)
+    pes = orc.icem_objective(x0, acts, p, orc.PendulumParams(), cost_fn=binds, use_pessimism=True)
+    assert np.all(pen < plain) and np.all(pes < plain)                   # thdot0 = 6.5 > 5: the constraint binds
+    c = binds(orc.rollout_actions(x0, acts[:, :, 0], full=True)[1], acts)
+    np.testing.assert_allclose(plain - pes, 10.0 * c, rtol=1e-6)
+    np.testing.assert_allclose(pen, pes, rtol=1e-5, atol=1e-5)            # mean of 3 identical vs max: rounding only
+    # array-valued bounds
+    u_min = -np.linspace(0.1, 1.0, horizon, dtype=np.float32).reshape(horizon, 1)
+    u_max = np.linspace(1.0, 0.2, horizon, dtype=np.float32).reshape(horizon, 1)
+    pb = orc.ICemParams(num_samples=64, num_elites=8, num_particles=1, num_steps=2, u_min=u_min, u_max=u_max)
+    _, ab, _ = orc.icem_sample_actions(key, mean, std, pb, horizon)
+    assert np.all(ab >= u_min[None]) and np.all(ab <= u_max[None])
+    assert np.array_equal(ab[:64], np.clip(acts[:64] * 0 + (mean[None] + (acts[:64] - acts[:64])) + ab[:64], u_min, u_max))
+    st = orc.icem_optimize(x0, orc.icem_init(jr.PRNGKey(1), horizon), pb, horizon)
+    assert np.all(st.best_sequence >= u_min) and np.all(st.best_sequence <= u_max)
