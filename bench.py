@@ -585,6 +585,214 @@ def run_ensemble(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# config 1: the reference's own test loop (tests/test_icemopt.py:19-32) as one launch
+# ------------------------------------------------------------------------------------------------
+MPC_T, MPC_H = 200, 20
+
+
+def run_closed_loop(args):
+    """A "step" is one 200-step closed-loop MPC episode from x0 = [-1, 0, 0] with iCemParams() defaults
+    (P = 10, N = 500, H = 20): plan -> true System.step -> warm start, 200 times, in ONE kernel launch."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return                                   # a single problem does not shard: "replicas only"
+    from oracle import c_twin, jax_prng as jr, mbpo_oracle as orc
+    p_or = orc.ICemParams()
+    tr_plan_written = transitions_per_step(1, MPC_H, p_or)                       # 515,000 (P = 10 as written)
+    if args.impl == "reference":
+        lib = c_twin.load(native=True)
+        cfg = c_twin.make_cfg(p_or, MPC_H)
+        p9 = orc.PendulumParams().packed()
+        ks = jr.split(jr.PRNGKey(0), 3)
+        st = orc.icem_init(ks[1], MPC_H)
+        T = 20                                                                   # bounded sample of the 200 steps
+        x0 = np.array([-1, 0, 0], np.float32)
+        c_twin.closed_loop(lib, cfg, p9, x0, st.key, st.best_sequence, 2)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            c_twin.closed_loop(lib, cfg, p9, x0, st.key, st.best_sequence, T)
+        dt = (time.perf_counter() - t0) / args.steps
+        ncores, model = host_info()
+        v = T * tr_plan_written / dt
+        emit_json({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+                   "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "ms_per_plan_call": dt * 1e3 / T,
+                   "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                   "config": {"workload": "config1_closed_loop", "mpc_steps": MPC_T, "horizon": MPC_H,
+                              "num_samples": 500, "num_particles": 10},
+                   "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": "%d of %d closed-loop steps, C restatement, one problem = one thread" % (T, MPC_T),
+                                    "host_cpu": model},
+                   "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}, GUARD)
+        return
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import mbpo_b200
+    from mbpo_b200.optimizers import iCemTO, iCemParams
+    from mbpo_b200.systems import PendulumSystem
+    mbpo_b200.config.math_mode = args.math
+    jrr = mbpo_b200.random
+    ks = jrr.split(jrr.PRNGKey(0, dev), 3)
+    system = PendulumSystem()
+    system_state = system.reset(ks[2])
+    cem = iCemTO(horizon=MPC_H, action_dim=1, system=None, opt_params=iCemParams(), key=ks[0])
+    cem.set_system(system)
+    st = cem.init(ks[1])
+    x0_host = system_state.x_next.cpu().pin_memory()
+    x0 = x0_host.to(dev)
+    for _ in range(max(args.warmup, 3)):
+        cem.closed_loop(x0, st, MPC_T)
+    torch.cuda.synchronize(dev)
+    steps = min(args.steps, 20)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    with ClockSampler(local_rank) as clk:
+        for k in range(steps):
+            flush.zero_()
+            starts[k].record()
+            states, rewards, actions, _ = cem.closed_loop(x0, st, MPC_T)
+            ends[k].record()
+        torch.cuda.synchronize(dev)
+    ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends)) / steps
+    total_reward = float(rewards.sum())
+    rew_host = torch.empty((MPC_T,), dtype=torch.float32).pin_memory()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for k in range(steps):
+        _, r, _, _ = cem.closed_loop(x0_host.to(dev, non_blocking=True), st, MPC_T)
+        rew_host.copy_(r, non_blocking=True)
+        torch.cuda.synchronize(dev)
+    e2e_s = (time.perf_counter() - t0) / steps
+    sm_max = 1965.0
+    try:
+        sm_max = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("sm_max_mhz", 1965.0))
+    except Exception:
+        pass
+    emit_json({
+        "metric": METRIC, "value": MPC_T * tr_plan_written / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "ms_per_plan_call": ms / MPC_T, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "config1_closed_loop", "mpc_steps": MPC_T, "horizon": MPC_H, "num_samples": 500,
+                   "num_elites": 50, "num_prev_elites": 15, "num_particles": 10, "cem_iterations": 5,
+                   "transitions_counted": "as written in the reference (x10 identical particles); distinct = value / 10",
+                   "l2": "flushed (256 MiB memset) before every timed step"},
+        "math_mode": args.math, "sum_rewards": total_reward, "reference_test_threshold": -400.0,
+        "clocks": clk.summary(),
+        "e2e": {"value": MPC_T * tr_plan_written / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
+                "h2d_bytes_per_step": 12, "d2h_bytes_per_step": 4 * MPC_T,
+                "api": "iCemTO.closed_loop(x0 from pinned host, 200 steps) -> rewards[200] to pinned host"},
+        "gpu_launches": steps,
+        "roofline": {"bound": "issue", "kernel": "icem_mpc_pendulum_kernel", "achieved": None,
+                     "peak": 148 * 4 * 32 * sm_max * 1e6 / 1e12, "unit": "T lane-instr/s", "frac": None, "traffic": None,
+                     "note": "one problem occupies one CTA of one SM: the episode is latency-bound by construction "
+                             "(1/148 of the chip); throughput configurations are config 2 / config 5"},
+        "cpu_baseline": None}, GUARD)
+
+
+# ------------------------------------------------------------------------------------------------
+# config 5: throughput sweep over the number of independent planning problems
+# ------------------------------------------------------------------------------------------------
+SWEEP_B = (1, 8, 64, 512, 4096, 32768, 262144, 1048576)
+
+
+def run_sweep(args):
+    """Config-2 parameters with B in SWEEP_B TOTAL problems sharded over the ranks (strong scaling per B)."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    wl = WORKLOADS["config2_batched_icem"]
+    H = wl["horizon"]
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        rows = []
+        for B in (1, 8, 64, 512):
+            w = dict(wl, B=B)
+            r = cpu_reference_step(w, steps=1, warmup=1, sample_B=B)
+            rows.append({"problems": B, "ms": r["ms_per_step"], "transitions_per_s": r["value"], "cores": r["cores"]})
+        ncores, model = host_info()
+        best = max(rows, key=lambda r: r["transitions_per_s"])
+        emit_json({"impl": "reference", "metric": METRIC, "value": best["transitions_per_s"], "unit": UNIT,
+                   "n_gpus": args.gpus, "steps": 1, "warmup": 1, "ms_per_step": best["ms"], "higher_is_better": True,
+                   "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                   "config": {"workload": "config5_sweep", "horizon": H, "num_samples": 512},
+                   "sweep": rows,
+                   "cpu_baseline": {"value": best["transitions_per_s"], "unit": UNIT, "cores": best["cores"], "kind": "port",
+                                    "sample": "B in {1, 8, 64, 512} (larger B scale linearly on the CPU)", "host_cpu": model},
+                   "e2e": {"value": best["transitions_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                           "d2h_bytes_per_step": 0}}, GUARD)
+        return
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import mbpo_b200
+    from mbpo_b200.optimizers import iCemTO, iCemParams
+    from mbpo_b200.parallel import shard_bounds
+    from mbpo_b200.systems import PendulumSystem
+    mbpo_b200.config.math_mode = args.math
+    p = iCemParams(**wl["params"])
+    opt = iCemTO(horizon=H, action_dim=1, opt_params=p)
+    opt.set_system(PendulumSystem())
+    Bmax = max(SWEEP_B)
+    lo_m, hi_m = shard_bounds(Bmax, rank, world)
+    # keys / states of the largest sweep point; smaller points use a prefix (same problems at every world size)
+    base_key = mbpo_b200.random.PRNGKey(0, dev)
+    rows = []
+    clocks = None
+    for B in SWEEP_B:
+        lo, hi = shard_bounds(B, rank, world)
+        n = hi - lo
+        keys = mbpo_b200.random.split(base_key, B)[lo:hi].contiguous() if n > 0 else None
+        if n > 0:
+            state = opt.init(keys)
+            x0 = torch.from_numpy(random_states(B, 0)[lo:hi].copy()).to(dev)
+        steps = 20 if B <= 4096 else (5 if B <= 32768 else 2)
+        for _ in range(3):
+            if n > 0:
+                opt.optimize(x0, state)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as clk:
+            e0.record()
+            for _ in range(steps):
+                if n > 0:
+                    opt.optimize(x0, state)
+            e1.record()
+            torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        rows.append({"problems": B, "ms_per_plan_call": ms, "transitions_per_s": transitions_per_step(B, H, p) / (ms * 1e-3)})
+        clocks = clk.summary()
+        if n > 0:
+            del state, x0, keys
+    if rank == 0:
+        top = rows[-1]
+        emit_json({"metric": METRIC, "value": top["transitions_per_s"], "unit": UNIT, "n_gpus": world, "steps": 2,
+                   "warmup": 3, "ms_per_step": top["ms_per_plan_call"], "higher_is_better": True, "scaling": "strong",
+                   "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                   "config": {"workload": "config5_sweep", "problems_total": [r["problems"] for r in rows], "horizon": H,
+                              "num_samples": 512, "num_particles": 1, "cem_iterations": 5,
+                              "parallelism": "problems sharded x%d" % world,
+                              "l2": "back-to-back launches; per-problem state is ~0.4 KB and the kernel works out of shared memory"},
+                   "math_mode": args.math, "sweep": rows, "clocks": clocks,
+                   "gpu_launches": sum((20 if r["problems"] <= 4096 else (5 if r["problems"] <= 32768 else 2)) * 2 for r in rows),
+                   "roofline": None, "cpu_baseline": None,
+                   "e2e": None}, GUARD)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 class _StdoutGuard:
     """Everything the libraries print (e.g. the NCCL version banner) goes to stderr; only the final
     JSON line reaches the real stdout."""
@@ -615,7 +823,9 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["config3_env_rollouts", "config4_ensemble_icem"], default="config2_batched_icem")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["config1_closed_loop", "config3_env_rollouts",
+                                                               "config4_ensemble_icem", "config5_sweep"],
+                    default="config2_batched_icem")
     ap.add_argument("--math", choices=["reference", "theta_carry"], default="reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -625,6 +835,10 @@ def main():
             return run_env(args)
         if args.workload == "config4_ensemble_icem":
             return run_ensemble(args)
+        if args.workload == "config1_closed_loop":
+            return run_closed_loop(args)
+        if args.workload == "config5_sweep":
+            return run_sweep(args)
         wl = WORKLOADS[args.workload]
         if args.impl == "reference":
             run_reference(args, args.workload, wl)
