@@ -14,7 +14,7 @@
 #include "host_util.h"
 #include "mlp_kernels.cuh"
 #include "mlp_tc_kernels.cuh"
-#include "ensemble_kernels.cuh"
+#include "ensemble_pp_kernels.cuh"
 #include "plan_dispatch.h"
 #include "staged_kernels.cuh"
 
@@ -614,7 +614,7 @@ int mbpo_ensemble_rollout(const MbpoMlpEnsembleParams* p, int horizon, const flo
   MBPO_REQUIRE(horizon >= 1 && B >= 0 && M >= 0, "ensemble_rollout: bad sizes");
   MBPO_REQUIRE(summarize == 0 || summarize == 1, "ensemble_rollout: bad summarize %d", summarize);
   if (static_cast<long long>(B) * M == 0) return MBPO_OK;
-  const int rc = ens::launch_ensemble_rollout(*p, horizon, x0, actions, B, M, summarize, returns_out,
+  const int rc = ens::launch_ensemble_rollout_auto(*p, horizon, x0, actions, B, M, summarize, returns_out,
                                               as_stream(stream), g_err, sizeof(g_err));
   if (rc != MBPO_OK) return rc;
   return check_launch("ensemble_rollout_kernel");

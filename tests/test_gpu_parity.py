@@ -649,9 +649,16 @@ def _ensemble_on_device(mb, cuda_device, ens):
     return MLPEnsembleSystem(), SystemParams(dynamics_params=dyn, reward_params=PendulumRewardParams())
 
 
-@pytest.mark.parametrize("B,M,H", [(1, 256, 5), (3, 139, 12), (2, 527, 8)])
-def test_ensemble_rollout_fused_tcgen05(mb, cuda_device, B, M, H):
-    """Fused cta_group::2 rollout kernel against the oracle (same bf16 operand rounding, fp32 accumulate)."""
+@pytest.fixture(params=["single", "pp"])
+def ens_variant(request, monkeypatch):
+    """Both fused rollout kernels (one row tile per CTA / two tiles ping-pong) at every size."""
+    monkeypatch.setenv("MBPO_ENS_VARIANT", request.param)
+    return request.param
+
+
+@pytest.mark.parametrize("B,M,H", [(1, 256, 5), (3, 139, 12), (2, 527, 8), (5, 300, 3)])
+def test_ensemble_rollout_fused_tcgen05(mb, cuda_device, ens_variant, B, M, H):
+    """Fused cta_group::2 rollout kernels against the oracle (same bf16 operand rounding, fp32 accumulate)."""
     ens = orc.make_mlp_ensemble(seed=3, members=5)
     sys_, sp = _ensemble_on_device(mb, cuda_device, ens)
     x0 = _random_states(B, 71)
