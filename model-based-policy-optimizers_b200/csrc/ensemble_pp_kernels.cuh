@@ -14,7 +14,9 @@
 //   A ring    the bf16 A operand exists only as a ring of five 16 KB chunks (64 K-columns x 128 rows):
 //             the epilogue of one tile fills chunks while the MMAs of the other tile drain them; a full
 //             A tile per row tile (2 x 64 KB) would not fit beside the 128 KB of resident weights.
-//             full[slot]  (leader CTA, 32 warp arrivals)   chunk published by both CTAs
+//             stage[tile] (leader CTA, 32 warp arrivals)   all four chunks of the tile's next A operand are
+//                                                          published by both CTAs (one arrive per warp per
+//                                                          stage: the MMAs cannot start earlier anyway)
 //             empty[slot] (both CTAs, tcgen05.commit)      the MMAs that read the chunk have completed
 //   order     epilogue warps, per horizon step:  E0(X) E0(Y) E1(X) E1(Y) E2(X) E2(Y) E3(X) E3(Y)
 //             MMA issuer,     per horizon step:  M0(X) M0(Y) M1(X) M1(Y) M2(X) M2(Y) M3(X) M3(Y)
@@ -39,8 +41,8 @@ struct PpSmem {
   static constexpr uint32_t W3 = W0 + 128 * 32;                          // 8 x 256 bf16 output layer hi/lo rows
   static constexpr uint32_t HB = W3 + 8 * HID * 2;                       // float [2][256]: 0.5 * b_h
   static constexpr uint32_t B_OUT = HB + 2 * HID * 4;                    // float [4]
-  static constexpr uint32_t BARS = B_OUT + 16;   // full[5] empty[5] acc_done[2] out_done[2] a0_full[2] bar_w
-  static constexpr uint32_t TMEM_PTR = BARS + (2 * PP_SLOTS + 7) * 8;
+  static constexpr uint32_t BARS = B_OUT + 16;   // stage[2] empty[5] acc_done[2] out_done[2] a0_full[2] bar_w
+  static constexpr uint32_t TMEM_PTR = BARS + (PP_SLOTS + 9) * 8;
   static constexpr uint32_t TOTAL = TMEM_PTR + 16;
 };
 static_assert(PpSmem::TOTAL <= 227 * 1024, "ping-pong ensemble rollout shared memory plan exceeds 227 KB");
@@ -53,11 +55,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ENS_THREADS, 1)
   const int lrow = ((warp & 3) << 5) | lane;           // row within a tile = TMEM lane
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  const bool row_owner = warp < 4;                     // the thread that carries the rows' state (one row per tile)
+  const bool row_owner = quarter == 3;   // warps 12-15 carry the rows' state: the warp scheduler favours the
+                                          // highest warp ids, and the state update is the serial link between steps
   float* s_hb = reinterpret_cast<float*>(smem + PpSmem::HB);
   float* s_b_out = reinterpret_cast<float*>(smem + PpSmem::B_OUT);
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + PpSmem::BARS);
-  uint64_t* bar_empty = bar_full + PP_SLOTS;
+  uint64_t* bar_stage = reinterpret_cast<uint64_t*>(smem + PpSmem::BARS);   // [2] leader: tile's A chunks published
+  uint64_t* bar_empty = bar_stage + 2;
   uint64_t* bar_acc = bar_empty + PP_SLOTS;            // [2] accumulator of layer 0/1/2 of tile t complete
   uint64_t* bar_out = bar_acc + 2;                     // [2] output-layer accumulator of tile t complete
   uint64_t* bar_a0 = bar_out + 2;                      // [2] leader: split-input rows of tile t published
@@ -71,11 +74,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ENS_THREADS, 1)
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
   }
   if (tid == 0) {
-    for (int s = 0; s < PP_SLOTS; ++s) {
-      mbar_init(bar_full + s, 2 * EPI_WARPS);
-      mbar_init(bar_empty + s, 1);
-    }
+    for (int s = 0; s < PP_SLOTS; ++s) mbar_init(bar_empty + s, 1);
     for (int t = 0; t < 2; ++t) {
+      mbar_init(bar_stage + t, 2 * EPI_WARPS);
       mbar_init(bar_acc + t, 1);
       mbar_init(bar_out + t, 1);
       mbar_init(bar_a0 + t, 2 * 4);
@@ -92,13 +93,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ENS_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
   const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-  const uint32_t bar_full_leader = map_to_cta(smem_u32(bar_full), 0);
+  const uint32_t bar_stage_leader = map_to_cta(smem_u32(bar_stage), 0);
   const uint32_t bar_a0_leader = map_to_cta(smem_u32(bar_a0), 0);
   constexpr uint32_t IDESC = umma_idesc_bf16(2 * TILE_M, HID);
   constexpr uint32_t IDESC_OUT = umma_idesc_bf16(2 * TILE_M, 16);
   uint32_t phase_w = 0;
   uint32_t ph_acc[2] = {0, 0}, ph_out[2] = {0, 0};   // epilogue warps
-  uint32_t ph_a0[2] = {0, 0};                        // MMA warp
+  uint32_t ph_a0[2] = {0, 0}, ph_stage[2] = {0, 0};  // MMA warp
   uint32_t ring_pos = 0;                             // chunks produced (epilogue warps) / consumed (MMA warp) so far
   uint32_t ring_slot = 0, ring_use = 0;              // ring_pos % PP_SLOTS, ring_pos / PP_SLOTS
   (void)ring_pos;
@@ -191,6 +192,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ENS_THREADS, 1)
               mbar_wait(bar_a0 + tl, ph_a0[tl]);
               ph_a0[tl] ^= 1;
               tc_fence_after();
+              ENS_TRACE(lane == 0, tl);
               if (elected) {
                 umma_bf16_ss_2sm(tmem_u + tl * HID, desc_a0 + static_cast<uint64_t>(tl * A0_TILE_STEP), desc_w0, IDESC, 0u);
                 umma_commit_2sm(bar_acc + tl);
@@ -203,14 +205,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ENS_THREADS, 1)
 #pragma unroll
               for (int tl = 0; tl < 2; ++tl) {
                 const uint32_t d = tmem_u + tl * HID;
-                // the tile has ONE accumulator: issue only when its previous epilogue has published all chunks
-                uint32_t slot = ring_slot, use = ring_use;
-#pragma unroll
-                for (int r = 0; r < PP_ROUNDS; ++r) {
-                  mbar_wait(bar_full + slot, use & 1);
-                  if (++slot == PP_SLOTS) { slot = 0; ++use; }
-                }
+                // the tile has ONE accumulator: its MMAs start when the previous epilogue has read all of it,
+                // i.e. when every warp of both CTAs has published the stage
+                mbar_wait(bar_stage + tl, ph_stage[tl]);
+                ph_stage[tl] ^= 1;
                 tc_fence_after();
+                ENS_TRACE(lane == 0, 2 + ((layer - 1) * 2 + tl) * 2);
 #pragma unroll
                 for (int r = 0; r < PP_ROUNDS; ++r) {
                   if (elected) {
@@ -225,6 +225,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ENS_THREADS, 1)
                   }
                   if (++ring_slot == PP_SLOTS) { ring_slot = 0; ++ring_use; }
                 }
+                ENS_TRACE(lane == 0, 3 + ((layer - 1) * 2 + tl) * 2);
               }
             }
           }
@@ -261,6 +262,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ENS_THREADS, 1)
               mbar_wait(bar_acc + tl, ph_acc[tl]);   // accumulator of this layer of this tile complete
               ph_acc[tl] ^= 1;
               tc_fence_after();
+              ENS_TRACE(tid == 0, 20 + (layer * 2 + tl) * 6);
+              ENS_TRACE(tid == 480, 60 + (layer * 2 + tl) * 6);
               const uint32_t d_src = tmem_lane + tl * HID + quarter * 16;
               const float* hb = s_hb + (layer > 0 ? layer - 1 : 0) * HID + quarter * 16;
 #pragma unroll
@@ -272,9 +275,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ENS_THREADS, 1)
                 uint8_t* dst = smem + PpSmem::RING + ring_slot * PP_SLOT_BYTES + (2 * quarter) * A_LBO + lrow * 16;
                 if (layer == 0) epilogue_round<16, false>(v, nullptr, dst);
                 else epilogue_round<16, true>(v, hb + r * 64, dst);
-                publish_round(bar_full_leader + ring_slot * 8, lane);
                 if (++ring_slot == PP_SLOTS) { ring_slot = 0; ++ring_use; }
+                ENS_TRACE(tid == 0, 21 + (layer * 2 + tl) * 6 + r);
+                ENS_TRACE(tid == 480, 61 + (layer * 2 + tl) * 6 + r);
               }
+              publish_round(bar_stage_leader + tl * 8, lane);   // one fence + arrive per warp per stage
             }
           }
           if (row_owner) {
@@ -283,6 +288,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ENS_THREADS, 1)
               mbar_wait(bar_out + tl, ph_out[tl]);
               ph_out[tl] ^= 1;
               tc_fence_after();
+              ENS_TRACE(tid == 384, 100 + tl);
               uint32_t o[8];
               tmem_ld8_nowait(tmem_lane + tl * HID, o);
               tmem_wait_ld8(o);
@@ -296,6 +302,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ENS_THREADS, 1)
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(bar_a0_leader + tl * 8);
+                ENS_TRACE(tid == 384, 102 + tl);
               }
             }
           }
