@@ -17,7 +17,8 @@
 //             stage[tile] (leader CTA, 32 warp arrivals)   all four chunks of the tile's next A operand are
 //                                                          published by both CTAs (one arrive per warp per
 //                                                          stage: the MMAs cannot start earlier anyway)
-//             empty[slot] (both CTAs, tcgen05.commit)      the MMAs that read the chunk have completed
+//             empty[slot][k] (both CTAs, tcgen05.commit)   the MMA that read K-step k (16 columns) of the chunk
+//                                                          has completed; a warp rewrites only its own K-step
 //   order     epilogue warps, per horizon step:  E0(X) E0(Y) E1(X) E1(Y) E2(X) E2(Y) E3(X) E3(Y)
 //             MMA issuer,     per horizon step:  M0(X) M0(Y) M1(X) M1(Y) M2(X) M2(Y) M3(X) M3(Y)
 //             (El = epilogue reading layer l's accumulator; E3 = output layer -> state update -> next
@@ -41,8 +42,8 @@ struct PpSmem {
   static constexpr uint32_t W3 = W0 + 128 * 32;                          // 8 x 256 bf16 output layer hi/lo rows
   static constexpr uint32_t HB = W3 + 8 * HID * 2;                       // float [2][256]: 0.5 * b_h
   static constexpr uint32_t B_OUT = HB + 2 * HID * 4;                    // float [4]
-  static constexpr uint32_t BARS = B_OUT + 16;   // stage[2] empty[5] acc_done[2] out_done[2] a0_full[2] bar_w
-  static constexpr uint32_t TMEM_PTR = BARS + (PP_SLOTS + 9) * 8;
+  static constexpr uint32_t BARS = B_OUT + 16;   // stage[2] empty[5][4] acc_done[2] out_done[2] a0_full[2] bar_w
+  static constexpr uint32_t TMEM_PTR = BARS + (4 * PP_SLOTS + 9) * 8;
   static constexpr uint32_t TOTAL = TMEM_PTR + 16;
 };
 static_assert(PpSmem::TOTAL <= 227 * 1024, "ping-pong ensemble rollout shared memory plan exceeds 227 KB");
@@ -61,7 +62,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ENS_THREADS, 1)
   float* s_b_out = reinterpret_cast<float*>(smem + PpSmem::B_OUT);
   uint64_t* bar_stage = reinterpret_cast<uint64_t*>(smem + PpSmem::BARS);   // [2] leader: tile's A chunks published
   uint64_t* bar_empty = bar_stage + 2;
-  uint64_t* bar_acc = bar_empty + PP_SLOTS;            // [2] accumulator of layer 0/1/2 of tile t complete
+  uint64_t* bar_acc = bar_empty + 4 * PP_SLOTS;            // [2] accumulator of layer 0/1/2 of tile t complete
   uint64_t* bar_out = bar_acc + 2;                     // [2] output-layer accumulator of tile t complete
   uint64_t* bar_a0 = bar_out + 2;                      // [2] leader: split-input rows of tile t published
   uint64_t* bar_w = bar_a0 + 2;
@@ -74,7 +75,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ENS_THREADS, 1)
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
   }
   if (tid == 0) {
-    for (int s = 0; s < PP_SLOTS; ++s) mbar_init(bar_empty + s, 1);
+    for (int s = 0; s < 4 * PP_SLOTS; ++s) mbar_init(bar_empty + s, 1);
     for (int t = 0; t < 2; ++t) {
       mbar_init(bar_stage + t, 2 * EPI_WARPS);
       mbar_init(bar_acc + t, 1);
@@ -216,11 +217,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ENS_THREADS, 1)
                   if (elected) {
                     const uint64_t da = desc_ring + static_cast<uint64_t>(ring_slot * SLOT_STEP);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
+                    for (int j = 0; j < 4; ++j) {
                       umma_bf16_ss_2sm(d, da + static_cast<uint64_t>(j * A_STEP),
                                        desc_w + static_cast<uint64_t>((4 * r + j) * w_step),
                                        layer < 3 ? IDESC : IDESC_OUT, (r | j) ? 1u : 0u);
-                    umma_commit_2sm(bar_empty + ring_slot);      // the chunk may be overwritten once these complete
+                      umma_commit_2sm(bar_empty + ring_slot * 4 + j);   // K-step j of the chunk may be rewritten
+                    }
                     if (r == PP_ROUNDS - 1) umma_commit_2sm(layer < 3 ? bar_acc + tl : bar_out + tl);
                   }
                   if (++ring_slot == PP_SLOTS) { ring_slot = 0; ++ring_use; }
@@ -270,7 +272,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ENS_THREADS, 1)
               for (int r = 0; r < PP_ROUNDS; ++r) {
                 uint32_t v[16];
                 tmem_ld16_nowait(d_src + r * 64, v);
-                if (ring_use > 0) mbar_wait(bar_empty + ring_slot, (ring_use - 1) & 1);   // chunk drained by its MMAs
+                if (ring_use > 0) mbar_wait(bar_empty + ring_slot * 4 + quarter, (ring_use - 1) & 1);   // K-step drained
                 tmem_wait_ld16(v);
                 uint8_t* dst = smem + PpSmem::RING + ring_slot * PP_SLOT_BYTES + (2 * quarter) * A_LBO + lrow * 16;
                 if (layer == 0) epilogue_round<16, false>(v, nullptr, dst);
