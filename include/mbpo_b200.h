@@ -111,7 +111,8 @@ typedef struct MbpoIcemTrace {
 int mbpo_abi_version(void);
 const char* mbpo_last_error(void);
 /* sizeof() of the ABI structs, so that a foreign binding can verify its own layout:
- * which = 0 MbpoIcemCfg, 1 MbpoPendulumParams, 2 MbpoMlpEnsembleParams, 3 MbpoIcemTrace;
+ * which = 0 MbpoIcemCfg, 1 MbpoPendulumParams, 2 MbpoMlpEnsembleParams, 3 MbpoIcemTrace,
+ * 4 MbpoPolicyParams;
  * anything else returns 0. */
 size_t mbpo_struct_size(int which);
 
@@ -214,6 +215,35 @@ int mbpo_env_rollout(int system_kind, const void* sys_params_host, int math_mode
                      float* steps, float* done, const float* first_obs, const float* actions,
                      int E, int T, float* observation_out, float* reward_out, float* discount_out,
                      float* next_observation_out, float* truncation_out, void* stream);
+
+/* ---- policy in the env loop: SAC / PPO data collection ------------------------------------- */
+/* The stochastic policy of sac/sac_networks.py:58-73 + sac/parametric_distribution.py:97-125:
+ * logits = MLP(obs) (swish; Dense = x @ W + b), loc, scale = split(logits, 2),
+ * action = tanh((softplus(scale) + min_std) * normal(key, [E, A]) + loc), or tanh(loc) when
+ * deterministic.  w[l] are flax Dense kernels [in, out] (device pointers, float32): w[0] [obs_dim, hidden],
+ * w[1..num_hidden-1] [hidden, hidden], w[num_hidden] [hidden, 2 * action_dim]; b[l] the biases. */
+#define MBPO_POLICY_MAX_LAYERS 5
+typedef struct MbpoPolicyParams {
+  int32_t num_hidden, hidden, obs_dim, action_dim;
+  const float* w[MBPO_POLICY_MAX_LAYERS];
+  const float* b[MBPO_POLICY_MAX_LAYERS];
+  float min_std;
+} MbpoPolicyParams;
+enum {
+  MBPO_KEYS_SAC = 0,     /* sac/sac.py:288-292      k, k_t = split(k); policy key = k_t          */
+  MBPO_KEYS_UNROLL = 1,  /* sac/acting.py:68-73     current, next = split(current); policy key = current, carry = next */
+  MBPO_KEYS_AS_IS = 2    /* sac/acting.py:35-55     actor_step(env, state, policy, key): key used directly */
+};
+/* T steps of actor_step (sac/acting.py:35-55) for E envs in one launch: policy forward, NormalTanh
+ * sample, the wrapped env step of mbpo_env_rollout, Transition out (time-major; action_out [T,E,A];
+ * observation[t] = next_observation[t-1], observation[0] = the incoming obs, as in mbpo_env_rollout).
+ * key_in / key_out: device uint32[2], the scan's carry key before / after the T steps. */
+int mbpo_actor_rollout(int system_kind, const void* sys_params_host, int math_mode, int prng_mode,
+                       const MbpoPolicyParams* policy_host, int deterministic, int key_convention,
+                       const uint32_t* key_in, int episode_length, int action_repeat, float* obs,
+                       float* steps, float* done, const float* first_obs, int E, int T, float* action_out,
+                       float* reward_out, float* discount_out, float* next_observation_out,
+                       float* truncation_out, uint32_t* key_out, void* stream);
 
 /* ---- stage 4: learned MLP-ensemble dynamics, batched forward on tcgen05 ------------------ */
 /* inp [R, x_dim+u_dim], member [R] (int32 ensemble member per row) -> delta [R, x_dim]. */

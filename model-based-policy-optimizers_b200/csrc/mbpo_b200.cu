@@ -14,6 +14,7 @@
 #include "host_util.h"
 #include "mlp_kernels.cuh"
 #include "mlp_tc_kernels.cuh"
+#include "actor_kernels.cuh"
 #include "ensemble_pp_kernels.cuh"
 #include "plan_dispatch.h"
 #include "staged_kernels.cuh"
@@ -184,6 +185,7 @@ size_t mbpo_struct_size(int which) {
     case 1: return sizeof(MbpoPendulumParams);
     case 2: return sizeof(MbpoMlpEnsembleParams);
     case 3: return sizeof(MbpoIcemTrace);
+    case 4: return sizeof(MbpoPolicyParams);
     default: return 0;
   }
 }
@@ -588,6 +590,96 @@ int mbpo_env_rollout(int system_kind, const void* sys_params_host, int math_mode
     default: env_rollout_pendulum_kernel<1, true><<<blocks, ENV_THREADS, 0, st>>>(a); break;
   }
   return check_launch("env_rollout_pendulum_kernel");
+}
+
+// ---- policy in the env loop: actor_step / generate_unroll / get_experience ------------------------------
+extern "C++" {
+namespace {
+template <int PRNG, int MATH>
+int launch_actor(const mbpo::ActorArgs& a, cudaStream_t st) {
+  using namespace mbpo;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // one wave, one CTA per SM: threads = ceil(E / SMs) rounded up to a warp, at most ACT_MAX_THREADS
+  int threads = ((a.E + sms - 1) / sms + 31) / 32 * 32;
+  if (threads > ACT_MAX_THREADS) threads = ACT_MAX_THREADS;
+  if (threads < 32) threads = 32;
+  ActorSmem lay;
+  int off = 0;
+  auto take = [&](int n) { const int o = off; off += (n + 3) / 4 * 4; return o; };
+  lay.w[0] = take(3 * ACT_W);
+  for (int l = 1; l < a.num_hidden; ++l) lay.w[l] = take(ACT_W * ACT_W);
+  lay.w[a.num_hidden] = take(ACT_W * 2);
+  for (int l = 0; l < a.num_hidden; ++l) lay.b[l] = take(ACT_W);
+  lay.b[a.num_hidden] = take(2);
+  lay.h = take(ACT_W * threads);
+  const size_t smem = static_cast<size_t>(off) * sizeof(float);
+  auto kernel = actor_rollout_pendulum_kernel<PRNG, MATH>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return fail(MBPO_ECUDA, "actor_rollout: smem attribute (%zu B): %s", smem, cudaGetErrorString(e));
+  const unsigned blocks = static_cast<unsigned>((a.E + threads - 1) / threads);
+  kernel<<<blocks, threads, smem, st>>>(a, lay);
+  return check_launch("actor_rollout_pendulum_kernel");
+}
+}  // namespace
+}  // extern "C++"
+
+int mbpo_actor_rollout(int system_kind, const void* sys_params_host, int math_mode, int prng_mode,
+                       const MbpoPolicyParams* policy_host, int deterministic, int key_convention,
+                       const uint32_t* key_in, int episode_length, int action_repeat, float* obs, float* steps,
+                       float* done, const float* first_obs, int E, int T, float* action_out, float* reward_out,
+                       float* discount_out, float* next_observation_out, float* truncation_out, uint32_t* key_out,
+                       void* stream) {
+  MBPO_REQUIRE(system_kind == MBPO_SYSTEM_PENDULUM || system_kind == MBPO_SYSTEM_MLP_ENSEMBLE,
+               "actor_rollout: unknown system_kind %d", system_kind);
+  if (system_kind != MBPO_SYSTEM_PENDULUM)
+    return fail(MBPO_EUNSUPPORTED, "actor_rollout: only MBPO_SYSTEM_PENDULUM has an inlined step");
+  MBPO_REQUIRE(sys_params_host && policy_host && key_in && obs && steps && done && first_obs,
+               "actor_rollout: null pointer");
+  MBPO_REQUIRE(action_out && reward_out && discount_out && next_observation_out && truncation_out,
+               "actor_rollout: every Transition buffer is required");
+  MBPO_REQUIRE(math_mode == 0 || math_mode == 1, "actor_rollout: bad math_mode %d", math_mode);
+  MBPO_REQUIRE(prng_mode == 0 || prng_mode == 1, "actor_rollout: bad prng_mode %d", prng_mode);
+  MBPO_REQUIRE(key_convention >= 0 && key_convention <= 2, "actor_rollout: bad key_convention %d", key_convention);
+  MBPO_REQUIRE(E >= 0 && T >= 0 && episode_length >= 1 && action_repeat >= 1, "actor_rollout: bad sizes");
+  if (policy_host->hidden != mbpo::ACT_W || policy_host->obs_dim != 3 || policy_host->action_dim != 1 ||
+      policy_host->num_hidden < 1 || policy_host->num_hidden > mbpo::ACT_MAX_HIDDEN)
+    return fail(MBPO_EUNSUPPORTED,
+                "actor_rollout: the policy kernel needs obs_dim == 3, action_dim == 1, 1..%d hidden layers of width %d "
+                "(got obs %d, act %d, %d x %d)",
+                mbpo::ACT_MAX_HIDDEN, mbpo::ACT_W, policy_host->obs_dim, policy_host->action_dim,
+                policy_host->num_hidden, policy_host->hidden);
+  for (int l = 0; l <= policy_host->num_hidden; ++l)
+    MBPO_REQUIRE(policy_host->w[l] && policy_host->b[l], "actor_rollout: null policy weights (layer %d)", l);
+  if (E == 0 || T == 0) {
+    if (key_out && key_out != key_in) {
+      const cudaError_t ce = cudaMemcpyAsync(key_out, key_in, 2 * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
+                                             as_stream(stream));
+      if (ce != cudaSuccess) return fail(MBPO_ECUDA, "actor_rollout copy: %s", cudaGetErrorString(ce));
+    }
+    return MBPO_OK;
+  }
+  mbpo::ActorArgs a;
+  a.sys = *static_cast<const MbpoPendulumParams*>(sys_params_host);
+  a.E = E; a.T = T; a.episode_length = episode_length; a.action_repeat = action_repeat;
+  a.num_hidden = policy_host->num_hidden; a.deterministic = deterministic; a.key_convention = key_convention;
+  a.min_std = policy_host->min_std;
+  for (int l = 0; l <= mbpo::ACT_MAX_HIDDEN; ++l) {
+    a.w[l] = l <= a.num_hidden ? policy_host->w[l] : nullptr;
+    a.b[l] = l <= a.num_hidden ? policy_host->b[l] : nullptr;
+  }
+  a.key_in = key_in;
+  a.obs = obs; a.steps = steps; a.done = done; a.first_obs = first_obs;
+  a.action_out = action_out; a.reward_out = reward_out; a.discount_out = discount_out;
+  a.next_observation_out = next_observation_out; a.truncation_out = truncation_out; a.key_out = key_out;
+  cudaStream_t st = as_stream(stream);
+  switch (prng_mode * 2 + math_mode) {
+    case 0: return launch_actor<0, 0>(a, st);
+    case 1: return launch_actor<0, 1>(a, st);
+    case 2: return launch_actor<1, 0>(a, st);
+    default: return launch_actor<1, 1>(a, st);
+  }
 }
 
 // ---- stage 4 ---------------------------------------------------------------------------------------

@@ -60,6 +60,15 @@ class IcemCfgC(C.Structure):
                                          "sigma")] + [("s_scale", C.c_float * MBPO_MAX_FREQ)]
 
 
+class PolicyParamsC(C.Structure):
+    """MbpoPolicyParams."""
+    _fields_ = [("num_hidden", C.c_int32), ("hidden", C.c_int32), ("obs_dim", C.c_int32), ("action_dim", C.c_int32),
+                ("w", C.c_void_p * 5), ("b", C.c_void_p * 5), ("min_std", C.c_float)]
+
+
+KEYS_SAC, KEYS_UNROLL, KEYS_AS_IS = 0, 1, 2
+
+
 class IcemTraceC(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("actions", "values", "elite_idx", "mean", "std", "best_value")]
 
@@ -88,6 +97,8 @@ SIGNATURES = {
     "mbpo_icem_clip_actions": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "mbpo_icem_mpc_closed_loop": (_I, [C.POINTER(IcemCfgC), _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "mbpo_env_rollout": (_I, [_I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "mbpo_actor_rollout": (_I, [_I, _P, _I, _I, C.POINTER(PolicyParamsC), _I, _I, _P, _I, _I, _P, _P, _P, _P, _I, _I,
+                                _P, _P, _P, _P, _P, _P, _P]),
     "mbpo_mlp_dynamics_forward": (_I, [C.POINTER(MlpEnsembleParamsC), _P, _P, _I, _P, _P]),
     "mbpo_ensemble_rollout": (_I, [C.POINTER(MlpEnsembleParamsC), _I, _P, _P, _I, _I, _I, _P, _P]),
 }
@@ -106,7 +117,7 @@ def _load() -> C.CDLL:
     got = lib.mbpo_abi_version()
     if got != MBPO_ABI_VERSION:
         raise ImportError("libmbpo_b200.so ABI version %d != binding version %d; rebuild" % (got, MBPO_ABI_VERSION))
-    for which, struct in enumerate((IcemCfgC, PendulumParamsC, MlpEnsembleParamsC, IcemTraceC)):
+    for which, struct in enumerate((IcemCfgC, PendulumParamsC, MlpEnsembleParamsC, IcemTraceC, PolicyParamsC)):
         if lib.mbpo_struct_size(which) != C.sizeof(struct):
             raise ImportError("struct layout mismatch for %s: C %d vs ctypes %d" % (
                 struct.__name__, lib.mbpo_struct_size(which), C.sizeof(struct)))

@@ -1,0 +1,129 @@
+"""Policy-in-the-loop data collection for SAC / PPO behind the reference's acting API.
+
+Mirrors mbpo/optimizers/policy_optimizers/sac/acting.py:35-78 (``actor_step``, ``generate_unroll``),
+sac/sac_networks.py:58-73 (``make_inference_fn``) and the experience scan of sac/sac.py:283-292
+(``get_experience``): the policy MLP forward, the NormalTanh sample (JAX's threefry draw, bit for bit),
+the wrapped env step and the Transition for T steps of E envs are ONE kernel launch
+(mbpo_actor_rollout); nothing is computed on the host.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from .config import config
+from .envs import EnvState, VmappedSystemEnv
+from .utils.optimizer_utils import Transition
+
+
+@dataclass
+class PolicyParams:
+    """flax Dense kernels [in, out] and biases of the policy network: obs -> 64 x num_hidden -> 2 * A."""
+    weights: List[torch.Tensor]
+    biases: List[torch.Tensor]
+    min_std: float = 0.001          # NormalTanhDistribution(min_std=0.001), parametric_distribution.py:100
+
+
+class Policy:
+    """What ``make_policy(params, deterministic)`` returns (sac_networks.py:61-70).  Calling it samples
+    actions for a batch of observations; actor_step / generate_unroll run it inside the env loop."""
+
+    def __init__(self, params: PolicyParams, deterministic: bool = False):
+        w = [t.to(torch.float32).contiguous() for t in params.weights]
+        b = [t.to(torch.float32).contiguous() for t in params.biases]
+        if len(w) < 2 or len(w) != len(b) or len(w) > 5:
+            raise _lib.MbpoUnsupported(_lib.MBPO_EUNSUPPORTED, "policy needs 1..4 hidden layers")
+        self.weights, self.biases = w, b
+        self.deterministic = bool(deterministic)
+        self.min_std = float(params.min_std)
+        s = _lib.PolicyParamsC()
+        s.num_hidden = len(w) - 1
+        s.hidden = w[0].shape[1]
+        s.obs_dim = w[0].shape[0]
+        s.action_dim = w[-1].shape[1] // 2
+        for i, (wi, bi) in enumerate(zip(w, b)):
+            s.w[i] = _lib.ptr(wi)
+            s.b[i] = _lib.ptr(bi)
+        s.min_std = self.min_std
+        self.struct = s
+
+    def __call__(self, observations: torch.Tensor, key_sample: torch.Tensor):
+        """policy(observations [E, X], key) -> (actions [E, A], {}).  Runs one actor step on a scratch env
+        state and returns its actions (the env outputs are discarded)."""
+        from .systems.pendulum_system import PendulumSystem
+        system = PendulumSystem()
+        env = VmappedSystemEnv(system, system.reset(device=observations.device).system_params, episode_length=1 << 30)
+        _, tr = actor_step(env, env.reset(observations), self, key_sample)
+        return tr.action, {}
+
+
+def make_inference_fn():
+    """sac_networks.make_inference_fn: returns make_policy(params, deterministic=False) -> Policy."""
+    def make_policy(params: PolicyParams, deterministic: bool = False) -> Policy:
+        return Policy(params, deterministic)
+    return make_policy
+
+
+def _rollout(env: VmappedSystemEnv, env_state: EnvState, policy: Policy, key: torch.Tensor, T: int,
+             key_convention: int, extra_fields: Sequence[str]):
+    for f in extra_fields:
+        if f != "truncation":
+            raise _lib.MbpoUnsupported(_lib.MBPO_EUNSUPPORTED, "extra field %r is not produced by the env kernel" % f)
+    system = env.system
+    X, A = system.x_dim, system.u_dim
+    obs = env_state.obs.to(torch.float32).contiguous().clone()
+    E = obs.shape[0]
+    dev = obs.device
+    steps = env_state.info["steps"].clone()
+    done = env_state.done.clone()
+    first = env_state.info["first_obs"].contiguous()
+    key = key.reshape(2).contiguous()
+    key_out = torch.empty_like(key)
+    buf = torch.empty((T + 1, E, X), dtype=torch.float32, device=dev)       # observation / next_observation views
+    buf[0].copy_(obs)
+    act = torch.empty((T, E, A), dtype=torch.float32, device=dev)
+    r = torch.empty((T, E), dtype=torch.float32, device=dev)
+    d = torch.empty((T, E), dtype=torch.float32, device=dev)
+    tr = torch.empty((T, E), dtype=torch.float32, device=dev)
+    params = system.pack_params(env_state.system_params)
+    with _lib.cuda_guard(obs):
+        _lib.check(_lib.lib.mbpo_actor_rollout(
+            system.system_kind, _lib.C.addressof(params), config.math_mode_id, config.prng_mode,
+            _lib.C.byref(policy.struct), int(policy.deterministic), key_convention, _lib.ptr(key), env.episode_length,
+            env.action_repeat, _lib.ptr(obs), _lib.ptr(steps), _lib.ptr(done), _lib.ptr(first), E, T, _lib.ptr(act),
+            _lib.ptr(r), _lib.ptr(d), _lib.ptr(buf[1:]), _lib.ptr(tr), _lib.ptr(key_out), _lib.stream_ptr(dev)))
+    nstate = EnvState(obs=obs, reward=r[-1] if T else env_state.reward, done=done,
+                      system_params=env_state.system_params,
+                      info=dict(steps=steps, truncation=tr[-1] if T else env_state.info["truncation"], first_obs=first))
+    extras = {"policy_extras": {}, "state_extras": {f: tr for f in extra_fields}}
+    transition = Transition(observation=buf[:T], action=act, reward=r, discount=d, next_observation=buf[1:],
+                            extras=extras)
+    return nstate, transition, key_out
+
+
+def actor_step(env: VmappedSystemEnv, env_state: EnvState, policy: Policy, key: torch.Tensor,
+               extra_fields: Sequence[str] = ()) -> Tuple[EnvState, Transition]:
+    """sac/acting.py:35-55: one step, the key is the policy's sample key.  Fields are [E, ...]."""
+    nstate, tr, _ = _rollout(env, env_state, policy, key, 1, _lib.KEYS_AS_IS, extra_fields)
+    ex = {"policy_extras": {}, "state_extras": {k: v[0] for k, v in tr.extras["state_extras"].items()}}
+    return nstate, Transition(tr.observation[0], tr.action[0], tr.reward[0], tr.discount[0], tr.next_observation[0], ex)
+
+
+def generate_unroll(env: VmappedSystemEnv, env_state: EnvState, policy: Policy, key: torch.Tensor, unroll_length: int,
+                    extra_fields: Sequence[str] = ()) -> Tuple[EnvState, Transition]:
+    """sac/acting.py:58-78: lax.scan of actor_step; per step current_key, next_key = split(current_key), the
+    policy samples with current_key.  Fields are time-major [T, E, ...]."""
+    nstate, tr, _ = _rollout(env, env_state, policy, key, unroll_length, _lib.KEYS_UNROLL, extra_fields)
+    return nstate, tr
+
+
+def get_experience(env: VmappedSystemEnv, env_state: EnvState, policy: Policy, key: torch.Tensor,
+                   num_env_steps: int) -> Tuple[torch.Tensor, EnvState, Transition]:
+    """The scan of SAC.get_experience (sac/sac.py:288-294): per step k, k_t = split(k), actor_step with k_t and
+    extra_fields=('truncation',).  Returns (carry key, env_state, transitions [T, E, ...]); the replay-buffer
+    insert and the normaliser update stay with the caller (SURVEY 8f-2 boundary)."""
+    nstate, tr, key_out = _rollout(env, env_state, policy, key, num_env_steps, _lib.KEYS_SAC, ("truncation",))
+    return key_out, nstate, tr

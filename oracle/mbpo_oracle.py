@@ -602,3 +602,97 @@ def env_rollout(x0: np.ndarray, actions: np.ndarray, episode_length: int,
     out["final_steps"] = steps
     out["final_done"] = done
     return out
+
+
+# ----------------------------------------------------------------------------------
+# Policy in the env loop: actor_step / generate_unroll / SAC get_experience
+#   sac/sac_networks.py:58-73 (make_inference_fn), sac/parametric_distribution.py:97-125
+#   (NormalTanhDistribution), sac/acting.py:35-78, sac/sac.py:283-292
+# ----------------------------------------------------------------------------------
+@dataclass
+class PolicyParams:
+    """flax Dense kernels [in, out] and biases of the policy MLP (swish): obs -> hidden.. -> 2 * A."""
+    weights: list
+    biases: list
+    min_std: float = 0.001
+
+
+def make_policy_params(seed: int = 7, obs_dim: int = 3, action_dim: int = 1, hidden=(64, 64, 64),
+                       scale: float = 1.0) -> PolicyParams:
+    rng = np.random.default_rng(seed)
+    dims = (obs_dim,) + tuple(hidden) + (2 * action_dim,)
+    ws = [(rng.standard_normal((dims[i], dims[i + 1])) * scale / np.sqrt(dims[i])).astype(F32)
+          for i in range(len(dims) - 1)]
+    bs = [(0.1 * rng.standard_normal(dims[i + 1])).astype(F32) for i in range(len(dims) - 1)]
+    return PolicyParams(ws, bs)
+
+
+def policy_logits(params: PolicyParams, obs: np.ndarray) -> np.ndarray:
+    """MLP(obs): Dense (x @ W + b) -> swish ... -> Dense, float32 (products summed in float64, rounded once)."""
+    a = np.asarray(obs, dtype=F32)
+    n = len(params.weights)
+    for i in range(n):
+        a = ((a.astype(np.float64) @ params.weights[i].astype(np.float64)).astype(F32) + params.biases[i]).astype(F32)
+        if i < n - 1:
+            a = swish(a.astype(F32)).astype(F32)
+    return a
+
+
+def softplus(x):
+    """jax.nn.softplus = logaddexp(x, 0)."""
+    x = np.asarray(x, dtype=F32)
+    return (np.maximum(x, F32(0)) + np.log1p(np.exp(-np.abs(x)))).astype(F32)
+
+
+def policy_sample(params: PolicyParams, obs: np.ndarray, key, deterministic: bool = False,
+                  partitionable: bool = False) -> np.ndarray:
+    """make_policy(params)(observations, key_sample) (sac_networks.py:61-70): actions [E, A]."""
+    logits = policy_logits(params, obs)
+    a_dim = logits.shape[-1] // 2
+    loc, scale = logits[..., :a_dim], logits[..., a_dim:]              # jnp.split(parameters, 2, axis=-1)
+    if deterministic:
+        return np.tanh(loc).astype(F32)                                # mode(): postprocess(dist.mode())
+    scale = (softplus(scale) + F32(params.min_std)).astype(F32)
+    e = obs.shape[0]
+    eps = jr.normal(key, e * a_dim, partitionable).reshape(e, a_dim)   # Normal._sample_n: normal(key, (1, E, A))
+    raw = ((scale * eps).astype(F32) + loc).astype(F32)                # scale * rnd + loc
+    return np.tanh(raw).astype(F32)                                    # distrax.Tanh().forward
+
+
+def actor_rollout(params: PolicyParams, x0: np.ndarray, key, num_steps: int, episode_length: int,
+                  key_convention: str = "sac", deterministic: bool = False, p: PendulumParams = PendulumParams(),
+                  action_repeat: int = 1, partitionable: bool = False, teacher_obs: Optional[np.ndarray] = None):
+    """T steps of actor_step inside the reference's scans.  key_convention: "sac" (sac.py:288-292:
+    k, k_t = split(k), policy key k_t), "unroll" (acting.py:68-73: current, next = split(current), policy key
+    current, carry next) or "as_is" (one actor_step with the given key).  teacher_obs [T, E, 3] forces the
+    observation seen at step t (per-step parity without chaotic drift).  Returns (Transition dict, carry key)."""
+    e = x0.shape[0]
+    obs = np.asarray(x0, dtype=F32).copy()
+    first = obs.copy()
+    steps = np.zeros(e, F32)
+    done = np.zeros(e, F32)
+    out = dict(observation=np.empty((num_steps, e, 3), F32), action=np.empty((num_steps, e, 1), F32),
+               reward=np.empty((num_steps, e), F32), discount=np.empty((num_steps, e), F32),
+               next_observation=np.empty((num_steps, e, 3), F32), truncation=np.empty((num_steps, e), F32))
+    key = np.asarray(key, dtype=U32)
+    for t in range(num_steps):
+        if key_convention == "as_is":
+            k_actor = key
+        else:
+            ks = jr.split(key, 2, partitionable)
+            if key_convention == "sac":
+                key, k_actor = ks[0], ks[1]
+            else:
+                k_actor, key = ks[0], ks[1]
+        if teacher_obs is not None:
+            obs = np.asarray(teacher_obs[t], dtype=F32)
+        act = policy_sample(params, obs, k_actor, deterministic, partitionable)
+        one = env_rollout(obs, act[:, 0][None], episode_length, p, action_repeat, steps0=steps, done0=done,
+                          first_obs=first)
+        out["observation"][t] = obs
+        out["action"][t] = act
+        for f in ("reward", "discount", "next_observation", "truncation"):
+            out[f][t] = one[f][0]
+        obs = one["next_observation"][0]
+        steps, done = one["final_steps"], one["final_done"]
+    return out, key

@@ -39,7 +39,7 @@ def test_header_symbols_are_exported(mb):
 def test_abi_version_and_struct_layout(mb):
     L = mb._lib
     assert L.lib.mbpo_abi_version() == L.MBPO_ABI_VERSION == 1
-    for which, st in enumerate((L.IcemCfgC, L.PendulumParamsC, L.MlpEnsembleParamsC, L.IcemTraceC)):
+    for which, st in enumerate((L.IcemCfgC, L.PendulumParamsC, L.MlpEnsembleParamsC, L.IcemTraceC, L.PolicyParamsC)):
         assert L.lib.mbpo_struct_size(which) == C.sizeof(st)
     assert L.lib.mbpo_struct_size(99) == 0
     assert C.sizeof(L.PendulumParamsC) == 36

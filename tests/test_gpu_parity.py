@@ -613,6 +613,94 @@ def test_env_rollout_abi_variants(mb, cuda_device):
 
 
 # ---------------------------------------------------------------------------------------------
+# policy in the env loop: actor_step / generate_unroll / get_experience
+# ---------------------------------------------------------------------------------------------
+def _policy_on_device(mb, cuda_device, pol, deterministic=False):
+    from mbpo_b200.acting import Policy, PolicyParams
+    return Policy(PolicyParams(weights=[_dev(w, cuda_device) for w in pol.weights],
+                               biases=[_dev(b, cuda_device) for b in pol.biases], min_std=pol.min_std), deterministic)
+
+
+@pytest.mark.parametrize("convention", ["sac", "unroll"])
+@pytest.mark.parametrize("hidden", [(64, 64, 64), (64,)])
+def test_actor_rollout_vs_oracle(mb, cuda_device, prng_mode, math_mode, convention, hidden):
+    """T steps of policy forward + NormalTanh sample + wrapped env step in one launch, per step against the
+    oracle teacher-forced on the GPU's observations; the PRNG carry key is bit exact."""
+    from mbpo_b200 import acting
+    from mbpo_b200.envs import wrap
+    from mbpo_b200.systems import PendulumSystem
+    E, T, L = 333, 23, 7
+    pol = orc.make_policy_params(seed=7, hidden=hidden)
+    policy = _policy_on_device(mb, cuda_device, pol)
+    system = PendulumSystem()
+    env = wrap(system, system.reset(device=cuda_device).system_params, episode_length=L)
+    x0 = _random_states(E, 91)
+    key = ojr.PRNGKey(5)
+    st = env.reset(_dev(x0, cuda_device))
+    if convention == "sac":
+        key_out, nst, tr = acting.get_experience(env, st, policy, _dev(key, cuda_device), T)
+    else:
+        nst, tr = acting.generate_unroll(env, st, policy, _dev(key, cuda_device), T, extra_fields=("truncation",))
+        key_out = None
+    g_obs = tr.observation.cpu().numpy()
+    want, okey = orc.actor_rollout(pol, x0, key, T, L, key_convention=convention, partitionable=prng_mode,
+                                   teacher_obs=g_obs)
+    if key_out is not None:
+        assert np.array_equal(key_out.cpu().numpy(), okey)
+    np.testing.assert_allclose(tr.action.cpu().numpy(), want["action"], rtol=2e-5, atol=2e-6)
+    # the env step is compared on the GPU's own actions (the policy was checked just above)
+    g_act = tr.action.cpu().numpy()[..., 0]
+    steps = np.zeros(E, np.float32); done = np.zeros(E, np.float32)
+    for t in range(T):
+        one = orc.env_rollout(g_obs[t], g_act[t][None], L, steps0=steps, done0=done, first_obs=x0)
+        np.testing.assert_allclose(tr.reward[t].cpu().numpy(), one["reward"][0], rtol=1e-5, atol=3e-6)
+        np.testing.assert_allclose(tr.next_observation[t].cpu().numpy(), one["next_observation"][0], rtol=1e-5, atol=2e-6)
+        assert np.array_equal(tr.discount[t].cpu().numpy(), one["discount"][0])
+        assert np.array_equal(tr.extras["state_extras"]["truncation"][t].cpu().numpy(), one["truncation"][0])
+        steps, done = one["final_steps"], one["final_done"]
+    assert np.array_equal(g_obs[1:], tr.next_observation[:-1].cpu().numpy())          # observation[t] = next_observation[t-1]
+    assert np.array_equal(nst.obs.cpu().numpy(), tr.next_observation[-1].cpu().numpy())
+    assert np.array_equal(nst.info["steps"].cpu().numpy(), steps) and np.array_equal(nst.done.cpu().numpy(), done)
+    assert float(tr.action.abs().max()) <= 1.0
+
+
+def test_actor_step_and_deterministic_policy(mb, cuda_device):
+    from mbpo_b200 import acting
+    from mbpo_b200.envs import wrap
+    from mbpo_b200.systems import PendulumSystem
+    E = 1000
+    pol = orc.make_policy_params(seed=8)
+    system = PendulumSystem()
+    env = wrap(system, system.reset(device=cuda_device).system_params, episode_length=50)
+    x0 = _random_states(E, 92)
+    key = ojr.PRNGKey(11)
+    st = env.reset(_dev(x0, cuda_device))
+    # actor_step: the key is the sample key itself (acting.py:35-55)
+    nst, tr = acting.actor_step(env, st, _policy_on_device(mb, cuda_device, pol), _dev(key, cuda_device),
+                                extra_fields=("truncation",))
+    want = orc.policy_sample(pol, x0, key)
+    np.testing.assert_allclose(tr.action.cpu().numpy(), want, rtol=2e-5, atol=2e-6)
+    assert tr.observation.shape == (E, 3) and tr.action.shape == (E, 1) and tr.reward.shape == (E,)
+    # the policy callable alone (make_inference_fn(...)(params)(obs, key))
+    make_policy = acting.make_inference_fn()
+    policy_fn = make_policy(acting.PolicyParams([_dev(w, cuda_device) for w in pol.weights],
+                                                [_dev(b, cuda_device) for b in pol.biases]))
+    a, extras = policy_fn(_dev(x0, cuda_device), _dev(key, cuda_device))
+    assert torch.equal(a, tr.action) and extras == {}
+    # deterministic: tanh(loc), no key dependence
+    det = _policy_on_device(mb, cuda_device, pol, deterministic=True)
+    _, t1 = acting.actor_step(env, st, det, _dev(key, cuda_device))
+    _, t2 = acting.actor_step(env, st, det, _dev(ojr.PRNGKey(99), cuda_device))
+    assert torch.equal(t1.action, t2.action)
+    np.testing.assert_allclose(t1.action.cpu().numpy(), orc.policy_sample(pol, x0, key, deterministic=True),
+                               rtol=2e-5, atol=2e-6)
+    # unsupported network shapes fail loudly
+    bad = orc.make_policy_params(seed=9, hidden=(32, 32))
+    with pytest.raises(mb.MbpoUnsupported):
+        acting.actor_step(env, st, _policy_on_device(mb, cuda_device, bad), _dev(key, cuda_device))
+
+
+# ---------------------------------------------------------------------------------------------
 # stage 4: learned MLP-ensemble dynamics forward
 # ---------------------------------------------------------------------------------------------
 def test_mlp_dynamics_forward(mb, cuda_device):

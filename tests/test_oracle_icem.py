@@ -234,3 +234,34 @@ def test_oracle_cost_fn_penalty_and_array_bounds():
     assert np.array_equal(ab[:64], np.clip(acts[:64] * 0 + (mean[None] + (acts[:64] - acts[:64])) + ab[:64], u_min, u_max))
     st = orc.icem_optimize(x0, orc.icem_init(jr.PRNGKey(1), horizon), pb, horizon)
     assert np.all(st.best_sequence >= u_min) and np.all(st.best_sequence <= u_max)
+
+
+def test_oracle_actor_rollout_conventions():
+    """Policy-in-the-loop oracle: key conventions of sac.py:288-292 vs acting.py:68-73, NormalTanh bounds,
+    deterministic mode, and agreement with env_rollout on the sampled actions."""
+    pol = orc.make_policy_params(seed=7)
+    E, T, L = 40, 9, 4
+    rng = np.random.default_rng(3)
+    th, w = rng.uniform(-np.pi, np.pi, E), rng.uniform(-8, 8, E)
+    x0 = np.stack([np.cos(th), np.sin(th), w], -1).astype(np.float32)
+    key = jr.PRNGKey(2)
+    sac, k_sac = orc.actor_rollout(pol, x0, key, T, L, key_convention="sac")
+    unr, k_unr = orc.actor_rollout(pol, x0, key, T, L, key_convention="unroll")
+    ks = jr.split(key, 2)
+    # first step: sac samples with the SECOND half of split(key), generate_unroll with the FIRST
+    assert np.array_equal(sac["action"][0], orc.policy_sample(pol, x0, ks[1]))
+    assert np.array_equal(unr["action"][0], orc.policy_sample(pol, x0, ks[0]))
+    assert not np.array_equal(k_sac, k_unr)
+    k = key
+    for _ in range(T):
+        k = jr.split(k, 2)[0]
+    assert np.array_equal(k, k_sac)
+    assert np.all(np.abs(sac["action"]) <= 1.0)
+    env = orc.env_rollout(x0, sac["action"][..., 0], L)
+    for f in ("reward", "discount", "next_observation", "truncation", "observation"):
+        assert np.array_equal(env[f], sac[f]), f
+    assert sac["truncation"][L - 1].all() and not sac["truncation"][L - 2].any()
+    det, _ = orc.actor_rollout(pol, x0, key, 2, L, deterministic=True)
+    assert np.array_equal(det["action"][0], np.tanh(orc.policy_logits(pol, x0)[:, :1]).astype(np.float32))
+    one, k1 = orc.actor_rollout(pol, x0, key, 1, L, key_convention="as_is")
+    assert np.array_equal(k1, key) and np.array_equal(one["action"][0], orc.policy_sample(pol, x0, key))
