@@ -793,6 +793,124 @@ def run_sweep(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# config 3 with the policy in the loop: SAC get_experience (policy forward + sample + env step)
+# ------------------------------------------------------------------------------------------------
+ACT_INSTR_NOTE = ("float32 policy MLP 3-64-64-64-2 on the CUDA cores: 2 x 4096 + 192 + 128 = 8,512 FMA per env-step "
+                  "are the algorithmic work; roofline = FP32 FMA issue rate (148 SMs x 128 lanes x sm_max_mhz)")
+ACT_FMA_PER_STEP = 2 * 64 * 64 + 3 * 64 + 64 * 2
+
+
+def run_actor(args):
+    """65,536 envs x T wrapped env steps with the SAC policy in the loop, envs sharded over the ranks."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from oracle import jax_prng as jr, mbpo_oracle as orc
+    pol = orc.make_policy_params(seed=7)
+    T = 200
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        E, Ts = 4096, 4                                  # bounded sample; NumPy restatement (BLAS matmuls)
+        x0 = random_states(ENV_E, 1)[:E]
+        orc.actor_rollout(pol, x0[:256], jr.PRNGKey(0), 1, ENV_EPISODE)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            orc.actor_rollout(pol, x0, jr.PRNGKey(0), Ts, ENV_EPISODE)
+        dt = (time.perf_counter() - t0) / args.steps
+        ncores, model = host_info()
+        v = E * Ts / dt
+        emit_json({"impl": "reference", "metric": "policy-in-the-loop env-steps/sec", "value": v, "unit": "env-steps/s",
+                   "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+                   "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                   "config": {"workload": "config3_actor_rollouts", "envs": ENV_E, "steps_per_call": T},
+                   "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": ncores, "kind": "port",
+                                    "sample": "%d envs x %d steps of 65536 x %d, NumPy oracle (BLAS threads)" % (E, Ts, T),
+                                    "host_cpu": model},
+                   "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}, GUARD)
+        return
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import mbpo_b200
+    from mbpo_b200 import acting
+    from mbpo_b200.envs import wrap
+    from mbpo_b200.parallel import shard_bounds
+    from mbpo_b200.systems import PendulumSystem
+    mbpo_b200.config.math_mode = args.math
+    lo, hi = shard_bounds(ENV_E, rank, world)
+    E = hi - lo
+    system = PendulumSystem()
+    env = wrap(system, system.reset(device=dev).system_params, episode_length=ENV_EPISODE)
+    policy = acting.Policy(acting.PolicyParams([torch.from_numpy(w).to(dev) for w in pol.weights],
+                                               [torch.from_numpy(b).to(dev) for b in pol.biases]))
+    x0_host = torch.from_numpy(random_states(ENV_E, 1)[lo:hi].copy()).pin_memory()
+    key = torch.from_numpy(jr.PRNGKey(rank)).to(dev)
+    st = env.reset(x0_host.to(dev))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+    for _ in range(max(args.warmup, 3)):
+        acting.get_experience(env, st, policy, key, T)
+    steps = min(args.steps, 10)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        for k in range(steps):
+            starts[k].record()
+            acting.get_experience(env, st, policy, key, T)
+            ends[k].record()
+        barrier()
+    ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends)) / steps
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    rew_host = torch.empty((T, E), dtype=torch.float32).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(steps):
+        st_k = env.reset(x0_host.to(dev, non_blocking=True))
+        _, _, trn = acting.get_experience(env, st_k, policy, key, T)
+        rew_host.copy_(trn.reward, non_blocking=True)
+        torch.cuda.synchronize(dev)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / steps
+    if rank == 0:
+        sm_max = 1965.0
+        try:
+            sm_max = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("sm_max_mhz", 1965.0))
+        except Exception:
+            pass
+        peak = 148 * 128 * sm_max * 1e6 / 1e12            # T FMA/s
+        achieved = E * T * ACT_FMA_PER_STEP / (ms * 1e-3) / 1e12
+        emit_json({
+            "metric": "policy-in-the-loop env-steps/sec", "value": ENV_E * T / (ms * 1e-3), "unit": "env-steps/s",
+            "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic (random-init policy)",
+            "config": {"workload": "config3_actor_rollouts", "envs": ENV_E, "steps_per_call": T,
+                       "policy": "3-64-64-64-2 swish, NormalTanh", "episode_length": ENV_EPISODE,
+                       "parallelism": "envs sharded x%d" % world,
+                       "l2": "per-call outputs %.0f MB > 126 MB L2; the kernel is FMA-issue bound" % (E * T * 28 / 1e6)},
+            "math_mode": args.math, "clocks": clk.summary(),
+            "e2e": {"value": ENV_E * T / e2e_s, "unit": "env-steps/s", "ms_per_step": e2e_s * 1e3,
+                    "h2d_bytes_per_step": int(x0_host.numel() * 4), "d2h_bytes_per_step": int(rew_host.numel() * 4),
+                    "api": "acting.get_experience(env, reset(x0 from pinned host), policy, key, T) -> rewards to host"},
+            "gpu_launches": steps,
+            "roofline": {"bound": "fma", "kernel": "actor_rollout_pendulum_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "T FMA/s", "frac": achieved / peak, "traffic": None, "note": ACT_INSTR_NOTE},
+            "cpu_baseline": None}, GUARD)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 class _StdoutGuard:
     """Everything the libraries print (e.g. the NCCL version banner) goes to stderr; only the final
     JSON line reaches the real stdout."""
@@ -823,7 +941,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["config1_closed_loop", "config3_env_rollouts",
+    ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["config1_closed_loop", "config3_env_rollouts", "config3_actor_rollouts",
                                                                "config4_ensemble_icem", "config5_sweep"],
                     default="config2_batched_icem")
     ap.add_argument("--math", choices=["reference", "theta_carry"], default="reference")
@@ -835,6 +953,8 @@ def main():
             return run_env(args)
         if args.workload == "config4_ensemble_icem":
             return run_ensemble(args)
+        if args.workload == "config3_actor_rollouts":
+            return run_actor(args)
         if args.workload == "config1_closed_loop":
             return run_closed_loop(args)
         if args.workload == "config5_sweep":
