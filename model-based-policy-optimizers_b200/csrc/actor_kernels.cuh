@@ -63,6 +63,22 @@ __device__ __forceinline__ float swish_exact(float x) {
 // jax.nn.softplus(x) = logaddexp(x, 0) = max(x, 0) + log1p(exp(-|x|))
 __device__ __forceinline__ float softplus_exact(float x) { return fmaxf(x, 0.0f) + log1pf(expf(-fabsf(x))); }
 
+// Packed float32 pair arithmetic (sm_100: FFMA2 takes a scalar and a register pair).  A 3-register FFMA issues
+// every other cycle per scheduler; the packed form retires two FMAs per issue slot, IEEE-rounded per element.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+// acc += s * w  (both elements)
+__device__ __forceinline__ void fma2_scalar(f32x2_t& acc, float s, f32x2_t w) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(pack2(s, s)), "l"(w));
+}
+
 struct ActorSmem {
   // float offsets into dynamic shared memory
   int w[ACT_MAX_HIDDEN + 1], b[ACT_MAX_HIDDEN + 1], h;
@@ -142,16 +158,19 @@ __global__ void __launch_bounds__(ACT_MAX_THREADS, 1) actor_rollout_pendulum_ker
       const float* bl = act_sm + lay.b[l];
 #pragma unroll 1
       for (int jc = 0; jc < ACT_W / 8; ++jc) {
-        float acc[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+        f32x2_t acc2[4] = {0ull, 0ull, 0ull, 0ull};      // 8 output units as 4 packed pairs
         const float4* wrow = reinterpret_cast<const float4*>(wl + jc * 8);
 #pragma unroll
         for (int k = 0; k < ACT_W; ++k) {
           const float4 wa = wrow[k * (ACT_W / 4)], wb = wrow[k * (ACT_W / 4) + 1];
-          acc[0] = fmaf(h[k], wa.x, acc[0]); acc[1] = fmaf(h[k], wa.y, acc[1]);
-          acc[2] = fmaf(h[k], wa.z, acc[2]); acc[3] = fmaf(h[k], wa.w, acc[3]);
-          acc[4] = fmaf(h[k], wb.x, acc[4]); acc[5] = fmaf(h[k], wb.y, acc[5]);
-          acc[6] = fmaf(h[k], wb.z, acc[6]); acc[7] = fmaf(h[k], wb.w, acc[7]);
+          fma2_scalar(acc2[0], h[k], pack2(wa.x, wa.y));
+          fma2_scalar(acc2[1], h[k], pack2(wa.z, wa.w));
+          fma2_scalar(acc2[2], h[k], pack2(wb.x, wb.y));
+          fma2_scalar(acc2[3], h[k], pack2(wb.z, wb.w));
         }
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) unpack2(acc2[i], acc[2 * i], acc[2 * i + 1]);
         const float4 ba = *reinterpret_cast<const float4*>(bl + jc * 8);
         const float4 bb = *reinterpret_cast<const float4*>(bl + jc * 8 + 4);
         const float bias[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
@@ -161,15 +180,16 @@ __global__ void __launch_bounds__(ACT_MAX_THREADS, 1) actor_rollout_pendulum_ker
 #pragma unroll
       for (int k = 0; k < ACT_W; ++k) h[k] = h_col[k * nthr];
     }
-    float loc = 0.0f, raw_scale = 0.0f;
+    float loc, raw_scale;
     {
       const float2* wo = reinterpret_cast<const float2*>(act_sm + lay.w[a.num_hidden]);   // [64][2]
+      f32x2_t o2 = 0ull;
 #pragma unroll
       for (int k = 0; k < ACT_W; ++k) {
         const float2 v = wo[k];
-        loc = fmaf(h[k], v.x, loc);
-        raw_scale = fmaf(h[k], v.y, raw_scale);
+        fma2_scalar(o2, h[k], pack2(v.x, v.y));
       }
+      unpack2(o2, loc, raw_scale);
       loc += act_sm[lay.b[a.num_hidden]];
       raw_scale += act_sm[lay.b[a.num_hidden] + 1];
     }
