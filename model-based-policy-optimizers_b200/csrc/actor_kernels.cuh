@@ -14,11 +14,13 @@
 //                                                   carry = next                                  (convention 1)
 //   env.step          the wrapper stack of env_kernels.cuh (AutoReset / Episode / BraxWrapper / System.step)
 //
-// One thread per environment, T steps per launch.  The network runs in float32 on the CUDA cores (the
+// One thread per PAIR of environments, T steps per launch.  The network runs in float32 on the CUDA cores (the
 // reference network is float32; operand rounding to bf16 would change the collected actions): the
-// thread's current activations live in 64 registers, the weights are read from shared memory with
-// warp-broadcast 128-bit loads (8 output units per pass: 2 loads feed 8 FFMAs), the next layer's
-// activations pass through a column of shared memory private to the thread (no block barrier).
+// thread's current activations live in registers as packed (env 0, env 1) pairs, the weights are read from
+// shared memory with warp-broadcast 128-bit loads, and each weight feeds one packed FFMA2 (scalar weight x
+// activation pair): 2 loads per 16 FMAs -- the kernel is bound by shared-memory load issue, so sharing every
+// weight fetch between two envs is what sets its speed.  The next layer's activations pass through a column of
+// shared memory private to the thread (no block barrier).
 // The random draw is JAX's: normal(key, (E * A,))[e] costs one threefry block per env and step.
 // CTAs are sized so that the envs spread evenly over the SMs in a single wave (one CTA per SM).
 #pragma once
@@ -30,7 +32,7 @@ namespace mbpo {
 
 constexpr int ACT_W = 64;             // hidden width
 constexpr int ACT_MAX_HIDDEN = 4;     // hidden layers
-constexpr int ACT_MAX_THREADS = 448;  // 14 warps: 64 + ~80 registers per thread fit 65,536 / 448 = 146
+constexpr int ACT_MAX_THREADS = 256;  // 8 warps x 64 envs; 128 activation + ~100 other registers per thread
 
 struct ActorArgs {
   MbpoPendulumParams sys;
@@ -74,7 +76,7 @@ __device__ __forceinline__ f32x2_t pack2(float lo, float hi) {
 __device__ __forceinline__ void unpack2(f32x2_t v, float& lo, float& hi) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
 }
-// acc += s * w  (both elements)
+// acc += s * v  (s scalar, v and acc pairs)
 __device__ __forceinline__ void fma2_scalar(f32x2_t& acc, float s, f32x2_t w) {
   asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(pack2(s, s)), "l"(w));
 }
@@ -82,6 +84,11 @@ __device__ __forceinline__ void fma2_scalar(f32x2_t& acc, float s, f32x2_t w) {
 struct ActorSmem {
   // float offsets into dynamic shared memory
   int w[ACT_MAX_HIDDEN + 1], b[ACT_MAX_HIDDEN + 1], h;
+};
+
+// Per-env state of the wrapper stack, two envs per thread.
+struct ActorEnv {
+  float c, s, w, th, f_c, f_s, f_w, f_th, steps, done;
 };
 
 template <int PRNG, int MATH>
@@ -102,31 +109,36 @@ __global__ void __launch_bounds__(ACT_MAX_THREADS, 1) actor_rollout_pendulum_ker
     if (tid < 2) act_sm[lay.b[L] + tid] = a.b[L][tid];
   }
   __syncthreads();
-  const int e = blockIdx.x * nthr + tid;
-  const int warp_e0 = e - lane;
+  // A warp owns 64 consecutive envs: lane i carries env warp_e0 + i (slot 0) and warp_e0 + 32 + i (slot 1), so
+  // every weight fetched from shared memory feeds both and every store stays a full 128-byte line.
+  const int warp_e0 = (blockIdx.x * (nthr >> 5) + warp) * 64;
   if (warp_e0 >= a.E) return;
-  const bool live = e < a.E;
-  const int n_valid = ((a.E - warp_e0) < 32 ? (a.E - warp_e0) : 32) * 3;
-  const int ee = live ? e : a.E - 1;
   const PendulumConsts pc(a.sys);
   float* tile = tiles[warp];
-  float* h_col = act_sm + lay.h + tid;     // this thread's activation column: h_col[k * nthr]
-
-  float c = a.obs[3 * ee], s = a.obs[3 * ee + 1], w = a.obs[3 * ee + 2];
-  const float f_c = a.first_obs[3 * ee], f_s = a.first_obs[3 * ee + 1], f_w = a.first_obs[3 * ee + 2];
-  float steps = a.steps[ee], done = a.done[ee];
+  f32x2_t* h_col = reinterpret_cast<f32x2_t*>(act_sm + lay.h) + tid;   // this thread's activation column (env pair)
   const float ep_len = static_cast<float>(a.episode_length);
   const float rep = static_cast<float>(a.action_repeat);
   const size_t E = static_cast<size_t>(a.E);
-  float th = (MATH == MBPO_MATH_REFERENCE) ? 0.0f : atan2_bounded(s, c);
-  const float f_th = (MATH == MBPO_MATH_REFERENCE) ? 0.0f : atan2_bounded(f_s, f_c);
-  Key2 key{a.key_in[0], a.key_in[1]};
 
-  float* p_act = a.action_out + ee;
-  float* p_rew = a.reward_out + ee;
-  float* p_dis = a.discount_out + ee;
-  float* p_tru = a.truncation_out + ee;
-  float* p_nxt = a.next_observation_out + static_cast<size_t>(warp_e0) * 3 + lane;
+  ActorEnv env[2];
+  int e_idx[2], ee[2], half_e0[2], n_valid[2];
+  bool live[2], half_live[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    half_e0[q] = warp_e0 + 32 * q;
+    e_idx[q] = half_e0[q] + lane;
+    live[q] = e_idx[q] < a.E;
+    half_live[q] = half_e0[q] < a.E;
+    ee[q] = live[q] ? e_idx[q] : a.E - 1;   // dead lanes shadow the last env, their stores are masked
+    const int rem = a.E - half_e0[q];
+    n_valid[q] = (rem < 32 ? (rem > 0 ? rem : 0) : 32) * 3;
+    env[q].c = a.obs[3 * ee[q]]; env[q].s = a.obs[3 * ee[q] + 1]; env[q].w = a.obs[3 * ee[q] + 2];
+    env[q].f_c = a.first_obs[3 * ee[q]]; env[q].f_s = a.first_obs[3 * ee[q] + 1]; env[q].f_w = a.first_obs[3 * ee[q] + 2];
+    env[q].steps = a.steps[ee[q]]; env[q].done = a.done[ee[q]];
+    env[q].th = (MATH == MBPO_MATH_REFERENCE) ? 0.0f : atan2_bounded(env[q].s, env[q].c);
+    env[q].f_th = (MATH == MBPO_MATH_REFERENCE) ? 0.0f : atan2_bounded(env[q].f_s, env[q].f_c);
+  }
+  Key2 key{a.key_in[0], a.key_in[1]};
 
 #pragma unroll 1
   for (int t = 0; t < a.T; ++t) {
@@ -138,18 +150,24 @@ __global__ void __launch_bounds__(ACT_MAX_THREADS, 1) actor_rollout_pendulum_ker
       if (a.key_convention == 0) { key = first; k_actor = second; }   // sac.py:290
       else { k_actor = first; key = second; }                          // acting.py:70
     }
-    // ---- policy network, float32 ----------------------------------------------------------------------
-    float h[ACT_W];
+    // ---- policy network, float32; every activation is a pair (env slot 0, env slot 1) -------------------
+    f32x2_t h[ACT_W];
     {
       const float4* w0 = reinterpret_cast<const float4*>(act_sm + lay.w[0]);   // [3][64]
       const float4* b0 = reinterpret_cast<const float4*>(act_sm + lay.b[0]);
 #pragma unroll
       for (int j4 = 0; j4 < ACT_W / 4; ++j4) {
         const float4 r0 = w0[j4], r1 = w0[ACT_W / 4 + j4], r2 = w0[2 * (ACT_W / 4) + j4], bb = b0[j4];
-        h[4 * j4 + 0] = swish_exact(fmaf(w, r2.x, fmaf(s, r1.x, c * r0.x)) + bb.x);
-        h[4 * j4 + 1] = swish_exact(fmaf(w, r2.y, fmaf(s, r1.y, c * r0.y)) + bb.y);
-        h[4 * j4 + 2] = swish_exact(fmaf(w, r2.z, fmaf(s, r1.z, c * r0.z)) + bb.z);
-        h[4 * j4 + 3] = swish_exact(fmaf(w, r2.w, fmaf(s, r1.w, c * r0.w)) + bb.w);
+        const float wr0[4] = {r0.x, r0.y, r0.z, r0.w}, wr1[4] = {r1.x, r1.y, r1.z, r1.w};
+        const float wr2[4] = {r2.x, r2.y, r2.z, r2.w}, wb[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float v[2];
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+            v[q] = swish_exact(fmaf(env[q].w, wr2[i], fmaf(env[q].s, wr1[i], env[q].c * wr0[i])) + wb[i]);
+          h[4 * j4 + i] = pack2(v[0], v[1]);
+        }
       }
     }
 #pragma unroll 1
@@ -158,81 +176,92 @@ __global__ void __launch_bounds__(ACT_MAX_THREADS, 1) actor_rollout_pendulum_ker
       const float* bl = act_sm + lay.b[l];
 #pragma unroll 1
       for (int jc = 0; jc < ACT_W / 8; ++jc) {
-        f32x2_t acc2[4] = {0ull, 0ull, 0ull, 0ull};      // 8 output units as 4 packed pairs
+        f32x2_t acc2[8] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};   // 8 output units x the env pair
         const float4* wrow = reinterpret_cast<const float4*>(wl + jc * 8);
 #pragma unroll
         for (int k = 0; k < ACT_W; ++k) {
           const float4 wa = wrow[k * (ACT_W / 4)], wb = wrow[k * (ACT_W / 4) + 1];
-          fma2_scalar(acc2[0], h[k], pack2(wa.x, wa.y));
-          fma2_scalar(acc2[1], h[k], pack2(wa.z, wa.w));
-          fma2_scalar(acc2[2], h[k], pack2(wb.x, wb.y));
-          fma2_scalar(acc2[3], h[k], pack2(wb.z, wb.w));
+          fma2_scalar(acc2[0], wa.x, h[k]); fma2_scalar(acc2[1], wa.y, h[k]);
+          fma2_scalar(acc2[2], wa.z, h[k]); fma2_scalar(acc2[3], wa.w, h[k]);
+          fma2_scalar(acc2[4], wb.x, h[k]); fma2_scalar(acc2[5], wb.y, h[k]);
+          fma2_scalar(acc2[6], wb.z, h[k]); fma2_scalar(acc2[7], wb.w, h[k]);
         }
-        float acc[8];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) unpack2(acc2[i], acc[2 * i], acc[2 * i + 1]);
         const float4 ba = *reinterpret_cast<const float4*>(bl + jc * 8);
         const float4 bb = *reinterpret_cast<const float4*>(bl + jc * 8 + 4);
         const float bias[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) h_col[(jc * 8 + i) * nthr] = swish_exact(acc[i] + bias[i]);
+        for (int i = 0; i < 8; ++i) {
+          float v0, v1;
+          unpack2(acc2[i], v0, v1);
+          h_col[(jc * 8 + i) * nthr] = pack2(swish_exact(v0 + bias[i]), swish_exact(v1 + bias[i]));
+        }
       }
 #pragma unroll
       for (int k = 0; k < ACT_W; ++k) h[k] = h_col[k * nthr];
     }
-    float loc, raw_scale;
+    float loc[2], raw_scale[2];
     {
       const float2* wo = reinterpret_cast<const float2*>(act_sm + lay.w[a.num_hidden]);   // [64][2]
-      f32x2_t o2 = 0ull;
+      f32x2_t l2 = 0ull, s2 = 0ull;
 #pragma unroll
       for (int k = 0; k < ACT_W; ++k) {
         const float2 v = wo[k];
-        fma2_scalar(o2, h[k], pack2(v.x, v.y));
+        fma2_scalar(l2, v.x, h[k]);
+        fma2_scalar(s2, v.y, h[k]);
       }
-      unpack2(o2, loc, raw_scale);
-      loc += act_sm[lay.b[a.num_hidden]];
-      raw_scale += act_sm[lay.b[a.num_hidden] + 1];
+      unpack2(l2, loc[0], loc[1]);
+      unpack2(s2, raw_scale[0], raw_scale[1]);
     }
-    float u;
-    if (a.deterministic) {
-      u = tanhf(loc);                                                   // mode(): tanh(loc)
-    } else {
-      const float eps = bits_to_normal(random_bits_at<PRNG>(k_actor, static_cast<uint32_t>(a.E), static_cast<uint32_t>(ee)));
-      const float scale = softplus_exact(raw_scale) + a.min_std;
-      u = tanhf(__fadd_rn(__fmul_rn(scale, eps), loc));                 // distrax Normal.sample: scale * rnd + loc
+    const float b_loc = act_sm[lay.b[a.num_hidden]], b_scale = act_sm[lay.b[a.num_hidden] + 1];
+    const size_t row = static_cast<size_t>(t) * E;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      if (!half_live[q]) continue;   // warp-uniform
+      ActorEnv& v = env[q];
+      float u;
+      if (a.deterministic) {
+        u = tanhf(loc[q] + b_loc);                                       // mode(): tanh(loc)
+      } else {
+        const float eps = bits_to_normal(random_bits_at<PRNG>(k_actor, static_cast<uint32_t>(a.E),
+                                                               static_cast<uint32_t>(ee[q])));
+        const float scale = softplus_exact(raw_scale[q] + b_scale) + a.min_std;
+        u = tanhf(__fadd_rn(__fmul_rn(scale, eps), loc[q] + b_loc));      // distrax Normal.sample: scale * rnd + loc
+      }
+      // ---- wrapped env step (env_kernels.cuh) ------------------------------------------------------------
+      v.steps = (v.done != 0.0f) ? 0.0f : v.steps;
+      v.done = 0.0f;
+      float rew = 0.0f;
+      for (int r = 0; r < a.action_repeat; ++r) {
+        float rr;
+        if (MATH == MBPO_MATH_REFERENCE) pendulum_step_ref(pc, v.c, v.s, v.w, u, rr);
+        else pendulum_step_theta(pc, v.th, v.w, u, rr);
+        rew = __fadd_rn(rew, rr);
+      }
+      if (MATH != MBPO_MATH_REFERENCE) sincos_bounded(v.th, v.s, v.c);
+      v.steps = __fadd_rn(v.steps, rep);
+      const bool over = v.steps >= ep_len;
+      const float trunc = over ? (1.0f - v.done) : 0.0f;
+      v.done = over ? 1.0f : v.done;
+      if (over) { v.c = v.f_c; v.s = v.f_s; v.w = v.f_w; v.th = v.f_th; }
+      warp_store3(tile, a.next_observation_out + (row + half_e0[q]) * 3 + lane, lane, n_valid[q], v.c, v.s, v.w);
+      if (live[q]) {
+        a.action_out[row + e_idx[q]] = u;
+        a.reward_out[row + e_idx[q]] = rew;
+        a.discount_out[row + e_idx[q]] = 1.0f - v.done;
+        a.truncation_out[row + e_idx[q]] = trunc;
+      }
     }
-    // ---- wrapped env step (env_kernels.cuh) --------------------------------------------------------------
-    steps = (done != 0.0f) ? 0.0f : steps;
-    done = 0.0f;
-    float rew = 0.0f;
-    for (int r = 0; r < a.action_repeat; ++r) {
-      float rr;
-      if (MATH == MBPO_MATH_REFERENCE) pendulum_step_ref(pc, c, s, w, u, rr);
-      else pendulum_step_theta(pc, th, w, u, rr);
-      rew = __fadd_rn(rew, rr);
-    }
-    if (MATH != MBPO_MATH_REFERENCE) sincos_bounded(th, s, c);
-    steps = __fadd_rn(steps, rep);
-    const bool over = steps >= ep_len;
-    const float trunc = over ? (1.0f - done) : 0.0f;
-    done = over ? 1.0f : done;
-    if (over) { c = f_c; s = f_s; w = f_w; th = f_th; }
-    warp_store3(tile, p_nxt, lane, n_valid, c, s, w);
-    p_nxt += 3 * E;
-    if (live) {
-      *p_act = u;
-      *p_rew = rew;
-      *p_dis = 1.0f - done;
-      *p_tru = trunc;
-    }
-    p_act += E; p_rew += E; p_dis += E; p_tru += E;
   }
-  if (live) {
-    a.obs[3 * e] = c; a.obs[3 * e + 1] = s; a.obs[3 * e + 2] = w;
-    a.steps[e] = steps;
-    a.done[e] = done;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    if (live[q]) {
+      const int e = e_idx[q];
+      a.obs[3 * e] = env[q].c; a.obs[3 * e + 1] = env[q].s; a.obs[3 * e + 2] = env[q].w;
+      a.steps[e] = env[q].steps;
+      a.done[e] = env[q].done;
+    }
   }
-  if (e == 0 && a.key_out) { a.key_out[0] = key.k0; a.key_out[1] = key.k1; }
+  if (blockIdx.x == 0 && tid == 0 && a.key_out) { a.key_out[0] = key.k0; a.key_out[1] = key.k1; }
 }
 
 }  // namespace mbpo

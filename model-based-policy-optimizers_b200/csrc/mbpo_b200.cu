@@ -601,10 +601,12 @@ int launch_actor(const mbpo::ActorArgs& a, cudaStream_t st) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  // one wave, one CTA per SM: threads = ceil(E / SMs) rounded up to a warp, at most ACT_MAX_THREADS
-  int threads = ((a.E + sms - 1) / sms + 31) / 32 * 32;
-  if (threads > ACT_MAX_THREADS) threads = ACT_MAX_THREADS;
-  if (threads < 32) threads = 32;
+  // one wave, one CTA per SM: a warp carries 64 envs; warps = ceil(E / 64 / SMs), at most ACT_MAX_THREADS / 32
+  const int warps_total = (a.E + 63) / 64;
+  int warps = (warps_total + sms - 1) / sms;
+  if (warps > ACT_MAX_THREADS / 32) warps = ACT_MAX_THREADS / 32;
+  if (warps < 1) warps = 1;
+  const int threads = warps * 32;
   ActorSmem lay;
   int off = 0;
   auto take = [&](int n) { const int o = off; off += (n + 3) / 4 * 4; return o; };
@@ -613,12 +615,12 @@ int launch_actor(const mbpo::ActorArgs& a, cudaStream_t st) {
   lay.w[a.num_hidden] = take(ACT_W * 2);
   for (int l = 0; l < a.num_hidden; ++l) lay.b[l] = take(ACT_W);
   lay.b[a.num_hidden] = take(2);
-  lay.h = take(ACT_W * threads);
+  lay.h = take(2 * ACT_W * threads);   // pairs
   const size_t smem = static_cast<size_t>(off) * sizeof(float);
   auto kernel = actor_rollout_pendulum_kernel<PRNG, MATH>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return fail(MBPO_ECUDA, "actor_rollout: smem attribute (%zu B): %s", smem, cudaGetErrorString(e));
-  const unsigned blocks = static_cast<unsigned>((a.E + threads - 1) / threads);
+  const unsigned blocks = static_cast<unsigned>((warps_total + warps - 1) / warps);
   kernel<<<blocks, threads, smem, st>>>(a, lay);
   return check_launch("actor_rollout_pendulum_kernel");
 }
