@@ -390,13 +390,26 @@ def run_env(args):
     n = buf[1:]
     r = torch.empty((T, E), device=dev); d = torch.empty((T, E), device=dev); tr = torch.empty((T, E), device=dev)
     params = system.pack_params(sp)
-    obs, steps, done, first = st.obs.clone(), st.info["steps"].clone(), st.done.clone(), st.info["first_obs"]
+    first = st.info["first_obs"]
+    # env state ping-pongs between two buffer sets: mbpo_env_unroll reads one and writes the other
+    state = [[st.obs.clone(), st.info["steps"].clone(), st.done.clone()],
+             [st.obs.clone(), st.info["steps"].clone(), st.done.clone()]]
+    flip = [0]
 
     def launch():
-        L.check(L.lib.mbpo_env_rollout(system.system_kind, L.C.addressof(params), mbpo_b200.config.math_mode_id, 3, 1,
-                                       ENV_EPISODE, 1, L.ptr(obs), L.ptr(steps), L.ptr(done), L.ptr(first),
-                                       L.ptr(acts), E, T, None, L.ptr(r), L.ptr(d), L.ptr(n), L.ptr(tr),
-                                       L.stream_ptr(dev)))
+        src, dst = state[flip[0]], state[flip[0] ^ 1]
+        flip[0] ^= 1
+        if args.env_sequential:      # the one-thread-per-env scan, for comparison
+            L.check(L.lib.mbpo_env_rollout(system.system_kind, L.C.addressof(params), mbpo_b200.config.math_mode_id,
+                                           3, 1, ENV_EPISODE, 1, L.ptr(src[0]), L.ptr(src[1]), L.ptr(src[2]),
+                                           L.ptr(first), L.ptr(acts), E, T, None, L.ptr(r), L.ptr(d), L.ptr(n),
+                                           L.ptr(tr), L.stream_ptr(dev)))
+            flip[0] ^= 1
+            return
+        L.check(L.lib.mbpo_env_unroll(system.system_kind, L.C.addressof(params), mbpo_b200.config.math_mode_id, 3, 1,
+                                      ENV_EPISODE, 1, L.ptr(src[0]), L.ptr(src[1]), L.ptr(src[2]), L.ptr(dst[0]),
+                                      L.ptr(dst[1]), L.ptr(dst[2]), L.ptr(first), L.ptr(acts), E, T, None, L.ptr(r),
+                                      L.ptr(d), L.ptr(n), L.ptr(tr), L.stream_ptr(dev)))
     for _ in range(max(args.warmup, 3)):
         launch()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
@@ -443,6 +456,7 @@ def run_env(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "config3_env_rollouts", "envs": ENV_E, "steps_per_call": T,
                        "episode_length": ENV_EPISODE, "action_repeat": 1, "parallelism": "envs sharded x%d" % world,
+                       "kernel": "sequential scan per env" if args.env_sequential else "episode pieces rolled concurrently",
                        "l2": "inputs+outputs %.2f GB per call >> 126 MB L2" % (E * T * ENV_BYTES_PER_TRANSITION / 1e9)},
             "math_mode": args.math, "clocks": clk.summary(),
             "e2e": {"value": ENV_E * T / e2e_s, "unit": "env-steps/s", "ms_per_step": e2e_s * 1e3,
@@ -946,6 +960,8 @@ def main():
                     default="config2_batched_icem")
     ap.add_argument("--math", choices=["reference", "theta_carry"], default="reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--env-sequential", action="store_true",
+                    help="config3_env_rollouts: time the one-thread-per-env scan instead of the episode-piece kernel")
     args = ap.parse_args()
     global GUARD
     with _StdoutGuard() as GUARD:

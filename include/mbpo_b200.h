@@ -216,6 +216,18 @@ int mbpo_env_rollout(int system_kind, const void* sys_params_host, int math_mode
                      int E, int T, float* observation_out, float* reward_out, float* discount_out,
                      float* next_observation_out, float* truncation_out, void* stream);
 
+/* The same T steps with the env state passed by value: obs_in/steps_in/done_in are read, the state
+ * after step T goes to obs_out/steps_out/done_out, which must NOT alias the inputs.  The pendulum
+ * System never ends an episode itself, so the AutoReset points follow from the step counters and
+ * the pieces between them are rolled concurrently (one thread per env and piece); results are
+ * bit-identical to mbpo_env_rollout.  steps must be integer-valued, as brax's are. */
+int mbpo_env_unroll(int system_kind, const void* sys_params_host, int math_mode, int x_dim,
+                    int action_dim, int episode_length, int action_repeat, const float* obs_in,
+                    const float* steps_in, const float* done_in, float* obs_out, float* steps_out,
+                    float* done_out, const float* first_obs, const float* actions, int E, int T,
+                    float* observation_out, float* reward_out, float* discount_out,
+                    float* next_observation_out, float* truncation_out, void* stream);
+
 /* ---- policy in the env loop: SAC / PPO data collection ------------------------------------- */
 /* The stochastic policy of sac/sac_networks.py:58-73 + sac/parametric_distribution.py:97-125:
  * logits = MLP(obs) (swish; Dense = x @ W + b), loc, scale = split(logits, 2),

@@ -23,9 +23,12 @@ namespace mbpo {
 struct EnvArgs {
   MbpoPendulumParams sys;
   int E, T, episode_length, action_repeat;
-  float* obs;            // [E,3] in/out
-  float* steps;          // [E]   in/out
-  float* done;           // [E]   in/out
+  const float* obs_in;   // [E,3]
+  const float* steps_in; // [E]
+  const float* done_in;  // [E]
+  float* obs;            // [E,3] out (may alias obs_in when segmented == 0)
+  float* steps;          // [E]   out
+  float* done;           // [E]   out
   const float* first_obs;  // [E,3]
   const float* actions;  // [T,E]
   float* observation_out;       // [T,E,3] or NULL
@@ -33,27 +36,43 @@ struct EnvArgs {
   float* discount_out;          // [T,E]   or NULL
   float* next_observation_out;  // [T,E,3] or NULL
   float* truncation_out;        // [T,E]   or NULL
+  int segmented;                // 1: blockIdx.y = episode segment (in/out state must not alias)
 };
 
 constexpr int ENV_CHUNK = 8;     // actions prefetched per thread (registers)
 constexpr int ENV_THREADS = 64;   // 1,024 CTAs for 65,536 envs: 6.9 per SM, 1% imbalance (128 threads: 14%)
 
 // Transposes a warp's 32 x 3 floats through shared memory so the [E,3] rows leave as three
-// fully coalesced 128-byte stores.  dst already points at this lane's first element.
-__device__ __forceinline__ void warp_store3(float* tile, float* dst, int lane, int n_valid, float a, float b, float c) {
+// fully coalesced 128-byte stores.  dst already points at this lane's first element; m0/m1/m2 say
+// whether the env owning element lane / lane+32 / lane+64 of the tile is written by this warp.
+__device__ __forceinline__ void warp_store3(float* tile, float* dst, int lane, bool m0, bool m1, bool m2, float a,
+                                            float b, float c) {
   tile[lane * 3] = a;
   tile[lane * 3 + 1] = b;
   tile[lane * 3 + 2] = c;
   __syncwarp();
   const float v0 = tile[lane], v1 = tile[lane + 32], v2 = tile[lane + 64];
   __syncwarp();
-  if (lane < n_valid) dst[0] = v0;
-  if (lane + 32 < n_valid) dst[32] = v1;
-  if (lane + 64 < n_valid) dst[64] = v2;
+  if (m0) dst[0] = v0;
+  if (m1) dst[32] = v1;
+  if (m2) dst[64] = v2;
+}
+__device__ __forceinline__ void warp_store3(float* tile, float* dst, int lane, int n_valid, float a, float b, float c) {
+  warp_store3(tile, dst, lane, lane < n_valid, lane + 32 < n_valid, lane + 64 < n_valid, a, b, c);
 }
 
-// OBS: also write the separate observation buffer.  OUT: write next_obs / reward / discount /
-// truncation (all four non-NULL; the C ABI falls back to the checked kernel otherwise).
+// Episode segments.  The pendulum System never terminates an episode itself (done = 0.0,
+// pendulum_system.py:36), so the AutoReset points of an env are known from its step counter alone
+// (training.py:98-107,120-124): the first after n0 = max(1, ceil((episode_length - steps) / repeat))
+// steps, then every L = ceil(episode_length / repeat) steps, and each reset restarts the env from
+// first_obs with steps = 0 (training.py:136).  The T-step rollout of one env is therefore 1 +
+// ceil((T - 1) / L) independent pieces; thread (env, k) rolls piece k, which multiplies the number
+// of independent dependency chains (65,536 envs alone are 3.5 warps per SM sub-partition).  The
+// results are those of the sequential scan, bit for bit.  steps must be integer-valued (< 2^24),
+// as brax's are.
+//
+// OBS: also write the separate observation buffer.  All of next_obs / reward / discount /
+// truncation are non-NULL (the C ABI falls back to the checked kernel otherwise).
 template <int MATH, bool OBS>
 __global__ void __launch_bounds__(ENV_THREADS) env_rollout_pendulum_kernel(const __grid_constant__ EnvArgs a) {
   __shared__ float tiles[ENV_THREADS / 32][96];
@@ -62,70 +81,101 @@ __global__ void __launch_bounds__(ENV_THREADS) env_rollout_pendulum_kernel(const
   const int warp_e0 = e - lane;
   if (warp_e0 >= a.E) return;
   const bool live = e < a.E;
-  const int n_valid = ((a.E - warp_e0) < 32 ? (a.E - warp_e0) : 32) * 3;
   const int ee = live ? e : a.E - 1;  // dead lanes shadow the last env, their stores are masked
   const PendulumConsts pc(a.sys);
   float* tile = tiles[warp];
+  const int seg = a.segmented ? static_cast<int>(blockIdx.y) : 0;
 
-  float c = a.obs[3 * ee], s = a.obs[3 * ee + 1], w = a.obs[3 * ee + 2];
+  float steps = a.steps_in[ee], done = a.done_in[ee];
+  // this thread's piece [t_beg, t_end) of the env's T steps
+  int t_beg = 0, t_end = a.T;
+  if (a.segmented) {
+    const int s0 = (done != 0.0f) ? 0 : __float2int_rn(steps);
+    const int rep_i = a.action_repeat;
+    const int n0 = (a.episode_length > s0) ? max(1, (a.episode_length - s0 + rep_i - 1) / rep_i) : 1;
+    const int len = max(1, (a.episode_length + rep_i - 1) / rep_i);
+    t_beg = (seg == 0) ? 0 : min(a.T, n0 + (seg - 1) * len);
+    t_end = min(a.T, n0 + seg * len);
+  }
+  const int w_beg = __reduce_min_sync(0xffffffffu, t_beg);
+  const int w_end = __reduce_max_sync(0xffffffffu, t_end);
+  if (w_beg >= w_end) return;
+
   const float f_c = a.first_obs[3 * ee], f_s = a.first_obs[3 * ee + 1], f_w = a.first_obs[3 * ee + 2];
-  float steps = a.steps[ee], done = a.done[ee];
+  float c, s, w;
+  if (seg == 0) {
+    c = a.obs_in[3 * ee]; s = a.obs_in[3 * ee + 1]; w = a.obs_in[3 * ee + 2];
+  } else {  // the step before this piece ended an episode: obs = first_obs, done = 1 (steps -> 0 below)
+    c = f_c; s = f_s; w = f_w;
+    done = 1.0f;
+  }
   const float ep_len = static_cast<float>(a.episode_length);
   const float rep = static_cast<float>(a.action_repeat);
   const size_t E = static_cast<size_t>(a.E);
   // theta-carry: the angle lives in a register across steps; [cos, sin] are only outputs
   float th = (MATH == MBPO_MATH_REFERENCE) ? 0.0f : atan2_bounded(s, c);
   const float f_th = (MATH == MBPO_MATH_REFERENCE) ? 0.0f : atan2_bounded(f_s, f_c);
+  // tile element j of a row belongs to env warp_e0 + j / 3
+  const int own0 = lane / 3, own1 = (lane + 32) / 3, own2 = (lane + 64) / 3;
 
   // running pointers, advanced by one time step per iteration
-  const float* p_act = a.actions + ee;
-  float* p_rew = a.reward_out + ee;
-  float* p_dis = a.discount_out + ee;
-  float* p_tru = a.truncation_out + ee;
-  float* p_nxt = a.next_observation_out + static_cast<size_t>(warp_e0) * 3 + lane;
-  float* p_obs = OBS ? a.observation_out + static_cast<size_t>(warp_e0) * 3 + lane : nullptr;
+  const size_t row0 = static_cast<size_t>(w_beg) * E;
+  const float* p_act = a.actions + row0 + ee;
+  float* p_rew = a.reward_out + row0 + ee;
+  float* p_dis = a.discount_out + row0 + ee;
+  float* p_tru = a.truncation_out + row0 + ee;
+  float* p_nxt = a.next_observation_out + (row0 + warp_e0) * 3 + lane;
+  float* p_obs = OBS ? a.observation_out + (row0 + warp_e0) * 3 + lane : nullptr;
 
   float u_buf[ENV_CHUNK];
 #pragma unroll
-  for (int k = 0; k < ENV_CHUNK; ++k) u_buf[k] = (k < a.T) ? __ldg(p_act + k * E) : 0.0f;
+  for (int k = 0; k < ENV_CHUNK; ++k) u_buf[k] = (w_beg + k < w_end) ? __ldg(p_act + k * E) : 0.0f;
   p_act += ENV_CHUNK * E;
 
-  for (int t0 = 0; t0 < a.T; t0 += ENV_CHUNK) {
+  for (int t0 = w_beg; t0 < w_end; t0 += ENV_CHUNK) {
     float u_cur[ENV_CHUNK];
 #pragma unroll
     for (int k = 0; k < ENV_CHUNK; ++k) u_cur[k] = u_buf[k];
     // prefetch the next chunk while this one computes
 #pragma unroll
-    for (int k = 0; k < ENV_CHUNK; ++k) u_buf[k] = (t0 + ENV_CHUNK + k < a.T) ? __ldg(p_act + k * E) : 0.0f;
+    for (int k = 0; k < ENV_CHUNK; ++k) u_buf[k] = (t0 + ENV_CHUNK + k < w_end) ? __ldg(p_act + k * E) : 0.0f;
     p_act += ENV_CHUNK * E;
-    const int kmax = (a.T - t0) < ENV_CHUNK ? (a.T - t0) : ENV_CHUNK;
+    const int kmax = (w_end - t0) < ENV_CHUNK ? (w_end - t0) : ENV_CHUNK;
 #pragma unroll
     for (int k = 0; k < ENV_CHUNK; ++k) {
       if (k < kmax) {
+        // envs of one warp share their piece boundaries unless their step counters differ
+        const bool act = live && (t0 + k >= t_beg) && (t0 + k < t_end);
+        const unsigned am = __ballot_sync(0xffffffffu, act);
+        const bool m0 = (am >> own0) & 1u, m1 = (am >> own1) & 1u, m2 = (am >> own2) & 1u;
         // AutoReset pre-step (training.py:120-124)
-        steps = (done != 0.0f) ? 0.0f : steps;
-        done = 0.0f;
+        if (act) {
+          steps = (done != 0.0f) ? 0.0f : steps;
+          done = 0.0f;
+        }
         if (OBS) {
-          warp_store3(tile, p_obs, lane, n_valid, c, s, w);
+          warp_store3(tile, p_obs, lane, m0, m1, m2, c, s, w);
           p_obs += 3 * E;
         }
-        // Episode: action_repeat x system.step with the same action (training.py:92-97)
-        float rew = 0.0f;
-        for (int r = 0; r < a.action_repeat; ++r) {
-          float rr;
-          if (MATH == MBPO_MATH_REFERENCE) pendulum_step_ref(pc, c, s, w, u_cur[k], rr);
-          else pendulum_step_theta(pc, th, w, u_cur[k], rr);
-          rew = __fadd_rn(rew, rr);
+        float rew = 0.0f, trunc = 0.0f;
+        if (act) {
+          // Episode: action_repeat x system.step with the same action (training.py:92-97)
+          for (int r = 0; r < a.action_repeat; ++r) {
+            float rr;
+            if (MATH == MBPO_MATH_REFERENCE) pendulum_step_ref(pc, c, s, w, u_cur[k], rr);
+            else pendulum_step_theta(pc, th, w, u_cur[k], rr);
+            rew = __fadd_rn(rew, rr);
+          }
+          if (MATH != MBPO_MATH_REFERENCE) sincos_bounded(th, s, c);
+          steps = __fadd_rn(steps, rep);
+          const bool over = steps >= ep_len;                   // training.py:98-107
+          trunc = over ? (1.0f - done) : 0.0f;                 // system done is always 0.0
+          done = over ? 1.0f : done;
+          if (over) { c = f_c; s = f_s; w = f_w; th = f_th; }  // training.py:136
         }
-        if (MATH != MBPO_MATH_REFERENCE) sincos_bounded(th, s, c);
-        steps = __fadd_rn(steps, rep);
-        const bool over = steps >= ep_len;                   // training.py:98-107
-        const float trunc = over ? (1.0f - done) : 0.0f;     // system done is always 0.0
-        done = over ? 1.0f : done;
-        if (over) { c = f_c; s = f_s; w = f_w; th = f_th; }  // training.py:136
-        warp_store3(tile, p_nxt, lane, n_valid, c, s, w);
+        warp_store3(tile, p_nxt, lane, m0, m1, m2, c, s, w);
         p_nxt += 3 * E;
-        if (live) {
+        if (act) {
           *p_rew = rew;
           *p_dis = 1.0f - done;
           *p_tru = trunc;
@@ -134,7 +184,7 @@ __global__ void __launch_bounds__(ENV_THREADS) env_rollout_pendulum_kernel(const
       }
     }
   }
-  if (live) {
+  if (live && t_beg < t_end && t_end == a.T) {  // the piece holding the last step owns the final state
     a.obs[3 * e] = c; a.obs[3 * e + 1] = s; a.obs[3 * e + 2] = w;
     a.steps[e] = steps;
     a.done[e] = done;
@@ -154,9 +204,9 @@ __global__ void __launch_bounds__(ENV_THREADS) env_rollout_pendulum_checked_kern
   const int ee = live ? e : a.E - 1;
   const PendulumConsts pc(a.sys);
   float* tile = tiles[warp];
-  float c = a.obs[3 * ee], s = a.obs[3 * ee + 1], w = a.obs[3 * ee + 2];
+  float c = a.obs_in[3 * ee], s = a.obs_in[3 * ee + 1], w = a.obs_in[3 * ee + 2];
   const float f_c = a.first_obs[3 * ee], f_s = a.first_obs[3 * ee + 1], f_w = a.first_obs[3 * ee + 2];
-  float steps = a.steps[ee], done = a.done[ee];
+  float steps = a.steps_in[ee], done = a.done_in[ee];
   const float ep_len = static_cast<float>(a.episode_length);
   const float rep = static_cast<float>(a.action_repeat);
   for (int t = 0; t < a.T; ++t) {

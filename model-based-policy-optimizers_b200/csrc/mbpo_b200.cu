@@ -558,14 +558,18 @@ int mbpo_icem_mpc_closed_loop(const MbpoIcemCfg* cfg, const void* sys_params_hos
 }
 
 // ---- env rollouts ----------------------------------------------------------------------------------
-int mbpo_env_rollout(int system_kind, const void* sys_params_host, int math_mode, int x_dim, int action_dim,
-                     int episode_length, int action_repeat, float* obs, float* steps, float* done,
-                     const float* first_obs, const float* actions, int E, int T, float* observation_out,
-                     float* reward_out, float* discount_out, float* next_observation_out, float* truncation_out,
-                     void* stream) {
+extern "C++" {
+namespace {
+int launch_env(int system_kind, const void* sys_params_host, int math_mode, int x_dim, int action_dim,
+               int episode_length, int action_repeat, const float* obs_in, const float* steps_in,
+               const float* done_in, float* obs, float* steps, float* done, const float* first_obs,
+               const float* actions, int E, int T, float* observation_out, float* reward_out, float* discount_out,
+               float* next_observation_out, float* truncation_out, bool segmented, void* stream) {
+  using namespace mbpo;
   if (system_kind != MBPO_SYSTEM_PENDULUM)
     return fail(MBPO_EUNSUPPORTED, "env_rollout: only MBPO_SYSTEM_PENDULUM has an inlined step");
-  MBPO_REQUIRE(sys_params_host && obs && steps && done && first_obs && actions, "env_rollout: null pointer");
+  MBPO_REQUIRE(sys_params_host && obs_in && steps_in && done_in && obs && steps && done && first_obs && actions,
+               "env_rollout: null pointer");
   MBPO_REQUIRE(action_dim == 1 && x_dim == 3, "env_rollout: pendulum needs action_dim == 1, x_dim == 3");
   MBPO_REQUIRE(math_mode == 0 || math_mode == 1, "env_rollout: bad math_mode %d", math_mode);
   MBPO_REQUIRE(episode_length >= 1 && action_repeat >= 1, "env_rollout: episode_length/action_repeat < 1");
@@ -574,12 +578,22 @@ int mbpo_env_rollout(int system_kind, const void* sys_params_host, int math_mode
   EnvArgs a;
   a.sys = *static_cast<const MbpoPendulumParams*>(sys_params_host);
   a.E = E; a.T = T; a.episode_length = episode_length; a.action_repeat = action_repeat;
+  a.obs_in = obs_in; a.steps_in = steps_in; a.done_in = done_in;
   a.obs = obs; a.steps = steps; a.done = done; a.first_obs = first_obs; a.actions = actions;
   a.observation_out = observation_out; a.reward_out = reward_out; a.discount_out = discount_out;
   a.next_observation_out = next_observation_out; a.truncation_out = truncation_out;
-  const unsigned blocks = static_cast<unsigned>((E + ENV_THREADS - 1) / ENV_THREADS);
-  cudaStream_t st = as_stream(stream);
   const bool all_out = reward_out && discount_out && next_observation_out && truncation_out;
+  // pieces between AutoReset points (env_kernels.cuh): the first is at least one step long
+  const long long len = (static_cast<long long>(episode_length) + action_repeat - 1) / action_repeat;
+  long long pieces = 1 + (static_cast<long long>(T) - 1 + len - 1) / len;
+  if (pieces > 65535) pieces = 1;
+  a.segmented = (segmented && all_out && pieces > 1) ? 1 : 0;
+  if (a.segmented)
+    MBPO_REQUIRE(obs != obs_in && steps != steps_in && done != done_in,
+                 "env_unroll: the outgoing env state must not alias the incoming one");
+  const dim3 blocks(static_cast<unsigned>((E + ENV_THREADS - 1) / ENV_THREADS),
+                    a.segmented ? static_cast<unsigned>(pieces) : 1u);
+  cudaStream_t st = as_stream(stream);
   const int sel = (all_out ? (observation_out ? 2 : 1) : 0) * 2 + math_mode;
   switch (sel) {
     case 0: env_rollout_pendulum_checked_kernel<0><<<blocks, ENV_THREADS, 0, st>>>(a); break;
@@ -590,6 +604,29 @@ int mbpo_env_rollout(int system_kind, const void* sys_params_host, int math_mode
     default: env_rollout_pendulum_kernel<1, true><<<blocks, ENV_THREADS, 0, st>>>(a); break;
   }
   return check_launch("env_rollout_pendulum_kernel");
+}
+}  // namespace
+}  // extern "C++"
+
+int mbpo_env_rollout(int system_kind, const void* sys_params_host, int math_mode, int x_dim, int action_dim,
+                     int episode_length, int action_repeat, float* obs, float* steps, float* done,
+                     const float* first_obs, const float* actions, int E, int T, float* observation_out,
+                     float* reward_out, float* discount_out, float* next_observation_out, float* truncation_out,
+                     void* stream) {
+  return launch_env(system_kind, sys_params_host, math_mode, x_dim, action_dim, episode_length, action_repeat, obs,
+                    steps, done, obs, steps, done, first_obs, actions, E, T, observation_out, reward_out,
+                    discount_out, next_observation_out, truncation_out, false, stream);
+}
+
+int mbpo_env_unroll(int system_kind, const void* sys_params_host, int math_mode, int x_dim, int action_dim,
+                    int episode_length, int action_repeat, const float* obs_in, const float* steps_in,
+                    const float* done_in, float* obs_out, float* steps_out, float* done_out,
+                    const float* first_obs, const float* actions, int E, int T, float* observation_out,
+                    float* reward_out, float* discount_out, float* next_observation_out, float* truncation_out,
+                    void* stream) {
+  return launch_env(system_kind, sys_params_host, math_mode, x_dim, action_dim, episode_length, action_repeat,
+                    obs_in, steps_in, done_in, obs_out, steps_out, done_out, first_obs, actions, E, T,
+                    observation_out, reward_out, discount_out, next_observation_out, truncation_out, true, stream);
 }
 
 // ---- policy in the env loop: actor_step / generate_unroll / get_experience ------------------------------

@@ -62,22 +62,26 @@ class VmappedSystemEnv:
         T, E, A = acts.shape
         X = self.system.x_dim
         dev = acts.device
-        obs = state.obs.clone()
-        steps = state.info["steps"].clone()
-        done = state.done.clone()
+        obs_in = state.obs.contiguous()
+        steps_in = state.info["steps"].contiguous()
+        done_in = state.done.contiguous()
         first = state.info["first_obs"].contiguous()
+        obs, steps, done = torch.empty_like(obs_in), torch.empty_like(steps_in), torch.empty_like(done_in)
         # observation[t] = next_observation[t-1]: both are views of one [T+1, E, X] buffer
         buf = torch.empty((T + 1, E, X), dtype=torch.float32, device=dev)
-        buf[0].copy_(obs)
+        buf[0].copy_(obs_in)
         o, n = buf[:T], buf[1:]
         r = torch.empty((T, E), dtype=torch.float32, device=dev)
         d = torch.empty((T, E), dtype=torch.float32, device=dev)
         tr = torch.empty((T, E), dtype=torch.float32, device=dev)
         params = self.system.pack_params(state.system_params)
+        if T == 0:
+            obs, steps, done = obs_in.clone(), steps_in.clone(), done_in.clone()
         with _lib.cuda_guard(acts):
-            _lib.check(_lib.lib.mbpo_env_rollout(
+            _lib.check(_lib.lib.mbpo_env_unroll(
                 self.system.system_kind, _lib.C.addressof(params), config.math_mode_id, X, A, self.episode_length,
-                self.action_repeat, _lib.ptr(obs), _lib.ptr(steps), _lib.ptr(done), _lib.ptr(first), _lib.ptr(acts),
+                self.action_repeat, _lib.ptr(obs_in), _lib.ptr(steps_in), _lib.ptr(done_in), _lib.ptr(obs),
+                _lib.ptr(steps), _lib.ptr(done), _lib.ptr(first), _lib.ptr(acts),
                 E, T, None, _lib.ptr(r), _lib.ptr(d), _lib.ptr(n), _lib.ptr(tr), _lib.stream_ptr(dev)))
         new_state = EnvState(obs=obs, reward=r[-1] if T else state.reward, done=done,
                              system_params=state.system_params,

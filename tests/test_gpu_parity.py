@@ -612,6 +612,54 @@ def test_env_rollout_abi_variants(mb, cuda_device):
     assert torch.equal(o2, o) and torch.equal(n2, n) and torch.equal(r2, r) and torch.equal(obs2, obs)
 
 
+@pytest.mark.parametrize("E,T,episode_length,action_repeat", [(1000, 61, 13, 1), (95, 50, 11, 3), (64, 5, 200, 1)])
+def test_env_unroll_ragged_episode_pieces(mb, cuda_device, math_mode, E, T, episode_length, action_repeat):
+    """mbpo_env_unroll rolls the pieces between AutoReset points concurrently.  Envs whose step
+    counters differ reset at different times inside one warp: the result must still equal the
+    sequential scan (mbpo_env_rollout) bit for bit, and the oracle's bookkeeping exactly."""
+    L = mb._lib
+    from mbpo_b200.envs import wrap, EnvState
+    from mbpo_b200.systems import PendulumSystem
+    sys_ = PendulumSystem()
+    sp = sys_.reset(device=cuda_device).system_params
+    env = wrap(sys_, sp, episode_length=episode_length, action_repeat=action_repeat)
+    rng = np.random.default_rng(71)
+    x0, first = _random_states(E, 72), _random_states(E, 73)
+    steps0 = (rng.integers(0, episode_length, E) // action_repeat * action_repeat).astype(np.float32)
+    done0 = (rng.uniform(size=E) < 0.2).astype(np.float32)
+    acts = rng.uniform(-1, 1, (T, E, 1)).astype(np.float32)
+    st = EnvState(obs=_dev(x0, cuda_device), reward=torch.zeros(E, device=cuda_device), done=_dev(done0, cuda_device),
+                  system_params=sp, info=dict(steps=_dev(steps0, cuda_device), truncation=torch.zeros(E, device=cuda_device),
+                                              first_obs=_dev(first, cuda_device)))
+    new, tr = env.unroll(st, _dev(acts, cuda_device))
+    assert torch.equal(st.obs, _dev(x0, cuda_device)) and torch.equal(st.info["steps"], _dev(steps0, cuda_device))
+    want = orc.env_rollout(x0, acts[..., 0], episode_length, action_repeat=action_repeat, steps0=steps0, done0=done0,
+                           first_obs=first)
+    assert np.array_equal(tr.discount.cpu().numpy(), want["discount"])
+    assert np.array_equal(tr.extras["state_extras"]["truncation"].cpu().numpy(), want["truncation"])
+    assert np.array_equal(new.info["steps"].cpu().numpy(), want["final_steps"])
+    assert np.array_equal(new.done.cpu().numpy(), want["final_done"])
+    # the sequential kernel through the in-place entry point
+    pp = sys_.pack_params(sp)
+    obs, steps, done = st.obs.clone(), st.info["steps"].clone(), st.done.clone()
+    n = torch.zeros((T, E, 3), device=cuda_device)
+    r, d, t_ = (torch.zeros((T, E), device=cuda_device) for _ in range(3))
+    L.check(L.lib.mbpo_env_rollout(0, L.C.addressof(pp), mb.config.math_mode_id, 3, 1, episode_length, action_repeat,
+                                   L.ptr(obs), L.ptr(steps), L.ptr(done), L.ptr(st.info["first_obs"]),
+                                   L.ptr(_dev(acts, cuda_device)), E, T, None, L.ptr(r), L.ptr(d), L.ptr(n), L.ptr(t_),
+                                   L.stream_ptr(cuda_device)))
+    assert torch.equal(n, tr.next_observation) and torch.equal(r, tr.reward) and torch.equal(d, tr.discount)
+    assert torch.equal(t_, tr.extras["state_extras"]["truncation"])
+    assert torch.equal(obs, new.obs) and torch.equal(steps, new.info["steps"]) and torch.equal(done, new.done)
+    # aliasing the outgoing state with the incoming one is refused when pieces run concurrently
+    if T > 1 and episode_length < T:
+        with pytest.raises(mb.MbpoError):
+            L.check(L.lib.mbpo_env_unroll(0, L.C.addressof(pp), 0, 3, 1, episode_length, action_repeat, L.ptr(obs),
+                                          L.ptr(steps), L.ptr(done), L.ptr(obs), L.ptr(steps), L.ptr(done),
+                                          L.ptr(st.info["first_obs"]), L.ptr(_dev(acts, cuda_device)), E, T, None,
+                                          L.ptr(r), L.ptr(d), L.ptr(n), L.ptr(t_), L.stream_ptr(cuda_device)))
+
+
 # ---------------------------------------------------------------------------------------------
 # policy in the env loop: actor_step / generate_unroll / get_experience (SURVEY 8f-2)
 # ---------------------------------------------------------------------------------------------
