@@ -73,9 +73,14 @@ __device__ __forceinline__ void warp_store3(float* tile, float* dst, int lane, i
 //
 // OBS: also write the separate observation buffer.  All of next_obs / reward / discount /
 // truncation are non-NULL (the C ABI falls back to the checked kernel otherwise).
-template <int MATH, bool OBS>
+//
+// FAST (host-checked: action_repeat == 1, |target_angle| <= 6, E % 4 == 0, 16-byte aligned
+// observation buffers, T*E*3 < 2^31): warps whose 32 envs are all live and share their piece
+// boundaries take a loop without per-lane masks, with 32-bit offsets and one 16-byte store per
+// lane for the [32,3] observation row; other warps (and FAST = false) take the general loop.
+template <int MATH, bool OBS, bool FAST>
 __global__ void __launch_bounds__(ENV_THREADS) env_rollout_pendulum_kernel(const __grid_constant__ EnvArgs a) {
-  __shared__ float tiles[ENV_THREADS / 32][96];
+  __shared__ __align__(16) float tiles[ENV_THREADS / 32][96];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int e = blockIdx.x * ENV_THREADS + threadIdx.x;
   const int warp_e0 = e - lane;
@@ -115,6 +120,66 @@ __global__ void __launch_bounds__(ENV_THREADS) env_rollout_pendulum_kernel(const
   // theta-carry: the angle lives in a register across steps; [cos, sin] are only outputs
   float th = (MATH == MBPO_MATH_REFERENCE) ? 0.0f : atan2_bounded(s, c);
   const float f_th = (MATH == MBPO_MATH_REFERENCE) ? 0.0f : atan2_bounded(f_s, f_c);
+  if (FAST) {
+    const bool uniform = __all_sync(0xffffffffu, live && t_beg == w_beg && t_end == w_end);
+    if (uniform) {
+      const unsigned Eu = static_cast<unsigned>(a.E);
+      unsigned off = static_cast<unsigned>(w_beg) * Eu + static_cast<unsigned>(e);            // [T,E] streams
+      unsigned off3 = (static_cast<unsigned>(w_beg) * Eu + static_cast<unsigned>(warp_e0)) * 3u + 4u * lane;
+      const bool row_lane = lane < 24;             // 24 lanes x 16 B = one [32,3] row
+      float* tile3 = tile + 3 * lane;
+      const float4* tile4 = reinterpret_cast<const float4*>(tile) + (row_lane ? lane : 0);
+      float u_buf[ENV_CHUNK];
+#pragma unroll
+      for (int k = 0; k < ENV_CHUNK; ++k) u_buf[k] = (w_beg + k < w_end) ? __ldg(a.actions + off + k * Eu) : 0.0f;
+      for (int t0 = w_beg; t0 < w_end; t0 += ENV_CHUNK) {
+        float u_cur[ENV_CHUNK];
+#pragma unroll
+        for (int k = 0; k < ENV_CHUNK; ++k) u_cur[k] = u_buf[k];
+#pragma unroll
+        for (int k = 0; k < ENV_CHUNK; ++k)
+          u_buf[k] = (t0 + ENV_CHUNK + k < w_end) ? __ldg(a.actions + off + (ENV_CHUNK + k) * Eu) : 0.0f;
+        const int kmax = (w_end - t0) < ENV_CHUNK ? (w_end - t0) : ENV_CHUNK;
+#pragma unroll
+        for (int k = 0; k < ENV_CHUNK; ++k) {
+          if (k < kmax) {
+            steps = (done != 0.0f) ? 0.0f : steps;               // training.py:120-124
+            if (OBS) {
+              tile3[0] = c; tile3[1] = s; tile3[2] = w;
+              __syncwarp();
+              const float4 v = *tile4;
+              __syncwarp();
+              if (row_lane) *reinterpret_cast<float4*>(a.observation_out + off3) = v;
+            }
+            float rew;
+            if (MATH == MBPO_MATH_REFERENCE) pendulum_step_ref<true>(pc, c, s, w, u_cur[k], rew);
+            else { pendulum_step_theta<true>(pc, th, w, u_cur[k], rew); sincos_bounded(th, s, c); }
+            rew = __fadd_rn(0.0f, rew);                          // the wrapper's reward sum starts at 0
+            steps = __fadd_rn(steps, 1.0f);
+            const bool over = steps >= ep_len;                   // training.py:98-107
+            done = over ? 1.0f : 0.0f;
+            if (over) { c = f_c; s = f_s; w = f_w; th = f_th; }  // training.py:136
+            tile3[0] = c; tile3[1] = s; tile3[2] = w;
+            __syncwarp();
+            const float4 v = *tile4;
+            __syncwarp();
+            if (row_lane) *reinterpret_cast<float4*>(a.next_observation_out + off3) = v;
+            a.reward_out[off] = rew;
+            a.discount_out[off] = 1.0f - done;
+            a.truncation_out[off] = done;                        // 1 - done_sys where the episode ends
+            off += Eu;
+            off3 += 3u * Eu;
+          }
+        }
+      }
+      if (t_end == a.T) {
+        a.obs[3 * e] = c; a.obs[3 * e + 1] = s; a.obs[3 * e + 2] = w;
+        a.steps[e] = steps;
+        a.done[e] = done;
+      }
+      return;
+    }
+  }
   // tile element j of a row belongs to env warp_e0 + j / 3
   const int own0 = lane / 3, own1 = (lane + 32) / 3, own2 = (lane + 64) / 3;
 

@@ -594,14 +594,22 @@ int launch_env(int system_kind, const void* sys_params_host, int math_mode, int 
   const dim3 blocks(static_cast<unsigned>((E + ENV_THREADS - 1) / ENV_THREADS),
                     a.segmented ? static_cast<unsigned>(pieces) : 1u);
   cudaStream_t st = as_stream(stream);
-  const int sel = (all_out ? (observation_out ? 2 : 1) : 0) * 2 + math_mode;
+  const auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  const bool fast = all_out && action_repeat == 1 && std::fabs(a.sys.target_angle) <= 6.0f && E % 4 == 0 &&
+                    aligned16(next_observation_out) && aligned16(observation_out) &&
+                    static_cast<long long>(T) * E * 3 < (1ll << 31);
+  const int sel = (all_out ? (observation_out ? 2 : 1) : 0) * 4 + math_mode * 2 + (fast ? 1 : 0);
   switch (sel) {
-    case 0: env_rollout_pendulum_checked_kernel<0><<<blocks, ENV_THREADS, 0, st>>>(a); break;
-    case 1: env_rollout_pendulum_checked_kernel<1><<<blocks, ENV_THREADS, 0, st>>>(a); break;
-    case 2: env_rollout_pendulum_kernel<0, false><<<blocks, ENV_THREADS, 0, st>>>(a); break;
-    case 3: env_rollout_pendulum_kernel<1, false><<<blocks, ENV_THREADS, 0, st>>>(a); break;
-    case 4: env_rollout_pendulum_kernel<0, true><<<blocks, ENV_THREADS, 0, st>>>(a); break;
-    default: env_rollout_pendulum_kernel<1, true><<<blocks, ENV_THREADS, 0, st>>>(a); break;
+    case 0: case 1: env_rollout_pendulum_checked_kernel<0><<<blocks, ENV_THREADS, 0, st>>>(a); break;
+    case 2: case 3: env_rollout_pendulum_checked_kernel<1><<<blocks, ENV_THREADS, 0, st>>>(a); break;
+    case 4: env_rollout_pendulum_kernel<0, false, false><<<blocks, ENV_THREADS, 0, st>>>(a); break;
+    case 5: env_rollout_pendulum_kernel<0, false, true><<<blocks, ENV_THREADS, 0, st>>>(a); break;
+    case 6: env_rollout_pendulum_kernel<1, false, false><<<blocks, ENV_THREADS, 0, st>>>(a); break;
+    case 7: env_rollout_pendulum_kernel<1, false, true><<<blocks, ENV_THREADS, 0, st>>>(a); break;
+    case 8: env_rollout_pendulum_kernel<0, true, false><<<blocks, ENV_THREADS, 0, st>>>(a); break;
+    case 9: env_rollout_pendulum_kernel<0, true, true><<<blocks, ENV_THREADS, 0, st>>>(a); break;
+    case 10: env_rollout_pendulum_kernel<1, true, false><<<blocks, ENV_THREADS, 0, st>>>(a); break;
+    default: env_rollout_pendulum_kernel<1, true, true><<<blocks, ENV_THREADS, 0, st>>>(a); break;
   }
   return check_launch("env_rollout_pendulum_kernel");
 }

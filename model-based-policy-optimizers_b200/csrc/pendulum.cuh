@@ -35,10 +35,13 @@ struct PendulumConsts {
 #define MBPO_TWO_PI_F 6.28318548f  /* float32(2*jnp.pi) */
 
 // ((d + pi) % (2*pi)) - pi with jnp's floored remainder (pendulum_reward.py:35).
+// SMALL: the caller guarantees |d + pi| < 4*pi (|theta| <= pi + max_speed*dt and a target angle
+// the host checked), which drops the fmod slow path from the instruction stream.
+template <bool SMALL = false>
 __device__ __forceinline__ float wrap_diff(float d) {
   const float x = d + MBPO_PI_F;
   float r;
-  if (fabsf(x) < 2.0f * MBPO_TWO_PI_F) {
+  if (SMALL || fabsf(x) < 2.0f * MBPO_TWO_PI_F) {
     // fmod is exact; for |x| < 4*pi it is x or x -/+ 2*pi (Sterbenz-exact subtraction)
     r = x;
     if (r >= MBPO_TWO_PI_F) r -= MBPO_TWO_PI_F;
@@ -50,33 +53,42 @@ __device__ __forceinline__ float wrap_diff(float d) {
   return r - MBPO_PI_F;
 }
 
+template <bool SMALL = false>
 __device__ __forceinline__ float reward_from(const PendulumConsts& p, float th, float thdot, float u) {
-  const float diff = wrap_diff(th - p.target_angle);
-  return -(p.angle_cost * (diff * diff) + 0.1f * (thdot * thdot)) - p.control_cost * (u * u);
+  // Every contraction is spelled out: a*b + c*d leaves the compiler a choice of which product to
+  // fuse, and it chooses differently in different loops -- the kernels must agree bit for bit.
+  const float diff = wrap_diff<SMALL>(th - p.target_angle);
+  const float t = fmaf(0.1f, __fmul_rn(thdot, thdot), __fmul_rn(p.angle_cost, __fmul_rn(diff, diff)));
+  return fmaf(-p.control_cost, __fmul_rn(u, u), -t);
+}
+
+// thdot + (3g/(2l) sin(th) + 3/(ml^2) u) dt, clipped (pendulum_dynamics.py:59-62)
+__device__ __forceinline__ float pendulum_next_thdot(const PendulumConsts& p, float sin_th, float w, float u) {
+  const float uu = __fmul_rn(fminf(fmaxf(u, -1.0f), 1.0f), p.max_torque);   // :59
+  const float thdd = fmaf(p.c_g, sin_th, __fmul_rn(p.c_u, uu));               // :60
+  return fminf(fmaxf(fmaf(thdd, p.dt, w), -p.max_speed), p.max_speed);        // :61-62 (=:41-42)
 }
 
 // One reference-literal step on the [cos, sin, thdot] state.
+template <bool SMALL = false>
 __device__ __forceinline__ void pendulum_step_ref(const PendulumConsts& p, float& c, float& s, float& w,
                                                   float u, float& reward) {
   const float th = atan2_bounded(s, c);                             // dynamics :35 / reward :32
-  reward = reward_from(p, th, w, u);                                // reward uses x, raw u
-  const float uu = fminf(fmaxf(u, -1.0f), 1.0f) * p.max_torque;     // :59
-  const float thdd = p.c_g * sin_bounded(th) + p.c_u * uu;          // :60
-  const float nw = fminf(fmaxf(w + thdd * p.dt, -p.max_speed), p.max_speed);   // :61-62 (=:41-42)
-  const float nth = th + nw * p.dt;                                 // :40
+  reward = reward_from<SMALL>(p, th, w, u);                         // reward uses x, raw u
+  const float nw = pendulum_next_thdot(p, sin_bounded(th), w, u);
+  const float nth = fmaf(nw, p.dt, th);                             // :40
   sincos_bounded(nth, s, c);                                        // :43
   w = nw;
 }
 
 // Theta-carry variant: the state is (theta, thdot) with theta kept in (-pi, pi], which is
 // what atan2(sin(newth), cos(newth)) returns up to rounding.
+template <bool SMALL = false>
 __device__ __forceinline__ void pendulum_step_theta(const PendulumConsts& p, float& th, float& w, float u,
                                                     float& reward) {
-  reward = reward_from(p, th, w, u);
-  const float uu = fminf(fmaxf(u, -1.0f), 1.0f) * p.max_torque;
-  const float thdd = p.c_g * sin_bounded(th) + p.c_u * uu;
-  const float nw = fminf(fmaxf(w + thdd * p.dt, -p.max_speed), p.max_speed);
-  float nth = th + nw * p.dt;
+  reward = reward_from<SMALL>(p, th, w, u);
+  const float nw = pendulum_next_thdot(p, sin_bounded(th), w, u);
+  float nth = fmaf(nw, p.dt, th);
   if (nth > MBPO_PI_F) nth -= MBPO_TWO_PI_F;
   if (nth < -MBPO_PI_F) nth += MBPO_TWO_PI_F;
   th = nth;
