@@ -79,7 +79,7 @@ __device__ __forceinline__ void warp_store3(float* tile, float* dst, int lane, i
 // boundaries take a loop without per-lane masks, with 32-bit offsets and one 16-byte store per
 // lane for the [32,3] observation row; other warps (and FAST = false) take the general loop.
 template <int MATH, bool OBS, bool FAST>
-__global__ void __launch_bounds__(ENV_THREADS) env_rollout_pendulum_kernel(const __grid_constant__ EnvArgs a) {
+__global__ void __launch_bounds__(ENV_THREADS, 18) env_rollout_pendulum_kernel(const __grid_constant__ EnvArgs a) {
   __shared__ __align__(16) float tiles[ENV_THREADS / 32][96];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int e = blockIdx.x * ENV_THREADS + threadIdx.x;
