@@ -240,7 +240,17 @@ typedef struct MbpoPolicyParams {
   const float* w[MBPO_POLICY_MAX_LAYERS];
   const float* b[MBPO_POLICY_MAX_LAYERS];
   float min_std;
+  /* head: MBPO_HEAD_NORMAL_TANH (above) or MBPO_HEAD_BPTT_ACTOR, the actor of bptt_optimizer.py:123-142,306-326:
+   * mu, sig = split(MLP((obs - obs_mean) / obs_std), 2); sig = clip(softplus(sig + sig_bias), sig_min, sig_max)
+   * (sig_bias = inv_softplus(init_stddev)); action = clip(tanh(mu + normal(key, (A,)) * sig), +-action_clip),
+   * or clip(tanh(mu)) when deterministic.  shared_noise = 1 draws normal(key, (A,)) once for every env (the key
+   * is not vmapped in BPTT's vmap(actor_loss, in_axes=(0, None, None)), bptt_optimizer.py:366-368).
+   * normalize = 0 feeds obs to the network as is. */
+  int32_t head, shared_noise, normalize;
+  float sig_bias, sig_min, sig_max, action_clip;
+  float obs_mean[4], obs_std[4];
 } MbpoPolicyParams;
+enum { MBPO_HEAD_NORMAL_TANH = 0, MBPO_HEAD_BPTT_ACTOR = 1 };
 enum {
   MBPO_KEYS_SAC = 0,     /* sac/sac.py:288-292      k, k_t = split(k); policy key = k_t          */
   MBPO_KEYS_UNROLL = 1,  /* sac/acting.py:68-73     current, next = split(current); policy key = current, carry = next */
@@ -256,6 +266,34 @@ int mbpo_actor_rollout(int system_kind, const void* sys_params_host, int math_mo
                        float* steps, float* done, const float* first_obs, int E, int T, float* action_out,
                        float* reward_out, float* discount_out, float* next_observation_out,
                        float* truncation_out, uint32_t* key_out, void* stream);
+
+/* ---- reverse pass through System.step rollouts; lambda returns (BPTT) ----------------------- */
+/* The cotangent pass of jax.value_and_grad through rollout_policy(..., stop_grads=True)
+ * (mbpo/utils/optimizer_utils.py:62-116; bptt_optimizer.py:327-376): the policy sees
+ * stop_gradient(obs), so cotangents reach its parameters through the actions only.  For E
+ * trajectories of T steps, given the forward trajectory (observation x_t, action a_t) and the
+ * cotangents of the Transition fields, writes g_action_out[t] = total cotangent reaching a_t and
+ * g_x0_out [E,X] (or NULL).  g_reward / g_next_obs / g_obs / g_action_in may be NULL (zero).
+ * observation[t+1] and next_observation[t] are the same value; g_obs[0] flows to g_x0_out.
+ * Element (t, e) of a per-step scalar array is base[t*stride_t + e*stride_e]; of an [.,.,X] array
+ * base[t*stride_xt + e*stride_xe + i]: the reference's vmapped [B,H,...] layout and the rollout
+ * kernels' time-major [T,E,...] layout both work without copies. */
+int mbpo_rollout_adjoint(int system_kind, const void* sys_params_host, int x_dim, int action_dim, int E,
+                         int T, long long stride_t, long long stride_e, long long stride_xt,
+                         long long stride_xe, const float* observation, const float* action,
+                         const float* g_reward, const float* g_next_obs, const float* g_obs,
+                         const float* g_action_in, float* g_action_out, float* g_x0_out, void* stream);
+
+/* lambda_return (mbpo/utils/optimizer_utils.py:119-131): inputs = reward + discount * next_values *
+ * (1 - lambda); returns[t] = inputs[t] + discount * lambda * returns[t+1], returns[T] = next_values[-1].
+ * E independent sequences of T steps, element (t, e) at base[t*stride_t + e*stride_e]. */
+int mbpo_lambda_return(const float* reward, const float* next_values, int E, int T, long long stride_t,
+                       long long stride_e, double discount, double lambda_, float* returns_out,
+                       void* stream);
+/* Its transpose (what jax.grad computes through it): cotangents of reward and next_values. */
+int mbpo_lambda_return_vjp(const float* g_returns, int E, int T, long long stride_t, long long stride_e,
+                           double discount, double lambda_, float* g_reward_out,
+                           float* g_next_values_out, void* stream);
 
 /* ---- stage 4: learned MLP-ensemble dynamics, batched forward on tcgen05 ------------------ */
 /* inp [R, x_dim+u_dim], member [R] (int32 ensemble member per row) -> delta [R, x_dim]. */

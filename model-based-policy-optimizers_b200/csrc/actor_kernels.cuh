@@ -39,6 +39,10 @@ struct ActorArgs {
   int E, T, episode_length, action_repeat;
   int num_hidden, deterministic, key_convention;  // 0: SAC get_experience, 1: generate_unroll, 2: use key as is
   float min_std;
+  // policy head (MBPO_HEAD_*): NormalTanh of SAC/PPO, or the BPTT actor (bptt_optimizer.py:123-142,306-326)
+  int head, shared_noise, normalize;
+  float sig_bias, sig_min, sig_max, action_clip;
+  float obs_mean[3], obs_std[3];
   const float* w[ACT_MAX_HIDDEN + 1];  // [3,64], [64,64] x (num_hidden-1), [64,2]   (flax Dense kernels, [in, out])
   const float* b[ACT_MAX_HIDDEN + 1];
   const uint32_t* key_in;       // [2] device
@@ -152,6 +156,15 @@ __global__ void __launch_bounds__(ACT_MAX_THREADS, 1) actor_rollout_pendulum_ker
     }
     // ---- policy network, float32; every activation is a pair (env slot 0, env slot 1) -------------------
     f32x2_t h[ACT_W];
+    float xin[2][3];   // the network input: obs, or (obs - mean) / std (bptt_optimizer.py:70-72,310)
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      xin[q][0] = env[q].c; xin[q][1] = env[q].s; xin[q][2] = env[q].w;
+      if (a.normalize) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) xin[q][i] = __fdiv_rn(__fsub_rn(xin[q][i], a.obs_mean[i]), a.obs_std[i]);
+      }
+    }
     {
       const float4* w0 = reinterpret_cast<const float4*>(act_sm + lay.w[0]);   // [3][64]
       const float4* b0 = reinterpret_cast<const float4*>(act_sm + lay.b[0]);
@@ -165,7 +178,7 @@ __global__ void __launch_bounds__(ACT_MAX_THREADS, 1) actor_rollout_pendulum_ker
           float v[2];
 #pragma unroll
           for (int q = 0; q < 2; ++q)
-            v[q] = swish_exact(fmaf(env[q].w, wr2[i], fmaf(env[q].s, wr1[i], env[q].c * wr0[i])) + wb[i]);
+            v[q] = swish_exact(fmaf(xin[q][2], wr2[i], fmaf(xin[q][1], wr1[i], xin[q][0] * wr0[i])) + wb[i]);
           h[4 * j4 + i] = pack2(v[0], v[1]);
         }
       }
@@ -219,11 +232,22 @@ __global__ void __launch_bounds__(ACT_MAX_THREADS, 1) actor_rollout_pendulum_ker
       if (!half_live[q]) continue;   // warp-uniform
       ActorEnv& v = env[q];
       float u;
-      if (a.deterministic) {
+      const uint32_t n_draw = a.shared_noise ? 1u : static_cast<uint32_t>(a.E);     // normal(key, (A,)) or (E, A)
+      const uint32_t i_draw = a.shared_noise ? 0u : static_cast<uint32_t>(ee[q]);
+      if (a.head == MBPO_HEAD_BPTT_ACTOR) {
+        // Actor.__call__ :137-142: sig = clip(softplus(sig + inv_softplus(init_stddev)), sig_min, sig_max);
+        // act :306-326: squash(mu) or squash(mu + normal(sample_key, mu.shape) * sig), squash = clip(tanh, +-0.999)
+        float pre = loc[q] + b_loc;
+        if (!a.deterministic) {
+          const float eps = bits_to_normal(random_bits_at<PRNG>(k_actor, n_draw, i_draw));
+          const float sig = fminf(fmaxf(softplus_exact(__fadd_rn(raw_scale[q] + b_scale, a.sig_bias)), a.sig_min), a.sig_max);
+          pre = __fadd_rn(pre, __fmul_rn(eps, sig));
+        }
+        u = fminf(fmaxf(tanhf(pre), -a.action_clip), a.action_clip);
+      } else if (a.deterministic) {
         u = tanhf(loc[q] + b_loc);                                       // mode(): tanh(loc)
       } else {
-        const float eps = bits_to_normal(random_bits_at<PRNG>(k_actor, static_cast<uint32_t>(a.E),
-                                                               static_cast<uint32_t>(ee[q])));
+        const float eps = bits_to_normal(random_bits_at<PRNG>(k_actor, n_draw, i_draw));
         const float scale = softplus_exact(raw_scale[q] + b_scale) + a.min_std;
         u = tanhf(__fadd_rn(__fmul_rn(scale, eps), loc[q] + b_loc));      // distrax Normal.sample: scale * rnd + loc
       }

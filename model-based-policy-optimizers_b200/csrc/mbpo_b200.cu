@@ -15,6 +15,7 @@
 #include "mlp_kernels.cuh"
 #include "mlp_tc_kernels.cuh"
 #include "actor_kernels.cuh"
+#include "adjoint_kernels.cuh"
 #include "ensemble_pp_kernels.cuh"
 #include "plan_dispatch.h"
 #include "staged_kernels.cuh"
@@ -699,6 +700,8 @@ int mbpo_actor_rollout(int system_kind, const void* sys_params_host, int math_mo
                 policy_host->num_hidden, policy_host->hidden);
   for (int l = 0; l <= policy_host->num_hidden; ++l)
     MBPO_REQUIRE(policy_host->w[l] && policy_host->b[l], "actor_rollout: null policy weights (layer %d)", l);
+  MBPO_REQUIRE(policy_host->head == MBPO_HEAD_NORMAL_TANH || policy_host->head == MBPO_HEAD_BPTT_ACTOR,
+               "actor_rollout: bad policy head %d", policy_host->head);
   if (E == 0 || T == 0) {
     if (key_out && key_out != key_in) {
       const cudaError_t ce = cudaMemcpyAsync(key_out, key_in, 2 * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
@@ -712,6 +715,10 @@ int mbpo_actor_rollout(int system_kind, const void* sys_params_host, int math_mo
   a.E = E; a.T = T; a.episode_length = episode_length; a.action_repeat = action_repeat;
   a.num_hidden = policy_host->num_hidden; a.deterministic = deterministic; a.key_convention = key_convention;
   a.min_std = policy_host->min_std;
+  a.head = policy_host->head; a.shared_noise = policy_host->shared_noise; a.normalize = policy_host->normalize;
+  a.sig_bias = policy_host->sig_bias; a.sig_min = policy_host->sig_min; a.sig_max = policy_host->sig_max;
+  a.action_clip = policy_host->action_clip;
+  for (int i = 0; i < 3; ++i) { a.obs_mean[i] = policy_host->obs_mean[i]; a.obs_std[i] = policy_host->obs_std[i]; }
   for (int l = 0; l <= mbpo::ACT_MAX_HIDDEN; ++l) {
     a.w[l] = l <= a.num_hidden ? policy_host->w[l] : nullptr;
     a.b[l] = l <= a.num_hidden ? policy_host->b[l] : nullptr;
@@ -727,6 +734,66 @@ int mbpo_actor_rollout(int system_kind, const void* sys_params_host, int math_mo
     case 2: return launch_actor<1, 0>(a, st);
     default: return launch_actor<1, 1>(a, st);
   }
+}
+
+// ---- reverse pass through System.step rollouts, lambda returns ---------------------------
+int mbpo_rollout_adjoint(int system_kind, const void* sys_params_host, int x_dim, int action_dim, int E, int T,
+                         long long stride_t, long long stride_e, long long stride_xt, long long stride_xe,
+                         const float* observation, const float* action, const float* g_reward,
+                         const float* g_next_obs, const float* g_obs, const float* g_action_in,
+                         float* g_action_out, float* g_x0_out, void* stream) {
+  if (system_kind != MBPO_SYSTEM_PENDULUM)
+    return fail(MBPO_EUNSUPPORTED, "rollout_adjoint: only MBPO_SYSTEM_PENDULUM has a hand-written adjoint");
+  MBPO_REQUIRE(sys_params_host && observation && action && g_action_out, "rollout_adjoint: null pointer");
+  MBPO_REQUIRE(action_dim == 1 && x_dim == 3, "rollout_adjoint: pendulum needs action_dim == 1, x_dim == 3");
+  MBPO_REQUIRE(E >= 0 && T >= 0, "rollout_adjoint: negative size");
+  if (E == 0) return MBPO_OK;
+  mbpo::AdjointArgs a;
+  a.sys = *static_cast<const MbpoPendulumParams*>(sys_params_host);
+  a.E = E; a.T = T; a.st_t = stride_t; a.st_e = stride_e; a.sx_t = stride_xt; a.sx_e = stride_xe;
+  a.observation = observation; a.action = action; a.g_reward = g_reward; a.g_next_obs = g_next_obs;
+  a.g_obs = g_obs; a.g_action_in = g_action_in; a.g_action_out = g_action_out; a.g_x0_out = g_x0_out;
+  mbpo::rollout_adjoint_pendulum_kernel<<<(E + 127) / 128, 128, 0, as_stream(stream)>>>(a);
+  return check_launch("rollout_adjoint_pendulum_kernel");
+}
+
+extern "C++" {
+namespace {
+mbpo::LambdaArgs lambda_args(int E, int T, long long stride_t, long long stride_e, double discount, double lambda_) {
+  mbpo::LambdaArgs a;
+  a.E = E; a.T = T; a.st_t = stride_t; a.st_e = stride_e;
+  // python floats are weakly typed: `discount * lambda_` and `1 - lambda_` are evaluated in double and
+  // rounded once when they meet the float32 arrays (optimizer_utils.py:127-130)
+  a.discount = static_cast<float>(discount);
+  a.lambda_ = static_cast<float>(lambda_);
+  a.one_minus_lambda = static_cast<float>(1.0 - lambda_);
+  a.discount_lambda = static_cast<float>(discount * lambda_);
+  return a;
+}
+}  // namespace
+}  // extern "C++"
+
+int mbpo_lambda_return(const float* reward, const float* next_values, int E, int T, long long stride_t,
+                       long long stride_e, double discount, double lambda_, float* returns_out, void* stream) {
+  MBPO_REQUIRE(reward && next_values && returns_out, "lambda_return: null pointer");
+  MBPO_REQUIRE(E >= 0 && T >= 0, "lambda_return: negative size");
+  if (E == 0 || T == 0) return MBPO_OK;
+  mbpo::LambdaArgs a = lambda_args(E, T, stride_t, stride_e, discount, lambda_);
+  a.reward = reward; a.next_values = next_values; a.out = returns_out; a.out2 = nullptr;
+  mbpo::lambda_return_kernel<<<(E + 127) / 128, 128, 0, as_stream(stream)>>>(a);
+  return check_launch("lambda_return_kernel");
+}
+
+int mbpo_lambda_return_vjp(const float* g_returns, int E, int T, long long stride_t, long long stride_e,
+                           double discount, double lambda_, float* g_reward_out, float* g_next_values_out,
+                           void* stream) {
+  MBPO_REQUIRE(g_returns && g_reward_out && g_next_values_out, "lambda_return_vjp: null pointer");
+  MBPO_REQUIRE(E >= 0 && T >= 0, "lambda_return_vjp: negative size");
+  if (E == 0 || T == 0) return MBPO_OK;
+  mbpo::LambdaArgs a = lambda_args(E, T, stride_t, stride_e, discount, lambda_);
+  a.reward = g_returns; a.next_values = nullptr; a.out = g_reward_out; a.out2 = g_next_values_out;
+  mbpo::lambda_return_transpose_kernel<<<(E + 127) / 128, 128, 0, as_stream(stream)>>>(a);
+  return check_launch("lambda_return_transpose_kernel");
 }
 
 // ---- stage 4 ---------------------------------------------------------------------------------------

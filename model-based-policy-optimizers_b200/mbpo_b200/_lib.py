@@ -63,10 +63,14 @@ class IcemCfgC(C.Structure):
 class PolicyParamsC(C.Structure):
     """MbpoPolicyParams."""
     _fields_ = [("num_hidden", C.c_int32), ("hidden", C.c_int32), ("obs_dim", C.c_int32), ("action_dim", C.c_int32),
-                ("w", C.c_void_p * 5), ("b", C.c_void_p * 5), ("min_std", C.c_float)]
+                ("w", C.c_void_p * 5), ("b", C.c_void_p * 5), ("min_std", C.c_float),
+                ("head", C.c_int32), ("shared_noise", C.c_int32), ("normalize", C.c_int32),
+                ("sig_bias", C.c_float), ("sig_min", C.c_float), ("sig_max", C.c_float), ("action_clip", C.c_float),
+                ("obs_mean", C.c_float * 4), ("obs_std", C.c_float * 4)]
 
 
 KEYS_SAC, KEYS_UNROLL, KEYS_AS_IS = 0, 1, 2
+HEAD_NORMAL_TANH, HEAD_BPTT_ACTOR = 0, 1
 
 
 class IcemTraceC(C.Structure):
@@ -74,7 +78,7 @@ class IcemTraceC(C.Structure):
 
 
 # name -> (restype, argtypes); every symbol include/mbpo_b200.h declares
-_P, _I, _F, _SZ = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+_P, _I, _F, _SZ, _LL = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_longlong
 SIGNATURES = {
     "mbpo_abi_version": (_I, []),
     "mbpo_last_error": (C.c_char_p, []),
@@ -100,6 +104,9 @@ SIGNATURES = {
     "mbpo_env_unroll": (_I, [_I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "mbpo_actor_rollout": (_I, [_I, _P, _I, _I, C.POINTER(PolicyParamsC), _I, _I, _P, _I, _I, _P, _P, _P, _P, _I, _I,
                                 _P, _P, _P, _P, _P, _P, _P]),
+    "mbpo_rollout_adjoint": (_I, [_I, _P, _I, _I, _I, _I, _LL, _LL, _LL, _LL, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "mbpo_lambda_return": (_I, [_P, _P, _I, _I, _LL, _LL, C.c_double, C.c_double, _P, _P]),
+    "mbpo_lambda_return_vjp": (_I, [_P, _I, _I, _LL, _LL, C.c_double, C.c_double, _P, _P, _P]),
     "mbpo_mlp_dynamics_forward": (_I, [C.POINTER(MlpEnsembleParamsC), _P, _P, _I, _P, _P]),
     "mbpo_ensemble_rollout": (_I, [C.POINTER(MlpEnsembleParamsC), _I, _P, _P, _I, _I, _I, _P, _P]),
 }

@@ -48,6 +48,7 @@ class Policy:
             s.w[i] = _lib.ptr(wi)
             s.b[i] = _lib.ptr(bi)
         s.min_std = self.min_std
+        s.head = _lib.HEAD_NORMAL_TANH
         self.struct = s
 
     def __call__(self, observations: torch.Tensor, key_sample: torch.Tensor):
@@ -58,6 +59,32 @@ class Policy:
         env = VmappedSystemEnv(system, system.reset(device=observations.device).system_params, episode_length=1 << 30)
         _, tr = actor_step(env, env.reset(observations), self, key_sample)
         return tr.action, {}
+
+
+class BpttActorPolicy(Policy):
+    """BPTT's actor as a policy for ``rollout_policy`` (bptt_optimizer.py:123-142 ``Actor``; :306-326 ``act``;
+    :246 ``train_policy = lambda obs, opt_state: self.act(obs, opt_state, evaluate=False)``):
+    mu, sig = split(MLP(normalize(obs)), 2); sig = clip(softplus(sig + inv_softplus(init_stddev)), sig_min, sig_max);
+    action = clip(tanh(mu + normal(sample_key, mu.shape) * sig), +-0.999) with sample_key, key = split(key, 2), or
+    clip(tanh(mu)) when evaluate.  obs_mean / obs_std are the state normaliser's (:70-72).  One key serves every
+    trajectory of a batch: the reference vmaps actor_loss over initial states only (:366-368)."""
+
+    def __init__(self, params: PolicyParams, init_stddev: float = 1.0, sig_min: float = 1e-6, sig_max: float = 1e2,
+                 obs_mean: Sequence[float] = None, obs_std: Sequence[float] = None, evaluate: bool = False):
+        super().__init__(params, deterministic=evaluate)
+        import numpy as np
+        s = self.struct
+        s.head = _lib.HEAD_BPTT_ACTOR
+        s.shared_noise = 1
+        x = np.float32(init_stddev)                                      # inv_softplus on a weak-typed python float
+        s.sig_bias = float(np.log(np.exp(x) - np.float32(1.0))) if init_stddev < 20.0 else float(x)
+        s.sig_min, s.sig_max, s.action_clip = float(sig_min), float(sig_max), 0.999
+        s.normalize = int(obs_mean is not None)
+        if obs_mean is not None:
+            mean = [float(v) for v in (obs_mean.tolist() if hasattr(obs_mean, "tolist") else obs_mean)]
+            std = [float(v) for v in (obs_std.tolist() if hasattr(obs_std, "tolist") else obs_std)]
+            for i in range(len(mean)):
+                s.obs_mean[i], s.obs_std[i] = mean[i], std[i]
 
 
 def make_inference_fn():

@@ -696,3 +696,164 @@ def actor_rollout(params: PolicyParams, x0: np.ndarray, key, num_steps: int, epi
         obs = one["next_observation"][0]
         steps, done = one["final_steps"], one["final_done"]
     return out, key
+
+
+# ----------------------------------------------------------------------------------
+# rollout_policy + its cotangent pass, lambda_return (BPTT)
+#   mbpo/utils/optimizer_utils.py:62-131; bptt_optimizer.py:123-142 (Actor), :306-326 (act),
+#   :327-352 (actor_loss), :361-376 (value_and_grad through the rollout)
+# ----------------------------------------------------------------------------------
+@dataclass
+class BpttActorParams:
+    """The BPTT actor: MLP params (PolicyParams layout), Actor's init_stddev / sig_min / sig_max
+    (bptt_optimizer.py:127-129) and the state normaliser's mean / std (:70-72)."""
+    mlp: PolicyParams
+    init_stddev: float = 1.0
+    sig_min: float = 1e-6
+    sig_max: float = 1e2
+    obs_mean: Optional[np.ndarray] = None
+    obs_std: Optional[np.ndarray] = None
+
+
+def inv_softplus(x: float) -> np.float32:
+    """bptt_optimizer.py:107-108: where(x < 20, log(exp(x) - 1), x) on a weak-typed python float."""
+    x32 = F32(x)
+    return F32(np.log(np.exp(x32) - F32(1.0))) if x < 20.0 else x32
+
+
+def bptt_actor(params: BpttActorParams, obs: np.ndarray):
+    """Actor.__call__ on normalised observations: (mu, sig) each [E, A]."""
+    x = np.asarray(obs, dtype=F32)
+    if params.obs_mean is not None:
+        x = ((x - np.asarray(params.obs_mean, F32)).astype(F32) / np.asarray(params.obs_std, F32)).astype(F32)
+    out = policy_logits(params.mlp, x)
+    a_dim = out.shape[-1] // 2
+    mu, sig = out[..., :a_dim], out[..., a_dim:]
+    sig = softplus((sig + inv_softplus(params.init_stddev)).astype(F32))
+    sig = np.clip(sig, F32(params.sig_min), F32(params.sig_max)).astype(F32)
+    return mu.astype(F32), sig
+
+
+def bptt_act(params: BpttActorParams, obs: np.ndarray, key, evaluate: bool, partitionable: bool = False):
+    """BPTT.act (:306-326) for a batch of observations sharing one key (the key is not vmapped at :366-368):
+    returns (actions [E, A], new key)."""
+    mu, sig = bptt_actor(params, obs)
+    squash = lambda v: np.clip(np.tanh(v).astype(F32), F32(-0.999), F32(0.999)).astype(F32)
+    if evaluate:
+        return squash(mu), np.asarray(key, dtype=U32)
+    ks = jr.split(key, 2, partitionable)
+    sample_key, new_key = ks[0], ks[1]
+    eps = jr.normal(sample_key, mu.shape[-1], partitionable)          # normal(sample_key, mu.shape), mu [A] per trajectory
+    return squash((mu + (eps[None, :] * sig).astype(F32)).astype(F32)), new_key
+
+
+def rollout_policy(params: BpttActorParams, x0: np.ndarray, key, horizon: int, evaluate: bool = False,
+                   p: PendulumParams = PendulumParams(), partitionable: bool = False,
+                   teacher_obs: Optional[np.ndarray] = None):
+    """vmap(rollout_policy, in_axes=(init_state: 0, policy_state: None)) (optimizer_utils.py:62-116) with BPTT's
+    train_policy: per step acs, new_state = policy(obs, state); system.step.  x0 [B, 3] -> dict of [B, H, ...]
+    arrays (observation, action, reward, next_observation, discount) and the carried key."""
+    b = x0.shape[0]
+    obs = np.asarray(x0, dtype=F32).copy()
+    out = dict(observation=np.empty((b, horizon, 3), F32), action=np.empty((b, horizon, 1), F32),
+               reward=np.empty((b, horizon), F32), next_observation=np.empty((b, horizon, 3), F32),
+               discount=np.ones((b, horizon), F32))
+    key = np.asarray(key, dtype=U32)
+    for t in range(horizon):
+        if teacher_obs is not None:
+            obs = np.asarray(teacher_obs[:, t], dtype=F32)
+        act, key = bptt_act(params, obs, key, evaluate, partitionable)
+        nxt, r = pendulum_step(obs, act[:, 0], p)
+        out["observation"][:, t] = obs
+        out["action"][:, t] = act
+        out["reward"][:, t] = r
+        out["next_observation"][:, t] = nxt
+        obs = nxt
+    return out, key
+
+
+def _clip_grad(x, lo, hi):
+    """d clip(x, lo, hi) / dx for jnp.clip = minimum(maximum(x, lo), hi); lax.max / lax.min give 0.5 at a tie."""
+    a = np.where(x > lo, 1.0, np.where(x == lo, 0.5, 0.0))
+    m = np.maximum(x, lo)
+    b = np.where(m < hi, 1.0, np.where(m == hi, 0.5, 0.0))
+    return a * b
+
+
+def pendulum_step_vjp(x, u, g_next, g_reward, p: PendulumParams = PendulumParams(), dtype=F32):
+    """Cotangents of one PendulumSystem.step: x [n,3], u [n], g_next [n,3], g_reward [n] -> (g_x [n,3], g_u [n]).
+    Derived by hand from pendulum_dynamics.py:29-63 and pendulum_reward.py:27-42; checked against central
+    differences of ``pendulum_step`` in float64 (tests/test_oracle_icem.py)."""
+    x = np.asarray(x, dtype=dtype); u = np.asarray(u, dtype=dtype)
+    g_next = np.asarray(g_next, dtype=dtype); g_reward = np.asarray(g_reward, dtype=dtype)
+    c, s, w = x[:, 0], x[:, 1], x[:, 2]
+    th = np.arctan2(s, c)
+    c_g = dtype(3.0) * dtype(p.g) / (dtype(2.0) * dtype(p.l))
+    c_u = dtype(3.0) / (dtype(p.m) * dtype(p.l) ** 2)
+    uu = np.clip(u, dtype(-1), dtype(1)) * dtype(p.max_torque)
+    thdd = c_g * np.sin(th) + c_u * uu
+    v = w + thdd * dtype(p.dt)
+    nw = np.clip(v, dtype(-p.max_speed), dtype(p.max_speed))
+    nth = th + nw * dtype(p.dt)
+    g_nth = np.cos(nth) * g_next[:, 1] - np.sin(nth) * g_next[:, 0]
+    g_nw = g_next[:, 2] + dtype(p.dt) * g_nth
+    g_v = g_nw * _clip_grad(v, dtype(-p.max_speed), dtype(p.max_speed)).astype(dtype)
+    g_thdd = dtype(p.dt) * g_v
+    two_pi = dtype(2 * np.pi)
+    diff = np.mod(th - dtype(p.target_angle) + dtype(np.pi), two_pi) - dtype(np.pi)
+    g_th = g_nth + g_thdd * c_g * np.cos(th) - g_reward * dtype(2.0) * dtype(p.angle_cost) * diff
+    g_w = g_v - g_reward * dtype(0.2) * w
+    g_u = (g_thdd * c_u * dtype(p.max_torque) * _clip_grad(u, dtype(-1), dtype(1)).astype(dtype)
+           - g_reward * dtype(2.0) * dtype(p.control_cost) * u)
+    r2 = c * c + s * s
+    inv = np.where(r2 > 0, dtype(1) / np.where(r2 > 0, r2, dtype(1)), dtype(0))
+    g_x = np.stack([-g_th * s * inv, g_th * c * inv, g_w], axis=-1)
+    return g_x.astype(dtype), g_u.astype(dtype)
+
+
+def rollout_policy_vjp(observation, action, g_reward=None, g_next_obs=None, g_obs=None, g_action=None,
+                       p: PendulumParams = PendulumParams(), dtype=F32):
+    """Cotangent pass of jax.grad through rollout_policy(..., stop_grads=True): observation [B,H,3], action
+    [B,H,1] and the cotangents of the Transition fields -> (g_action_total [B,H,1], g_x0 [B,3]).
+    g_action_total[t] is what reaches a_t = policy(stop_gradient(obs_t)); the parameter gradient is
+    sum_t (da_t / dtheta)^T g_action_total[t]."""
+    b, h = observation.shape[:2]
+    z1, z3 = np.zeros((b, h), dtype), np.zeros((b, h, 3), dtype)
+    g_reward = z1 if g_reward is None else np.asarray(g_reward, dtype)
+    g_next_obs = z3 if g_next_obs is None else np.asarray(g_next_obs, dtype)
+    g_obs = z3 if g_obs is None else np.asarray(g_obs, dtype)
+    g_action = np.zeros((b, h, 1), dtype) if g_action is None else np.asarray(g_action, dtype)
+    lam = np.zeros((b, 3), dtype)
+    out = np.empty((b, h, 1), dtype)
+    for t in range(h - 1, -1, -1):
+        g_next = lam + g_next_obs[:, t] + (g_obs[:, t + 1] if t + 1 < h else 0)
+        lam, g_u = pendulum_step_vjp(observation[:, t], action[:, t, 0], g_next, g_reward[:, t], p, dtype)
+        out[:, t, 0] = g_u + g_action[:, t, 0]
+    return out, (lam + (g_obs[:, 0] if h > 0 else 0)).astype(dtype)
+
+
+def lambda_return(reward, next_values, discount: float, lambda_: float, dtype=F32):
+    """optimizer_utils.py:119-131 along the last axis ([..., H]); python floats are weakly typed."""
+    reward = np.asarray(reward, dtype); next_values = np.asarray(next_values, dtype)
+    inputs = (reward + ((dtype(discount) * next_values).astype(dtype) * dtype(1 - lambda_)).astype(dtype)).astype(dtype)
+    dl = dtype(discount * lambda_)
+    agg = next_values[..., -1]
+    out = np.empty_like(inputs)
+    for t in range(inputs.shape[-1] - 1, -1, -1):
+        agg = (inputs[..., t] + (dl * agg).astype(dtype)).astype(dtype)
+        out[..., t] = agg
+    return out
+
+
+def lambda_return_vjp(g_returns, discount: float, lambda_: float, dtype=F32):
+    """Transpose of lambda_return: (g_reward, g_next_values), each [..., H]."""
+    g = np.asarray(g_returns, dtype)
+    dl, dn = dtype(discount * lambda_), dtype(discount) * dtype(1 - lambda_)
+    g_inp = np.empty_like(g)
+    acc = np.zeros(g.shape[:-1], dtype)
+    for t in range(g.shape[-1]):
+        acc = (g[..., t] + dl * acc).astype(dtype)
+        g_inp[..., t] = acc
+    g_nv = (dn * g_inp).astype(dtype)
+    g_nv[..., -1] += dl * g_inp[..., -1]
+    return g_inp, g_nv

@@ -863,8 +863,11 @@ def test_icem_plan_with_ensemble_system(mb, cuda_device):
 def test_errors(mb, cuda_device):
     from mbpo_b200.optimizers import iCemTO, iCemParams, AbstractCost
     from mbpo_b200.systems import PendulumSystem, System
+    oc = iCemTO(horizon=20, action_dim=1, opt_params=iCemParams(num_samples=64, num_particles=1),
+                cost_fn=AbstractCost(20))                                             # the abstract cost has no body
+    oc.set_system(PendulumSystem())
     with pytest.raises(NotImplementedError):
-        iCemTO(horizon=20, action_dim=1, cost_fn=AbstractCost(20))
+        oc.act(torch.tensor([-1.0, 0.0, 0.0], device=cuda_device), oc.init(mb.random.PRNGKey(0, cuda_device)))
     opt = iCemTO(horizon=21, action_dim=1, opt_params=iCemParams(num_particles=1))   # no compiled kernel for H=21
     opt.set_system(PendulumSystem())
     st = opt.init(mb.random.PRNGKey(0, cuda_device))
@@ -913,3 +916,201 @@ def test_full_size_config2_properties(mb, cuda_device):
     # planning beats the zero sequence (which is always among the candidates)
     zero = rollout_returns(sys_, st.system_params, x0, torch.zeros((B, 1, H, 1), device=cuda_device))[:, 0]
     assert bool((n1.best_reward >= zero).all())
+
+
+# ---------------------------------------------------------------------------------------------
+# rollout_policy, its cotangent pass and lambda_return (BPTT)
+# ---------------------------------------------------------------------------------------------
+def _bptt_policy(mb, cuda_device, hidden=(64, 64), evaluate=False, normalize=True, seed=17):
+    from mbpo_b200.acting import BpttActorPolicy, PolicyParams
+    pol = orc.make_policy_params(seed=seed, hidden=hidden)
+    mean = np.array([0.1, -0.2, 0.5], np.float32) if normalize else None
+    std = np.array([0.7, 0.8, 3.0], np.float32) if normalize else None
+    oparams = orc.BpttActorParams(mlp=pol, init_stddev=0.5, sig_min=1e-6, sig_max=1e2, obs_mean=mean, obs_std=std)
+    policy = BpttActorPolicy(PolicyParams(weights=[_dev(w, cuda_device) for w in pol.weights],
+                                          biases=[_dev(b, cuda_device) for b in pol.biases]),
+                             init_stddev=0.5, sig_min=1e-6, sig_max=1e2, obs_mean=mean, obs_std=std, evaluate=evaluate)
+    return policy, oparams
+
+
+@pytest.mark.parametrize("evaluate", [False, True])
+@pytest.mark.parametrize("hidden,normalize", [((64, 64), True), ((64, 64, 64), False)])
+def test_rollout_policy_vs_oracle(mb, cuda_device, prng_mode, evaluate, hidden, normalize):
+    """rollout_policy with BPTT's train_policy in one launch, per step against the oracle teacher-forced on the
+    GPU's observations; the carried key is bit exact and every trajectory of the batch shares the draw."""
+    from mbpo_b200.systems import PendulumSystem
+    from mbpo_b200.utils.optimizer_utils import rollout_policy
+    B, H = 203, 15
+    policy, oparams = _bptt_policy(mb, cuda_device, hidden, evaluate, normalize)
+    system = PendulumSystem()
+    sp = system.reset(device=cuda_device).system_params
+    x0 = _random_states(B, 101)
+    key = ojr.PRNGKey(9)
+    tr = rollout_policy(system, sp, _dev(x0, cuda_device), policy, _dev(key, cuda_device), H)
+    assert tr.observation.shape == (B, H, 3) and tr.action.shape == (B, H, 1) and tr.reward.shape == (B, H)
+    g_obs = tr.observation.cpu().numpy()
+    want, okey = orc.rollout_policy(oparams, x0, key, H, evaluate=evaluate, partitionable=prng_mode, teacher_obs=g_obs)
+    key_out = tr.extras["policy_state_key"].cpu().numpy()
+    if evaluate:
+        assert np.array_equal(key_out, key)
+    else:
+        assert np.array_equal(key_out, okey)
+    np.testing.assert_allclose(tr.action.cpu().numpy(), want["action"], rtol=3e-5, atol=3e-6)
+    assert float(tr.action.abs().max()) <= 0.999 + 1e-7
+    # the System step on the GPU's own actions
+    nxt, rew = orc.pendulum_step(g_obs.reshape(-1, 3), tr.action.cpu().numpy().reshape(-1))
+    np.testing.assert_allclose(tr.next_observation.cpu().numpy().reshape(-1, 3), nxt, rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(tr.reward.cpu().numpy().reshape(-1), rew, rtol=1e-5, atol=3e-6)
+    assert np.array_equal(g_obs[:, 0], x0) and np.array_equal(g_obs[:, 1:], tr.next_observation.cpu().numpy()[:, :-1])
+    assert bool((tr.discount == 1).all())
+    # single init_state form: fields [H, ...], same bits as row 0 of the batch
+    one = rollout_policy(system, sp, _dev(x0[0], cuda_device), policy, _dev(key, cuda_device), H)
+    assert one.observation.shape == (H, 3) and torch.equal(one.action, tr.action[0]) and torch.equal(one.reward, tr.reward[0])
+    with pytest.raises(mb.MbpoUnsupported):
+        rollout_policy(system, sp, _dev(x0, cuda_device), policy, _dev(key, cuda_device), H, stop_grads=False)
+    with pytest.raises(mb.MbpoUnsupported):
+        rollout_policy(system, sp, _dev(x0, cuda_device), lambda o, s: (o, s), _dev(key, cuda_device), H)
+
+
+def test_rollout_policy_vjp_vs_oracle(mb, cuda_device):
+    """The reverse scan through System.step against the oracle's hand-derived cotangent pass evaluated in
+    float64 on the same float32 trajectory, for both array layouts the kernel accepts."""
+    from mbpo_b200.systems import PendulumSystem
+    from mbpo_b200.utils.optimizer_utils import Transition, rollout_policy, rollout_policy_vjp
+    B, H = 300, 20
+    policy, _ = _bptt_policy(mb, cuda_device)
+    system = PendulumSystem()
+    sp = system.reset(device=cuda_device).system_params
+    x0 = _random_states(B, 111)
+    tr = rollout_policy(system, sp, _dev(x0, cuda_device), policy, _dev(ojr.PRNGKey(3), cuda_device), H)
+    rng = np.random.default_rng(112)
+    g_r, g_n = rng.standard_normal((B, H)).astype(np.float32), rng.standard_normal((B, H, 3)).astype(np.float32)
+    g_o, g_a = rng.standard_normal((B, H, 3)).astype(np.float32), rng.standard_normal((B, H, 1)).astype(np.float32)
+    obs, act = tr.observation.cpu().numpy(), tr.action.cpu().numpy()
+    for use in [(True, True, True, True), (True, False, False, False), (False, True, False, True)]:
+        args = [a if u else None for a, u in zip((g_r, g_n, g_o, g_a), use)]
+        want_a, want_x0 = orc.rollout_policy_vjp(obs, act, *args, dtype=np.float64)
+        dargs = [None if a is None else _dev(a, cuda_device) for a in args]
+        got_a, got_x0 = rollout_policy_vjp(system, sp, tr, *dargs)                       # time-major strided views
+        dense = Transition(*(f.contiguous() for f in tr[:5]))
+        got_a2, got_x02 = rollout_policy_vjp(system, sp, dense, *dargs)                  # the reference's [B, H, ...]
+        assert torch.equal(got_a, got_a2) and torch.equal(got_x0, got_x02)
+        scale = np.abs(want_a).max(axis=(1, 2), keepdims=True) + 1e-3                    # adjoints grow along the horizon
+        assert float(np.abs((got_a.cpu().numpy() - want_a) / scale).max()) < 2e-4
+        scale0 = np.abs(want_x0).max(axis=1, keepdims=True) + 1e-3
+        assert float(np.abs((got_x0.cpu().numpy() - want_x0) / scale0).max()) < 2e-4
+
+
+def test_bptt_actor_gradient_matches_autograd(mb, cuda_device):
+    """End to end: forward kernel -> cotangents of a loss -> adjoint kernel -> one batched backward of the policy
+    network equals torch autograd through the whole differentiable rollout (policy on detached observations,
+    pendulum dynamics and reward written in torch, float64) -- the gradient jax.value_and_grad returns in
+    BPTT._train_step (bptt_optimizer.py:361-376)."""
+    from mbpo_b200.systems import PendulumSystem
+    from mbpo_b200.utils.optimizer_utils import lambda_return, lambda_return_vjp, rollout_policy, rollout_policy_vjp
+    B, H, disc, lam = 64, 12, 0.99, 0.95
+    policy, oparams = _bptt_policy(mb, cuda_device, hidden=(64, 64), seed=23)
+    system = PendulumSystem()
+    sp = system.reset(device=cuda_device).system_params
+    x0 = _random_states(B, 121)
+    key = ojr.PRNGKey(4)
+    tr = rollout_policy(system, sp, _dev(x0, cuda_device), policy, _dev(key, cuda_device), H)
+    rng = np.random.default_rng(122)
+    wv = _dev(rng.standard_normal(3).astype(np.float32), cuda_device)                 # a linear "critic" v(x) = wv . x
+    # loss = -mean(lambda_return(reward, v(next_obs)) * disc_t)
+    pc = torch.cumprod(torch.tensor([1.0] + [disc] * (H - 1), device=cuda_device), 0)
+    nv = tr.next_observation @ wv
+    lv = lambda_return(tr.reward, nv, disc, lam)
+    np.testing.assert_array_equal(lv.cpu().numpy(), orc.lambda_return(tr.reward.cpu().numpy(), nv.cpu().numpy(), disc, lam))
+    g_lv = -(pc / (B * H)).expand(B, H).contiguous()
+    g_rew, g_nv = lambda_return_vjp(g_lv, disc, lam)
+    want_gr, want_gnv = orc.lambda_return_vjp(g_lv.cpu().numpy(), disc, lam)
+    np.testing.assert_allclose(g_rew.cpu().numpy(), want_gr, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(g_nv.cpu().numpy(), want_gnv, rtol=1e-6, atol=1e-9)
+    g_next = g_nv[..., None] * wv
+    g_act, _ = rollout_policy_vjp(system, sp, tr, g_reward=g_rew, g_next_observation=g_next)
+
+    # the policy network in torch (float64), used both for the batched backward and for the autograd reference
+    ws = [_dev(w, cuda_device).double().requires_grad_(True) for w in oparams.mlp.weights]
+    bs = [_dev(b, cuda_device).double().requires_grad_(True) for b in oparams.mlp.biases]
+    mean, std = _dev(oparams.obs_mean, cuda_device).double(), _dev(oparams.obs_std, cuda_device).double()
+    eps_t = []                                                                          # the draws the kernel used
+    k = key
+    for _ in range(H):
+        ks = ojr.split(k, 2)
+        eps_t.append(float(ojr.normal(ks[0], 1)[0]))
+        k = ks[1]
+    sig_bias = float(orc.inv_softplus(oparams.init_stddev))
+
+    def actor(o, eps):
+        h = (o - mean) / std
+        for i in range(len(ws)):
+            h = h @ ws[i] + bs[i]
+            if i < len(ws) - 1:
+                h = h * torch.sigmoid(h)
+        mu, sg = h[..., :1], h[..., 1:]
+        sg = torch.clamp(torch.nn.functional.softplus(sg + sig_bias), 1e-6, 1e2)
+        return torch.clamp(torch.tanh(mu + eps * sg), -0.999, 0.999)
+    # (1) our pipeline: one batched backward over all (obs_t, g_action_t) rows
+    eps_all = torch.tensor(eps_t, device=cuda_device, dtype=torch.float64).reshape(1, H, 1)
+    a_re = actor(tr.observation.double().detach(), eps_all)
+    np.testing.assert_allclose(a_re.detach().cpu().numpy(), tr.action.cpu().numpy(), rtol=3e-5, atol=3e-6)
+    grads_ours = torch.autograd.grad((a_re * g_act.double()).sum(), ws + bs)
+    # (2) autograd through the whole rollout
+    p = orc.PendulumParams()
+    x = _dev(x0, cuda_device).double()
+    rews, nvs = [], []
+    for t in range(H):
+        a = actor(x.detach(), eps_t[t])[:, 0]
+        th = torch.atan2(x[:, 1], x[:, 0])
+        d = torch.remainder(th - p.target_angle + np.pi, 2 * np.pi) - np.pi
+        rews.append(-(p.angle_cost * d ** 2 + 0.1 * x[:, 2] ** 2) - p.control_cost * a ** 2)
+        thdd = 3 * p.g / (2 * p.l) * torch.sin(th) + 3.0 / (p.m * p.l ** 2) * torch.clamp(a, -1, 1) * p.max_torque
+        nw = torch.clamp(x[:, 2] + thdd * p.dt, -p.max_speed, p.max_speed)
+        nth = th + nw * p.dt
+        x = torch.stack([torch.cos(nth), torch.sin(nth), nw], -1)
+        nvs.append(x @ wv.double())
+    rews, nvs = torch.stack(rews, 1), torch.stack(nvs, 1)
+    inputs = rews + disc * nvs * (1 - lam)
+    agg, rets = nvs[:, -1], []
+    for t in range(H - 1, -1, -1):
+        agg = inputs[:, t] + disc * lam * agg
+        rets.append(agg)
+    rets = torch.stack(rets[::-1], 1)
+    loss = -(rets * pc.double()).mean()
+    grads_ref = torch.autograd.grad(loss, ws + bs)
+    for go, gr in zip(grads_ours, grads_ref):
+        denom = float(gr.abs().max()) + 1e-12
+        assert float((go - gr).abs().max()) / denom < 2e-3, (float((go - gr).abs().max()), denom)
+
+
+def test_bptt_golden_fixture(mb, cuda_device):
+    """The committed vectors of tests/golden/bptt_golden.npz (frozen oracle outputs): rollout_policy teacher-free
+    over 10 steps, the cotangent pass on the fixture's trajectory, lambda_return bit for bit."""
+    import os
+    from mbpo_b200.acting import BpttActorPolicy, PolicyParams
+    from mbpo_b200.systems import PendulumSystem
+    from mbpo_b200.utils.optimizer_utils import Transition, lambda_return, lambda_return_vjp, rollout_policy, rollout_policy_vjp
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bptt_golden.npz"))
+    pol = orc.make_policy_params(seed=33, hidden=(64, 64))
+    policy = BpttActorPolicy(PolicyParams([_dev(w, cuda_device) for w in pol.weights], [_dev(b, cuda_device) for b in pol.biases]),
+                             init_stddev=0.5, obs_mean=[0.1, -0.2, 0.5], obs_std=[0.7, 0.8, 3.0])
+    system = PendulumSystem()
+    sp = system.reset(device=cuda_device).system_params
+    tr = rollout_policy(system, sp, _dev(G["x0"], cuda_device), policy, _dev(G["key"], cuda_device), 10)
+    assert np.array_equal(tr.extras["policy_state_key"].cpu().numpy(), G["key_out"])
+    # 10 closed-loop steps: 1-ulp differences grow a little along the horizon
+    np.testing.assert_allclose(tr.action.cpu().numpy(), G["tr_action"], rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(tr.next_observation.cpu().numpy(), G["tr_next_observation"], rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(tr.reward.cpu().numpy(), G["tr_reward"], rtol=1e-3, atol=1e-4)
+    fix = Transition(*(_dev(G["tr_" + k], cuda_device) for k in ("observation", "action", "reward", "discount", "next_observation")))
+    ga, gx0 = rollout_policy_vjp(system, sp, fix, *(_dev(G[k], cuda_device) for k in ("g_reward", "g_next_obs", "g_obs", "g_action")))
+    scale = np.abs(G["vjp_g_action"]).max(axis=(1, 2), keepdims=True) + 1e-3
+    assert float(np.abs((ga.cpu().numpy() - G["vjp_g_action"]) / scale).max()) < 2e-4
+    scale0 = np.abs(G["vjp_g_x0"]).max(axis=1, keepdims=True) + 1e-3
+    assert float(np.abs((gx0.cpu().numpy() - G["vjp_g_x0"]) / scale0).max()) < 2e-4
+    lv = lambda_return(_dev(G["tr_reward"], cuda_device), _dev(G["next_values"], cuda_device), 0.99, 0.95)
+    assert np.array_equal(lv.cpu().numpy(), G["lambda_returns"])
+    gr, gnv = lambda_return_vjp(_dev(G["g_reward"], cuda_device), 0.99, 0.95)
+    np.testing.assert_allclose(gr.cpu().numpy(), G["lambda_g_reward"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(gnv.cpu().numpy(), G["lambda_g_next_values"], rtol=1e-6, atol=1e-7)
