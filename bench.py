@@ -925,6 +925,156 @@ def run_actor(args):
         dist.destroy_process_group()
 
 
+BPTT_B, BPTT_H, BPTT_DISCOUNT, BPTT_LAMBDA = 65536, 20, 0.99, 0.97      # horizon / lambda_ of tests/test_bptt.py:51-57
+BPTT_ADJ_BYTES = 12 + 4 + 4 + 12 + 4         # observation, action, g_reward, g_next_obs read; g_action written
+
+
+def run_bptt(args):
+    """BPTT's differentiated rollout: rollout_policy forward (policy in the loop), lambda_return,
+    its transpose and the reverse scan through System.step, for 65,536 initial states x horizon 20."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from oracle import jax_prng as jr, mbpo_oracle as orc
+    pol = orc.make_policy_params(seed=7, hidden=(64, 64))
+    metric = "BPTT rollout + cotangent pass, transitions/sec"
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        B = 4096
+        actor = orc.BpttActorParams(mlp=pol, init_stddev=2.0)
+        x0 = random_states(BPTT_B, 1)[:B]
+        g = np.random.default_rng(3).standard_normal((B, BPTT_H)).astype(np.float32)
+
+        def once():
+            tr, _ = orc.rollout_policy(actor, x0, jr.PRNGKey(0), BPTT_H)
+            nv = tr["next_observation"][..., 2]
+            orc.lambda_return(tr["reward"], nv, BPTT_DISCOUNT, BPTT_LAMBDA)
+            gr, gnv = orc.lambda_return_vjp(g, BPTT_DISCOUNT, BPTT_LAMBDA)
+            gn = np.zeros((B, BPTT_H, 3), np.float32)
+            gn[..., 2] = gnv
+            orc.rollout_policy_vjp(tr["observation"], tr["action"], gr, gn)
+        once()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            once()
+        dt = (time.perf_counter() - t0) / args.steps
+        ncores, model = host_info()
+        v = B * BPTT_H / dt
+        emit_json({"impl": "reference", "metric": metric, "value": v, "unit": "transitions/s", "n_gpus": args.gpus,
+                   "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+                   "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                   "config": {"workload": "bptt_rollout_grad", "initial_states": BPTT_B, "horizon": BPTT_H},
+                   "cpu_baseline": {"value": v, "unit": "transitions/s", "cores": ncores, "kind": "port",
+                                    "sample": "%d of %d initial states, NumPy oracle (BLAS threads)" % (B, BPTT_B),
+                                    "host_cpu": model},
+                   "e2e": {"value": v, "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}, GUARD)
+        return
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import mbpo_b200
+    from mbpo_b200 import acting
+    from mbpo_b200.parallel import shard_bounds
+    from mbpo_b200.systems import PendulumSystem
+    from mbpo_b200.utils.optimizer_utils import lambda_return, lambda_return_vjp, rollout_policy, rollout_policy_vjp
+    lo, hi = shard_bounds(BPTT_B, rank, world)
+    B, H = hi - lo, BPTT_H
+    system = PendulumSystem()
+    sp = system.reset(device=dev).system_params
+    policy = acting.BpttActorPolicy(acting.PolicyParams([torch.from_numpy(w).to(dev) for w in pol.weights],
+                                                        [torch.from_numpy(b).to(dev) for b in pol.biases]), init_stddev=2.0)
+    x0_host = torch.from_numpy(random_states(BPTT_B, 1)[lo:hi].copy()).pin_memory()
+    x0 = x0_host.to(dev)
+    key = torch.from_numpy(jr.PRNGKey(0)).to(dev)
+    g_lv = torch.from_numpy(np.random.default_rng(3).standard_normal((H, BPTT_B)).astype(np.float32)[:, lo:hi].copy()).to(dev).t()
+    wv = torch.tensor([0.3, -0.2, 0.1], device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+    adj_ms = []
+
+    def step(x0_dev, timed=False):
+        tr = rollout_policy(system, sp, x0_dev, policy, key, H)
+        nv = tr.next_observation @ wv                                  # stand-in for the critic (the caller's network)
+        lv = lambda_return(tr.reward, nv, BPTT_DISCOUNT, BPTT_LAMBDA)
+        g_r, g_nv = lambda_return_vjp(g_lv, BPTT_DISCOUNT, BPTT_LAMBDA)
+        g_n = g_nv[..., None] * wv
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        g_a, g_x0 = rollout_policy_vjp(system, sp, tr, g_reward=g_r, g_next_observation=g_n)
+        if timed:
+            e1.record()
+            adj_ms.append((e0, e1))
+        return lv, g_a
+    for _ in range(max(args.warmup, 3)):
+        step(x0)
+    steps = min(args.steps, 20)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        for k in range(steps):
+            flush.zero_()
+            starts[k].record()
+            step(x0, timed=True)
+            ends[k].record()
+        barrier()
+    ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends)) / steps
+    a_ms = sum(s.elapsed_time(e) for s, e in adj_ms) / len(adj_ms)
+    t = torch.tensor([ms, a_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, a_ms = float(t[0]), float(t[1])
+    ga_host = torch.empty((B, H, 1), dtype=torch.float32).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(steps):
+        _, g_a = step(x0_host.to(dev, non_blocking=True))
+        ga_host.copy_(g_a, non_blocking=True)
+        torch.cuda.synchronize(dev)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / steps
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = B * H * BPTT_ADJ_BYTES / (a_ms * 1e-3) / 1e9
+        emit_json({
+            "metric": metric, "value": BPTT_B * H / (ms * 1e-3), "unit": "transitions/s", "n_gpus": world, "steps": steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic (random-init policy)",
+            "config": {"workload": "bptt_rollout_grad", "initial_states": BPTT_B, "horizon": H,
+                       "policy": "BPTT actor 3-64-64-2 swish", "discount": BPTT_DISCOUNT, "lambda": BPTT_LAMBDA,
+                       "parallelism": "initial states sharded x%d" % world,
+                       "l2": "flushed (256 MiB memset) before every timed step"},
+            "clocks": clk.summary(),
+            "adjoint_kernel_ms": a_ms,
+            "e2e": {"value": BPTT_B * H / e2e_s, "unit": "transitions/s", "ms_per_step": e2e_s * 1e3,
+                    "h2d_bytes_per_step": int(x0_host.numel() * 4), "d2h_bytes_per_step": int(ga_host.numel() * 4),
+                    "api": "rollout_policy -> lambda_return -> lambda_return_vjp -> rollout_policy_vjp; x0 from pinned host, g_action to host"},
+            "gpu_launches": 4 * steps,
+            "roofline": {"bound": "hbm", "kernel": "rollout_adjoint_pendulum_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "algorithmic_bytes_per_transition": BPTT_ADJ_BYTES,
+                         "note": "the step is dominated by the float32 policy MLP of the forward rollout (FMA-issue bound, see "
+                                 "config3_actor_rollouts); the roofline object describes the reverse scan",
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
+            "cpu_baseline": None}, GUARD)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 class _StdoutGuard:
     """Everything the libraries print (e.g. the NCCL version banner) goes to stderr; only the final
     JSON line reaches the real stdout."""
@@ -956,7 +1106,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["config1_closed_loop", "config3_env_rollouts", "config3_actor_rollouts",
-                                                               "config4_ensemble_icem", "config5_sweep"],
+                                                               "config4_ensemble_icem", "config5_sweep", "bptt_rollout_grad"],
                     default="config2_batched_icem")
     ap.add_argument("--math", choices=["reference", "theta_carry"], default="reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -973,6 +1123,8 @@ def main():
             return run_actor(args)
         if args.workload == "config1_closed_loop":
             return run_closed_loop(args)
+        if args.workload == "bptt_rollout_grad":
+            return run_bptt(args)
         if args.workload == "config5_sweep":
             return run_sweep(args)
         wl = WORKLOADS[args.workload]
