@@ -44,6 +44,9 @@ UNIT = "transitions/s"
 # Thread-level instructions the fused plan kernel executes per transition on the default
 # workload, measured with ncu (smsp__thread_inst_executed.sum / transitions; profiles/).  Used
 # for roofline.achieved = executed lane-instructions per second; see DESIGN.md.
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
+# captures (profiles/r01c_plan_kernel_ncu_full.txt, profiles/r01c_env_pieces_kernel_ncu_full.txt); N = 1 only.
+NCU_TRAFFIC_BYTES = {"config2_batched_icem": 681216, "config3_env_rollouts": 268336640 + 1518277000}
 LANE_INSTR_PER_TRANSITION = {("config2_batched_icem", "reference"): 229.7,
                              ("config2_batched_icem", "theta_carry"): 185.1}
 
@@ -285,7 +288,7 @@ def run_ours(args, wl_name, wl):
             "achieved": (tr_step * ipt / (kernel_ms * 1e-3) / 1e12) if ipt else None,
             "peak": issue_peak, "unit": "T lane-instr/s",
             "frac": (tr_step * ipt / (kernel_ms * 1e-3) / 1e12 / issue_peak) if ipt else None,
-            "traffic": None,
+            "traffic": NCU_TRAFFIC_BYTES.get(wl_name) if (world == 1 and args.math == "reference") else None,
             "lane_instr_per_transition": ipt,
             "peak_source": "148 SMs x 4 SMSPs x 32 lanes x sm_max_mhz (MEASURED_PEAKS.json)",
             "note": "the fused plan keeps actions in shared memory: HBM traffic is ~0 B/transition, so the "
@@ -464,7 +467,9 @@ def run_env(args):
                     "api": "VmappedSystemEnv.unroll(actions[T,E,1] from pinned host) -> Transition; rewards to host"},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "kernel": "env_rollout_pendulum_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": NCU_TRAFFIC_BYTES["config3_env_rollouts"] if world == 1 else None,
+                         "algorithmic_bytes_per_launch": E * T * ENV_BYTES_PER_TRANSITION,
                          "algorithmic_bytes_per_transition": ENV_BYTES_PER_TRANSITION,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
             "cpu_baseline": None}, GUARD)

@@ -1025,8 +1025,8 @@ def test_bptt_actor_gradient_matches_autograd(mb, cuda_device):
     g_lv = -(pc / (B * H)).expand(B, H).contiguous()
     g_rew, g_nv = lambda_return_vjp(g_lv, disc, lam)
     want_gr, want_gnv = orc.lambda_return_vjp(g_lv.cpu().numpy(), disc, lam)
-    np.testing.assert_allclose(g_rew.cpu().numpy(), want_gr, rtol=1e-6, atol=1e-9)
-    np.testing.assert_allclose(g_nv.cpu().numpy(), want_gnv, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(g_rew.cpu().numpy(), want_gr, rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(g_nv.cpu().numpy(), want_gnv, rtol=1e-5, atol=1e-9)
     g_next = g_nv[..., None] * wv
     g_act, _ = rollout_policy_vjp(system, sp, tr, g_reward=g_rew, g_next_observation=g_next)
 
@@ -1112,5 +1112,5 @@ def test_bptt_golden_fixture(mb, cuda_device):
     lv = lambda_return(_dev(G["tr_reward"], cuda_device), _dev(G["next_values"], cuda_device), 0.99, 0.95)
     assert np.array_equal(lv.cpu().numpy(), G["lambda_returns"])
     gr, gnv = lambda_return_vjp(_dev(G["g_reward"], cuda_device), 0.99, 0.95)
-    np.testing.assert_allclose(gr.cpu().numpy(), G["lambda_g_reward"], rtol=1e-6, atol=1e-7)
-    np.testing.assert_allclose(gnv.cpu().numpy(), G["lambda_g_next_values"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(gr.cpu().numpy(), G["lambda_g_reward"], rtol=1e-5, atol=1e-6)     # fused vs unfused mul-add
+    np.testing.assert_allclose(gnv.cpu().numpy(), G["lambda_g_next_values"], rtol=1e-5, atol=1e-6)
