@@ -72,11 +72,11 @@ __global__ void prng_draw_kernel(const uint32_t* __restrict__ keys, long long to
 
 int prng_draw(const uint32_t* keys, int M, int n, int prng_mode, int what, float lo, float hi, void* out,
               void* stream) {
-  MBPO_REQUIRE(keys && out, "prng: null pointer");
   MBPO_REQUIRE(M >= 0 && n >= 0, "prng: negative size");
   MBPO_REQUIRE(prng_mode == 0 || prng_mode == 1, "prng: bad prng_mode %d", prng_mode);
   const long long total = static_cast<long long>(M) * n;
   if (total == 0) return MBPO_OK;
+  MBPO_REQUIRE(keys && out, "prng: null pointer");
   const int threads = 256;
   const unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);
   if (prng_mode == 0)
@@ -150,11 +150,11 @@ int run_plan(const MbpoIcemCfg* c, const void* sys_params_host, const float* x0,
              const MbpoIcemTrace* trace, const MpcArgs* mpc, void* stream) {
   int rc = validate_cfg(c);
   if (rc != MBPO_OK) return rc;
-  MBPO_REQUIRE(sys_params_host && x0 && key_in && best_seq_in && best_seq_out && key_out, "plan: null pointer");
-  MBPO_REQUIRE(mpc != nullptr || best_value_out != nullptr, "plan: best_value_out is null");
   MBPO_REQUIRE(B >= 0, "plan: B < 0");
   if (!plan_fusable(c, true)) return MBPO_EUNSUPPORTED;
   if (B == 0) return MBPO_OK;
+  MBPO_REQUIRE(sys_params_host && x0 && key_in && best_seq_in && best_seq_out && key_out, "plan: null pointer");
+  MBPO_REQUIRE(mpc != nullptr || best_value_out != nullptr, "plan: best_value_out is null");
   PlanArgs a;
   fill_plan_args(a, c, static_cast<const MbpoPendulumParams*>(sys_params_host), x0, key_in, best_seq_in, B,
                  best_seq_out, best_value_out, key_out, trace);
@@ -245,11 +245,11 @@ int mbpo_icem_cfg_init(MbpoIcemCfg* cfg, int horizon, int action_dim, int x_dim,
 
 // ---- PRNG ------------------------------------------------------------------------------------
 int mbpo_prng_split(const uint32_t* keys, int M, int num, int prng_mode, uint32_t* keys_out, void* stream) {
-  MBPO_REQUIRE(keys && keys_out, "prng_split: null pointer");
   MBPO_REQUIRE(M >= 0 && num >= 0, "prng_split: negative size");
   MBPO_REQUIRE(prng_mode == 0 || prng_mode == 1, "prng_split: bad prng_mode %d", prng_mode);
   const long long total = static_cast<long long>(M) * num;
   if (total == 0) return MBPO_OK;
+  MBPO_REQUIRE(keys && keys_out, "prng_split: null pointer");
   const int threads = 256;
   const unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);
   if (prng_mode == 0) prng_split_kernel<0><<<blocks, threads, 0, as_stream(stream)>>>(keys, total, num, keys_out);
@@ -275,11 +275,11 @@ int mbpo_powerlaw_noise(const MbpoIcemCfg* cfg, const uint32_t* keys, int M, flo
                         void* stream) {
   const int rc = validate_cfg(cfg);
   if (rc != MBPO_OK) return rc;
-  MBPO_REQUIRE(keys && noise_out, "powerlaw_noise: null pointer");
   MBPO_REQUIRE(M >= 0, "powerlaw_noise: M < 0");
   if (!horizon_supported(cfg->horizon))
     return fail(MBPO_EUNSUPPORTED, "horizon %d has no compiled sampling kernel (" MBPO_H_LIST_STR ")", cfg->horizon);
   if (M == 0) return MBPO_OK;
+  MBPO_REQUIRE(keys && noise_out, "powerlaw_noise: null pointer");
   const ScaleTable tbl = make_scale_table(cfg);
   switch (cfg->horizon) {
 #define X(h) \
@@ -296,11 +296,11 @@ int mbpo_icem_sample_actions(const MbpoIcemCfg* cfg, const uint32_t* carry_key, 
                              void* stream) {
   const int rc = validate_cfg(cfg);
   if (rc != MBPO_OK) return rc;
-  MBPO_REQUIRE(carry_key && mean && std_ && actions_out && next_key_out, "sample_actions: null pointer");
   MBPO_REQUIRE(B >= 0 && B <= 65535, "sample_actions: B %d outside [0, 65535]", B);
   if (!horizon_supported(cfg->horizon))
     return fail(MBPO_EUNSUPPORTED, "horizon %d has no compiled sampling kernel (" MBPO_H_LIST_STR ")", cfg->horizon);
   if (B == 0) return MBPO_OK;
+  MBPO_REQUIRE(carry_key && mean && std_ && actions_out && next_key_out, "sample_actions: null pointer");
   const ScaleTable tbl = make_scale_table(cfg);
   switch (cfg->horizon) {
 #define X(h)                                                                                                    \
@@ -321,10 +321,10 @@ int mbpo_system_step(int system_kind, const void* sys_params_host, int math_mode
                "system_step: unknown system_kind %d", system_kind);
   if (system_kind != MBPO_SYSTEM_PENDULUM)
     return fail(MBPO_EUNSUPPORTED, "system_step: only MBPO_SYSTEM_PENDULUM has an inlined step");
-  MBPO_REQUIRE(sys_params_host && x && u && x_next && reward, "system_step: null pointer");
   MBPO_REQUIRE(math_mode == 0 || math_mode == 1, "system_step: bad math_mode %d", math_mode);
   MBPO_REQUIRE(R >= 0, "system_step: R < 0");
   if (R == 0) return MBPO_OK;
+  MBPO_REQUIRE(sys_params_host && x && u && x_next && reward, "system_step: null pointer");
   const MbpoPendulumParams sys = *static_cast<const MbpoPendulumParams*>(sys_params_host);
   const int threads = 128;
   const unsigned blocks = static_cast<unsigned>((R + threads - 1) / threads);
@@ -347,13 +347,13 @@ int mbpo_rollout_actions(int system_kind, const void* sys_params_host, int math_
   }
   if (system_kind != MBPO_SYSTEM_PENDULUM)
     return fail(MBPO_EUNSUPPORTED, "rollout_actions: unknown system_kind %d", system_kind);
-  MBPO_REQUIRE(sys_params_host && x0 && actions, "rollout_actions: null pointer");
   MBPO_REQUIRE(action_dim == 1 && x_dim == 3, "rollout_actions: pendulum needs action_dim == 1, x_dim == 3");
   MBPO_REQUIRE(horizon >= 1 && horizon <= 4096, "rollout_actions: horizon %d outside [1, 4096]", horizon);
   MBPO_REQUIRE(math_mode == 0 || math_mode == 1, "rollout_actions: bad math_mode %d", math_mode);
   MBPO_REQUIRE(B >= 0 && M >= 0, "rollout_actions: negative size");
   const long long total = static_cast<long long>(B) * M;
   if (total == 0) return MBPO_OK;
+  MBPO_REQUIRE(sys_params_host && x0 && actions, "rollout_actions: null pointer");
   const MbpoPendulumParams sys = *static_cast<const MbpoPendulumParams*>(sys_params_host);
   const int threads = 128;
   const int HS = horizon | 1;
@@ -385,11 +385,11 @@ int mbpo_icem_elite_refit(const MbpoIcemCfg* cfg, const float* actions, const fl
                           int32_t* elite_idx_out, void* stream) {
   const int rc = validate_cfg(cfg);
   if (rc != MBPO_OK) return rc;
+  MBPO_REQUIRE(B >= 0, "elite_refit: B < 0");
+  if (B == 0) return MBPO_OK;
   MBPO_REQUIRE(actions && values && mean_in && std_in && best_value_in && best_seq_in && mean_out && std_out &&
                    best_value_out && best_seq_out,
                "elite_refit: null pointer");
-  MBPO_REQUIRE(B >= 0, "elite_refit: B < 0");
-  if (B == 0) return MBPO_OK;
   RefitScalars rs;
   rs.M = cfg->num_samples + cfg->num_prev_elites;
   rs.K = cfg->num_elites;
@@ -438,9 +438,7 @@ int mbpo_icem_plan_staged(const MbpoIcemCfg* cfg, const void* sys_params_host, c
                           void* stream) {
   int rc = validate_cfg(cfg);
   if (rc != MBPO_OK) return rc;
-  MBPO_REQUIRE(sys_params_host && x0 && key_in && best_seq_in && best_seq_out && best_value_out && key_out &&
-                   workspace,
-               "plan_staged: null pointer");
+  MBPO_REQUIRE(sys_params_host, "plan_staged: null pointer");
   MBPO_REQUIRE(B >= 0 && B <= 65535, "plan_staged: B %d outside [0, 65535]", B);
   if (cfg->system_kind != MBPO_SYSTEM_PENDULUM && cfg->system_kind != MBPO_SYSTEM_MLP_ENSEMBLE)
     return fail(MBPO_EUNSUPPORTED, "plan_staged: unknown system_kind %d", cfg->system_kind);
@@ -455,6 +453,8 @@ int mbpo_icem_plan_staged(const MbpoIcemCfg* cfg, const void* sys_params_host, c
     return fail(MBPO_EWORKSPACE, "plan_staged: workspace %zu B < required %zu B", workspace_bytes,
                 mbpo_icem_workspace_bytes(cfg, B));
   if (B == 0) return MBPO_OK;
+  MBPO_REQUIRE(x0 && key_in && best_seq_in && best_seq_out && best_value_out && key_out && workspace,
+               "plan_staged: null pointer");
   const size_t M = static_cast<size_t>(cfg->num_samples) + cfg->num_prev_elites;
   const size_t D = static_cast<size_t>(cfg->horizon) * cfg->action_dim;
   const size_t b = static_cast<size_t>(B);
@@ -534,10 +534,10 @@ int mbpo_icem_penalize(float* values, const float* cost, long long n, int num_pa
 
 int mbpo_icem_clip_actions(float* actions, const float* u_min, const float* u_max, int B, int M, int N, int D,
                            void* stream) {
-  MBPO_REQUIRE(actions && u_min && u_max, "clip_actions: null pointer");
   MBPO_REQUIRE(B >= 0 && M >= 0 && N >= 0 && N <= M && D >= 1, "clip_actions: bad sizes");
   const long long total = static_cast<long long>(B) * M * D;
   if (total == 0) return MBPO_OK;
+  MBPO_REQUIRE(actions && u_min && u_max, "clip_actions: null pointer");
   clip_actions_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, as_stream(stream)>>>(actions, u_min, u_max,
                                                                                                  total, M, N, D);
   return check_launch("clip_actions_kernel");
@@ -569,13 +569,13 @@ int launch_env(int system_kind, const void* sys_params_host, int math_mode, int 
   using namespace mbpo;
   if (system_kind != MBPO_SYSTEM_PENDULUM)
     return fail(MBPO_EUNSUPPORTED, "env_rollout: only MBPO_SYSTEM_PENDULUM has an inlined step");
-  MBPO_REQUIRE(sys_params_host && obs_in && steps_in && done_in && obs && steps && done && first_obs && actions,
-               "env_rollout: null pointer");
   MBPO_REQUIRE(action_dim == 1 && x_dim == 3, "env_rollout: pendulum needs action_dim == 1, x_dim == 3");
   MBPO_REQUIRE(math_mode == 0 || math_mode == 1, "env_rollout: bad math_mode %d", math_mode);
   MBPO_REQUIRE(episode_length >= 1 && action_repeat >= 1, "env_rollout: episode_length/action_repeat < 1");
   MBPO_REQUIRE(E >= 0 && T >= 0, "env_rollout: negative size");
-  if (E == 0 || T == 0) return MBPO_OK;
+  if (E == 0 || T == 0) return MBPO_OK;     // empty arrays have no address
+  MBPO_REQUIRE(sys_params_host && obs_in && steps_in && done_in && obs && steps && done && first_obs && actions,
+               "env_rollout: null pointer");
   EnvArgs a;
   a.sys = *static_cast<const MbpoPendulumParams*>(sys_params_host);
   a.E = E; a.T = T; a.episode_length = episode_length; a.action_repeat = action_repeat;
@@ -744,10 +744,10 @@ int mbpo_rollout_adjoint(int system_kind, const void* sys_params_host, int x_dim
                          float* g_action_out, float* g_x0_out, void* stream) {
   if (system_kind != MBPO_SYSTEM_PENDULUM)
     return fail(MBPO_EUNSUPPORTED, "rollout_adjoint: only MBPO_SYSTEM_PENDULUM has a hand-written adjoint");
-  MBPO_REQUIRE(sys_params_host && observation && action && g_action_out, "rollout_adjoint: null pointer");
   MBPO_REQUIRE(action_dim == 1 && x_dim == 3, "rollout_adjoint: pendulum needs action_dim == 1, x_dim == 3");
   MBPO_REQUIRE(E >= 0 && T >= 0, "rollout_adjoint: negative size");
   if (E == 0) return MBPO_OK;
+  MBPO_REQUIRE(sys_params_host && observation && action && g_action_out, "rollout_adjoint: null pointer");
   mbpo::AdjointArgs a;
   a.sys = *static_cast<const MbpoPendulumParams*>(sys_params_host);
   a.E = E; a.T = T; a.st_t = stride_t; a.st_e = stride_e; a.sx_t = stride_xt; a.sx_e = stride_xe;
@@ -775,9 +775,9 @@ mbpo::LambdaArgs lambda_args(int E, int T, long long stride_t, long long stride_
 
 int mbpo_lambda_return(const float* reward, const float* next_values, int E, int T, long long stride_t,
                        long long stride_e, double discount, double lambda_, float* returns_out, void* stream) {
-  MBPO_REQUIRE(reward && next_values && returns_out, "lambda_return: null pointer");
   MBPO_REQUIRE(E >= 0 && T >= 0, "lambda_return: negative size");
   if (E == 0 || T == 0) return MBPO_OK;
+  MBPO_REQUIRE(reward && next_values && returns_out, "lambda_return: null pointer");
   mbpo::LambdaArgs a = lambda_args(E, T, stride_t, stride_e, discount, lambda_);
   a.reward = reward; a.next_values = next_values; a.out = returns_out; a.out2 = nullptr;
   mbpo::lambda_return_kernel<<<(E + 127) / 128, 128, 0, as_stream(stream)>>>(a);
@@ -787,9 +787,9 @@ int mbpo_lambda_return(const float* reward, const float* next_values, int E, int
 int mbpo_lambda_return_vjp(const float* g_returns, int E, int T, long long stride_t, long long stride_e,
                            double discount, double lambda_, float* g_reward_out, float* g_next_values_out,
                            void* stream) {
-  MBPO_REQUIRE(g_returns && g_reward_out && g_next_values_out, "lambda_return_vjp: null pointer");
   MBPO_REQUIRE(E >= 0 && T >= 0, "lambda_return_vjp: negative size");
   if (E == 0 || T == 0) return MBPO_OK;
+  MBPO_REQUIRE(g_returns && g_reward_out && g_next_values_out, "lambda_return_vjp: null pointer");
   mbpo::LambdaArgs a = lambda_args(E, T, stride_t, stride_e, discount, lambda_);
   a.reward = g_returns; a.next_values = nullptr; a.out = g_reward_out; a.out2 = g_next_values_out;
   mbpo::lambda_return_transpose_kernel<<<(E + 127) / 128, 128, 0, as_stream(stream)>>>(a);

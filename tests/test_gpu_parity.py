@@ -918,6 +918,91 @@ def test_full_size_config2_properties(mb, cuda_device):
     assert bool((n1.best_reward >= zero).all())
 
 
+def test_full_size_config3_properties(mb, cuda_device):
+    """BASELINE config 3 at full size (65,536 envs x 1,000 steps, episode_length 200): the episode-piece kernel
+    against the one-scan-per-env kernel bit for bit, the AutoReset bookkeeping in closed form, a random sample of
+    transitions against the oracle, and shard invariance (an env range alone = its slice of the full launch)."""
+    L = mb._lib
+    from mbpo_b200.envs import wrap
+    from mbpo_b200.systems import PendulumSystem
+    E, T, EP = 65536, 1000, 200
+    sys_ = PendulumSystem()
+    sp = sys_.reset(device=cuda_device).system_params
+    env = wrap(sys_, sp, episode_length=EP)
+    x0 = _dev(_random_states(E, 1), cuda_device)
+    acts = torch.rand((T, E, 1), device=cuda_device, generator=torch.Generator(cuda_device).manual_seed(2)) * 2 - 1
+    st = env.reset(x0)
+    new, tr = env.unroll(st, acts)
+    # sequential kernel, in place
+    pp = sys_.pack_params(sp)
+    obs, steps, done = st.obs.clone(), st.info["steps"].clone(), st.done.clone()
+    n = torch.empty((T, E, 3), device=cuda_device)
+    r, d, t_ = (torch.empty((T, E), device=cuda_device) for _ in range(3))
+    L.check(L.lib.mbpo_env_rollout(0, L.C.addressof(pp), 0, 3, 1, EP, 1, L.ptr(obs), L.ptr(steps), L.ptr(done),
+                                   L.ptr(st.info["first_obs"]), L.ptr(acts), E, T, None, L.ptr(r), L.ptr(d), L.ptr(n),
+                                   L.ptr(t_), L.stream_ptr(cuda_device)))
+    assert torch.equal(n, tr.next_observation) and torch.equal(r, tr.reward)
+    assert torch.equal(d, tr.discount) and torch.equal(t_, tr.extras["state_extras"]["truncation"])
+    assert torch.equal(obs, new.obs) and torch.equal(steps, new.info["steps"]) and torch.equal(done, new.done)
+    del n, r, d, t_
+    # bookkeeping in closed form: an episode ends (discount 0, truncation 1, obs reset) exactly at t % 200 == 199
+    ends = (torch.arange(T, device=cuda_device) % EP == EP - 1).float()[:, None].expand(T, E)
+    assert torch.equal(tr.discount, 1 - ends) and torch.equal(tr.extras["state_extras"]["truncation"], ends)
+    assert torch.equal(tr.next_observation[EP - 1::EP], x0[None].expand(T // EP, E, 3))
+    assert bool((new.info["steps"] == EP).all()) and bool((new.done == 1).all())
+    assert bool(torch.isfinite(tr.reward).all()) and float(tr.reward.max()) <= 0.0
+    assert float((tr.next_observation[..., 0] ** 2 + tr.next_observation[..., 1] ** 2 - 1).abs().max()) < 1e-5
+    # a random sample of transitions against the oracle (teacher-forced on the GPU's observations)
+    g = torch.Generator().manual_seed(5)
+    ti, ei = torch.randint(0, T, (20000,), generator=g), torch.randint(0, E, (20000,), generator=g)
+    keep = (ti % EP) != EP - 1                                         # the step that resets returns first_obs instead
+    ti, ei = ti[keep].to(cuda_device), ei[keep].to(cuda_device)
+    xs, us = tr.observation[ti, ei].cpu().numpy(), acts[ti, ei, 0].cpu().numpy()
+    nxt, rew = orc.pendulum_step(xs, us)
+    np.testing.assert_allclose(tr.next_observation[ti, ei].cpu().numpy(), nxt, rtol=RTOL, atol=2e-6)
+    np.testing.assert_allclose(tr.reward[ti, ei].cpu().numpy(), rew, rtol=RTOL, atol=3e-6)
+    # shard invariance: envs [8192, 16384) alone (rank 1 of 8) = that slice of the full launch
+    lo, hi = 8192, 16384
+    st_sl = env.reset(x0[lo:hi].contiguous())
+    new_sl, tr_sl = env.unroll(st_sl, acts[:, lo:hi].contiguous())
+    assert torch.equal(tr_sl.next_observation, tr.next_observation[:, lo:hi]) and torch.equal(tr_sl.reward, tr.reward[:, lo:hi])
+    assert torch.equal(new_sl.obs, new.obs[lo:hi])
+
+
+def test_empty_and_degenerate_inputs(mb, cuda_device):
+    """Zero problems / envs / steps are valid calls that launch nothing; one env, one step and a one-step episode
+    exercise the piece arithmetic at its corners."""
+    from mbpo_b200.envs import wrap
+    from mbpo_b200.optimizers import iCemTO, iCemParams
+    from mbpo_b200.systems import PendulumSystem
+    from mbpo_b200.utils import lambda_return, rollout_actions
+    sys_ = PendulumSystem()
+    sp = sys_.reset(device=cuda_device).system_params
+    env = wrap(sys_, sp, episode_length=5)
+    st0 = env.reset(torch.zeros((0, 3), device=cuda_device))
+    new, tr = env.unroll(st0, torch.zeros((7, 0, 1), device=cuda_device))                 # no envs
+    assert tr.reward.shape == (7, 0) and new.obs.shape == (0, 3)
+    x0 = _dev(_random_states(3, 9), cuda_device)
+    st = env.reset(x0)
+    new, tr = env.unroll(st, torch.zeros((0, 3, 1), device=cuda_device))                  # no steps: state unchanged
+    assert tr.reward.shape == (0, 3) and torch.equal(new.obs, x0) and torch.equal(new.info["steps"], st.info["steps"])
+    env1 = wrap(sys_, sp, episode_length=1)                                               # every step ends an episode
+    acts = torch.full((6, 3, 1), 0.3, device=cuda_device)
+    new, tr = env1.unroll(env1.reset(x0), acts)
+    want = orc.env_rollout(x0.cpu().numpy(), acts[..., 0].cpu().numpy(), 1)
+    assert np.array_equal(tr.discount.cpu().numpy(), want["discount"]) and bool((tr.discount == 0).all())
+    assert torch.equal(tr.next_observation, x0[None].expand(6, 3, 3))
+    np.testing.assert_allclose(tr.reward.cpu().numpy(), want["reward"], rtol=RTOL, atol=3e-6)
+    opt = iCemTO(horizon=20, action_dim=1, opt_params=iCemParams(num_samples=64, num_particles=1))
+    opt.set_system(sys_)
+    st_b0 = opt.init(torch.zeros((0, 2), dtype=torch.uint32, device=cuda_device))
+    a, nst = opt.act(torch.zeros((0, 3), device=cuda_device), st_b0)                      # no problems
+    assert a.shape == (0, 1) and nst.best_sequence.shape == (0, 20, 1)
+    tr0 = rollout_actions(sys_, sp, torch.zeros((0, 3), device=cuda_device), torch.zeros((0, 4, 20, 1), device=cuda_device), 20)
+    assert tr0.reward.shape == (0, 4, 20)
+    assert lambda_return(torch.zeros((0, 9), device=cuda_device), torch.zeros((0, 9), device=cuda_device), 0.99, 0.9).shape == (0, 9)
+
+
 # ---------------------------------------------------------------------------------------------
 # rollout_policy, its cotangent pass and lambda_return (BPTT; SURVEY 8f-4)
 # ---------------------------------------------------------------------------------------------
