@@ -267,6 +267,18 @@ int mbpo_actor_rollout(int system_kind, const void* sys_params_host, int math_mo
                        float* reward_out, float* discount_out, float* next_observation_out,
                        float* truncation_out, uint32_t* key_out, void* stream);
 
+/* The same launch, also emitting what PPO's policy returns beside the action (ppo/ppo_network.py:59-84;
+ * sac/parametric_distribution.py:66-83): raw_action_out [T,E,A] = the pre-tanh sample, log_prob_out [T,E] =
+ * Normal(loc, scale).log_prob(raw) - Tanh.forward_log_det_jacobian(raw) summed over the action axis.  Both NULL
+ * or both given; ignored for deterministic policies (the reference returns {} there). */
+int mbpo_actor_rollout_extras(int system_kind, const void* sys_params_host, int math_mode, int prng_mode,
+                              const MbpoPolicyParams* policy_host, int deterministic, int key_convention,
+                              const uint32_t* key_in, int episode_length, int action_repeat, float* obs,
+                              float* steps, float* done, const float* first_obs, int E, int T,
+                              float* action_out, float* reward_out, float* discount_out,
+                              float* next_observation_out, float* truncation_out, uint32_t* key_out,
+                              float* raw_action_out, float* log_prob_out, void* stream);
+
 /* ---- reverse pass through System.step rollouts; lambda returns (BPTT) ----------------------- */
 /* The cotangent pass of jax.value_and_grad through rollout_policy(..., stop_grads=True)
  * (mbpo/utils/optimizer_utils.py:62-116; bptt_optimizer.py:327-376): the policy sees

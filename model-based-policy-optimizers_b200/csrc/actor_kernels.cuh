@@ -56,6 +56,8 @@ struct ActorArgs {
   float* next_observation_out;  // [T,E,3]
   float* truncation_out;        // [T,E]
   uint32_t* key_out;            // [2] carry key after T steps
+  float* raw_action_out;        // [T,E] or NULL: PPO's policy_extras['raw_action'] (pre-tanh sample)
+  float* log_prob_out;          // [T,E] or NULL: PPO's policy_extras['log_prob']
 };
 
 // jax.nn.swish(x) = x * sigmoid(x), sigmoid = 1 / (1 + exp(-x)).  ex2.approx (2^-22 relative) and rcp.approx
@@ -249,7 +251,19 @@ __global__ void __launch_bounds__(ACT_MAX_THREADS, 1) actor_rollout_pendulum_ker
       } else {
         const float eps = bits_to_normal(random_bits_at<PRNG>(k_actor, n_draw, i_draw));
         const float scale = softplus_exact(raw_scale[q] + b_scale) + a.min_std;
-        u = tanhf(__fadd_rn(__fmul_rn(scale, eps), loc[q] + b_loc));      // distrax Normal.sample: scale * rnd + loc
+        const float mu = loc[q] + b_loc;
+        const float raw = __fadd_rn(__fmul_rn(scale, eps), mu);          // distrax Normal.sample: scale * rnd + loc
+        u = tanhf(raw);
+        if (a.raw_action_out && live[q]) {
+          // ppo_network.py:72-80: raw_actions = sample_no_postprocessing; log_prob = Normal.log_prob(raw) -
+          // Tanh.forward_log_det_jacobian(raw), summed over the action axis (parametric_distribution.py:76-83);
+          // distrax: -0.5 * ((x - loc) / scale)^2 - (0.5 * log(2 pi) + log(scale)); 2 * (log 2 - x - softplus(-2 x))
+          const float z = __fdiv_rn(__fsub_rn(raw, mu), scale);
+          const float lp = __fsub_rn(__fmul_rn(-0.5f, __fmul_rn(z, z)), __fadd_rn(0.918938533f, logf(scale)));
+          const float ldj = __fmul_rn(2.0f, __fsub_rn(__fsub_rn(0.693147181f, raw), softplus_exact(__fmul_rn(-2.0f, raw))));
+          a.raw_action_out[static_cast<size_t>(t) * E + e_idx[q]] = raw;
+          a.log_prob_out[static_cast<size_t>(t) * E + e_idx[q]] = __fsub_rn(lp, ldj);
+        }
       }
       // ---- wrapped env step (env_kernels.cuh) ------------------------------------------------------------
       v.steps = (v.done != 0.0f) ? 0.0f : v.steps;

@@ -679,14 +679,31 @@ int mbpo_actor_rollout(int system_kind, const void* sys_params_host, int math_mo
                        float* done, const float* first_obs, int E, int T, float* action_out, float* reward_out,
                        float* discount_out, float* next_observation_out, float* truncation_out, uint32_t* key_out,
                        void* stream) {
+  return mbpo_actor_rollout_extras(system_kind, sys_params_host, math_mode, prng_mode, policy_host, deterministic,
+                                   key_convention, key_in, episode_length, action_repeat, obs, steps, done, first_obs,
+                                   E, T, action_out, reward_out, discount_out, next_observation_out, truncation_out,
+                                   key_out, nullptr, nullptr, stream);
+}
+
+int mbpo_actor_rollout_extras(int system_kind, const void* sys_params_host, int math_mode, int prng_mode,
+                              const MbpoPolicyParams* policy_host, int deterministic, int key_convention,
+                              const uint32_t* key_in, int episode_length, int action_repeat, float* obs,
+                              float* steps, float* done, const float* first_obs, int E, int T, float* action_out,
+                              float* reward_out, float* discount_out, float* next_observation_out,
+                              float* truncation_out, uint32_t* key_out, float* raw_action_out, float* log_prob_out,
+                              void* stream) {
   MBPO_REQUIRE(system_kind == MBPO_SYSTEM_PENDULUM || system_kind == MBPO_SYSTEM_MLP_ENSEMBLE,
                "actor_rollout: unknown system_kind %d", system_kind);
   if (system_kind != MBPO_SYSTEM_PENDULUM)
     return fail(MBPO_EUNSUPPORTED, "actor_rollout: only MBPO_SYSTEM_PENDULUM has an inlined step");
-  MBPO_REQUIRE(sys_params_host && policy_host && key_in && obs && steps && done && first_obs,
-               "actor_rollout: null pointer");
-  MBPO_REQUIRE(action_out && reward_out && discount_out && next_observation_out && truncation_out,
-               "actor_rollout: every Transition buffer is required");
+  MBPO_REQUIRE(sys_params_host && policy_host && key_in, "actor_rollout: null pointer");
+  MBPO_REQUIRE((raw_action_out == nullptr) == (log_prob_out == nullptr),
+               "actor_rollout: raw_action_out and log_prob_out come together");
+  if (E > 0 && T > 0) {                      // empty arrays have no address
+    MBPO_REQUIRE(obs && steps && done && first_obs, "actor_rollout: null pointer");
+    MBPO_REQUIRE(action_out && reward_out && discount_out && next_observation_out && truncation_out,
+                 "actor_rollout: every Transition buffer is required");
+  }
   MBPO_REQUIRE(math_mode == 0 || math_mode == 1, "actor_rollout: bad math_mode %d", math_mode);
   MBPO_REQUIRE(prng_mode == 0 || prng_mode == 1, "actor_rollout: bad prng_mode %d", prng_mode);
   MBPO_REQUIRE(key_convention >= 0 && key_convention <= 2, "actor_rollout: bad key_convention %d", key_convention);
@@ -727,6 +744,7 @@ int mbpo_actor_rollout(int system_kind, const void* sys_params_host, int math_mo
   a.obs = obs; a.steps = steps; a.done = done; a.first_obs = first_obs;
   a.action_out = action_out; a.reward_out = reward_out; a.discount_out = discount_out;
   a.next_observation_out = next_observation_out; a.truncation_out = truncation_out; a.key_out = key_out;
+  a.raw_action_out = raw_action_out; a.log_prob_out = log_prob_out;
   cudaStream_t st = as_stream(stream);
   switch (prng_mode * 2 + math_mode) {
     case 0: return launch_actor<0, 0>(a, st);

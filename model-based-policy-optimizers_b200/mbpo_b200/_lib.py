@@ -104,6 +104,8 @@ SIGNATURES = {
     "mbpo_env_unroll": (_I, [_I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "mbpo_actor_rollout": (_I, [_I, _P, _I, _I, C.POINTER(PolicyParamsC), _I, _I, _P, _I, _I, _P, _P, _P, _P, _I, _I,
                                 _P, _P, _P, _P, _P, _P, _P]),
+    "mbpo_actor_rollout_extras": (_I, [_I, _P, _I, _I, C.POINTER(PolicyParamsC), _I, _I, _P, _I, _I, _P, _P, _P, _P, _I,
+                                       _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mbpo_rollout_adjoint": (_I, [_I, _P, _I, _I, _I, _I, _LL, _LL, _LL, _LL, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mbpo_lambda_return": (_I, [_P, _P, _I, _I, _LL, _LL, C.c_double, C.c_double, _P, _P]),
     "mbpo_lambda_return_vjp": (_I, [_P, _I, _I, _LL, _LL, C.c_double, C.c_double, _P, _P, _P]),

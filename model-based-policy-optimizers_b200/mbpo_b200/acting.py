@@ -31,7 +31,11 @@ class Policy:
     """What ``make_policy(params, deterministic)`` returns (sac_networks.py:61-70).  Calling it samples
     actions for a batch of observations; actor_step / generate_unroll run it inside the env loop."""
 
-    def __init__(self, params: PolicyParams, deterministic: bool = False):
+    def __init__(self, params: PolicyParams, deterministic: bool = False, obs_mean: Sequence[float] = None,
+                 obs_std: Sequence[float] = None, emit_extras: bool = False):
+        """obs_mean / obs_std: the running-statistics normaliser the reference passes as ``normalizer_params``
+        (``policy_network.apply(normalizer_params, policy_params, obs)``: (obs - mean) / std); emit_extras: PPO's
+        policy also returns {'log_prob', 'raw_action'} (ppo_network.py:72-80)."""
         w = [t.to(torch.float32).contiguous() for t in params.weights]
         b = [t.to(torch.float32).contiguous() for t in params.biases]
         if len(w) < 2 or len(w) != len(b) or len(w) > 5:
@@ -50,6 +54,17 @@ class Policy:
         s.min_std = self.min_std
         s.head = _lib.HEAD_NORMAL_TANH
         self.struct = s
+        self.emit_extras = bool(emit_extras) and not self.deterministic
+        self._set_normalizer(obs_mean, obs_std)
+
+    def _set_normalizer(self, obs_mean, obs_std):
+        s = self.struct
+        s.normalize = int(obs_mean is not None)
+        if obs_mean is not None:
+            mean = [float(v) for v in (obs_mean.tolist() if hasattr(obs_mean, "tolist") else obs_mean)]
+            std = [float(v) for v in (obs_std.tolist() if hasattr(obs_std, "tolist") else obs_std)]
+            for i in range(len(mean)):
+                s.obs_mean[i], s.obs_std[i] = mean[i], std[i]
 
     def __call__(self, observations: torch.Tensor, key_sample: torch.Tensor):
         """policy(observations [E, X], key) -> (actions [E, A], {}).  Runs one actor step on a scratch env
@@ -71,7 +86,7 @@ class BpttActorPolicy(Policy):
 
     def __init__(self, params: PolicyParams, init_stddev: float = 1.0, sig_min: float = 1e-6, sig_max: float = 1e2,
                  obs_mean: Sequence[float] = None, obs_std: Sequence[float] = None, evaluate: bool = False):
-        super().__init__(params, deterministic=evaluate)
+        super().__init__(params, deterministic=evaluate, obs_mean=obs_mean, obs_std=obs_std)
         import numpy as np
         s = self.struct
         s.head = _lib.HEAD_BPTT_ACTOR
@@ -79,18 +94,20 @@ class BpttActorPolicy(Policy):
         x = np.float32(init_stddev)                                      # inv_softplus on a weak-typed python float
         s.sig_bias = float(np.log(np.exp(x) - np.float32(1.0))) if init_stddev < 20.0 else float(x)
         s.sig_min, s.sig_max, s.action_clip = float(sig_min), float(sig_max), 0.999
-        s.normalize = int(obs_mean is not None)
-        if obs_mean is not None:
-            mean = [float(v) for v in (obs_mean.tolist() if hasattr(obs_mean, "tolist") else obs_mean)]
-            std = [float(v) for v in (obs_std.tolist() if hasattr(obs_std, "tolist") else obs_std)]
-            for i in range(len(mean)):
-                s.obs_mean[i], s.obs_std[i] = mean[i], std[i]
 
 
 def make_inference_fn():
     """sac_networks.make_inference_fn: returns make_policy(params, deterministic=False) -> Policy."""
-    def make_policy(params: PolicyParams, deterministic: bool = False) -> Policy:
-        return Policy(params, deterministic)
+    def make_policy(params: PolicyParams, deterministic: bool = False, obs_mean=None, obs_std=None) -> Policy:
+        return Policy(params, deterministic, obs_mean, obs_std)
+    return make_policy
+
+
+def make_ppo_inference_fn():
+    """ppo/ppo_network.py:59-84 make_inference_fn: the same NormalTanh policy, whose sample also returns
+    {'log_prob', 'raw_action'}; they arrive in Transition.extras['policy_extras'] ([T, E] / [T, E, A])."""
+    def make_policy(params: PolicyParams, deterministic: bool = False, obs_mean=None, obs_std=None) -> Policy:
+        return Policy(params, deterministic, obs_mean, obs_std, emit_extras=True)
     return make_policy
 
 
@@ -116,16 +133,20 @@ def _rollout(env: VmappedSystemEnv, env_state: EnvState, policy: Policy, key: to
     d = torch.empty((T, E), dtype=torch.float32, device=dev)
     tr = torch.empty((T, E), dtype=torch.float32, device=dev)
     params = system.pack_params(env_state.system_params)
+    raw = torch.empty((T, E, A), dtype=torch.float32, device=dev) if policy.emit_extras else None
+    logp = torch.empty((T, E), dtype=torch.float32, device=dev) if policy.emit_extras else None
     with _lib.cuda_guard(obs):
-        _lib.check(_lib.lib.mbpo_actor_rollout(
+        _lib.check(_lib.lib.mbpo_actor_rollout_extras(
             system.system_kind, _lib.C.addressof(params), config.math_mode_id, config.prng_mode,
             _lib.C.byref(policy.struct), int(policy.deterministic), key_convention, _lib.ptr(key), env.episode_length,
             env.action_repeat, _lib.ptr(obs), _lib.ptr(steps), _lib.ptr(done), _lib.ptr(first), E, T, _lib.ptr(act),
-            _lib.ptr(r), _lib.ptr(d), _lib.ptr(buf[1:]), _lib.ptr(tr), _lib.ptr(key_out), _lib.stream_ptr(dev)))
+            _lib.ptr(r), _lib.ptr(d), _lib.ptr(buf[1:]), _lib.ptr(tr), _lib.ptr(key_out), _lib.ptr(raw), _lib.ptr(logp),
+            _lib.stream_ptr(dev)))
     nstate = EnvState(obs=obs, reward=r[-1] if T else env_state.reward, done=done,
                       system_params=env_state.system_params,
                       info=dict(steps=steps, truncation=tr[-1] if T else env_state.info["truncation"], first_obs=first))
-    extras = {"policy_extras": {}, "state_extras": {f: tr for f in extra_fields}}
+    policy_extras = {"log_prob": logp, "raw_action": raw} if policy.emit_extras else {}
+    extras = {"policy_extras": policy_extras, "state_extras": {f: tr for f in extra_fields}}
     transition = Transition(observation=buf[:T], action=act, reward=r, discount=d, next_observation=buf[1:],
                             extras=extras)
     return nstate, transition, key_out
@@ -135,7 +156,8 @@ def actor_step(env: VmappedSystemEnv, env_state: EnvState, policy: Policy, key: 
                extra_fields: Sequence[str] = ()) -> Tuple[EnvState, Transition]:
     """sac/acting.py:35-55: one step, the key is the policy's sample key.  Fields are [E, ...]."""
     nstate, tr, _ = _rollout(env, env_state, policy, key, 1, _lib.KEYS_AS_IS, extra_fields)
-    ex = {"policy_extras": {}, "state_extras": {k: v[0] for k, v in tr.extras["state_extras"].items()}}
+    ex = {"policy_extras": {k: v[0] for k, v in tr.extras["policy_extras"].items()},
+          "state_extras": {k: v[0] for k, v in tr.extras["state_extras"].items()}}
     return nstate, Transition(tr.observation[0], tr.action[0], tr.reward[0], tr.discount[0], tr.next_observation[0], ex)
 
 

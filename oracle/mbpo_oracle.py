@@ -645,9 +645,14 @@ def softplus(x):
 
 
 def policy_sample(params: PolicyParams, obs: np.ndarray, key, deterministic: bool = False,
-                  partitionable: bool = False) -> np.ndarray:
-    """make_policy(params)(observations, key_sample) (sac_networks.py:61-70): actions [E, A]."""
-    logits = policy_logits(params, obs)
+                  partitionable: bool = False, obs_mean=None, obs_std=None, with_extras: bool = False):
+    """make_policy(params)(observations, key_sample) (sac_networks.py:61-70): actions [E, A].  obs_mean / obs_std:
+    the normaliser params applied by the policy network ((obs - mean) / std).  with_extras: PPO's policy
+    (ppo/ppo_network.py:66-80) -> (actions, raw_actions [E, A], log_prob [E])."""
+    x = np.asarray(obs, dtype=F32)
+    if obs_mean is not None:
+        x = ((x - np.asarray(obs_mean, F32)).astype(F32) / np.asarray(obs_std, F32)).astype(F32)
+    logits = policy_logits(params, x)
     a_dim = logits.shape[-1] // 2
     loc, scale = logits[..., :a_dim], logits[..., a_dim:]              # jnp.split(parameters, 2, axis=-1)
     if deterministic:
@@ -656,7 +661,15 @@ def policy_sample(params: PolicyParams, obs: np.ndarray, key, deterministic: boo
     e = obs.shape[0]
     eps = jr.normal(key, e * a_dim, partitionable).reshape(e, a_dim)   # Normal._sample_n: normal(key, (1, E, A))
     raw = ((scale * eps).astype(F32) + loc).astype(F32)                # scale * rnd + loc
-    return np.tanh(raw).astype(F32)                                    # distrax.Tanh().forward
+    act = np.tanh(raw).astype(F32)                                     # distrax.Tanh().forward
+    if not with_extras:
+        return act
+    # parametric_distribution.py:76-83 with distrax 0.1.x: Normal.log_prob = -0.5 * ((x - loc) / scale)^2 -
+    # (0.5 * log(2 pi) + log(scale)); Tanh.forward_log_det_jacobian(x) = 2 * (log(2) - x - softplus(-2 x))
+    z = ((raw - loc).astype(F32) / scale).astype(F32)
+    lp = (F32(-0.5) * (z * z).astype(F32) - (F32(0.5 * np.log(2 * np.pi)) + np.log(scale).astype(F32))).astype(F32)
+    ldj = (F32(2.0) * ((F32(np.log(2.0)) - raw).astype(F32) - softplus((F32(-2.0) * raw).astype(F32)))).astype(F32)
+    return act, raw, (lp - ldj).astype(F32).sum(axis=-1)
 
 
 def actor_rollout(params: PolicyParams, x0: np.ndarray, key, num_steps: int, episode_length: int,

@@ -748,6 +748,48 @@ def test_actor_step_and_deterministic_policy(mb, cuda_device):
         acting.actor_step(env, st, _policy_on_device(mb, cuda_device, bad), _dev(key, cuda_device))
 
 
+def test_ppo_policy_extras_and_normaliser(mb, cuda_device, prng_mode):
+    """PPO's generate_unroll (ppo/ppo.py:194-213): the policy also returns raw_action and log_prob
+    (ppo_network.py:66-80), and the policy network normalises observations with the running statistics."""
+    from mbpo_b200 import acting
+    from mbpo_b200.envs import wrap
+    from mbpo_b200.systems import PendulumSystem
+    E, T, L = 257, 11, 6
+    pol = orc.make_policy_params(seed=13, hidden=(64, 64))
+    mean, std = np.array([0.05, -0.1, 0.4], np.float32), np.array([0.7, 0.75, 3.5], np.float32)
+    make_policy = acting.make_ppo_inference_fn()
+    policy = make_policy(acting.PolicyParams([_dev(w, cuda_device) for w in pol.weights],
+                                             [_dev(b, cuda_device) for b in pol.biases]), obs_mean=mean, obs_std=std)
+    system = PendulumSystem()
+    env = wrap(system, system.reset(device=cuda_device).system_params, episode_length=L)
+    x0 = _random_states(E, 131)
+    key = ojr.PRNGKey(21)
+    nst, tr = acting.generate_unroll(env, env.reset(_dev(x0, cuda_device)), policy, _dev(key, cuda_device), T,
+                                     extra_fields=("truncation",))
+    pe = tr.extras["policy_extras"]
+    assert pe["raw_action"].shape == (T, E, 1) and pe["log_prob"].shape == (T, E)
+    g_obs = tr.observation.cpu().numpy()
+    k = key
+    for t in range(T):
+        ks = ojr.split(k, 2, prng_mode)
+        k_actor, k = ks[0], ks[1]                                          # acting.py:68-73
+        act, raw, logp = orc.policy_sample(pol, g_obs[t], k_actor, partitionable=prng_mode, obs_mean=mean, obs_std=std,
+                                           with_extras=True)
+        np.testing.assert_allclose(tr.action[t].cpu().numpy(), act, rtol=2e-5, atol=2e-6)
+        np.testing.assert_allclose(pe["raw_action"][t].cpu().numpy(), raw, rtol=2e-5, atol=3e-6)
+        # log_prob divides by scale and takes its log: compare with a tolerance on the standardised residual
+        np.testing.assert_allclose(pe["log_prob"][t].cpu().numpy(), logp, rtol=1e-4, atol=1e-4)
+    assert torch.equal(torch.tanh(pe["raw_action"]), tr.action)
+    # a deterministic policy returns no extras, like the reference's `{}`
+    det = make_policy(acting.PolicyParams([_dev(w, cuda_device) for w in pol.weights],
+                                          [_dev(b, cuda_device) for b in pol.biases]), deterministic=True,
+                      obs_mean=mean, obs_std=std)
+    _, trd = acting.generate_unroll(env, env.reset(_dev(x0, cuda_device)), det, _dev(key, cuda_device), 2)
+    assert trd.extras["policy_extras"] == {}
+    want = np.tanh(orc.policy_logits(pol, ((x0 - mean) / std).astype(np.float32))[:, :1])
+    np.testing.assert_allclose(trd.action[0].cpu().numpy(), want, rtol=2e-5, atol=2e-6)
+
+
 # ---------------------------------------------------------------------------------------------
 # stage 4: learned MLP-ensemble dynamics forward
 # ---------------------------------------------------------------------------------------------
