@@ -249,8 +249,13 @@ typedef struct MbpoPolicyParams {
   int32_t head, shared_noise, normalize;
   float sig_bias, sig_min, sig_max, action_clip;
   float obs_mean[4], obs_std[4];
+  /* which kernel runs the network: MBPO_ACTOR_AUTO picks the tcgen05 kernel (hidden -> hidden layers as TF32 x 3
+   * split-precision MMAs, fp32 accumulate in TMEM) for 2..3 hidden layers and the CUDA-core kernel otherwise;
+   * MBPO_ACTOR_TCGEN05 with an unsupported depth is MBPO_EUNSUPPORTED. */
+  int32_t kernel;
 } MbpoPolicyParams;
 enum { MBPO_HEAD_NORMAL_TANH = 0, MBPO_HEAD_BPTT_ACTOR = 1 };
+enum { MBPO_ACTOR_AUTO = 0, MBPO_ACTOR_CUDA_CORES = 1, MBPO_ACTOR_TCGEN05 = 2 };
 enum {
   MBPO_KEYS_SAC = 0,     /* sac/sac.py:288-292      k, k_t = split(k); policy key = k_t          */
   MBPO_KEYS_UNROLL = 1,  /* sac/acting.py:68-73     current, next = split(current); policy key = current, carry = next */

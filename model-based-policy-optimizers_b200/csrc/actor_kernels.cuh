@@ -97,6 +97,64 @@ struct ActorEnv {
   float c, s, w, th, f_c, f_s, f_w, f_th, steps, done;
 };
 
+// The policy head: turns the network's two outputs (loc, raw scale; biases already added) into the action of
+// env `e` at step t, drawing from k_actor like the reference, and emits PPO's policy_extras when asked.
+template <int PRNG>
+__device__ __forceinline__ float actor_head(const ActorArgs& a, Key2 k_actor, float mu, float raw_sc, int e, bool live,
+                                            int t) {
+  const uint32_t n_draw = a.shared_noise ? 1u : static_cast<uint32_t>(a.E);     // normal(key, (A,)) or (E, A)
+  const uint32_t i_draw = a.shared_noise ? 0u : static_cast<uint32_t>(e);
+  if (a.head == MBPO_HEAD_BPTT_ACTOR) {
+    // Actor.__call__ :137-142: sig = clip(softplus(sig + inv_softplus(init_stddev)), sig_min, sig_max);
+    // act :306-326: squash(mu) or squash(mu + normal(sample_key, mu.shape) * sig), squash = clip(tanh, +-0.999)
+    float pre = mu;
+    if (!a.deterministic) {
+      const float eps = bits_to_normal(random_bits_at<PRNG>(k_actor, n_draw, i_draw));
+      const float sig = fminf(fmaxf(softplus_exact(__fadd_rn(raw_sc, a.sig_bias)), a.sig_min), a.sig_max);
+      pre = __fadd_rn(pre, __fmul_rn(eps, sig));
+    }
+    return fminf(fmaxf(tanhf(pre), -a.action_clip), a.action_clip);
+  }
+  if (a.deterministic) return tanhf(mu);                               // mode(): tanh(loc)
+  const float eps = bits_to_normal(random_bits_at<PRNG>(k_actor, n_draw, i_draw));
+  const float scale = softplus_exact(raw_sc) + a.min_std;
+  const float raw = __fadd_rn(__fmul_rn(scale, eps), mu);              // distrax Normal.sample: scale * rnd + loc
+  if (a.raw_action_out && live) {
+    // ppo_network.py:72-80: raw_actions = sample_no_postprocessing; log_prob = Normal.log_prob(raw) -
+    // Tanh.forward_log_det_jacobian(raw), summed over the action axis (parametric_distribution.py:76-83);
+    // distrax: -0.5 * ((x - loc) / scale)^2 - (0.5 * log(2 pi) + log(scale)); 2 * (log 2 - x - softplus(-2 x))
+    const float z = __fdiv_rn(__fsub_rn(raw, mu), scale);
+    const float lp = __fsub_rn(__fmul_rn(-0.5f, __fmul_rn(z, z)), __fadd_rn(0.918938533f, logf(scale)));
+    const float ldj = __fmul_rn(2.0f, __fsub_rn(__fsub_rn(0.693147181f, raw), softplus_exact(__fmul_rn(-2.0f, raw))));
+    const size_t i = static_cast<size_t>(t) * a.E + e;
+    a.raw_action_out[i] = raw;
+    a.log_prob_out[i] = __fsub_rn(lp, ldj);
+  }
+  return tanhf(raw);
+}
+
+// The wrapped env step of env_kernels.cuh on one env's registers; returns the step's reward, sets trunc.
+template <int MATH>
+__device__ __forceinline__ float actor_env_step(const ActorArgs& a, const PendulumConsts& pc, ActorEnv& v, float u,
+                                                float ep_len, float rep, float& trunc) {
+  v.steps = (v.done != 0.0f) ? 0.0f : v.steps;
+  v.done = 0.0f;
+  float rew = 0.0f;
+  for (int r = 0; r < a.action_repeat; ++r) {
+    float rr;
+    if (MATH == MBPO_MATH_REFERENCE) pendulum_step_ref(pc, v.c, v.s, v.w, u, rr);
+    else pendulum_step_theta(pc, v.th, v.w, u, rr);
+    rew = __fadd_rn(rew, rr);
+  }
+  if (MATH != MBPO_MATH_REFERENCE) sincos_bounded(v.th, v.s, v.c);
+  v.steps = __fadd_rn(v.steps, rep);
+  const bool over = v.steps >= ep_len;
+  trunc = over ? (1.0f - v.done) : 0.0f;
+  v.done = over ? 1.0f : v.done;
+  if (over) { v.c = v.f_c; v.s = v.f_s; v.w = v.f_w; v.th = v.f_th; }
+  return rew;
+}
+
 template <int PRNG, int MATH>
 __global__ void __launch_bounds__(ACT_MAX_THREADS, 1) actor_rollout_pendulum_kernel(const __grid_constant__ ActorArgs a,
                                                                                     const ActorSmem lay) {
@@ -233,54 +291,9 @@ __global__ void __launch_bounds__(ACT_MAX_THREADS, 1) actor_rollout_pendulum_ker
     for (int q = 0; q < 2; ++q) {
       if (!half_live[q]) continue;   // warp-uniform
       ActorEnv& v = env[q];
-      float u;
-      const uint32_t n_draw = a.shared_noise ? 1u : static_cast<uint32_t>(a.E);     // normal(key, (A,)) or (E, A)
-      const uint32_t i_draw = a.shared_noise ? 0u : static_cast<uint32_t>(ee[q]);
-      if (a.head == MBPO_HEAD_BPTT_ACTOR) {
-        // Actor.__call__ :137-142: sig = clip(softplus(sig + inv_softplus(init_stddev)), sig_min, sig_max);
-        // act :306-326: squash(mu) or squash(mu + normal(sample_key, mu.shape) * sig), squash = clip(tanh, +-0.999)
-        float pre = loc[q] + b_loc;
-        if (!a.deterministic) {
-          const float eps = bits_to_normal(random_bits_at<PRNG>(k_actor, n_draw, i_draw));
-          const float sig = fminf(fmaxf(softplus_exact(__fadd_rn(raw_scale[q] + b_scale, a.sig_bias)), a.sig_min), a.sig_max);
-          pre = __fadd_rn(pre, __fmul_rn(eps, sig));
-        }
-        u = fminf(fmaxf(tanhf(pre), -a.action_clip), a.action_clip);
-      } else if (a.deterministic) {
-        u = tanhf(loc[q] + b_loc);                                       // mode(): tanh(loc)
-      } else {
-        const float eps = bits_to_normal(random_bits_at<PRNG>(k_actor, n_draw, i_draw));
-        const float scale = softplus_exact(raw_scale[q] + b_scale) + a.min_std;
-        const float mu = loc[q] + b_loc;
-        const float raw = __fadd_rn(__fmul_rn(scale, eps), mu);          // distrax Normal.sample: scale * rnd + loc
-        u = tanhf(raw);
-        if (a.raw_action_out && live[q]) {
-          // ppo_network.py:72-80: raw_actions = sample_no_postprocessing; log_prob = Normal.log_prob(raw) -
-          // Tanh.forward_log_det_jacobian(raw), summed over the action axis (parametric_distribution.py:76-83);
-          // distrax: -0.5 * ((x - loc) / scale)^2 - (0.5 * log(2 pi) + log(scale)); 2 * (log 2 - x - softplus(-2 x))
-          const float z = __fdiv_rn(__fsub_rn(raw, mu), scale);
-          const float lp = __fsub_rn(__fmul_rn(-0.5f, __fmul_rn(z, z)), __fadd_rn(0.918938533f, logf(scale)));
-          const float ldj = __fmul_rn(2.0f, __fsub_rn(__fsub_rn(0.693147181f, raw), softplus_exact(__fmul_rn(-2.0f, raw))));
-          a.raw_action_out[static_cast<size_t>(t) * E + e_idx[q]] = raw;
-          a.log_prob_out[static_cast<size_t>(t) * E + e_idx[q]] = __fsub_rn(lp, ldj);
-        }
-      }
-      // ---- wrapped env step (env_kernels.cuh) ------------------------------------------------------------
-      v.steps = (v.done != 0.0f) ? 0.0f : v.steps;
-      v.done = 0.0f;
-      float rew = 0.0f;
-      for (int r = 0; r < a.action_repeat; ++r) {
-        float rr;
-        if (MATH == MBPO_MATH_REFERENCE) pendulum_step_ref(pc, v.c, v.s, v.w, u, rr);
-        else pendulum_step_theta(pc, v.th, v.w, u, rr);
-        rew = __fadd_rn(rew, rr);
-      }
-      if (MATH != MBPO_MATH_REFERENCE) sincos_bounded(v.th, v.s, v.c);
-      v.steps = __fadd_rn(v.steps, rep);
-      const bool over = v.steps >= ep_len;
-      const float trunc = over ? (1.0f - v.done) : 0.0f;
-      v.done = over ? 1.0f : v.done;
-      if (over) { v.c = v.f_c; v.s = v.f_s; v.w = v.f_w; v.th = v.f_th; }
+      const float u = actor_head<PRNG>(a, k_actor, loc[q] + b_loc, raw_scale[q] + b_scale, ee[q], live[q], t);
+      float trunc;
+      const float rew = actor_env_step<MATH>(a, pc, v, u, ep_len, rep, trunc);
       warp_store3(tile, a.next_observation_out + (row + half_e0[q]) * 3 + lane, lane, n_valid[q], v.c, v.s, v.w);
       if (live[q]) {
         a.action_out[row + e_idx[q]] = u;

@@ -1,0 +1,294 @@
+// Policy-in-the-loop data collection with the policy network on the 5th-generation tensor cores.
+//
+// Same computation, arguments and outputs as actor_rollout_pendulum_kernel (actor_kernels.cuh: T steps of
+// actor_step, sac/acting.py:35-55, for E envs in one launch).  The hidden -> hidden layers of the policy MLP
+// (64 x 64, the GEMM-shaped part: M = envs) run as tcgen05.mma kind::tf32 with the accumulator in TMEM; the
+// reference network is float32, so every operand is split into a TF32 head and a TF32 tail
+//     a = a_hi + a_lo,  w = w_hi + w_lo,   a.w ~= a_hi.w_hi + a_lo.w_hi + a_hi.w_lo      (fp32 accumulate)
+// with both parts rounded to nearest (|a_lo| <= 2^-12 |a|): the dropped a_lo.w_lo term is 2^-24 relative, i.e.
+// the products are fp32-accurate and the actions agree with the float32 oracle to the same tolerance as the
+// CUDA-core kernel.
+//
+//   CTA           256 threads = two independent tiles of 128 envs (thread = env = TMEM lane); while one tile
+//                 waits for its MMAs the other runs its epilogue on the same SM sub-partitions
+//   A operand     activations [128 x 64] as two fp32 planes (hi, lo) in the canonical K-major no-swizzle UMMA
+//                 layout, written by the epilogue itself: 16-byte chunk kc (4 K-values) of row r at
+//                 kc * 2048 + r * 16 (SBO = 128 B, LBO = 2048 B)
+//   B operand     each hidden -> hidden weight matrix as two planes (hi, lo), element (n, k) at
+//                 (k / 4) * 1024 + n * 16 + (k % 4) * 4, resident in shared memory for the whole launch
+//   D             64 TMEM columns per tile; per layer 8 K-steps x 3 products = 24 tcgen05.mma (M128 N64 K8)
+//                 issued by one thread of the tile, tcgen05.commit -> mbarrier, tcgen05.ld.32x32b epilogue
+//   layer 0       (K = 3) and the output layer (N = 2) stay on the CUDA cores, fused into the epilogues
+//   head, PRNG, wrapped env step, Transition stores: the shared device functions of actor_kernels.cuh
+#pragma once
+#include "actor_kernels.cuh"
+#include "mlp_tc_kernels.cuh"
+
+namespace mbpo {
+namespace atc {
+
+using namespace tc;   // PTX wrappers: mbarrier, fences, umma_desc, tmem_ld32, umma_commit
+
+constexpr int TILE = 128;                 // envs per tile = TMEM lanes
+constexpr int TILES_PER_CTA = 2;
+constexpr int THREADS = TILE * TILES_PER_CTA;
+constexpr int W = ACT_W;                  // 64
+constexpr int KCH = W / 4;                // 16-byte chunks (4 fp32) along K
+constexpr uint32_t A_LBO_ = TILE * 16;    // 2048
+constexpr uint32_t W_LBO_ = W * 16;       // 1024
+constexpr uint32_t A_PLANE = TILE * W * 4;   // 32768
+constexpr uint32_t W_PLANE = W * W * 4;      // 16384
+constexpr int MAX_HH = 2;                 // hidden -> hidden layers held in shared memory (num_hidden <= 3)
+constexpr int TMEM_COLS_ = 128;           // 2 tiles x 64 fp32 columns
+
+struct Smem {
+  static constexpr uint32_t A = 0;                                         // [tile][hi, lo] planes
+  static constexpr uint32_t WH = A + TILES_PER_CTA * 2 * A_PLANE;          // [layer][hi, lo] planes
+  static constexpr uint32_t W0 = WH + MAX_HH * 2 * W_PLANE;                // float [3][64]
+  static constexpr uint32_t B0 = W0 + 3 * W * 4;                           // float [64]
+  static constexpr uint32_t BH = B0 + W * 4;                               // float [MAX_HH][64]
+  static constexpr uint32_t WO = BH + MAX_HH * W * 4;                      // float [64][2]
+  static constexpr uint32_t BO = WO + W * 2 * 4;                           // float [2] (+ pad)
+  static constexpr uint32_t TILES = BO + 16;                               // float [8 warps][96]: row transposition
+  static constexpr uint32_t BARS = TILES + (THREADS / 32) * 96 * 4;        // mma_done[2]
+  static constexpr uint32_t TMEM_PTR = BARS + 16;
+  static constexpr uint32_t TOTAL = TMEM_PTR + 16;
+};
+static_assert(Smem::TOTAL <= 227 * 1024, "tensor-core actor kernel shared memory plan exceeds 227 KB");
+
+// Instruction descriptor for kind::tf32: D = F32 (1 @ [4,6)), A = B = TF32 (2 @ [7,10), [10,13)), K-major,
+// N >> 3 @ [17,23), M >> 4 @ [24,29).
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 128-thread barrier of one tile (named barriers 1 and 2; barrier 0 is __syncthreads)
+__device__ __forceinline__ void tile_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(TILE) : "memory"); }
+
+// v ~= hi + lo, both exactly representable in TF32 (low 13 mantissa bits clear): hi = v rounded to nearest,
+// so |lo| <= 2^-12 |v| and rounding lo loses <= 2^-24 |v| -- the three-product sum is fp32-accurate.
+__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+  lo = __uint_as_float((__float_as_uint(v - hi) + 0x1000u) & 0xFFFFE000u);
+}
+
+template <int PRNG, int MATH>
+__global__ void __launch_bounds__(THREADS, 1) actor_rollout_tc_kernel(const __grid_constant__ ActorArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = tid / TILE, r = tid % TILE;            // tile of the CTA, row of the tile
+  float* s_w0 = reinterpret_cast<float*>(smem + Smem::W0);
+  float* s_b0 = reinterpret_cast<float*>(smem + Smem::B0);
+  float* s_bh = reinterpret_cast<float*>(smem + Smem::BH);
+  float* s_wo = reinterpret_cast<float*>(smem + Smem::WO);
+  float* s_bo = reinterpret_cast<float*>(smem + Smem::BO);
+  float* tile = reinterpret_cast<float*>(smem + Smem::TILES) + warp * 96;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::BARS);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + Smem::TMEM_PTR);
+  const int L = a.num_hidden, HH = L - 1;
+
+  // ---- one-time setup: TMEM, mbarriers, policy parameters -> shared memory ---------------------------------
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                 "r"(TMEM_COLS_));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_barrier_init();
+  }
+  for (int l = 0; l < HH; ++l) {
+    const float* wl = a.w[l + 1];                        // flax Dense kernel [in = k][out = n]
+    uint8_t* hi = smem + Smem::WH + (l * 2 + 0) * W_PLANE;
+    uint8_t* lo = smem + Smem::WH + (l * 2 + 1) * W_PLANE;
+    for (int i = tid; i < W * W; i += THREADS) {
+      const int k = i / W, n = i % W;
+      float h, t;
+      split_tf32(wl[i], h, t);
+      const uint32_t off = (k / 4) * W_LBO_ + n * 16 + (k % 4) * 4;
+      *reinterpret_cast<float*>(hi + off) = h;
+      *reinterpret_cast<float*>(lo + off) = t;
+    }
+    for (int i = tid; i < W; i += THREADS) s_bh[l * W + i] = a.b[l + 1][i];
+  }
+  for (int i = tid; i < 3 * W; i += THREADS) s_w0[i] = a.w[0][i];
+  for (int i = tid; i < W; i += THREADS) s_b0[i] = a.b[0][i];
+  for (int i = tid; i < W * 2; i += THREADS) s_wo[i] = a.w[L][i];
+  if (tid < 2) s_bo[tid] = a.b[L][tid];
+  fence_proxy_async();          // the weight planes are read by the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  const int tile_idx = blockIdx.x * TILES_PER_CTA + g;
+  const int tile_e0 = tile_idx * TILE;
+  if (tile_e0 < a.E) {          // tile-uniform: an idle tile skips the loop (it shares no barrier with the other)
+    const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + g * W;   // lanes, columns
+    const uint32_t tmem_d = tmem_base + g * W;
+    uint8_t* a_hi = smem + Smem::A + (g * 2 + 0) * A_PLANE;
+    uint8_t* a_lo = smem + Smem::A + (g * 2 + 1) * A_PLANE;
+    const uint32_t a_hi_addr = smem_u32(a_hi), a_lo_addr = smem_u32(a_lo);
+    const uint32_t wh_addr = smem_u32(smem + Smem::WH);
+    uint64_t* bar_mma = &bars[g];
+    uint32_t phase = 0;
+    constexpr uint32_t IDESC = umma_idesc_tf32(TILE, W);
+
+    const PendulumConsts pc(a.sys);
+    const float ep_len = static_cast<float>(a.episode_length);
+    const float rep = static_cast<float>(a.action_repeat);
+    const size_t E = static_cast<size_t>(a.E);
+    const int e = tile_e0 + r;
+    const bool live = e < a.E;
+    const int ee = live ? e : a.E - 1;                 // dead rows shadow the last env, their stores are masked
+    const int warp_e0 = e - lane;
+    const int rem = a.E - warp_e0;
+    const int n_valid = (rem < 32 ? (rem > 0 ? rem : 0) : 32) * 3;
+    ActorEnv v;
+    v.c = a.obs[3 * ee]; v.s = a.obs[3 * ee + 1]; v.w = a.obs[3 * ee + 2];
+    v.f_c = a.first_obs[3 * ee]; v.f_s = a.first_obs[3 * ee + 1]; v.f_w = a.first_obs[3 * ee + 2];
+    v.steps = a.steps[ee]; v.done = a.done[ee];
+    v.th = (MATH == MBPO_MATH_REFERENCE) ? 0.0f : atan2_bounded(v.s, v.c);
+    v.f_th = (MATH == MBPO_MATH_REFERENCE) ? 0.0f : atan2_bounded(v.f_s, v.f_c);
+    Key2 key{a.key_in[0], a.key_in[1]};
+
+#pragma unroll 1
+    for (int t = 0; t < a.T; ++t) {
+      // ---- key plumbing (every thread carries the same keys) ----------------------------------------------
+      Key2 k_actor = key;
+      if (a.key_convention != 2) {
+        Key2 first, second;
+        split2<PRNG>(key, first, second);
+        if (a.key_convention == 0) { key = first; k_actor = second; }   // sac.py:290
+        else { k_actor = first; key = second; }                          // acting.py:70
+      }
+      // ---- layer 0 on the CUDA cores: thread = env, 4 hidden units per 16-byte chunk ----------------------------
+      float xin[3] = {v.c, v.s, v.w};
+      if (a.normalize) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) xin[i] = __fdiv_rn(__fsub_rn(xin[i], a.obs_mean[i]), a.obs_std[i]);
+      }
+      float loc = 0.0f, raw_sc = 0.0f;
+#pragma unroll 4
+      for (int kc = 0; kc < KCH; ++kc) {
+        const float4 r0 = *reinterpret_cast<const float4*>(s_w0 + kc * 4);
+        const float4 r1 = *reinterpret_cast<const float4*>(s_w0 + W + kc * 4);
+        const float4 r2 = *reinterpret_cast<const float4*>(s_w0 + 2 * W + kc * 4);
+        const float4 bb = *reinterpret_cast<const float4*>(s_b0 + kc * 4);
+        const float w0r[4] = {r0.x, r0.y, r0.z, r0.w}, w1r[4] = {r1.x, r1.y, r1.z, r1.w};
+        const float w2r[4] = {r2.x, r2.y, r2.z, r2.w}, b0r[4] = {bb.x, bb.y, bb.z, bb.w};
+        float hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          // the same float operations as the CUDA-core kernel's first layer
+          const float h = swish_exact(fmaf(xin[2], w2r[i], fmaf(xin[1], w1r[i], xin[0] * w0r[i])) + b0r[i]);
+          if (HH == 0) {          // no hidden -> hidden layer: straight to the output layer (not dispatched today)
+            loc = fmaf(h, s_wo[(kc * 4 + i) * 2], loc);
+            raw_sc = fmaf(h, s_wo[(kc * 4 + i) * 2 + 1], raw_sc);
+          }
+          split_tf32(h, hi[i], lo[i]);
+        }
+        *reinterpret_cast<float4*>(a_hi + kc * A_LBO_ + r * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(a_lo + kc * A_LBO_ + r * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      fence_proxy_async();      // generic-proxy writes of A -> visible to the tensor core
+      tile_sync(g);
+
+#pragma unroll 1
+      for (int l = 0; l < HH; ++l) {
+        // ---- 24 x tcgen05.mma (M128 N64 K8): hi.hi + lo.hi + hi.lo, one issuing thread per tile --------------------
+        if (r == 0) {
+          tc_fence_after();
+          const uint32_t w_hi = wh_addr + (l * 2 + 0) * W_PLANE, w_lo = wh_addr + (l * 2 + 1) * W_PLANE;
+#pragma unroll
+          for (int ks = 0; ks < W / 8; ++ks) {
+            const uint64_t da_hi = umma_desc(a_hi_addr + ks * 2 * A_LBO_, A_LBO_, SBO);
+            const uint64_t da_lo = umma_desc(a_lo_addr + ks * 2 * A_LBO_, A_LBO_, SBO);
+            const uint64_t db_hi = umma_desc(w_hi + ks * 2 * W_LBO_, W_LBO_, SBO);
+            const uint64_t db_lo = umma_desc(w_lo + ks * 2 * W_LBO_, W_LBO_, SBO);
+            umma_tf32_ss(tmem_d, da_lo, db_hi, IDESC, ks > 0 ? 1u : 0u);     // small terms first
+            umma_tf32_ss(tmem_d, da_hi, db_lo, IDESC, 1u);
+            umma_tf32_ss(tmem_d, da_hi, db_hi, IDESC, 1u);
+          }
+          umma_commit(bar_mma);   // implies tcgen05.fence::before_thread_sync
+        }
+        mbar_wait(bar_mma, phase);   // accumulator complete; the A planes are free again
+        phase ^= 1;
+        tc_fence_after();
+        // ---- epilogue: TMEM -> registers, bias + swish, next A operand or the output layer -------------------------
+        const float* bias = s_bh + l * W;
+        const bool last = (l == HH - 1);
+#pragma unroll
+        for (int c = 0; c < W / 32; ++c) {
+          uint32_t acc[32];
+          tmem_ld32(tmem_acc + c * 32, acc);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float h[4], hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int col = c * 32 + q * 4 + i;
+              h[i] = swish_exact(__uint_as_float(acc[q * 4 + i]) + bias[col]);
+              if (last) {
+                const float2 wo = *reinterpret_cast<const float2*>(s_wo + col * 2);
+                loc = fmaf(h[i], wo.x, loc);
+                raw_sc = fmaf(h[i], wo.y, raw_sc);
+              } else {
+                split_tf32(h[i], hi[i], lo[i]);
+              }
+            }
+            if (!last) {
+              const int kc = c * 8 + q;
+              *reinterpret_cast<float4*>(a_hi + kc * A_LBO_ + r * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<float4*>(a_lo + kc * A_LBO_ + r * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          }
+        }
+        tc_fence_before();      // order the tcgen05.ld above before the next MMA overwrites the accumulator
+        fence_proxy_async();
+        tile_sync(g);
+      }
+      // ---- head, wrapped env step, Transition ------------------------------------------------------------------
+      const float u = actor_head<PRNG>(a, k_actor, loc + s_bo[0], raw_sc + s_bo[1], ee, live, t);
+      float trunc;
+      const float rew = actor_env_step<MATH>(a, pc, v, u, ep_len, rep, trunc);
+      const size_t row = static_cast<size_t>(t) * E;
+      if (warp_e0 < a.E)        // warp-uniform
+        warp_store3(tile, a.next_observation_out + (row + warp_e0) * 3 + lane, lane, n_valid, v.c, v.s, v.w);
+      if (live) {
+        a.action_out[row + e] = u;
+        a.reward_out[row + e] = rew;
+        a.discount_out[row + e] = 1.0f - v.done;
+        a.truncation_out[row + e] = trunc;
+      }
+    }
+    if (live) {
+      a.obs[3 * e] = v.c; a.obs[3 * e + 1] = v.s; a.obs[3 * e + 2] = v.w;
+      a.steps[e] = v.steps;
+      a.done[e] = v.done;
+    }
+    if (tile_idx == 0 && r == 0 && a.key_out) { a.key_out[0] = key.k0; a.key_out[1] = key.k1; }
+  }
+
+  // ---- teardown ----------------------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS_));
+  }
+}
+
+}  // namespace atc
+}  // namespace mbpo

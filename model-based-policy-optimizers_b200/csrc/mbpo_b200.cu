@@ -15,6 +15,7 @@
 #include "mlp_kernels.cuh"
 #include "mlp_tc_kernels.cuh"
 #include "actor_kernels.cuh"
+#include "actor_tc_kernels.cuh"
 #include "adjoint_kernels.cuh"
 #include "ensemble_pp_kernels.cuh"
 #include "plan_dispatch.h"
@@ -670,6 +671,20 @@ int launch_actor(const mbpo::ActorArgs& a, cudaStream_t st) {
   kernel<<<blocks, threads, smem, st>>>(a, lay);
   return check_launch("actor_rollout_pendulum_kernel");
 }
+
+template <int PRNG, int MATH>
+int launch_actor_tc(const mbpo::ActorArgs& a, cudaStream_t st) {
+  using namespace mbpo;
+  auto kernel = atc::actor_rollout_tc_kernel<PRNG, MATH>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(atc::Smem::TOTAL));
+  if (e != cudaSuccess)
+    return fail(MBPO_ECUDA, "actor_rollout (tcgen05): smem attribute (%u B): %s", atc::Smem::TOTAL, cudaGetErrorString(e));
+  const int tiles = (a.E + atc::TILE - 1) / atc::TILE;
+  const unsigned blocks = static_cast<unsigned>((tiles + atc::TILES_PER_CTA - 1) / atc::TILES_PER_CTA);
+  kernel<<<blocks, atc::THREADS, atc::Smem::TOTAL, st>>>(a);
+  return check_launch("actor_rollout_tc_kernel");
+}
 }  // namespace
 }  // extern "C++"
 
@@ -746,6 +761,20 @@ int mbpo_actor_rollout_extras(int system_kind, const void* sys_params_host, int 
   a.next_observation_out = next_observation_out; a.truncation_out = truncation_out; a.key_out = key_out;
   a.raw_action_out = raw_action_out; a.log_prob_out = log_prob_out;
   cudaStream_t st = as_stream(stream);
+  MBPO_REQUIRE(policy_host->kernel >= MBPO_ACTOR_AUTO && policy_host->kernel <= MBPO_ACTOR_TCGEN05,
+               "actor_rollout: bad policy kernel selector %d", policy_host->kernel);
+  const bool tc_ok = a.num_hidden >= 2 && a.num_hidden <= 1 + mbpo::atc::MAX_HH;
+  if (policy_host->kernel == MBPO_ACTOR_TCGEN05 && !tc_ok)
+    return fail(MBPO_EUNSUPPORTED, "actor_rollout: the tcgen05 kernel holds 1..%d hidden -> hidden layers (got %d hidden layers)",
+                mbpo::atc::MAX_HH, a.num_hidden);
+  if (tc_ok && policy_host->kernel != MBPO_ACTOR_CUDA_CORES) {
+    switch (prng_mode * 2 + math_mode) {
+      case 0: return launch_actor_tc<0, 0>(a, st);
+      case 1: return launch_actor_tc<0, 1>(a, st);
+      case 2: return launch_actor_tc<1, 0>(a, st);
+      default: return launch_actor_tc<1, 1>(a, st);
+    }
+  }
   switch (prng_mode * 2 + math_mode) {
     case 0: return launch_actor<0, 0>(a, st);
     case 1: return launch_actor<0, 1>(a, st);

@@ -663,23 +663,26 @@ def test_env_unroll_ragged_episode_pieces(mb, cuda_device, math_mode, E, T, epis
 # ---------------------------------------------------------------------------------------------
 # policy in the env loop: actor_step / generate_unroll / get_experience
 # ---------------------------------------------------------------------------------------------
-def _policy_on_device(mb, cuda_device, pol, deterministic=False):
+def _policy_on_device(mb, cuda_device, pol, deterministic=False, kernel="auto"):
     from mbpo_b200.acting import Policy, PolicyParams
     return Policy(PolicyParams(weights=[_dev(w, cuda_device) for w in pol.weights],
-                               biases=[_dev(b, cuda_device) for b in pol.biases], min_std=pol.min_std), deterministic)
+                               biases=[_dev(b, cuda_device) for b in pol.biases], min_std=pol.min_std), deterministic,
+                  kernel=kernel)
 
 
 @pytest.mark.parametrize("convention", ["sac", "unroll"])
-@pytest.mark.parametrize("hidden", [(64, 64, 64), (64,)])
-def test_actor_rollout_vs_oracle(mb, cuda_device, prng_mode, math_mode, convention, hidden):
+@pytest.mark.parametrize("hidden,kernel", [((64, 64, 64), "tcgen05"), ((64, 64, 64), "cuda_cores"), ((64, 64), "tcgen05"),
+                                           ((64,), "auto")])
+def test_actor_rollout_vs_oracle(mb, cuda_device, prng_mode, math_mode, convention, hidden, kernel):
     """T steps of policy forward + NormalTanh sample + wrapped env step in one launch, per step against the
-    oracle teacher-forced on the GPU's observations; the PRNG carry key is bit exact."""
+    oracle teacher-forced on the GPU's observations; the PRNG carry key is bit exact.  Both kernels: the
+    float32 network on the CUDA cores, and the hidden -> hidden layers as TF32 x 3 split-precision tcgen05 MMAs."""
     from mbpo_b200 import acting
     from mbpo_b200.envs import wrap
     from mbpo_b200.systems import PendulumSystem
     E, T, L = 333, 23, 7
     pol = orc.make_policy_params(seed=7, hidden=hidden)
-    policy = _policy_on_device(mb, cuda_device, pol)
+    policy = _policy_on_device(mb, cuda_device, pol, kernel=kernel)
     system = PendulumSystem()
     env = wrap(system, system.reset(device=cuda_device).system_params, episode_length=L)
     x0 = _random_states(E, 91)
