@@ -9,16 +9,19 @@
 // the products are fp32-accurate and the actions agree with the float32 oracle to the same tolerance as the
 // CUDA-core kernel.
 //
-//   CTA           256 threads = two independent tiles of 128 envs (thread = env = TMEM lane); while one tile
-//                 waits for its MMAs the other runs its epilogue on the same SM sub-partitions
-//   A operand     activations [128 x 64] as two fp32 planes (hi, lo) in the canonical K-major no-swizzle UMMA
-//                 layout, written by the epilogue itself: 16-byte chunk kc (4 K-values) of row r at
-//                 kc * 2048 + r * 16 (SBO = 128 B, LBO = 2048 B)
+//   CTA           512 threads = four independent tiles of 128 envs (thread = env = TMEM lane).  A tile's step is a
+//                 chain of short phases separated by tensor-core and barrier latencies; four tiles per SM (four
+//                 warps per scheduler) are what keeps the issue slots busy
+//   A operand     a tile never holds a whole [128 x 64] activation matrix: the producer (layer 0 on the CUDA
+//                 cores, or the epilogue of the previous accumulator) emits 16 columns at a time into a ring of
+//                 two 16 KB slots (hi and lo planes, canonical K-major no-swizzle UMMA layout: 16-byte chunk kc of
+//                 row r at kc * 2048 + r * 16), the six MMAs that consume a slot are issued as soon as the tile has
+//                 written it, and a tcgen05.commit per slot tells the producer when it may be overwritten -- the
+//                 MMAs of one quarter run under the production of the next
 //   B operand     each hidden -> hidden weight matrix as two planes (hi, lo), element (n, k) at
 //                 (k / 4) * 1024 + n * 16 + (k % 4) * 4, resident in shared memory for the whole launch
-//   D             64 TMEM columns per tile; per layer 8 K-steps x 3 products = 24 tcgen05.mma (M128 N64 K8)
-//                 issued by one thread of the tile, tcgen05.commit -> mbarrier, tcgen05.ld.32x32b epilogue
-//   layer 0       (K = 3) and the output layer (N = 2) stay on the CUDA cores, fused into the epilogues
+//   D             two 64-column TMEM accumulators per tile, alternating between layers (512 columns per CTA)
+//   layer 0       (K = 3) and the output layer (N = 2) stay on the CUDA cores, fused into the producers
 //   head, PRNG, wrapped env step, Transition stores: the shared device functions of actor_kernels.cuh
 #pragma once
 #include "actor_kernels.cuh"
@@ -27,31 +30,34 @@
 namespace mbpo {
 namespace atc {
 
-using namespace tc;   // PTX wrappers: mbarrier, fences, umma_desc, tmem_ld32, umma_commit
+using namespace tc;   // PTX wrappers: mbarrier, fences, umma_desc, umma_commit
 
 constexpr int TILE = 128;                 // envs per tile = TMEM lanes
-constexpr int TILES_PER_CTA = 2;
+constexpr int TILES_PER_CTA = 4;
 constexpr int THREADS = TILE * TILES_PER_CTA;
 constexpr int W = ACT_W;                  // 64
-constexpr int KCH = W / 4;                // 16-byte chunks (4 fp32) along K
-constexpr uint32_t A_LBO_ = TILE * 16;    // 2048
-constexpr uint32_t W_LBO_ = W * 16;       // 1024
-constexpr uint32_t A_PLANE = TILE * W * 4;   // 32768
-constexpr uint32_t W_PLANE = W * W * 4;      // 16384
+constexpr int QC = 16;                    // columns a producer emits per ring slot (two K = 8 MMA steps)
+constexpr int QUARTERS = W / QC;
+constexpr uint32_t A_LBO_ = TILE * 16;    // 2048: next 16-byte K-chunk of A
+constexpr uint32_t W_LBO_ = W * 16;       // 1024: next 16-byte K-chunk of W
+constexpr uint32_t SLOT_PLANE = (QC / 4) * A_LBO_;   // 8192: one plane (hi or lo) of a slot
+constexpr uint32_t SLOT_BYTES = 2 * SLOT_PLANE;      // 16384
+constexpr int SLOTS = 2;
+constexpr uint32_t W_PLANE = W * W * 4;   // 16384
 constexpr int MAX_HH = 2;                 // hidden -> hidden layers held in shared memory (num_hidden <= 3)
-constexpr int TMEM_COLS_ = 128;           // 2 tiles x 64 fp32 columns
+constexpr int TMEM_COLS_ = 512;           // 4 tiles x 2 accumulators x 64 fp32 columns
 
 struct Smem {
-  static constexpr uint32_t A = 0;                                         // [tile][hi, lo] planes
-  static constexpr uint32_t WH = A + TILES_PER_CTA * 2 * A_PLANE;          // [layer][hi, lo] planes
+  static constexpr uint32_t A = 0;                                         // [tile][slot][hi, lo]
+  static constexpr uint32_t WH = A + TILES_PER_CTA * SLOTS * SLOT_BYTES;   // [layer][hi, lo] planes
   static constexpr uint32_t W0 = WH + MAX_HH * 2 * W_PLANE;                // float [3][64]
   static constexpr uint32_t B0 = W0 + 3 * W * 4;                           // float [64]
   static constexpr uint32_t BH = B0 + W * 4;                               // float [MAX_HH][64]
   static constexpr uint32_t WO = BH + MAX_HH * W * 4;                      // float [64][2]
   static constexpr uint32_t BO = WO + W * 2 * 4;                           // float [2] (+ pad)
-  static constexpr uint32_t TILES = BO + 16;                               // float [8 warps][96]: row transposition
-  static constexpr uint32_t BARS = TILES + (THREADS / 32) * 96 * 4;        // mma_done[2]
-  static constexpr uint32_t TMEM_PTR = BARS + 16;
+  static constexpr uint32_t TILES = BO + 16;                               // float [16 warps][96]: row transposition
+  static constexpr uint32_t BARS = TILES + (THREADS / 32) * 96 * 4;        // per tile: slot_free[2], layer_done
+  static constexpr uint32_t TMEM_PTR = BARS + TILES_PER_CTA * 4 * 8;
   static constexpr uint32_t TOTAL = TMEM_PTR + 16;
 };
 static_assert(Smem::TOTAL <= 227 * 1024, "tensor-core actor kernel shared memory plan exceeds 227 KB");
@@ -73,7 +79,16 @@ __device__ __forceinline__ void umma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, u
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// 128-thread barrier of one tile (named barriers 1 and 2; barrier 0 is __syncthreads)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// 128-thread barrier of one tile (named barriers 1..4; barrier 0 is __syncthreads)
 __device__ __forceinline__ void tile_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(TILE) : "memory"); }
 
 // v ~= hi + lo, both exactly representable in TF32 (low 13 mantissa bits clear): hi = v rounded to nearest,
@@ -94,7 +109,7 @@ __global__ void __launch_bounds__(THREADS, 1) actor_rollout_tc_kernel(const __gr
   float* s_wo = reinterpret_cast<float*>(smem + Smem::WO);
   float* s_bo = reinterpret_cast<float*>(smem + Smem::BO);
   float* tile = reinterpret_cast<float*>(smem + Smem::TILES) + warp * 96;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::BARS);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::BARS) + g * 4;   // slot_free[0], slot_free[1], layer_done
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + Smem::TMEM_PTR);
   const int L = a.num_hidden, HH = L - 1;
 
@@ -104,9 +119,10 @@ __global__ void __launch_bounds__(THREADS, 1) actor_rollout_tc_kernel(const __gr
                  "r"(TMEM_COLS_));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  if (tid == 0) {
+  if (r == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
     fence_barrier_init();
   }
   for (int l = 0; l < HH; ++l) {
@@ -135,16 +151,16 @@ __global__ void __launch_bounds__(THREADS, 1) actor_rollout_tc_kernel(const __gr
 
   const int tile_idx = blockIdx.x * TILES_PER_CTA + g;
   const int tile_e0 = tile_idx * TILE;
-  if (tile_e0 < a.E) {          // tile-uniform: an idle tile skips the loop (it shares no barrier with the other)
-    const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + g * W;   // lanes, columns
-    const uint32_t tmem_d = tmem_base + g * W;
-    uint8_t* a_hi = smem + Smem::A + (g * 2 + 0) * A_PLANE;
-    uint8_t* a_lo = smem + Smem::A + (g * 2 + 1) * A_PLANE;
-    const uint32_t a_hi_addr = smem_u32(a_hi), a_lo_addr = smem_u32(a_lo);
-    const uint32_t wh_addr = smem_u32(smem + Smem::WH);
-    uint64_t* bar_mma = &bars[g];
-    uint32_t phase = 0;
+  if (tile_e0 < a.E) {          // tile-uniform: an idle tile skips the loop (tiles share no barrier in it)
+    const uint32_t tmem_tile = tmem_base + g * 2 * W;                                        // two accumulators
+    const uint32_t tmem_rd = tmem_tile + (static_cast<uint32_t>((warp & 3) * 32) << 16);    // this warp's 32 lanes
+    uint8_t* ring = smem + Smem::A + g * SLOTS * SLOT_BYTES;
+    // descriptors: only the start-address field (16-byte units, bits [0,14)) varies
+    const uint64_t da0 = umma_desc(smem_u32(ring), A_LBO_, SBO);
+    const uint64_t db0 = umma_desc(smem_u32(smem + Smem::WH), W_LBO_, SBO);
     constexpr uint32_t IDESC = umma_idesc_tf32(TILE, W);
+    uint32_t uses = 0;          // ring slots written so far (slot = uses & 1)
+    uint32_t layer_phase = 0;
 
     const PendulumConsts pc(a.sys);
     const float ep_len = static_cast<float>(a.episode_length);
@@ -174,91 +190,94 @@ __global__ void __launch_bounds__(THREADS, 1) actor_rollout_tc_kernel(const __gr
         if (a.key_convention == 0) { key = first; k_actor = second; }   // sac.py:290
         else { k_actor = first; key = second; }                          // acting.py:70
       }
-      // ---- layer 0 on the CUDA cores: thread = env, 4 hidden units per 16-byte chunk ----------------------------
       float xin[3] = {v.c, v.s, v.w};
       if (a.normalize) {
 #pragma unroll
         for (int i = 0; i < 3; ++i) xin[i] = __fdiv_rn(__fsub_rn(xin[i], a.obs_mean[i]), a.obs_std[i]);
       }
       float loc = 0.0f, raw_sc = 0.0f;
-#pragma unroll 4
-      for (int kc = 0; kc < KCH; ++kc) {
-        const float4 r0 = *reinterpret_cast<const float4*>(s_w0 + kc * 4);
-        const float4 r1 = *reinterpret_cast<const float4*>(s_w0 + W + kc * 4);
-        const float4 r2 = *reinterpret_cast<const float4*>(s_w0 + 2 * W + kc * 4);
-        const float4 bb = *reinterpret_cast<const float4*>(s_b0 + kc * 4);
-        const float w0r[4] = {r0.x, r0.y, r0.z, r0.w}, w1r[4] = {r1.x, r1.y, r1.z, r1.w};
-        const float w2r[4] = {r2.x, r2.y, r2.z, r2.w}, b0r[4] = {bb.x, bb.y, bb.z, bb.w};
-        float hi[4], lo[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          // the same float operations as the CUDA-core kernel's first layer
-          const float h = swish_exact(fmaf(xin[2], w2r[i], fmaf(xin[1], w1r[i], xin[0] * w0r[i])) + b0r[i]);
-          if (HH == 0) {          // no hidden -> hidden layer: straight to the output layer (not dispatched today)
-            loc = fmaf(h, s_wo[(kc * 4 + i) * 2], loc);
-            raw_sc = fmaf(h, s_wo[(kc * 4 + i) * 2 + 1], raw_sc);
-          }
-          split_tf32(h, hi[i], lo[i]);
-        }
-        *reinterpret_cast<float4*>(a_hi + kc * A_LBO_ + r * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(a_lo + kc * A_LBO_ + r * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-      }
-      fence_proxy_async();      // generic-proxy writes of A -> visible to the tensor core
-      tile_sync(g);
 
+      // stage s produces the A operand of hidden -> hidden layer s: from layer 0 on the CUDA cores (s = 0) or from
+      // accumulator (s - 1) & 1; its MMAs accumulate into accumulator s & 1.  Stage HH is the output layer.
 #pragma unroll 1
-      for (int l = 0; l < HH; ++l) {
-        // ---- 24 x tcgen05.mma (M128 N64 K8): hi.hi + lo.hi + hi.lo, one issuing thread per tile --------------------
-        if (r == 0) {
+      for (int s = 0; s <= HH; ++s) {
+        const bool to_mma = s < HH;
+        const float* bias = s_bh + (s - 1) * W;
+        const uint32_t acc_src = tmem_rd + ((s - 1) & 1) * W;
+#pragma unroll 1
+        for (int qd = 0; qd < QUARTERS; ++qd) {
+          float h[QC];
+          if (s == 0) {
+            // ---- layer 0: the same float operations as the CUDA-core kernel's first layer -------------------------
+#pragma unroll
+            for (int j4 = 0; j4 < QC / 4; ++j4) {
+              const int c0 = qd * QC + j4 * 4;
+              const float4 r0 = *reinterpret_cast<const float4*>(s_w0 + c0);
+              const float4 r1 = *reinterpret_cast<const float4*>(s_w0 + W + c0);
+              const float4 r2 = *reinterpret_cast<const float4*>(s_w0 + 2 * W + c0);
+              const float4 bb = *reinterpret_cast<const float4*>(s_b0 + c0);
+              const float w0r[4] = {r0.x, r0.y, r0.z, r0.w}, w1r[4] = {r1.x, r1.y, r1.z, r1.w};
+              const float w2r[4] = {r2.x, r2.y, r2.z, r2.w}, b0r[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                h[j4 * 4 + i] = swish_exact(fmaf(xin[2], w2r[i], fmaf(xin[1], w1r[i], xin[0] * w0r[i])) + b0r[i]);
+            }
+          } else {
+            // ---- epilogue of the previous layer: 16 accumulator columns, bias + swish ---------------------------
+            uint32_t acc[QC];
+            tmem_ld16(acc_src + qd * QC, acc);
+#pragma unroll
+            for (int i = 0; i < QC; ++i) h[i] = swish_exact(__uint_as_float(acc[i]) + bias[qd * QC + i]);
+          }
+          if (!to_mma) {        // output layer on the CUDA cores, float32
+#pragma unroll
+            for (int i = 0; i < QC; ++i) {
+              const float2 wo = *reinterpret_cast<const float2*>(s_wo + (qd * QC + i) * 2);
+              loc = fmaf(h[i], wo.x, loc);
+              raw_sc = fmaf(h[i], wo.y, raw_sc);
+            }
+            continue;
+          }
+          // ---- hi / lo planes of the 16 columns into the ring slot ----------------------------------------------------
+          const uint32_t slot = uses & 1u;
+          if (uses >= SLOTS) mbar_wait(&bars[slot], ((uses >> 1) - 1u) & 1u);   // the MMAs that read it have retired
+          uint8_t* dst = ring + slot * SLOT_BYTES + r * 16;
+#pragma unroll
+          for (int j4 = 0; j4 < QC / 4; ++j4) {
+            float hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split_tf32(h[j4 * 4 + i], hi[i], lo[i]);
+            *reinterpret_cast<float4*>(dst + j4 * A_LBO_) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(dst + SLOT_PLANE + j4 * A_LBO_) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+          }
+          fence_proxy_async();      // generic-proxy writes of A -> visible to the tensor core
+          tile_sync(g);
+          if (r == 0) {
+            // ---- 6 x tcgen05.mma (M128 N64 K8): lo.hi + hi.lo + hi.hi for the two K-steps of this slot ------------------
+            tc_fence_after();
+            const uint32_t d = tmem_tile + (s & 1) * W;
+            const uint64_t a_hi = da0 + ((slot * SLOT_BYTES) >> 4), a_lo = a_hi + (SLOT_PLANE >> 4);
+            const uint64_t b_hi = db0 + ((static_cast<uint32_t>(s) * 2u * W_PLANE + qd * 4u * W_LBO_) >> 4);
+            const uint64_t b_lo = b_hi + (W_PLANE >> 4);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const uint64_t ao = static_cast<uint64_t>((j * 2 * A_LBO_) >> 4), bo = static_cast<uint64_t>((j * 2 * W_LBO_) >> 4);
+              umma_tf32_ss(d, a_lo + ao, b_hi + bo, IDESC, (qd | j) ? 1u : 0u);     // small terms first
+              umma_tf32_ss(d, a_hi + ao, b_lo + bo, IDESC, 1u);
+              umma_tf32_ss(d, a_hi + ao, b_hi + bo, IDESC, 1u);
+            }
+            umma_commit(&bars[slot]);                       // slot free when these MMAs have read it
+            if (qd == QUARTERS - 1) umma_commit(&bars[2]);  // accumulator s & 1 complete
+          }
+          ++uses;
+        }
+        if (to_mma) {
+          mbar_wait(&bars[2], layer_phase);
+          layer_phase ^= 1u;
           tc_fence_after();
-          const uint32_t w_hi = wh_addr + (l * 2 + 0) * W_PLANE, w_lo = wh_addr + (l * 2 + 1) * W_PLANE;
-#pragma unroll
-          for (int ks = 0; ks < W / 8; ++ks) {
-            const uint64_t da_hi = umma_desc(a_hi_addr + ks * 2 * A_LBO_, A_LBO_, SBO);
-            const uint64_t da_lo = umma_desc(a_lo_addr + ks * 2 * A_LBO_, A_LBO_, SBO);
-            const uint64_t db_hi = umma_desc(w_hi + ks * 2 * W_LBO_, W_LBO_, SBO);
-            const uint64_t db_lo = umma_desc(w_lo + ks * 2 * W_LBO_, W_LBO_, SBO);
-            umma_tf32_ss(tmem_d, da_lo, db_hi, IDESC, ks > 0 ? 1u : 0u);     // small terms first
-            umma_tf32_ss(tmem_d, da_hi, db_lo, IDESC, 1u);
-            umma_tf32_ss(tmem_d, da_hi, db_hi, IDESC, 1u);
-          }
-          umma_commit(bar_mma);   // implies tcgen05.fence::before_thread_sync
+        } else {
+          tc_fence_before();      // order this step's tcgen05.ld before the next step's MMAs into the same columns
         }
-        mbar_wait(bar_mma, phase);   // accumulator complete; the A planes are free again
-        phase ^= 1;
-        tc_fence_after();
-        // ---- epilogue: TMEM -> registers, bias + swish, next A operand or the output layer -------------------------
-        const float* bias = s_bh + l * W;
-        const bool last = (l == HH - 1);
-#pragma unroll
-        for (int c = 0; c < W / 32; ++c) {
-          uint32_t acc[32];
-          tmem_ld32(tmem_acc + c * 32, acc);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float h[4], hi[4], lo[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int col = c * 32 + q * 4 + i;
-              h[i] = swish_exact(__uint_as_float(acc[q * 4 + i]) + bias[col]);
-              if (last) {
-                const float2 wo = *reinterpret_cast<const float2*>(s_wo + col * 2);
-                loc = fmaf(h[i], wo.x, loc);
-                raw_sc = fmaf(h[i], wo.y, raw_sc);
-              } else {
-                split_tf32(h[i], hi[i], lo[i]);
-              }
-            }
-            if (!last) {
-              const int kc = c * 8 + q;
-              *reinterpret_cast<float4*>(a_hi + kc * A_LBO_ + r * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-              *reinterpret_cast<float4*>(a_lo + kc * A_LBO_ + r * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-            }
-          }
-        }
-        tc_fence_before();      // order the tcgen05.ld above before the next MMA overwrites the accumulator
-        fence_proxy_async();
-        tile_sync(g);
       }
       // ---- head, wrapped env step, Transition ------------------------------------------------------------------
       const float u = actor_head<PRNG>(a, k_actor, loc + s_bo[0], raw_sc + s_bo[1], ee, live, t);
