@@ -9,15 +9,17 @@
 // the products are fp32-accurate and the actions agree with the float32 oracle to the same tolerance as the
 // CUDA-core kernel.
 //
-//   CTA           512 threads = four independent tiles of 128 envs (thread = env = TMEM lane).  A tile's step is a
-//                 chain of short phases separated by tensor-core and barrier latencies; four tiles per SM (four
-//                 warps per scheduler) are what keeps the issue slots busy
+//   CTA           four independent tiles of 128 envs (512 producer threads: thread = env = TMEM lane) plus one
+//                 MMA-issuing warp per tile.  A tile's step is a chain of short phases separated by tensor-core
+//                 latencies; four tiles per SM (four producer warps per scheduler) keep the issue slots busy, and
+//                 the warps of a tile meet only through mbarriers (no block or named barrier in the step loop)
 //   A operand     a tile never holds a whole [128 x 64] activation matrix: the producer (layer 0 on the CUDA
 //                 cores, or the epilogue of the previous accumulator) emits 16 columns at a time into a ring of
 //                 two 16 KB slots (hi and lo planes, canonical K-major no-swizzle UMMA layout: 16-byte chunk kc of
-//                 row r at kc * 2048 + r * 16), the six MMAs that consume a slot are issued as soon as the tile has
-//                 written it, and a tcgen05.commit per slot tells the producer when it may be overwritten -- the
-//                 MMAs of one quarter run under the production of the next
+//                 row r at kc * 2048 + r * 16); each producer warp arrives on the slot's `full` mbarrier, the tile's
+//                 issuer waits for the four arrivals and issues the six MMAs that consume the slot, and a
+//                 tcgen05.commit per slot tells the producers when it may be overwritten -- the MMAs of one quarter
+//                 run under the production of the next
 //   B operand     each hidden -> hidden weight matrix as two planes (hi, lo), element (n, k) at
 //                 (k / 4) * 1024 + n * 16 + (k % 4) * 4, resident in shared memory for the whole launch
 //   D             two 64-column TMEM accumulators per tile, alternating between layers (512 columns per CTA)
@@ -34,7 +36,8 @@ using namespace tc;   // PTX wrappers: mbarrier, fences, umma_desc, umma_commit
 
 constexpr int TILE = 128;                 // envs per tile = TMEM lanes
 constexpr int TILES_PER_CTA = 4;
-constexpr int THREADS = TILE * TILES_PER_CTA;
+constexpr int ENV_THREADS_ = TILE * TILES_PER_CTA;      // 512 producer threads: thread = env
+constexpr int THREADS = ENV_THREADS_ + 32 * TILES_PER_CTA;   // + one MMA-issuing warp per tile (one lane active)
 constexpr int W = ACT_W;                  // 64
 constexpr int QC = 16;                    // columns a producer emits per ring slot (two K = 8 MMA steps)
 constexpr int QUARTERS = W / QC;
@@ -56,8 +59,8 @@ struct Smem {
   static constexpr uint32_t WO = BH + MAX_HH * W * 4;                      // float [64][2]
   static constexpr uint32_t BO = WO + W * 2 * 4;                           // float [2] (+ pad)
   static constexpr uint32_t TILES = BO + 16;                               // float [16 warps][96]: row transposition
-  static constexpr uint32_t BARS = TILES + (THREADS / 32) * 96 * 4;        // per tile: slot_free[2], layer_done
-  static constexpr uint32_t TMEM_PTR = BARS + TILES_PER_CTA * 4 * 8;
+  static constexpr uint32_t BARS = TILES + (ENV_THREADS_ / 32) * 96 * 4;   // per tile: slot_free[2], layer_done, full[2]
+  static constexpr uint32_t TMEM_PTR = BARS + TILES_PER_CTA * 8 * 8;
   static constexpr uint32_t TOTAL = TMEM_PTR + 16;
 };
 static_assert(Smem::TOTAL <= 227 * 1024, "tensor-core actor kernel shared memory plan exceeds 227 KB");
@@ -88,28 +91,88 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-// 128-thread barrier of one tile (named barriers 1..4; barrier 0 is __syncthreads)
-__device__ __forceinline__ void tile_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(TILE) : "memory"); }
-
-// v ~= hi + lo, both exactly representable in TF32 (low 13 mantissa bits clear): hi = v rounded to nearest,
-// so |lo| <= 2^-12 |v| and rounding lo loses <= 2^-24 |v| -- the three-product sum is fp32-accurate.
+// mbarrier helpers on precomputed 32-bit shared addresses (the generic -> shared conversion stays out of the loops)
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_a(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float to_tf32(float v) {   // round to nearest TF32 (low 13 mantissa bits clear)
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+// v ~= hi + lo, both exactly representable in TF32: hi = v rounded to nearest, so |lo| <= 2^-12 |v| and rounding
+// lo loses <= 2^-24 |v| -- the three-product sum is fp32-accurate.
 __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
-  hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
-  lo = __uint_as_float((__float_as_uint(v - hi) + 0x1000u) & 0xFFFFE000u);
+  hi = to_tf32(v);
+  lo = to_tf32(v - hi);
+}
+// packed float32 pairs (one issue slot for two lanes of work; IEEE-rounded per element)
+__device__ __forceinline__ f32x2_t add2(f32x2_t x, f32x2_t y) {
+  f32x2_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(y));
+  return r;
+}
+__device__ __forceinline__ f32x2_t mul2(f32x2_t x, f32x2_t y) {
+  f32x2_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(y));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// swish_exact (actor_kernels.cuh) on a pair: x * rcp(1 + ex2(-x * log2(e))), the same operations per element
+__device__ __forceinline__ void swish2(float x0, float x1, float& y0, float& y1) {
+  const f32x2_t x = pack2(x0, x1);
+  float t0, t1;
+  unpack2(mul2(x, pack2(-1.44269504f, -1.44269504f)), t0, t1);
+  float d0, d1;
+  unpack2(add2(pack2(ex2_approx(t0), ex2_approx(t1)), pack2(1.0f, 1.0f)), d0, d1);
+  unpack2(mul2(x, pack2(rcp_approx(d0), rcp_approx(d1))), y0, y1);
+}
+// v ~= hi + lo for a pair
+__device__ __forceinline__ void split_tf32_2(float v0, float v1, float& h0, float& h1, float& l0, float& l1) {
+  h0 = to_tf32(v0); h1 = to_tf32(v1);
+  float d0, d1;
+  unpack2(add2(pack2(v0, v1), pack2(-h0, -h1)), d0, d1);
+  l0 = to_tf32(d0); l1 = to_tf32(d1);
 }
 
 template <int PRNG, int MATH>
 __global__ void __launch_bounds__(THREADS, 1) actor_rollout_tc_kernel(const __grid_constant__ ActorArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = tid / TILE, r = tid % TILE;            // tile of the CTA, row of the tile
+  const bool issuer_warp = tid >= ENV_THREADS_;
+  const int g = issuer_warp ? (tid - ENV_THREADS_) / 32 : tid / TILE;   // tile of the CTA
+  const int r = tid % TILE;                                             // row of the tile (producer threads)
   float* s_w0 = reinterpret_cast<float*>(smem + Smem::W0);
   float* s_b0 = reinterpret_cast<float*>(smem + Smem::B0);
   float* s_bh = reinterpret_cast<float*>(smem + Smem::BH);
   float* s_wo = reinterpret_cast<float*>(smem + Smem::WO);
   float* s_bo = reinterpret_cast<float*>(smem + Smem::BO);
-  float* tile = reinterpret_cast<float*>(smem + Smem::TILES) + warp * 96;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::BARS) + g * 4;   // slot_free[0], slot_free[1], layer_done
+  float* tile = reinterpret_cast<float*>(smem + Smem::TILES) + (warp & 15) * 96;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::BARS) + g * 8;   // slot_free[2], layer_done, -, full[2]
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + Smem::TMEM_PTR);
   const int L = a.num_hidden, HH = L - 1;
 
@@ -119,10 +182,12 @@ __global__ void __launch_bounds__(THREADS, 1) actor_rollout_tc_kernel(const __gr
                  "r"(TMEM_COLS_));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  if (r == 0) {
+  if (!issuer_warp && r == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     mbar_init(&bars[2], 1);
+    mbar_init(&bars[4], TILE / 32);   // one arrival per producer warp
+    mbar_init(&bars[5], TILE / 32);
     fence_barrier_init();
   }
   for (int l = 0; l < HH; ++l) {
@@ -151,16 +216,50 @@ __global__ void __launch_bounds__(THREADS, 1) actor_rollout_tc_kernel(const __gr
 
   const int tile_idx = blockIdx.x * TILES_PER_CTA + g;
   const int tile_e0 = tile_idx * TILE;
-  if (tile_e0 < a.E) {          // tile-uniform: an idle tile skips the loop (tiles share no barrier in it)
-    const uint32_t tmem_tile = tmem_base + g * 2 * W;                                        // two accumulators
+  const uint32_t tmem_tile = tmem_base + g * 2 * W;                                          // two accumulators
+  uint8_t* ring = smem + Smem::A + g * SLOTS * SLOT_BYTES;
+  if (issuer_warp) {
+    // ---- MMA issuer of tile g: one lane follows the producers' schedule (T steps x HH stages x 4 quarters) -----
+    if (tile_e0 < a.E && lane == 0) {
+      // descriptors: only the start-address field (16-byte units, bits [0,14)) varies
+      const uint64_t da0 = umma_desc(smem_u32(ring), A_LBO_, SBO);
+      const uint64_t db0 = umma_desc(smem_u32(smem + Smem::WH), W_LBO_, SBO);
+      constexpr uint32_t IDESC = umma_idesc_tf32(TILE, W);
+      uint32_t uses = 0;
+      const uint32_t bar0 = smem_u32(bars);
+#pragma unroll 1
+      for (int t = 0; t < a.T; ++t) {
+#pragma unroll 1
+        for (int s = 0; s < HH; ++s) {
+          const uint32_t d = tmem_tile + (s & 1) * W;
+#pragma unroll 1
+          for (int qd = 0; qd < QUARTERS; ++qd) {
+            const uint32_t slot = uses & 1u;
+            mbar_wait_a(bar0 + (4u + slot) * 8u, (uses >> 1) & 1u);   // the four producer warps have written the slot
+            tc_fence_after();
+            // ---- 6 x tcgen05.mma (M128 N64 K8): lo.hi + hi.lo + hi.hi for the two K-steps of this slot ----------------
+            const uint64_t a_hi = da0 + ((slot * SLOT_BYTES) >> 4), a_lo = a_hi + (SLOT_PLANE >> 4);
+            const uint64_t b_hi = db0 + ((static_cast<uint32_t>(s) * 2u * W_PLANE + qd * 4u * W_LBO_) >> 4);
+            const uint64_t b_lo = b_hi + (W_PLANE >> 4);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const uint64_t ao = static_cast<uint64_t>((j * 2 * A_LBO_) >> 4), bo = static_cast<uint64_t>((j * 2 * W_LBO_) >> 4);
+              umma_tf32_ss(d, a_lo + ao, b_hi + bo, IDESC, (qd | j) ? 1u : 0u);     // small terms first
+              umma_tf32_ss(d, a_hi + ao, b_lo + bo, IDESC, 1u);
+              umma_tf32_ss(d, a_hi + ao, b_hi + bo, IDESC, 1u);
+            }
+            umma_commit_a(bar0 + slot * 8u);                        // slot free when these MMAs have read it
+            if (qd == QUARTERS - 1) umma_commit_a(bar0 + 16u);      // accumulator s & 1 complete
+            ++uses;
+          }
+        }
+      }
+    }
+  } else if (tile_e0 < a.E) {   // tile-uniform: an idle tile skips the loop (tiles share no barrier in it)
     const uint32_t tmem_rd = tmem_tile + (static_cast<uint32_t>((warp & 3) * 32) << 16);    // this warp's 32 lanes
-    uint8_t* ring = smem + Smem::A + g * SLOTS * SLOT_BYTES;
-    // descriptors: only the start-address field (16-byte units, bits [0,14)) varies
-    const uint64_t da0 = umma_desc(smem_u32(ring), A_LBO_, SBO);
-    const uint64_t db0 = umma_desc(smem_u32(smem + Smem::WH), W_LBO_, SBO);
-    constexpr uint32_t IDESC = umma_idesc_tf32(TILE, W);
     uint32_t uses = 0;          // ring slots written so far (slot = uses & 1)
     uint32_t layer_phase = 0;
+    const uint32_t bar0 = smem_u32(bars);
 
     const PendulumConsts pc(a.sys);
     const float ep_len = static_cast<float>(a.episode_length);
@@ -218,65 +317,59 @@ __global__ void __launch_bounds__(THREADS, 1) actor_rollout_tc_kernel(const __gr
               const float4 bb = *reinterpret_cast<const float4*>(s_b0 + c0);
               const float w0r[4] = {r0.x, r0.y, r0.z, r0.w}, w1r[4] = {r1.x, r1.y, r1.z, r1.w};
               const float w2r[4] = {r2.x, r2.y, r2.z, r2.w}, b0r[4] = {bb.x, bb.y, bb.z, bb.w};
+              float pre[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                h[j4 * 4 + i] = swish_exact(fmaf(xin[2], w2r[i], fmaf(xin[1], w1r[i], xin[0] * w0r[i])) + b0r[i]);
+              for (int i = 0; i < 4; ++i) pre[i] = fmaf(xin[2], w2r[i], fmaf(xin[1], w1r[i], xin[0] * w0r[i])) + b0r[i];
+              swish2(pre[0], pre[1], h[j4 * 4], h[j4 * 4 + 1]);
+              swish2(pre[2], pre[3], h[j4 * 4 + 2], h[j4 * 4 + 3]);
             }
           } else {
             // ---- epilogue of the previous layer: 16 accumulator columns, bias + swish ---------------------------
             uint32_t acc[QC];
             tmem_ld16(acc_src + qd * QC, acc);
 #pragma unroll
-            for (int i = 0; i < QC; ++i) h[i] = swish_exact(__uint_as_float(acc[i]) + bias[qd * QC + i]);
+            for (int j4 = 0; j4 < QC / 4; ++j4) {
+              const float4 bb = *reinterpret_cast<const float4*>(bias + qd * QC + j4 * 4);
+              float x0, x1, x2, x3;
+              unpack2(add2(pack2(__uint_as_float(acc[j4 * 4]), __uint_as_float(acc[j4 * 4 + 1])), pack2(bb.x, bb.y)), x0, x1);
+              unpack2(add2(pack2(__uint_as_float(acc[j4 * 4 + 2]), __uint_as_float(acc[j4 * 4 + 3])), pack2(bb.z, bb.w)), x2, x3);
+              swish2(x0, x1, h[j4 * 4], h[j4 * 4 + 1]);
+              swish2(x2, x3, h[j4 * 4 + 2], h[j4 * 4 + 3]);
+            }
           }
           if (!to_mma) {        // output layer on the CUDA cores, float32
 #pragma unroll
-            for (int i = 0; i < QC; ++i) {
-              const float2 wo = *reinterpret_cast<const float2*>(s_wo + (qd * QC + i) * 2);
+            for (int i = 0; i < QC; i += 2) {
+              const float4 wo = *reinterpret_cast<const float4*>(s_wo + (qd * QC + i) * 2);
               loc = fmaf(h[i], wo.x, loc);
               raw_sc = fmaf(h[i], wo.y, raw_sc);
+              loc = fmaf(h[i + 1], wo.z, loc);
+              raw_sc = fmaf(h[i + 1], wo.w, raw_sc);
             }
             continue;
           }
           // ---- hi / lo planes of the 16 columns into the ring slot ----------------------------------------------------
           const uint32_t slot = uses & 1u;
-          if (uses >= SLOTS) mbar_wait(&bars[slot], ((uses >> 1) - 1u) & 1u);   // the MMAs that read it have retired
+          if (uses >= SLOTS) mbar_wait_a(bar0 + slot * 8u, ((uses >> 1) - 1u) & 1u);   // the MMAs that read it have retired
           uint8_t* dst = ring + slot * SLOT_BYTES + r * 16;
 #pragma unroll
           for (int j4 = 0; j4 < QC / 4; ++j4) {
             float hi[4], lo[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) split_tf32(h[j4 * 4 + i], hi[i], lo[i]);
+            split_tf32_2(h[j4 * 4], h[j4 * 4 + 1], hi[0], hi[1], lo[0], lo[1]);
+            split_tf32_2(h[j4 * 4 + 2], h[j4 * 4 + 3], hi[2], hi[3], lo[2], lo[3]);
             *reinterpret_cast<float4*>(dst + j4 * A_LBO_) = make_float4(hi[0], hi[1], hi[2], hi[3]);
             *reinterpret_cast<float4*>(dst + SLOT_PLANE + j4 * A_LBO_) = make_float4(lo[0], lo[1], lo[2], lo[3]);
           }
           fence_proxy_async();      // generic-proxy writes of A -> visible to the tensor core
-          tile_sync(g);
-          if (r == 0) {
-            // ---- 6 x tcgen05.mma (M128 N64 K8): lo.hi + hi.lo + hi.hi for the two K-steps of this slot ------------------
-            tc_fence_after();
-            const uint32_t d = tmem_tile + (s & 1) * W;
-            const uint64_t a_hi = da0 + ((slot * SLOT_BYTES) >> 4), a_lo = a_hi + (SLOT_PLANE >> 4);
-            const uint64_t b_hi = db0 + ((static_cast<uint32_t>(s) * 2u * W_PLANE + qd * 4u * W_LBO_) >> 4);
-            const uint64_t b_lo = b_hi + (W_PLANE >> 4);
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const uint64_t ao = static_cast<uint64_t>((j * 2 * A_LBO_) >> 4), bo = static_cast<uint64_t>((j * 2 * W_LBO_) >> 4);
-              umma_tf32_ss(d, a_lo + ao, b_hi + bo, IDESC, (qd | j) ? 1u : 0u);     // small terms first
-              umma_tf32_ss(d, a_hi + ao, b_lo + bo, IDESC, 1u);
-              umma_tf32_ss(d, a_hi + ao, b_hi + bo, IDESC, 1u);
-            }
-            umma_commit(&bars[slot]);                       // slot free when these MMAs have read it
-            if (qd == QUARTERS - 1) umma_commit(&bars[2]);  // accumulator s & 1 complete
-          }
+          tc_fence_before();        // and this thread's accumulator reads are ordered before the MMAs they feed
+          __syncwarp();
+          if (lane == 0) mbar_arrive_a(bar0 + (4u + slot) * 8u);
           ++uses;
         }
         if (to_mma) {
-          mbar_wait(&bars[2], layer_phase);
+          mbar_wait_a(bar0 + 16u, layer_phase);
           layer_phase ^= 1u;
           tc_fence_after();
-        } else {
-          tc_fence_before();      // order this step's tcgen05.ld before the next step's MMAs into the same columns
         }
       }
       // ---- head, wrapped env step, Transition ------------------------------------------------------------------
