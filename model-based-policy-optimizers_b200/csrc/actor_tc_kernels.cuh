@@ -110,10 +110,10 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void umma_commit_a(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ float to_tf32(float v) {   // round to nearest TF32 (low 13 mantissa bits clear)
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-  return __uint_as_float(r);
+// round to nearest TF32 (low 13 mantissa bits clear, ties away from zero like cvt.rna.tf32.f32 -- which ptxas
+// expands to a five-instruction sequence on sm_100a; the integer form is two)
+__device__ __forceinline__ float to_tf32(float v) {
+  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
 }
 // v ~= hi + lo, both exactly representable in TF32: hi = v rounded to nearest, so |lo| <= 2^-12 |v| and rounding
 // lo loses <= 2^-24 |v| -- the three-product sum is fp32-accurate.
