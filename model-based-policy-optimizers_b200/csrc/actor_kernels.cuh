@@ -97,26 +97,31 @@ struct ActorEnv {
   float c, s, w, th, f_c, f_s, f_w, f_th, steps, done;
 };
 
-// The policy head: turns the network's two outputs (loc, raw scale; biases already added) into the action of
-// env `e` at step t, drawing from k_actor like the reference, and emits PPO's policy_extras when asked.
+// The policy's standard-normal draw for env `e`: normal(key, (E, A))[e], or the one draw normal(key, (A,)) every
+// env shares (BPTT); 0 for a deterministic policy.  Independent of the network, so a kernel may take it early.
 template <int PRNG>
-__device__ __forceinline__ float actor_head(const ActorArgs& a, Key2 k_actor, float mu, float raw_sc, int e, bool live,
-                                            int t) {
-  const uint32_t n_draw = a.shared_noise ? 1u : static_cast<uint32_t>(a.E);     // normal(key, (A,)) or (E, A)
+__device__ __forceinline__ float actor_draw(const ActorArgs& a, Key2 k_actor, int e) {
+  if (a.deterministic) return 0.0f;
+  const uint32_t n_draw = a.shared_noise ? 1u : static_cast<uint32_t>(a.E);
   const uint32_t i_draw = a.shared_noise ? 0u : static_cast<uint32_t>(e);
+  return bits_to_normal(random_bits_at<PRNG>(k_actor, n_draw, i_draw));
+}
+
+// The policy head: turns the network's two outputs (loc, raw scale; biases already added) and the draw eps into
+// the action of env `e` at step t, and emits PPO's policy_extras when asked.
+__device__ __forceinline__ float actor_head(const ActorArgs& a, float eps, float mu, float raw_sc, int e, bool live,
+                                            int t) {
   if (a.head == MBPO_HEAD_BPTT_ACTOR) {
     // Actor.__call__ :137-142: sig = clip(softplus(sig + inv_softplus(init_stddev)), sig_min, sig_max);
     // act :306-326: squash(mu) or squash(mu + normal(sample_key, mu.shape) * sig), squash = clip(tanh, +-0.999)
     float pre = mu;
     if (!a.deterministic) {
-      const float eps = bits_to_normal(random_bits_at<PRNG>(k_actor, n_draw, i_draw));
       const float sig = fminf(fmaxf(softplus_exact(__fadd_rn(raw_sc, a.sig_bias)), a.sig_min), a.sig_max);
       pre = __fadd_rn(pre, __fmul_rn(eps, sig));
     }
     return fminf(fmaxf(tanhf(pre), -a.action_clip), a.action_clip);
   }
   if (a.deterministic) return tanhf(mu);                               // mode(): tanh(loc)
-  const float eps = bits_to_normal(random_bits_at<PRNG>(k_actor, n_draw, i_draw));
   const float scale = softplus_exact(raw_sc) + a.min_std;
   const float raw = __fadd_rn(__fmul_rn(scale, eps), mu);              // distrax Normal.sample: scale * rnd + loc
   if (a.raw_action_out && live) {
@@ -291,7 +296,8 @@ __global__ void __launch_bounds__(ACT_MAX_THREADS, 1) actor_rollout_pendulum_ker
     for (int q = 0; q < 2; ++q) {
       if (!half_live[q]) continue;   // warp-uniform
       ActorEnv& v = env[q];
-      const float u = actor_head<PRNG>(a, k_actor, loc[q] + b_loc, raw_scale[q] + b_scale, ee[q], live[q], t);
+      const float u = actor_head(a, actor_draw<PRNG>(a, k_actor, ee[q]), loc[q] + b_loc, raw_scale[q] + b_scale, ee[q],
+                                 live[q], t);
       float trunc;
       const float rew = actor_env_step<MATH>(a, pc, v, u, ep_len, rep, trunc);
       warp_store3(tile, a.next_observation_out + (row + half_e0[q]) * 3 + lane, lane, n_valid[q], v.c, v.s, v.w);

@@ -151,12 +151,20 @@ __device__ __forceinline__ void swish2(float x0, float x1, float& y0, float& y1)
   unpack2(add2(pack2(ex2_approx(t0), ex2_approx(t1)), pack2(1.0f, 1.0f)), d0, d1);
   unpack2(mul2(x, pack2(rcp_approx(d0), rcp_approx(d1))), y0, y1);
 }
-// v ~= hi + lo for a pair
+// v ~= hi + lo for a pair.  The tensor core reads TF32 operands from 32-bit containers and ignores the low 13
+// mantissa bits, so lo needs no mask: adding half a TF32 ulp to its bit pattern makes that truncation a
+// round-to-nearest (|lo| <= 2^-12 |v|: the rounding loses at most 2^-24 |v|).
 __device__ __forceinline__ void split_tf32_2(float v0, float v1, float& h0, float& h1, float& l0, float& l1) {
   h0 = to_tf32(v0); h1 = to_tf32(v1);
   float d0, d1;
   unpack2(add2(pack2(v0, v1), pack2(-h0, -h1)), d0, d1);
-  l0 = to_tf32(d0); l1 = to_tf32(d1);
+  l0 = __uint_as_float(__float_as_uint(d0) + 0x1000u);
+  l1 = __uint_as_float(__float_as_uint(d1) + 0x1000u);
+}
+__device__ __forceinline__ f32x2_t fma2(f32x2_t x, f32x2_t y, f32x2_t z) {
+  f32x2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(x), "l"(y), "l"(z));
+  return r;
 }
 
 template <int PRNG, int MATH>
@@ -294,7 +302,8 @@ __global__ void __launch_bounds__(THREADS, 1) actor_rollout_tc_kernel(const __gr
 #pragma unroll
         for (int i = 0; i < 3; ++i) xin[i] = __fdiv_rn(__fsub_rn(xin[i], a.obs_mean[i]), a.obs_std[i]);
       }
-      float loc = 0.0f, raw_sc = 0.0f;
+      float loc = 0.0f, raw_sc = 0.0f, eps = 0.0f;
+      const f32x2_t x0p = pack2(xin[0], xin[0]), x1p = pack2(xin[1], xin[1]), x2p = pack2(xin[2], xin[2]);
 
       // stage s produces the A operand of hidden -> hidden layer s: from layer 0 on the CUDA cores (s = 0) or from
       // accumulator (s - 1) & 1; its MMAs accumulate into accumulator s & 1.  Stage HH is the output layer.
@@ -317,9 +326,14 @@ __global__ void __launch_bounds__(THREADS, 1) actor_rollout_tc_kernel(const __gr
               const float4 bb = *reinterpret_cast<const float4*>(s_b0 + c0);
               const float w0r[4] = {r0.x, r0.y, r0.z, r0.w}, w1r[4] = {r1.x, r1.y, r1.z, r1.w};
               const float w2r[4] = {r2.x, r2.y, r2.z, r2.w}, b0r[4] = {bb.x, bb.y, bb.z, bb.w};
+              // the same float operations per element as the CUDA-core kernel's first layer, two units per instruction
               float pre[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) pre[i] = fmaf(xin[2], w2r[i], fmaf(xin[1], w1r[i], xin[0] * w0r[i])) + b0r[i];
+              for (int i = 0; i < 4; i += 2) {
+                const f32x2_t acc2 = fma2(x2p, pack2(w2r[i], w2r[i + 1]),
+                                          fma2(x1p, pack2(w1r[i], w1r[i + 1]), mul2(x0p, pack2(w0r[i], w0r[i + 1]))));
+                unpack2(add2(acc2, pack2(b0r[i], b0r[i + 1])), pre[i], pre[i + 1]);
+              }
               swish2(pre[0], pre[1], h[j4 * 4], h[j4 * 4 + 1]);
               swish2(pre[2], pre[3], h[j4 * 4 + 2], h[j4 * 4 + 3]);
             }
@@ -366,6 +380,7 @@ __global__ void __launch_bounds__(THREADS, 1) actor_rollout_tc_kernel(const __gr
           if (lane == 0) mbar_arrive_a(bar0 + (4u + slot) * 8u);
           ++uses;
         }
+        if (s == 0) eps = actor_draw<PRNG>(a, k_actor, ee);   // network-independent: fills the first MMA wait
         if (to_mma) {
           mbar_wait_a(bar0 + 16u, layer_phase);
           layer_phase ^= 1u;
@@ -373,7 +388,7 @@ __global__ void __launch_bounds__(THREADS, 1) actor_rollout_tc_kernel(const __gr
         }
       }
       // ---- head, wrapped env step, Transition ------------------------------------------------------------------
-      const float u = actor_head<PRNG>(a, k_actor, loc + s_bo[0], raw_sc + s_bo[1], ee, live, t);
+      const float u = actor_head(a, eps, loc + s_bo[0], raw_sc + s_bo[1], ee, live, t);
       float trunc;
       const float rew = actor_env_step<MATH>(a, pc, v, u, ep_len, rep, trunc);
       const size_t row = static_cast<size_t>(t) * E;
