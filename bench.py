@@ -818,6 +818,10 @@ def run_sweep(args):
 ACT_INSTR_NOTE = ("float32 policy MLP 3-64-64-64-2 on the CUDA cores: 2 x 4096 + 192 + 128 = 8,512 FMA per env-step "
                   "are the algorithmic work; roofline = FP32 FMA issue rate (148 SMs x 128 lanes x sm_max_mhz)")
 ACT_FMA_PER_STEP = 2 * 64 * 64 + 3 * 64 + 64 * 2
+ACT_MUFU_PER_STEP = 2 * 3 * 64        # swish = x * rcp(1 + ex2(.)): two MUFU per hidden activation, 192 activations
+ACT_TC_NOTE = ("hidden->hidden policy layers as TF32 x 3 split-precision tcgen05 MMAs (fp32-accurate, accumulate in TMEM); "
+               "the tensor pipe is ~25% busy and the epilogues bound the kernel: the nearest hard limit is the MUFU pipe "
+               "(16 results/clk/SM, 2 per float32 swish activation x 192 activations per env-step); roofline = that rate")
 
 
 def run_actor(args):
@@ -866,7 +870,8 @@ def run_actor(args):
     system = PendulumSystem()
     env = wrap(system, system.reset(device=dev).system_params, episode_length=ENV_EPISODE)
     policy = acting.Policy(acting.PolicyParams([torch.from_numpy(w).to(dev) for w in pol.weights],
-                                               [torch.from_numpy(b).to(dev) for b in pol.biases]))
+                                               [torch.from_numpy(b).to(dev) for b in pol.biases]),
+                           kernel=args.actor_kernel)
     x0_host = torch.from_numpy(random_states(ENV_E, 1)[lo:hi].copy()).pin_memory()
     key = torch.from_numpy(jr.PRNGKey(rank)).to(dev)
     st = env.reset(x0_host.to(dev))
@@ -908,23 +913,33 @@ def run_actor(args):
             sm_max = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("sm_max_mhz", 1965.0))
         except Exception:
             pass
-        peak = 148 * 128 * sm_max * 1e6 / 1e12            # T FMA/s
-        achieved = E * T * ACT_FMA_PER_STEP / (ms * 1e-3) / 1e12
+        tc = args.actor_kernel != "cuda_cores"
+        if tc:
+            peak = 148 * 16 * sm_max * 1e6 / 1e12         # T MUFU results/s
+            achieved = E * T * ACT_MUFU_PER_STEP / (ms * 1e-3) / 1e12
+            roof = {"bound": "xu", "kernel": "actor_rollout_tc_kernel", "achieved": achieved, "peak": peak,
+                    "unit": "T MUFU/s", "frac": achieved / peak, "traffic": None, "note": ACT_TC_NOTE,
+                    "tensor_tflops_issued": E * T * 3 * 2 * 2 * 64 * 64 / (ms * 1e-3) / 1e12}
+        else:
+            peak = 148 * 128 * sm_max * 1e6 / 1e12        # T FMA/s
+            achieved = E * T * ACT_FMA_PER_STEP / (ms * 1e-3) / 1e12
+            roof = {"bound": "fma", "kernel": "actor_rollout_pendulum_kernel", "achieved": achieved, "peak": peak,
+                    "unit": "T FMA/s", "frac": achieved / peak, "traffic": None, "note": ACT_INSTR_NOTE}
         emit_json({
             "metric": "policy-in-the-loop env-steps/sec", "value": ENV_E * T / (ms * 1e-3), "unit": "env-steps/s",
             "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic (random-init policy)",
             "config": {"workload": "config3_actor_rollouts", "envs": ENV_E, "steps_per_call": T,
                        "policy": "3-64-64-64-2 swish, NormalTanh", "episode_length": ENV_EPISODE,
+                       "policy_kernel": "tcgen05 (TF32 x 3 split precision)" if tc else "CUDA cores (float32 FFMA2)",
                        "parallelism": "envs sharded x%d" % world,
-                       "l2": "per-call outputs %.0f MB > 126 MB L2; the kernel is FMA-issue bound" % (E * T * 28 / 1e6)},
+                       "l2": "per-call outputs %.0f MB > 126 MB L2; the kernel is compute bound" % (E * T * 28 / 1e6)},
             "math_mode": args.math, "clocks": clk.summary(),
             "e2e": {"value": ENV_E * T / e2e_s, "unit": "env-steps/s", "ms_per_step": e2e_s * 1e3,
                     "h2d_bytes_per_step": int(x0_host.numel() * 4), "d2h_bytes_per_step": int(rew_host.numel() * 4),
                     "api": "acting.get_experience(env, reset(x0 from pinned host), policy, key, T) -> rewards to host"},
             "gpu_launches": steps,
-            "roofline": {"bound": "fma", "kernel": "actor_rollout_pendulum_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "T FMA/s", "frac": achieved / peak, "traffic": None, "note": ACT_INSTR_NOTE},
+            "roofline": roof,
             "cpu_baseline": None}, GUARD)
     if world > 1:
         dist.destroy_process_group()
@@ -1115,6 +1130,8 @@ def main():
                     default="config2_batched_icem")
     ap.add_argument("--math", choices=["reference", "theta_carry"], default="reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--actor-kernel", choices=["auto", "cuda_cores", "tcgen05"], default="auto",
+                    help="config3_actor_rollouts: which kernel runs the policy network")
     ap.add_argument("--env-sequential", action="store_true",
                     help="config3_env_rollouts: time the one-thread-per-env scan instead of the episode-piece kernel")
     args = ap.parse_args()
