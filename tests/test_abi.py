@@ -136,6 +136,16 @@ def test_api_surface_matches_reference(mb):
     assert list(inspect.signature(iCEMOptimizer.__init__).parameters)[:5] == ["self", "horizon", "opt_params", "system", "key"]
     assert list(inspect.signature(System.step).parameters) == ["self", "x", "u", "system_params"]
     assert list(inspect.signature(rollout_actions).parameters) == ["system", "system_params", "init_state", "actions", "horizon"]
+    from mbpo_b200 import acting
+    from mbpo_b200.utils import lambda_return, rollout_policy
+    assert list(inspect.signature(rollout_policy).parameters) == [                       # optimizer_utils.py:63-71
+        "system", "system_params", "init_state", "policy", "policy_state", "horizon", "stop_grads"]
+    assert inspect.signature(rollout_policy).parameters["stop_grads"].default is True
+    assert list(inspect.signature(lambda_return).parameters) == ["reward", "next_values", "discount", "lambda_"]   # :120-123
+    assert list(inspect.signature(acting.actor_step).parameters) == [                    # sac/acting.py:35-40
+        "env", "env_state", "policy", "key", "extra_fields"]
+    assert list(inspect.signature(acting.generate_unroll).parameters) == [               # sac/acting.py:58-64
+        "env", "env_state", "policy", "key", "unroll_length", "extra_fields"]
     assert issubclass(iCemTO, BaseOptimizer) and issubclass(PendulumSystem, System)
     assert iCEMOptimizer(horizon=20).can_act_in_batches is False
     s = PendulumSystem()
