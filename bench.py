@@ -873,7 +873,7 @@ def run_actor(args):
                                                [torch.from_numpy(b).to(dev) for b in pol.biases]),
                            kernel=args.actor_kernel)
     x0_host = torch.from_numpy(random_states(ENV_E, 1)[lo:hi].copy()).pin_memory()
-    key = torch.from_numpy(jr.PRNGKey(rank)).to(dev)
+    key = torch.from_numpy(jr.PRNGKey(0)).to(dev)       # one key for all ranks: a shard draws its slice of the stream
     st = env.reset(x0_host.to(dev))
 
     def barrier():
@@ -881,7 +881,7 @@ def run_actor(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
     for _ in range(max(args.warmup, 3)):
-        acting.get_experience(env, st, policy, key, T)
+        acting.get_experience(env, st, policy, key, T, env_offset=lo, total_envs=ENV_E)
     steps = min(args.steps, 10)
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
@@ -889,7 +889,7 @@ def run_actor(args):
         barrier()
         for k in range(steps):
             starts[k].record()
-            acting.get_experience(env, st, policy, key, T)
+            acting.get_experience(env, st, policy, key, T, env_offset=lo, total_envs=ENV_E)
             ends[k].record()
         barrier()
     ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends)) / steps
@@ -902,7 +902,7 @@ def run_actor(args):
     t0 = time.perf_counter()
     for k in range(steps):
         st_k = env.reset(x0_host.to(dev, non_blocking=True))
-        _, _, trn = acting.get_experience(env, st_k, policy, key, T)
+        _, _, trn = acting.get_experience(env, st_k, policy, key, T, env_offset=lo, total_envs=ENV_E)
         rew_host.copy_(trn.reward, non_blocking=True)
         torch.cuda.synchronize(dev)
     barrier()

@@ -253,6 +253,10 @@ typedef struct MbpoPolicyParams {
    * split-precision MMAs, fp32 accumulate in TMEM) for 2..3 hidden layers and the CUDA-core kernel otherwise;
    * MBPO_ACTOR_TCGEN05 with an unsupported depth is MBPO_EUNSUPPORTED. */
   int32_t kernel;
+  /* env sharding: the policy's draw is normal(key, (num_envs, A))[env], so a rank that owns envs
+   * [draw_offset, draw_offset + E) of draw_total reproduces the unsharded stream bit for bit (draw_total = 0: the
+   * launch owns every env, i.e. draw_total = E, draw_offset = 0). */
+  int32_t draw_offset, draw_total;
 } MbpoPolicyParams;
 enum { MBPO_HEAD_NORMAL_TANH = 0, MBPO_HEAD_BPTT_ACTOR = 1 };
 enum { MBPO_ACTOR_AUTO = 0, MBPO_ACTOR_CUDA_CORES = 1, MBPO_ACTOR_TCGEN05 = 2 };

@@ -41,6 +41,7 @@ struct ActorArgs {
   float min_std;
   // policy head (MBPO_HEAD_*): NormalTanh of SAC/PPO, or the BPTT actor (bptt_optimizer.py:123-142,306-326)
   int head, shared_noise, normalize;
+  int draw_offset, draw_total;   // env sharding of the draw normal(key, (draw_total, A))[draw_offset + e]
   float sig_bias, sig_min, sig_max, action_clip;
   float obs_mean[3], obs_std[3];
   const float* w[ACT_MAX_HIDDEN + 1];  // [3,64], [64,64] x (num_hidden-1), [64,2]   (flax Dense kernels, [in, out])
@@ -102,8 +103,8 @@ struct ActorEnv {
 template <int PRNG>
 __device__ __forceinline__ float actor_draw(const ActorArgs& a, Key2 k_actor, int e) {
   if (a.deterministic) return 0.0f;
-  const uint32_t n_draw = a.shared_noise ? 1u : static_cast<uint32_t>(a.E);
-  const uint32_t i_draw = a.shared_noise ? 0u : static_cast<uint32_t>(e);
+  const uint32_t n_draw = a.shared_noise ? 1u : static_cast<uint32_t>(a.draw_total);
+  const uint32_t i_draw = a.shared_noise ? 0u : static_cast<uint32_t>(a.draw_offset + e);
   return bits_to_normal(random_bits_at<PRNG>(k_actor, n_draw, i_draw));
 }
 

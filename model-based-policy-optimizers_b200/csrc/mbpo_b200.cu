@@ -750,6 +750,12 @@ int mbpo_actor_rollout_extras(int system_kind, const void* sys_params_host, int 
   a.head = policy_host->head; a.shared_noise = policy_host->shared_noise; a.normalize = policy_host->normalize;
   a.sig_bias = policy_host->sig_bias; a.sig_min = policy_host->sig_min; a.sig_max = policy_host->sig_max;
   a.action_clip = policy_host->action_clip;
+  MBPO_REQUIRE(policy_host->draw_total == 0 ||
+                   (policy_host->draw_offset >= 0 && policy_host->draw_offset + E <= policy_host->draw_total),
+               "actor_rollout: envs [%d, %d) are not inside draw_total %d", policy_host->draw_offset,
+               policy_host->draw_offset + E, policy_host->draw_total);
+  a.draw_total = policy_host->draw_total > 0 ? policy_host->draw_total : E;
+  a.draw_offset = policy_host->draw_total > 0 ? policy_host->draw_offset : 0;
   for (int i = 0; i < 3; ++i) { a.obs_mean[i] = policy_host->obs_mean[i]; a.obs_std[i] = policy_host->obs_std[i]; }
   for (int l = 0; l <= mbpo::ACT_MAX_HIDDEN; ++l) {
     a.w[l] = l <= a.num_hidden ? policy_host->w[l] : nullptr;

@@ -114,7 +114,7 @@ def make_ppo_inference_fn():
 
 
 def _rollout(env: VmappedSystemEnv, env_state: EnvState, policy: Policy, key: torch.Tensor, T: int,
-             key_convention: int, extra_fields: Sequence[str]):
+             key_convention: int, extra_fields: Sequence[str], env_offset: int = 0, total_envs: int = None):
     for f in extra_fields:
         if f != "truncation":
             raise _lib.MbpoUnsupported(_lib.MBPO_EUNSUPPORTED, "extra field %r is not produced by the env kernel" % f)
@@ -135,6 +135,9 @@ def _rollout(env: VmappedSystemEnv, env_state: EnvState, policy: Policy, key: to
     d = torch.empty((T, E), dtype=torch.float32, device=dev)
     tr = torch.empty((T, E), dtype=torch.float32, device=dev)
     params = system.pack_params(env_state.system_params)
+    # a shard of the envs draws its slice of normal(key, (total_envs, A)): same bits as the unsharded launch
+    policy.struct.draw_total = int(total_envs) if total_envs is not None else 0
+    policy.struct.draw_offset = int(env_offset) if total_envs is not None else 0
     raw = torch.empty((T, E, A), dtype=torch.float32, device=dev) if policy.emit_extras else None
     logp = torch.empty((T, E), dtype=torch.float32, device=dev) if policy.emit_extras else None
     with _lib.cuda_guard(obs):
@@ -164,17 +167,23 @@ def actor_step(env: VmappedSystemEnv, env_state: EnvState, policy: Policy, key: 
 
 
 def generate_unroll(env: VmappedSystemEnv, env_state: EnvState, policy: Policy, key: torch.Tensor, unroll_length: int,
-                    extra_fields: Sequence[str] = ()) -> Tuple[EnvState, Transition]:
+                    extra_fields: Sequence[str] = (), env_offset: int = 0,
+                    total_envs: int = None) -> Tuple[EnvState, Transition]:
     """sac/acting.py:58-78: lax.scan of actor_step; per step current_key, next_key = split(current_key), the
     policy samples with current_key.  Fields are time-major [T, E, ...]."""
-    nstate, tr, _ = _rollout(env, env_state, policy, key, unroll_length, _lib.KEYS_UNROLL, extra_fields)
+    nstate, tr, _ = _rollout(env, env_state, policy, key, unroll_length, _lib.KEYS_UNROLL, extra_fields, env_offset,
+                             total_envs)
     return nstate, tr
 
 
 def get_experience(env: VmappedSystemEnv, env_state: EnvState, policy: Policy, key: torch.Tensor,
-                   num_env_steps: int) -> Tuple[torch.Tensor, EnvState, Transition]:
+                   num_env_steps: int, env_offset: int = 0,
+                   total_envs: int = None) -> Tuple[torch.Tensor, EnvState, Transition]:
     """The scan of SAC.get_experience (sac/sac.py:288-294): per step k, k_t = split(k), actor_step with k_t and
-    extra_fields=('truncation',).  Returns (carry key, env_state, transitions [T, E, ...]); the replay-buffer
+    extra_fields=('truncation',).  env_offset / total_envs (additive): this call owns envs [env_offset, env_offset + E)
+    of total_envs sharded over ranks, and draws its slice of the unsharded noise.
+    Returns (carry key, env_state, transitions [T, E, ...]); the replay-buffer
     insert and the normaliser update stay with the caller (SURVEY 8f-2 boundary)."""
-    nstate, tr, key_out = _rollout(env, env_state, policy, key, num_env_steps, _lib.KEYS_SAC, ("truncation",))
+    nstate, tr, key_out = _rollout(env, env_state, policy, key, num_env_steps, _lib.KEYS_SAC, ("truncation",),
+                                   env_offset, total_envs)
     return key_out, nstate, tr

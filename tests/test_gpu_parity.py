@@ -751,6 +751,31 @@ def test_actor_step_and_deterministic_policy(mb, cuda_device):
         acting.actor_step(env, st, _policy_on_device(mb, cuda_device, bad), _dev(key, cuda_device))
 
 
+@pytest.mark.parametrize("kernel", ["tcgen05", "cuda_cores"])
+def test_actor_rollout_env_sharding_is_bit_identical(mb, cuda_device, kernel):
+    """Envs sharded over ranks: each shard draws its slice of normal(key, (num_envs, A)), so the shards together
+    reproduce the unsharded launch bit for bit (the multi-GPU invariant of DESIGN.md section 4.3)."""
+    from mbpo_b200 import acting
+    from mbpo_b200.envs import wrap
+    from mbpo_b200.systems import PendulumSystem
+    E, T = 700, 9
+    pol = orc.make_policy_params(seed=5, hidden=(64, 64))
+    policy = _policy_on_device(mb, cuda_device, pol, kernel=kernel)
+    system = PendulumSystem()
+    env = wrap(system, system.reset(device=cuda_device).system_params, episode_length=4)
+    x0 = _dev(_random_states(E, 141), cuda_device)
+    key = _dev(ojr.PRNGKey(8), cuda_device)
+    k_all, s_all, tr_all = acting.get_experience(env, env.reset(x0), policy, key, T)
+    cuts = [0, 256, 300, E]
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        k, s, tr = acting.get_experience(env, env.reset(x0[lo:hi].contiguous()), policy, key, T, env_offset=lo, total_envs=E)
+        assert torch.equal(tr.action, tr_all.action[:, lo:hi]) and torch.equal(tr.reward, tr_all.reward[:, lo:hi])
+        assert torch.equal(tr.next_observation, tr_all.next_observation[:, lo:hi]) and torch.equal(k, k_all)
+        assert torch.equal(s.obs, s_all.obs[lo:hi])
+    with pytest.raises(mb.MbpoError):
+        acting.get_experience(env, env.reset(x0[:10].contiguous()), policy, key, T, env_offset=695, total_envs=E)
+
+
 def test_ppo_policy_extras_and_normaliser(mb, cuda_device, prng_mode):
     """PPO's generate_unroll (ppo/ppo.py:194-213): the policy also returns raw_action and log_prob
     (ppo_network.py:66-80), and the policy network normalises observations with the running statistics."""
