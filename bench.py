@@ -617,10 +617,13 @@ def run_closed_loop(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return                                   # a single problem does not shard: "replicas only"
-    from oracle import c_twin, jax_prng as jr, mbpo_oracle as orc
-    p_or = orc.ICemParams()
-    tr_plan_written = transitions_per_step(1, MPC_H, p_or)                       # 515,000 (P = 10 as written)
+    from types import SimpleNamespace
+    defaults = SimpleNamespace(num_particles=10, num_samples=500, num_elites=50, num_steps=5,
+                               elite_set_fraction=0.3)                           # iCemParams() (icem_optimizer.py:39-50)
+    tr_plan_written = transitions_per_step(1, MPC_H, defaults)                   # 515,000 (P = 10 as written)
     if args.impl == "reference":
+        from oracle import c_twin, jax_prng as jr, mbpo_oracle as orc            # CPU arm only
+        p_or = orc.ICemParams()
         lib = c_twin.load(native=True)
         cfg = c_twin.make_cfg(p_or, MPC_H)
         p9 = orc.PendulumParams().packed()
@@ -818,6 +821,16 @@ def run_sweep(args):
 ACT_INSTR_NOTE = ("float32 policy MLP 3-64-64-64-2 on the CUDA cores: 2 x 4096 + 192 + 128 = 8,512 FMA per env-step "
                   "are the algorithmic work; roofline = FP32 FMA issue rate (148 SMs x 128 lanes x sm_max_mhz)")
 ACT_FMA_PER_STEP = 2 * 64 * 64 + 3 * 64 + 64 * 2
+
+
+def make_policy_numpy(seed=7, hidden=(64, 64, 64), obs_dim=3, action_dim=1):
+    """Random-init policy MLP (flax Dense kernels [in, out] + biases); same construction as
+    oracle.make_policy_params so both arms of the bench run the same network."""
+    rng = np.random.default_rng(seed)
+    dims = (obs_dim,) + tuple(hidden) + (2 * action_dim,)
+    ws = [(rng.standard_normal((dims[i], dims[i + 1])) / np.sqrt(dims[i])).astype(np.float32) for i in range(len(dims) - 1)]
+    bs = [(0.1 * rng.standard_normal(dims[i + 1])).astype(np.float32) for i in range(len(dims) - 1)]
+    return ws, bs
 ACT_MUFU_PER_STEP = 2 * 3 * 64        # swish = x * rcp(1 + ex2(.)): two MUFU per hidden activation, 192 activations
 ACT_TC_NOTE = ("hidden->hidden policy layers as TF32 x 3 split-precision tcgen05 MMAs (fp32-accurate, accumulate in TMEM); "
                "the tensor pipe is ~25% busy and the epilogues bound the kernel: the nearest hard limit is the MUFU pipe "
@@ -831,12 +844,13 @@ def run_actor(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    from oracle import jax_prng as jr, mbpo_oracle as orc
-    pol = orc.make_policy_params(seed=7)
+    pol_w, pol_b = make_policy_numpy(seed=7)
     T = 200
     if args.impl == "reference":
         if rank != 0:
             return
+        from oracle import jax_prng as jr, mbpo_oracle as orc                    # CPU arm only
+        pol = orc.PolicyParams(pol_w, pol_b)
         E, Ts = 4096, 4                                  # bounded sample; NumPy restatement (BLAS matmuls)
         x0 = random_states(ENV_E, 1)[:E]
         orc.actor_rollout(pol, x0[:256], jr.PRNGKey(0), 1, ENV_EPISODE)
@@ -869,11 +883,11 @@ def run_actor(args):
     E = hi - lo
     system = PendulumSystem()
     env = wrap(system, system.reset(device=dev).system_params, episode_length=ENV_EPISODE)
-    policy = acting.Policy(acting.PolicyParams([torch.from_numpy(w).to(dev) for w in pol.weights],
-                                               [torch.from_numpy(b).to(dev) for b in pol.biases]),
+    policy = acting.Policy(acting.PolicyParams([torch.from_numpy(w).to(dev) for w in pol_w],
+                                               [torch.from_numpy(b).to(dev) for b in pol_b]),
                            kernel=args.actor_kernel)
     x0_host = torch.from_numpy(random_states(ENV_E, 1)[lo:hi].copy()).pin_memory()
-    key = torch.from_numpy(jr.PRNGKey(0)).to(dev)       # one key for all ranks: a shard draws its slice of the stream
+    key = mbpo_b200.random.PRNGKey(0, dev)              # one key for all ranks: a shard draws its slice of the stream
     st = env.reset(x0_host.to(dev))
 
     def barrier():
@@ -957,14 +971,14 @@ def run_bptt(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    from oracle import jax_prng as jr, mbpo_oracle as orc
-    pol = orc.make_policy_params(seed=7, hidden=(64, 64))
+    pol_w, pol_b = make_policy_numpy(seed=7, hidden=(64, 64))
     metric = "BPTT rollout + cotangent pass, transitions/sec"
     if args.impl == "reference":
         if rank != 0:
             return
+        from oracle import jax_prng as jr, mbpo_oracle as orc                    # CPU arm only
         B = 4096
-        actor = orc.BpttActorParams(mlp=pol, init_stddev=2.0)
+        actor = orc.BpttActorParams(mlp=orc.PolicyParams(pol_w, pol_b), init_stddev=2.0)
         x0 = random_states(BPTT_B, 1)[:B]
         g = np.random.default_rng(3).standard_normal((B, BPTT_H)).astype(np.float32)
 
@@ -1005,11 +1019,11 @@ def run_bptt(args):
     B, H = hi - lo, BPTT_H
     system = PendulumSystem()
     sp = system.reset(device=dev).system_params
-    policy = acting.BpttActorPolicy(acting.PolicyParams([torch.from_numpy(w).to(dev) for w in pol.weights],
-                                                        [torch.from_numpy(b).to(dev) for b in pol.biases]), init_stddev=2.0)
+    policy = acting.BpttActorPolicy(acting.PolicyParams([torch.from_numpy(w).to(dev) for w in pol_w],
+                                                        [torch.from_numpy(b).to(dev) for b in pol_b]), init_stddev=2.0)
     x0_host = torch.from_numpy(random_states(BPTT_B, 1)[lo:hi].copy()).pin_memory()
     x0 = x0_host.to(dev)
-    key = torch.from_numpy(jr.PRNGKey(0)).to(dev)
+    key = mbpo_b200.random.PRNGKey(0, dev)
     g_lv = torch.from_numpy(np.random.default_rng(3).standard_normal((H, BPTT_B)).astype(np.float32)[:, lo:hi].copy()).to(dev).t()
     wv = torch.tensor([0.3, -0.2, 0.1], device=dev)
 
