@@ -1039,6 +1039,71 @@ def test_full_size_config3_properties(mb, cuda_device):
     assert torch.equal(new_sl.obs, new.obs[lo:hi])
 
 
+@pytest.mark.parametrize("E,T", [(1, 1), (31, 3), (129, 5), (257, 2), (500, 4)])
+def test_no_out_of_bounds_writes_for_ragged_sizes(mb, cuda_device, E, T):
+    """Every output of the env and policy-rollout kernels is placed inside a larger NaN-filled buffer: partial
+    warps, partial tiles and the row-transposing stores must leave the guard zones on both sides untouched, and
+    the guarded call must equal the plain call bit for bit."""
+    L = mb._lib
+    from mbpo_b200 import acting
+    from mbpo_b200.envs import wrap
+    from mbpo_b200.systems import PendulumSystem
+    G = 256                                                    # guard floats before and after every array
+    sys_ = PendulumSystem()
+    sp = sys_.reset(device=cuda_device).system_params
+    env = wrap(sys_, sp, episode_length=2)
+    pp = sys_.pack_params(sp)
+    x0 = _dev(_random_states(E, 151), cuda_device)
+    acts = _dev(np.random.default_rng(152).uniform(-1, 1, (T, E, 1)).astype(np.float32), cuda_device)
+    st = env.reset(x0)
+
+    def guarded(n, dtype=torch.float32):
+        buf = torch.full((n + 2 * G,), float("nan"), device=cuda_device, dtype=torch.float32)
+        if dtype != torch.float32:
+            buf = torch.full((n + 2 * G,), 0x7FC00000, device=cuda_device, dtype=torch.int64).to(dtype)
+        return buf, buf[G:G + n]
+
+    def intact(buf, n):
+        head, tail = buf[:G], buf[G + n:]
+        if buf.dtype == torch.float32:
+            return bool(torch.isnan(head).all()) and bool(torch.isnan(tail).all())
+        return bool((head == 0x7FC00000).all()) and bool((tail == 0x7FC00000).all())
+    # ---- env unroll -------------------------------------------------------------------------------------------
+    _, tr = env.unroll(st, acts)
+    bufs = {k: guarded(n) for k, n in dict(obs=3 * E, steps=E, done=E, nxt=3 * T * E, r=T * E, d=T * E, t=T * E).items()}
+    L.check(L.lib.mbpo_env_unroll(0, L.C.addressof(pp), 0, 3, 1, 2, 1, L.ptr(st.obs), L.ptr(st.info["steps"]),
+                                  L.ptr(st.done), bufs["obs"][1].data_ptr(), bufs["steps"][1].data_ptr(),
+                                  bufs["done"][1].data_ptr(), L.ptr(st.info["first_obs"]), L.ptr(acts), E, T, None,
+                                  bufs["r"][1].data_ptr(), bufs["d"][1].data_ptr(), bufs["nxt"][1].data_ptr(),
+                                  bufs["t"][1].data_ptr(), L.stream_ptr(cuda_device)))
+    for k, n in dict(obs=3 * E, steps=E, done=E, nxt=3 * T * E, r=T * E, d=T * E, t=T * E).items():
+        assert intact(bufs[k][0], n), k
+    assert torch.equal(bufs["nxt"][1].reshape(T, E, 3), tr.next_observation) and torch.equal(bufs["r"][1].reshape(T, E), tr.reward)
+    # ---- policy in the loop, both kernels ---------------------------------------------------------------------------
+    pol = orc.make_policy_params(seed=9, hidden=(64, 64))
+    key = _dev(ojr.PRNGKey(2), cuda_device)
+    for kernel in ("tcgen05", "cuda_cores"):
+        policy = _policy_on_device(mb, cuda_device, pol, kernel=kernel)
+        policy.emit_extras = True
+        _, _, tra = acting.get_experience(env, st, policy, key, T)
+        sizes = dict(obs=3 * E, steps=E, done=E, act=T * E, r=T * E, d=T * E, nxt=3 * T * E, t=T * E, raw=T * E, lp=T * E)
+        b = {k: guarded(n) for k, n in sizes.items()}
+        kb, kv = guarded(2, torch.uint32)
+        b["obs"][1].copy_(st.obs.reshape(-1)); b["steps"][1].copy_(st.info["steps"]); b["done"][1].copy_(st.done)
+        policy.struct.draw_total = 0
+        L.check(L.lib.mbpo_actor_rollout_extras(
+            0, L.C.addressof(pp), 0, mb.config.prng_mode, L.C.byref(policy.struct), 0, L.KEYS_SAC, L.ptr(key), 2, 1,
+            b["obs"][1].data_ptr(), b["steps"][1].data_ptr(), b["done"][1].data_ptr(), L.ptr(st.info["first_obs"]), E, T,
+            b["act"][1].data_ptr(), b["r"][1].data_ptr(), b["d"][1].data_ptr(), b["nxt"][1].data_ptr(),
+            b["t"][1].data_ptr(), kv.data_ptr(), b["raw"][1].data_ptr(), b["lp"][1].data_ptr(), L.stream_ptr(cuda_device)))
+        for k, n in sizes.items():
+            assert intact(b[k][0], n), (kernel, k)
+        assert intact(kb, 2), kernel
+        assert torch.equal(b["act"][1].reshape(T, E, 1), tra.action) and torch.equal(b["nxt"][1].reshape(T, E, 3), tra.next_observation)
+        assert torch.equal(b["lp"][1].reshape(T, E), tra.extras["policy_extras"]["log_prob"])
+        assert not bool(torch.isnan(b["act"][1]).any()) and not bool(torch.isnan(b["nxt"][1]).any())
+
+
 def test_empty_and_degenerate_inputs(mb, cuda_device):
     """Zero problems / envs / steps are valid calls that launch nothing; one env, one step and a one-step episode
     exercise the piece arithmetic at its corners."""
