@@ -46,7 +46,9 @@ UNIT = "transitions/s"
 # for roofline.achieved = executed lane-instructions per second; see DESIGN.md.
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
 # captures (profiles/r01c_plan_kernel_ncu_full.txt, profiles/r01c_env_pieces_kernel_ncu_full.txt); N = 1 only.
-NCU_TRAFFIC_BYTES = {"config2_batched_icem": 681216, "config3_env_rollouts": 268336640 + 1518277000}
+NCU_TRAFFIC_BYTES = {"config2_batched_icem": 681216, "config3_env_rollouts": 268336640 + 1518277000,
+                     # profiles/r01d_actor_tc_kernel_ncu_full.txt, profiles/r01b_ensemble_pp_kernel_ncu_full.txt
+                     "config3_actor_rollouts_tcgen05": 2874880 + 311553792, "config4_ensemble_icem": 8923136}
 LANE_INSTR_PER_TRANSITION = {("config2_batched_icem", "reference"): 229.7,
                              ("config2_batched_icem", "theta_carry"): 185.1}
 
@@ -596,7 +598,8 @@ def run_ensemble(args):
                     "api": "iCemTO.act with MLPEnsembleSystem (staged plan: sample -> ensemble rollout -> refit)"},
             "gpu_launches": steps * (1 + 3 * ENS_S + 1),
             "roofline": {"bound": "tensor", "kernel": "ensemble_rollout_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": NCU_TRAFFIC_BYTES["config4_ensemble_icem"] if world == 1 else None,
                          "kernel_ms": k_ms, "flops_per_launch": flops,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"},
             "cpu_baseline": None}, GUARD)
@@ -932,7 +935,9 @@ def run_actor(args):
             peak = 148 * 16 * sm_max * 1e6 / 1e12         # T MUFU results/s
             achieved = E * T * ACT_MUFU_PER_STEP / (ms * 1e-3) / 1e12
             roof = {"bound": "xu", "kernel": "actor_rollout_tc_kernel", "achieved": achieved, "peak": peak,
-                    "unit": "T MUFU/s", "frac": achieved / peak, "traffic": None, "note": ACT_TC_NOTE,
+                    "unit": "T MUFU/s", "frac": achieved / peak,
+                    "traffic": NCU_TRAFFIC_BYTES["config3_actor_rollouts_tcgen05"] if world == 1 else None,
+                    "note": ACT_TC_NOTE,
                     "tensor_tflops_issued": E * T * 3 * 2 * 2 * 64 * 64 / (ms * 1e-3) / 1e12}
         else:
             peak = 148 * 128 * sm_max * 1e6 / 1e12        # T FMA/s
