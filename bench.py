@@ -129,12 +129,21 @@ def host_info():
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle's plain-C twin (OpenMP over problems) on a bounded sample of the workload
 # ------------------------------------------------------------------------------------------------
+def host_threads() -> int:
+    """Host threads the CPU arm may use.  torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm runs
+    on rank 0 alone and asks OpenMP for the whole host explicitly."""
+    try:
+        return max(len(os.sched_getaffinity(0)), 1)
+    except AttributeError:
+        return max(os.cpu_count() or 1, 1)
+
+
 def cpu_reference_step(wl, steps: int, warmup: int, sample_B: int | None = None):
     """Times `steps` plan calls of the CPU restatement on a bounded sample; returns dict."""
     from oracle import c_twin, jax_prng as jr, mbpo_oracle as orc
     lib = c_twin.load(native=True)
     p = orc.ICemParams(**wl["params"])
-    cores = lib.orc_max_threads()
+    cores = host_threads()
     B = sample_B or max(cores * 32, 64)
     B = min(B, wl["B"]) if wl["B"] > 1 else 1
     cfg = c_twin.make_cfg(p, wl["horizon"])
@@ -144,10 +153,10 @@ def cpu_reference_step(wl, steps: int, warmup: int, sample_B: int | None = None)
     seq = np.zeros((B, wl["horizon"]), np.float32)
     used = cores
     for _ in range(max(warmup, 1)):
-        c_twin.optimize_batch(lib, cfg, p9, x0[: max(B // 8, 1)], keys[: max(B // 8, 1)], seq[: max(B // 8, 1)])
+        c_twin.optimize_batch(lib, cfg, p9, x0[: max(B // 8, 1)], keys[: max(B // 8, 1)], seq[: max(B // 8, 1)], cores)
     t0 = time.perf_counter()
     for _ in range(steps):
-        _, _, _, used = c_twin.optimize_batch(lib, cfg, p9, x0, keys, seq)
+        _, _, _, used = c_twin.optimize_batch(lib, cfg, p9, x0, keys, seq, cores)
     dt = (time.perf_counter() - t0) / steps
     tr = transitions_per_step(B, wl["horizon"], p)
     return dict(value=tr / dt, ms_per_step=dt * 1e3, cores=used, sample_B=B,
@@ -347,10 +356,10 @@ def run_env(args):
         x0 = random_states(ENV_E, 1)[:E]
         acts = np.random.default_rng(2).uniform(-1, 1, (T, E)).astype(np.float32)
         p9 = orc.PendulumParams().packed()
-        c_twin.env_rollout(lib, p9, x0[:256], acts[:, :256].copy(), ENV_EPISODE)
+        c_twin.env_rollout(lib, p9, x0[:256], acts[:, :256].copy(), ENV_EPISODE, num_threads=host_threads())
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            out = c_twin.env_rollout(lib, p9, x0, acts, ENV_EPISODE)
+            out = c_twin.env_rollout(lib, p9, x0, acts, ENV_EPISODE, num_threads=host_threads())
         dt = (time.perf_counter() - t0) / args.steps
         ncores, model = host_info()
         v = E * T / dt

@@ -42,6 +42,7 @@ struct ActorArgs {
   // policy head (MBPO_HEAD_*): NormalTanh of SAC/PPO, or the BPTT actor (bptt_optimizer.py:123-142,306-326)
   int head, shared_noise, normalize;
   int draw_offset, draw_total;   // env sharding of the draw normal(key, (draw_total, A))[draw_offset + e]
+  int tiles_per_cta;             // tcgen05 kernel: live 128-env tiles per CTA (1..4), fewer when E is small
   float sig_bias, sig_min, sig_max, action_clip;
   float obs_mean[3], obs_std[3];
   const float* w[ACT_MAX_HIDDEN + 1];  // [3,64], [64,64] x (num_hidden-1), [64,2]   (flax Dense kernels, [in, out])

@@ -222,8 +222,10 @@ __global__ void __launch_bounds__(THREADS, 1) actor_rollout_tc_kernel(const __gr
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
-  const int tile_idx = blockIdx.x * TILES_PER_CTA + g;
-  const int tile_e0 = tile_idx * TILE;
+  // Few envs: spread the tiles over more SMs (a.tiles_per_cta < 4) -- a tile alone on an SM steps faster than
+  // four sharing it, and the launch is T sequential steps whatever the grid.
+  const int tile_idx = blockIdx.x * a.tiles_per_cta + g;
+  const int tile_e0 = g < a.tiles_per_cta ? tile_idx * TILE : a.E;
   const uint32_t tmem_tile = tmem_base + g * 2 * W;                                          // two accumulators
   uint8_t* ring = smem + Smem::A + g * SLOTS * SLOT_BYTES;
   if (issuer_warp) {

@@ -681,8 +681,13 @@ int launch_actor_tc(const mbpo::ActorArgs& a, cudaStream_t st) {
   if (e != cudaSuccess)
     return fail(MBPO_ECUDA, "actor_rollout (tcgen05): smem attribute (%u B): %s", atc::Smem::TOTAL, cudaGetErrorString(e));
   const int tiles = (a.E + atc::TILE - 1) / atc::TILE;
-  const unsigned blocks = static_cast<unsigned>((tiles + atc::TILES_PER_CTA - 1) / atc::TILES_PER_CTA);
-  kernel<<<blocks, atc::THREADS, atc::Smem::TOTAL, st>>>(a);
+  const int sms = device_sm_count();
+  int tpc = (tiles + sms - 1) / sms;
+  tpc = tpc < 1 ? 1 : (tpc > atc::TILES_PER_CTA ? atc::TILES_PER_CTA : tpc);
+  ActorArgs b = a;
+  b.tiles_per_cta = tpc;
+  const unsigned blocks = static_cast<unsigned>((tiles + tpc - 1) / tpc);
+  kernel<<<blocks, atc::THREADS, atc::Smem::TOTAL, st>>>(b);
   return check_launch("actor_rollout_tc_kernel");
 }
 }  // namespace
