@@ -288,17 +288,24 @@ __global__ void __launch_bounds__(THREADS, 1) actor_rollout_tc_kernel(const __gr
     v.th = (MATH == MBPO_MATH_REFERENCE) ? 0.0f : atan2_bounded(v.s, v.c);
     v.f_th = (MATH == MBPO_MATH_REFERENCE) ? 0.0f : atan2_bounded(v.f_s, v.f_c);
     Key2 key{a.key_in[0], a.key_in[1]};
+    // (every thread carries the same keys) per step: k, k_t = split(k) in the caller's convention
+    auto advance_keys = [&](Key2 k, Key2& k_act, Key2& k_carry) {
+      k_act = k; k_carry = k;
+      if (a.key_convention != 2) {
+        Key2 first, second;
+        split2<PRNG>(k, first, second);
+        if (a.key_convention == 0) { k_carry = first; k_act = second; }   // sac.py:290
+        else { k_act = first; k_carry = second; }                          // acting.py:70
+      }
+    };
+    Key2 k_actor_next, key_next;
+    advance_keys(key, k_actor_next, key_next);
 
 #pragma unroll 1
     for (int t = 0; t < a.T; ++t) {
-      // ---- key plumbing (every thread carries the same keys) ----------------------------------------------
-      Key2 k_actor = key;
-      if (a.key_convention != 2) {
-        Key2 first, second;
-        split2<PRNG>(key, first, second);
-        if (a.key_convention == 0) { key = first; k_actor = second; }   // sac.py:290
-        else { k_actor = first; key = second; }                          // acting.py:70
-      }
+      // ---- key plumbing: this step's keys were derived during the previous step's last MMA wait ------------------
+      const Key2 k_actor = k_actor_next;
+      key = key_next;
       float xin[3] = {v.c, v.s, v.w};
       if (a.normalize) {
 #pragma unroll
@@ -382,7 +389,9 @@ __global__ void __launch_bounds__(THREADS, 1) actor_rollout_tc_kernel(const __gr
           if (lane == 0) mbar_arrive_a(bar0 + (4u + slot) * 8u);
           ++uses;
         }
-        if (s == 0) eps = actor_draw<PRNG>(a, k_actor, ee);   // network-independent: fills the first MMA wait
+        // network-independent work fills the MMA waits: this step's draw, the next step's keys
+        if (s == 0) eps = actor_draw<PRNG>(a, k_actor, ee);
+        if (s == HH - 1) advance_keys(key, k_actor_next, key_next);
         if (to_mma) {
           mbar_wait_a(bar0 + 16u, layer_phase);
           layer_phase ^= 1u;
