@@ -101,9 +101,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ENS_THREADS, 1)
   uint32_t phase_w = 0;
   uint32_t ph_acc[2] = {0, 0}, ph_out[2] = {0, 0};   // epilogue warps
   uint32_t ph_a0[2] = {0, 0}, ph_stage[2] = {0, 0};  // MMA warp
-  uint32_t ring_pos = 0;                             // chunks produced (epilogue warps) / consumed (MMA warp) so far
-  uint32_t ring_slot = 0, ring_use = 0;              // ring_pos % PP_SLOTS, ring_pos / PP_SLOTS
-  (void)ring_pos;
+  // position in the A-chunk ring: chunks produced (epilogue warps) / consumed (MMA warp) so far, kept as
+  // (position % PP_SLOTS, position / PP_SLOTS)
+  uint32_t ring_slot = 0, ring_use = 0;
   const PendulumConsts pc(a.reward);
 
   const int num_groups = (a.R + 4 * TILE_M - 1) / (4 * TILE_M);
