@@ -11,6 +11,13 @@ Reference files restated here (paths relative to /root/reference):
   mbpo/systems/brax_wrapper.py:40-50, mbpo/optimizers/policy_optimizers/brax_utils/
   training.py:71-137, .../sac/acting.py:35-55              vmapped env step + wrappers
   mbpo/utils/network_utils.py:5-17                         MLP template (learned dynamics)
+  mbpo/optimizers/policy_optimizers/sac/sac_networks.py:58-73, sac/parametric_distribution.py:66-125,
+  ppo/ppo_network.py:59-84, sac/sac.py:283-292             policy in the env loop (NormalTanh sample, log_prob)
+  mbpo/utils/optimizer_utils.py:62-131                     rollout_policy, lambda_return
+  mbpo/optimizers/policy_optimizers/bptt_optimizer.py:107-142,306-376   BPTT actor / act / the differentiated rollout
+    (the cotangent pass is derived by hand here and pinned against finite differences and torch autograd,
+    tests/test_oracle_bptt.py; distrax's Normal.log_prob / Tanh.forward_log_det_jacobian are restated from the
+    published distrax 0.1.x formulas -- distrax is a third-party dependency absent from /root/reference)
 
 PARITY PINNING: the reference is pure JAX, JAX cannot be installed here, and the
 reference's tests hold no golden vectors (tests/test_icemopt.py:37-38 is the threshold
