@@ -660,6 +660,46 @@ def test_env_unroll_ragged_episode_pieces(mb, cuda_device, math_mode, E, T, epis
                                           L.ptr(r), L.ptr(d), L.ptr(n), L.ptr(t_), L.stream_ptr(cuda_device)))
 
 
+def test_env_unroll_random_shapes_match_sequential_scan(mb, cuda_device):
+    """Thirty random (envs, steps, episode_length, action_repeat, step counters, done flags): the episode-piece
+    launch equals the one-scan-per-env launch bit for bit, whichever loop (mask-free or general) each warp takes."""
+    L = mb._lib
+    from mbpo_b200.systems import PendulumSystem
+    sys_ = PendulumSystem()
+    sp = sys_.reset(device=cuda_device).system_params
+    pp = sys_.pack_params(sp)
+    rng = np.random.default_rng(2024)
+    for case in range(30):
+        E = int(rng.choice([1, 7, 32, 33, 64, 100, 128, 255, 256, 1000, 4097]))
+        T = int(rng.integers(1, 70))
+        ep = int(rng.integers(1, 40))
+        rep = int(rng.choice([1, 1, 1, 2, 3]))
+        uniform = bool(rng.integers(0, 2))
+        x0, first = _random_states(E, 500 + case), _random_states(E, 900 + case)
+        steps0 = (np.zeros(E) if uniform else rng.integers(0, ep, E) // rep * rep).astype(np.float32)
+        done0 = (np.zeros(E) if uniform else rng.uniform(size=E) < 0.3).astype(np.float32)
+        acts = _dev(rng.uniform(-1.2, 1.2, (T, E)).astype(np.float32), cuda_device)
+        outs = []
+        for which in ("unroll", "rollout"):
+            obs, steps, done = _dev(x0, cuda_device), _dev(steps0, cuda_device), _dev(done0, cuda_device)
+            n = torch.full((T, E, 3), float("nan"), device=cuda_device)
+            r, d, t_ = (torch.full((T, E), float("nan"), device=cuda_device) for _ in range(3))
+            if which == "unroll":
+                o2, s2, d2 = torch.empty_like(obs), torch.empty_like(steps), torch.empty_like(done)
+                L.check(L.lib.mbpo_env_unroll(0, L.C.addressof(pp), 0, 3, 1, ep, rep, L.ptr(obs), L.ptr(steps), L.ptr(done),
+                                              L.ptr(o2), L.ptr(s2), L.ptr(d2), L.ptr(_dev(first, cuda_device)), L.ptr(acts),
+                                              E, T, None, L.ptr(r), L.ptr(d), L.ptr(n), L.ptr(t_), L.stream_ptr(cuda_device)))
+                outs.append((n, r, d, t_, o2, s2, d2))
+            else:
+                L.check(L.lib.mbpo_env_rollout(0, L.C.addressof(pp), 0, 3, 1, ep, rep, L.ptr(obs), L.ptr(steps), L.ptr(done),
+                                               L.ptr(_dev(first, cuda_device)), L.ptr(acts), E, T, None, L.ptr(r), L.ptr(d),
+                                               L.ptr(n), L.ptr(t_), L.stream_ptr(cuda_device)))
+                outs.append((n, r, d, t_, obs, steps, done))
+        for a_, b_ in zip(*outs):
+            assert torch.equal(a_, b_), (case, E, T, ep, rep, uniform)
+        assert not bool(torch.isnan(outs[0][0]).any()) and not bool(torch.isnan(outs[0][1]).any())
+
+
 # ---------------------------------------------------------------------------------------------
 # policy in the env loop: actor_step / generate_unroll / get_experience (SURVEY 8f-2)
 # ---------------------------------------------------------------------------------------------
