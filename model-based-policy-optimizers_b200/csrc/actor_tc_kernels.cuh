@@ -39,17 +39,25 @@ constexpr int TILES_PER_CTA = 4;
 constexpr int ENV_THREADS_ = TILE * TILES_PER_CTA;      // 512 producer threads: thread = env
 constexpr int THREADS = ENV_THREADS_ + 32 * TILES_PER_CTA;   // + one MMA-issuing warp per tile (one lane active)
 constexpr int W = ACT_W;                  // 64
-constexpr int QC = 16;                    // columns a producer emits per ring slot (two K = 8 MMA steps)
+#ifndef MBPO_ATC_QC
+#define MBPO_ATC_QC 16
+#endif
+#ifndef MBPO_ATC_SLOTS
+#define MBPO_ATC_SLOTS 2
+#endif
+constexpr int QC = MBPO_ATC_QC;           // columns a producer emits per ring slot (QC / 8 MMA K-steps)
 constexpr int QUARTERS = W / QC;
 constexpr uint32_t A_LBO_ = TILE * 16;    // 2048: next 16-byte K-chunk of A
 constexpr uint32_t W_LBO_ = W * 16;       // 1024: next 16-byte K-chunk of W
 constexpr uint32_t SLOT_PLANE = (QC / 4) * A_LBO_;   // 8192: one plane (hi or lo) of a slot
 constexpr uint32_t SLOT_BYTES = 2 * SLOT_PLANE;      // 16384
-constexpr int SLOTS = 2;
+constexpr int SLOTS = MBPO_ATC_SLOTS;
 constexpr uint32_t W_PLANE = W * W * 4;   // 16384
 constexpr int MAX_HH = 2;                 // hidden -> hidden layers held in shared memory (num_hidden <= 3)
 constexpr int TMEM_COLS_ = 512;           // 4 tiles x 2 accumulators x 64 fp32 columns
 
+constexpr int BARS_PER_TILE = 2 * SLOTS + 2;
+constexpr uint32_t BAR_FULL = SLOTS * 8u, BAR_LAYER = 2u * SLOTS * 8u;   // byte offsets inside a tile's barrier block
 struct Smem {
   static constexpr uint32_t A = 0;                                         // [tile][slot][hi, lo]
   static constexpr uint32_t WH = A + TILES_PER_CTA * SLOTS * SLOT_BYTES;   // [layer][hi, lo] planes
@@ -59,8 +67,8 @@ struct Smem {
   static constexpr uint32_t WO = BH + MAX_HH * W * 4;                      // float [64][2]
   static constexpr uint32_t BO = WO + W * 2 * 4;                           // float [2] (+ pad)
   static constexpr uint32_t TILES = BO + 16;                               // float [16 warps][96]: row transposition
-  static constexpr uint32_t BARS = TILES + (ENV_THREADS_ / 32) * 96 * 4;   // per tile: slot_free[2], layer_done, full[2]
-  static constexpr uint32_t TMEM_PTR = BARS + TILES_PER_CTA * 8 * 8;
+  static constexpr uint32_t BARS = TILES + (ENV_THREADS_ / 32) * 96 * 4;   // per tile: slot_free[SLOTS], full[SLOTS], layer_done
+  static constexpr uint32_t TMEM_PTR = BARS + TILES_PER_CTA * BARS_PER_TILE * 8;
   static constexpr uint32_t TOTAL = TMEM_PTR + 16;
 };
 static_assert(Smem::TOTAL <= 227 * 1024, "tensor-core actor kernel shared memory plan exceeds 227 KB");
@@ -91,6 +99,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ldq(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld16(taddr, v); }
+__device__ __forceinline__ void tmem_ldq(uint32_t taddr, uint32_t (&v)[8]) { tmem_ld8(taddr, v); }
 // mbarrier helpers on precomputed 32-bit shared addresses (the generic -> shared conversion stays out of the loops)
 __device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -180,7 +196,7 @@ __global__ void __launch_bounds__(THREADS, 1) actor_rollout_tc_kernel(const __gr
   float* s_wo = reinterpret_cast<float*>(smem + Smem::WO);
   float* s_bo = reinterpret_cast<float*>(smem + Smem::BO);
   float* tile = reinterpret_cast<float*>(smem + Smem::TILES) + (warp & 15) * 96;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::BARS) + g * 8;   // slot_free[2], layer_done, -, full[2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::BARS) + g * BARS_PER_TILE;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + Smem::TMEM_PTR);
   const int L = a.num_hidden, HH = L - 1;
 
@@ -191,11 +207,11 @@ __global__ void __launch_bounds__(THREADS, 1) actor_rollout_tc_kernel(const __gr
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (!issuer_warp && r == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    mbar_init(&bars[2], 1);
-    mbar_init(&bars[4], TILE / 32);   // one arrival per producer warp
-    mbar_init(&bars[5], TILE / 32);
+    for (int i = 0; i < SLOTS; ++i) {
+      mbar_init(&bars[i], 1);                    // slot_free: one tcgen05.commit
+      mbar_init(&bars[SLOTS + i], TILE / 32);    // full: one arrival per producer warp
+    }
+    mbar_init(&bars[2 * SLOTS], 1);              // layer_done
     fence_barrier_init();
   }
   for (int l = 0; l < HH; ++l) {
@@ -244,22 +260,22 @@ __global__ void __launch_bounds__(THREADS, 1) actor_rollout_tc_kernel(const __gr
           const uint32_t d = tmem_tile + (s & 1) * W;
 #pragma unroll 1
           for (int qd = 0; qd < QUARTERS; ++qd) {
-            const uint32_t slot = uses & 1u;
-            mbar_wait_a(bar0 + (4u + slot) * 8u, (uses >> 1) & 1u);   // the four producer warps have written the slot
+            const uint32_t slot = uses % SLOTS;
+            mbar_wait_a(bar0 + BAR_FULL + slot * 8u, (uses / SLOTS) & 1u);   // the four producer warps have written the slot
             tc_fence_after();
             // ---- 6 x tcgen05.mma (M128 N64 K8): lo.hi + hi.lo + hi.hi for the two K-steps of this slot ----------------
             const uint64_t a_hi = da0 + ((slot * SLOT_BYTES) >> 4), a_lo = a_hi + (SLOT_PLANE >> 4);
-            const uint64_t b_hi = db0 + ((static_cast<uint32_t>(s) * 2u * W_PLANE + qd * 4u * W_LBO_) >> 4);
+            const uint64_t b_hi = db0 + ((static_cast<uint32_t>(s) * 2u * W_PLANE + qd * (QC / 4) * W_LBO_) >> 4);
             const uint64_t b_lo = b_hi + (W_PLANE >> 4);
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
+            for (int j = 0; j < QC / 8; ++j) {
               const uint64_t ao = static_cast<uint64_t>((j * 2 * A_LBO_) >> 4), bo = static_cast<uint64_t>((j * 2 * W_LBO_) >> 4);
               umma_tf32_ss(d, a_lo + ao, b_hi + bo, IDESC, (qd | j) ? 1u : 0u);     // small terms first
               umma_tf32_ss(d, a_hi + ao, b_lo + bo, IDESC, 1u);
               umma_tf32_ss(d, a_hi + ao, b_hi + bo, IDESC, 1u);
             }
             umma_commit_a(bar0 + slot * 8u);                        // slot free when these MMAs have read it
-            if (qd == QUARTERS - 1) umma_commit_a(bar0 + 16u);      // accumulator s & 1 complete
+            if (qd == QUARTERS - 1) umma_commit_a(bar0 + BAR_LAYER);   // accumulator s & 1 complete
             ++uses;
           }
         }
@@ -349,7 +365,7 @@ __global__ void __launch_bounds__(THREADS, 1) actor_rollout_tc_kernel(const __gr
           } else {
             // ---- epilogue of the previous layer: 16 accumulator columns, bias + swish ---------------------------
             uint32_t acc[QC];
-            tmem_ld16(acc_src + qd * QC, acc);
+            tmem_ldq(acc_src + qd * QC, acc);
 #pragma unroll
             for (int j4 = 0; j4 < QC / 4; ++j4) {
               const float4 bb = *reinterpret_cast<const float4*>(bias + qd * QC + j4 * 4);
@@ -372,8 +388,8 @@ __global__ void __launch_bounds__(THREADS, 1) actor_rollout_tc_kernel(const __gr
             continue;
           }
           // ---- hi / lo planes of the 16 columns into the ring slot ----------------------------------------------------
-          const uint32_t slot = uses & 1u;
-          if (uses >= SLOTS) mbar_wait_a(bar0 + slot * 8u, ((uses >> 1) - 1u) & 1u);   // the MMAs that read it have retired
+          const uint32_t slot = uses % SLOTS;
+          if (uses >= SLOTS) mbar_wait_a(bar0 + slot * 8u, ((uses / SLOTS) - 1u) & 1u);   // the MMAs that read it have retired
           uint8_t* dst = ring + slot * SLOT_BYTES + r * 16;
 #pragma unroll
           for (int j4 = 0; j4 < QC / 4; ++j4) {
@@ -386,14 +402,14 @@ __global__ void __launch_bounds__(THREADS, 1) actor_rollout_tc_kernel(const __gr
           fence_proxy_async();      // generic-proxy writes of A -> visible to the tensor core
           tc_fence_before();        // and this thread's accumulator reads are ordered before the MMAs they feed
           __syncwarp();
-          if (lane == 0) mbar_arrive_a(bar0 + (4u + slot) * 8u);
+          if (lane == 0) mbar_arrive_a(bar0 + BAR_FULL + slot * 8u);
           ++uses;
         }
         // network-independent work fills the MMA waits: this step's draw, the next step's keys
         if (s == 0) eps = actor_draw<PRNG>(a, k_actor, ee);
         if (s == HH - 1) advance_keys(key, k_actor_next, key_next);
         if (to_mma) {
-          mbar_wait_a(bar0 + 16u, layer_phase);
+          mbar_wait_a(bar0 + BAR_LAYER, layer_phase);
           layer_phase ^= 1u;
           tc_fence_after();
         }
