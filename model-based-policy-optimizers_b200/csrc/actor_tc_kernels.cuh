@@ -107,6 +107,7 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
 }
 __device__ __forceinline__ void tmem_ldq(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld16(taddr, v); }
 __device__ __forceinline__ void tmem_ldq(uint32_t taddr, uint32_t (&v)[8]) { tmem_ld8(taddr, v); }
+__device__ __forceinline__ void tmem_ldq(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld32(taddr, v); }
 // mbarrier helpers on precomputed 32-bit shared addresses (the generic -> shared conversion stays out of the loops)
 __device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
