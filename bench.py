@@ -1147,6 +1147,129 @@ def emit_json(obj, guard):
     os.write(guard.saved, (json.dumps(obj) + "\n").encode())
 
 
+# ------------------------------------------------------------------------------------------------
+# replay insert: the Transition buffers of a config-3 unroll appended to SAC's UniformSamplingQueue
+# ------------------------------------------------------------------------------------------------
+REPLAY_E, REPLAY_T, REPLAY_D, REPLAY_ROWS = 65536, 200, 10, 1 << 24
+
+
+def run_replay(args):
+    """One step = UniformSamplingQueue.insert of 65,536 envs x 200 steps (13.1 M rows of 10 floats, sac.py:296-303)
+    into a queue of 2**24 rows; the queue is full after the second step, so the timed inserts are the ones on which
+    brax rolls the whole buffer.  Algorithmic bytes: 40 B read + 40 B written per row."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    E, T, D = REPLAY_E, REPLAY_T, REPLAY_D
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import brax_replay as obr, jax_prng as jr
+        Es, Ts, R = 4096, 50, 1 << 18          # bounded sample: 204,800 rows into a full queue of 262,144
+        rng = np.random.default_rng(0)
+        f = [rng.standard_normal((Ts * Es, w)).astype(np.float32) for w in (3, 1, 1, 1, 3, 1)]
+        q = obr.UniformSamplingQueue(R, D, 1)
+        st = q.insert(q.init(jr.PRNGKey(0)), np.zeros((R, D), np.float32))
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            st = q.insert(st, np.concatenate(f, axis=1))
+        dt = (time.perf_counter() - t0) / args.steps
+        ncores, model = host_info()
+        v = Es * Ts / dt
+        emit_json({"impl": "reference", "metric": "replay rows inserted/sec", "value": v, "unit": "rows/s",
+                   "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+                   "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                   "config": {"workload": "config3_replay_insert", "envs": E, "steps_per_call": T, "row_floats": D},
+                   "cpu_baseline": {"value": v, "unit": "rows/s", "cores": 1, "kind": "port",
+                                    "sample": "%d rows per step into a full queue of %d rows (NumPy restatement of "
+                                              "brax insert_internal: ravel + roll + slice update)" % (Es * Ts, R),
+                                    "host_cpu": model},
+                   "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}, GUARD)
+        return
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import mbpo_b200
+    from mbpo_b200.replay_buffers import UniformSamplingQueue
+    from mbpo_b200.utils.optimizer_utils import Transition
+    z = lambda *sh: torch.zeros(sh, device=dev)
+    dummy = Transition(z(3), z(1), z(), z(), z(3), {"state_extras": {"truncation": z()}, "policy_extras": {}})
+    q = UniformSamplingQueue(REPLAY_ROWS, dummy, 256)
+    st = q.init(mbpo_b200.random.PRNGKey(0, dev))
+    g = lambda *sh: torch.randn(sh, device=dev)
+    buf = g(T + 1, E, 3)
+    tr = Transition(buf[:T], g(T, E, 1), g(T, E), g(T, E), buf[1:], {"state_extras": {"truncation": g(T, E)},
+                                                                      "policy_extras": {}})
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        st = q.insert(st, tr)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        for k in range(args.steps):
+            starts[k].record()
+            st = q.insert(st, tr)
+            ends[k].record()
+        barrier()
+    ms = sum(a.elapsed_time(b) for a, b in zip(starts, ends)) / args.steps
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    rows = E * T
+    # end to end: a sampled batch (the learner's input) read back to the host after every insert
+    batch_host = torch.empty((256, D), dtype=torch.float32).pin_memory()
+    rew_host_in = torch.randn((T, E), dtype=torch.float32).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        rew = rew_host_in.to(dev, non_blocking=True)
+        st = q.insert(st, tr._replace(reward=rew))
+        st, batch = q.sample(st)
+        batch_host[:, 4].copy_(batch.reward, non_blocking=True)
+        torch.cuda.synchronize(dev)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = rows * 8 * D / (ms * 1e-3) / 1e9
+        cpu = None
+        emit_json({
+            "metric": "replay rows inserted/sec", "value": world * rows / (ms * 1e-3), "unit": "rows/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config3_replay_insert", "envs": E, "steps_per_call": T, "row_floats": D,
+                       "queue_rows": REPLAY_ROWS, "parallelism": "one queue per GPU x%d" % world,
+                       "l2": "%.2f GB moved per insert >> 126 MB L2" % (rows * 8 * D / 1e9)},
+            "clocks": clk.summary(),
+            "e2e": {"value": world * rows / e2e_s, "unit": "rows/s", "ms_per_step": e2e_s * 1e3,
+                    "h2d_bytes_per_step": int(rew_host_in.numel() * 4), "d2h_bytes_per_step": 256 * 4,
+                    "api": "UniformSamplingQueue.insert(Transition with rewards from pinned host) + sample() -> "
+                           "rewards of the batch to the host"},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "hbm", "kernel": "replay_pack_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "algorithmic_bytes_per_launch": rows * 8 * D, "algorithmic_bytes_per_row": 8 * D,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
+            "cpu_baseline": cpu}, GUARD)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -1154,7 +1277,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["config1_closed_loop", "config3_env_rollouts", "config3_actor_rollouts",
-                                                               "config4_ensemble_icem", "config5_sweep", "bptt_rollout_grad"],
+                                                               "config4_ensemble_icem", "config5_sweep", "bptt_rollout_grad",
+                                                               "config3_replay_insert"],
                     default="config2_batched_icem")
     ap.add_argument("--math", choices=["reference", "theta_carry"], default="reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -1177,6 +1301,8 @@ def main():
             return run_bptt(args)
         if args.workload == "config5_sweep":
             return run_sweep(args)
+        if args.workload == "config3_replay_insert":
+            return run_replay(args)
         wl = WORKLOADS[args.workload]
         if args.impl == "reference":
             run_reference(args, args.workload, wl)

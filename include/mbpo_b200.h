@@ -112,7 +112,7 @@ int mbpo_abi_version(void);
 const char* mbpo_last_error(void);
 /* sizeof() of the ABI structs, so that a foreign binding can verify its own layout:
  * which = 0 MbpoIcemCfg, 1 MbpoPendulumParams, 2 MbpoMlpEnsembleParams, 3 MbpoIcemTrace,
- * 4 MbpoPolicyParams;
+ * 4 MbpoPolicyParams, 5 MbpoReplayState, 6 MbpoReplayFields;
  * anything else returns 0. */
 size_t mbpo_struct_size(int which);
 
@@ -328,6 +328,65 @@ int mbpo_mlp_dynamics_forward(const MbpoMlpEnsembleParams* params_host, const fl
  * the horizon-mean reward.  One fused tcgen05 kernel (CTA pairs, weights resident in shared memory). */
 int mbpo_ensemble_rollout(const MbpoMlpEnsembleParams* params_host, int horizon, const float* x0,
                           const float* actions, int B, int M, int summarize, float* returns_out, void* stream);
+
+/* ---- replay buffer (brax UniformSamplingQueue) and BraxWrapper.reset ---------------------------
+ * The data format either side of the env rollouts: SAC appends every collected Transition to a
+ * brax UniformSamplingQueue (mbpo/optimizers/policy_optimizers/sac/sac.py:202-205,303) and
+ * BraxWrapper.reset draws each env's first observation from the true buffer
+ * (mbpo/systems/brax_wrapper.py:25-38, tests/test_sac.py:15-28).  brax is a third-party
+ * dependency; its published algorithm (brax/training/replay_buffers.py: QueueBase.insert_internal,
+ * UniformSamplingQueue.sample_internal) is restated in oracle/brax_replay.py.
+ *
+ * Storage is a RING: logical row i (brax's data[i]) lives in physical row (head + i) % capacity.
+ * brax's jnp.roll(data, roll) of the whole buffer on every insert into a full queue becomes
+ * head -= roll; no row moves.  A row is ravel_pytree(Transition): the fields side by side. */
+typedef struct MbpoReplayState {
+  float* data;               /* device, [capacity, row_width] physical rows            */
+  long long capacity;        /* max_replay_size                                         */
+  int32_t row_width;         /* D                                                       */
+  int32_t reserved;
+  long long head;            /* physical row of logical row 0                           */
+  long long insert_position; /* brax ReplayBufferState.insert_position (logical)        */
+  long long sample_position; /* brax ReplayBufferState.sample_position (logical)        */
+} MbpoReplayState;
+
+#define MBPO_REPLAY_MAX_FIELDS 8
+typedef struct MbpoReplayFields {
+  int32_t num_fields;
+  int32_t width[MBPO_REPLAY_MAX_FIELDS];    /* columns of field f                      */
+  const float* ptr[MBPO_REPLAY_MAX_FIELDS]; /* device, [n_rows, width[f]] dense        */
+} MbpoReplayFields;
+
+/* jax.random.randint(key, (n,), minval, maxval) (int32) for M keys: out int32[M, n]. */
+int mbpo_prng_randint(const uint32_t* keys /*[M,2]*/, int M, int n, int prng_mode, int minval, int maxval,
+                      int32_t* out /*[M,n]*/, void* stream);
+
+/* QueueBase.insert_internal: appends n_rows rows assembled from the field arrays (time-major
+ * rollout buffers [T, E, w] are [T*E, w] dense: the order jnp.concatenate gives at sac.py:296) and
+ * updates head / insert_position / sample_position of *state_host exactly like brax's roll.
+ * n_rows > capacity is MBPO_EINVAL (brax raises ValueError). */
+int mbpo_replay_insert(MbpoReplayState* state_host, const MbpoReplayFields* fields_host, long long n_rows,
+                       void* stream);
+
+/* UniformSamplingQueue.sample_internal: key_out = split(key)[0]; idx = randint(split(key)[1],
+ * (batch,), sample_position, insert_position); batch_out[i] = data[idx[i] mod capacity].
+ * idx_out may be NULL. */
+int mbpo_replay_sample(const MbpoReplayState* state_host, const uint32_t* key /*[2]*/, int prng_mode,
+                       int sample_batch_size, uint32_t* key_out /*[2]*/, int32_t* idx_out /*[batch]*/,
+                       float* batch_out /*[batch, D]*/, void* stream);
+
+/* Logical rows [first, first + n) in brax's order (ReplayBufferState.data[first:first+n]). */
+int mbpo_replay_read(const MbpoReplayState* state_host, long long first, long long n, float* rows_out /*[n,D]*/,
+                     void* stream);
+
+/* vmap(BraxWrapper.reset)(rngs) (brax_wrapper.py:25-38 under VmapWrapper.reset,
+ * brax_utils/training.py:66-69): per env keys = split(rng, 2); the buffer is sampled under keys[0]
+ * (a batch of sample_batch_size, element 0 kept, :30); obs = row[0:x_dim], reward = row[reward_col];
+ * system_params.key = keys[1].  idx_out (the logical row each env drew) may be NULL. */
+int mbpo_env_reset_from_buffer(const MbpoReplayState* state_host, const uint32_t* rngs /*[E,2]*/, int E,
+                               int prng_mode, int sample_batch_size, int x_dim, int reward_col,
+                               float* obs_out /*[E,X]*/, float* reward_out /*[E]*/,
+                               uint32_t* sys_key_out /*[E,2]*/, int32_t* idx_out /*[E]*/, void* stream);
 
 #ifdef __cplusplus
 }

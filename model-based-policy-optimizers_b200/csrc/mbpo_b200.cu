@@ -188,6 +188,8 @@ size_t mbpo_struct_size(int which) {
     case 2: return sizeof(MbpoMlpEnsembleParams);
     case 3: return sizeof(MbpoIcemTrace);
     case 4: return sizeof(MbpoPolicyParams);
+    case 5: return sizeof(MbpoReplayState);
+    case 6: return sizeof(MbpoReplayFields);
     default: return 0;
   }
 }

@@ -1,0 +1,314 @@
+// Replay buffer (brax UniformSamplingQueue) and BraxWrapper.reset: C ABI + kernels.
+//
+// Replaces brax/training/replay_buffers.py QueueBase.insert_internal / UniformSamplingQueue.sample_internal as the
+// reference calls them at mbpo/optimizers/policy_optimizers/sac/sac.py:202-205,303 and
+// mbpo/systems/brax_wrapper.py:25-38.  The queue is a ring in HBM (logical row i = physical row (head + i) % capacity),
+// so inserting into a full queue moves no rows (brax rolls the whole buffer).  HBM-bound byte shuffling: insert reads
+// and writes 4*D bytes per row, both coalesced.
+#include <cuda_runtime.h>
+
+#include "../../include/mbpo_b200.h"
+#include "host_util.h"
+#include "threefry.cuh"
+
+using namespace mbpo;
+
+namespace {
+
+struct FieldTable {
+  int num_fields;
+  int col_end[MBPO_REPLAY_MAX_FIELDS];  // exclusive prefix end of field f
+  int width[MBPO_REPLAY_MAX_FIELDS];
+  const float* ptr[MBPO_REPLAY_MAX_FIELDS];
+};
+
+// offset of randint inside [0, span): jax/_src/random.py _randint on 32-bit words
+template <int MODE>
+__device__ __forceinline__ uint32_t randint_offset_at(Key2 key, uint32_t n, uint32_t w, uint32_t span) {
+  Key2 k1, k2;
+  split2<MODE>(key, k1, k2);
+  const uint32_t hi = random_bits_at<MODE>(k1, n, w);
+  const uint32_t lo = random_bits_at<MODE>(k2, n, w);
+  uint32_t mult = 65536u % span;
+  mult = (mult * mult) % span;
+  const uint32_t off = (hi % span) * mult + (lo % span);
+  return off % span;
+}
+
+__host__ __device__ __forceinline__ uint32_t randint_span(int minval, int maxval) {
+  return (maxval <= minval) ? 1u : static_cast<uint32_t>(maxval) - static_cast<uint32_t>(minval);
+}
+
+template <int MODE>
+__global__ void prng_randint_kernel(const uint32_t* __restrict__ keys, long long total, int n, int minval,
+                                    uint32_t span, int32_t* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long m = i / n;
+  const uint32_t w = static_cast<uint32_t>(i % n);
+  const Key2 k{keys[2 * m], keys[2 * m + 1]};
+  out[i] = static_cast<int32_t>(static_cast<uint32_t>(minval) + randint_offset_at<MODE>(k, n, w, span));
+}
+
+// One CTA packs `rows_per_cta` consecutive rows through shared memory: every field's block of the tile is one dense
+// run in HBM and is read with full-line loads (all of a thread's loads are issued before the first is used), the tile
+// is assembled row-major in shared memory, and leaves as one dense run of the ring (split only at the ring's end).
+constexpr int PACK_THREADS = 256;
+constexpr int PACK_MAX_LOADS = 10;  // loads a thread keeps in flight
+
+__global__ void __launch_bounds__(PACK_THREADS)
+replay_pack_kernel(FieldTable ft, int D, int rows_per_cta, long long n_rows, float* __restrict__ data,
+                   long long capacity, long long first_physical) {
+  extern __shared__ float tile[];  // [rows_per_cta, D]
+  const long long row0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
+  const long long left = n_rows - row0;
+  const unsigned rows = static_cast<unsigned>(left < rows_per_cta ? left : rows_per_cta);
+  // The tile's words in field-major order: q in [rows * col_start(f), rows * col_end(f)) walks field f's dense block.
+  const unsigned total = rows * static_cast<unsigned>(D);
+  for (unsigned base = threadIdx.x; base < total; base += PACK_THREADS * PACK_MAX_LOADS) {
+    float v[PACK_MAX_LOADS];
+    unsigned slot[PACK_MAX_LOADS];
+#pragma unroll
+    for (int k = 0; k < PACK_MAX_LOADS; ++k) {
+      const unsigned q = base + k * PACK_THREADS;
+      slot[k] = 0xFFFFFFFFu;
+      if (q < total) {
+        int f = 0;
+#pragma unroll
+        for (int g = 0; g < MBPO_REPLAY_MAX_FIELDS - 1; ++g)
+          f += (g < ft.num_fields - 1 && q >= rows * static_cast<unsigned>(ft.col_end[g])) ? 1 : 0;
+        const unsigned w = static_cast<unsigned>(ft.width[f]);
+        const unsigned col0 = static_cast<unsigned>(ft.col_end[f]) - w;
+        const unsigned j = q - rows * col0;
+        const unsigned r = (w == 1u) ? j : j / w;
+        v[k] = __ldcs(ft.ptr[f] + row0 * w + j);
+        slot[k] = r * static_cast<unsigned>(D) + col0 + (j - r * w);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < PACK_MAX_LOADS; ++k)
+      if (slot[k] != 0xFFFFFFFFu) tile[slot[k]] = v[k];
+  }
+  __syncthreads();
+  const unsigned words = rows * static_cast<unsigned>(D);
+  long long p0 = first_physical + row0;                  // physical row of the tile's first row
+  if (p0 >= capacity) p0 -= capacity;
+  const long long until_end = (capacity - p0) * D;       // words before the ring wraps
+  float* __restrict__ dst = data + p0 * D;
+  for (unsigned i = threadIdx.x; i < words; i += PACK_THREADS) {
+    if (static_cast<long long>(i) < until_end) dst[i] = tile[i];
+    else data[static_cast<long long>(i) - until_end] = tile[i];
+  }
+}
+
+template <int MODE>
+__global__ void replay_sample_kernel(const float* __restrict__ data, long long capacity, int D, long long head,
+                                     const uint32_t* __restrict__ key, int batch, int minval, uint32_t span,
+                                     uint32_t* __restrict__ key_out, int32_t* __restrict__ idx_out,
+                                     float* __restrict__ batch_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch) return;
+  const Key2 k{key[0], key[1]};
+  Key2 next, sample_key;
+  split2<MODE>(k, next, sample_key);
+  if (i == 0) {
+    key_out[0] = next.k0;
+    key_out[1] = next.k1;
+  }
+  const int32_t idx = static_cast<int32_t>(static_cast<uint32_t>(minval) +
+                                           randint_offset_at<MODE>(sample_key, static_cast<uint32_t>(batch),
+                                                                   static_cast<uint32_t>(i), span));
+  if (idx_out) idx_out[i] = idx;
+  long long l = static_cast<long long>(idx) % capacity;  // jnp.take(mode='wrap')
+  if (l < 0) l += capacity;
+  long long p = head + l;
+  if (p >= capacity) p -= capacity;
+  const float* src = data + p * D;
+  float* dst = batch_out + static_cast<long long>(i) * D;
+  for (int c = 0; c < D; ++c) dst[c] = src[c];
+}
+
+__global__ void replay_read_kernel(const float* __restrict__ data, long long capacity, int D, long long head,
+                                   long long first, long long total_words, float* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total_words) return;
+  const long long r = i / D;
+  const int c = static_cast<int>(i - r * D);
+  long long p = head + first + r;
+  p %= capacity;
+  out[i] = data[p * D + c];
+}
+
+template <int MODE>
+__global__ void env_reset_kernel(const float* __restrict__ data, long long capacity, int D, long long head,
+                                 const uint32_t* __restrict__ rngs, int E, int batch, int minval, uint32_t span,
+                                 int x_dim, int reward_col, float* __restrict__ obs_out,
+                                 float* __restrict__ reward_out, uint32_t* __restrict__ sys_key_out,
+                                 int32_t* __restrict__ idx_out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const Key2 rng{rngs[2 * e], rngs[2 * e + 1]};
+  Key2 buffer_key, sys_key, next, sample_key;
+  split2<MODE>(rng, buffer_key, sys_key);          // brax_wrapper.py:26
+  split2<MODE>(buffer_key, next, sample_key);      // sample_internal: key, sample_key = split(buffer_state.key)
+  const int32_t idx = static_cast<int32_t>(static_cast<uint32_t>(minval) +
+                                           randint_offset_at<MODE>(sample_key, static_cast<uint32_t>(batch), 0u, span));
+  long long l = static_cast<long long>(idx) % capacity;
+  if (l < 0) l += capacity;
+  long long p = head + l;
+  if (p >= capacity) p -= capacity;
+  const float* row = data + p * D;
+  for (int c = 0; c < x_dim; ++c) obs_out[static_cast<long long>(e) * x_dim + c] = row[c];
+  reward_out[e] = row[reward_col];
+  sys_key_out[2 * e] = sys_key.k0;
+  sys_key_out[2 * e + 1] = sys_key.k1;
+  if (idx_out) idx_out[e] = idx;
+}
+
+int check_state(const MbpoReplayState* s, const char* who) {
+  MBPO_REQUIRE(s != nullptr, "%s: state is null", who);
+  MBPO_REQUIRE(s->data != nullptr, "%s: data is null", who);
+  MBPO_REQUIRE(s->capacity >= 1 && s->row_width >= 1, "%s: capacity %lld / row_width %d", who, s->capacity,
+               s->row_width);
+  MBPO_REQUIRE(s->head >= 0 && s->head < s->capacity, "%s: head %lld outside [0, %lld)", who, s->head, s->capacity);
+  MBPO_REQUIRE(s->insert_position >= 0 && s->insert_position <= s->capacity && s->sample_position >= 0 &&
+                   s->sample_position <= s->capacity,
+               "%s: positions (%lld, %lld) outside [0, %lld]", who, s->insert_position, s->sample_position,
+               s->capacity);
+  MBPO_REQUIRE(s->capacity < (1LL << 31), "%s: capacity %lld needs int32 indices like brax", who, s->capacity);
+  return MBPO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mbpo_prng_randint(const uint32_t* keys, int M, int n, int prng_mode, int minval, int maxval, int32_t* out,
+                      void* stream) {
+  MBPO_REQUIRE(M >= 0 && n >= 0, "prng_randint: negative size");
+  MBPO_REQUIRE(prng_mode == 0 || prng_mode == 1, "prng_randint: bad prng_mode %d", prng_mode);
+  const long long total = static_cast<long long>(M) * n;
+  if (total == 0) return MBPO_OK;
+  MBPO_REQUIRE(keys && out, "prng_randint: null pointer");
+  const uint32_t span = randint_span(minval, maxval);
+  const int threads = 256;
+  const unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);
+  if (prng_mode == 0)
+    prng_randint_kernel<0><<<blocks, threads, 0, as_stream(stream)>>>(keys, total, n, minval, span, out);
+  else
+    prng_randint_kernel<1><<<blocks, threads, 0, as_stream(stream)>>>(keys, total, n, minval, span, out);
+  return check_launch("prng_randint_kernel");
+}
+
+int mbpo_replay_insert(MbpoReplayState* s, const MbpoReplayFields* fields, long long n_rows, void* stream) {
+  int rc = check_state(s, "replay_insert");
+  if (rc != MBPO_OK) return rc;
+  MBPO_REQUIRE(fields != nullptr, "replay_insert: fields is null");
+  MBPO_REQUIRE(fields->num_fields >= 1 && fields->num_fields <= MBPO_REPLAY_MAX_FIELDS,
+               "replay_insert: num_fields %d outside [1, %d]", fields->num_fields, MBPO_REPLAY_MAX_FIELDS);
+  MBPO_REQUIRE(n_rows >= 0, "replay_insert: n_rows < 0");
+  MBPO_REQUIRE(n_rows <= s->capacity,
+               "replay_insert: trying to insert a batch of %lld samples larger than the maximum replay size %lld",
+               n_rows, s->capacity);
+  FieldTable ft{};
+  ft.num_fields = fields->num_fields;
+  int col = 0;
+  for (int f = 0; f < fields->num_fields; ++f) {
+    MBPO_REQUIRE(fields->width[f] >= 1, "replay_insert: field %d has width %d", f, fields->width[f]);
+    MBPO_REQUIRE(n_rows == 0 || fields->ptr[f] != nullptr, "replay_insert: field %d is null", f);
+    col += fields->width[f];
+    ft.col_end[f] = col;
+    ft.width[f] = fields->width[f];
+    ft.ptr[f] = fields->ptr[f];
+  }
+  MBPO_REQUIRE(col == s->row_width, "replay_insert: field widths sum to %d, row_width is %d", col, s->row_width);
+  if (n_rows == 0) return MBPO_OK;
+  // brax insert_internal: roll = min(0, len(data) - position - len(update)); data = roll(data, roll); position += roll
+  long long roll = s->capacity - s->insert_position - n_rows;
+  if (roll > 0) roll = 0;
+  const long long head = ((s->head - roll) % s->capacity + s->capacity) % s->capacity;  // roll by r: new[i] = old[i - r]
+  const long long position = s->insert_position + roll;
+  const long long first_physical = (head + position) % s->capacity;
+  // tile of rows_per_cta rows in at most 40 KB of shared memory (5 CTAs per SM)
+  int rows_per_cta = static_cast<int>((40 * 1024) / (4 * static_cast<long long>(s->row_width)));
+  if (rows_per_cta > 256) rows_per_cta = 256;
+  if (rows_per_cta >= 32) rows_per_cta &= ~31;
+  MBPO_REQUIRE(rows_per_cta >= 1, "replay_insert: a row of %d floats does not fit the staging tile", s->row_width);
+  const long long blocks = (n_rows + rows_per_cta - 1) / rows_per_cta;
+  MBPO_REQUIRE(blocks < (1LL << 31), "replay_insert: n_rows %lld too large for one launch", n_rows);
+  const size_t smem = static_cast<size_t>(rows_per_cta) * s->row_width * sizeof(float);
+  replay_pack_kernel<<<static_cast<unsigned>(blocks), PACK_THREADS, smem, as_stream(stream)>>>(
+      ft, s->row_width, rows_per_cta, n_rows, s->data, s->capacity, first_physical);
+  rc = check_launch("replay_pack_kernel");
+  if (rc != MBPO_OK) return rc;
+  s->head = head;
+  s->insert_position = (position + n_rows) % (s->capacity + 1);
+  const long long sp = s->sample_position + roll;
+  s->sample_position = sp > 0 ? sp : 0;
+  return MBPO_OK;
+}
+
+int mbpo_replay_sample(const MbpoReplayState* s, const uint32_t* key, int prng_mode, int sample_batch_size,
+                       uint32_t* key_out, int32_t* idx_out, float* batch_out, void* stream) {
+  int rc = check_state(s, "replay_sample");
+  if (rc != MBPO_OK) return rc;
+  MBPO_REQUIRE(prng_mode == 0 || prng_mode == 1, "replay_sample: bad prng_mode %d", prng_mode);
+  MBPO_REQUIRE(sample_batch_size >= 1, "replay_sample: sample_batch_size %d < 1", sample_batch_size);
+  MBPO_REQUIRE(key && key_out && batch_out, "replay_sample: null pointer");
+  const int minval = static_cast<int>(s->sample_position), maxval = static_cast<int>(s->insert_position);
+  const uint32_t span = randint_span(minval, maxval);
+  const int threads = 128;
+  const unsigned blocks = static_cast<unsigned>((sample_batch_size + threads - 1) / threads);
+  if (prng_mode == 0)
+    replay_sample_kernel<0><<<blocks, threads, 0, as_stream(stream)>>>(
+        s->data, s->capacity, s->row_width, s->head, key, sample_batch_size, minval, span, key_out, idx_out, batch_out);
+  else
+    replay_sample_kernel<1><<<blocks, threads, 0, as_stream(stream)>>>(
+        s->data, s->capacity, s->row_width, s->head, key, sample_batch_size, minval, span, key_out, idx_out, batch_out);
+  return check_launch("replay_sample_kernel");
+}
+
+int mbpo_replay_read(const MbpoReplayState* s, long long first, long long n, float* rows_out, void* stream) {
+  int rc = check_state(s, "replay_read");
+  if (rc != MBPO_OK) return rc;
+  MBPO_REQUIRE(first >= 0 && n >= 0 && first + n <= s->capacity, "replay_read: rows [%lld, %lld) outside [0, %lld)",
+               first, first + n, s->capacity);
+  if (n == 0) return MBPO_OK;
+  MBPO_REQUIRE(rows_out != nullptr, "replay_read: rows_out is null");
+  const long long total = n * s->row_width;
+  const int threads = 256;
+  const long long blocks = (total + threads - 1) / threads;
+  MBPO_REQUIRE(blocks < (1LL << 31), "replay_read: too many rows for one launch");
+  replay_read_kernel<<<static_cast<unsigned>(blocks), threads, 0, as_stream(stream)>>>(
+      s->data, s->capacity, s->row_width, s->head, first, total, rows_out);
+  return check_launch("replay_read_kernel");
+}
+
+int mbpo_env_reset_from_buffer(const MbpoReplayState* s, const uint32_t* rngs, int E, int prng_mode,
+                               int sample_batch_size, int x_dim, int reward_col, float* obs_out, float* reward_out,
+                               uint32_t* sys_key_out, int32_t* idx_out, void* stream) {
+  int rc = check_state(s, "env_reset_from_buffer");
+  if (rc != MBPO_OK) return rc;
+  MBPO_REQUIRE(prng_mode == 0 || prng_mode == 1, "env_reset_from_buffer: bad prng_mode %d", prng_mode);
+  MBPO_REQUIRE(E >= 0, "env_reset_from_buffer: E < 0");
+  MBPO_REQUIRE(sample_batch_size >= 1, "env_reset_from_buffer: sample_batch_size %d < 1", sample_batch_size);
+  MBPO_REQUIRE(x_dim >= 1 && x_dim <= s->row_width && reward_col >= 0 && reward_col < s->row_width,
+               "env_reset_from_buffer: x_dim %d / reward_col %d outside a row of %d", x_dim, reward_col, s->row_width);
+  if (E == 0) return MBPO_OK;
+  MBPO_REQUIRE(rngs && obs_out && reward_out && sys_key_out, "env_reset_from_buffer: null pointer");
+  const int minval = static_cast<int>(s->sample_position), maxval = static_cast<int>(s->insert_position);
+  const uint32_t span = randint_span(minval, maxval);
+  const int threads = 128;
+  const unsigned blocks = static_cast<unsigned>((E + threads - 1) / threads);
+  if (prng_mode == 0)
+    env_reset_kernel<0><<<blocks, threads, 0, as_stream(stream)>>>(s->data, s->capacity, s->row_width, s->head, rngs, E,
+                                                                  sample_batch_size, minval, span, x_dim, reward_col,
+                                                                  obs_out, reward_out, sys_key_out, idx_out);
+  else
+    env_reset_kernel<1><<<blocks, threads, 0, as_stream(stream)>>>(s->data, s->capacity, s->row_width, s->head, rngs, E,
+                                                                  sample_batch_size, minval, span, x_dim, reward_col,
+                                                                  obs_out, reward_out, sys_key_out, idx_out);
+  return check_launch("env_reset_kernel");
+}
+
+}  // extern "C"

@@ -79,6 +79,21 @@ class IcemTraceC(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("actions", "values", "elite_idx", "mean", "std", "best_value")]
 
 
+MBPO_REPLAY_MAX_FIELDS = 8
+
+
+class ReplayStateC(C.Structure):
+    """MbpoReplayState."""
+    _fields_ = [("data", C.c_void_p), ("capacity", C.c_longlong), ("row_width", C.c_int32), ("reserved", C.c_int32),
+                ("head", C.c_longlong), ("insert_position", C.c_longlong), ("sample_position", C.c_longlong)]
+
+
+class ReplayFieldsC(C.Structure):
+    """MbpoReplayFields."""
+    _fields_ = [("num_fields", C.c_int32), ("width", C.c_int32 * MBPO_REPLAY_MAX_FIELDS),
+                ("ptr", C.c_void_p * MBPO_REPLAY_MAX_FIELDS)]
+
+
 # name -> (restype, argtypes); every symbol include/mbpo_b200.h declares
 _P, _I, _F, _SZ, _LL = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_longlong
 SIGNATURES = {
@@ -113,6 +128,11 @@ SIGNATURES = {
     "mbpo_lambda_return_vjp": (_I, [_P, _I, _I, _LL, _LL, C.c_double, C.c_double, _P, _P, _P]),
     "mbpo_mlp_dynamics_forward": (_I, [C.POINTER(MlpEnsembleParamsC), _P, _P, _I, _P, _P]),
     "mbpo_ensemble_rollout": (_I, [C.POINTER(MlpEnsembleParamsC), _I, _P, _P, _I, _I, _I, _P, _P]),
+    "mbpo_prng_randint": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
+    "mbpo_replay_insert": (_I, [C.POINTER(ReplayStateC), C.POINTER(ReplayFieldsC), _LL, _P]),
+    "mbpo_replay_sample": (_I, [C.POINTER(ReplayStateC), _P, _I, _I, _P, _P, _P, _P]),
+    "mbpo_replay_read": (_I, [C.POINTER(ReplayStateC), _LL, _LL, _P, _P]),
+    "mbpo_env_reset_from_buffer": (_I, [C.POINTER(ReplayStateC), _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
 }
 
 
@@ -129,7 +149,8 @@ def _load() -> C.CDLL:
     got = lib.mbpo_abi_version()
     if got != MBPO_ABI_VERSION:
         raise ImportError("libmbpo_b200.so ABI version %d != binding version %d; rebuild" % (got, MBPO_ABI_VERSION))
-    for which, struct in enumerate((IcemCfgC, PendulumParamsC, MlpEnsembleParamsC, IcemTraceC, PolicyParamsC)):
+    for which, struct in enumerate((IcemCfgC, PendulumParamsC, MlpEnsembleParamsC, IcemTraceC, PolicyParamsC, ReplayStateC,
+                                    ReplayFieldsC)):
         if lib.mbpo_struct_size(which) != C.sizeof(struct):
             raise ImportError("struct layout mismatch for %s: C %d vs ctypes %d" % (
                 struct.__name__, lib.mbpo_struct_size(which), C.sizeof(struct)))

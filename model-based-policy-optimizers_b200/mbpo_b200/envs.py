@@ -31,9 +31,10 @@ class EnvState(_Replaceable):
 
 class VmappedSystemEnv:
     def __init__(self, system: System, system_params: SystemParams, episode_length: int = 1000,
-                 action_repeat: int = 1):
+                 action_repeat: int = 1, brax_env=None):
         self.system = system
         self.init_system_params = system_params
+        self.brax_env = brax_env      # a systems.BraxWrapper: resets draw from its true buffer
         self.episode_length = int(episode_length)
         self.action_repeat = int(action_repeat)
 
@@ -45,13 +46,24 @@ class VmappedSystemEnv:
     def observation_size(self) -> int:
         return self.system.x_dim
 
-    def reset(self, first_obs: torch.Tensor) -> EnvState:
-        """The reference samples first observations from the true replay buffer
-        (brax_wrapper.py:25-38); here the caller supplies them: first_obs [E, X]."""
-        obs = first_obs.to(torch.float32).contiguous().clone()
+    def reset(self, rng_or_first_obs: torch.Tensor) -> EnvState:
+        """uint32 keys [E, 2] (``env.reset(jr.split(env_key, num_envs))``, sac.py:411-412): every env draws its first
+        observation and reward from the true replay buffer and gets its own system_params key
+        (brax_wrapper.py:25-38; needs ``wrap(BraxWrapper(...))``).  float32 [E, X]: the caller supplies the first
+        observations.  Either way the Episode / AutoReset wrappers' info starts as training.py:87-89,115-116."""
+        if rng_or_first_obs.dtype in (torch.uint32, torch.int32):
+            if self.brax_env is None:
+                raise _lib.MbpoError(_lib.MBPO_EINVAL, "reset(keys) needs the env built by wrap(BraxWrapper(...)): "
+                                     "first observations come from its true buffer")
+            st = self.brax_env.reset(rng_or_first_obs.reshape(-1, 2))
+            obs, reward, params = st.obs, st.reward, st.system_params
+        else:
+            obs = rng_or_first_obs.to(torch.float32).contiguous().clone()
+            reward, params = None, self.init_system_params
         e = obs.shape[0]
         zeros = torch.zeros(e, dtype=torch.float32, device=obs.device)
-        return EnvState(obs=obs, reward=zeros.clone(), done=zeros.clone(), system_params=self.init_system_params,
+        return EnvState(obs=obs, reward=zeros.clone() if reward is None else reward, done=zeros.clone(),
+                        system_params=params,
                         info=dict(steps=zeros.clone(), truncation=zeros.clone(), first_obs=obs.clone()))
 
     def unroll(self, state: EnvState, actions: torch.Tensor):
@@ -97,7 +109,16 @@ class VmappedSystemEnv:
         return new_state
 
 
-def wrap(system: System, system_params: SystemParams, episode_length: int = 1000,
-         action_repeat: int = 1) -> VmappedSystemEnv:
-    """training.py:29-47 ``wrap`` applied to BraxWrapper(system, ...)."""
-    return VmappedSystemEnv(system, system_params, episode_length, action_repeat)
+def wrap(env_or_system, *args, **kwargs) -> VmappedSystemEnv:
+    """training.py:29-47 ``wrap(env, episode_length=1000, action_repeat=1)`` with ``env`` a systems.BraxWrapper; also
+    accepts ``wrap(system, system_params, episode_length, action_repeat)`` (resets then take the first observations
+    from the caller)."""
+    if isinstance(env_or_system, System):
+        return VmappedSystemEnv(env_or_system, *args, **kwargs)
+
+    def _lengths(episode_length: int = 1000, action_repeat: int = 1):
+        return int(episode_length), int(action_repeat)
+
+    episode_length, action_repeat = _lengths(*args, **kwargs)
+    env = env_or_system
+    return VmappedSystemEnv(env.system, env.init_system_params, episode_length, action_repeat, brax_env=env)

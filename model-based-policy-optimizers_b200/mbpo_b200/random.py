@@ -68,3 +68,13 @@ def normal(key: torch.Tensor, n: int) -> torch.Tensor:
         _lib.check(_lib.lib.mbpo_prng_normal(_lib.ptr(key), key.numel() // 2, n, config.prng_mode, _lib.ptr(out),
                                              _lib.stream_ptr(key.device)))
     return out
+
+
+def randint(key: torch.Tensor, n: int, minval: int, maxval: int) -> torch.Tensor:
+    """jax.random.randint(key, (n,), minval, maxval) (int32)."""
+    key = _as_keys(key)
+    out = torch.empty(key.shape[:-1] + (n,), dtype=torch.int32, device=key.device)
+    with _lib.cuda_guard(key):
+        _lib.check(_lib.lib.mbpo_prng_randint(_lib.ptr(key), key.numel() // 2, n, config.prng_mode, int(minval),
+                                              int(maxval), _lib.ptr(out), _lib.stream_ptr(key.device)))
+    return out

@@ -1,8 +1,9 @@
 """mbpo.systems work-alike (mbpo/systems/__init__.py:1-4)."""
 from .base_systems import System, SystemParams, SystemState
+from .brax_wrapper import BraxWrapper
 from .mlp_ensemble_system import MLPEnsembleSystem, MlpEnsembleDynamicsParams
 from .pendulum_system import (PendulumDynamics, PendulumDynamicsParams, PendulumReward, PendulumRewardParams,
                               PendulumSystem)
 
-__all__ = ["MLPEnsembleSystem", "MlpEnsembleDynamicsParams", "System", "SystemParams", "SystemState", "PendulumSystem", "PendulumDynamics", "PendulumDynamicsParams",
+__all__ = ["BraxWrapper", "MLPEnsembleSystem", "MlpEnsembleDynamicsParams", "System", "SystemParams", "SystemState", "PendulumSystem", "PendulumDynamics", "PendulumDynamicsParams",
            "PendulumReward", "PendulumRewardParams"]

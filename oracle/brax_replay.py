@@ -1,0 +1,91 @@
+"""ORACLE (test infrastructure, NOT product code) -- NumPy restatement of brax's UniformSamplingQueue
+and of the reference's BraxWrapper.reset that draws initial states from it.
+
+brax is a third-party dependency absent from /root/reference (setup.py:19, unpinned) and not installable
+here; this file restates the published algorithm of ``brax/training/replay_buffers.py`` (brax 0.9-0.10,
+``QueueBase.init / insert_internal``, ``UniformSamplingQueue.sample_internal``):
+
+  * data: float32 [max_replay_size, D], a row = ``ravel_pytree`` of one Transition (fields in NamedTuple
+    order, dict keys sorted), ``insert_position`` / ``sample_position`` int32, ``key``;
+  * insert: ``roll = min(0, len(data) - position - len(update))``; if roll: ``data = roll(data, roll, axis=0)``;
+    ``position += roll``; write the update at ``position``; ``position = (position + len(update)) %
+    (len(data) + 1)``; ``sample_position = max(0, sample_position + roll)``;
+  * sample: ``key, sample_key = split(key)``; ``idx = randint(sample_key, (batch,), sample_position,
+    insert_position)``; ``batch = take(data, idx, axis=0, mode='wrap')``.
+
+Reference call sites: mbpo/systems/brax_wrapper.py:25-38 (reset), mbpo/optimizers/base_optimizer.py:44-57
+(dummy buffer), mbpo/optimizers/policy_optimizers/sac/sac.py:202-205,303 (SAC's replay buffer and insert),
+tests/test_sac.py:15-28.  PARITY UNPINNED against a brax / JAX run; the randint arithmetic is restated in
+oracle/jax_prng.py.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline/reference legs may import this module.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, replace
+
+import numpy as np
+
+from . import jax_prng as jp
+
+
+@dataclass
+class ReplayBufferState:
+    data: np.ndarray            # float32 [R, D]
+    insert_position: int
+    sample_position: int
+    key: np.ndarray             # uint32 [2]
+
+
+class UniformSamplingQueue:
+    def __init__(self, max_replay_size: int, row_width: int, sample_batch_size: int, partitionable: bool = False):
+        self.R, self.D, self.batch = int(max_replay_size), int(row_width), int(sample_batch_size)
+        self.partitionable = partitionable
+
+    def init(self, key) -> ReplayBufferState:
+        return ReplayBufferState(np.zeros((self.R, self.D), np.float32), 0, 0, np.asarray(key, np.uint32).copy())
+
+    def insert(self, st: ReplayBufferState, rows: np.ndarray) -> ReplayBufferState:
+        rows = np.asarray(rows, np.float32).reshape(-1, self.D)
+        n = rows.shape[0]
+        if n > self.R:
+            raise ValueError("Trying to insert a batch of samples larger than the maximum replay size")
+        data = st.data
+        position = st.insert_position
+        roll = min(0, self.R - position - n)
+        if roll:
+            data = np.roll(data, roll, axis=0)
+        else:
+            data = data.copy()
+        position = position + roll
+        data[position:position + n] = rows
+        position = (position + n) % (self.R + 1)
+        sample_position = max(0, st.sample_position + roll)
+        return ReplayBufferState(data, position, sample_position, st.key)
+
+    def sample(self, st: ReplayBufferState):
+        k = jp.split(st.key, 2, self.partitionable)
+        idx = jp.randint(k[1], self.batch, st.sample_position, st.insert_position, self.partitionable)
+        batch = st.data[np.mod(idx.astype(np.int64), self.R)]
+        return replace(st, key=k[0]), batch, idx
+
+
+def brax_wrapper_reset(rngs: np.ndarray, queue: UniformSamplingQueue, st: ReplayBufferState, x_dim: int,
+                       action_dim: int):
+    """vmap(BraxWrapper.reset)(rngs) (brax_wrapper.py:25-38; VmapWrapper.reset, brax_utils/training.py:66-69):
+    per env ``keys = split(rng, 2)``, the buffer is sampled under ``keys[0]``, element 0 of the batch gives
+    ``obs`` and ``reward``, ``system_params.key = keys[1]``, ``done = 0``."""
+    rngs = np.asarray(rngs, np.uint32).reshape(-1, 2)
+    E = rngs.shape[0]
+    obs = np.zeros((E, x_dim), np.float32)
+    reward = np.zeros(E, np.float32)
+    sys_keys = np.zeros((E, 2), np.uint32)
+    idx0 = np.zeros(E, np.int32)
+    for e in range(E):
+        keys = jp.split(rngs[e], 2, queue.partitionable)
+        _, batch, idx = queue.sample(replace(st, key=keys[0]))
+        obs[e] = batch[0, :x_dim]
+        reward[e] = batch[0, x_dim + action_dim]
+        sys_keys[e] = keys[1]
+        idx0[e] = idx[0]
+    return obs, reward, sys_keys, idx0

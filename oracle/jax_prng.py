@@ -142,3 +142,29 @@ def bits_to_normal(bits) -> np.ndarray:
 
 def normal(key, n: int, partitionable: bool = False) -> np.ndarray:
     return bits_to_normal(random_bits(key, n, partitionable))
+
+
+def randint(key, n: int, minval: int, maxval: int, partitionable: bool = False) -> np.ndarray:
+    """jax.random.randint(key, (n,), minval, maxval) for the default int32 dtype.
+
+    Restates jax/_src/random.py ``_randint`` (JAX 0.4.x): ``k1, k2 = split(key)``; 32 bits from each;
+    ``span = uint32(maxval - minval)`` (1 when ``maxval <= minval`` so that minval is returned);
+    ``multiplier = ((2**16 % span) ** 2) % span``; ``offset = ((hi % span) * multiplier + lo % span) % span``
+    with uint32 wrap-around; result ``minval + int32(offset)``.  (The ``maxval`` out-of-range branch cannot
+    trigger for int32 bounds.)  UNPINNED against a JAX run (no JAX in this image); used by
+    brax's UniformSamplingQueue.sample, reference call site mbpo/systems/brax_wrapper.py:29.
+    """
+    k = split(key, 2, partitionable)
+    hi = random_bits(k[0], n, partitionable).astype(np.uint64)
+    lo = random_bits(k[1], n, partitionable).astype(np.uint64)
+    minval = int(np.int32(minval))
+    maxval = int(np.int32(maxval))
+    span = np.uint64((maxval - minval) & 0xFFFFFFFF)
+    if maxval <= minval:
+        span = np.uint64(1)
+    m32 = np.uint64(0xFFFFFFFF)
+    mult = np.uint64(2 ** 16) % span
+    mult = ((mult * mult) & m32) % span
+    off = (((hi % span) * mult) & m32) + (lo % span)
+    off = (off & m32) % span
+    return (np.int64(minval) + off.astype(np.int64)).astype(np.int64).astype(np.int32)

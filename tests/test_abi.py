@@ -39,7 +39,8 @@ def test_header_symbols_are_exported(mb):
 def test_abi_version_and_struct_layout(mb):
     L = mb._lib
     assert L.lib.mbpo_abi_version() == L.MBPO_ABI_VERSION == 1
-    for which, st in enumerate((L.IcemCfgC, L.PendulumParamsC, L.MlpEnsembleParamsC, L.IcemTraceC, L.PolicyParamsC)):
+    for which, st in enumerate((L.IcemCfgC, L.PendulumParamsC, L.MlpEnsembleParamsC, L.IcemTraceC, L.PolicyParamsC,
+                                L.ReplayStateC, L.ReplayFieldsC)):
         assert L.lib.mbpo_struct_size(which) == C.sizeof(st)
     assert L.lib.mbpo_struct_size(99) == 0
     assert C.sizeof(L.PendulumParamsC) == 36
@@ -84,6 +85,20 @@ def test_error_codes_without_gpu(mb):
     assert L.lib.mbpo_prng_split(None, 4, 2, 0, None, None) == L.MBPO_EINVAL
     assert L.lib.mbpo_system_step(0, None, 0, None, None, 4, None, None, None) == L.MBPO_EINVAL
     assert L.lib.mbpo_system_step(9, None, 0, None, None, 4, None, None, None) == L.MBPO_EINVAL
+    # replay queue: argument errors are reported before anything is launched
+    st = L.ReplayStateC(data=None, capacity=10, row_width=9)
+    assert L.lib.mbpo_replay_insert(C.byref(st), None, 1, None) == L.MBPO_EINVAL
+    st = L.ReplayStateC(data=0x1000, capacity=10, row_width=9)
+    fields = L.ReplayFieldsC(num_fields=1)
+    fields.width[0], fields.ptr[0] = 9, 0x2000
+    assert L.lib.mbpo_replay_insert(C.byref(st), C.byref(fields), 11, None) == L.MBPO_EINVAL   # brax raises ValueError
+    assert b"larger than the maximum replay size" in L.lib.mbpo_last_error()
+    fields.width[0] = 8
+    assert L.lib.mbpo_replay_insert(C.byref(st), C.byref(fields), 1, None) == L.MBPO_EINVAL
+    assert b"row_width" in L.lib.mbpo_last_error()
+    assert L.lib.mbpo_replay_sample(C.byref(st), None, 0, 4, None, None, None, None) == L.MBPO_EINVAL
+    assert L.lib.mbpo_env_reset_from_buffer(C.byref(st), None, 4, 0, 1, 3, 9, None, None, None, None, None) == L.MBPO_EINVAL
+    assert L.lib.mbpo_prng_randint(None, 4, 2, 0, 0, 10, None, None) == L.MBPO_EINVAL
     with pytest.raises(mb.MbpoError):
         L.check(L.MBPO_EINVAL)
     with pytest.raises(NotImplementedError):
@@ -146,6 +161,16 @@ def test_api_surface_matches_reference(mb):
         "env", "env_state", "policy", "key", "extra_fields"]
     assert list(inspect.signature(acting.generate_unroll).parameters)[:6] == [           # sac/acting.py:58-64
         "env", "env_state", "policy", "key", "unroll_length", "extra_fields"]                # (+ additive sharding kwargs)
+    from mbpo_b200.replay_buffers import UniformSamplingQueue
+    from mbpo_b200.systems import BraxWrapper
+    assert list(inspect.signature(UniformSamplingQueue.__init__).parameters)[:4] == [    # brax replay_buffers.QueueBase
+        "self", "max_replay_size", "dummy_data_sample", "sample_batch_size"]
+    assert list(inspect.signature(UniformSamplingQueue.insert).parameters) == ["self", "buffer_state", "samples"]
+    assert list(inspect.signature(UniformSamplingQueue.sample).parameters) == ["self", "buffer_state"]
+    assert list(inspect.signature(BraxWrapper.__init__).parameters) == [                 # brax_wrapper.py:15-19
+        "self", "system", "system_params", "sample_buffer_state", "sample_buffer"]
+    assert list(inspect.signature(BraxWrapper.reset).parameters) == ["self", "rng"]
+    assert list(inspect.signature(BraxWrapper.step).parameters) == ["self", "state", "action"]
     assert issubclass(iCemTO, BaseOptimizer) and issubclass(PendulumSystem, System)
     assert iCEMOptimizer(horizon=20).can_act_in_batches is False
     s = PendulumSystem()

@@ -1,0 +1,210 @@
+"""GPU parity tests of the replay queue and BraxWrapper.reset (mbpo_replay_*, mbpo_env_reset_from_buffer,
+mbpo_prng_randint) against oracle/brax_replay.py and oracle/jax_prng.randint.  Everything here is integer / byte
+work: the bar is bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import brax_replay as obr
+from oracle import jax_prng as ojr
+from oracle import mbpo_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mb(cuda_device):
+    import mbpo_b200
+    return mbpo_b200
+
+
+@pytest.fixture(params=[False, True], ids=["legacy", "partitionable"])
+def prng_mode(request, mb):
+    mb.config.threefry_partitionable = request.param
+    yield request.param
+    mb.config.threefry_partitionable = False
+
+
+def _dev(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def _sac_dummy(mb, dev):
+    """sac.py:194-200: scalar reward / discount, truncation in extras -> a row of 2X + A + 3 = 10 floats."""
+    from mbpo_b200.utils.optimizer_utils import Transition
+    z = torch.zeros
+    return Transition(observation=z(3, device=dev), action=z(1, device=dev), reward=z((), device=dev),
+                      discount=z((), device=dev), next_observation=z(3, device=dev),
+                      extras={"state_extras": {"truncation": z((), device=dev)}, "policy_extras": {}})
+
+
+def _true_dummy(mb, dev):
+    """tests/test_sac.py:15-19: no extras -> a row of 9 floats."""
+    from mbpo_b200.utils.optimizer_utils import Transition
+    z = torch.zeros
+    return Transition(observation=z(3, device=dev), action=z(1, device=dev), reward=z((), device=dev),
+                      discount=z((), device=dev), next_observation=z(3, device=dev))
+
+
+def _rows_of(tr, n):
+    """ravel_pytree order of a Transition batch: the fields side by side."""
+    cols = [tr.observation.reshape(n, 3), tr.action.reshape(n, 1), tr.reward.reshape(n, 1),
+            tr.discount.reshape(n, 1), tr.next_observation.reshape(n, 3)]
+    if isinstance(tr.extras, dict):
+        cols.append(tr.extras["state_extras"]["truncation"].reshape(n, 1))
+    return torch.cat(cols, dim=1).cpu().numpy()
+
+
+@pytest.mark.parametrize("minval,maxval", [(0, 10), (3, 3), (7, 2), (-5, 5), (0, 2 ** 31 - 1), (-2 ** 31, 2 ** 31 - 1),
+                                            (0, 1), (0, 65537), (100, 1_000_000)])
+def test_randint_bit_exact(mb, cuda_device, prng_mode, minval, maxval):
+    rng = np.random.default_rng(maxval & 0xFFFF)
+    keys = rng.integers(0, 2 ** 32, size=(5, 2), dtype=np.uint64).astype(np.uint32)
+    for n in (1, 2, 7, 64):
+        got = mb.random.randint(_dev(keys, cuda_device), n, minval, maxval).cpu().numpy()
+        want = np.stack([ojr.randint(k, n, minval, maxval, prng_mode) for k in keys])
+        assert got.dtype == np.int32 and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("layout", ["sac", "true"])
+def test_queue_insert_sample_match_oracle(mb, cuda_device, prng_mode, layout):
+    from mbpo_b200.replay_buffers import UniformSamplingQueue
+    from mbpo_b200.utils.optimizer_utils import Transition
+    dev = cuda_device
+    dummy = _sac_dummy(mb, dev) if layout == "sac" else _true_dummy(mb, dev)
+    D = 10 if layout == "sac" else 9
+    R, batch = 53, 17
+    q = UniformSamplingQueue(R, dummy, batch)
+    assert q.row_width == D
+    oq = obr.UniformSamplingQueue(R, D, batch, prng_mode)
+    key = ojr.PRNGKey(11)
+    st, ost = q.init(_dev(key, dev)), oq.init(key)
+    rng = np.random.default_rng(3)
+    for n in [1, 6, 40, 0, 7, 53, 2, 52, 9, 9, 9]:        # fills, wraps, replaces the whole queue, empty insert
+        g = lambda *s: torch.from_numpy(rng.standard_normal(s).astype(np.float32)).to(dev)
+        extras = {"state_extras": {"truncation": g(n)}, "policy_extras": {}} if layout == "sac" else ()
+        tr = Transition(observation=g(n, 3), action=g(n, 1), reward=g(n), discount=g(n), next_observation=g(n, 3),
+                        extras=extras)
+        st = q.insert(st, tr)
+        ost = oq.insert(ost, _rows_of(tr, n))
+        assert (st.insert_position, st.sample_position) == (ost.insert_position, ost.sample_position)
+        assert q.size(st) == ost.insert_position - ost.sample_position
+        live = ost.insert_position
+        assert np.array_equal(st.data.cpu().numpy()[:live], ost.data[:live])
+        st, got, idx = q.sample_with_indices(st)
+        ost, want_rows, want_idx = oq.sample(ost)
+        assert np.array_equal(idx.cpu().numpy(), want_idx)
+        assert np.array_equal(st.key.cpu().numpy(), ost.key)
+        assert np.array_equal(_rows_of(got, batch), want_rows)
+        assert got.observation.shape == (batch, 3) and got.reward.shape == (batch,)
+    with pytest.raises(ValueError):
+        g = lambda *s: torch.zeros(s, device=dev)
+        q.insert(st, Transition(g(R + 1, 3), g(R + 1, 1), g(R + 1), g(R + 1), g(R + 1, 3),
+                                {"state_extras": {"truncation": g(R + 1)}, "policy_extras": {}} if layout == "sac" else ()))
+
+
+def test_sample_from_empty_queue_returns_row_zero(mb, cuda_device):
+    from mbpo_b200.replay_buffers import UniformSamplingQueue
+    q = UniformSamplingQueue(10, _true_dummy(mb, cuda_device), 8)
+    st = q.init(_dev(ojr.PRNGKey(0), cuda_device))
+    st2, batch, idx = q.sample_with_indices(st)
+    assert torch.all(idx == 0) and torch.all(batch.observation == 0)
+    assert np.array_equal(st2.key.cpu().numpy(), ojr.split(ojr.PRNGKey(0), 2)[0])
+
+
+@pytest.mark.parametrize("sample_batch_size", [1, 5])
+def test_brax_wrapper_reset_matches_oracle(mb, cuda_device, prng_mode, sample_batch_size):
+    """tests/test_sac.py:15-28 builds the true buffer; BraxWrapper.reset under VmapWrapper draws every env's first
+    observation from it (brax_wrapper.py:25-38)."""
+    from mbpo_b200.replay_buffers import UniformSamplingQueue
+    from mbpo_b200.systems import BraxWrapper, PendulumSystem
+    from mbpo_b200.utils.optimizer_utils import Transition
+    dev = cuda_device
+    system = PendulumSystem()
+    q = UniformSamplingQueue(10, _true_dummy(mb, dev), sample_batch_size)
+    oq = obr.UniformSamplingQueue(10, 9, sample_batch_size, prng_mode)
+    st, ost = q.init(_dev(ojr.PRNGKey(0), dev)), oq.init(ojr.PRNGKey(0))
+    rng = np.random.default_rng(5)
+    for n in (4, 4, 4):                                    # the third insert wraps the ring (head != 0)
+        g = lambda *s: torch.from_numpy(rng.standard_normal(s).astype(np.float32)).to(dev)
+        tr = Transition(g(n, 3), g(n, 1), g(n), g(n), g(n, 3))
+        st, ost = q.insert(st, tr), oq.insert(ost, _rows_of(tr, n))
+    assert st.head != 0
+    params = system.init_params(_dev(ojr.PRNGKey(1), dev))
+    env = BraxWrapper(system, params, st, q)
+    E = 300
+    rngs = ojr.split(ojr.PRNGKey(9), E, prng_mode)
+    state = env.reset(_dev(rngs, dev))
+    obs, reward, sys_keys, _ = obr.brax_wrapper_reset(rngs, oq, ost, 3, 1)
+    assert np.array_equal(state.obs.cpu().numpy(), obs)
+    assert np.array_equal(state.reward.cpu().numpy(), reward)
+    assert np.array_equal(state.system_params.key.cpu().numpy(), sys_keys)
+    assert torch.all(state.done == 0) and state.pipeline_state is None
+    assert len(np.unique(obs, axis=0)) > 1                # several different rows were drawn
+    one = env.reset(_dev(rngs[7], dev))                  # un-vmapped call
+    assert np.array_equal(one.obs.cpu().numpy(), obs[7]) and one.reward.shape == ()
+    nxt = env.step(state, torch.zeros((E, 1), device=dev))
+    want = orc.pendulum_step(obs, np.zeros(E, np.float32))
+    np.testing.assert_allclose(nxt.obs.cpu().numpy(), want[0], rtol=1e-5, atol=1e-6)
+
+
+def test_collect_insert_sample_cycle(mb, cuda_device):
+    """SAC's get_experience (sac.py:283-304): wrap(BraxWrapper) -> reset(keys) -> unroll -> insert the time-major
+    Transition -> sample; every row of the queue is a transition of the unroll in (t, e) order."""
+    from mbpo_b200 import envs
+    from mbpo_b200.replay_buffers import UniformSamplingQueue
+    from mbpo_b200.systems import BraxWrapper, PendulumSystem
+    from mbpo_b200.utils.optimizer_utils import Transition
+    dev = cuda_device
+    system = PendulumSystem()
+    true_q = UniformSamplingQueue(10, _true_dummy(mb, dev), 1)
+    first = system.reset(device=dev)
+    true_st = true_q.insert(true_q.init(_dev(ojr.PRNGKey(0), dev)),
+                            Transition(first.x_next[None], torch.zeros((1, 1), device=dev), first.reward[None],
+                                       torch.full((1,), 0.99, device=dev), first.x_next[None]))
+    env = envs.wrap(BraxWrapper(system, system.init_params(_dev(ojr.PRNGKey(1), dev)), true_st, true_q),
+                    episode_length=7, action_repeat=1)
+    E, T = 96, 20
+    state = env.reset(mb.random.split(_dev(ojr.PRNGKey(2), dev), E))
+    assert torch.equal(state.obs, first.x_next.expand(E, 3))          # the true buffer holds one row
+    actions = torch.from_numpy(np.random.default_rng(0).uniform(-1, 1, (T, E, 1)).astype(np.float32)).to(dev)
+    state, tr = env.unroll(state, actions)
+    R = 2000                                                          # T * E = 1920: the second insert wraps the ring
+    q = UniformSamplingQueue(R, _sac_dummy(mb, dev), 256)
+    st = q.init(_dev(ojr.PRNGKey(3), dev))
+    st = q.insert(st, tr)
+    state, tr2 = env.unroll(state, actions[:5])
+    st = q.insert(st, tr2)
+    want = np.concatenate([_rows_of(tr, T * E), _rows_of(tr2, 5 * E)])[-R:]
+    assert st.insert_position == R
+    assert np.array_equal(st.data.cpu().numpy(), want)
+    st, batch, idx = q.sample_with_indices(st)
+    assert np.array_equal(_rows_of(batch, 256), want[idx.cpu().numpy()])
+    assert batch.extras["state_extras"]["truncation"].shape == (256,)
+
+
+def test_insert_at_full_size_is_a_permutation_free_copy(mb, cuda_device):
+    """Config-3 sized rows (65,536 envs x 16 steps = 1 M rows of 10 floats), size-independent check: column sums of
+    the queue equal the fields' sums exactly (integers below 2**24 in float64 accumulation), before and after the
+    ring wraps, and the logical order is the insert order."""
+    from mbpo_b200.replay_buffers import UniformSamplingQueue
+    from mbpo_b200.utils.optimizer_utils import Transition
+    dev = cuda_device
+    E, T = 65536, 16
+    n = E * T
+    q = UniformSamplingQueue(n + 1000, _sac_dummy(mb, dev), 1)
+    st = q.init(_dev(ojr.PRNGKey(0), dev))
+    for rep in range(2):                                              # the second insert wraps the ring
+        gen = torch.Generator(device=dev).manual_seed(rep)
+        g = lambda *s: torch.randint(0, 1000, s, generator=gen, device=dev).to(torch.float32)
+        tr = Transition(g(T, E, 3), g(T, E, 1), g(T, E), g(T, E), g(T, E, 3),
+                        {"state_extras": {"truncation": g(T, E)}, "policy_extras": {}})
+        st = q.insert(st, tr)
+        data = st.data
+        live = data[st.insert_position - n:st.insert_position]
+        want = torch.cat([tr.observation.reshape(n, 3), tr.action.reshape(n, 1), tr.reward.reshape(n, 1),
+                          tr.discount.reshape(n, 1), tr.next_observation.reshape(n, 3),
+                          tr.extras["state_extras"]["truncation"].reshape(n, 1)], dim=1)
+        assert torch.equal(live, want)
+        assert torch.equal(live.double().sum(0), want.double().sum(0))
+    assert st.head != 0 and st.insert_position == n + 1000

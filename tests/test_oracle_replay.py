@@ -1,0 +1,92 @@
+"""CPU tests of the replay-queue oracle (oracle/brax_replay.py, oracle/jax_prng.randint): the restatement of brax's
+UniformSamplingQueue and jax.random.randint against independent brute-force statements of the same published
+algorithms.  No JAX/brax exists in this image: parity with a real run is unpinned (said so in the oracle headers)."""
+import numpy as np
+import pytest
+
+from oracle import brax_replay as br
+from oracle import jax_prng as jp
+
+
+def _randint_bigint(key, n, minval, maxval):
+    """_randint with python integers: (hi * 2**32 + lo) % span computed the way JAX does, in uint32 steps."""
+    k = jp.split(key, 2)
+    hi, lo = jp.random_bits(k[0], n), jp.random_bits(k[1], n)
+    span = 1 if maxval <= minval else (maxval - minval) % 2 ** 32
+    out = []
+    for h, l in zip(hi.tolist(), lo.tolist()):
+        mult = (2 ** 16) % span
+        mult = ((mult * mult) % 2 ** 32) % span
+        off = (((h % span) * mult) % 2 ** 32 + l % span) % 2 ** 32
+        out.append(minval + off % span)
+    return np.array(out, dtype=np.int64)
+
+
+@pytest.mark.parametrize("minval,maxval", [(0, 10), (3, 3), (7, 2), (-5, 5), (0, 2 ** 31 - 1), (-2 ** 31, 2 ** 31 - 1),
+                                            (0, 1), (0, 65536), (0, 65537), (100, 1_000_000)])
+def test_randint_matches_bigint_statement(minval, maxval):
+    key = jp.PRNGKey(minval * 31 + maxval)
+    got = jp.randint(key, 257, minval, maxval)
+    want = _randint_bigint(key, 257, minval, maxval)
+    assert got.dtype == np.int32 and np.array_equal(got.astype(np.int64), want)
+    if maxval > minval:
+        assert got.min() >= minval and got.max() < maxval
+    else:
+        assert np.all(got == minval)
+
+
+def test_randint_small_spans_are_exactly_the_128_bit_remainder():
+    """When the uint32 products cannot wrap (span <= 2**16) the result is (hi * 2**32 + lo) % span."""
+    key = jp.PRNGKey(5)
+    k = jp.split(key, 2)
+    hi, lo = jp.random_bits(k[0], 100).astype(object), jp.random_bits(k[1], 100).astype(object)
+    for span in (1, 2, 3, 10, 1000, 65535, 65536):
+        got = jp.randint(key, 100, 0, span)
+        want = np.array([(int(h) * 2 ** 32 + int(l)) % span for h, l in zip(hi, lo)])
+        assert np.array_equal(got, want)
+
+
+def test_queue_keeps_the_last_rows_in_order():
+    """Whatever the insert sizes, the queue holds the most recent min(total, R) rows, oldest first, and
+    insert_position / sample_position follow brax's roll arithmetic."""
+    rng = np.random.default_rng(0)
+    R, D = 37, 9
+    q = br.UniformSamplingQueue(R, D, 4)
+    st = q.init(jp.PRNGKey(0))
+    everything = np.zeros((0, D), np.float32)
+    for n in [1, 5, 30, 1, 37, 2, 0, 36, 7, 7, 7]:
+        rows = rng.standard_normal((n, D)).astype(np.float32)
+        st = q.insert(st, rows)
+        everything = np.concatenate([everything, rows])
+        live = min(len(everything), R)
+        assert st.insert_position == live and st.sample_position == 0
+        assert np.array_equal(st.data[:live], everything[len(everything) - live:])
+    with pytest.raises(ValueError):
+        q.insert(st, np.zeros((R + 1, D), np.float32))
+
+
+def test_sample_draws_live_rows_and_advances_the_key():
+    q = br.UniformSamplingQueue(10, 9, 64)
+    st = q.init(jp.PRNGKey(0))
+    st0, batch, idx = q.sample(st)                       # empty queue: span 1 -> row 0 (zeros)
+    assert np.all(idx == 0) and np.all(batch == 0)
+    assert np.array_equal(st0.key, jp.split(jp.PRNGKey(0), 2)[0])
+    st = q.insert(st, np.arange(27, dtype=np.float32).reshape(3, 9))
+    st1, batch, idx = q.sample(st)
+    assert idx.min() >= 0 and idx.max() < 3 and set(idx.tolist()) == {0, 1, 2}
+    assert np.array_equal(batch, st.data[idx])
+    st2, batch2, idx2 = q.sample(st1)
+    assert not np.array_equal(idx, idx2)
+
+
+def test_brax_wrapper_reset_per_env_keys():
+    q = br.UniformSamplingQueue(10, 9, 1)
+    st = q.insert(q.init(jp.PRNGKey(0)), np.arange(45, dtype=np.float32).reshape(5, 9))
+    rngs = jp.split(jp.PRNGKey(7), 6)
+    obs, reward, sys_keys, idx = br.brax_wrapper_reset(rngs, q, st, 3, 1)
+    for e in range(6):
+        keys = jp.split(rngs[e], 2)
+        assert np.array_equal(sys_keys[e], keys[1])
+        want = jp.randint(jp.split(keys[0], 2)[1], 1, 0, 5)[0]
+        assert idx[e] == want
+        assert np.array_equal(obs[e], st.data[want, :3]) and reward[e] == st.data[want, 4]
