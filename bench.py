@@ -48,7 +48,9 @@ UNIT = "transitions/s"
 # captures (profiles/r01c_plan_kernel_ncu_full.txt, profiles/r01c_env_pieces_kernel_ncu_full.txt); N = 1 only.
 NCU_TRAFFIC_BYTES = {"config2_batched_icem": 681216, "config3_env_rollouts": 268336640 + 1518277000,
                      # profiles/r01d_actor_tc_kernel_ncu_full.txt, profiles/r01b_ensemble_pp_kernel_ncu_full.txt
-                     "config3_actor_rollouts_tcgen05": 2874880 + 311553792, "config4_ensemble_icem": 8923136}
+                     "config3_actor_rollouts_tcgen05": 2874880 + 311553792, "config4_ensemble_icem": 8923136,
+                     # profiles/r01e_replay_pack_kernel_ncu_full.txt (observation / next_observation overlap: L2 hits)
+                     "config3_replay_insert": 384913664 + 465484288}
 LANE_INSTR_PER_TRANSITION = {("config2_batched_icem", "reference"): 229.7,
                              ("config2_batched_icem", "theta_carry"): 185.1}
 
@@ -1162,9 +1164,7 @@ def run_replay(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     E, T, D = REPLAY_E, REPLAY_T, REPLAY_D
-    if args.impl == "reference":
-        if rank != 0:
-            return
+    def cpu_arm(steps):
         from oracle import brax_replay as obr, jax_prng as jr
         Es, Ts, R = 4096, 50, 1 << 18          # bounded sample: 204,800 rows into a full queue of 262,144
         rng = np.random.default_rng(0)
@@ -1172,19 +1172,24 @@ def run_replay(args):
         q = obr.UniformSamplingQueue(R, D, 1)
         st = q.insert(q.init(jr.PRNGKey(0)), np.zeros((R, D), np.float32))
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(steps):
             st = q.insert(st, np.concatenate(f, axis=1))
-        dt = (time.perf_counter() - t0) / args.steps
-        ncores, model = host_info()
-        v = Es * Ts / dt
+        dt = (time.perf_counter() - t0) / steps
+        _, model = host_info()
+        return dt, {"value": Es * Ts / dt, "unit": "rows/s", "cores": 1, "kind": "port",
+                    "sample": "%d rows per step into a full queue of %d rows (NumPy restatement of brax "
+                              "insert_internal: ravel + roll + slice update)" % (Es * Ts, R), "host_cpu": model}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        dt, cpu = cpu_arm(args.steps)
+        v = cpu["value"]
         emit_json({"impl": "reference", "metric": "replay rows inserted/sec", "value": v, "unit": "rows/s",
                    "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                    "config": {"workload": "config3_replay_insert", "envs": E, "steps_per_call": T, "row_floats": D},
-                   "cpu_baseline": {"value": v, "unit": "rows/s", "cores": 1, "kind": "port",
-                                    "sample": "%d rows per step into a full queue of %d rows (NumPy restatement of "
-                                              "brax insert_internal: ravel + roll + slice update)" % (Es * Ts, R),
-                                    "host_cpu": model},
+                   "cpu_baseline": cpu,
                    "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}, GUARD)
         return
     torch.cuda.set_device(local_rank)
@@ -1247,7 +1252,7 @@ def run_replay(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = rows * 8 * D / (ms * 1e-3) / 1e9
-        cpu = None
+        cpu = None if (args.no_cpu_baseline or world > 1) else cpu_arm(10)[1]
         emit_json({
             "metric": "replay rows inserted/sec", "value": world * rows / (ms * 1e-3), "unit": "rows/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
@@ -1262,7 +1267,8 @@ def run_replay(args):
                            "rewards of the batch to the host"},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "kernel": "replay_pack_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": NCU_TRAFFIC_BYTES["config3_replay_insert"] if world == 1 else None,
                          "algorithmic_bytes_per_launch": rows * 8 * D, "algorithmic_bytes_per_row": 8 * D,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
             "cpu_baseline": cpu}, GUARD)

@@ -19,6 +19,7 @@ struct FieldTable {
   int num_fields;
   int col_end[MBPO_REPLAY_MAX_FIELDS];  // exclusive prefix end of field f
   int width[MBPO_REPLAY_MAX_FIELDS];
+  unsigned magic[MBPO_REPLAY_MAX_FIELDS];  // floor(2^32 / width) + 1: j / width = umulhi(j, magic) inside a tile
   const float* ptr[MBPO_REPLAY_MAX_FIELDS];
 };
 
@@ -51,53 +52,108 @@ __global__ void prng_randint_kernel(const uint32_t* __restrict__ keys, long long
 }
 
 // One CTA packs `rows_per_cta` consecutive rows through shared memory: every field's block of the tile is one dense
-// run in HBM and is read with full-line loads (all of a thread's loads are issued before the first is used), the tile
-// is assembled row-major in shared memory, and leaves as one dense run of the ring (split only at the ring's end).
+// run in HBM, read with 16-byte loads (one per field issued before the first is used), the tile is assembled row-major
+// in shared memory and leaves as one dense run of the ring with 16-byte stores.  The tile sits in shared memory at the
+// same offset modulo 16 bytes as its destination, so both sides of the copy are aligned.  (First version: one thread
+// per word with the field looked up per word -- ~100 instructions per word, issue-bound at 38% of HBM.)
 constexpr int PACK_THREADS = 256;
-constexpr int PACK_MAX_LOADS = 10;  // loads a thread keeps in flight
+constexpr int PACK_LOADS = 5;   // 16-byte loads a thread keeps in flight
 
+// scatters the words j .. j+n-1 of field (w, col0) of the tile into its row-major image
+__device__ __forceinline__ void pack_scatter(float* tile, int D, unsigned w, unsigned col0, unsigned magic,
+                                             unsigned j, const float* x, int n) {
+  unsigned r = (w == 1u) ? j : __umulhi(j, magic);   // j / w (exact: j * w < 2^32)
+  unsigned c = j - r * w;
+  unsigned at = r * static_cast<unsigned>(D) + col0 + c;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k < n) tile[at] = x[k];
+    ++c;
+    ++at;
+    if (c == w) {
+      c = 0;
+      at += static_cast<unsigned>(D) - w;
+    }
+  }
+}
+
+template <bool VEC>
 __global__ void __launch_bounds__(PACK_THREADS)
 replay_pack_kernel(FieldTable ft, int D, int rows_per_cta, long long n_rows, float* __restrict__ data,
                    long long capacity, long long first_physical) {
-  extern __shared__ float tile[];  // [rows_per_cta, D]
+  extern __shared__ __align__(16) float pack_smem[];
+  const unsigned tid = threadIdx.x;
   const long long row0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
   const long long left = n_rows - row0;
   const unsigned rows = static_cast<unsigned>(left < rows_per_cta ? left : rows_per_cta);
-  // The tile's words in field-major order: q in [rows * col_start(f), rows * col_end(f)) walks field f's dense block.
-  const unsigned total = rows * static_cast<unsigned>(D);
-  for (unsigned base = threadIdx.x; base < total; base += PACK_THREADS * PACK_MAX_LOADS) {
-    float v[PACK_MAX_LOADS];
-    unsigned slot[PACK_MAX_LOADS];
-#pragma unroll
-    for (int k = 0; k < PACK_MAX_LOADS; ++k) {
-      const unsigned q = base + k * PACK_THREADS;
-      slot[k] = 0xFFFFFFFFu;
-      if (q < total) {
-        int f = 0;
-#pragma unroll
-        for (int g = 0; g < MBPO_REPLAY_MAX_FIELDS - 1; ++g)
-          f += (g < ft.num_fields - 1 && q >= rows * static_cast<unsigned>(ft.col_end[g])) ? 1 : 0;
-        const unsigned w = static_cast<unsigned>(ft.width[f]);
-        const unsigned col0 = static_cast<unsigned>(ft.col_end[f]) - w;
-        const unsigned j = q - rows * col0;
-        const unsigned r = (w == 1u) ? j : j / w;
-        v[k] = __ldcs(ft.ptr[f] + row0 * w + j);
-        slot[k] = r * static_cast<unsigned>(D) + col0 + (j - r * w);
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < PACK_MAX_LOADS; ++k)
-      if (slot[k] != 0xFFFFFFFFu) tile[slot[k]] = v[k];
-  }
-  __syncthreads();
-  const unsigned words = rows * static_cast<unsigned>(D);
   long long p0 = first_physical + row0;                  // physical row of the tile's first row
   if (p0 >= capacity) p0 -= capacity;
-  const long long until_end = (capacity - p0) * D;       // words before the ring wraps
-  float* __restrict__ dst = data + p0 * D;
-  for (unsigned i = threadIdx.x; i < words; i += PACK_THREADS) {
-    if (static_cast<long long>(i) < until_end) dst[i] = tile[i];
-    else data[static_cast<long long>(i) - until_end] = tile[i];
+  const long long g0 = p0 * D;                           // first word of the tile in the ring
+  const unsigned total = rows * static_cast<unsigned>(D);
+  const long long until_end = capacity * D - g0;         // words before the ring wraps
+  const unsigned shift = VEC ? static_cast<unsigned>(g0 & 3) : 0u;
+  float* tile = pack_smem + shift;
+
+  if (VEC && (rows & 3u) == 0u) {
+    // The tile's 16-byte words in field-major order: q4 in [rows * col_start(f) / 4, rows * col_end(f) / 4) walks
+    // field f's dense block.  PACK_LOADS loads per thread are issued before the first is scattered.
+    const unsigned total4 = total >> 2;
+    for (unsigned base = tid; base < total4; base += PACK_THREADS * PACK_LOADS) {
+      float4 x[PACK_LOADS];
+      unsigned fld[PACK_LOADS], j0[PACK_LOADS];
+#pragma unroll
+      for (int k = 0; k < PACK_LOADS; ++k) {
+        const unsigned q4 = base + k * PACK_THREADS;
+        fld[k] = 0xFFFFFFFFu;
+        if (q4 < total4) {
+          unsigned f = 0;
+#pragma unroll
+          for (int g = 0; g < MBPO_REPLAY_MAX_FIELDS - 1; ++g)
+            f += (g < ft.num_fields - 1 && 4u * q4 >= rows * static_cast<unsigned>(ft.col_end[g])) ? 1u : 0u;
+          const unsigned w = static_cast<unsigned>(ft.width[f]);
+          const unsigned j = 4u * q4 - rows * (static_cast<unsigned>(ft.col_end[f]) - w);
+          x[k] = __ldcs(reinterpret_cast<const float4*>(ft.ptr[f] + row0 * w + j));
+          fld[k] = f;
+          j0[k] = j;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < PACK_LOADS; ++k) {
+        if (fld[k] != 0xFFFFFFFFu) {
+          const unsigned w = static_cast<unsigned>(ft.width[fld[k]]);
+          pack_scatter(tile, D, w, static_cast<unsigned>(ft.col_end[fld[k]]) - w, ft.magic[fld[k]], j0[k], &x[k].x, 4);
+        }
+      }
+    }
+  } else {
+    for (int f = 0; f < ft.num_fields; ++f) {
+      const unsigned w = static_cast<unsigned>(ft.width[f]);
+      const unsigned col0 = static_cast<unsigned>(ft.col_end[f]) - w;
+      const unsigned words = rows * w;
+      const float* __restrict__ src = ft.ptr[f] + row0 * w;
+      for (unsigned j = tid; j < words; j += PACK_THREADS) {
+        const float y = __ldcs(src + j);
+        pack_scatter(tile, D, w, col0, ft.magic[f], j, &y, 1);
+      }
+    }
+  }
+  __syncthreads();
+  if (VEC && static_cast<long long>(total) <= until_end) {
+    float* __restrict__ dst = data + g0;
+    const unsigned head = (4u - shift) & 3u;
+    const unsigned h = head < total ? head : total;
+    if (tid < h) dst[tid] = tile[tid];
+    const unsigned nvec = (total - h) >> 2;
+    const float4* t4 = reinterpret_cast<const float4*>(tile + h);
+    float4* d4 = reinterpret_cast<float4*>(dst + h);
+    for (unsigned k = tid; k < nvec; k += PACK_THREADS) d4[k] = t4[k];
+    for (unsigned i = h + 4u * nvec + tid; i < total; i += PACK_THREADS) dst[i] = tile[i];
+  } else {
+    float* __restrict__ dst = data + g0;
+    for (unsigned i = tid; i < total; i += PACK_THREADS) {
+      if (static_cast<long long>(i) < until_end) dst[i] = tile[i];
+      else data[static_cast<long long>(i) - until_end] = tile[i];
+    }
   }
 }
 
@@ -219,6 +275,7 @@ int mbpo_replay_insert(MbpoReplayState* s, const MbpoReplayFields* fields, long 
     col += fields->width[f];
     ft.col_end[f] = col;
     ft.width[f] = fields->width[f];
+    ft.magic[f] = static_cast<unsigned>((1ULL << 32) / static_cast<unsigned>(fields->width[f]) + 1ULL);
     ft.ptr[f] = fields->ptr[f];
   }
   MBPO_REQUIRE(col == s->row_width, "replay_insert: field widths sum to %d, row_width is %d", col, s->row_width);
@@ -229,16 +286,23 @@ int mbpo_replay_insert(MbpoReplayState* s, const MbpoReplayFields* fields, long 
   const long long head = ((s->head - roll) % s->capacity + s->capacity) % s->capacity;  // roll by r: new[i] = old[i - r]
   const long long position = s->insert_position + roll;
   const long long first_physical = (head + position) % s->capacity;
-  // tile of rows_per_cta rows in at most 40 KB of shared memory (5 CTAs per SM)
-  int rows_per_cta = static_cast<int>((40 * 1024) / (4 * static_cast<long long>(s->row_width)));
-  if (rows_per_cta > 256) rows_per_cta = 256;
+  // tile of rows_per_cta rows in at most 20 KB of shared memory: 5 x 16 bytes per thread in flight
+  int rows_per_cta = static_cast<int>((20 * 1024) / (4 * static_cast<long long>(s->row_width)));
+  if (rows_per_cta > 512) rows_per_cta = 512;
   if (rows_per_cta >= 32) rows_per_cta &= ~31;
   MBPO_REQUIRE(rows_per_cta >= 1, "replay_insert: a row of %d floats does not fit the staging tile", s->row_width);
   const long long blocks = (n_rows + rows_per_cta - 1) / rows_per_cta;
   MBPO_REQUIRE(blocks < (1LL << 31), "replay_insert: n_rows %lld too large for one launch", n_rows);
-  const size_t smem = static_cast<size_t>(rows_per_cta) * s->row_width * sizeof(float);
-  replay_pack_kernel<<<static_cast<unsigned>(blocks), PACK_THREADS, smem, as_stream(stream)>>>(
-      ft, s->row_width, rows_per_cta, n_rows, s->data, s->capacity, first_physical);
+  const size_t smem = (static_cast<size_t>(rows_per_cta) * s->row_width + 4) * sizeof(float);
+  // 16-byte copies when every block of a tile starts on a 16-byte boundary
+  bool vec = (reinterpret_cast<uintptr_t>(s->data) & 15u) == 0 && rows_per_cta % 4 == 0;
+  for (int f = 0; f < fields->num_fields; ++f) vec = vec && (reinterpret_cast<uintptr_t>(fields->ptr[f]) & 15u) == 0;
+  if (vec)
+    replay_pack_kernel<true><<<static_cast<unsigned>(blocks), PACK_THREADS, smem, as_stream(stream)>>>(
+        ft, s->row_width, rows_per_cta, n_rows, s->data, s->capacity, first_physical);
+  else
+    replay_pack_kernel<false><<<static_cast<unsigned>(blocks), PACK_THREADS, smem, as_stream(stream)>>>(
+        ft, s->row_width, rows_per_cta, n_rows, s->data, s->capacity, first_physical);
   rc = check_launch("replay_pack_kernel");
   if (rc != MBPO_OK) return rc;
   s->head = head;
