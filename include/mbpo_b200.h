@@ -388,6 +388,19 @@ int mbpo_env_reset_from_buffer(const MbpoReplayState* state_host, const uint32_t
                                float* obs_out /*[E,X]*/, float* reward_out /*[E]*/,
                                uint32_t* sys_key_out /*[E,2]*/, int32_t* idx_out /*[E]*/, void* stream);
 
+/* EvalWrapper (mbpo/optimizers/policy_optimizers/brax_utils/training.py:156-199) folded over the Transition of an
+ * unroll, as acting.Evaluator uses it (sac/acting.py:82-151): per env, in step order and in float32,
+ *   episode_steps  = active ? steps_t : episode_steps     (steps_t: EpisodeWrapper's counter after step t)
+ *   episode_reward += reward_t * active
+ *   active        *= discount_t                            (discount = 1 - done, acting.py:51)
+ * steps_t is rebuilt from steps_in / done_in (the env state the unroll started from) and the discount stream:
+ * steps = (done ? 0 : steps) + action_repeat (training.py:98,120-124).  reward / discount are [T, E] with the
+ * given strides; episode_reward, episode_steps, active are [E], read and written (EvalWrapper.reset gives 0, 0, 1),
+ * so an evaluation may be folded chunk by chunk. */
+int mbpo_eval_metrics(const float* reward, const float* discount, const float* steps_in /*[E]*/,
+                      const float* done_in /*[E]*/, int action_repeat, int E, int T, long long stride_t,
+                      long long stride_e, float* episode_reward, float* episode_steps, float* active, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -221,6 +221,32 @@ __global__ void env_reset_kernel(const float* __restrict__ data, long long capac
   if (idx_out) idx_out[e] = idx;
 }
 
+// EvalWrapper folded over an unroll: one thread per env, the [T, E] streams are read a line per warp per step.
+__global__ void eval_metrics_kernel(const float* __restrict__ reward, const float* __restrict__ discount,
+                                    const float* __restrict__ steps_in, const float* __restrict__ done_in,
+                                    float action_repeat, int E, int T, long long stride_t, long long stride_e,
+                                    float* __restrict__ episode_reward, float* __restrict__ episode_steps,
+                                    float* __restrict__ active) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  float steps = steps_in[e], done = done_in[e];
+  float sum = episode_reward[e], ep_steps = episode_steps[e], act = active[e];
+  const float* r = reward + e * stride_e;
+  const float* d = discount + e * stride_e;
+#pragma unroll 4
+  for (int t = 0; t < T; ++t) {
+    const float rt = __ldcs(r + t * stride_t), dt = __ldcs(d + t * stride_t);
+    steps = __fadd_rn(done != 0.0f ? 0.0f : steps, action_repeat);       // training.py:98,120-124
+    ep_steps = act != 0.0f ? steps : ep_steps;                           // :181-185
+    sum = __fadd_rn(sum, __fmul_rn(rt, act));                            // :186-190 (a + b * active, unfused)
+    act = __fmul_rn(act, dt);                                            // :191
+    done = __fsub_rn(1.0f, dt);
+  }
+  episode_reward[e] = sum;
+  episode_steps[e] = ep_steps;
+  active[e] = act;
+}
+
 int check_state(const MbpoReplayState* s, const char* who) {
   MBPO_REQUIRE(s != nullptr, "%s: state is null", who);
   MBPO_REQUIRE(s->data != nullptr, "%s: data is null", who);
@@ -373,6 +399,21 @@ int mbpo_env_reset_from_buffer(const MbpoReplayState* s, const uint32_t* rngs, i
                                                                   sample_batch_size, minval, span, x_dim, reward_col,
                                                                   obs_out, reward_out, sys_key_out, idx_out);
   return check_launch("env_reset_kernel");
+}
+
+int mbpo_eval_metrics(const float* reward, const float* discount, const float* steps_in, const float* done_in,
+                      int action_repeat, int E, int T, long long stride_t, long long stride_e, float* episode_reward,
+                      float* episode_steps, float* active, void* stream) {
+  MBPO_REQUIRE(E >= 0 && T >= 0, "eval_metrics: negative size");
+  MBPO_REQUIRE(action_repeat >= 1, "eval_metrics: action_repeat %d < 1", action_repeat);
+  if (E == 0) return MBPO_OK;
+  MBPO_REQUIRE(steps_in && done_in && episode_reward && episode_steps && active, "eval_metrics: null pointer");
+  MBPO_REQUIRE(T == 0 || (reward && discount), "eval_metrics: null pointer");
+  const int threads = 128;
+  eval_metrics_kernel<<<(E + threads - 1) / threads, threads, 0, as_stream(stream)>>>(
+      reward, discount, steps_in, done_in, static_cast<float>(action_repeat), E, T, stride_t, stride_e, episode_reward,
+      episode_steps, active);
+  return check_launch("eval_metrics_kernel");
 }
 
 }  // extern "C"

@@ -187,3 +187,72 @@ def get_experience(env: VmappedSystemEnv, env_state: EnvState, policy: Policy, k
     nstate, tr, key_out = _rollout(env, env_state, policy, key, num_env_steps, _lib.KEYS_SAC, ("truncation",),
                                    env_offset, total_envs)
     return key_out, nstate, tr
+
+
+def eval_metrics(env_state: EnvState, transitions: Transition, action_repeat: int = 1, carry=None):
+    """EvalWrapper (brax_utils/training.py:156-199) folded over the Transition of an unroll that started from
+    ``env_state``: -> (episode_reward [E], episode_steps [E], active_episodes [E]).  ``carry`` = the triple of an
+    earlier chunk of the same evaluation (default: EvalWrapper.reset's zeros, zeros, ones)."""
+    r, d = transitions.reward, transitions.discount
+    T, E = r.shape
+    dev = r.device
+    if carry is None:
+        carry = (torch.zeros(E, device=dev), torch.zeros(E, device=dev), torch.ones(E, device=dev))
+    ep_reward, ep_steps, active = [c.to(torch.float32).contiguous().clone() for c in carry]
+    if r.stride() != d.stride():
+        d = d.contiguous()
+        r = r.contiguous()
+    steps_in, done_in = env_state.info["steps"].contiguous(), env_state.done.contiguous()
+    with _lib.cuda_guard(r):
+        _lib.check(_lib.lib.mbpo_eval_metrics(r.data_ptr(), d.data_ptr(), _lib.ptr(steps_in), _lib.ptr(done_in),
+                                              int(action_repeat), E, T, r.stride(0) if T else 0, r.stride(1) if T else 1,
+                                              _lib.ptr(ep_reward), _lib.ptr(ep_steps), _lib.ptr(active),
+                                              _lib.stream_ptr(dev)))
+    return ep_reward, ep_steps, active
+
+
+class Evaluator:
+    """sac/acting.py:82-151.  ``eval_env`` is the wrapped env (``envs.wrap(BraxWrapper(...), episode_length,
+    action_repeat)``); every evaluation resets ``num_eval_envs`` envs from the true buffer, unrolls one episode with
+    ``eval_policy_fn(policy_params)`` in one launch and folds EvalWrapper's episode metrics over the Transition."""
+
+    def __init__(self, eval_env: VmappedSystemEnv, eval_policy_fn, num_eval_envs: int, episode_length: int,
+                 action_repeat: int, key: torch.Tensor):
+        self._key = key
+        self._eval_walltime = 0.
+        self._env = eval_env
+        self._policy_fn = eval_policy_fn
+        self._num_eval_envs = int(num_eval_envs)
+        self._unroll_length = int(episode_length) // int(action_repeat)
+        self._action_repeat = int(action_repeat)
+        self._steps_per_unroll = int(episode_length) * int(num_eval_envs)
+
+    def _generate_eval_unroll(self, policy_params, key: torch.Tensor):
+        from . import random as jr
+        reset_keys = jr.split(key, self._num_eval_envs)
+        first = self._env.reset(reset_keys)
+        nstate, tr = generate_unroll(self._env, first, self._policy_fn(policy_params), key, self._unroll_length)
+        ep_reward, ep_steps, active = eval_metrics(first, tr, self._action_repeat)
+        nstate.info["eval_metrics"] = dict(episode_metrics={"reward": ep_reward}, active_episodes=active,
+                                           episode_steps=ep_steps)
+        return nstate
+
+    def run_evaluation(self, policy_params, training_metrics, unroll_key: torch.Tensor = None,
+                       aggregate_episodes: bool = True):
+        import time
+        import numpy as np
+        from . import random as jr
+        if unroll_key is None:
+            keys = jr.split(self._key, 2)
+            self._key, unroll_key = keys[0], keys[1]
+        t = time.time()
+        eval_state = self._generate_eval_unroll(policy_params, unroll_key)
+        em = eval_state.info["eval_metrics"]
+        values = {name: v.cpu().numpy() for name, v in em["episode_metrics"].items()}     # synchronises
+        epoch_eval_time = time.time() - t
+        metrics = {"eval/episode_%s" % name: (np.mean(v) if aggregate_episodes else v) for name, v in values.items()}
+        metrics["eval/avg_episode_length"] = np.mean(em["episode_steps"].cpu().numpy())
+        metrics["eval/epoch_eval_time"] = epoch_eval_time
+        metrics["eval/sps"] = self._steps_per_unroll / epoch_eval_time
+        self._eval_walltime = self._eval_walltime + epoch_eval_time
+        return {"eval/walltime": self._eval_walltime, **training_metrics, **metrics}

@@ -89,3 +89,21 @@ def brax_wrapper_reset(rngs: np.ndarray, queue: UniformSamplingQueue, st: Replay
         sys_keys[e] = keys[1]
         idx0[e] = idx[0]
     return obs, reward, sys_keys, idx0
+
+
+def eval_metrics(reward, discount, steps_in, done_in, action_repeat: int):
+    """EvalWrapper.step (brax_utils/training.py:172-199) folded over the [T, E] reward / discount streams of an unroll
+    that started from (steps_in, done_in), from EvalWrapper.reset's zeros (:159-170).  float32, step order.
+    -> (episode_reward [E], episode_steps [E], active_episodes [E])."""
+    F = np.float32
+    reward, discount = np.asarray(reward, F), np.asarray(discount, F)
+    steps, done = np.asarray(steps_in, F).copy(), np.asarray(done_in, F).copy()
+    E = steps.shape[0]
+    ep_reward, ep_steps, active = np.zeros(E, F), np.zeros(E, F), np.ones(E, F)
+    for t in range(reward.shape[0]):
+        steps = (np.where(done != 0, F(0), steps) + F(action_repeat)).astype(F)     # :98,120-124
+        ep_steps = np.where(active != 0, steps, ep_steps)                           # :181-185
+        ep_reward = (ep_reward + (reward[t] * active).astype(F)).astype(F)          # :186-190
+        active = (active * discount[t]).astype(F)                                   # :191, discount = 1 - done
+        done = (F(1) - discount[t]).astype(F)
+    return ep_reward, ep_steps, active

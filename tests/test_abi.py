@@ -99,6 +99,7 @@ def test_error_codes_without_gpu(mb):
     assert L.lib.mbpo_replay_sample(C.byref(st), None, 0, 4, None, None, None, None) == L.MBPO_EINVAL
     assert L.lib.mbpo_env_reset_from_buffer(C.byref(st), None, 4, 0, 1, 3, 9, None, None, None, None, None) == L.MBPO_EINVAL
     assert L.lib.mbpo_prng_randint(None, 4, 2, 0, 0, 10, None, None) == L.MBPO_EINVAL
+    assert L.lib.mbpo_eval_metrics(None, None, None, None, 1, 4, 4, 4, 1, None, None, None, None) == L.MBPO_EINVAL
     with pytest.raises(mb.MbpoError):
         L.check(L.MBPO_EINVAL)
     with pytest.raises(NotImplementedError):
@@ -171,6 +172,10 @@ def test_api_surface_matches_reference(mb):
         "self", "system", "system_params", "sample_buffer_state", "sample_buffer"]
     assert list(inspect.signature(BraxWrapper.reset).parameters) == ["self", "rng"]
     assert list(inspect.signature(BraxWrapper.step).parameters) == ["self", "state", "action"]
+    assert list(inspect.signature(acting.Evaluator.__init__).parameters) == [            # sac/acting.py:85-88
+        "self", "eval_env", "eval_policy_fn", "num_eval_envs", "episode_length", "action_repeat", "key"]
+    assert list(inspect.signature(acting.Evaluator.run_evaluation).parameters) == [      # :118-122
+        "self", "policy_params", "training_metrics", "unroll_key", "aggregate_episodes"]
     assert issubclass(iCemTO, BaseOptimizer) and issubclass(PendulumSystem, System)
     assert iCEMOptimizer(horizon=20).can_act_in_batches is False
     s = PendulumSystem()

@@ -208,3 +208,77 @@ def test_insert_at_full_size_is_a_permutation_free_copy(mb, cuda_device):
         assert torch.equal(live, want)
         assert torch.equal(live.double().sum(0), want.double().sum(0))
     assert st.head != 0 and st.insert_position == n + 1000
+
+
+def test_eval_metrics_match_oracle_and_fold_in_chunks(mb, cuda_device):
+    from mbpo_b200 import acting
+    from mbpo_b200.envs import EnvState
+    from mbpo_b200.utils.optimizer_utils import Transition
+    dev = cuda_device
+    rng = np.random.default_rng(1)
+    T, E, rep = 57, 1000, 2
+    reward = rng.standard_normal((T, E)).astype(np.float32)
+    discount = (rng.random((T, E)) > 0.02).astype(np.float32)         # dones at arbitrary steps
+    steps0 = (rng.integers(0, 5, E) * rep).astype(np.float32)
+    done0 = (rng.random(E) < 0.1).astype(np.float32)
+    want = obr.eval_metrics(reward, discount, steps0, done0, rep)
+    st = EnvState(obs=None, reward=None, done=_dev(done0, dev), system_params=None, info={"steps": _dev(steps0, dev)})
+    tr = Transition(None, None, _dev(reward, dev), _dev(discount, dev), None)
+    got = acting.eval_metrics(st, tr, rep)
+    for g, w in zip(got, want):
+        assert np.array_equal(g.cpu().numpy(), w)
+    # two chunks: the second starts from the env state the first ended in
+    k = 20
+    a = acting.eval_metrics(st, Transition(None, None, tr.reward[:k], tr.discount[:k], None), rep)
+    steps, done = steps0.copy(), done0.copy()
+    for t in range(k):
+        steps = np.where(done != 0, 0, steps) + rep
+        done = 1 - discount[t]
+    st2 = EnvState(obs=None, reward=None, done=_dev(done.astype(np.float32), dev), system_params=None,
+                   info={"steps": _dev(steps.astype(np.float32), dev)})
+    b = acting.eval_metrics(st2, Transition(None, None, tr.reward[k:], tr.discount[k:], None), rep, carry=a)
+    for g, w in zip(b, want):
+        assert np.array_equal(g.cpu().numpy(), w)
+
+
+def test_evaluator_runs_one_episode_per_env(mb, cuda_device):
+    """sac/acting.py:82-151: reset from the true buffer, one deterministic episode per eval env, EvalWrapper's metrics.
+    Checked against the oracle's actor rollout teacher-forced on the GPU's observations and its fold of the rewards."""
+    from mbpo_b200 import acting, envs
+    from mbpo_b200.replay_buffers import UniformSamplingQueue
+    from mbpo_b200.systems import BraxWrapper, PendulumSystem
+    from mbpo_b200.utils.optimizer_utils import Transition
+    dev = cuda_device
+    system = PendulumSystem()
+    q = UniformSamplingQueue(10, _true_dummy(mb, dev), 1)
+    first = system.reset(device=dev)
+    st = q.insert(q.init(_dev(ojr.PRNGKey(0), dev)),
+                  Transition(first.x_next[None], torch.zeros((1, 1), device=dev), first.reward[None],
+                             torch.full((1,), 0.99, device=dev), first.x_next[None]))
+    L, rep, E = 50, 1, 64
+    env = envs.wrap(BraxWrapper(system, system.init_params(_dev(ojr.PRNGKey(1), dev)), st, q), L, rep)
+    pol = orc.make_policy_params(seed=7)
+    make_policy = acting.make_inference_fn()
+    import functools
+    params = acting.PolicyParams([_dev(w, dev) for w in pol.weights], [_dev(b, dev) for b in pol.biases])
+    ev = acting.Evaluator(env, functools.partial(make_policy, deterministic=True), num_eval_envs=E, episode_length=L,
+                          action_repeat=rep, key=_dev(ojr.PRNGKey(4), dev))
+    key = _dev(ojr.PRNGKey(6), dev)
+    state = ev._generate_eval_unroll(params, key)
+    em = state.info["eval_metrics"]
+    assert torch.all(em["active_episodes"] == 0) and torch.all(em["episode_steps"] == L)
+    # the same unroll through the public pieces
+    first_state = env.reset(mb.random.split(key, E))
+    nst, tr = acting.generate_unroll(env, first_state, make_policy(params, deterministic=True), key, L // rep)
+    want = obr.eval_metrics(tr.reward.cpu().numpy(), tr.discount.cpu().numpy(), np.zeros(E, np.float32),
+                            np.zeros(E, np.float32), rep)
+    assert np.array_equal(em["episode_metrics"]["reward"].cpu().numpy(), want[0])
+    x0 = np.tile(np.array([-1, 0, 0], np.float32), (E, 1))
+    o, _ = orc.actor_rollout(pol, x0, ojr.PRNGKey(6), L, L, key_convention="unroll", deterministic=True,
+                             teacher_obs=tr.observation.cpu().numpy())
+    np.testing.assert_allclose(tr.reward.cpu().numpy(), o["reward"], rtol=1e-5, atol=3e-6)
+    metrics = ev.run_evaluation(params, {"training/sps": 1.0}, unroll_key=key)
+    assert metrics["eval/episode_reward"] == np.mean(want[0]) and metrics["eval/avg_episode_length"] == L
+    assert metrics["training/sps"] == 1.0 and metrics["eval/sps"] > 0 and metrics["eval/walltime"] > 0
+    m2 = ev.run_evaluation(params, {}, aggregate_episodes=False)       # draws its own key
+    assert m2["eval/episode_reward"].shape == (E,)

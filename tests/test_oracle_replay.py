@@ -90,3 +90,26 @@ def test_brax_wrapper_reset_per_env_keys():
         want = jp.randint(jp.split(keys[0], 2)[1], 1, 0, 5)[0]
         assert idx[e] == want
         assert np.array_equal(obs[e], st.data[want, :3]) and reward[e] == st.data[want, 4]
+
+
+def test_eval_metrics_fold_matches_a_per_env_statement():
+    """EvalWrapper: rewards are summed while the first episode is active; episode_steps freezes at its last step."""
+    rng = np.random.default_rng(0)
+    T, E, L, rep = 23, 40, 7, 2
+    reward = rng.standard_normal((T, E)).astype(np.float32)
+    steps0 = (rng.integers(0, 3, E) * rep).astype(np.float32)
+    done0 = (rng.random(E) < 0.2).astype(np.float32)
+    discount = np.ones((T, E), np.float32)
+    want_r, want_s = np.zeros(E, np.float32), np.zeros(E, np.float32)
+    for e in range(E):
+        s, d, active = steps0[e], done0[e], True
+        for t in range(T):
+            s = (0 if d else s) + rep
+            d = 1.0 if s >= L else 0.0
+            discount[t, e] = 1.0 - d
+            if active:
+                want_r[e] = np.float32(want_r[e] + reward[t, e])
+                want_s[e] = s
+            active = active and not d
+    got_r, got_s, active = br.eval_metrics(reward, discount, steps0, done0, rep)
+    assert np.array_equal(got_r, want_r) and np.array_equal(got_s, want_s) and np.all(active == 0)
