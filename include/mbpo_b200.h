@@ -401,6 +401,28 @@ int mbpo_eval_metrics(const float* reward, const float* discount, const float* s
                       const float* done_in /*[E]*/, int action_repeat, int E, int T, long long stride_t,
                       long long stride_e, float* episode_reward, float* episode_steps, float* active, void* stream);
 
+/* ---- observation normaliser (brax running_statistics) ------------------------------------------
+ * running_statistics.update(normalizer_params, transitions.observation, pmap_axis_name) as SAC / PPO call it after
+ * every collection (sac/sac.py:298-301): count += n; mean += sum(batch - mean) / count; summed_variance +=
+ * sum((batch - old_mean) * (batch - new_mean)); std = clip(sqrt(max(summed_variance, 0) / count)).
+ * Split at the one exchange step of the path: _accumulate reduces this rank's rows to sums[2X + 1] (float64:
+ * sum d, sum d*d with d = batch - old_mean in float32, and the row count), the caller all-reduces sums over the ranks
+ * (the reference's psum), _finalize applies the update with step_increment = sums[2X].  sum(d * (d - mean_update)) = sum d*d - mean_update * sum d,
+ * so one pass over the rows and one all-reduce replace the reference's two of each.  Deterministic: per-CTA partials
+ * are combined in a fixed order (no atomics).  workspace: mbpo_running_statistics_workspace_bytes(X) bytes. */
+size_t mbpo_running_statistics_workspace_bytes(int X);
+int mbpo_running_statistics_accumulate(const float* batch /*[n_rows, X]*/, long long n_rows, int X,
+                                       const float* mean /*[X]*/, void* workspace, size_t workspace_bytes,
+                                       double* sums_out /*[2X+1]*/, void* stream);
+int mbpo_running_statistics_finalize(const double* sums /*[2X+1]*/, int X,
+                                     const float* count_in /*[1]*/, const float* mean_in /*[X]*/,
+                                     const float* summed_variance_in /*[X]*/, float std_min_value, float std_max_value,
+                                     float* count_out /*[1]*/, float* mean_out /*[X]*/, float* summed_variance_out /*[X]*/,
+                                     float* std_out /*[X]*/, void* stream);
+/* running_statistics.normalize: out = (batch - mean) / std, clipped to +-max_abs_value when it is > 0. */
+int mbpo_running_statistics_normalize(const float* batch /*[n_rows, X]*/, long long n_rows, int X, const float* mean,
+                                      const float* std, float max_abs_value, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -247,6 +247,87 @@ __global__ void eval_metrics_kernel(const float* __restrict__ reward, const floa
   active[e] = act;
 }
 
+// ---- running statistics ---------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_CTAS = 148 * 4;
+constexpr int RS_MAX_X = 64;
+
+// Pass 1: every thread walks words i = gid, gid + stride, ... of the flat [n_rows * X] batch with stride a multiple
+// of X, so its column x = i % X never changes: two float64 accumulators per thread, coalesced 4-byte reads.
+__global__ void __launch_bounds__(RS_THREADS)
+running_stats_partial_kernel(const float* __restrict__ batch, long long total_words, int X,
+                             const float* __restrict__ mean, long long stride, double* __restrict__ partials) {
+  __shared__ double sh[2][RS_THREADS];
+  const long long gid = static_cast<long long>(blockIdx.x) * RS_THREADS + threadIdx.x;
+  double s1 = 0.0, s2 = 0.0;
+  if (gid < stride) {
+    const float m = mean[gid % X];
+    for (long long i = gid; i < total_words; i += stride) {
+      const float d = __fsub_rn(__ldcs(batch + i), m);      // diff_to_old_mean in float32, like the reference
+      s1 += static_cast<double>(d);
+      s2 += static_cast<double>(d) * static_cast<double>(d);
+    }
+  }
+  sh[0][threadIdx.x] = s1;
+  sh[1][threadIdx.x] = s2;
+  __syncthreads();
+  // fixed-order combine: thread x (< X) adds the lanes of its column in index order
+  if (threadIdx.x < X) {
+    const int first = static_cast<int>(((threadIdx.x - (static_cast<long long>(blockIdx.x) * RS_THREADS) % X) % X + X) % X);
+    double a = 0.0, b = 0.0;
+    for (int t = first; t < RS_THREADS; t += X) {
+      a += sh[0][t];
+      b += sh[1][t];
+    }
+    partials[(static_cast<long long>(blockIdx.x) * 2) * X + threadIdx.x] = a;
+    partials[(static_cast<long long>(blockIdx.x) * 2 + 1) * X + threadIdx.x] = b;
+  }
+}
+
+__global__ void running_stats_combine_kernel(const double* __restrict__ partials, int ctas, int X, double n_rows,
+                                             double* __restrict__ sums) {
+  const int j = threadIdx.x;  // 0 .. 2X-1: (which, x)
+  if (j == 2 * X) sums[j] = n_rows;
+  if (j >= 2 * X) return;
+  const int which = j / X, x = j % X;
+  double a = 0.0;
+  for (int c = 0; c < ctas; ++c) a += partials[(static_cast<long long>(c) * 2 + which) * X + x];
+  sums[j] = a;
+}
+
+__global__ void running_stats_finalize_kernel(const double* __restrict__ sums, int X,
+                                              const float* __restrict__ count_in, const float* __restrict__ mean_in,
+                                              const float* __restrict__ sv_in, float std_min, float std_max,
+                                              float* __restrict__ count_out, float* __restrict__ mean_out,
+                                              float* __restrict__ sv_out, float* __restrict__ std_out) {
+  const int x = threadIdx.x;
+  if (x >= X) return;
+  const float count = __fadd_rn(count_in[0], static_cast<float>(sums[2 * X]));   // step_increment (psum-ed)
+  const double mean_update = sums[x] / static_cast<double>(count);
+  const float mean = __fadd_rn(mean_in[x], static_cast<float>(mean_update));
+  // sum(d_old * d_new) with d_new = d_old - mean_update
+  const double variance_update = sums[X + x] - mean_update * sums[x];
+  const float sv = __fadd_rn(sv_in[x], static_cast<float>(variance_update));
+  float sd = sqrtf(__fdiv_rn(fmaxf(sv, 0.0f), count));
+  sd = fminf(fmaxf(sd, std_min), std_max);
+  __syncthreads();
+  if (x == 0) count_out[0] = count;
+  mean_out[x] = mean;
+  sv_out[x] = sv;
+  std_out[x] = sd;
+}
+
+__global__ void running_stats_normalize_kernel(const float* __restrict__ batch, long long total_words, int X,
+                                               const float* __restrict__ mean, const float* __restrict__ std,
+                                               float max_abs, float* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total_words) return;
+  const int x = static_cast<int>(i % X);
+  float v = __fdiv_rn(__fsub_rn(batch[i], mean[x]), std[x]);
+  if (max_abs > 0.0f) v = fminf(fmaxf(v, -max_abs), max_abs);
+  out[i] = v;
+}
+
 int check_state(const MbpoReplayState* s, const char* who) {
   MBPO_REQUIRE(s != nullptr, "%s: state is null", who);
   MBPO_REQUIRE(s->data != nullptr, "%s: data is null", who);
@@ -414,6 +495,62 @@ int mbpo_eval_metrics(const float* reward, const float* discount, const float* s
       reward, discount, steps_in, done_in, static_cast<float>(action_repeat), E, T, stride_t, stride_e, episode_reward,
       episode_steps, active);
   return check_launch("eval_metrics_kernel");
+}
+
+size_t mbpo_running_statistics_workspace_bytes(int X) {
+  if (X < 1 || X > RS_MAX_X) return 0;
+  return static_cast<size_t>(RS_CTAS) * 2 * X * sizeof(double);
+}
+
+int mbpo_running_statistics_accumulate(const float* batch, long long n_rows, int X, const float* mean,
+                                       void* workspace, size_t workspace_bytes, double* sums_out, void* stream) {
+  MBPO_REQUIRE(X >= 1 && X <= RS_MAX_X, "running_statistics: X %d outside [1, %d]", X, RS_MAX_X);
+  MBPO_REQUIRE(n_rows >= 0, "running_statistics: n_rows < 0");
+  MBPO_REQUIRE(mean && workspace && sums_out, "running_statistics: null pointer");
+  MBPO_REQUIRE(n_rows == 0 || batch, "running_statistics: batch is null");
+  if (workspace_bytes < mbpo_running_statistics_workspace_bytes(X))
+    return fail(MBPO_EWORKSPACE, "running_statistics: workspace %zu < %zu bytes", workspace_bytes,
+                mbpo_running_statistics_workspace_bytes(X));
+  MBPO_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 7u) == 0, "running_statistics: workspace not 8-byte aligned");
+  const long long total = n_rows * X;
+  // the largest multiple of X that the grid covers: every thread keeps one column
+  const long long stride = (static_cast<long long>(RS_CTAS) * RS_THREADS / X) * X;
+  running_stats_partial_kernel<<<RS_CTAS, RS_THREADS, 0, as_stream(stream)>>>(batch, total, X, mean, stride,
+                                                                             static_cast<double*>(workspace));
+  int rc = check_launch("running_stats_partial_kernel");
+  if (rc != MBPO_OK) return rc;
+  running_stats_combine_kernel<<<1, 2 * RS_MAX_X + 32, 0, as_stream(stream)>>>(
+      static_cast<const double*>(workspace), RS_CTAS, X, static_cast<double>(n_rows), sums_out);
+  return check_launch("running_stats_combine_kernel");
+}
+
+int mbpo_running_statistics_finalize(const double* sums, int X, const float* count_in,
+                                     const float* mean_in, const float* summed_variance_in, float std_min_value,
+                                     float std_max_value, float* count_out, float* mean_out,
+                                     float* summed_variance_out, float* std_out, void* stream) {
+  MBPO_REQUIRE(X >= 1 && X <= RS_MAX_X, "running_statistics: X %d outside [1, %d]", X, RS_MAX_X);
+  MBPO_REQUIRE(sums && count_in && mean_in && summed_variance_in && count_out && mean_out && summed_variance_out &&
+                   std_out, "running_statistics: null pointer");
+  running_stats_finalize_kernel<<<1, RS_MAX_X, 0, as_stream(stream)>>>(sums, X, count_in, mean_in,
+                                                                       summed_variance_in, std_min_value,
+                                                                       std_max_value, count_out, mean_out,
+                                                                       summed_variance_out, std_out);
+  return check_launch("running_stats_finalize_kernel");
+}
+
+int mbpo_running_statistics_normalize(const float* batch, long long n_rows, int X, const float* mean,
+                                      const float* std, float max_abs_value, float* out, void* stream) {
+  MBPO_REQUIRE(X >= 1 && X <= RS_MAX_X, "running_statistics: X %d outside [1, %d]", X, RS_MAX_X);
+  MBPO_REQUIRE(n_rows >= 0, "running_statistics: n_rows < 0");
+  if (n_rows == 0) return MBPO_OK;
+  MBPO_REQUIRE(batch && mean && std && out, "running_statistics: null pointer");
+  const long long total = n_rows * X;
+  const int threads = 256;
+  const long long blocks = (total + threads - 1) / threads;
+  MBPO_REQUIRE(blocks < (1LL << 31), "running_statistics: too many rows for one launch");
+  running_stats_normalize_kernel<<<static_cast<unsigned>(blocks), threads, 0, as_stream(stream)>>>(
+      batch, total, X, mean, std, max_abs_value, out);
+  return check_launch("running_stats_normalize_kernel");
 }
 
 }  // extern "C"

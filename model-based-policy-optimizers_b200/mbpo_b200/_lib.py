@@ -132,6 +132,10 @@ SIGNATURES = {
     "mbpo_replay_insert": (_I, [C.POINTER(ReplayStateC), C.POINTER(ReplayFieldsC), _LL, _P]),
     "mbpo_replay_sample": (_I, [C.POINTER(ReplayStateC), _P, _I, _I, _P, _P, _P, _P]),
     "mbpo_replay_read": (_I, [C.POINTER(ReplayStateC), _LL, _LL, _P, _P]),
+    "mbpo_running_statistics_workspace_bytes": (_SZ, [_I]),
+    "mbpo_running_statistics_accumulate": (_I, [_P, _LL, _I, _P, _P, _SZ, _P, _P]),
+    "mbpo_running_statistics_finalize": (_I, [_P, _I, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P]),
+    "mbpo_running_statistics_normalize": (_I, [_P, _LL, _I, _P, _P, _F, _P, _P]),
     "mbpo_eval_metrics": (_I, [_P, _P, _P, _P, _I, _I, _I, _LL, _LL, _P, _P, _P, _P]),
     "mbpo_env_reset_from_buffer": (_I, [C.POINTER(ReplayStateC), _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
 }

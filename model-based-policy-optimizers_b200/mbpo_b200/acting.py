@@ -256,3 +256,39 @@ class Evaluator:
         metrics["eval/sps"] = self._steps_per_unroll / epoch_eval_time
         self._eval_walltime = self._eval_walltime + epoch_eval_time
         return {"eval/walltime": self._eval_walltime, **training_metrics, **metrics}
+
+
+class ExperienceCollector:
+    """SAC.get_experience in full (sac/sac.py:283-304): the scan of actor steps (one launch), the observation
+    normaliser update (running_statistics.update, with the psum over ranks when ``pmap_axis_name`` is given) and the
+    replay-buffer insert.  Same argument order and return value as the reference method."""
+
+    def __init__(self, env: VmappedSystemEnv, make_policy, replay_buffer, num_env_steps_between_updates: int,
+                 pmap_axis_name: str = None, env_offset: int = 0, total_envs: int = None):
+        self.env = env
+        self.make_policy = make_policy                 # make_policy((normalizer_params, policy_params)) -> Policy
+        self.replay_buffer = replay_buffer
+        self.num_env_steps_between_updates = int(num_env_steps_between_updates)
+        self._PMAP_AXIS_NAME = pmap_axis_name
+        self._env_offset, self._total_envs = env_offset, total_envs
+
+    def get_experience(self, normalizer_params, policy_params, env_state: EnvState, buffer_state, key: torch.Tensor):
+        from . import running_statistics
+        policy = self.make_policy((normalizer_params, policy_params))
+        key, env_state, transitions = get_experience(self.env, env_state, policy, key,
+                                                     self.num_env_steps_between_updates, self._env_offset,
+                                                     self._total_envs)
+        normalizer_params = running_statistics.update(normalizer_params, transitions.observation,
+                                                      pmap_axis_name=self._PMAP_AXIS_NAME)
+        buffer_state = self.replay_buffer.insert(buffer_state, transitions)
+        return normalizer_params, env_state, buffer_state, key
+
+
+def make_normalized_inference_fn(emit_extras: bool = False, kernel: str = "auto"):
+    """sac_networks.make_inference_fn with ``normalize_observations=True`` (sac_networks.py:58-73):
+    make_policy((normalizer_params, policy_params), deterministic) -> Policy that reads (obs - mean) / std."""
+    def make_policy(params, deterministic: bool = False) -> Policy:
+        normalizer_params, policy_params = params
+        return Policy(policy_params, deterministic, normalizer_params.mean, normalizer_params.std,
+                      emit_extras=emit_extras, kernel=kernel)
+    return make_policy

@@ -107,3 +107,48 @@ def eval_metrics(reward, discount, steps_in, done_in, action_repeat: int):
         active = (active * discount[t]).astype(F)                                   # :191, discount = 1 - done
         done = (F(1) - discount[t]).astype(F)
     return ep_reward, ep_steps, active
+
+
+# ---- brax.training.acme.running_statistics (third party, absent; restated from the published algorithm) --------------
+def running_statistics_init(size: int):
+    F = np.float32
+    return dict(count=F(0), mean=np.zeros(size, F), summed_variance=np.zeros(size, F), std=np.ones(size, F))
+
+
+def running_statistics_update(state, batch, std_min_value=1e-6, std_max_value=1e6, accumulate=np.float32):
+    """running_statistics.update as written (call site sac/sac.py:298-301): count += n; diff_to_old_mean = batch - mean;
+    mean += sum(diff_to_old_mean) / count; summed_variance += sum(diff_to_old_mean * (batch - new_mean));
+    std = clip(sqrt(max(summed_variance, 0) / count)).  ``accumulate`` is the dtype of the two sums (XLA's reduction
+    order is unspecified: float32 pairwise here, float64 for a tight check)."""
+    F = np.float32
+    X = state["mean"].shape[0]
+    batch = np.asarray(batch, F).reshape(-1, X)
+    count = F(state["count"] + F(batch.shape[0]))
+    d_old = (batch - state["mean"]).astype(F)
+    mean_update = (d_old.sum(0, dtype=accumulate) / accumulate(count)).astype(F)
+    mean = (state["mean"] + mean_update).astype(F)
+    d_new = (batch - mean).astype(F)
+    var_update = (d_old * d_new).astype(F).sum(0, dtype=accumulate).astype(F)
+    sv = (state["summed_variance"] + var_update).astype(F)
+    std = np.clip(np.sqrt(np.maximum(sv, F(0)) / count).astype(F), F(std_min_value), F(std_max_value))
+    return dict(count=count, mean=mean, summed_variance=sv, std=std)
+
+
+def running_statistics_sums(batch, mean):
+    """What mbpo_running_statistics_accumulate returns for one rank: float64 [2X] = (sum d, sum d*d), d in float32."""
+    X = mean.shape[0]
+    d = (np.asarray(batch, np.float32).reshape(-1, X) - mean).astype(np.float32).astype(np.float64)
+    return np.concatenate([d.sum(0), (d * d).sum(0)])
+
+
+def running_statistics_finalize(state, sums, step_increment, std_min_value=1e-6, std_max_value=1e6):
+    """mbpo_running_statistics_finalize: sum(d_old * d_new) = sum d*d - mean_update * sum d."""
+    F = np.float32
+    X = state["mean"].shape[0]
+    count = F(state["count"] + F(step_increment))
+    mean_update = sums[:X] / np.float64(count)
+    mean = (state["mean"] + mean_update.astype(F)).astype(F)
+    var_update = sums[X:] - mean_update * sums[:X]
+    sv = (state["summed_variance"] + var_update.astype(F)).astype(F)
+    std = np.clip(np.sqrt(np.maximum(sv, F(0)) / count).astype(F), F(std_min_value), F(std_max_value))
+    return dict(count=count, mean=mean, summed_variance=sv, std=std)

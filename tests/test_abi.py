@@ -99,6 +99,11 @@ def test_error_codes_without_gpu(mb):
     assert L.lib.mbpo_replay_sample(C.byref(st), None, 0, 4, None, None, None, None) == L.MBPO_EINVAL
     assert L.lib.mbpo_env_reset_from_buffer(C.byref(st), None, 4, 0, 1, 3, 9, None, None, None, None, None) == L.MBPO_EINVAL
     assert L.lib.mbpo_prng_randint(None, 4, 2, 0, 0, 10, None, None) == L.MBPO_EINVAL
+    assert L.lib.mbpo_running_statistics_workspace_bytes(3) == 148 * 4 * 2 * 3 * 8
+    assert L.lib.mbpo_running_statistics_workspace_bytes(1000) == 0
+    assert L.lib.mbpo_running_statistics_accumulate(None, 4, 3, None, None, 0, None, None) == L.MBPO_EINVAL
+    assert L.lib.mbpo_running_statistics_accumulate(0x1000, 4, 3, 0x1000, 0x1000, 8, 0x1000, None) == L.MBPO_EWORKSPACE
+    assert L.lib.mbpo_running_statistics_finalize(None, 3, None, None, None, 1e-6, 1e6, None, None, None, None, None) == L.MBPO_EINVAL
     assert L.lib.mbpo_eval_metrics(None, None, None, None, 1, 4, 4, 4, 1, None, None, None, None) == L.MBPO_EINVAL
     with pytest.raises(mb.MbpoError):
         L.check(L.MBPO_EINVAL)

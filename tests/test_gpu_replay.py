@@ -282,3 +282,109 @@ def test_evaluator_runs_one_episode_per_env(mb, cuda_device):
     assert metrics["training/sps"] == 1.0 and metrics["eval/sps"] > 0 and metrics["eval/walltime"] > 0
     m2 = ev.run_evaluation(params, {}, aggregate_episodes=False)       # draws its own key
     assert m2["eval/episode_reward"].shape == (E,)
+
+
+@pytest.mark.parametrize("X", [3, 1, 17])
+def test_running_statistics_update_and_normalize(mb, cuda_device, X):
+    """running_statistics.update / normalize (sac.py:298-301) against the oracle's restatement of the update as
+    written (float64 sums); tolerance rel 1e-5 (XLA's reduction order is unspecified).  The kernel is deterministic:
+    the same batch gives the same bits."""
+    from mbpo_b200 import running_statistics as rs
+    dev = cuda_device
+    rng = np.random.default_rng(X)
+    st, ost = rs.init_state(X, dev), obr.running_statistics_init(X)
+    for shape in ((1,), (7,), (20, 32), (3, 1000, 5)):
+        batch = (rng.standard_normal(shape + (X,)) * rng.uniform(0.1, 8, X) + rng.uniform(-2, 2, X)).astype(np.float32)
+        new = rs.update(st, _dev(batch, dev))
+        again = rs.update(st, _dev(batch, dev))
+        ost = obr.running_statistics_update(ost, batch, accumulate=np.float64)
+        for k in ("count", "mean", "summed_variance", "std"):
+            np.testing.assert_allclose(getattr(new, k).cpu().numpy(), ost[k], rtol=1e-5, atol=1e-6)
+            assert torch.equal(getattr(new, k), getattr(again, k))
+        st = new
+    batch = rng.standard_normal((100, X)).astype(np.float32)
+    got = rs.normalize(_dev(batch, dev), st).cpu().numpy()
+    np.testing.assert_allclose(got, (batch - ost["mean"]) / ost["std"], rtol=1e-5, atol=1e-6)
+    got = rs.normalize(_dev(batch, dev), st, max_abs_value=0.5).cpu().numpy()
+    assert np.abs(got).max() <= 0.5
+
+
+def test_running_statistics_at_full_size_and_sharded(mb, cuda_device):
+    """65,536 envs x 200 observations: the update equals float64 mean / std of the rows (size-independent property),
+    and shard sums added together (the all-reduce of the multi-GPU path) give the unsharded statistics."""
+    from mbpo_b200 import _lib as L, running_statistics as rs
+    dev = cuda_device
+    gen = torch.Generator(device=dev).manual_seed(0)
+    obs = torch.randn((200, 65536, 3), generator=gen, device=dev) * torch.tensor([1.0, 0.5, 8.0], device=dev) + 0.25
+    st = rs.update(rs.init_state(3, dev), obs)
+    flat = obs.reshape(-1, 3).double()
+    np.testing.assert_allclose(st.mean.cpu().numpy(), flat.mean(0).cpu().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(st.std.cpu().numpy(), flat.std(0, unbiased=False).cpu().numpy(), rtol=1e-5)
+    assert float(st.count) == 200 * 65536
+    # two "ranks": accumulate each half, add the sums (what all_reduce_sums does), finalize once
+    st0 = rs.init_state(3, dev)
+    ws_bytes = L.lib.mbpo_running_statistics_workspace_bytes(3)
+    ws = torch.empty(ws_bytes // 8, dtype=torch.float64, device=dev)
+    total = torch.zeros(7, dtype=torch.float64, device=dev)
+    for part in (obs[:, :30000].contiguous(), obs[:, 30000:].contiguous()):
+        sums = torch.empty(7, dtype=torch.float64, device=dev)
+        L.check(L.lib.mbpo_running_statistics_accumulate(L.ptr(part), part.numel() // 3, 3, L.ptr(st0.mean), L.ptr(ws),
+                                                         ws_bytes, L.ptr(sums), L.stream_ptr(dev)))
+        total += sums
+    out = [torch.empty(1, device=dev)] + [torch.empty(3, device=dev) for _ in range(3)]
+    L.check(L.lib.mbpo_running_statistics_finalize(L.ptr(total), 3, L.ptr(st0.count.reshape(1)), L.ptr(st0.mean),
+                                                   L.ptr(st0.summed_variance), 1e-6, 1e6, *[L.ptr(o) for o in out],
+                                                   L.stream_ptr(dev)))
+    assert float(out[0]) == float(st.count)
+    np.testing.assert_allclose(out[1].cpu().numpy(), st.mean.cpu().numpy(), rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(out[3].cpu().numpy(), st.std.cpu().numpy(), rtol=1e-6)
+
+
+def test_get_experience_in_full(mb, cuda_device):
+    """sac.py:283-304: actor steps -> running_statistics.update(transitions.observation) -> replay_buffer.insert, twice
+    (the second collection runs the policy on observations normalised with the first one's statistics)."""
+    from mbpo_b200 import acting, envs, running_statistics as rs
+    from mbpo_b200.replay_buffers import UniformSamplingQueue
+    from mbpo_b200.systems import BraxWrapper, PendulumSystem
+    from mbpo_b200.utils.optimizer_utils import Transition
+    dev = cuda_device
+    system = PendulumSystem()
+    tq = UniformSamplingQueue(10, _true_dummy(mb, dev), 1)
+    first = system.reset(device=dev)
+    tst = tq.insert(tq.init(_dev(ojr.PRNGKey(0), dev)),
+                    Transition(first.x_next[None], torch.zeros((1, 1), device=dev), first.reward[None],
+                               torch.full((1,), 0.99, device=dev), first.x_next[None]))
+    E, T, L = 256, 20, 200
+    env = envs.wrap(BraxWrapper(system, system.init_params(_dev(ojr.PRNGKey(1), dev)), tst, tq), L, 1)
+    pol = orc.make_policy_params(seed=7)
+    params = acting.PolicyParams([_dev(w, dev) for w in pol.weights], [_dev(b, dev) for b in pol.biases])
+    q = UniformSamplingQueue(2 ** 14, _sac_dummy(mb, dev), 64)
+    col = acting.ExperienceCollector(env, acting.make_normalized_inference_fn(), q, T)
+    norm, buf = rs.init_state(3, dev), q.init(_dev(ojr.PRNGKey(2), dev))
+    state = env.reset(mb.random.split(_dev(ojr.PRNGKey(3), dev), E))
+    key = _dev(ojr.PRNGKey(4), dev)
+    onorm = obr.running_statistics_init(3)
+    okey = ojr.PRNGKey(4)
+    rows = []
+    for it in range(2):
+        prev_norm, prev_state = norm, state
+        norm, state, buf, key = col.get_experience(norm, params, state, buf, key)
+        live = buf.data[buf.insert_position - T * E:buf.insert_position].cpu().numpy()
+        obs = live[:, :3].reshape(T, E, 3)
+        # the policy saw (obs - mean) / std of the statistics before this collection (the GPU's own: after 20 steps
+        # from the hanging state std(cos) is ~1e-3, so a 1e-7 difference in the mean is 1e-4 after normalisation;
+        # the statistics themselves are compared below)
+        m, sd = prev_norm.mean.cpu().numpy(), prev_norm.std.cpu().numpy()
+        want, okey = orc.actor_rollout(pol, prev_state.obs.cpu().numpy(), okey, T, L, key_convention="sac",
+                                       teacher_obs=((obs - m) / sd).astype(np.float32))
+        np.testing.assert_allclose(live[:, 3].reshape(T, E), want["action"][..., 0], rtol=5e-5, atol=5e-6)
+        assert np.array_equal(key.cpu().numpy(), okey)
+        onorm = obr.running_statistics_update(onorm, obs, accumulate=np.float64)
+        for k in ("count", "mean", "std"):
+            np.testing.assert_allclose(getattr(norm, k).cpu().numpy(), onorm[k], rtol=1e-5, atol=1e-6)
+        rows.append(live)
+    assert buf.insert_position == 2 * T * E and float(norm.count) == 2 * T * E
+    assert np.array_equal(buf.data[:T * E].cpu().numpy(), rows[0])
+    # observation[t+1] = next_observation[t] inside a collection, and the second starts where the first ended
+    r0, r1 = rows[0].reshape(T, E, 10), rows[1].reshape(T, E, 10)
+    assert np.array_equal(r0[1:, :, :3], r0[:-1, :, 6:9]) and np.array_equal(r1[0, :, :3], r0[-1, :, 6:9])

@@ -113,3 +113,26 @@ def test_eval_metrics_fold_matches_a_per_env_statement():
             active = active and not d
     got_r, got_s, active = br.eval_metrics(reward, discount, steps0, done0, rep)
     assert np.array_equal(got_r, want_r) and np.array_equal(got_s, want_s) and np.all(active == 0)
+
+
+def test_running_statistics_one_pass_form_equals_the_reference_form():
+    """The kernel's single-pass algebra (sum d, sum d*d in float64, one exchange) against the update as brax writes it
+    (two passes); also against plain mean / variance of everything seen."""
+    rng = np.random.default_rng(0)
+    st_a = br.running_statistics_init(3)
+    st_b = br.running_statistics_init(3)
+    seen = np.zeros((0, 3), np.float32)
+    for n in (1, 7, 1000, 50_000):
+        batch = (rng.standard_normal((n, 3)) * [1.0, 0.1, 8.0] + [0.5, -2.0, 0.0]).astype(np.float32)
+        st_a = br.running_statistics_update(st_a, batch, accumulate=np.float64)
+        st_b = br.running_statistics_finalize(st_b, br.running_statistics_sums(batch, st_b["mean"]), n)
+        seen = np.concatenate([seen, batch])
+        for k in ("count", "mean", "summed_variance", "std"):
+            np.testing.assert_allclose(st_b[k], st_a[k], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(st_b["mean"], seen.mean(0, dtype=np.float64), rtol=1e-5, atol=1e-6)
+        if len(seen) > 1:
+            np.testing.assert_allclose(st_b["std"], seen.std(0, dtype=np.float64), rtol=1e-5, atol=1e-6)
+    f32 = br.running_statistics_update(br.running_statistics_init(3), seen)        # float32 sums, as XLA would
+    np.testing.assert_allclose(f32["mean"], st_b["mean"], rtol=1e-4, atol=1e-5)
+    one = br.running_statistics_update(br.running_statistics_init(2), np.zeros((4, 2), np.float32))
+    assert np.all(one["std"] == np.float32(1e-6))                                   # std_min_value clip

@@ -70,3 +70,42 @@ def test_world_size_2_gloo_gather(tmp_path, total):
     a0 = torch.load(os.path.join(str(tmp_path), "a0.pt"))
     a1 = torch.load(os.path.join(str(tmp_path), "a1.pt"))
     assert torch.equal(a0, a1) and a0.shape == (total, 1)
+
+
+def _stats_worker(rank, world, port, out_dir):
+    """The one exchange step of the data-collection path: running_statistics' psum as an all-reduce of the float64
+    sums.  The per-rank sums come from the oracle here (no GPU); the product's all_reduce_sums carries them."""
+    import sys
+    import numpy as np
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "model-based-policy-optimizers_b200"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mbpo_b200.parallel import shard_bounds
+    from mbpo_b200.running_statistics import all_reduce_sums
+    from oracle import brax_replay as obr
+    rng = np.random.default_rng(0)
+    obs = (rng.standard_normal((20, 101, 3)) * [1.0, 0.3, 8.0] + [0.5, -1.0, 0.0]).astype(np.float32)   # [T, E, X]
+    state = obr.running_statistics_update(obr.running_statistics_init(3), obs[:2])      # a non-trivial old mean
+    lo, hi = shard_bounds(obs.shape[1], rank, world)                                    # unequal env shards: 51 / 50
+    mine = obs[:, lo:hi]
+    sums = np.concatenate([obr.running_statistics_sums(mine, state["mean"]), [mine.shape[0] * mine.shape[1]]])
+    total = all_reduce_sums(torch.from_numpy(sums)).numpy()
+    got = obr.running_statistics_finalize(state, total[:6], total[6])
+    want = obr.running_statistics_update(state, obs, accumulate=np.float64)
+    assert total[6] == 20 * 101
+    for k in ("count", "mean", "summed_variance", "std"):
+        np.testing.assert_allclose(got[k], want[k], rtol=1e-5, atol=1e-6)
+    torch.save(torch.from_numpy(np.concatenate([got["mean"], got["std"]])), os.path.join(out_dir, "s%d.pt" % rank))
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_running_statistics(tmp_path):
+    port = _free_port()
+    mp.spawn(_stats_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    s0 = torch.load(os.path.join(str(tmp_path), "s0.pt"))
+    s1 = torch.load(os.path.join(str(tmp_path), "s1.pt"))
+    assert torch.equal(s0, s1)                      # every rank ends with the same statistics
