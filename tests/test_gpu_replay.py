@@ -388,3 +388,96 @@ def test_get_experience_in_full(mb, cuda_device):
     # observation[t+1] = next_observation[t] inside a collection, and the second starts where the first ended
     r0, r1 = rows[0].reshape(T, E, 10), rows[1].reshape(T, E, 10)
     assert np.array_equal(r0[1:, :, :3], r0[:-1, :, 6:9]) and np.array_equal(r1[0, :, :3], r0[-1, :, 6:9])
+
+
+def test_guard_zones_around_every_output(mb, cuda_device):
+    """No out-of-bounds writes (compute-sanitizer is not available on the pool): every output buffer of the replay /
+    reset / eval / statistics entry points sits between sentinel-filled guard zones, for ragged sizes and for ring
+    positions that make a tile cross the ring's end and start on every alignment modulo 16 bytes."""
+    L = mb._lib
+    dev = cuda_device
+    G, SENT = 64, -12345.0
+
+    def guarded(n, dtype=torch.float32):
+        full = torch.full((n + 2 * G,), SENT, dtype=dtype, device=dev)
+        return full, full[G:G + n]
+
+    def intact(full, n):
+        ref = torch.tensor(SENT, device=dev).to(full.dtype)
+        return bool(torch.all(full[:G] == ref)) and bool(torch.all(full[G + n:] == ref))
+
+    rng = np.random.default_rng(0)
+    for R, D, widths in ((101, 10, (3, 1, 1, 1, 3, 1)), (64, 9, (3, 1, 1, 1, 3)), (37, 5, (5,)), (1000, 23, (20, 3))):
+        full, ring = guarded(R * D)
+        ring.zero_()
+        st = L.ReplayStateC(data=ring.data_ptr(), capacity=R, row_width=D)
+        logical = np.zeros((R, D), np.float32)
+        oq = obr.UniformSamplingQueue(R, D, 1)
+        ost = oq.init(ojr.PRNGKey(0))
+        for n in (1, 3, R // 2, R - 1, 7, R, 2, 33 % R + 1):
+            rows = rng.standard_normal((n, D)).astype(np.float32)
+            fields = L.ReplayFieldsC(num_fields=len(widths))
+            keep, col = [], 0
+            for f, w in enumerate(widths):
+                t = _dev(rows[:, col:col + w].copy(), dev)
+                keep.append(t)
+                fields.width[f], fields.ptr[f] = w, t.data_ptr()
+                col += w
+            L.check(L.lib.mbpo_replay_insert(L.C.byref(st), L.C.byref(fields), n, L.stream_ptr(dev)))
+            ost = oq.insert(ost, rows)
+            assert intact(full, R * D)
+            out_full, out = guarded(R * D)
+            L.check(L.lib.mbpo_replay_read(L.C.byref(st), 0, R, out.data_ptr(), L.stream_ptr(dev)))
+            assert intact(out_full, R * D)
+            live = ost.insert_position
+            assert np.array_equal(out.cpu().numpy().reshape(R, D)[:live], ost.data[:live])
+            assert (st.insert_position, st.sample_position) == (ost.insert_position, ost.sample_position)
+        # sample / reset outputs
+        key = _dev(ojr.PRNGKey(1), dev)
+        for batch in (1, 5, 129):
+            kf, k = guarded(2)
+            idf, idx = guarded(batch)
+            bf, b = guarded(batch * D)
+            L.check(L.lib.mbpo_replay_sample(L.C.byref(st), key.data_ptr(), 0, batch, k.view(torch.uint32).data_ptr(),
+                                             idx.view(torch.int32).data_ptr(), b.data_ptr(), L.stream_ptr(dev)))
+            assert intact(kf, 2) and intact(idf, batch) and intact(bf, batch * D)
+        for E in (1, 31, 130):
+            rngs = _dev(ojr.split(ojr.PRNGKey(2), E), dev)
+            of, o = guarded(E * 3)
+            rf, r = guarded(E)
+            kf, k = guarded(E * 2)
+            L.check(L.lib.mbpo_env_reset_from_buffer(L.C.byref(st), rngs.data_ptr(), E, 0, 1, min(3, D), D - 1,
+                                                     o.data_ptr(), r.data_ptr(), k.view(torch.uint32).data_ptr(), None,
+                                                     L.stream_ptr(dev)))
+            assert intact(of, E * 3) and intact(rf, E) and intact(kf, E * 2)
+    # eval metrics and running statistics
+    for E, T in ((1, 1), (33, 7), (257, 3)):
+        r, d = torch.randn((T, E), device=dev), torch.ones((T, E), device=dev)
+        z = torch.zeros(E, device=dev)
+        outs = [guarded(E) for _ in range(3)]
+        for _, v in outs:
+            v.fill_(1.0)
+        L.check(L.lib.mbpo_eval_metrics(r.data_ptr(), d.data_ptr(), z.data_ptr(), z.data_ptr(), 1, E, T, E, 1,
+                                        outs[0][1].data_ptr(), outs[1][1].data_ptr(), outs[2][1].data_ptr(),
+                                        L.stream_ptr(dev)))
+        assert all(intact(f, E) for f, _ in outs)
+    for X, n in ((1, 1), (3, 1000), (17, 33), (64, 5)):
+        batch = torch.randn((n, X), device=dev)
+        ws_bytes = L.lib.mbpo_running_statistics_workspace_bytes(X)
+        wf, ws = guarded(ws_bytes // 8, torch.float64)
+        sf, sums = guarded(2 * X + 1, torch.float64)
+        mean = torch.zeros(X, device=dev)
+        L.check(L.lib.mbpo_running_statistics_accumulate(batch.data_ptr(), n, X, mean.data_ptr(), ws.data_ptr(), ws_bytes,
+                                                         sums.data_ptr(), L.stream_ptr(dev)))
+        assert intact(wf, ws_bytes // 8) and intact(sf, 2 * X + 1)
+        assert float(sums[2 * X]) == n
+        np.testing.assert_allclose(sums[:X].cpu().numpy(), batch.double().sum(0).cpu().numpy(), rtol=1e-12, atol=1e-9)
+        outs = [guarded(1)] + [guarded(X) for _ in range(3)]
+        cnt, sv = torch.zeros(1, device=dev), torch.zeros(X, device=dev)
+        L.check(L.lib.mbpo_running_statistics_finalize(sums.data_ptr(), X, cnt.data_ptr(), mean.data_ptr(), sv.data_ptr(),
+                                                       1e-6, 1e6, *[v.data_ptr() for _, v in outs], L.stream_ptr(dev)))
+        assert intact(outs[0][0], 1) and all(intact(f, X) for f, _ in outs[1:])
+        nf, nout = guarded(n * X)
+        L.check(L.lib.mbpo_running_statistics_normalize(batch.data_ptr(), n, X, outs[1][1].data_ptr(), outs[3][1].data_ptr(),
+                                                        0.0, nout.data_ptr(), L.stream_ptr(dev)))
+        assert intact(nf, n * X)
