@@ -423,6 +423,26 @@ int mbpo_running_statistics_finalize(const double* sums /*[2X+1]*/, int X,
 int mbpo_running_statistics_normalize(const float* batch /*[n_rows, X]*/, long long n_rows, int X, const float* mean,
                                       const float* std, float max_abs_value, float* out, void* stream);
 
+/* BPTT's own Normalizer (mbpo/optimizers/policy_optimizers/bptt_optimizer.py:31-75; update_normalizers :297-303, the
+ * state normaliser's mean / std are what the BPTT actor kernel reads): update(x, state) with n = x.shape[0]:
+ *   new_mean = (mean * size + sum(x)) / total;  s_n = std^2 * size + sum((x - new_mean)^2) + size * (mean - new_mean)^2;
+ *   std = max(sqrt(s_n / total), 1e-8);  size = total.
+ * Same split as the running statistics: sums[2X+1] from mbpo_running_statistics_accumulate (d = x - mean), all-reduced
+ * by the caller when the batch is sharded, then this call; with delta = sum d / total,
+ * sum((x - new_mean)^2) = sum d*d - 2 delta sum d + n delta^2.  size is a float64 scalar on the device. */
+int mbpo_normalizer_finalize(const double* sums /*[2X+1]*/, int X, const double* size_in /*[1]*/,
+                             const float* mean_in /*[X]*/, const float* std_in /*[X]*/, float eps,
+                             double* size_out /*[1]*/, float* mean_out /*[X]*/, float* std_out /*[X]*/, void* stream);
+
+/* Normalizer.inverse (bptt_optimizer.py:73-75): out = x * std + mean. */
+int mbpo_normalizer_inverse(const float* batch /*[n_rows, X]*/, long long n_rows, int X, const float* mean,
+                            const float* std, float* out, void* stream);
+
+/* jnp.take(buffer_state.data, idx, axis=0, mode='wrap') (bptt_optimizer.py:447-449): rows_out[i] = data[idx[i] mod
+ * capacity] in brax's logical row order. */
+int mbpo_replay_take(const MbpoReplayState* state_host, const int32_t* idx /*[n]*/, long long n,
+                     float* rows_out /*[n, D]*/, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -328,6 +328,47 @@ __global__ void running_stats_normalize_kernel(const float* __restrict__ batch, 
   out[i] = v;
 }
 
+__global__ void normalizer_finalize_kernel(const double* __restrict__ sums, int X, const double* __restrict__ size_in,
+                                          const float* __restrict__ mean_in, const float* __restrict__ std_in, float eps,
+                                          double* __restrict__ size_out, float* __restrict__ mean_out,
+                                          float* __restrict__ std_out) {
+  const int x = threadIdx.x;
+  if (x >= X) return;
+  const double size = size_in[0], n = sums[2 * X], total = size + n;
+  const double delta = sums[x] / total;                                   // new_mean - mean
+  const double sq = sums[X + x] - 2.0 * delta * sums[x] + n * delta * delta;   // sum((x - new_mean)^2)
+  const double sd = static_cast<double>(std_in[x]);
+  const double s_n = sd * sd * size + sq + size * delta * delta;
+  const float mean = static_cast<float>(static_cast<double>(mean_in[x]) + delta);
+  const float new_std = sqrtf(static_cast<float>(s_n / total));
+  __syncthreads();
+  if (x == 0) size_out[0] = total;
+  mean_out[x] = mean;
+  std_out[x] = fmaxf(new_std, eps);
+}
+
+__global__ void normalizer_inverse_kernel(const float* __restrict__ batch, long long total_words, int X,
+                                         const float* __restrict__ mean, const float* __restrict__ std,
+                                         float* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total_words) return;
+  const int x = static_cast<int>(i % X);
+  out[i] = __fadd_rn(__fmul_rn(batch[i], std[x]), mean[x]);
+}
+
+__global__ void replay_take_kernel(const float* __restrict__ data, long long capacity, int D, long long head,
+                                   const int32_t* __restrict__ idx, long long total_words, float* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total_words) return;
+  const long long r = i / D;
+  const int c = static_cast<int>(i - r * D);
+  long long l = static_cast<long long>(idx[r]) % capacity;  // mode='wrap'
+  if (l < 0) l += capacity;
+  long long p = head + l;
+  if (p >= capacity) p -= capacity;
+  out[i] = data[p * D + c];
+}
+
 int check_state(const MbpoReplayState* s, const char* who) {
   MBPO_REQUIRE(s != nullptr, "%s: state is null", who);
   MBPO_REQUIRE(s->data != nullptr, "%s: data is null", who);
@@ -551,6 +592,46 @@ int mbpo_running_statistics_normalize(const float* batch, long long n_rows, int 
   running_stats_normalize_kernel<<<static_cast<unsigned>(blocks), threads, 0, as_stream(stream)>>>(
       batch, total, X, mean, std, max_abs_value, out);
   return check_launch("running_stats_normalize_kernel");
+}
+
+int mbpo_normalizer_finalize(const double* sums, int X, const double* size_in, const float* mean_in,
+                             const float* std_in, float eps, double* size_out, float* mean_out, float* std_out,
+                             void* stream) {
+  MBPO_REQUIRE(X >= 1 && X <= RS_MAX_X, "normalizer: X %d outside [1, %d]", X, RS_MAX_X);
+  MBPO_REQUIRE(sums && size_in && mean_in && std_in && size_out && mean_out && std_out, "normalizer: null pointer");
+  normalizer_finalize_kernel<<<1, RS_MAX_X, 0, as_stream(stream)>>>(sums, X, size_in, mean_in, std_in, eps, size_out,
+                                                                    mean_out, std_out);
+  return check_launch("normalizer_finalize_kernel");
+}
+
+int mbpo_normalizer_inverse(const float* batch, long long n_rows, int X, const float* mean, const float* std,
+                            float* out, void* stream) {
+  MBPO_REQUIRE(X >= 1 && X <= RS_MAX_X, "normalizer: X %d outside [1, %d]", X, RS_MAX_X);
+  MBPO_REQUIRE(n_rows >= 0, "normalizer: n_rows < 0");
+  if (n_rows == 0) return MBPO_OK;
+  MBPO_REQUIRE(batch && mean && std && out, "normalizer: null pointer");
+  const long long total = n_rows * X;
+  const int threads = 256;
+  const long long blocks = (total + threads - 1) / threads;
+  MBPO_REQUIRE(blocks < (1LL << 31), "normalizer: too many rows for one launch");
+  normalizer_inverse_kernel<<<static_cast<unsigned>(blocks), threads, 0, as_stream(stream)>>>(batch, total, X, mean, std,
+                                                                                            out);
+  return check_launch("normalizer_inverse_kernel");
+}
+
+int mbpo_replay_take(const MbpoReplayState* s, const int32_t* idx, long long n, float* rows_out, void* stream) {
+  int rc = check_state(s, "replay_take");
+  if (rc != MBPO_OK) return rc;
+  MBPO_REQUIRE(n >= 0, "replay_take: n < 0");
+  if (n == 0) return MBPO_OK;
+  MBPO_REQUIRE(idx && rows_out, "replay_take: null pointer");
+  const long long total = n * s->row_width;
+  const int threads = 256;
+  const long long blocks = (total + threads - 1) / threads;
+  MBPO_REQUIRE(blocks < (1LL << 31), "replay_take: too many rows for one launch");
+  replay_take_kernel<<<static_cast<unsigned>(blocks), threads, 0, as_stream(stream)>>>(
+      s->data, s->capacity, s->row_width, s->head, idx, total, rows_out);
+  return check_launch("replay_take_kernel");
 }
 
 }  // extern "C"

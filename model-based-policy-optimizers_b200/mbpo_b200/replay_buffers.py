@@ -152,6 +152,16 @@ class UniformSamplingQueue:
                                                    _lib.stream_ptr(dev)))
         return buffer_state.replace(key=key_out), self.unflatten(rows), idx
 
+    def take(self, buffer_state: ReplayBufferState, idx: torch.Tensor) -> Any:
+        """unflatten(jnp.take(buffer_state.data, idx, axis=0, mode='wrap')) (bptt_optimizer.py:447-450)."""
+        idx = idx.to(torch.int32).contiguous().reshape(-1)
+        rows = torch.empty((idx.numel(), self._row_width), dtype=torch.float32, device=buffer_state.ring.device)
+        st = buffer_state._c()
+        with _lib.cuda_guard(buffer_state.ring):
+            _lib.check(_lib.lib.mbpo_replay_take(_lib.C.byref(st), _lib.ptr(idx), idx.numel(), _lib.ptr(rows),
+                                                 _lib.stream_ptr(rows.device)))
+        return self.unflatten(rows)
+
     def unflatten(self, rows: torch.Tensor) -> Any:
         """[n, D] rows -> the dummy sample's structure (column views of ``rows``)."""
         leaves, col = [], 0

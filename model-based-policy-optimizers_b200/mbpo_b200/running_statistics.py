@@ -83,3 +83,72 @@ def normalize(batch: torch.Tensor, mean_std: RunningStatisticsState, max_abs_val
             _lib.ptr(b), b.numel() // X, X, _lib.ptr(mean_std.mean.contiguous()), _lib.ptr(mean_std.std.contiguous()),
             float(max_abs_value) if max_abs_value is not None else 0.0, _lib.ptr(out), _lib.stream_ptr(b.device)))
     return out
+
+
+# ---- BPTT's own Normalizer (mbpo/optimizers/policy_optimizers/bptt_optimizer.py:31-75) -------------------------------
+EPS = 1e-8
+
+
+@dataclass
+class NormalizerState(_Replaceable):
+    """bptt_optimizer.py:31-35.  ``size`` is a float64 scalar on the device (the reference's traced int)."""
+    mean: torch.Tensor = None
+    std: torch.Tensor = None
+    size: torch.Tensor = None
+
+
+class Normalizer:
+    """bptt_optimizer.py:37-75: ``update(x, state)`` / ``normalize(x, state)`` / ``inverse(x, state)``; the state
+    normaliser's mean / std are what acting.BpttActorPolicy reads.  ``group`` (additive): all-reduce the sums when the
+    batch is sharded over ranks."""
+
+    def __init__(self, input_shape, device=None):
+        self.input_shape = tuple(input_shape)
+        self._device = device
+
+    def initialize_normalizer_state(self) -> NormalizerState:
+        dev = _lib.require_cuda(self._device)
+        n = self.input_shape[0]
+        return NormalizerState(mean=torch.zeros(n, dtype=torch.float32, device=dev),
+                               std=torch.ones(n, dtype=torch.float32, device=dev),
+                               size=torch.zeros((), dtype=torch.float64, device=dev))
+
+    @staticmethod
+    def update(x: torch.Tensor, state: NormalizerState, group=None) -> NormalizerState:
+        X = state.mean.shape[-1]
+        b = x.to(torch.float32).contiguous()
+        n_rows = b.numel() // X
+        dev = b.device
+        ws_bytes = _lib.lib.mbpo_running_statistics_workspace_bytes(X)
+        if ws_bytes == 0:
+            raise _lib.MbpoUnsupported(_lib.MBPO_EUNSUPPORTED, "Normalizer: input size %d has no kernel" % X)
+        workspace = torch.empty(ws_bytes // 8, dtype=torch.float64, device=dev)
+        sums = torch.empty(2 * X + 1, dtype=torch.float64, device=dev)
+        mean_in, std_in = state.mean.contiguous(), state.std.contiguous()
+        size_in = state.size.to(torch.float64).reshape(1).contiguous()
+        size, mean, std = torch.empty_like(size_in), torch.empty_like(mean_in), torch.empty_like(std_in)
+        with _lib.cuda_guard(b):
+            _lib.check(_lib.lib.mbpo_running_statistics_accumulate(_lib.ptr(b), n_rows, X, _lib.ptr(mean_in),
+                                                                   _lib.ptr(workspace), ws_bytes, _lib.ptr(sums),
+                                                                   _lib.stream_ptr(dev)))
+            if group is not None:
+                all_reduce_sums(sums, group)
+            _lib.check(_lib.lib.mbpo_normalizer_finalize(_lib.ptr(sums), X, _lib.ptr(size_in), _lib.ptr(mean_in),
+                                                         _lib.ptr(std_in), EPS, _lib.ptr(size), _lib.ptr(mean),
+                                                         _lib.ptr(std), _lib.stream_ptr(dev)))
+        return NormalizerState(mean=mean, std=std, size=size.reshape(()))
+
+    @staticmethod
+    def normalize(x: torch.Tensor, state: NormalizerState) -> torch.Tensor:
+        return normalize(x, RunningStatisticsState(mean=state.mean, std=state.std))
+
+    @staticmethod
+    def inverse(x: torch.Tensor, state: NormalizerState) -> torch.Tensor:
+        X = state.mean.shape[-1]
+        b = x.to(torch.float32).contiguous()
+        out = torch.empty_like(b)
+        with _lib.cuda_guard(b):
+            _lib.check(_lib.lib.mbpo_normalizer_inverse(_lib.ptr(b), b.numel() // X, X, _lib.ptr(state.mean.contiguous()),
+                                                        _lib.ptr(state.std.contiguous()), _lib.ptr(out),
+                                                        _lib.stream_ptr(b.device)))
+        return out

@@ -152,3 +152,23 @@ def running_statistics_finalize(state, sums, step_increment, std_min_value=1e-6,
     sv = (state["summed_variance"] + var_update.astype(F)).astype(F)
     std = np.clip(np.sqrt(np.maximum(sv, F(0)) / count).astype(F), F(std_min_value), F(std_max_value))
     return dict(count=count, mean=mean, summed_variance=sv, std=std)
+
+
+# ---- BPTT's own Normalizer (reference code: mbpo/optimizers/policy_optimizers/bptt_optimizer.py:31-75) ---------------
+def normalizer_init(size: int):
+    return dict(mean=np.zeros(size, np.float32), std=np.ones(size, np.float32), size=0)
+
+
+def normalizer_update(x, state, accumulate=np.float64):
+    """Normalizer.update as written (:51-66).  ``accumulate``: dtype of the two sums."""
+    F = np.float32
+    X = state["mean"].shape[0]
+    x = np.asarray(x, F).reshape(-1, X)
+    new_size = x.shape[0]
+    total = new_size + state["size"]
+    new_mean = ((state["mean"] * F(state["size"]) + x.sum(0, dtype=accumulate).astype(F)) / F(total)).astype(F)
+    new_s_n = (np.square(state["std"]) * F(state["size"])
+               + np.square((x - new_mean).astype(F)).sum(0, dtype=accumulate).astype(F)
+               + F(state["size"]) * np.square(state["mean"] - new_mean)).astype(F)
+    new_std = np.sqrt(new_s_n / F(total)).astype(F)
+    return dict(mean=new_mean, std=np.maximum(new_std, F(1e-8)), size=total)

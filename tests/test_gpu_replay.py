@@ -481,3 +481,44 @@ def test_guard_zones_around_every_output(mb, cuda_device):
         L.check(L.lib.mbpo_running_statistics_normalize(batch.data_ptr(), n, X, outs[1][1].data_ptr(), outs[3][1].data_ptr(),
                                                         0.0, nout.data_ptr(), L.stream_ptr(dev)))
         assert intact(nf, n * X)
+
+
+def test_bptt_normalizer_and_take(mb, cuda_device):
+    """bptt_optimizer.py:31-75 Normalizer (update / normalize / inverse), :297-303 update_normalizers on state and
+    reward, and :447-450 randint + take(mode='wrap') of evaluation rows from the true buffer."""
+    from mbpo_b200.replay_buffers import UniformSamplingQueue
+    from mbpo_b200.running_statistics import Normalizer
+    from mbpo_b200.utils.optimizer_utils import Transition
+    dev = cuda_device
+    rng = np.random.default_rng(0)
+    for X in (3, 1):
+        nz = Normalizer((X,), dev)
+        st, ost = nz.initialize_normalizer_state(), obr.normalizer_init(X)
+        for n in (1, 10, 2000, 65536):
+            x = (rng.standard_normal((n, X)) * rng.uniform(0.1, 8, X) + rng.uniform(-2, 2, X)).astype(np.float32)
+            st, ost = nz.update(_dev(x, dev), st), obr.normalizer_update(x, ost)
+            assert float(st.size) == ost["size"]
+            np.testing.assert_allclose(st.mean.cpu().numpy(), ost["mean"], rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(st.std.cpu().numpy(), ost["std"], rtol=1e-5, atol=1e-6)
+        x = rng.standard_normal((50, X)).astype(np.float32)
+        z = nz.normalize(_dev(x, dev), st)
+        np.testing.assert_allclose(z.cpu().numpy(), (x - ost["mean"]) / ost["std"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(nz.inverse(z, st).cpu().numpy(), x, rtol=1e-5, atol=1e-5)
+    const = nz.update(torch.full((8, 1), 2.5, device=dev), nz.initialize_normalizer_state())
+    assert float(const.std) == np.float32(1e-8) and float(const.mean) == 2.5            # std floor EPS
+    # evaluation rows: randint over the live range, take with wrap
+    q = UniformSamplingQueue(50, _true_dummy(mb, dev), 10)
+    g = lambda *s: torch.from_numpy(rng.standard_normal(s).astype(np.float32)).to(dev)
+    st = q.init(_dev(ojr.PRNGKey(0), dev))
+    for n in (30, 30):                                                                   # head != 0
+        st = q.insert(st, Transition(g(n, 3), g(n, 1), g(n), g(n), g(n, 3)))
+    eval_rng = ojr.PRNGKey(5)
+    idx = mb.random.randint(_dev(eval_rng, dev), 100, st.sample_position, st.insert_position)
+    assert np.array_equal(idx.cpu().numpy(), ojr.randint(eval_rng, 100, 0, 50))
+    rows = q.take(st, idx)
+    data = st.data.cpu().numpy()
+    assert np.array_equal(rows.observation.cpu().numpy(), data[idx.cpu().numpy(), :3])
+    wrapped = q.take(st, idx + 50 * 3)                                                    # mode='wrap'
+    assert torch.equal(wrapped.observation, rows.observation)
+    neg = q.take(st, idx - 50)
+    assert torch.equal(neg.reward, rows.reward)

@@ -136,3 +136,19 @@ def test_running_statistics_one_pass_form_equals_the_reference_form():
     np.testing.assert_allclose(f32["mean"], st_b["mean"], rtol=1e-4, atol=1e-5)
     one = br.running_statistics_update(br.running_statistics_init(2), np.zeros((4, 2), np.float32))
     assert np.all(one["std"] == np.float32(1e-6))                                   # std_min_value clip
+
+
+def test_bptt_normalizer_matches_plain_mean_and_std():
+    """Normalizer.update (bptt_optimizer.py:51-66) is the parallel-variance combine: after any sequence of batches it
+    equals mean / std (ddof=0) of everything seen."""
+    rng = np.random.default_rng(0)
+    st = br.normalizer_init(3)
+    seen = np.zeros((0, 3), np.float32)
+    for n in (1, 5, 300, 20_000):
+        x = (rng.standard_normal((n, 3)) * [1.0, 0.1, 8.0] + [0.5, -2.0, 0.0]).astype(np.float32)
+        st = br.normalizer_update(x, st)
+        seen = np.concatenate([seen, x])
+        assert st["size"] == len(seen)
+        np.testing.assert_allclose(st["mean"], seen.mean(0, dtype=np.float64), rtol=2e-5, atol=1e-6)
+        if len(seen) > 1:
+            np.testing.assert_allclose(st["std"], seen.std(0, dtype=np.float64), rtol=2e-5, atol=1e-6)
