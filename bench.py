@@ -975,6 +975,149 @@ def run_actor(args):
         dist.destroy_process_group()
 
 
+def run_collect(args):
+    """SAC.get_experience in full (sac/sac.py:283-304) per step: 65,536 envs x 200 actor steps (policy in the loop,
+    one launch) -> running_statistics.update of the observation normaliser (the psum over ranks is an NCCL all-reduce
+    of 7 doubles) -> replay insert of the 13.1 M transitions into a queue of 2**24 rows.  Envs sharded over ranks; each
+    rank owns the queue of its envs (the reference's pmap keeps one replay buffer per device)."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    pol_w, pol_b = make_policy_numpy(seed=7)
+    T = 200
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import brax_replay as obr, jax_prng as jr, mbpo_oracle as orc          # CPU arm only
+        pol = orc.PolicyParams(pol_w, pol_b)
+        E, Ts, R = 4096, 4, 1 << 16                      # bounded sample of the same pipeline
+        x0 = random_states(ENV_E, 1)[:E]
+        q = obr.UniformSamplingQueue(R, 10, 1)
+        qs = q.insert(q.init(jr.PRNGKey(0)), np.zeros((R, 10), np.float32))
+        norm = obr.running_statistics_init(3)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            tr, _ = orc.actor_rollout(pol, (x0 - norm["mean"]) / norm["std"], jr.PRNGKey(0), Ts, ENV_EPISODE)
+            norm = obr.running_statistics_update(norm, tr["observation"])
+            n = Ts * E
+            qs = q.insert(qs, np.concatenate([tr["observation"].reshape(n, 3), tr["action"].reshape(n, 1),
+                                              tr["reward"].reshape(n, 1), tr["discount"].reshape(n, 1),
+                                              tr["next_observation"].reshape(n, 3), tr["truncation"].reshape(n, 1)], 1))
+        dt = (time.perf_counter() - t0) / args.steps
+        ncores, model = host_info()
+        v = E * Ts / dt
+        emit_json({"impl": "reference", "metric": "SAC get_experience env-steps/sec", "value": v, "unit": "env-steps/s",
+                   "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+                   "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                   "config": {"workload": "config3_collect_experience", "envs": ENV_E, "steps_per_call": T},
+                   "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": ncores, "kind": "port",
+                                    "sample": "%d envs x %d steps of 65536 x %d into a full queue of %d rows, NumPy "
+                                              "oracle (BLAS threads)" % (E, Ts, T, R), "host_cpu": model},
+                   "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}, GUARD)
+        return
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import mbpo_b200
+    from mbpo_b200 import acting, running_statistics as rs
+    from mbpo_b200.envs import wrap
+    from mbpo_b200.parallel import shard_bounds
+    from mbpo_b200.replay_buffers import UniformSamplingQueue
+    from mbpo_b200.systems import PendulumSystem
+    from mbpo_b200.utils.optimizer_utils import Transition
+    mbpo_b200.config.math_mode = args.math
+    lo, hi = shard_bounds(ENV_E, rank, world)
+    E = hi - lo
+    system = PendulumSystem()
+    env = wrap(system, system.reset(device=dev).system_params, episode_length=ENV_EPISODE)
+    w_host = [torch.from_numpy(w).pin_memory() for w in pol_w]
+    b_host = [torch.from_numpy(b).pin_memory() for b in pol_b]
+    params = acting.PolicyParams([w.to(dev) for w in w_host], [b.to(dev) for b in b_host])
+    z = lambda *sh: torch.zeros(sh, device=dev)
+    dummy = Transition(z(3), z(1), z(), z(), z(3), {"state_extras": {"truncation": z()}, "policy_extras": {}})
+    queue = UniformSamplingQueue(REPLAY_ROWS // world, dummy, 256)
+    col = acting.ExperienceCollector(env, acting.make_normalized_inference_fn(kernel=args.actor_kernel), queue, T,
+                                     pmap_axis_name="i" if world > 1 else None, env_offset=lo, total_envs=ENV_E)
+    state = env.reset(torch.from_numpy(random_states(ENV_E, 1)[lo:hi].copy()).to(dev))
+    norm, buf = rs.init_state(3, dev), queue.init(mbpo_b200.random.PRNGKey(1, dev))
+    key = mbpo_b200.random.PRNGKey(0, dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        norm, state, buf, key = col.get_experience(norm, params, state, buf, key)
+    steps = min(args.steps, 20)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        for k in range(steps):
+            starts[k].record()
+            norm, state, buf, key = col.get_experience(norm, params, state, buf, key)
+            ends[k].record()
+        barrier()
+    ms = sum(a.elapsed_time(b) for a, b in zip(starts, ends)) / steps
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    # end to end: the learner's new policy parameters arrive from pinned host memory before every collection, the
+    # normaliser statistics (what the learner logs / checkpoints) go back to the host after it
+    stats_host = torch.empty(7, dtype=torch.float32).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(steps):
+        params = acting.PolicyParams([w.to(dev, non_blocking=True) for w in w_host],
+                                     [b.to(dev, non_blocking=True) for b in b_host])
+        norm, state, buf, key = col.get_experience(norm, params, state, buf, key)
+        stats_host[:3].copy_(norm.mean, non_blocking=True)
+        stats_host[3:6].copy_(norm.std, non_blocking=True)
+        stats_host[6:].copy_(norm.count.reshape(1), non_blocking=True)
+        torch.cuda.synchronize(dev)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / steps
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    if rank == 0:
+        sm_max = 1965.0
+        try:
+            sm_max = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("sm_max_mhz", 1965.0))
+        except Exception:
+            pass
+        peak = 148 * 16 * sm_max * 1e6 / 1e12
+        achieved = E * T * ACT_MUFU_PER_STEP / (ms * 1e-3) / 1e12
+        h2d = sum(int(w.numel()) for w in w_host + b_host) * 4
+        emit_json({
+            "metric": "SAC get_experience env-steps/sec", "value": ENV_E * T / (ms * 1e-3), "unit": "env-steps/s",
+            "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic (random-init policy)",
+            "config": {"workload": "config3_collect_experience", "envs": ENV_E, "steps_per_call": T,
+                       "policy": "3-64-64-64-2 swish, NormalTanh, normalised observations",
+                       "episode_length": ENV_EPISODE, "queue_rows": REPLAY_ROWS, "parallelism": "envs sharded x%d" % world,
+                       "stages": "actor rollout (tcgen05) -> running_statistics.update (+ all-reduce) -> replay insert",
+                       "l2": "per-call Transition buffers %.0f MB > 126 MB L2" % (E * T * 40 / 1e6)},
+            "math_mode": args.math, "clocks": clk.summary(),
+            "e2e": {"value": ENV_E * T / e2e_s, "unit": "env-steps/s", "ms_per_step": e2e_s * 1e3,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 28,
+                    "api": "ExperienceCollector.get_experience(normalizer, policy params from pinned host, env_state, "
+                           "buffer_state, key) -> normaliser statistics to the host"},
+            "gpu_launches": steps * 5,
+            "roofline": {"bound": "xu", "kernel": "actor_rollout_tc_kernel (dominant: the whole step is timed)",
+                         "achieved": achieved, "peak": peak, "unit": "T MUFU/s", "frac": achieved / peak, "traffic": None,
+                         "note": ACT_TC_NOTE},
+            "cpu_baseline": None}, GUARD)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 BPTT_B, BPTT_H, BPTT_DISCOUNT, BPTT_LAMBDA = 65536, 20, 0.99, 0.97      # horizon / lambda_ of tests/test_bptt.py:51-57
 BPTT_ADJ_BYTES = 12 + 4 + 4 + 12 + 4         # observation, action, g_reward, g_next_obs read; g_action written
 
@@ -1284,7 +1427,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["config1_closed_loop", "config3_env_rollouts", "config3_actor_rollouts",
                                                                "config4_ensemble_icem", "config5_sweep", "bptt_rollout_grad",
-                                                               "config3_replay_insert"],
+                                                               "config3_replay_insert", "config3_collect_experience"],
                     default="config2_batched_icem")
     ap.add_argument("--math", choices=["reference", "theta_carry"], default="reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -1309,6 +1452,8 @@ def main():
             return run_sweep(args)
         if args.workload == "config3_replay_insert":
             return run_replay(args)
+        if args.workload == "config3_collect_experience":
+            return run_collect(args)
         wl = WORKLOADS[args.workload]
         if args.impl == "reference":
             run_reference(args, args.workload, wl)

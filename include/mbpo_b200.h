@@ -249,6 +249,10 @@ typedef struct MbpoPolicyParams {
   int32_t head, shared_noise, normalize;
   float sig_bias, sig_min, sig_max, action_clip;
   float obs_mean[4], obs_std[4];
+  /* device-resident normaliser statistics (float[obs_dim] each): when non-NULL the kernels read these instead of
+   * obs_mean / obs_std, so a collection loop never reads the running statistics back to the host. */
+  const float* obs_mean_dev;
+  const float* obs_std_dev;
   /* which kernel runs the network: MBPO_ACTOR_AUTO picks the tcgen05 kernel (hidden -> hidden layers as TF32 x 3
    * split-precision MMAs, fp32 accumulate in TMEM) for 2..3 hidden layers and the CUDA-core kernel otherwise;
    * MBPO_ACTOR_TCGEN05 with an unsupported depth is MBPO_EUNSUPPORTED. */

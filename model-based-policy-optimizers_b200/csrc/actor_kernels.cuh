@@ -45,6 +45,8 @@ struct ActorArgs {
   int tiles_per_cta;             // tcgen05 kernel: live 128-env tiles per CTA (1..4), fewer when E is small
   float sig_bias, sig_min, sig_max, action_clip;
   float obs_mean[3], obs_std[3];
+  const float* obs_mean_dev;    // device-resident statistics (override obs_mean / obs_std when non-null)
+  const float* obs_std_dev;
   const float* w[ACT_MAX_HIDDEN + 1];  // [3,64], [64,64] x (num_hidden-1), [64,2]   (flax Dense kernels, [in, out])
   const float* b[ACT_MAX_HIDDEN + 1];
   const uint32_t* key_in;       // [2] device
@@ -167,7 +169,12 @@ __global__ void __launch_bounds__(ACT_MAX_THREADS, 1) actor_rollout_pendulum_ker
                                                                                     const ActorSmem lay) {
   extern __shared__ __align__(16) float act_sm[];
   __shared__ float tiles[ACT_MAX_THREADS / 32][96];
+  __shared__ float norm_sm[8];     // normaliser mean [0..2], std [4..6]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
+  if (tid < 3) {
+    norm_sm[tid] = a.obs_mean_dev ? a.obs_mean_dev[tid] : a.obs_mean[tid];
+    norm_sm[4 + tid] = a.obs_std_dev ? a.obs_std_dev[tid] : a.obs_std[tid];
+  }
   // ---- policy parameters -> shared memory (once per launch) ----------------------------------------
   {
     const int L = a.num_hidden;
@@ -229,7 +236,7 @@ __global__ void __launch_bounds__(ACT_MAX_THREADS, 1) actor_rollout_pendulum_ker
       xin[q][0] = env[q].c; xin[q][1] = env[q].s; xin[q][2] = env[q].w;
       if (a.normalize) {
 #pragma unroll
-        for (int i = 0; i < 3; ++i) xin[q][i] = __fdiv_rn(__fsub_rn(xin[q][i], a.obs_mean[i]), a.obs_std[i]);
+        for (int i = 0; i < 3; ++i) xin[q][i] = __fdiv_rn(__fsub_rn(xin[q][i], norm_sm[i]), norm_sm[4 + i]);
       }
     }
     {

@@ -192,7 +192,12 @@ __device__ __forceinline__ f32x2_t fma2(f32x2_t x, f32x2_t y, f32x2_t z) {
 template <int PRNG, int MATH>
 __global__ void __launch_bounds__(THREADS, 1) actor_rollout_tc_kernel(const __grid_constant__ ActorArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ float norm_sm[8];     // normaliser mean [0..2], std [4..6]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 3) {
+    norm_sm[tid] = a.obs_mean_dev ? a.obs_mean_dev[tid] : a.obs_mean[tid];
+    norm_sm[4 + tid] = a.obs_std_dev ? a.obs_std_dev[tid] : a.obs_std[tid];
+  }
   const bool issuer_warp = tid >= ENV_THREADS_;
   const int g = issuer_warp ? (tid - ENV_THREADS_) / 32 : tid / TILE;   // tile of the CTA
   const int r = tid % TILE;                                             // row of the tile (producer threads)
@@ -331,7 +336,7 @@ __global__ void __launch_bounds__(THREADS, 1) actor_rollout_tc_kernel(const __gr
       float xin[3] = {v.c, v.s, v.w};
       if (a.normalize) {
 #pragma unroll
-        for (int i = 0; i < 3; ++i) xin[i] = __fdiv_rn(__fsub_rn(xin[i], a.obs_mean[i]), a.obs_std[i]);
+        for (int i = 0; i < 3; ++i) xin[i] = __fdiv_rn(__fsub_rn(xin[i], norm_sm[i]), norm_sm[4 + i]);
       }
       float loc = 0.0f, raw_sc = 0.0f, eps = 0.0f;
       const f32x2_t x0p = pack2(xin[0], xin[0]), x1p = pack2(xin[1], xin[1]), x2p = pack2(xin[2], xin[2]);

@@ -764,6 +764,9 @@ int mbpo_actor_rollout_extras(int system_kind, const void* sys_params_host, int 
   a.draw_total = policy_host->draw_total > 0 ? policy_host->draw_total : E;
   a.draw_offset = policy_host->draw_total > 0 ? policy_host->draw_offset : 0;
   for (int i = 0; i < 3; ++i) { a.obs_mean[i] = policy_host->obs_mean[i]; a.obs_std[i] = policy_host->obs_std[i]; }
+  MBPO_REQUIRE((policy_host->obs_mean_dev == nullptr) == (policy_host->obs_std_dev == nullptr),
+               "actor_rollout: obs_mean_dev and obs_std_dev come together");
+  a.obs_mean_dev = policy_host->obs_mean_dev; a.obs_std_dev = policy_host->obs_std_dev;
   for (int l = 0; l <= mbpo::ACT_MAX_HIDDEN; ++l) {
     a.w[l] = l <= a.num_hidden ? policy_host->w[l] : nullptr;
     a.b[l] = l <= a.num_hidden ? policy_host->b[l] : nullptr;

@@ -66,7 +66,8 @@ class PolicyParamsC(C.Structure):
                 ("w", C.c_void_p * 5), ("b", C.c_void_p * 5), ("min_std", C.c_float),
                 ("head", C.c_int32), ("shared_noise", C.c_int32), ("normalize", C.c_int32),
                 ("sig_bias", C.c_float), ("sig_min", C.c_float), ("sig_max", C.c_float), ("action_clip", C.c_float),
-                ("obs_mean", C.c_float * 4), ("obs_std", C.c_float * 4), ("kernel", C.c_int32),
+                ("obs_mean", C.c_float * 4), ("obs_std", C.c_float * 4),
+                ("obs_mean_dev", C.c_void_p), ("obs_std_dev", C.c_void_p), ("kernel", C.c_int32),
                 ("draw_offset", C.c_int32), ("draw_total", C.c_int32)]
 
 

@@ -60,9 +60,15 @@ class Policy:
         self._set_normalizer(obs_mean, obs_std)
 
     def _set_normalizer(self, obs_mean, obs_std):
+        """Sequences of floats go into the struct by value; CUDA tensors stay on the device (the kernels read them
+        through obs_mean_dev / obs_std_dev: no read-back of the running statistics in a collection loop)."""
         s = self.struct
         s.normalize = int(obs_mean is not None)
-        if obs_mean is not None:
+        s.obs_mean_dev = s.obs_std_dev = None
+        if torch.is_tensor(obs_mean) and obs_mean.is_cuda:
+            self._norm = (obs_mean.to(torch.float32).contiguous(), obs_std.to(torch.float32).contiguous())
+            s.obs_mean_dev, s.obs_std_dev = _lib.ptr(self._norm[0]), _lib.ptr(self._norm[1])
+        elif obs_mean is not None:
             mean = [float(v) for v in (obs_mean.tolist() if hasattr(obs_mean, "tolist") else obs_mean)]
             std = [float(v) for v in (obs_std.tolist() if hasattr(obs_std, "tolist") else obs_std)]
             for i in range(len(mean)):
