@@ -1431,7 +1431,7 @@ def main():
                     default="config2_batched_icem")
     ap.add_argument("--math", choices=["reference", "theta_carry"], default="reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--actor-kernel", choices=["auto", "cuda_cores", "tcgen05"], default="auto",
+    ap.add_argument("--actor-kernel", choices=["auto", "cuda_cores", "tcgen05", "tcgen05_wide"], default="auto",
                     help="config3_actor_rollouts: which kernel runs the policy network")
     ap.add_argument("--env-sequential", action="store_true",
                     help="config3_env_rollouts: time the one-thread-per-env scan instead of the episode-piece kernel")

@@ -263,7 +263,11 @@ typedef struct MbpoPolicyParams {
   int32_t draw_offset, draw_total;
 } MbpoPolicyParams;
 enum { MBPO_HEAD_NORMAL_TANH = 0, MBPO_HEAD_BPTT_ACTOR = 1 };
-enum { MBPO_ACTOR_AUTO = 0, MBPO_ACTOR_CUDA_CORES = 1, MBPO_ACTOR_TCGEN05 = 2 };
+/* MBPO_ACTOR_TCGEN05 = the throughput kernel (four 128-env tiles per CTA, thread = env); MBPO_ACTOR_TCGEN05_WIDE = the
+ * latency kernel (one tile per CTA, sixteen producer warps + PRNG warps: a step takes a third of the time when the
+ * envs do not fill the GPU).  Both produce the same bits.  MBPO_ACTOR_AUTO takes the wide kernel when there is at most
+ * one tile per SM. */
+enum { MBPO_ACTOR_AUTO = 0, MBPO_ACTOR_CUDA_CORES = 1, MBPO_ACTOR_TCGEN05 = 2, MBPO_ACTOR_TCGEN05_WIDE = 3 };
 enum {
   MBPO_KEYS_SAC = 0,     /* sac/sac.py:288-292      k, k_t = split(k); policy key = k_t          */
   MBPO_KEYS_UNROLL = 1,  /* sac/acting.py:68-73     current, next = split(current); policy key = current, carry = next */

@@ -43,6 +43,7 @@ struct ActorArgs {
   int head, shared_noise, normalize;
   int draw_offset, draw_total;   // env sharding of the draw normal(key, (draw_total, A))[draw_offset + e]
   int tiles_per_cta;             // tcgen05 kernel: live 128-env tiles per CTA (1..4), fewer when E is small
+  int rows_per_cta;              // wide tcgen05 kernel: live rows of a CTA's 128-row tile (32, 64 or 128)
   float sig_bias, sig_min, sig_max, action_clip;
   float obs_mean[3], obs_std[3];
   const float* obs_mean_dev;    // device-resident statistics (override obs_mean / obs_std when non-null)

@@ -388,13 +388,24 @@ __global__ void __launch_bounds__(THREADS, 1) actor_rollout_tc_kernel(const __gr
             }
           }
           if (!to_mma) {        // output layer on the CUDA cores, float32
+            // one partial per 16-column quarter, the quarters added in order: the order of the wide kernel
+            // (actor_tc_wide_kernels.cuh), whose quarters live in different threads -- both kernels agree bit for bit
+            static_assert(QC <= 16 && 16 % QC == 0, "output-layer partials are per 16 columns");
+            float pl = 0.0f, ps = 0.0f;
 #pragma unroll
             for (int i = 0; i < QC; i += 2) {
               const float4 wo = *reinterpret_cast<const float4*>(s_wo + (qd * QC + i) * 2);
-              loc = fmaf(h[i], wo.x, loc);
-              raw_sc = fmaf(h[i], wo.y, raw_sc);
-              loc = fmaf(h[i + 1], wo.z, loc);
-              raw_sc = fmaf(h[i + 1], wo.w, raw_sc);
+              pl = fmaf(h[i], wo.x, pl);
+              ps = fmaf(h[i], wo.y, ps);
+              pl = fmaf(h[i + 1], wo.z, pl);
+              ps = fmaf(h[i + 1], wo.w, ps);
+            }
+            if (QC == 16) {
+              loc = qd == 0 ? pl : __fadd_rn(loc, pl);
+              raw_sc = qd == 0 ? ps : __fadd_rn(raw_sc, ps);
+            } else {            // ring experiments with narrower slots: plain running sum
+              loc += pl;
+              raw_sc += ps;
             }
             continue;
           }

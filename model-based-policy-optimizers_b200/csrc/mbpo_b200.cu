@@ -16,6 +16,7 @@
 #include "mlp_tc_kernels.cuh"
 #include "actor_kernels.cuh"
 #include "actor_tc_kernels.cuh"
+#include "actor_tc_wide_kernels.cuh"
 #include "adjoint_kernels.cuh"
 #include "ensemble_pp_kernels.cuh"
 #include "plan_dispatch.h"
@@ -692,6 +693,23 @@ int launch_actor_tc(const mbpo::ActorArgs& a, cudaStream_t st) {
   kernel<<<blocks, atc::THREADS, atc::Smem::TOTAL, st>>>(b);
   return check_launch("actor_rollout_tc_kernel");
 }
+template <int PRNG, int MATH>
+int launch_actor_tc_wide(const mbpo::ActorArgs& a, cudaStream_t st) {
+  using namespace mbpo;
+  auto kernel = atcw::actor_rollout_tc_wide_kernel<PRNG, MATH>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(atcw::WSmem::TOTAL));
+  if (e != cudaSuccess)
+    return fail(MBPO_ECUDA, "actor_rollout (tcgen05, wide): smem attribute (%u B): %s", atcw::WSmem::TOTAL,
+                cudaGetErrorString(e));
+  // fewer live rows per CTA while that still leaves an SM for every CTA (the issue slots of an SM bound a step)
+  const int sms = device_sm_count();
+  ActorArgs b = a;
+  b.rows_per_cta = a.E <= 32 * sms ? 32 : (a.E <= 64 * sms ? 64 : atc::TILE);
+  const unsigned ctas = static_cast<unsigned>((a.E + b.rows_per_cta - 1) / b.rows_per_cta);
+  kernel<<<ctas, atcw::WTHREADS, atcw::WSmem::TOTAL, st>>>(b);
+  return check_launch("actor_rollout_tc_wide_kernel");
+}
 }  // namespace
 }  // extern "C++"
 
@@ -777,12 +795,23 @@ int mbpo_actor_rollout_extras(int system_kind, const void* sys_params_host, int 
   a.next_observation_out = next_observation_out; a.truncation_out = truncation_out; a.key_out = key_out;
   a.raw_action_out = raw_action_out; a.log_prob_out = log_prob_out;
   cudaStream_t st = as_stream(stream);
-  MBPO_REQUIRE(policy_host->kernel >= MBPO_ACTOR_AUTO && policy_host->kernel <= MBPO_ACTOR_TCGEN05,
+  MBPO_REQUIRE(policy_host->kernel >= MBPO_ACTOR_AUTO && policy_host->kernel <= MBPO_ACTOR_TCGEN05_WIDE,
                "actor_rollout: bad policy kernel selector %d", policy_host->kernel);
   const bool tc_ok = a.num_hidden >= 2 && a.num_hidden <= 1 + mbpo::atc::MAX_HH;
-  if (policy_host->kernel == MBPO_ACTOR_TCGEN05 && !tc_ok)
+  if ((policy_host->kernel == MBPO_ACTOR_TCGEN05 || policy_host->kernel == MBPO_ACTOR_TCGEN05_WIDE) && !tc_ok)
     return fail(MBPO_EUNSUPPORTED, "actor_rollout: the tcgen05 kernel holds 1..%d hidden -> hidden layers (got %d hidden layers)",
                 mbpo::atc::MAX_HH, a.num_hidden);
+  // few envs (at most one 128-env tile per SM): the latency kernel; otherwise the throughput kernel
+  const bool wide = policy_host->kernel == MBPO_ACTOR_TCGEN05_WIDE ||
+                    (policy_host->kernel == MBPO_ACTOR_AUTO && (E + mbpo::atc::TILE - 1) / mbpo::atc::TILE <= device_sm_count());
+  if (tc_ok && wide) {
+    switch (prng_mode * 2 + math_mode) {
+      case 0: return launch_actor_tc_wide<0, 0>(a, st);
+      case 1: return launch_actor_tc_wide<0, 1>(a, st);
+      case 2: return launch_actor_tc_wide<1, 0>(a, st);
+      default: return launch_actor_tc_wide<1, 1>(a, st);
+    }
+  }
   if (tc_ok && policy_host->kernel != MBPO_ACTOR_CUDA_CORES) {
     switch (prng_mode * 2 + math_mode) {
       case 0: return launch_actor_tc<0, 0>(a, st);

@@ -73,7 +73,7 @@ class PolicyParamsC(C.Structure):
 
 KEYS_SAC, KEYS_UNROLL, KEYS_AS_IS = 0, 1, 2
 HEAD_NORMAL_TANH, HEAD_BPTT_ACTOR = 0, 1
-ACTOR_AUTO, ACTOR_CUDA_CORES, ACTOR_TCGEN05 = 0, 1, 2
+ACTOR_AUTO, ACTOR_CUDA_CORES, ACTOR_TCGEN05, ACTOR_TCGEN05_WIDE = 0, 1, 2, 3
 
 
 class IcemTraceC(C.Structure):

@@ -36,7 +36,8 @@ class Policy:
         """obs_mean / obs_std: the running-statistics normaliser the reference passes as ``normalizer_params``
         (``policy_network.apply(normalizer_params, policy_params, obs)``: (obs - mean) / std); emit_extras: PPO's
         policy also returns {'log_prob', 'raw_action'} (ppo_network.py:72-80); kernel: "auto" (tcgen05 for 2..3
-        hidden layers, CUDA cores otherwise), "cuda_cores" or "tcgen05"."""
+        hidden layers -- the wide latency kernel when the envs do not fill the GPU --, CUDA cores otherwise),
+        "cuda_cores", "tcgen05" (throughput kernel) or "tcgen05_wide" (latency kernel)."""
         w = [t.to(torch.float32).contiguous() for t in params.weights]
         b = [t.to(torch.float32).contiguous() for t in params.biases]
         if len(w) < 2 or len(w) != len(b) or len(w) > 5:
@@ -54,7 +55,8 @@ class Policy:
             s.b[i] = _lib.ptr(bi)
         s.min_std = self.min_std
         s.head = _lib.HEAD_NORMAL_TANH
-        s.kernel = {"auto": _lib.ACTOR_AUTO, "cuda_cores": _lib.ACTOR_CUDA_CORES, "tcgen05": _lib.ACTOR_TCGEN05}[kernel]
+        s.kernel = {"auto": _lib.ACTOR_AUTO, "cuda_cores": _lib.ACTOR_CUDA_CORES, "tcgen05": _lib.ACTOR_TCGEN05,
+                    "tcgen05_wide": _lib.ACTOR_TCGEN05_WIDE}[kernel]
         self.struct = s
         self.emit_extras = bool(emit_extras) and not self.deterministic
         self._set_normalizer(obs_mean, obs_std)

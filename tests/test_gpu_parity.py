@@ -712,7 +712,7 @@ def _policy_on_device(mb, cuda_device, pol, deterministic=False, kernel="auto"):
 
 @pytest.mark.parametrize("convention", ["sac", "unroll"])
 @pytest.mark.parametrize("hidden,kernel", [((64, 64, 64), "tcgen05"), ((64, 64, 64), "cuda_cores"), ((64, 64), "tcgen05"),
-                                           ((64,), "auto")])
+                                           ((64,), "auto"), ((64, 64, 64), "tcgen05_wide"), ((64, 64), "tcgen05_wide")])
 def test_actor_rollout_vs_oracle(mb, cuda_device, prng_mode, math_mode, convention, hidden, kernel):
     """T steps of policy forward + NormalTanh sample + wrapped env step in one launch, per step against the
     oracle teacher-forced on the GPU's observations; the PRNG carry key is bit exact.  Both kernels: the
@@ -791,7 +791,45 @@ def test_actor_step_and_deterministic_policy(mb, cuda_device):
         acting.actor_step(env, st, _policy_on_device(mb, cuda_device, bad), _dev(key, cuda_device))
 
 
-@pytest.mark.parametrize("kernel", ["tcgen05", "cuda_cores"])
+@pytest.mark.parametrize("hidden", [(64, 64, 64), (64, 64)])
+@pytest.mark.parametrize("E,T", [(1, 3), (129, 17), (1000, 40), (4096, 5)])
+def test_wide_and_four_tile_tcgen05_kernels_agree_bit_for_bit(mb, cuda_device, hidden, E, T):
+    """The latency kernel (one tile per CTA, sixteen producer warps, PRNG warps) and the throughput kernel (four tiles
+    per CTA, thread = env) are the same computation in the same order: every output and the carry key are equal, for
+    SAC's head, PPO's extras and BPTT's actor."""
+    from mbpo_b200 import acting
+    from mbpo_b200.envs import wrap
+    from mbpo_b200.systems import PendulumSystem
+    pol = orc.make_policy_params(seed=E + T, hidden=hidden)
+    system = PendulumSystem()
+    env = wrap(system, system.reset(device=cuda_device).system_params, episode_length=7)
+    x0 = _dev(_random_states(E, 5), cuda_device)
+    key = _dev(ojr.PRNGKey(E), cuda_device)
+    params = acting.PolicyParams([_dev(w, cuda_device) for w in pol.weights], [_dev(b, cuda_device) for b in pol.biases])
+
+    def run(kernel, which):
+        if which == "ppo":
+            policy = acting.Policy(params, False, [0.1, -0.2, 0.5], [0.7, 0.8, 3.0], emit_extras=True, kernel=kernel)
+        elif which == "bptt":
+            policy = acting.BpttActorPolicy(params, init_stddev=0.5, obs_mean=[0.1, -0.2, 0.5], obs_std=[0.7, 0.8, 3.0])
+            policy.struct.kernel = {"tcgen05": mb._lib.ACTOR_TCGEN05, "tcgen05_wide": mb._lib.ACTOR_TCGEN05_WIDE}[kernel]
+        else:
+            policy = acting.Policy(params, which == "det", kernel=kernel)
+        st = env.reset(x0)
+        key_out, nst, tr = acting.get_experience(env, st, policy, key, T)
+        outs = [key_out, nst.obs, nst.done, nst.info["steps"], tr.action, tr.reward, tr.discount, tr.next_observation,
+                tr.extras["state_extras"]["truncation"]]
+        outs += list(tr.extras["policy_extras"].values())
+        return outs
+
+    for which in ("sac", "det", "ppo", "bptt"):
+        a, b = run("tcgen05", which), run("tcgen05_wide", which)
+        assert len(a) == len(b)
+        for x, y in zip(a, b):
+            assert torch.equal(x, y), which
+
+
+@pytest.mark.parametrize("kernel", ["tcgen05", "cuda_cores", "tcgen05_wide"])
 def test_actor_rollout_env_sharding_is_bit_identical(mb, cuda_device, kernel):
     """Envs sharded over ranks: each shard draws its slice of normal(key, (num_envs, A)), so the shards together
     reproduce the unsharded launch bit for bit (the multi-GPU invariant of DESIGN.md section 4.3)."""
