@@ -103,6 +103,71 @@ class VmappedSystemEnv:
                                 extras={"state_extras": {"truncation": tr}})
         return new_state, transition
 
+    def unroll_streamed(self, state: EnvState, actions_host: torch.Tensor, reward_host: torch.Tensor = None,
+                        chunk_steps: int = 64):
+        """``unroll`` for actions that live in pinned host memory: the T steps are cut into chunks and the host ->
+        device copy of chunk k + 1, the rollout of chunk k and the device -> host copy of chunk k - 1's rewards run
+        concurrently on three streams (PCIe is full duplex; the rollout itself is a few percent of either copy).
+        Same bits as ``unroll`` (chunked == whole).  ``reward_host`` [T, E] (pinned) receives the
+        rewards; the caller's stream is ordered after everything, so one synchronize covers the copies too."""
+        if actions_host.is_cuda or not actions_host.is_pinned():
+            raise _lib.MbpoError(_lib.MBPO_EINVAL, "unroll_streamed: actions_host must be a pinned host tensor")
+        T, E, A = actions_host.shape
+        X = self.system.x_dim
+        dev = state.obs.device
+        main = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_streams"):
+            self._streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        s_in, s_out = self._streams
+        acts = torch.empty((T, E, A), dtype=torch.float32, device=dev)
+        buf = torch.empty((T + 1, E, X), dtype=torch.float32, device=dev)
+        buf[0].copy_(state.obs)
+        r = torch.empty((T, E), dtype=torch.float32, device=dev)
+        d = torch.empty((T, E), dtype=torch.float32, device=dev)
+        tr = torch.empty((T, E), dtype=torch.float32, device=dev)
+        first = state.info["first_obs"].contiguous()
+        cur = [state.obs.contiguous(), state.info["steps"].contiguous(), state.done.contiguous()]
+        nxt = [torch.empty_like(t) for t in cur]
+        spare = [torch.empty_like(t) for t in cur]
+        params = self.system.pack_params(state.system_params)
+        s_in.wait_stream(main)              # acts / buf exist before the copies start
+        s_out.wait_stream(main)
+        bounds = [(t0, min(t0 + chunk_steps, T)) for t0 in range(0, T, max(int(chunk_steps), 1))]
+        ev_in = []
+        with torch.cuda.stream(s_in):
+            for t0, t1 in bounds:
+                acts[t0:t1].copy_(actions_host[t0:t1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(s_in)
+                ev_in.append(ev)
+        with _lib.cuda_guard(acts):
+            for k, (t0, t1) in enumerate(bounds):
+                main.wait_event(ev_in[k])
+                _lib.check(_lib.lib.mbpo_env_unroll(
+                    self.system.system_kind, _lib.C.addressof(params), config.math_mode_id, X, A, self.episode_length,
+                    self.action_repeat, _lib.ptr(cur[0]), _lib.ptr(cur[1]), _lib.ptr(cur[2]), _lib.ptr(nxt[0]),
+                    _lib.ptr(nxt[1]), _lib.ptr(nxt[2]), _lib.ptr(first), acts[t0:t1].data_ptr(), E, t1 - t0, None,
+                    r[t0:t1].data_ptr(), d[t0:t1].data_ptr(), buf[1 + t0:1 + t1].data_ptr(), tr[t0:t1].data_ptr(),
+                    main.cuda_stream))
+                cur, nxt, spare = nxt, spare, cur
+                if reward_host is not None:
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    s_out.wait_event(ev)
+                    with torch.cuda.stream(s_out):
+                        reward_host[t0:t1].copy_(r[t0:t1], non_blocking=True)
+        # the caller's stream is ordered after both side streams: buffers allocated on it may be reused in its order
+        # (no record_stream: that would keep the caching allocator from recycling the big blocks call after call)
+        main.wait_stream(s_in)
+        main.wait_stream(s_out)
+        new_state = EnvState(obs=cur[0], reward=r[-1] if T else state.reward, done=cur[2],
+                             system_params=state.system_params,
+                             info=dict(steps=cur[1], truncation=tr[-1] if T else state.info["truncation"],
+                                       first_obs=first))
+        transition = Transition(observation=buf[:T], action=acts, reward=r, discount=d, next_observation=buf[1:],
+                                extras={"state_extras": {"truncation": tr}})
+        return new_state, transition
+
     def step(self, state: EnvState, action: torch.Tensor) -> EnvState:
         """One wrapped env step: action [E, A]."""
         new_state, _ = self.unroll(state, action.reshape(1, *action.shape))

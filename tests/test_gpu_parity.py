@@ -791,6 +791,31 @@ def test_actor_step_and_deterministic_policy(mb, cuda_device):
         acting.actor_step(env, st, _policy_on_device(mb, cuda_device, bad), _dev(key, cuda_device))
 
 
+@pytest.mark.parametrize("E,T,chunk", [(1000, 37, 5), (256, 200, 64), (77, 10, 100)])
+def test_env_unroll_streamed_equals_unroll(mb, cuda_device, E, T, chunk):
+    """Actions in pinned host memory, copies and rollout overlapped on three streams: same bits as unroll, rewards
+    delivered to the host buffer."""
+    from mbpo_b200.envs import wrap
+    from mbpo_b200.systems import PendulumSystem
+    system = PendulumSystem()
+    env = wrap(system, system.reset(device=cuda_device).system_params, episode_length=23)
+    x0 = _dev(_random_states(E, 3), cuda_device)
+    acts_host = torch.from_numpy(np.random.default_rng(4).uniform(-1, 1, (T, E, 1)).astype(np.float32)).pin_memory()
+    rew_host = torch.zeros((T, E), dtype=torch.float32).pin_memory()
+    st = env.reset(x0)
+    n1, t1 = env.unroll(st, acts_host.to(cuda_device))
+    n2, t2 = env.unroll_streamed(st, acts_host, rew_host, chunk_steps=chunk)
+    torch.cuda.synchronize()
+    for a, b in ((t1.observation, t2.observation), (t1.action, t2.action), (t1.reward, t2.reward),
+                 (t1.discount, t2.discount), (t1.next_observation, t2.next_observation),
+                 (t1.extras["state_extras"]["truncation"], t2.extras["state_extras"]["truncation"]),
+                 (n1.obs, n2.obs), (n1.done, n2.done), (n1.info["steps"], n2.info["steps"])):
+        assert torch.equal(a, b)
+    assert torch.equal(rew_host, t1.reward.cpu())
+    with pytest.raises(mb.MbpoError):
+        env.unroll_streamed(st, acts_host.to(cuda_device))
+
+
 @pytest.mark.parametrize("hidden", [(64, 64, 64), (64, 64)])
 @pytest.mark.parametrize("E,T", [(1, 3), (129, 17), (1000, 40), (4096, 5)])
 def test_wide_and_four_tile_tcgen05_kernels_agree_bit_for_bit(mb, cuda_device, hidden, E, T):
