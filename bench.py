@@ -928,13 +928,19 @@ def run_actor(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     rew_host = torch.empty((T, E), dtype=torch.float32).pin_memory()
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(steps):
+
+    def e2e_step():
         st_k = env.reset(x0_host.to(dev, non_blocking=True))
         _, _, trn = acting.get_experience(env, st_k, policy, key, T, env_offset=lo, total_envs=ENV_E)
         rew_host.copy_(trn.reward, non_blocking=True)
         torch.cuda.synchronize(dev)
+        return trn
+    for _ in range(3):                 # untimed: the allocator's second set of output blocks
+        trn = e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(steps):
+        trn = e2e_step()
     barrier()
     e2e_s = (time.perf_counter() - t0) / steps
     if rank == 0:
@@ -1379,14 +1385,19 @@ def run_replay(args):
     # end to end: a sampled batch (the learner's input) read back to the host after every insert
     batch_host = torch.empty((256, D), dtype=torch.float32).pin_memory()
     rew_host_in = torch.randn((T, E), dtype=torch.float32).pin_memory()
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(args.steps):
+    def e2e_step(st):
         rew = rew_host_in.to(dev, non_blocking=True)
         st = q.insert(st, tr._replace(reward=rew))
         st, batch = q.sample(st)
         batch_host[:, 4].copy_(batch.reward, non_blocking=True)
         torch.cuda.synchronize(dev)
+        return st
+    for _ in range(3):
+        st = e2e_step(st)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        st = e2e_step(st)
     barrier()
     e2e_s = (time.perf_counter() - t0) / args.steps
     if rank == 0:
