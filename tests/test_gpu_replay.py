@@ -522,3 +522,33 @@ def test_bptt_normalizer_and_take(mb, cuda_device):
     assert torch.equal(wrapped.observation, rows.observation)
     neg = q.take(st, idx - 50)
     assert torch.equal(neg.reward, rows.reward)
+
+
+def test_graphed_rollout_replays_the_same_bits(mb, cuda_device):
+    """The collection call captured in a CUDA graph (launch-bound regime: 32 envs x 20 steps, tests/test_sac.py's
+    shape): three replays equal three get_experience calls chained by hand, bit for bit."""
+    from mbpo_b200 import acting
+    from mbpo_b200.envs import wrap
+    from mbpo_b200.systems import PendulumSystem
+    dev = cuda_device
+    E, T, L = 32, 20, 50
+    pol = orc.make_policy_params(seed=3)
+    policy = acting.Policy(acting.PolicyParams([_dev(w, dev) for w in pol.weights], [_dev(b, dev) for b in pol.biases]))
+    system = PendulumSystem()
+    env = wrap(system, system.reset(device=dev).system_params, episode_length=L)
+    rng = np.random.default_rng(0)
+    th, w = rng.uniform(-np.pi, np.pi, E), rng.uniform(-8, 8, E)
+    x0 = _dev(np.stack([np.cos(th), np.sin(th), w], -1).astype(np.float32), dev)
+    key = _dev(ojr.PRNGKey(9), dev)
+    st = env.reset(x0)
+    collect = acting.GraphedRollout(env, st, policy, key, T)
+    k, s = key, st
+    for it in range(3):
+        k, s, tr = acting.get_experience(env, s, policy, k, T)
+        gk, gs, gtr = collect()
+        assert torch.equal(gk, k) and torch.equal(gs.obs, s.obs) and torch.equal(gs.done, s.done)
+        assert torch.equal(gs.info["steps"], s.info["steps"])
+        for a, b in ((gtr.observation, tr.observation), (gtr.action, tr.action), (gtr.reward, tr.reward),
+                     (gtr.discount, tr.discount), (gtr.next_observation, tr.next_observation),
+                     (gtr.extras["state_extras"]["truncation"], tr.extras["state_extras"]["truncation"])):
+            assert torch.equal(a, b), it
