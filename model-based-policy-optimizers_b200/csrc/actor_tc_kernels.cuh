@@ -400,7 +400,11 @@ __global__ void __launch_bounds__(THREADS, 1) actor_rollout_tc_kernel(const __gr
               pl = fmaf(h[i + 1], wo.z, pl);
               ps = fmaf(h[i + 1], wo.w, ps);
             }
+#ifdef MBPO_ATC_SERIAL_OUT     // A/B switch: the single 64-term chain of the first version (not bit-equal to the wide kernel)
+            if (false) {
+#else
             if (QC == 16) {
+#endif
               loc = qd == 0 ? pl : __fadd_rn(loc, pl);
               raw_sc = qd == 0 ? ps : __fadd_rn(raw_sc, ps);
             } else {            // ring experiments with narrower slots: plain running sum

@@ -26,7 +26,8 @@ SYSTEM_PENDULUM, SYSTEM_MLP_ENSEMBLE = 0, 1
 MATH_REFERENCE, MATH_THETA_CARRY = 0, 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmbpo_b200.so")
+# MBPO_B200_LIB: another build of the same ABI (A/B measurements of kernel variants); default = the in-tree library
+LIB_PATH = os.environ.get("MBPO_B200_LIB") or os.path.join(_HERE, "libmbpo_b200.so")
 
 
 class MbpoError(RuntimeError):
