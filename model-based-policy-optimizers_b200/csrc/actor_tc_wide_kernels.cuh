@@ -7,12 +7,14 @@
 // The reference's own configurations are in that regime (tests/test_sac.py: num_envs = 32, 20 steps per collection),
 // and so is every shard of config 3 at 4 or 8 GPUs (8,192 envs = 64 tiles for 148 SMs).  Here
 //
-//   producers     16 warps: warp = 4 * q + lane_quarter; thread (q, row) owns the 16 columns [16 q, 16 q + 16) of its
+//   producers     16 warps: warp = 4 * q + lane_quarter; the four threads (q = 0..3, row) share the 64 columns of their
 //                 env's row in every layer: layer 0, the bias + swish epilogues and the TF32 hi / lo split run four
 //                 wide per env.  TMEM lane quarter = warp % 4, as the hardware requires.
-//   A operand     four 16 KB slots, slot q written by the four warps of column quarter q, all at once; the issuer takes
-//                 them in the order 0..3 (the accumulation order of the four-tile kernel).  A slot is rewritten only
-//                 after `layer_done` of the MMAs that read it, so there are no slot_free barriers.
+//   A operand     four 16 KB slots.  A stage runs in four time slices: in slice j thread (q, row) produces columns
+//                 16 j + 4 q .. + 3 -- one 16-byte chunk of slot j -- so slot j is complete a quarter of the way through
+//                 the stage and its MMAs run under the production of slot j + 1; the issuer takes the slots in the
+//                 order 0..3 (the accumulation order of the four-tile kernel).  A slot is rewritten only after
+//                 `layer_done` of the MMAs that read it, so there are no slot_free barriers.
 //   output layer  every thread folds its 16 columns into a partial (loc, scale) pair; the four partials of a row are
 //                 added in quarter order by the q = 0 thread -- the four-tile kernel adds its quarters in the same
 //                 order, so both kernels (and therefore sharded and unsharded launches) agree bit for bit.
@@ -61,6 +63,12 @@ struct WSmem {
 };
 static_assert(WSmem::TOTAL <= 227 * 1024, "wide tensor-core actor kernel shared memory plan exceeds 227 KB");
 
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void named_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
@@ -112,7 +120,7 @@ __global__ void __launch_bounds__(WTHREADS, 1) actor_rollout_tc_wide_kernel(cons
   }
   const int rows = a.rows_per_cta;                  // live rows of this CTA's tile: 32, 64 or 128
   if (tid == 32) {
-    for (int i = 0; i < QUARTERS; ++i) mbar_init(&bars[i], rows / 32);   // full[q]: one arrival per live warp of the quarter
+    for (int i = 0; i < QUARTERS; ++i) mbar_init(&bars[i], QUARTERS * (rows / 32));   // full[j]: every live producer warp
     mbar_init(&bars[QUARTERS], 1);                                        // layer_done
     fence_barrier_init();
   }
@@ -204,7 +212,7 @@ __global__ void __launch_bounds__(WTHREADS, 1) actor_rollout_tc_wide_kernel(cons
     if (blockIdx.x == 0 && r == 0 && a.key_out) { a.key_out[0] = key.k0; a.key_out[1] = key.k1; }
   } else {
     // ---- producers ----------------------------------------------------------------------------------------------
-    const uint32_t tmem_rd = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + q * QC;
+    const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);   // this warp's 32 lanes
     uint32_t layer_phase = 0;
     const PendulumConsts pc(a.sys);
     const float ep_len = static_cast<float>(a.episode_length);
@@ -236,22 +244,24 @@ __global__ void __launch_bounds__(WTHREADS, 1) actor_rollout_tc_wide_kernel(cons
     long long prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long last_ = clock64();
 #endif
-    uint8_t* slot_dst = smem + WSmem::A + q * SLOT_BYTES + r * 16;
-    const uint32_t full_bar = bar0 + q * 8u;
+    uint8_t* chunk_dst = smem + WSmem::A + q * A_LBO_ + r * 16;   // chunk q of a slot's hi plane (+ slot offset)
 
 #pragma unroll 1
     for (int t = 0; t < a.T; ++t) {
       const f32x2_t x0p = pack2(xin.x, xin.x), x1p = pack2(xin.y, xin.y), x2p = pack2(xin.z, xin.z);
       float pl = 0.0f, ps = 0.0f;       // this quarter's partial of the output layer
 #pragma unroll 1
-      for (int s = 0; s <= HH; ++s) {
-        const bool to_mma = s < HH;
-        float h[QC];
-        if (s == 0) {
-          // ---- layer 0: the same float operations per element as the four-tile kernel -----------------------------
-#pragma unroll
-          for (int j4 = 0; j4 < QC / 4; ++j4) {
-            const int c0 = q * QC + j4 * 4;
+      for (int s = 0; s < HH; ++s) {
+        // ---- a stage that feeds MMAs, in four time slices: in slice j the four threads of a row produce the four
+        // 4-column chunks of ring slot j (thread q: columns 16 j + 4 q ..), so slot j is complete a quarter of the way
+        // through the stage and its six MMAs run under the production of slot j + 1 -- the issuer still takes the
+        // slots in the order 0..3, i.e. the accumulation order of the four-tile kernel.
+#pragma unroll 1
+        for (int j = 0; j < QUARTERS; ++j) {
+          const int c0 = j * QC + q * 4;
+          float h[4];
+          if (s == 0) {
+            // layer 0: the same float operations per element as the four-tile kernel
             const float4 r0 = *reinterpret_cast<const float4*>(s_w0 + c0);
             const float4 r1 = *reinterpret_cast<const float4*>(s_w0 + W + c0);
             const float4 r2 = *reinterpret_cast<const float4*>(s_w0 + 2 * W + c0);
@@ -265,55 +275,63 @@ __global__ void __launch_bounds__(WTHREADS, 1) actor_rollout_tc_wide_kernel(cons
                                         fma2(x1p, pack2(w1r[i], w1r[i + 1]), mul2(x0p, pack2(w0r[i], w0r[i + 1]))));
               unpack2(add2(acc2, pack2(b0r[i], b0r[i + 1])), pre[i], pre[i + 1]);
             }
-            swish2(pre[0], pre[1], h[j4 * 4], h[j4 * 4 + 1]);
-            swish2(pre[2], pre[3], h[j4 * 4 + 2], h[j4 * 4 + 3]);
-          }
-        } else {
-          // ---- epilogue of the previous layer: this quarter's 16 accumulator columns, bias + swish --------------
-          const float* bias = s_bh + (s - 1) * W + q * QC;
-          uint32_t acc[QC];
-          tmem_ldq(tmem_rd + ((s - 1) & 1) * W, acc);
-#pragma unroll
-          for (int j4 = 0; j4 < QC / 4; ++j4) {
-            const float4 bb = *reinterpret_cast<const float4*>(bias + j4 * 4);
+            swish2(pre[0], pre[1], h[0], h[1]);
+            swish2(pre[2], pre[3], h[2], h[3]);
+          } else {
+            // epilogue of the previous layer: four accumulator columns, bias + swish
+            uint32_t acc[4];
+            tmem_ld4(tmem_row + ((s - 1) & 1) * W + c0, acc);
+            const float4 bb = *reinterpret_cast<const float4*>(s_bh + (s - 1) * W + c0);
             float x0, x1, x2, x3;
-            unpack2(add2(pack2(__uint_as_float(acc[j4 * 4]), __uint_as_float(acc[j4 * 4 + 1])), pack2(bb.x, bb.y)), x0, x1);
-            unpack2(add2(pack2(__uint_as_float(acc[j4 * 4 + 2]), __uint_as_float(acc[j4 * 4 + 3])), pack2(bb.z, bb.w)), x2, x3);
-            swish2(x0, x1, h[j4 * 4], h[j4 * 4 + 1]);
-            swish2(x2, x3, h[j4 * 4 + 2], h[j4 * 4 + 3]);
+            unpack2(add2(pack2(__uint_as_float(acc[0]), __uint_as_float(acc[1])), pack2(bb.x, bb.y)), x0, x1);
+            unpack2(add2(pack2(__uint_as_float(acc[2]), __uint_as_float(acc[3])), pack2(bb.z, bb.w)), x2, x3);
+            swish2(x0, x1, h[0], h[1]);
+            swish2(x2, x3, h[2], h[3]);
           }
-        }
-        ATCW_CLK(s == 0 ? 0 : (to_mma ? 3 : 6));          // compute of the stage
-        if (!to_mma) {          // output layer on the CUDA cores, float32: this quarter's partial
-#pragma unroll
-          for (int i = 0; i < QC; i += 2) {
-            const float4 wo = *reinterpret_cast<const float4*>(s_wo + (q * QC + i) * 2);
-            pl = fmaf(h[i], wo.x, pl);
-            ps = fmaf(h[i], wo.y, ps);
-            pl = fmaf(h[i + 1], wo.z, pl);
-            ps = fmaf(h[i + 1], wo.w, ps);
-          }
-          ATCW_CLK(7);
-          break;
-        }
-        // ---- hi / lo planes of the 16 columns into slot q (free: layer_done of its last readers was waited for) --
-#pragma unroll
-        for (int j4 = 0; j4 < QC / 4; ++j4) {
+          // hi / lo planes of the chunk into slot j (free: layer_done of its last readers was waited for)
           float hi[4], lo[4];
-          split_tf32_2(h[j4 * 4], h[j4 * 4 + 1], hi[0], hi[1], lo[0], lo[1]);
-          split_tf32_2(h[j4 * 4 + 2], h[j4 * 4 + 3], hi[2], hi[3], lo[2], lo[3]);
-          *reinterpret_cast<float4*>(slot_dst + j4 * A_LBO_) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<float4*>(slot_dst + SLOT_PLANE + j4 * A_LBO_) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+          split_tf32_2(h[0], h[1], hi[0], hi[1], lo[0], lo[1]);
+          split_tf32_2(h[2], h[3], hi[2], hi[3], lo[2], lo[3]);
+          uint8_t* dst = chunk_dst + j * SLOT_BYTES;
+          *reinterpret_cast<float4*>(dst) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<float4*>(dst + SLOT_PLANE) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+          fence_proxy_async();      // generic-proxy writes of A -> visible to the tensor core
+          tc_fence_before();        // and this thread's accumulator reads are ordered before the MMAs they feed
+          __syncwarp();
+          if (lane == 0) mbar_arrive_a(bar0 + j * 8u);
         }
-        fence_proxy_async();      // generic-proxy writes of A -> visible to the tensor core
-        tc_fence_before();        // and this thread's accumulator reads are ordered before the MMAs they feed
-        __syncwarp();
-        if (lane == 0) mbar_arrive_a(full_bar);
-        ATCW_CLK(s == 0 ? 1 : 4);                          // split + stores + fences + arrive
+        ATCW_CLK(s == 0 ? 0 : 3);                          // production of the stage
         mbar_wait_a(bar0 + BAR_LAYER_W, layer_phase);
         layer_phase ^= 1u;
         tc_fence_after();
         ATCW_CLK(s == 0 ? 2 : 5);                          // MMA wait
+      }
+      {
+        // ---- output layer on the CUDA cores, float32: thread q folds the contiguous columns [16 q, 16 q + 16) of the
+        // last hidden layer into a partial, as the four-tile kernel does per quarter
+        float h[QC];
+        const float* bias = s_bh + (HH - 1) * W + q * QC;
+        uint32_t acc[QC];
+        tmem_ldq(tmem_row + ((HH - 1) & 1) * W + q * QC, acc);
+#pragma unroll
+        for (int j4 = 0; j4 < QC / 4; ++j4) {
+          const float4 bb = *reinterpret_cast<const float4*>(bias + j4 * 4);
+          float x0, x1, x2, x3;
+          unpack2(add2(pack2(__uint_as_float(acc[j4 * 4]), __uint_as_float(acc[j4 * 4 + 1])), pack2(bb.x, bb.y)), x0, x1);
+          unpack2(add2(pack2(__uint_as_float(acc[j4 * 4 + 2]), __uint_as_float(acc[j4 * 4 + 3])), pack2(bb.z, bb.w)), x2, x3);
+          swish2(x0, x1, h[j4 * 4], h[j4 * 4 + 1]);
+          swish2(x2, x3, h[j4 * 4 + 2], h[j4 * 4 + 3]);
+        }
+        ATCW_CLK(6);
+#pragma unroll
+        for (int i = 0; i < QC; i += 2) {
+          const float4 wo = *reinterpret_cast<const float4*>(s_wo + (q * QC + i) * 2);
+          pl = fmaf(h[i], wo.x, pl);
+          ps = fmaf(h[i], wo.y, ps);
+          pl = fmaf(h[i + 1], wo.z, pl);
+          ps = fmaf(h[i + 1], wo.w, ps);
+        }
+        ATCW_CLK(7);
       }
       // ---- the four partials of a row meet in its q = 0 thread -----------------------------------------------------
       if (q != 0) {
