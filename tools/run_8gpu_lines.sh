@@ -4,7 +4,8 @@ N=${1:-8}
 OUT=gpurun_out/bench_${N}gpu.jsonl
 : > $OUT
 port=29520
-for wl in config2_batched_icem config3_env_rollouts config3_actor_rollouts config3_collect_experience; do
+WLS=${2:-"config2_batched_icem config3_env_rollouts config3_actor_rollouts config3_collect_experience"}
+for wl in $WLS; do
   port=$((port + 1))
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $port \
     bench.py --gpus $N --workload $wl --steps 20 --warmup 3 --no-cpu-baseline >> $OUT 2>> gpurun_out/bench_${N}gpu.err
