@@ -451,6 +451,18 @@ int mbpo_normalizer_inverse(const float* batch /*[n_rows, X]*/, long long n_rows
 int mbpo_replay_take(const MbpoReplayState* state_host, const int32_t* idx /*[n]*/, long long n,
                      float* rows_out /*[n, D]*/, void* stream);
 
+/* PPO's generalised advantage estimation over the Transition of an unroll
+ * (mbpo/optimizers/policy_optimizers/ppo/losses.py:128-184 compute_gae; call site :87-99): per env, one reverse scan
+ *   deltas = (rewards + discount * (1 - termination) * values[t+1] - values) * (1 - truncation)
+ *   acc    = deltas + discount * (1 - termination) * (1 - truncation) * lambda * acc
+ *   vs     = acc + values;   advantages = (rewards + discount * (1 - termination) * vs[t+1] - values) * (1 - truncation)
+ * with values[T] = vs[T] = bootstrap_value, every product and sum rounded once in the order written (python floats are
+ * weakly typed: discount and lambda are rounded to float32).  All [T, E] arrays share (stride_t, stride_e); both
+ * outputs are stop_gradient in the reference, so there is no transpose. */
+int mbpo_compute_gae(const float* truncation, const float* termination, const float* rewards, const float* values,
+                     const float* bootstrap_value /*[E]*/, int E, int T, long long stride_t, long long stride_e,
+                     double discount, double lambda_, float* vs_out, float* advantages_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -369,6 +369,32 @@ __global__ void replay_take_kernel(const float* __restrict__ data, long long cap
   out[i] = data[p * D + c];
 }
 
+// PPO's GAE: one thread per env, one reverse pass, six [T, E] streams (a line per warp per step).
+__global__ void compute_gae_kernel(const float* __restrict__ truncation, const float* __restrict__ termination,
+                                   const float* __restrict__ rewards, const float* __restrict__ values,
+                                   const float* __restrict__ bootstrap, int E, int T, long long st_t, long long st_e,
+                                   float discount, float lambda_, float* __restrict__ vs_out,
+                                   float* __restrict__ adv_out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const long long base = e * st_e;
+  float v_next = bootstrap[e], vs_next = v_next, acc = 0.0f;
+#pragma unroll 4
+  for (int t = T - 1; t >= 0; --t) {
+    const long long i = base + t * st_t;
+    const float tm = __fsub_rn(1.0f, __ldcs(truncation + i));
+    const float dn = __fmul_rn(discount, __fsub_rn(1.0f, __ldcs(termination + i)));   // discount * (1 - termination)
+    const float r = __ldcs(rewards + i), v = __ldcs(values + i);
+    const float delta = __fmul_rn(__fsub_rn(__fadd_rn(r, __fmul_rn(dn, v_next)), v), tm);                    // :160-161
+    acc = __fadd_rn(delta, __fmul_rn(__fmul_rn(__fmul_rn(dn, tm), lambda_), acc));                           // :169
+    const float vs = __fadd_rn(acc, v);                                                                      // :178
+    adv_out[i] = __fmul_rn(__fsub_rn(__fadd_rn(r, __fmul_rn(dn, vs_next)), v), tm);                          // :182-183
+    vs_out[i] = vs;
+    v_next = v;
+    vs_next = vs;
+  }
+}
+
 int check_state(const MbpoReplayState* s, const char* who) {
   MBPO_REQUIRE(s != nullptr, "%s: state is null", who);
   MBPO_REQUIRE(s->data != nullptr, "%s: data is null", who);
@@ -632,6 +658,20 @@ int mbpo_replay_take(const MbpoReplayState* s, const int32_t* idx, long long n, 
   replay_take_kernel<<<static_cast<unsigned>(blocks), threads, 0, as_stream(stream)>>>(
       s->data, s->capacity, s->row_width, s->head, idx, total, rows_out);
   return check_launch("replay_take_kernel");
+}
+
+int mbpo_compute_gae(const float* truncation, const float* termination, const float* rewards, const float* values,
+                     const float* bootstrap_value, int E, int T, long long stride_t, long long stride_e,
+                     double discount, double lambda_, float* vs_out, float* advantages_out, void* stream) {
+  MBPO_REQUIRE(E >= 0 && T >= 0, "compute_gae: negative size");
+  if (E == 0 || T == 0) return MBPO_OK;
+  MBPO_REQUIRE(truncation && termination && rewards && values && bootstrap_value && vs_out && advantages_out,
+               "compute_gae: null pointer");
+  const int threads = 128;
+  compute_gae_kernel<<<(E + threads - 1) / threads, threads, 0, as_stream(stream)>>>(
+      truncation, termination, rewards, values, bootstrap_value, E, T, stride_t, stride_e,
+      static_cast<float>(discount), static_cast<float>(lambda_), vs_out, advantages_out);
+  return check_launch("compute_gae_kernel");
 }
 
 }  // extern "C"

@@ -141,6 +141,7 @@ SIGNATURES = {
     "mbpo_normalizer_finalize": (_I, [_P, _I, _P, _P, _P, _F, _P, _P, _P, _P]),
     "mbpo_normalizer_inverse": (_I, [_P, _LL, _I, _P, _P, _P, _P]),
     "mbpo_replay_take": (_I, [C.POINTER(ReplayStateC), _P, _LL, _P, _P]),
+    "mbpo_compute_gae": (_I, [_P, _P, _P, _P, _P, _I, _I, _LL, _LL, C.c_double, C.c_double, _P, _P, _P]),
     "mbpo_eval_metrics": (_I, [_P, _P, _P, _P, _I, _I, _I, _LL, _LL, _P, _P, _P, _P]),
     "mbpo_env_reset_from_buffer": (_I, [C.POINTER(ReplayStateC), _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
 }

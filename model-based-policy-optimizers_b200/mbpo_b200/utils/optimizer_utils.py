@@ -190,3 +190,22 @@ def lambda_return_vjp(g_returns: torch.Tensor, discount: float, lambda_: float):
                                                    float(lambda_), g_r.data_ptr(), g_nv.data_ptr(),
                                                    _lib.stream_ptr(g.device)))
     return g_r.reshape(g_returns.shape), g_nv.reshape(g_returns.shape)
+
+
+def compute_gae(truncation: torch.Tensor, termination: torch.Tensor, rewards: torch.Tensor, values: torch.Tensor,
+                bootstrap_value: torch.Tensor, lambda_: float = 1.0, discount: float = 0.99):
+    """PPO's generalised advantage estimation (ppo/losses.py:128-184 ``compute_gae``; brax's argument order with
+    ``self.gae_lambda`` / ``self.discounting`` as keywords): [T, B] inputs (time-major, as the loss makes them at
+    :78) and ``bootstrap_value`` [B] -> (vs [T, B], advantages [T, B]), both stop-gradient.  One reverse pass per
+    env in one launch; every product and sum is rounded once in the order the reference writes them."""
+    tr = truncation.to(torch.float32)
+    T, B = tr.shape
+    tr = tr.contiguous()
+    te, r, v = (x.to(torch.float32).contiguous() for x in (termination, rewards, values))
+    bv = bootstrap_value.to(torch.float32).contiguous()
+    vs, adv = torch.empty_like(tr), torch.empty_like(tr)
+    with _lib.cuda_guard(tr):
+        _lib.check(_lib.lib.mbpo_compute_gae(_lib.ptr(tr), _lib.ptr(te), _lib.ptr(r), _lib.ptr(v), _lib.ptr(bv), B, T, B, 1,
+                                             float(discount), float(lambda_), _lib.ptr(vs), _lib.ptr(adv),
+                                             _lib.stream_ptr(tr.device)))
+    return vs, adv

@@ -172,3 +172,24 @@ def normalizer_update(x, state, accumulate=np.float64):
                + F(state["size"]) * np.square(state["mean"] - new_mean)).astype(F)
     new_std = np.sqrt(new_s_n / F(total)).astype(F)
     return dict(mean=new_mean, std=np.maximum(new_std, F(1e-8)), size=total)
+
+
+def compute_gae(truncation, termination, rewards, values, bootstrap_value, lambda_=1.0, discount=0.99):
+    """ppo/losses.py:128-184 compute_gae as written, float32 ([T, B] time-major; python floats weakly typed)."""
+    F = np.float32
+    truncation, termination, rewards, values = (np.asarray(x, F) for x in (truncation, termination, rewards, values))
+    bootstrap_value = np.asarray(bootstrap_value, F)
+    d, lam = F(discount), F(lambda_)
+    truncation_mask = (F(1) - truncation).astype(F)
+    values_t_plus_1 = np.concatenate([values[1:], bootstrap_value[None]], axis=0)
+    dn = (d * (F(1) - termination).astype(F)).astype(F)
+    deltas = (((rewards + (dn * values_t_plus_1).astype(F)).astype(F) - values).astype(F) * truncation_mask).astype(F)
+    acc = np.zeros_like(bootstrap_value)
+    out = np.empty_like(values)
+    for t in range(values.shape[0] - 1, -1, -1):
+        acc = (deltas[t] + ((((dn[t] * truncation_mask[t]).astype(F)) * lam).astype(F) * acc).astype(F)).astype(F)
+        out[t] = acc
+    vs = (out + values).astype(F)
+    vs_t_plus_1 = np.concatenate([vs[1:], bootstrap_value[None]], axis=0)
+    advantages = (((rewards + (dn * vs_t_plus_1).astype(F)).astype(F) - values).astype(F) * truncation_mask).astype(F)
+    return vs, advantages

@@ -104,6 +104,7 @@ def test_error_codes_without_gpu(mb):
     assert L.lib.mbpo_running_statistics_accumulate(None, 4, 3, None, None, 0, None, None) == L.MBPO_EINVAL
     assert L.lib.mbpo_running_statistics_accumulate(0x1000, 4, 3, 0x1000, 0x1000, 8, 0x1000, None) == L.MBPO_EWORKSPACE
     assert L.lib.mbpo_running_statistics_finalize(None, 3, None, None, None, 1e-6, 1e6, None, None, None, None, None) == L.MBPO_EINVAL
+    assert L.lib.mbpo_compute_gae(None, None, None, None, None, 4, 4, 4, 1, 0.99, 0.95, None, None, None) == L.MBPO_EINVAL
     assert L.lib.mbpo_eval_metrics(None, None, None, None, 1, 4, 4, 4, 1, None, None, None, None) == L.MBPO_EINVAL
     with pytest.raises(mb.MbpoError):
         L.check(L.MBPO_EINVAL)
@@ -177,6 +178,9 @@ def test_api_surface_matches_reference(mb):
         "self", "system", "system_params", "sample_buffer_state", "sample_buffer"]
     assert list(inspect.signature(BraxWrapper.reset).parameters) == ["self", "rng"]
     assert list(inspect.signature(BraxWrapper.step).parameters) == ["self", "state", "action"]
+    from mbpo_b200.utils import compute_gae
+    assert list(inspect.signature(compute_gae).parameters) == [                          # ppo/losses.py:128-134 (+ brax's keywords)
+        "truncation", "termination", "rewards", "values", "bootstrap_value", "lambda_", "discount"]
     assert list(inspect.signature(acting.Evaluator.__init__).parameters) == [            # sac/acting.py:85-88
         "self", "eval_env", "eval_policy_fn", "num_eval_envs", "episode_length", "action_repeat", "key"]
     assert list(inspect.signature(acting.Evaluator.run_evaluation).parameters) == [      # :118-122

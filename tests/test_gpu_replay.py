@@ -552,3 +552,22 @@ def test_graphed_rollout_replays_the_same_bits(mb, cuda_device):
                      (gtr.discount, tr.discount), (gtr.next_observation, tr.next_observation),
                      (gtr.extras["state_extras"]["truncation"], tr.extras["state_extras"]["truncation"])):
             assert torch.equal(a, b), it
+
+
+@pytest.mark.parametrize("T,B", [(1, 1), (5, 33), (20, 2048), (200, 300)])
+def test_compute_gae_bit_exact(mb, cuda_device, T, B):
+    """ppo/losses.py:128-184 on the Transition of an unroll: elementwise float32 operations in the reference's order,
+    so the scan is bit-exact against the oracle."""
+    from mbpo_b200.utils import compute_gae
+    rng = np.random.default_rng(T * 1000 + B)
+    r = rng.standard_normal((T, B)).astype(np.float32)
+    v = rng.standard_normal((T, B)).astype(np.float32) * 3
+    boot = rng.standard_normal(B).astype(np.float32)
+    trunc = (rng.random((T, B)) < 0.05).astype(np.float32)
+    done = np.maximum(trunc, (rng.random((T, B)) < 0.05).astype(np.float32))
+    discount_field = 1 - done                                      # Transition.discount = 1 - done
+    term = ((1 - discount_field) * (1 - trunc)).astype(np.float32)  # losses.py:89
+    for lam, d in ((0.95, 0.99), (1.0, 0.9), (0.0, 0.99)):
+        vs, adv = compute_gae(*[_dev(x, cuda_device) for x in (trunc, term, r, v, boot)], lambda_=lam, discount=d)
+        want_vs, want_adv = obr.compute_gae(trunc, term, r, v, boot, lam, d)
+        assert np.array_equal(vs.cpu().numpy(), want_vs) and np.array_equal(adv.cpu().numpy(), want_adv)

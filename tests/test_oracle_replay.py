@@ -152,3 +152,26 @@ def test_bptt_normalizer_matches_plain_mean_and_std():
         np.testing.assert_allclose(st["mean"], seen.mean(0, dtype=np.float64), rtol=2e-5, atol=1e-6)
         if len(seen) > 1:
             np.testing.assert_allclose(st["std"], seen.std(0, dtype=np.float64), rtol=2e-5, atol=1e-6)
+
+
+def test_compute_gae_reduces_to_discounted_returns():
+    """lambda = 1, no truncation / termination: vs_t = sum_k discount^k r_{t+k} + discount^(T-t) bootstrap, and the
+    advantage is vs_t - V_t' (one-step form on vs); a termination cuts the bootstrap, a truncation zeroes the delta."""
+    rng = np.random.default_rng(0)
+    T, B, d = 12, 5, 0.9
+    r = rng.standard_normal((T, B)).astype(np.float32)
+    v = rng.standard_normal((T, B)).astype(np.float32)
+    boot = rng.standard_normal(B).astype(np.float32)
+    z = np.zeros((T, B), np.float32)
+    vs, adv = br.compute_gae(z, z, r, v, boot, lambda_=1.0, discount=d)
+    want = np.zeros((T + 1, B)); want[T] = boot
+    for t in range(T - 1, -1, -1):
+        want[t] = r[t] + d * want[t + 1]
+    np.testing.assert_allclose(vs, want[:T], rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(adv, r + d * want[1:] - v, rtol=2e-5, atol=2e-5)
+    term = z.copy(); term[7] = 1.0                      # episode ends after step 7: nothing flows back across it
+    vs2, _ = br.compute_gae(z, term, r, v, boot, lambda_=1.0, discount=d)
+    np.testing.assert_allclose(vs2[7], r[7], rtol=1e-6, atol=1e-6)
+    trunc = z.copy(); trunc[3] = 1.0                    # truncated step: delta and advantage masked
+    vs3, adv3 = br.compute_gae(trunc, z, r, v, boot, lambda_=0.95, discount=d)
+    assert np.all(adv3[3] == 0) and np.array_equal(vs3[3], v[3])
