@@ -42,7 +42,16 @@ static_assert(QC == 16 && QUARTERS == 4, "the wide kernel splits a row into four
 constexpr int PRODUCERS = TILE * QUARTERS;        // 512
 constexpr int PRNG_THREADS = TILE;                // 128
 constexpr int WTHREADS = PRODUCERS + PRNG_THREADS + 32;   // + the issuer warp = 672
-constexpr int WTMEM_COLS = 2 * W;                 // two 64-column accumulators
+#ifndef MBPO_ATCW_A_TMEM
+#define MBPO_ATCW_A_TMEM 0
+#endif
+// Experiment (-DMBPO_ATCW_A_TMEM=1): A operand in tensor memory -- the producers write the hi / lo planes with
+// tcgen05.st next to the accumulators and the MMAs read them from there (no shared-memory stores, no generic -> async
+// proxy fence per slice).  Same bits; measured 4.55-4.62 us per step against 4.50-4.58 us through shared memory
+// (tcgen05.st + wait::st cost what st.shared + the proxy fence cost), so shared memory stays the default.
+constexpr bool A_TMEM = MBPO_ATCW_A_TMEM != 0;
+constexpr int WTMEM_COLS = A_TMEM ? 4 * W : 2 * W;   // two 64-column accumulators (+ A hi, A lo: 64 columns each)
+constexpr uint32_t TM_A_HI = 2 * W, TM_A_LO = 3 * W;
 constexpr int STEP_BAR = 1, PART_BAR = 2, EPS_BAR = 3;    // named barriers
 
 struct WSmem {
@@ -68,6 +77,22 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
                : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, float a, float b, float c, float d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(a)),
+               "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d))
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 __device__ __forceinline__ void named_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
@@ -175,9 +200,16 @@ __global__ void __launch_bounds__(WTHREADS, 1) actor_rollout_tc_wide_kernel(cons
 #pragma unroll
             for (int j = 0; j < QC / 8; ++j) {
               const uint64_t ao = static_cast<uint64_t>((j * 2 * A_LBO_) >> 4), bo = static_cast<uint64_t>((j * 2 * W_LBO_) >> 4);
-              umma_tf32_ss(d, a_lo + ao, b_hi + bo, IDESC, (qd | j) ? 1u : 0u);     // small terms first
-              umma_tf32_ss(d, a_hi + ao, b_lo + bo, IDESC, 1u);
-              umma_tf32_ss(d, a_hi + ao, b_hi + bo, IDESC, 1u);
+              if (A_TMEM) {
+                const uint32_t col = static_cast<uint32_t>(qd * QC + j * 8);      // K-step: 8 columns of A
+                umma_tf32_ts(d, tmem_base + TM_A_LO + col, b_hi + bo, IDESC, (qd | j) ? 1u : 0u);   // small terms first
+                umma_tf32_ts(d, tmem_base + TM_A_HI + col, b_lo + bo, IDESC, 1u);
+                umma_tf32_ts(d, tmem_base + TM_A_HI + col, b_hi + bo, IDESC, 1u);
+              } else {
+                umma_tf32_ss(d, a_lo + ao, b_hi + bo, IDESC, (qd | j) ? 1u : 0u);     // small terms first
+                umma_tf32_ss(d, a_hi + ao, b_lo + bo, IDESC, 1u);
+                umma_tf32_ss(d, a_hi + ao, b_hi + bo, IDESC, 1u);
+              }
             }
           }
           umma_commit_a(bar0 + BAR_LAYER_W);             // accumulator s & 1 complete, every slot read
@@ -293,11 +325,17 @@ __global__ void __launch_bounds__(WTHREADS, 1) actor_rollout_tc_wide_kernel(cons
           float hi[4], lo[4];
           split_tf32_2(h[0], h[1], hi[0], hi[1], lo[0], lo[1]);
           split_tf32_2(h[2], h[3], hi[2], hi[3], lo[2], lo[3]);
-          uint8_t* dst = chunk_dst + j * SLOT_BYTES;
-          *reinterpret_cast<float4*>(dst) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<float4*>(dst + SLOT_PLANE) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-          fence_proxy_async();      // generic-proxy writes of A -> visible to the tensor core
-          tc_fence_before();        // and this thread's accumulator reads are ordered before the MMAs they feed
+          if (A_TMEM) {
+            tmem_st4(tmem_row + TM_A_HI + c0, hi[0], hi[1], hi[2], hi[3]);
+            tmem_st4(tmem_row + TM_A_LO + c0, lo[0], lo[1], lo[2], lo[3]);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          } else {
+            uint8_t* dst = chunk_dst + j * SLOT_BYTES;
+            *reinterpret_cast<float4*>(dst) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(dst + SLOT_PLANE) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            fence_proxy_async();    // generic-proxy writes of A -> visible to the tensor core
+          }
+          tc_fence_before();        // this thread's tensor-memory accesses are ordered before the MMAs they feed
           __syncwarp();
           if (lane == 0) mbar_arrive_a(bar0 + j * 8u);
         }
