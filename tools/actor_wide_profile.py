@@ -1,4 +1,6 @@
-"""Builds the library with -DMBPO_ATCW_PROFILE into a scratch .so and prints the wide actor kernel's phase clocks."""
+"""Two launches of the wide (latency) actor kernel at a given env count.  With the library built by
+`MBPO_EXTRA_NVCC_FLAGS=-DMBPO_ATCW_PROFILE python model-based-policy-optimizers_b200/build.py --force` the kernel prints
+its per-step phase clocks (clock64); it is also the target of the ncu capture in profiles/."""
 import os, subprocess, sys
 import numpy as np
 import torch
