@@ -571,3 +571,60 @@ def test_compute_gae_bit_exact(mb, cuda_device, T, B):
         vs, adv = compute_gae(*[_dev(x, cuda_device) for x in (trunc, term, r, v, boot)], lambda_=lam, discount=d)
         want_vs, want_adv = obr.compute_gae(trunc, term, r, v, boot, lam, d)
         assert np.array_equal(vs.cpu().numpy(), want_vs) and np.array_equal(adv.cpu().numpy(), want_adv)
+
+
+def test_kernels_reproduce_the_replay_golden_vectors(mb, cuda_device, prng_mode):
+    """The committed fixture tests/golden/replay_golden.npz through the CUDA path: randint words, the queue's insert /
+    sample history with the ring wrapping, BraxWrapper.reset draws (bit for bit), the two normalisers (rel 1e-5), the
+    evaluation metrics and PPO's GAE (bit for bit)."""
+    import os
+    from mbpo_b200 import acting, running_statistics as rs
+    from mbpo_b200.envs import EnvState
+    from mbpo_b200.replay_buffers import UniformSamplingQueue
+    from mbpo_b200.systems import BraxWrapper, PendulumSystem
+    from mbpo_b200.utils import compute_gae
+    from mbpo_b200.utils.optimizer_utils import Transition
+    dev = cuda_device
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "replay_golden.npz"))
+    tag = "part" if prng_mode else "legacy"
+    for s, (lo, hi) in enumerate([(0, 10), (-5, 5), (0, 65537), (3, 3)]):
+        got = mb.random.randint(_dev(ojr.PRNGKey(s), dev), 16, lo, hi)
+        assert np.array_equal(got.cpu().numpy(), g["randint_%s" % tag][s])
+    q = UniformSamplingQueue(32, _sac_dummy(mb, dev), 8)
+    st = q.init(_dev(ojr.PRNGKey(7), dev))
+    for k in range(5):
+        r = _dev(g["rows_%d" % k], dev)
+        tr = Transition(r[:, 0:3], r[:, 3:4], r[:, 4], r[:, 5], r[:, 6:9],
+                        {"state_extras": {"truncation": r[:, 9]}, "policy_extras": {}})
+        st = q.insert(st, tr)
+        st, batch, idx = q.sample_with_indices(st)
+        assert np.array_equal(idx.cpu().numpy(), g["q_%s_%d_idx" % (tag, k)])
+        assert np.array_equal(_rows_of(batch, 8), g["q_%s_%d_batch" % (tag, k)])
+        assert np.array_equal(st.key.cpu().numpy(), g["q_%s_%d_key" % (tag, k)])
+        assert [st.insert_position, st.sample_position] == g["q_%s_%d_positions" % (tag, k)].tolist()
+    assert np.array_equal(st.data.cpu().numpy(), g["q_%s_data" % tag])
+    system = PendulumSystem()
+    one = UniformSamplingQueue(32, _sac_dummy(mb, dev), 1)
+    env = BraxWrapper(system, system.init_params(_dev(ojr.PRNGKey(1), dev)), st, one)
+    state = env.reset(_dev(g["reset_%s_rngs" % tag], dev))
+    assert np.array_equal(state.obs.cpu().numpy(), g["reset_%s_obs" % tag])
+    assert np.array_equal(state.reward.cpu().numpy(), g["reset_%s_reward" % tag])
+    assert np.array_equal(state.system_params.key.cpu().numpy(), g["reset_%s_keys" % tag])
+    stats, nz = rs.init_state(3, dev), rs.Normalizer((3,), dev)
+    norm = nz.initialize_normalizer_state()
+    for k in range(6):
+        o = _dev(g["obs"][k], dev)
+        stats, norm = rs.update(stats, o), nz.update(o, norm)
+        got = torch.cat([stats.count.reshape(1), stats.mean, stats.summed_variance, stats.std]).cpu().numpy()
+        np.testing.assert_allclose(got, g["stats_%d" % k], rtol=1e-5, atol=1e-6)
+        got = torch.cat([norm.size.reshape(1).float(), norm.mean, norm.std]).cpu().numpy()
+        np.testing.assert_allclose(got, g["norm_%d" % k], rtol=1e-5, atol=1e-6)
+    vs, adv = compute_gae(*[_dev(g["gae_" + k], dev) for k in ("truncation", "termination", "reward", "values",
+                                                                "bootstrap")], lambda_=0.95, discount=0.99)
+    assert np.array_equal(vs.cpu().numpy(), g["gae_vs"]) and np.array_equal(adv.cpu().numpy(), g["gae_advantages"])
+    z = torch.zeros(9, device=dev)
+    st0 = EnvState(obs=None, reward=None, done=z, system_params=None, info={"steps": z})
+    er, es, ea = acting.eval_metrics(st0, Transition(None, None, _dev(g["gae_reward"], dev), _dev(g["gae_discount"], dev),
+                                                     None), 1)
+    assert np.array_equal(er.cpu().numpy(), g["eval_reward"]) and np.array_equal(es.cpu().numpy(), g["eval_steps"])
+    assert np.array_equal(ea.cpu().numpy(), g["eval_active"])

@@ -175,3 +175,32 @@ def test_compute_gae_reduces_to_discounted_returns():
     trunc = z.copy(); trunc[3] = 1.0                    # truncated step: delta and advantage masked
     vs3, adv3 = br.compute_gae(trunc, z, r, v, boot, lambda_=0.95, discount=d)
     assert np.all(adv3[3] == 0) and np.array_equal(vs3[3], v[3])
+
+
+def test_oracle_reproduces_the_replay_golden_vectors():
+    """tests/golden/replay_golden.npz (made by make_golden_replay.py) freezes the oracle's answers: integer / byte
+    results bit for bit, the float statistics exactly too (same NumPy operations)."""
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_golden_replay as mg
+    g = np.load(os.path.join(here, "golden", "replay_golden.npz"))
+    rows, obs, gae = mg.inputs()
+    assert np.array_equal(g["obs"], obs) and all(np.array_equal(g["rows_%d" % k], r) for k, r in enumerate(rows))
+    for tag, part in (("legacy", False), ("part", True)):
+        got = np.stack([jp.randint(jp.PRNGKey(s), 16, lo, hi, part)
+                        for s, (lo, hi) in enumerate([(0, 10), (-5, 5), (0, 65537), (3, 3)])])
+        assert np.array_equal(got, g["randint_%s" % tag])
+        q = br.UniformSamplingQueue(32, 10, mg.BATCH, part)
+        st = q.init(jp.PRNGKey(7))
+        for k, r in enumerate(rows):
+            st = q.insert(st, r)
+            st, batch, idx = q.sample(st)
+            assert np.array_equal(idx, g["q_%s_%d_idx" % (tag, k)]) and np.array_equal(batch, g["q_%s_%d_batch" % (tag, k)])
+            assert np.array_equal(st.key, g["q_%s_%d_key" % (tag, k)])
+            assert [st.insert_position, st.sample_position] == g["q_%s_%d_positions" % (tag, k)].tolist()
+        assert np.array_equal(st.data, g["q_%s_data" % tag])
+    vs, adv = br.compute_gae(gae["truncation"], g["gae_termination"], gae["reward"], gae["values"], gae["bootstrap"],
+                             0.95, 0.99)
+    assert np.array_equal(vs, g["gae_vs"]) and np.array_equal(adv, g["gae_advantages"])
