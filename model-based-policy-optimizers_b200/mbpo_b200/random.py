@@ -70,11 +70,17 @@ def normal(key: torch.Tensor, n: int) -> torch.Tensor:
     return out
 
 
-def randint(key: torch.Tensor, n: int, minval: int, maxval: int) -> torch.Tensor:
-    """jax.random.randint(key, (n,), minval, maxval) (int32)."""
+def randint(key: torch.Tensor, n, minval: int, maxval: int) -> torch.Tensor:
+    """jax.random.randint(key, shape, minval, maxval) (int32).  ``n``: an int (shape ``(n,)``) or a shape tuple -- JAX
+    draws the words of a multi-dimensional shape in row-major order, so ``shape=(a, b)`` is the ``a * b`` draw reshaped
+    (bptt_optimizer.py:389-391 ``transition_indices``)."""
     key = _as_keys(key)
-    out = torch.empty(key.shape[:-1] + (n,), dtype=torch.int32, device=key.device)
+    shape = (int(n),) if isinstance(n, int) else tuple(int(d) for d in n)
+    count = 1
+    for d in shape:
+        count *= d
+    out = torch.empty(key.shape[:-1] + (count,), dtype=torch.int32, device=key.device)
     with _lib.cuda_guard(key):
-        _lib.check(_lib.lib.mbpo_prng_randint(_lib.ptr(key), key.numel() // 2, n, config.prng_mode, int(minval),
+        _lib.check(_lib.lib.mbpo_prng_randint(_lib.ptr(key), key.numel() // 2, count, config.prng_mode, int(minval),
                                               int(maxval), _lib.ptr(out), _lib.stream_ptr(key.device)))
-    return out
+    return out.reshape(key.shape[:-1] + shape)

@@ -64,6 +64,9 @@ def test_randint_bit_exact(mb, cuda_device, prng_mode, minval, maxval):
         got = mb.random.randint(_dev(keys, cuda_device), n, minval, maxval).cpu().numpy()
         want = np.stack([ojr.randint(k, n, minval, maxval, prng_mode) for k in keys])
         assert got.dtype == np.int32 and np.array_equal(got, want)
+    # a shape tuple is the flat draw reshaped (bptt_optimizer.py:389-391: shape=(updates, batch_size))
+    got = mb.random.randint(_dev(keys[0], cuda_device), (4, 16), minval, maxval).cpu().numpy()
+    assert got.shape == (4, 16) and np.array_equal(got.reshape(-1), ojr.randint(keys[0], 64, minval, maxval, prng_mode))
 
 
 @pytest.mark.parametrize("layout", ["sac", "true"])
