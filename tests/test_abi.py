@@ -124,6 +124,25 @@ def test_no_cpu_fallback(mb):
         PendulumSystem().step(torch.zeros(3), torch.zeros(1), SystemParams())
     with pytest.raises(mb.MbpoError):
         mb.random.split(torch.zeros(2, dtype=torch.uint32))
+    # the replay queue, the normalisers, GAE and the evaluation metrics have no CPU path either
+    from mbpo_b200 import running_statistics as rs
+    from mbpo_b200.replay_buffers import UniformSamplingQueue
+    from mbpo_b200.utils import compute_gae
+    from mbpo_b200.utils.optimizer_utils import Transition
+    z = torch.zeros
+    q = UniformSamplingQueue(8, Transition(z(3), z(1), z(()), z(()), z(3)), 2)
+    assert q.row_width == 9
+    st = q.init(torch.zeros(2, dtype=torch.int32).view(torch.uint32))      # host tensors: every launch refuses them
+    with pytest.raises(mb.MbpoError):
+        q.insert(st, Transition(z(4, 3), z(4, 1), z(4), z(4), z(4, 3)))
+    with pytest.raises(mb.MbpoError):
+        q.sample(st)
+    with pytest.raises(mb.MbpoError):
+        rs.init_state(3)
+    with pytest.raises(mb.MbpoError):
+        rs.update(rs.RunningStatisticsState(z(()), z(3), z(3), torch.ones(3)), z(5, 3))
+    with pytest.raises(mb.MbpoError):
+        compute_gae(z(4, 2), z(4, 2), z(4, 2), z(4, 2), z(2))
     opt = iCemTO(horizon=20, action_dim=1, opt_params=iCemParams())
     opt.set_system(PendulumSystem())
     cfg = opt._cfg()                                   # host-only: allowed
