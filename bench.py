@@ -1059,7 +1059,7 @@ def run_collect(args):
         torch.cuda.synchronize(dev)
 
     for _ in range(max(args.warmup, 3)):
-        norm, state, buf, key = col.get_experience(norm, params, state, buf, key)
+        norm, state, buf = col.get_experience(norm, params, state, buf, key); key = col.last_key
     steps = min(args.steps, 20)
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
@@ -1067,7 +1067,7 @@ def run_collect(args):
         barrier()
         for k in range(steps):
             starts[k].record()
-            norm, state, buf, key = col.get_experience(norm, params, state, buf, key)
+            norm, state, buf = col.get_experience(norm, params, state, buf, key); key = col.last_key
             ends[k].record()
         barrier()
     ms = sum(a.elapsed_time(b) for a, b in zip(starts, ends)) / steps
@@ -1083,7 +1083,7 @@ def run_collect(args):
     for k in range(steps):
         params = acting.PolicyParams([w.to(dev, non_blocking=True) for w in w_host],
                                      [b.to(dev, non_blocking=True) for b in b_host])
-        norm, state, buf, key = col.get_experience(norm, params, state, buf, key)
+        norm, state, buf = col.get_experience(norm, params, state, buf, key); key = col.last_key
         stats_host[:3].copy_(norm.mean, non_blocking=True)
         stats_host[3:6].copy_(norm.std, non_blocking=True)
         stats_host[6:].copy_(norm.count.reshape(1), non_blocking=True)

@@ -269,7 +269,8 @@ class Evaluator:
 class ExperienceCollector:
     """SAC.get_experience in full (sac/sac.py:283-304): the scan of actor steps (one launch), the observation
     normaliser update (running_statistics.update, with the psum over ranks when ``pmap_axis_name`` is given) and the
-    replay-buffer insert.  Same argument order and return value as the reference method."""
+    replay-buffer insert.  Same argument order and return value as the reference method (the carry key of the scan,
+    which the reference drops, is kept in ``last_key``)."""
 
     def __init__(self, env: VmappedSystemEnv, make_policy, replay_buffer, num_env_steps_between_updates: int,
                  pmap_axis_name: str = None, env_offset: int = 0, total_envs: int = None):
@@ -279,6 +280,7 @@ class ExperienceCollector:
         self.num_env_steps_between_updates = int(num_env_steps_between_updates)
         self._PMAP_AXIS_NAME = pmap_axis_name
         self._env_offset, self._total_envs = env_offset, total_envs
+        self.last_key = None
 
     def get_experience(self, normalizer_params, policy_params, env_state: EnvState, buffer_state, key: torch.Tensor):
         from . import running_statistics
@@ -289,7 +291,8 @@ class ExperienceCollector:
         normalizer_params = running_statistics.update(normalizer_params, transitions.observation,
                                                       pmap_axis_name=self._PMAP_AXIS_NAME)
         buffer_state = self.replay_buffer.insert(buffer_state, transitions)
-        return normalizer_params, env_state, buffer_state, key
+        self.last_key = key            # the scan's carry key (the reference discards it: sac.py:294,304)
+        return normalizer_params, env_state, buffer_state
 
 
 def make_normalized_inference_fn(emit_extras: bool = False, kernel: str = "auto"):

@@ -202,6 +202,8 @@ def test_api_surface_matches_reference(mb):
         "truncation", "termination", "rewards", "values", "bootstrap_value", "lambda_", "discount"]
     assert list(inspect.signature(acting.Evaluator.__init__).parameters) == [            # sac/acting.py:85-88
         "self", "eval_env", "eval_policy_fn", "num_eval_envs", "episode_length", "action_repeat", "key"]
+    assert list(inspect.signature(acting.ExperienceCollector.get_experience).parameters) == [   # sac/sac.py:283-285
+        "self", "normalizer_params", "policy_params", "env_state", "buffer_state", "key"]
     assert list(inspect.signature(acting.Evaluator.run_evaluation).parameters) == [      # :118-122
         "self", "policy_params", "training_metrics", "unroll_key", "aggregate_episodes"]
     assert issubclass(iCemTO, BaseOptimizer) and issubclass(PendulumSystem, System)

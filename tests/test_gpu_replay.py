@@ -371,7 +371,8 @@ def test_get_experience_in_full(mb, cuda_device):
     rows = []
     for it in range(2):
         prev_norm, prev_state = norm, state
-        norm, state, buf, key = col.get_experience(norm, params, state, buf, key)
+        norm, state, buf = col.get_experience(norm, params, state, buf, key)      # sac.py:283-304: a 3-tuple
+        key = col.last_key
         live = buf.data[buf.insert_position - T * E:buf.insert_position].cpu().numpy()
         obs = live[:, :3].reshape(T, E, 3)
         # the policy saw (obs - mean) / std of the statistics before this collection (the GPU's own: after 20 steps
