@@ -42,12 +42,18 @@ def all_reduce_sums(sums: torch.Tensor, group=None) -> torch.Tensor:
     return sums
 
 
-def update(state: RunningStatisticsState, batch: torch.Tensor, *, std_min_value: float = 1e-6,
-           std_max_value: float = 1e6, pmap_axis_name: Optional[str] = None, group=None) -> RunningStatisticsState:
+def update(state: RunningStatisticsState, batch: torch.Tensor, *, weights=None, std_min_value: float = 1e-6,
+           std_max_value: float = 1e6, pmap_axis_name: Optional[str] = None, validate_shapes: bool = True,
+           group=None) -> RunningStatisticsState:
     """running_statistics.update(state, batch, pmap_axis_name=...): batch [..., X] (any leading batch dims).
     With ``pmap_axis_name`` (or an explicit ``group``) the sums are all-reduced over the process group, so every rank
     ends with the statistics of the union of the ranks' batches."""
     X = state.mean.shape[-1]
+    if weights is not None:      # brax's keyword; no caller in the reference passes it (sac.py:298-301, ppo.py)
+        raise _lib.MbpoUnsupported(_lib.MBPO_EUNSUPPORTED, "running_statistics.update: weighted updates have no kernel")
+    if validate_shapes and batch.shape[-1] != X:
+        raise ValueError("running_statistics.update: batch [..., %d] does not match the statistics [%d]" % (
+            batch.shape[-1], X))
     b = batch.to(torch.float32).contiguous()
     n_rows = b.numel() // X
     dev = b.device

@@ -202,6 +202,11 @@ def test_api_surface_matches_reference(mb):
         "truncation", "termination", "rewards", "values", "bootstrap_value", "lambda_", "discount"]
     assert list(inspect.signature(acting.Evaluator.__init__).parameters) == [            # sac/acting.py:85-88
         "self", "eval_env", "eval_policy_fn", "num_eval_envs", "episode_length", "action_repeat", "key"]
+    from mbpo_b200 import running_statistics as rs
+    assert list(inspect.signature(rs.update).parameters)[:7] == [                        # brax acme/running_statistics.update
+        "state", "batch", "weights", "std_min_value", "std_max_value", "pmap_axis_name", "validate_shapes"]
+    assert list(inspect.signature(rs.normalize).parameters) == ["batch", "mean_std", "max_abs_value"]
+    assert list(inspect.signature(rs.Normalizer.update).parameters)[:2] == ["x", "state"]   # bptt_optimizer.py:51
     assert list(inspect.signature(acting.ExperienceCollector.get_experience).parameters) == [   # sac/sac.py:283-285
         "self", "normalizer_params", "policy_params", "env_state", "buffer_state", "key"]
     assert list(inspect.signature(acting.Evaluator.run_evaluation).parameters) == [      # :118-122
