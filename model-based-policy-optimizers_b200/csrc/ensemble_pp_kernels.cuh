@@ -340,8 +340,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ENS_THREADS, 1)
 
 // Chooses the kernel: the two-tile kernel needs half as many CTA pairs per row, so it is used whenever the
 // one-tile kernel would need more than one round of CTA pairs (throughput shapes); small row counts keep
-// the one-tile kernel, which spreads them over more SMs (latency shapes).  MBPO_ENS_VARIANT=single|pp
-// overrides the choice (used by the tests to cover both kernels at small sizes).
+// the one-tile kernel, which spreads them over more SMs (latency shapes).  The row count alone decides
+// (no run-time switch); the tests reach each kernel through its own sizes.
 inline int launch_ensemble_rollout_auto(const MbpoMlpEnsembleParams& p, int horizon, const float* x0,
                                         const float* actions, int B, int M, int summarize, float* returns_out,
                                         cudaStream_t st, char* err, size_t errlen) {
@@ -349,11 +349,7 @@ inline int launch_ensemble_rollout_auto(const MbpoMlpEnsembleParams& p, int hori
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long R = static_cast<long long>(B) * M;
-  bool use_pp = R > static_cast<long long>(2 * TILE_M) * (sms / 2);
-  if (const char* v = getenv("MBPO_ENS_VARIANT")) {
-    if (v[0] == 'p') use_pp = true;
-    else if (v[0] == 's') use_pp = false;
-  }
+  const bool use_pp = R > static_cast<long long>(2 * TILE_M) * (sms / 2);
   if (!use_pp) return launch_ensemble_rollout(p, horizon, x0, actions, B, M, summarize, returns_out, st, err, errlen);
   if (p.hidden != HID || p.x_dim != 3 || p.u_dim != 1 || p.num_members < 1) {
     snprintf(err, errlen,

@@ -12,7 +12,6 @@
 #include "../../include/mbpo_b200.h"
 #include "env_kernels.cuh"
 #include "host_util.h"
-#include "mlp_kernels.cuh"
 #include "mlp_tc_kernels.cuh"
 #include "actor_kernels.cuh"
 #include "actor_tc_kernels.cuh"
@@ -895,12 +894,7 @@ int mbpo_mlp_dynamics_forward(const MbpoMlpEnsembleParams* p, const float* inp, 
   MBPO_REQUIRE(R >= 0, "mlp_dynamics_forward: R < 0");
   MBPO_REQUIRE(p->w_in && p->b_in && p->w_h && p->b_h && p->w_out && p->b_out, "mlp_dynamics_forward: null weights");
   if (R == 0) return MBPO_OK;
-  // bring-up switch: MBPO_MLP_IMPL=simt selects the CUDA-core cross-check kernel
-  const char* impl = getenv("MBPO_MLP_IMPL");
-  const int rc = (impl && impl[0] == 's')
-                     ? launch_mlp_forward(*p, inp, member, R, delta_out, as_stream(stream), g_err, sizeof(g_err))
-                     : tc::launch_mlp_forward_tc(*p, inp, member, R, delta_out, as_stream(stream), g_err,
-                                                 sizeof(g_err));
+  const int rc = tc::launch_mlp_forward_tc(*p, inp, member, R, delta_out, as_stream(stream), g_err, sizeof(g_err));
   if (rc != MBPO_OK) return rc;
   return check_launch("mlp_dynamics_forward");
 }

@@ -15,6 +15,7 @@ class _Config:
 
     threefry_partitionable: bool = False
     math_mode: str = "reference"
+    enable_x64: bool = False      # mirrors jax_enable_x64; only random.PRNGKey's seed handling depends on it
 
     @property
     def prng_mode(self) -> int:

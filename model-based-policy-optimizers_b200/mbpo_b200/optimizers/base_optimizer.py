@@ -31,7 +31,21 @@ class BaseOptimizer:
         raise NotImplementedError
 
     def dummy_true_buffer_state(self, key: torch.Tensor):
-        """The reference builds a 10-slot brax UniformSamplingQueue here (base_optimizer.py:44-57);
-        the planning path only carries it.  We carry the key so the field stays non-empty."""
+        """base_optimizer.py:44-57: a 10-slot brax UniformSamplingQueue of dummy Transitions
+        (observation [x_dim], action [u_dim], reward [1], discount [1], next_observation [x_dim]), ``.init(key)``.
+        The state is what ``BraxWrapper(sample_buffer_state=...)`` expects.  A batch of keys [B, 2] (the additive
+        vmapped ``init``) gives the vmapped pytree: ring [B, 10, D], key [B, 2]."""
         assert self.system is not None, "Base optimizer requires system to be defined."
-        return {"key": key}
+        from ..replay_buffers import UniformSamplingQueue
+        from ..utils.optimizer_utils import Transition
+        dev = key.device
+        z = lambda n: torch.zeros((n,), dtype=torch.float32, device=dev)
+        dummy_transition = Transition(observation=z(self.system.x_dim), action=z(self.system.u_dim), reward=z(1),
+                                      discount=z(1), next_observation=z(self.system.x_dim))
+        sampling_buffer = UniformSamplingQueue(max_replay_size=10, dummy_data_sample=dummy_transition,
+                                               sample_batch_size=1)
+        if key.dim() == 1:
+            return sampling_buffer.init(key)
+        state = sampling_buffer.init(key.reshape(-1, 2)[0])
+        batch = tuple(key.shape[:-1])
+        return state.replace(ring=state.ring.expand(batch + tuple(state.ring.shape)).contiguous(), key=key)

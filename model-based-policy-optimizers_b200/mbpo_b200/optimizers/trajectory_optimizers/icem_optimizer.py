@@ -151,9 +151,7 @@ class iCemTO(BaseOptimizer):
                   trace: bool = False):
         """x0 [B,X], key [B,2], best_seq [B,H,A] -> (best_seq', best_value, key', trace dict|None)."""
         if self.cost_fn is not None or self._array_bounds():
-            if trace:
-                raise _lib.MbpoUnsupported(_lib.MBPO_EUNSUPPORTED, "trace dumps exist for the fused plan only")
-            return self._plan_general(x0, key, best_seq, system_params) + (None,)
+            return self._plan_general(x0, key, best_seq, system_params, trace=trace)
         cfg = self._cfg()
         B = x0.shape[0]
         dev = x0.device
@@ -192,7 +190,8 @@ class iCemTO(BaseOptimizer):
                                                           _lib.stream_ptr(dev)))
         return out_seq, out_val, out_key, tr
 
-    def _plan_general(self, x0: torch.Tensor, key: torch.Tensor, best_seq: torch.Tensor, system_params):
+    def _plan_general(self, x0: torch.Tensor, key: torch.Tensor, best_seq: torch.Tensor, system_params,
+                      trace: bool = False):
         """iCemTO.optimize with a constraint cost (:161-166) and / or array-valued bounds (:47-48): the
         per-stage C-ABI kernels composed on the caller's stream.  Every number is produced by the CUDA
         library except the user's own cost function, which is vmapped torch code on the same device."""
@@ -229,6 +228,7 @@ class iCemTO(BaseOptimizer):
         obs = torch.empty((B, M, H, X), dtype=torch.float32, device=dev) if cost_batched is not None else None
         s_rew = L.SUMMARIZE_MAX if self.use_optimism else L.SUMMARIZE_MEAN    # :112-115
         s_cost = L.SUMMARIZE_MAX if self.use_pessimism else L.SUMMARIZE_MEAN  # :116-119
+        tr = {n: [] for n in ("actions", "values", "elite_idx", "mean", "std", "best_value")} if trace else None
         with L.cuda_guard(x0):
             for _ in range(S):
                 nxt_carry = torch.empty_like(carry)
@@ -251,11 +251,18 @@ class iCemTO(BaseOptimizer):
                                                      s_cost, float(p.lambda_constraint), st))
                 n_mean, n_std = torch.empty_like(mean), torch.empty_like(std)
                 n_bval, n_bseq = torch.empty_like(bval), torch.empty_like(bseq)
+                eidx = torch.empty((B, cfg.num_elites), dtype=torch.int32, device=dev) if trace else None
                 L.check(L.lib.mbpo_icem_elite_refit(L.C.byref(cfg), L.ptr(actions), L.ptr(values), L.ptr(mean),
                                                     L.ptr(std), L.ptr(bval), L.ptr(bseq), B, L.ptr(n_mean),
-                                                    L.ptr(n_std), L.ptr(n_bval), L.ptr(n_bseq), None, st))
+                                                    L.ptr(n_std), L.ptr(n_bval), L.ptr(n_bseq), L.ptr(eidx), st))
                 carry, mean, std, bval, bseq = nxt_carry, n_mean, n_std, n_bval, n_bseq
-        return bseq, bval, out_key
+                if trace:                                 # the per-iteration dumps of the fused kernel, same layout
+                    for n, v in (("actions", actions.reshape(B, M, D)), ("values", values), ("elite_idx", eidx),
+                                 ("mean", mean.reshape(B, D)), ("std", std.reshape(B, D)), ("best_value", bval)):
+                        tr[n].append(v.clone())
+        if trace:
+            tr = {n: torch.stack(v) for n, v in tr.items()}
+        return bseq, bval, out_key, tr
 
     def _canon(self, initial_state: torch.Tensor, opt_state: iCemOptimizerState):
         single = initial_state.dim() == 1

@@ -13,10 +13,13 @@ from .config import config
 
 
 def PRNGKey(seed: int, device=None) -> torch.Tensor:
-    """jax.random.PRNGKey for a 64-bit seed: uint32[2] = [seed >> 32, seed & 0xffffffff]."""
+    """jax.random.PRNGKey: uint32[2].  With ``config.enable_x64`` False (JAX's default, which the reference never
+    changes) the seed is truncated to 32 bits and the high word is 0: PRNGKey(-1) = [0, 0xffffffff],
+    PRNGKey((7 << 32) | 9) = [0, 9].  With it True the high word is (seed >> 32) & 0xffffffff."""
     dev = _lib.require_cuda(device)
-    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
-    hi, lo = seed >> 32, seed & 0xFFFFFFFF
+    seed = int(seed)
+    hi = (seed >> 32) & 0xFFFFFFFF if config.enable_x64 else 0
+    lo = seed & 0xFFFFFFFF
     # torch has no uint32 constructor from python ints > 2^31 on all versions: go through int64
     return torch.tensor([hi, lo], dtype=torch.int64).to(torch.uint32).to(dev)
 

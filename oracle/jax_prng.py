@@ -56,10 +56,15 @@ def threefry2x32(k0, k1, x0, x1):
     return x0, x1
 
 
-def PRNGKey(seed: int) -> np.ndarray:
-    """jax.random.PRNGKey for a seed that fits 32 bits: [hi=0, lo=seed]."""
+def PRNGKey(seed: int, enable_x64: bool = False) -> np.ndarray:
+    """jax.random.PRNGKey (jax/_src/prng.py random_seed -> threefry_seed).  A Python int goes through
+    ``jnp.asarray(np.int64(seed))``: with ``jax_enable_x64`` off (the reference never turns it on) that is an
+    int32 truncation, and ``shift_right_logical(seed, 32)`` of a 32-bit value is 0 -- so the key is
+    ``[0, seed & 0xffffffff]`` whatever the seed (PRNGKey(-1) = [0, 0xffffffff], PRNGKey((7 << 32) | 9) = [0, 9]).
+    With x64 on, the high word is ``(seed >> 32) & 0xffffffff`` of the int64."""
     seed = int(seed)
-    return np.array([(seed >> 32) & 0xFFFFFFFF, seed & 0xFFFFFFFF], dtype=U32)
+    hi = (seed >> 32) & 0xFFFFFFFF if enable_x64 else 0
+    return np.array([hi, seed & 0xFFFFFFFF], dtype=U32)
 
 
 def _threefry_2x32_counts(key, counts):

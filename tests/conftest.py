@@ -33,3 +33,30 @@ def c_oracle():
     if not os.path.exists(lib) or os.path.getmtime(lib) < os.path.getmtime(src):
         subprocess.run(["make", "-s", "-C", cdir], check=True)
     return ctypes.CDLL(lib)
+
+
+_BUDGET_REPORT = {}
+
+
+@pytest.fixture(scope="session")
+def budget_report():
+    """Collects the measured error fractions of the float64-budget tests (tests/f64_truth.py); written at the end
+    of the session to gpurun_out/f64_budget_report_{cpu,gpu}.json (a copy per round lives under profiles/)."""
+    def record(name, **fields):
+        _BUDGET_REPORT[name] = fields
+    return record
+
+
+def pytest_sessionfinish(session, exitstatus):
+    if not _BUDGET_REPORT:
+        return
+    import json
+    try:
+        import torch
+        where = "gpu" if torch.cuda.is_available() else "cpu"
+    except Exception:
+        where = "cpu"
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "f64_budget_report_%s.json" % where), "w") as f:
+        json.dump(_BUDGET_REPORT, f, indent=1, sort_keys=True)

@@ -31,7 +31,10 @@ def test_legacy_known_answers():
     k = KATS["legacy"]
     key0 = jr.PRNGKey(0)
     assert key0.tolist() == [0, 0] and jr.PRNGKey(42).tolist() == [0, 42]
-    assert jr.PRNGKey((7 << 32) | 9).tolist() == [7, 9]
+    # x64 disabled (the reference's setting): the seed is truncated to 32 bits, the high word is always 0
+    assert jr.PRNGKey((7 << 32) | 9).tolist() == [0, 9] and jr.PRNGKey(-1).tolist() == [0, 0xFFFFFFFF]
+    assert jr.PRNGKey((7 << 32) | 9, enable_x64=True).tolist() == [7, 9]
+    assert jr.PRNGKey(-1, enable_x64=True).tolist() == [0xFFFFFFFF, 0xFFFFFFFF]
     sp = jr.split(key0)
     assert sp.tolist() == k["split_prngkey0"]
     assert jr.normal(key0, 1)[0] == pytest.approx(k["normal_prngkey0"], rel=1e-6)
