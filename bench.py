@@ -41,18 +41,21 @@ GUARD = None
 METRIC = "iCEM model-rollout transitions/sec (pop x horizon x problems x CEM iterations)"
 UNIT = "transitions/s"
 
-# Thread-level instructions the fused plan kernel executes per transition on the default
-# workload, measured with ncu (smsp__thread_inst_executed.sum / transitions; profiles/).  Used
-# for roofline.achieved = executed lane-instructions per second; see DESIGN.md.
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
-# captures (profiles/r01c_plan_kernel_ncu_full.txt, profiles/r01c_env_pieces_kernel_ncu_full.txt); N = 1 only.
-NCU_TRAFFIC_BYTES = {"config2_batched_icem": 681216, "config3_env_rollouts": 268336640 + 1518277000,
-                     # profiles/r01d_actor_tc_kernel_ncu_full.txt, profiles/r01b_ensemble_pp_kernel_ncu_full.txt
-                     "config3_actor_rollouts_tcgen05": 2874880 + 311553792, "config4_ensemble_icem": 8923136,
-                     # profiles/r01e_replay_pack_kernel_ncu_full.txt (observation / next_observation overlap: L2 hits)
-                     "config3_replay_insert": 384913664 + 465484288}
-LANE_INSTR_PER_TRANSITION = {("config2_batched_icem", "reference"): 229.7,
-                             ("config2_batched_icem", "theta_carry"): 185.1}
+# Roofline inputs measured with ncu live in a tracked file (profiles/roofline_inputs.json): per workload the
+# executed lane-instructions per transition (smsp__inst_executed.sum x 32 / transitions) and the DRAM traffic per
+# launch of the dominant kernel, each stamped with the commit of the kernel it was captured from.
+ALGORITHMIC_LANE_INSTR_PER_TRANSITION = 220.0      # ~110 rollout + ~110 sampling, fused plan
+
+
+def roofline_inputs():
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "roofline_inputs.json")))
+    except Exception:
+        return {}
+
+
+def ncu_traffic(workload):
+    return (roofline_inputs().get(workload) or {}).get("dram_bytes_per_launch")
 
 
 def transitions_per_step(B, horizon, p):
@@ -151,7 +154,8 @@ def cpu_reference_step(wl, steps: int, warmup: int, sample_B: int | None = None)
     cfg = c_twin.make_cfg(p, wl["horizon"])
     p9 = orc.PendulumParams().packed()
     x0 = random_states(wl["B"], 0)[:B]
-    keys = orc.split_keys(jr.PRNGKey(0).reshape(1, 2), wl["B"])[0][:B]
+    # the GPU arm's keys: opt.init(split(PRNGKey(0), B)).key = split(k, 3)[2] per problem (icem_optimizer.py:123)
+    keys = orc.split_keys(orc.split_keys(jr.PRNGKey(0).reshape(1, 2), wl["B"])[0], 3)[:B, 2].copy()
     seq = np.zeros((B, wl["horizon"]), np.float32)
     used = cores
     for _ in range(max(warmup, 1)):
@@ -176,7 +180,7 @@ def run_reference(args, wl_name, wl):
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(wl_name, wl, args.gpus, l2="n/a (CPU)"),
+        "config": workload_config(wl_name, wl, args.gpus),
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                          "sample": r["sample"], "host_cpu": model, "host_logical_cpus": ncores,
                          "note": "CPU restatement of the reference semantics (oracle/c) -- the reference's JAX "
@@ -187,14 +191,15 @@ def run_reference(args, wl_name, wl):
     emit_json(line, GUARD)
 
 
-def workload_config(name, wl, gpus, l2):
+def workload_config(name, wl, gpus):
     p = dict(num_particles=10, num_samples=500, num_elites=50, num_steps=5, exponent=0.0, alpha=0.0)
     p.update(wl["params"])
     return {"workload": name, "problems_per_gpu": wl["B"], "problems_total": wl["B"] * gpus, "horizon": wl["horizon"],
             "num_samples": p["num_samples"], "num_elites": p["num_elites"], "num_prev_elites": 15,
             "num_particles": p["num_particles"], "cem_iterations": p["num_steps"], "exponent": p["exponent"],
             "alpha": p["alpha"], "system": "analytic pendulum", "parallelism": "problems sharded x%d" % gpus,
-            "l2": l2}
+            # one text for both arms, so that their configs compare equal
+            "l2": "GPU arm: flushed (256 MiB memset) before every timed step; CPU arm: n/a"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -294,19 +299,29 @@ def run_ours(args, wl_name, wl):
             pass
         sm_max = float(peaks.get("sm_max_mhz", 1965.0))
         issue_peak = 148 * 4 * 32 * sm_max * 1e6 / 1e12          # T lane-instr/s
-        ipt = LANE_INSTR_PER_TRANSITION.get((wl_name, args.math))
+        ri = (roofline_inputs().get(wl_name + ("" if args.math == "reference" else "_" + args.math)) or {})
+        executed = ri.get("executed_lane_instr_per_transition")
         kernel_ms = ms_per_step                                   # one fused kernel per step: event time = launch time
+        tps = tr_step / (kernel_ms * 1e-3)
+        algorithmic = tps * ALGORITHMIC_LANE_INSTR_PER_TRANSITION / 1e12
         roofline = {
             "bound": "issue", "kernel": "icem_plan_pendulum_kernel",
-            "achieved": (tr_step * ipt / (kernel_ms * 1e-3) / 1e12) if ipt else None,
-            "peak": issue_peak, "unit": "T lane-instr/s",
-            "frac": (tr_step * ipt / (kernel_ms * 1e-3) / 1e12 / issue_peak) if ipt else None,
-            "traffic": NCU_TRAFFIC_BYTES.get(wl_name) if (world == 1 and args.math == "reference") else None,
-            "lane_instr_per_transition": ipt,
+            "achieved": algorithmic, "peak": issue_peak, "unit": "T lane-instr/s",
+            "frac": algorithmic / issue_peak,
+            "frac_algorithmic": algorithmic / issue_peak,
+            "algorithmic_lane_instr_per_transition": ALGORITHMIC_LANE_INSTR_PER_TRANSITION,
+            "issue_util": (tps * executed / 1e12 / issue_peak) if executed else None,
+            "executed_lane_instr_per_transition": executed,
+            "inputs_from": ri.get("source"), "inputs_commit": ri.get("kernel_commit"),
+            "traffic": ncu_traffic(wl_name) if (world == 1 and args.math == "reference") else None,
             "peak_source": "148 SMs x 4 SMSPs x 32 lanes x sm_max_mhz (MEASURED_PEAKS.json)",
-            "note": "the fused plan keeps actions in shared memory: HBM traffic is ~0 B/transition, so the "
-                    "limiting roofline is the SM issue rate, not HBM or the tensor pipe (DESIGN.md)",
+            "note": "the fused plan keeps actions in shared memory: HBM traffic is ~0 B/transition, so the limiting "
+                    "roofline is the SM issue rate.  frac = frac_algorithmic counts SURVEY 8(d)'s 220 lane-instructions "
+                    "per transition as the useful work; issue_util counts what the kernel executes (ncu)",
         }
+        others = None
+        if world == 1 and wl_name == "config2_batched_icem" and not args.no_others:
+            others = measure_others(args)
         cpu = None
         if not args.no_cpu_baseline:
             r = cpu_reference_step(wl, steps=1, warmup=1)
@@ -317,7 +332,7 @@ def run_ours(args, wl_name, wl):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(wl_name, wl, world, l2="flushed (256 MiB memset) before every timed step"),
+            "config": workload_config(wl_name, wl, world),
             "math_mode": args.math,
             "ms_per_plan_call": ms_per_step,
             "pop_x_horizon_x_problems_per_s": B * world * p.num_samples * H / (ms_per_step * 1e-3),
@@ -330,9 +345,57 @@ def run_ours(args, wl_name, wl):
             "roofline": roofline,
             "cpu_baseline": cpu,
         }
+        if others is not None:
+            line["others"] = others
         emit_json(line, GUARD)
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_others(args):
+    """BASELINE.json's other single-GPU configurations, measured in this same process right after the headline so
+    that they sit under the same driver clock and loaded-library record: config 1 (the reference's own closed-loop
+    test), config 3 (vmapped env rollouts; the same with the policy in the loop) and config 4 (learned-ensemble
+    iCEM), each with its own CPU leg on a bounded sample.  Compact entries; `python bench.py --workload <name>`
+    prints the full line of any of them."""
+    global _CAPTURE
+    from types import SimpleNamespace
+    out = {}
+    table = (("config1_closed_loop", run_closed_loop), ("config3_env_rollouts", run_env),
+             ("config3_actor_rollouts", run_actor), ("config4_ensemble_icem", run_ensemble))
+    for name, fn in table:
+        entry = {}
+        for impl in ("ours", "reference"):
+            if impl == "reference" and args.no_cpu_baseline:
+                continue
+            a = SimpleNamespace(**vars(args))
+            a.impl, a.workload = impl, name
+            a.steps = min(args.steps, 5) if impl == "ours" else 1
+            a.warmup = 3 if impl == "ours" else 1
+            _CAPTURE = []
+            try:
+                fn(a)
+                got = _CAPTURE[-1] if _CAPTURE else {"error": "no line"}
+            except Exception as e:                       # one broken leg must not take the headline line down
+                got = {"error": "%s: %s" % (type(e).__name__, e)}
+            finally:
+                _CAPTURE = None
+            if impl == "ours":
+                roof = got.get("roofline") or {}
+                entry.update({k: got.get(k) for k in ("metric", "value", "unit", "ms_per_step", "clocks", "gpu_launches",
+                                                      "error") if k in got})
+                entry["roofline"] = {k: roof.get(k) for k in ("bound", "kernel", "achieved", "peak", "unit", "frac",
+                                                               "traffic") if k in roof}
+                e2e = got.get("e2e") or {}
+                entry["e2e"] = {k: e2e.get(k) for k in ("value", "unit", "ms_per_step", "h2d_bytes_per_step",
+                                                         "d2h_bytes_per_step") if k in e2e}
+                for k in ("ms_per_plan_call", "sum_rewards"):
+                    if k in got:
+                        entry[k] = got[k]
+            else:
+                entry["cpu_baseline"] = got.get("cpu_baseline") or got
+        out[name] = entry
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -483,7 +546,7 @@ def run_env(args):
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "kernel": "env_rollout_pendulum_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES["config3_env_rollouts"] if world == 1 else None,
+                         "traffic": ncu_traffic("config3_env_rollouts") if world == 1 else None,
                          "algorithmic_bytes_per_launch": E * T * ENV_BYTES_PER_TRANSITION,
                          "algorithmic_bytes_per_transition": ENV_BYTES_PER_TRANSITION,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
@@ -518,9 +581,31 @@ def run_ensemble(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        if rank == 0:
-            emit_json({"impl": "reference", "unavailable": "no CPU restatement of the learned-ensemble System is timed "
-                       "(the reference ships no learned-dynamics System; config 4 is a new System)"}, GUARD)
+        if rank != 0:
+            return
+        from oracle import mbpo_oracle as orc                                     # CPU arm only
+        ens = orc.make_mlp_ensemble(seed=3, members=ENS_E)
+        rows, Hs = 1039, 5                                  # one problem's candidates, 5 of the 50 steps
+        x0 = random_states(1, 0)
+        acts = np.random.default_rng(1).uniform(-1, 1, (1, rows, Hs)).astype(np.float32)
+        orc.ensemble_rollout_returns(x0, acts[:, :64], ens, bf16=True)
+        t0 = time.perf_counter()
+        for _ in range(max(args.steps, 1)):
+            orc.ensemble_rollout_returns(x0, acts, ens, bf16=True)
+        dt = (time.perf_counter() - t0) / max(args.steps, 1)
+        ncores, model = host_info()
+        v = rows * ENS_E * Hs / dt                           # member-transitions per second = the metric's unit
+        emit_json({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+                   "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+                   "scaling": "weak", "vs_baseline": None, "dtype": "bf16-rounded operands, f32 accumulate (NumPy)",
+                   "data": "synthetic (random-init ensemble weights)",
+                   "config": {"workload": "config4_ensemble_icem", "problems_per_gpu": ENS_B, "num_samples": ENS_N,
+                              "horizon": ENS_H, "members": ENS_E},
+                   "cpu_baseline": {"value": v, "unit": UNIT, "cores": ncores, "kind": "port",
+                                    "sample": "rollouts only: %d candidates x %d members x %d of %d steps, NumPy oracle "
+                                              "(BLAS threads); the reference ships no learned-dynamics System" % (
+                                                  rows, ENS_E, Hs, ENS_H), "host_cpu": model},
+                   "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}, GUARD)
         return
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -612,7 +697,7 @@ def run_ensemble(args):
             "gpu_launches": steps * (1 + 3 * ENS_S + 1),
             "roofline": {"bound": "tensor", "kernel": "ensemble_rollout_kernel", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES["config4_ensemble_icem"] if world == 1 else None,
+                         "traffic": ncu_traffic("config4_ensemble_icem") if world == 1 else None,
                          "kernel_ms": k_ms, "flops_per_launch": flops,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"},
             "cpu_baseline": None}, GUARD)
@@ -955,7 +1040,7 @@ def run_actor(args):
             achieved = E * T * ACT_MUFU_PER_STEP / (ms * 1e-3) / 1e12
             roof = {"bound": "xu", "kernel": "actor_rollout_tc_kernel", "achieved": achieved, "peak": peak,
                     "unit": "T MUFU/s", "frac": achieved / peak,
-                    "traffic": NCU_TRAFFIC_BYTES["config3_actor_rollouts_tcgen05"] if world == 1 else None,
+                    "traffic": ncu_traffic("config3_actor_rollouts_tcgen05") if world == 1 else None,
                     "note": ACT_TC_NOTE,
                     "tensor_tflops_issued": E * T * 3 * 2 * 2 * 64 * 64 / (ms * 1e-3) / 1e12}
         else:
@@ -1295,7 +1380,13 @@ class _StdoutGuard:
 _real_print = print
 
 
+_CAPTURE = None        # a list while run_ours collects the other configurations' lines instead of printing them
+
+
 def emit_json(obj, guard):
+    if _CAPTURE is not None:
+        _CAPTURE.append(obj)
+        return
     sys.stdout.flush()
     os.write(guard.saved, (json.dumps(obj) + "\n").encode())
 
@@ -1424,7 +1515,7 @@ def run_replay(args):
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "kernel": "replay_pack_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES["config3_replay_insert"] if world == 1 else None,
+                         "traffic": ncu_traffic("config3_replay_insert") if world == 1 else None,
                          "algorithmic_bytes_per_launch": rows * 8 * D, "algorithmic_bytes_per_row": 8 * D,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
             "cpu_baseline": cpu}, GUARD)
@@ -1444,6 +1535,8 @@ def main():
                     default="config2_batched_icem")
     ap.add_argument("--math", choices=["reference", "theta_carry"], default="reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-others", action="store_true",
+                    help="default workload: skip the compact measurements of configs 1, 3 and 4 (the `others` key)")
     ap.add_argument("--actor-kernel", choices=["auto", "cuda_cores", "tcgen05", "tcgen05_wide"], default="auto",
                     help="config3_actor_rollouts: which kernel runs the policy network")
     ap.add_argument("--env-sequential", action="store_true",

@@ -138,6 +138,12 @@ int mbpo_prng_normal(const uint32_t* keys, int M, int n, int prng_mode, float* o
  * bits_out (optional) receives the raw uint32 words behind sr and si: [M, 2, H/2+1]. */
 int mbpo_powerlaw_noise(const MbpoIcemCfg* cfg_host, const uint32_t* keys /*[M,2]*/, int M,
                         float* noise_out /*[M,H]*/, uint32_t* bits_out, void* stream);
+/* The same function through the any-horizon kernel (rolled loops, twiddle table in the constant
+ * bank; general_utils.py:134-143 takes any `size`, iCemTO any `horizon`, icem_optimizer.py:94-96).
+ * mbpo_powerlaw_noise / mbpo_icem_sample_actions use it for every horizon in [2, MBPO_MAX_HORIZON]
+ * without an unrolled instance; for the unrolled horizons both give the same bits. */
+int mbpo_powerlaw_noise_rolled(const MbpoIcemCfg* cfg_host, const uint32_t* keys /*[M,2]*/, int M,
+                               float* noise_out /*[M,H]*/, uint32_t* bits_out, void* stream);
 /* One iCEM iteration of key plumbing + sampling (icem_optimizer.py:174-192) for B problems. */
 int mbpo_icem_sample_actions(const MbpoIcemCfg* cfg_host, const uint32_t* carry_key /*[B,2]*/,
                              const float* mean /*[B,H,A]*/, const float* std /*[B,H,A]*/, int B,

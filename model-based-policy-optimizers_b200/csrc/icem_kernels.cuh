@@ -16,58 +16,43 @@ namespace mbpo {
 // Rollout of one action row held in shared/global memory; returns the horizon-mean reward
 // (icem_optimizer.py:160 inner jnp.mean over rollout_actions(...).reward).
 // ------------------------------------------------------------------------------------------
-template <int MATH, typename ActFn>
+// SMALL: the host checked |target_angle| <= 6, so the reward's floored mod needs no fmod slow path.
+template <int MATH, bool SMALL = false, typename ActFn>
 __device__ __forceinline__ float rollout_return(const PendulumConsts& pc, float c0, float s0, float w0, int H,
                                                 ActFn act) {
   float acc = 0.0f;
-  if (MATH == MBPO_MATH_REFERENCE) {
-    float c = c0, s = s0, w = w0;
+  float th = atan2_bounded(s0, c0), w = w0;
 #pragma unroll 2
-    for (int t = 0; t < H; ++t) {
-      float r;
-      pendulum_step_ref(pc, c, s, w, act(t), r);
-      acc = __fadd_rn(acc, r);
-    }
-  } else {
-    float th = atan2_bounded(s0, c0), w = w0;
-#pragma unroll 2
-    for (int t = 0; t < H; ++t) {
-      float r;
-      pendulum_step_theta(pc, th, w, act(t), r);
-      acc = __fadd_rn(acc, r);
-    }
+  for (int t = 0; t < H; ++t) {
+    float r;
+    if (MATH == MBPO_MATH_REFERENCE) pendulum_step_ref_th<SMALL>(pc, th, w, act(t), r);
+    else pendulum_step_theta<SMALL>(pc, th, w, act(t), r);
+    acc = __fadd_rn(acc, r);
   }
   return __fdiv_rn(acc, static_cast<float>(H));
 }
 
-// Two independent rollouts from the same initial state, interleaved step by step: the horizon
-// recurrence is a serial dependency chain, so a second chain in the same thread doubles the
-// instruction-level parallelism at a cost of ~8 registers.
-template <int MATH>
-__device__ __forceinline__ void rollout_return2(const PendulumConsts& pc, float c0, float s0, float w0, int H,
+// Two independent rollouts from the same initial state (th0 = atan2(s0, c0), computed once per problem by the
+// caller), interleaved step by step: the horizon recurrence is a serial dependency chain, so a second chain in
+// the same thread doubles the instruction-level parallelism at a cost of ~8 registers.
+template <int MATH, bool SMALL>
+__device__ __forceinline__ void rollout_return2(const PendulumConsts& pc, float th0, float w0, int H,
                                                 const float* __restrict__ row_a, const float* __restrict__ row_b,
                                                 float& ret_a, float& ret_b) {
   float acc_a = 0.0f, acc_b = 0.0f;
-  if (MATH == MBPO_MATH_REFERENCE) {
-    float ca = c0, sa = s0, wa = w0, cb = c0, sb = s0, wb = w0;
+  float tha = th0, wa = w0, thb = th0, wb = w0;
 #pragma unroll 1
-    for (int t = 0; t < H; ++t) {
-      float ra, rb;
-      pendulum_step_ref(pc, ca, sa, wa, row_a[t], ra);
-      pendulum_step_ref(pc, cb, sb, wb, row_b[t], rb);
-      acc_a = __fadd_rn(acc_a, ra);
-      acc_b = __fadd_rn(acc_b, rb);
+  for (int t = 0; t < H; ++t) {
+    float ra, rb;
+    if (MATH == MBPO_MATH_REFERENCE) {
+      pendulum_step_ref_th<SMALL>(pc, tha, wa, row_a[t], ra);
+      pendulum_step_ref_th<SMALL>(pc, thb, wb, row_b[t], rb);
+    } else {
+      pendulum_step_theta<SMALL>(pc, tha, wa, row_a[t], ra);
+      pendulum_step_theta<SMALL>(pc, thb, wb, row_b[t], rb);
     }
-  } else {
-    float tha = atan2_bounded(s0, c0), wa = w0, thb = tha, wb = w0;
-#pragma unroll 1
-    for (int t = 0; t < H; ++t) {
-      float ra, rb;
-      pendulum_step_theta(pc, tha, wa, row_a[t], ra);
-      pendulum_step_theta(pc, thb, wb, row_b[t], rb);
-      acc_a = __fadd_rn(acc_a, ra);
-      acc_b = __fadd_rn(acc_b, rb);
-    }
+    acc_a = __fadd_rn(acc_a, ra);
+    acc_b = __fadd_rn(acc_b, rb);
   }
   ret_a = __fdiv_rn(acc_a, static_cast<float>(H));
   ret_b = __fdiv_rn(acc_b, static_cast<float>(H));
@@ -162,7 +147,7 @@ struct PlanCtaSmem {
 template <int H, int PRNG, int MATH, int THREADS>
 __device__ __forceinline__ void plan_problem(const PlanArgs& a, const PlanCtaSmem<H>& sm, const PendulumConsts& pc,
                                              const RefitScalars& rs, const float* prev_best, Key2 key_in,
-                                             Key2& key_new, float x_c, float x_s, float x_w, int slot, int slots) {
+                                             Key2& key_new, float x_th, float x_w, int slot, int slots) {
   constexpr int HS = PlanSmem<H>::HS;
   const int N = a.N, M = a.N + a.Np, K = a.K;
   const int tid = threadIdx.x;
@@ -233,7 +218,7 @@ __device__ __forceinline__ void plan_problem(const PlanArgs& a, const PlanCtaSme
         Key2 skey_n;
         if (PRNG == MBPO_PRNG_LEGACY) { skey_n.k0 = flat[2 * (n + 1)]; skey_n.k1 = flat[2 * (n + 1) + 1]; }
         else skey_n = split_at<1>(sampling_rng, static_cast<uint32_t>(N + 1), static_cast<uint32_t>(n + 1));
-        const Key2 dim_key = split_at<PRNG>(skey_n, 1u, 0u);   // vmap(split(x, action_dim)), A == 1  (:180)
+        const Key2 dim_key = split1<PRNG>(skey_n);             // vmap(split(x, action_dim)), A == 1  (:180)
         float* row = act + static_cast<size_t>(n) * HS;
         colored_noise_row<H, PRNG>(dim_key, a.scale, row, nullptr, [&](int t, float y) {
           const float v = __fadd_rn(mean[t], __fmul_rn(y, std_[t]));           // :190
@@ -242,8 +227,8 @@ __device__ __forceinline__ void plan_problem(const PlanArgs& a, const PlanCtaSme
       }
       const int r0 = n0 < N ? n0 : N, r1 = n1 < N ? n1 : N;   // idle slots roll out the zero row
       float ret0, ret1;
-      rollout_return2<MATH>(pc, x_c, x_s, x_w, H, act + static_cast<size_t>(r0) * HS,
-                            act + static_cast<size_t>(r1) * HS, ret0, ret1);
+      rollout_return2<MATH, true>(pc, x_th, x_w, H, act + static_cast<size_t>(r0) * HS,
+                                  act + static_cast<size_t>(r1) * HS, ret0, ret1);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int n = h ? n1 : n0;
@@ -298,7 +283,8 @@ __global__ void zero_row_value_kernel(const MbpoPendulumParams sys, int H, int P
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const PendulumConsts pc(sys);
-  const float ret = rollout_return<MATH>(pc, x0[3 * b], x0[3 * b + 1], x0[3 * b + 2], H, [](int) { return 0.0f; });
+  const float ret = rollout_return<MATH, true>(pc, x0[3 * b], x0[3 * b + 1], x0[3 * b + 2], H,
+                                               [](int) { return 0.0f; });
   out[b] = summarize_particles(ret, P, summarize);
 }
 
@@ -315,8 +301,8 @@ __global__ void __launch_bounds__(THREADS, MINB) icem_plan_pendulum_kernel(const
   for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
     const float x_c = a.x0[3 * b], x_s = a.x0[3 * b + 1], x_w = a.x0[3 * b + 2];
     Key2 k_in{a.key_in[2 * b], a.key_in[2 * b + 1]}, k_new;
-    plan_problem<H, PRNG, MATH, THREADS>(a, sm, pc, rs, a.best_seq_in + static_cast<size_t>(b) * H, k_in, k_new, x_c,
-                                         x_s, x_w, b, a.B);
+    plan_problem<H, PRNG, MATH, THREADS>(a, sm, pc, rs, a.best_seq_in + static_cast<size_t>(b) * H, k_in, k_new,
+                                         atan2_bounded(x_s, x_c), x_w, b, a.B);
     // ---- epilogue (:251) -----------------------------------------------------------------
     if (tid < H) a.best_seq_out[static_cast<size_t>(b) * H + tid] = sm.best_seq[tid];
     if (tid == 0) {
@@ -357,7 +343,8 @@ __global__ void __launch_bounds__(THREADS, MINB)
     for (int t = 0; t < m.T; ++t) {
       const float x_c = xs[0], x_s = xs[1], x_w = xs[2];
       Key2 k_in{sm.state_key[0], sm.state_key[1]}, k_new;
-      plan_problem<H, PRNG, MATH, THREADS>(a, sm, pc, rs, sm.best_seq, k_in, k_new, x_c, x_s, x_w, 0, 1);
+      plan_problem<H, PRNG, MATH, THREADS>(a, sm, pc, rs, sm.best_seq, k_in, k_new, atan2_bounded(x_s, x_c), x_w, 0,
+                                           1);
       if (tid == 0) {
         sm.state_key[0] = k_new.k0; sm.state_key[1] = k_new.k1;
         const float u = sm.best_seq[0];                       // opt_state.action (:67-69)
@@ -448,6 +435,64 @@ __global__ void __launch_bounds__(STAGED_THREADS) sample_actions_kernel(const __
   const float* mrow = mean + static_cast<size_t>(b) * H * A + ad;
   const float* srow = std_ + static_cast<size_t>(b) * H * A + ad;
   colored_noise_row<H, PRNG>(dk, tbl.v, stage[threadIdx.x], nullptr, [&](int t, float y) {
+    const float v = __fadd_rn(mrow[static_cast<size_t>(t) * A], __fmul_rn(y, srow[static_cast<size_t>(t) * A]));
+    row[static_cast<size_t>(t) * A] = fminf(fmaxf(v, u_min), u_max);
+  });
+}
+
+// ---- any horizon (runtime H): same key tree and operation order, rolled loops (noise.cuh) --------------
+// `stage` is dynamic shared memory: blockDim.x rows of (H | 1) floats.
+template <int PRNG>
+__global__ void __launch_bounds__(STAGED_THREADS)
+    powerlaw_noise_rt_kernel(const __grid_constant__ ScaleTable tbl, const __grid_constant__ TwiddleTable tw, int H,
+                             const uint32_t* __restrict__ keys, int M, float* __restrict__ out,
+                             uint32_t* __restrict__ bits_out) {
+  extern __shared__ __align__(16) float stage_rt[];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  Key2 k{keys[2 * i], keys[2 * i + 1]};
+  float* row = out + static_cast<size_t>(i) * H;
+  colored_noise_row_rt<PRNG>(H, k, tbl.v, tw, stage_rt + static_cast<size_t>(threadIdx.x) * (H | 1),
+                             bits_out ? bits_out + static_cast<size_t>(i) * 2 * (H / 2 + 1) : nullptr,
+                             [&](int t, float y) { row[t] = y; });
+}
+
+template <int PRNG>
+__global__ void __launch_bounds__(STAGED_THREADS)
+    sample_actions_rt_kernel(const __grid_constant__ ScaleTable tbl, const __grid_constant__ TwiddleTable tw, int H,
+                             const uint32_t* __restrict__ carry_key, const float* __restrict__ mean,
+                             const float* __restrict__ std_, int N, int Np, int A, float u_min, float u_max,
+                             float* __restrict__ actions, uint32_t* __restrict__ next_key,
+                             uint32_t* __restrict__ particle_keys) {
+  extern __shared__ __align__(16) float stage_rt[];
+  const int b = blockIdx.y;
+  const int M = N + Np;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * A) return;
+  const int n = idx / A, ad = idx % A;
+  Key2 ck{carry_key[2 * b], carry_key[2 * b + 1]}, sampling_rng, particles_rng;
+  split2<PRNG>(ck, sampling_rng, particles_rng);                                                          // :174
+  if (ad == 0 && particle_keys) {
+    const Key2 pk = split_at<PRNG>(particles_rng, static_cast<uint32_t>(M), static_cast<uint32_t>(n));   // :177
+    particle_keys[(static_cast<size_t>(b) * M + n) * 2] = pk.k0;
+    particle_keys[(static_cast<size_t>(b) * M + n) * 2 + 1] = pk.k1;
+  }
+  if (idx == 0) {
+    const Key2 nk = split_at<PRNG>(sampling_rng, static_cast<uint32_t>(N + 1), 0u);                       // :176
+    next_key[2 * b] = nk.k0;
+    next_key[2 * b + 1] = nk.k1;
+  }
+  float* row = actions + (static_cast<size_t>(b) * M + n) * H * A + ad;  // element t at row[t*A]
+  if (n >= N) {  // kept-elite rows: closure zeros (:192,:245)
+    for (int t = 0; t < H; ++t) row[static_cast<size_t>(t) * A] = 0.0f;
+    return;
+  }
+  const Key2 sk = split_at<PRNG>(sampling_rng, static_cast<uint32_t>(N + 1), static_cast<uint32_t>(n + 1));
+  const Key2 dk = split_at<PRNG>(sk, static_cast<uint32_t>(A), static_cast<uint32_t>(ad));                // :180
+  const float* mrow = mean + static_cast<size_t>(b) * H * A + ad;
+  const float* srow = std_ + static_cast<size_t>(b) * H * A + ad;
+  colored_noise_row_rt<PRNG>(H, dk, tbl.v, tw, stage_rt + static_cast<size_t>(threadIdx.x) * (H | 1), nullptr,
+                             [&](int t, float y) {
     const float v = __fadd_rn(mrow[static_cast<size_t>(t) * A], __fmul_rn(y, srow[static_cast<size_t>(t) * A]));
     row[static_cast<size_t>(t) * A] = fminf(fmaxf(v, u_min), u_max);
   });

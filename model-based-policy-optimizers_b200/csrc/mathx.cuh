@@ -21,9 +21,18 @@ __device__ __forceinline__ float bits_to_uniform(uint32_t bits, float lo, float 
 // between log1p implementations (XLA's own is a polynomial), ~20 instructions cheaper.
 // GUARD = false drops the |x| == 1 -> +-inf special case for callers whose argument is provably
 // inside (-1, 1).
+// log(v) = lg2(v) * ln 2 with the bare MUFU.LG2 (lg2.approx.ftz): what __logf computes for a normal v, without
+// the denormal-input guard nvcc wraps around it (three instructions per call).  The callers' arguments are 0
+// (-> -inf in both) or >= 2^-24.
+__device__ __forceinline__ float log_normal_arg(float v) {
+  float l;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(v));
+  return l * 0.693147182f;
+}
+
 template <bool GUARD = true>
 __device__ __forceinline__ float erf_inv_f32(float x) {
-  float w = -__logf(1.0f - __fmul_rn(x, x));
+  float w = -log_normal_arg(1.0f - __fmul_rn(x, x));
   float p;
   if (w < 5.0f) {
     w = w - 2.5f;
@@ -108,10 +117,21 @@ __device__ __forceinline__ float sin_bounded(float x) {
 // atan2(y, x) for finite inputs: atan(min/max) by a degree-17 odd minimax polynomial
 // (max abs error 7e-8 on [0, 1]) and quadrant fix-ups; atan2(+-0, +-0) = +-0 like NumPy/XLA
 // for (0, +0).
+// UNIT = true: the caller guarantees max(|x|, |y|) is a normal float (a [cos, sin] pair out of sincos_bounded has
+// max >= 0.707): min * MUFU.RCP(max) without the zero test and the denormal scaling __fdividef carries -- the
+// same bits as the guarded form for every such input, eight instructions shorter.
+template <bool UNIT = false>
 __device__ __forceinline__ float atan2_bounded(float y, float x) {
   const float ax = fabsf(x), ay = fabsf(y);
   const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-  const float t = (mx > 0.0f) ? __fdividef(mn, mx) : 0.0f;
+  float t;
+  if (UNIT) {
+    float rcp;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(mx));
+    t = __fmul_rn(rcp, mn);
+  } else {
+    t = (mx > 0.0f) ? __fdividef(mn, mx) : 0.0f;
+  }
   const float u = t * t;
   float q = 2.974586547e-03f;
   q = fmaf(q, u, -1.658116880e-02f);

@@ -114,6 +114,25 @@ ScaleTable make_scale_table(const MbpoIcemCfg* c) {
   return t;
 }
 
+int launch_noise_rolled(const MbpoIcemCfg* cfg, const ScaleTable& tbl, const uint32_t* keys, int M, float* noise_out,
+                        uint32_t* bits_out, void* stream) {
+  TwiddleTable tw;
+  fill_twiddles(cfg->horizon, tw);
+  const int threads = STAGED_THREADS;
+  const size_t smem = static_cast<size_t>(threads) * (cfg->horizon | 1) * sizeof(float);
+  const unsigned blocks = static_cast<unsigned>((M + threads - 1) / threads);
+  auto k0 = powerlaw_noise_rt_kernel<0>;
+  auto k1 = powerlaw_noise_rt_kernel<1>;
+  const cudaError_t e = cudaFuncSetAttribute(cfg->prng_mode == 0 ? k0 : k1,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return fail(MBPO_ECUDA, "powerlaw_noise smem attr: %s", cudaGetErrorString(e));
+  if (cfg->prng_mode == 0)
+    k0<<<blocks, threads, smem, as_stream(stream)>>>(tbl, tw, cfg->horizon, keys, M, noise_out, bits_out);
+  else
+    k1<<<blocks, threads, smem, as_stream(stream)>>>(tbl, tw, cfg->horizon, keys, M, noise_out, bits_out);
+  return check_launch("powerlaw_noise_rt_kernel");
+}
+
 // ---- fused plan --------------------------------------------------------------------------
 void fill_plan_args(PlanArgs& a, const MbpoIcemCfg* c, const MbpoPendulumParams* sys, const float* x0,
                     const uint32_t* key_in, const float* best_seq_in, int B, float* best_seq_out,
@@ -156,6 +175,9 @@ int run_plan(const MbpoIcemCfg* c, const void* sys_params_host, const float* x0,
   if (B == 0) return MBPO_OK;
   MBPO_REQUIRE(sys_params_host && x0 && key_in && best_seq_in && best_seq_out && key_out, "plan: null pointer");
   MBPO_REQUIRE(mpc != nullptr || best_value_out != nullptr, "plan: best_value_out is null");
+  // the fused kernel's reward wrap has no fmod slow path (pendulum.cuh wrap_diff<true>): |theta - target + pi| < 4 pi
+  if (!(std::fabs(static_cast<const MbpoPendulumParams*>(sys_params_host)->target_angle) <= 6.0f))
+    return fail(MBPO_EUNSUPPORTED, "fused plan: |target_angle| > 6 rad; use mbpo_icem_plan_staged");
   PlanArgs a;
   fill_plan_args(a, c, static_cast<const MbpoPendulumParams*>(sys_params_host), x0, key_in, best_seq_in, B,
                  best_seq_out, best_value_out, key_out, trace);
@@ -279,11 +301,11 @@ int mbpo_powerlaw_noise(const MbpoIcemCfg* cfg, const uint32_t* keys, int M, flo
   const int rc = validate_cfg(cfg);
   if (rc != MBPO_OK) return rc;
   MBPO_REQUIRE(M >= 0, "powerlaw_noise: M < 0");
-  if (!horizon_supported(cfg->horizon))
-    return fail(MBPO_EUNSUPPORTED, "horizon %d has no compiled sampling kernel (" MBPO_H_LIST_STR ")", cfg->horizon);
   if (M == 0) return MBPO_OK;
   MBPO_REQUIRE(keys && noise_out, "powerlaw_noise: null pointer");
   const ScaleTable tbl = make_scale_table(cfg);
+  // any other horizon: the rolled-loop kernel (same words, same operation order)
+  if (!horizon_supported(cfg->horizon)) return launch_noise_rolled(cfg, tbl, keys, M, noise_out, bits_out, stream);
   switch (cfg->horizon) {
 #define X(h) \
   case h:    \
@@ -294,17 +316,45 @@ int mbpo_powerlaw_noise(const MbpoIcemCfg* cfg, const uint32_t* keys, int M, flo
   return MBPO_EUNSUPPORTED;
 }
 
+int mbpo_powerlaw_noise_rolled(const MbpoIcemCfg* cfg, const uint32_t* keys, int M, float* noise_out,
+                               uint32_t* bits_out, void* stream) {
+  const int rc = validate_cfg(cfg);
+  if (rc != MBPO_OK) return rc;
+  MBPO_REQUIRE(M >= 0, "powerlaw_noise_rolled: M < 0");
+  if (M == 0) return MBPO_OK;
+  MBPO_REQUIRE(keys && noise_out, "powerlaw_noise_rolled: null pointer");
+  return launch_noise_rolled(cfg, make_scale_table(cfg), keys, M, noise_out, bits_out, stream);
+}
+
 int mbpo_icem_sample_actions(const MbpoIcemCfg* cfg, const uint32_t* carry_key, const float* mean, const float* std_,
                              int B, float* actions_out, uint32_t* next_key_out, uint32_t* particle_keys_out,
                              void* stream) {
   const int rc = validate_cfg(cfg);
   if (rc != MBPO_OK) return rc;
   MBPO_REQUIRE(B >= 0 && B <= 65535, "sample_actions: B %d outside [0, 65535]", B);
-  if (!horizon_supported(cfg->horizon))
-    return fail(MBPO_EUNSUPPORTED, "horizon %d has no compiled sampling kernel (" MBPO_H_LIST_STR ")", cfg->horizon);
   if (B == 0) return MBPO_OK;
   MBPO_REQUIRE(carry_key && mean && std_ && actions_out && next_key_out, "sample_actions: null pointer");
   const ScaleTable tbl = make_scale_table(cfg);
+  if (!horizon_supported(cfg->horizon)) {   // any other horizon: the rolled-loop kernel (same words, same order)
+    TwiddleTable tw;
+    fill_twiddles(cfg->horizon, tw);
+    const int threads = STAGED_THREADS;
+    const size_t smem = static_cast<size_t>(threads) * (cfg->horizon | 1) * sizeof(float);
+    const int N = cfg->num_samples, Np = cfg->num_prev_elites, A = cfg->action_dim;
+    const dim3 grid(static_cast<unsigned>(((N + Np) * A + threads - 1) / threads), static_cast<unsigned>(B));
+    auto k0 = sample_actions_rt_kernel<0>;
+    auto k1 = sample_actions_rt_kernel<1>;
+    const cudaError_t e = cudaFuncSetAttribute(cfg->prng_mode == 0 ? k0 : k1,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return fail(MBPO_ECUDA, "sample_actions smem attr: %s", cudaGetErrorString(e));
+    if (cfg->prng_mode == 0)
+      k0<<<grid, threads, smem, as_stream(stream)>>>(tbl, tw, cfg->horizon, carry_key, mean, std_, N, Np, A, cfg->u_min,
+                                                     cfg->u_max, actions_out, next_key_out, particle_keys_out);
+    else
+      k1<<<grid, threads, smem, as_stream(stream)>>>(tbl, tw, cfg->horizon, carry_key, mean, std_, N, Np, A, cfg->u_min,
+                                                     cfg->u_max, actions_out, next_key_out, particle_keys_out);
+    return check_launch("sample_actions_rt_kernel");
+  }
   switch (cfg->horizon) {
 #define X(h)                                                                                                    \
   case h:                                                                                                       \

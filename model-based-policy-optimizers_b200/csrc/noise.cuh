@@ -9,6 +9,7 @@
 // The irfft is a direct real DFT with compile-time twiddles (they fold into FFMA immediates)
 // that exploits y[t], y[H-t] sharing the cosine sum and having opposite sine sums.
 #pragma once
+#include "../../include/mbpo_b200.h"
 #include "mathx.cuh"
 #include "threefry.cuh"
 
@@ -115,34 +116,211 @@ __device__ __forceinline__ void colored_noise_row(Key2 rng, const float* __restr
 #pragma unroll
   for (int k = 1; k < S::F; ++k) si[k] = (k < LASTK) ? stage[S::F + k - 1] : 0.0f;
 
-  // t = 0
-  {
-    float a = sr[0] * tw.c[0];
+  if constexpr (!S::EVEN) {
+    // odd H: outputs t and H - t share the cosine sum and have opposite sine sums
+    {
+      float a = __fmul_rn(sr[0], tw.c[0]);
 #pragma unroll
-    for (int k = 1; k < LASTK; ++k) a = fmaf(sr[k], 2.0f * tw.c[0], a);
-    if (S::EVEN) a = fmaf(sr[S::F - 1], tw.c[0], a);
-    emit(0, a);
-  }
-#pragma unroll
-  for (int t = 1; 2 * t < H; ++t) {
-    float a = sr[0] * tw.c[0];
-    float b = 0.0f;
-#pragma unroll
-    for (int k = 1; k < LASTK; ++k) {
-      a = fmaf(sr[k], 2.0f * tw.c[(k * t) % H], a);
-      b = fmaf(si[k], 2.0f * tw.s[(k * t) % H], b);
+      for (int k = 1; k < LASTK; ++k) a = fmaf(sr[k], 2.0f * tw.c[0], a);
+      emit(0, a);
     }
-    if (S::EVEN) a = fmaf(sr[S::F - 1], (t & 1) ? -tw.c[0] : tw.c[0], a);
-    emit(t, a - b);
-    emit(H - t, a + b);
-  }
-  if (S::EVEN) {
-    constexpr int t = H / 2;
-    float a = sr[0] * tw.c[0];
 #pragma unroll
-    for (int k = 1; k < LASTK; ++k) a = fmaf(sr[k], (k & 1) ? -2.0f * tw.c[0] : 2.0f * tw.c[0], a);
-    a = fmaf(sr[S::F - 1], (t & 1) ? -tw.c[0] : tw.c[0], a);
-    emit(t, a);
+    for (int t = 1; 2 * t < H; ++t) {
+      float a = __fmul_rn(sr[0], tw.c[0]);
+      float b = 0.0f;
+#pragma unroll
+      for (int k = 1; k < LASTK; ++k) {
+        a = fmaf(sr[k], 2.0f * tw.c[(k * t) % H], a);
+        b = fmaf(si[k], 2.0f * tw.s[(k * t) % H], b);
+      }
+      emit(t, __fsub_rn(a, b));
+      emit(H - t, __fadd_rn(a, b));
+    }
+  } else {
+    // even H: one more split.  With h = H/2, cos(2 pi k (t + h) / H) = (-1)^k cos(2 pi k t / H) (sin likewise), so
+    // the even-k and odd-k partial sums ae, ao (cosine) and be, bo (sine) of one t give FOUR outputs:
+    //   y[t]     = (ae + ao) - (be + bo) + n        y[H - t] = (ae + ao) + (be + bo) + n
+    //   y[h + t] = (ae - ao) - (be - bo) + nh       y[h - t] = (ae - ao) + (be - bo) + nh
+    // (n, nh: the Nyquist bin with the sign of (-1)^t, (-1)^(t + h)) -- half the multiply-adds of the t / H - t
+    // pairing alone.  colored_noise_row_rt evaluates the same expressions in the same order.
+    constexpr int h = H / 2;
+    // __fmul_rn / __fadd_rn: a plain product feeding a sum is a candidate for FMA contraction, which the
+    // compiler applies differently in the unrolled and the rolled routine (1 ulp apart); these are not.
+    const float d = __fmul_rn(sr[0], tw.c[0]);
+    const float nq = __fmul_rn(sr[h], tw.c[0]);
+    {
+      float ae = d, ao = 0.0f;
+#pragma unroll
+      for (int k = 1; k < h; ++k) {
+        if (k & 1) ao = fmaf(sr[k], 2.0f * tw.c[0], ao);
+        else ae = fmaf(sr[k], 2.0f * tw.c[0], ae);
+      }
+      emit(0, __fadd_rn(__fadd_rn(ae, ao), nq));
+      emit(h, __fadd_rn(__fsub_rn(ae, ao), (h & 1) ? -nq : nq));
+    }
+#pragma unroll
+    for (int t = 1; 2 * t <= h; ++t) {
+      float ae = d, ao = 0.0f, be = 0.0f, bo = 0.0f;
+#pragma unroll
+      for (int k = 1; k < h; ++k) {
+        if (k & 1) {
+          ao = fmaf(sr[k], 2.0f * tw.c[(k * t) % H], ao);
+          bo = fmaf(si[k], 2.0f * tw.s[(k * t) % H], bo);
+        } else {
+          ae = fmaf(sr[k], 2.0f * tw.c[(k * t) % H], ae);
+          be = fmaf(si[k], 2.0f * tw.s[(k * t) % H], be);
+        }
+      }
+      const float n = (t & 1) ? -nq : nq;
+      const float p = __fadd_rn(ae, ao), r = __fadd_rn(be, bo);
+      emit(t, __fadd_rn(__fsub_rn(p, r), n));
+      emit(H - t, __fadd_rn(__fadd_rn(p, r), n));
+      if (2 * t < h) {
+        const float nh = ((t + h) & 1) ? -nq : nq;
+        const float q = __fsub_rn(ae, ao), v = __fsub_rn(be, bo);
+        emit(h + t, __fadd_rn(__fsub_rn(q, v), nh));
+        emit(h - t, __fadd_rn(__fadd_rn(q, v), nh));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Any horizon (iCemTO(horizon=...) is a free int in the reference, icem_optimizer.py:94-96;
+// powerlaw_psd_gaussian takes any size, general_utils.py:134-143).  Same key tree, same words,
+// same operation ORDER as the unrolled instances above -- so the six compiled horizons give the
+// same bits through either routine -- but rolled loops and a twiddle table in the constant bank
+// (every lane of a warp reads the same entry: a broadcast).  The staged normals stay in `stage`
+// while the outputs are emitted, so `emit` must not write to `stage`.
+// ------------------------------------------------------------------------------------------
+struct TwiddleTable {
+  float c[MBPO_MAX_HORIZON];  // cos(2 pi j / H) / H
+  float s[MBPO_MAX_HORIZON];  // sin(2 pi j / H) / H
+};
+
+// Host: the table detail::Twiddle<H> holds at compile time, by the same double arithmetic.
+inline void fill_twiddles(int H, TwiddleTable& t) {
+  for (int j = 0; j < MBPO_MAX_HORIZON; ++j) t.c[j] = t.s[j] = 0.0f;
+  for (int j = 0; j < H; ++j) {
+    double a = 6.283185307179586476925 * j / H;
+    if (a > 3.14159265358979323846) a -= 6.283185307179586476925;
+    t.c[j] = static_cast<float>(detail::ccos(a) / H);
+    t.s[j] = static_cast<float>(detail::csin(a) / H);
+  }
+}
+
+template <int MODE, bool IMAG>
+__device__ __forceinline__ void stage_normals_rt(int H, Key2 key, const float* __restrict__ scale, float* stage,
+                                                 uint32_t* bits_out) {
+  const int F = H / 2 + 1;
+  const int HALF = (F + (F & 1)) / 2;
+  const int LASTK = (H % 2 == 0) ? F - 1 : F;
+  auto put = [&](int k, uint32_t word) {
+    if (bits_out) bits_out[k] = word;
+    if (!IMAG) {
+      stage[k] = bits_to_normal(word) * scale[k];
+    } else if (k >= 1 && k < LASTK) {
+      stage[F + k - 1] = bits_to_normal(word) * scale[k];
+    }
+  };
+  if (MODE == 1) {
+#pragma unroll 2
+    for (int f = 0; f < F; ++f) {
+      uint32_t x0 = 0u, x1 = static_cast<uint32_t>(f);
+      threefry2x32(key.k0, key.k1, x0, x1);
+      put(f, x0 ^ x1);
+    }
+  } else {
+#pragma unroll 2
+    for (int j = 0; j < HALF; ++j) {
+      uint32_t x0 = static_cast<uint32_t>(j);
+      uint32_t x1 = (HALF + j < F) ? static_cast<uint32_t>(HALF + j) : 0u;
+      threefry2x32(key.k0, key.k1, x0, x1);
+      put(j, x0);
+      if (HALF + j < F) put(HALF + j, x1);
+    }
+  }
+}
+
+template <int MODE, typename Emit>
+__device__ __forceinline__ void colored_noise_row_rt(int H, Key2 rng, const float* __restrict__ scale,
+                                                     const TwiddleTable& tw, float* stage, uint32_t* bits_out,
+                                                     Emit emit) {
+  const int F = H / 2 + 1;
+  const bool even = (H % 2) == 0;
+  const int LASTK = even ? F - 1 : F;
+  Key2 key_sr, key_si;
+  split3_first2<MODE>(rng, key_sr, key_si);
+  stage_normals_rt<MODE, false>(H, key_sr, scale, stage, bits_out);
+  stage_normals_rt<MODE, true>(H, key_si, scale, stage, bits_out ? bits_out + F : nullptr);
+  const float* sr = stage;          // sr[k], k in [0, F)
+  const float* si = stage + F - 1;  // si[k], k in [1, LASTK)
+  const float c0 = tw.c[0];
+  if (!even) {
+    {
+      float a = __fmul_rn(sr[0], c0);
+      for (int k = 1; k < LASTK; ++k) a = fmaf(sr[k], 2.0f * c0, a);
+      emit(0, a);
+    }
+    for (int t = 1; 2 * t < H; ++t) {
+      float a = __fmul_rn(sr[0], c0);
+      float b = 0.0f;
+      int j = 0;  // (k * t) % H
+#pragma unroll 4
+      for (int k = 1; k < LASTK; ++k) {
+        j += t;
+        if (j >= H) j -= H;
+        a = fmaf(sr[k], 2.0f * tw.c[j], a);
+        b = fmaf(si[k], 2.0f * tw.s[j], b);
+      }
+      emit(t, __fsub_rn(a, b));
+      emit(H - t, __fadd_rn(a, b));
+    }
+  } else {
+    const int h = H / 2;
+    const float d = __fmul_rn(sr[0], c0);
+    const float nq = __fmul_rn(sr[h], c0);
+    {
+      float ae = d, ao = 0.0f;
+      for (int k = 1; k + 1 < h; k += 2) {
+        ao = fmaf(sr[k], 2.0f * c0, ao);
+        ae = fmaf(sr[k + 1], 2.0f * c0, ae);
+      }
+      if ((h & 1) == 0) ao = fmaf(sr[h - 1], 2.0f * c0, ao);   // k = h - 1 is odd and has no even partner below h
+      emit(0, __fadd_rn(__fadd_rn(ae, ao), nq));
+      emit(h, __fadd_rn(__fsub_rn(ae, ao), (h & 1) ? -nq : nq));
+    }
+    for (int t = 1; 2 * t <= h; ++t) {
+      float ae = d, ao = 0.0f, be = 0.0f, bo = 0.0f;
+      int j = 0;  // (k * t) % H
+#pragma unroll 2
+      for (int k = 1; k + 1 < h; k += 2) {
+        j += t;
+        if (j >= H) j -= H;
+        ao = fmaf(sr[k], 2.0f * tw.c[j], ao);
+        bo = fmaf(si[k], 2.0f * tw.s[j], bo);
+        j += t;
+        if (j >= H) j -= H;
+        ae = fmaf(sr[k + 1], 2.0f * tw.c[j], ae);
+        be = fmaf(si[k + 1], 2.0f * tw.s[j], be);
+      }
+      if ((h & 1) == 0) {
+        j += t;
+        if (j >= H) j -= H;
+        ao = fmaf(sr[h - 1], 2.0f * tw.c[j], ao);
+        bo = fmaf(si[h - 1], 2.0f * tw.s[j], bo);
+      }
+      const float n = (t & 1) ? -nq : nq;
+      const float p = __fadd_rn(ae, ao), r = __fadd_rn(be, bo);
+      emit(t, __fadd_rn(__fsub_rn(p, r), n));
+      emit(H - t, __fadd_rn(__fadd_rn(p, r), n));
+      if (2 * t < h) {
+        const float nh = ((t + h) & 1) ? -nq : nq;
+        const float q = __fsub_rn(ae, ao), v = __fsub_rn(be, bo);
+        emit(h + t, __fadd_rn(__fsub_rn(q, v), nh));
+        emit(h - t, __fadd_rn(__fadd_rn(q, v), nh));
+      }
+    }
   }
 }
 

@@ -81,6 +81,23 @@ __device__ __forceinline__ void pendulum_step_ref(const PendulumConsts& p, float
   w = nw;
 }
 
+// The same reference-literal step for a loop that only needs the rewards: theta = atan2(sin, cos) of the CURRENT
+// state comes in, theta of the NEXT state goes out -- atan2 of the freshly computed [cos(newth), sin(newth)] as
+// pendulum_dynamics.py:35 evaluates it at the next step, so every value has the bits pendulum_step_ref produces;
+// the pair is a unit vector, which lets atan2 skip its zero / denormal guard.  The first theta of a rollout is
+// atan2_bounded(s0, c0) (guarded: the caller's initial state is arbitrary).
+template <bool SMALL = false>
+__device__ __forceinline__ void pendulum_step_ref_th(const PendulumConsts& p, float& th, float& w, float u,
+                                                     float& reward) {
+  reward = reward_from<SMALL>(p, th, w, u);
+  const float nw = pendulum_next_thdot(p, sin_bounded(th), w, u);
+  const float nth = fmaf(nw, p.dt, th);
+  float s, c;
+  sincos_bounded(nth, s, c);
+  th = atan2_bounded<true>(s, c);
+  w = nw;
+}
+
 // Theta-carry variant: the state is (theta, thdot) with theta kept in (-pi, pi], which is
 // what atan2(sin(newth), cos(newth)) returns up to rounding.
 template <bool SMALL = false>

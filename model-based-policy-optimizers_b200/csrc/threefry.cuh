@@ -78,6 +78,15 @@ __device__ __forceinline__ uint32_t random_bits_at(Key2 key, uint32_t n, uint32_
   return legacy_word(key, n, w);
 }
 
+// split(key, 1)[0]: both words of the only child come out of ONE block in either layout (legacy: counters
+// (0, 1) -> flat [y0, y1]; partitionable: counter (0, 0) -> (y0, y1)).
+template <int MODE>
+__device__ __forceinline__ Key2 split1(Key2 key) {
+  uint32_t x0 = 0u, x1 = (MODE == 1) ? 0u : 1u;
+  threefry2x32(key.k0, key.k1, x0, x1);
+  return Key2{x0, x1};
+}
+
 // split(key, 2) -> both children.  Legacy: flat = [y0(0,2), y0(1,3), y1(0,2), y1(1,3)].
 template <int MODE>
 __device__ __forceinline__ void split2(Key2 key, Key2& a, Key2& b) {

@@ -108,6 +108,7 @@ SIGNATURES = {
     "mbpo_prng_uniform": (_I, [_P, _I, _I, _I, _F, _F, _P, _P]),
     "mbpo_prng_normal": (_I, [_P, _I, _I, _I, _P, _P]),
     "mbpo_powerlaw_noise": (_I, [C.POINTER(IcemCfgC), _P, _I, _P, _P, _P]),
+    "mbpo_powerlaw_noise_rolled": (_I, [C.POINTER(IcemCfgC), _P, _I, _P, _P, _P]),
     "mbpo_icem_sample_actions": (_I, [C.POINTER(IcemCfgC), _P, _P, _P, _I, _P, _P, _P, _P]),
     "mbpo_system_step": (_I, [_I, _P, _I, _P, _P, _I, _P, _P, _P]),
     "mbpo_rollout_actions": (_I, [_I, _P, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P]),

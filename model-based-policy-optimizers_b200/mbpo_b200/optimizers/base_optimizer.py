@@ -46,6 +46,7 @@ class BaseOptimizer:
                                                sample_batch_size=1)
         if key.dim() == 1:
             return sampling_buffer.init(key)
-        state = sampling_buffer.init(key.reshape(-1, 2)[0])
         batch = tuple(key.shape[:-1])
+        flat = key.reshape(-1, 2)
+        state = sampling_buffer.init(flat[0] if flat.shape[0] else torch.zeros((2,), dtype=key.dtype, device=dev))
         return state.replace(ring=state.ring.expand(batch + tuple(state.ring.shape)).contiguous(), key=key)

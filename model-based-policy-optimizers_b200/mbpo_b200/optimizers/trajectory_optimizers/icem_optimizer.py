@@ -131,6 +131,14 @@ class iCemTO(BaseOptimizer):
         cfg.math_mode = config.math_mode_id
         return cfg
 
+    def _fused(self, cfg, packed_params) -> bool:
+        """Whether mbpo_icem_plan / mbpo_icem_mpc_closed_loop (one launch) take this configuration; otherwise the
+        staged plan (the same per-stage kernels, one launch per stage and iteration) runs it."""
+        if not _lib.lib.mbpo_icem_plan_is_fused(_lib.C.byref(cfg)):
+            return False
+        target = getattr(packed_params, "target_angle", 0.0)        # the fused reward wrap assumes |target| <= 6 rad
+        return abs(float(target)) <= 6.0
+
     # ---- reference API -------------------------------------------------------------------------
     def init(self, key: torch.Tensor, true_buffer_state=None) -> iCemOptimizerState:
         """icem_optimizer.py:121-132.  key [2] -> single-problem state; key [B, 2] -> B problems."""
@@ -161,7 +169,7 @@ class iCemTO(BaseOptimizer):
         out_key = torch.empty((B, 2), dtype=torch.uint32, device=dev)
         params = self.system.pack_params(system_params)
         tr_c, tr = None, None
-        fused = bool(_lib.lib.mbpo_icem_plan_is_fused(_lib.C.byref(cfg)))
+        fused = self._fused(cfg, params)
         with _lib.cuda_guard(x0):
             if fused:
                 if trace:
@@ -179,9 +187,11 @@ class iCemTO(BaseOptimizer):
                                                    _lib.ptr(out_val), _lib.ptr(out_key),
                                                    _lib.C.byref(tr_c) if tr_c is not None else None,
                                                    _lib.stream_ptr(dev)))
+            elif trace:
+                # the per-stage kernels composed from Python dump the same per-iteration arrays (and give the
+                # same bits as mbpo_icem_plan_staged: the same kernels in the same order)
+                return self._plan_general(x0, key, best_seq, system_params, trace=True)
             else:
-                if trace:
-                    raise _lib.MbpoUnsupported(_lib.MBPO_EUNSUPPORTED, "trace dumps exist for the fused plan only")
                 nbytes = _lib.lib.mbpo_icem_workspace_bytes(_lib.C.byref(cfg), B)
                 ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
                 _lib.check(_lib.lib.mbpo_icem_plan_staged(_lib.C.byref(cfg), _lib.C.addressof(params), _lib.ptr(x0),
@@ -295,11 +305,11 @@ class iCemTO(BaseOptimizer):
     def closed_loop(self, initial_state: torch.Tensor, opt_state: iCemOptimizerState, num_steps: int):
         """Returns (states [T, (B,) X], rewards [T, (B)], actions [T, (B,) A], new opt_state)."""
         assert self.system is not None, "iCem optimizer requires system to be defined."
-        if self.cost_fn is not None or self._array_bounds():
-            raise _lib.MbpoUnsupported(_lib.MBPO_EUNSUPPORTED, "closed_loop runs the fused plan kernel, which has no "
-                                       "cost_fn / array-valued bounds; loop over act() instead")
         single, x0, key, seq = self._canon(initial_state, opt_state)
         cfg = self._cfg()
+        params = self.system.pack_params(opt_state.system_params)
+        if self.cost_fn is not None or self._array_bounds() or not self._fused(cfg, params):
+            return self._closed_loop_staged(single, x0, key, seq, opt_state, num_steps)
         B, dev = x0.shape[0], x0.device
         H, A = self.opt_dim
         states = torch.empty((num_steps, B, x0.shape[1]), dtype=torch.float32, device=dev)
@@ -307,7 +317,6 @@ class iCemTO(BaseOptimizer):
         actions = torch.empty((num_steps, B, A), dtype=torch.float32, device=dev)
         out_seq = torch.empty((B, H, A), dtype=torch.float32, device=dev)
         out_key = torch.empty((B, 2), dtype=torch.uint32, device=dev)
-        params = self.system.pack_params(opt_state.system_params)
         with _lib.cuda_guard(x0):
             _lib.check(_lib.lib.mbpo_icem_mpc_closed_loop(
                 _lib.C.byref(cfg), _lib.C.addressof(params), _lib.ptr(x0), _lib.ptr(key), _lib.ptr(seq), B, num_steps,
@@ -316,6 +325,31 @@ class iCemTO(BaseOptimizer):
         if single:
             states, rewards, actions, out_seq, out_key = states[:, 0], rewards[:, 0], actions[:, 0], out_seq[0], out_key[0]
         return states, rewards, actions, opt_state.replace(key=out_key, best_sequence=out_seq)
+
+
+    def _closed_loop_staged(self, single, x0, key, seq, opt_state, num_steps):
+        """The same loop for configurations without a fused kernel (cost_fn, array-valued bounds, a horizon without an
+        unrolled instance, a population beyond shared memory, a learned System): plan -> System.step -> warm start,
+        one plan call and one step launch per MPC step, all on the device."""
+        states, rewards, actions = [], [], []
+        sp = opt_state.system_params
+        x = x0
+        for _ in range(num_steps):
+            seq, _, key, _ = self._plan_raw(x, key, seq, sp)
+            u = seq[:, 0, :].contiguous()
+            nxt = self.system.step(x, u, sp)
+            x = nxt.x_next
+            states.append(x); rewards.append(nxt.reward); actions.append(u)
+        B, dev = x0.shape[0], x0.device
+        if num_steps:
+            states, rewards, actions = torch.stack(states), torch.stack(rewards), torch.stack(actions)
+        else:
+            states = torch.empty((0, B, x0.shape[1]), dtype=torch.float32, device=dev)
+            rewards = torch.empty((0, B), dtype=torch.float32, device=dev)
+            actions = torch.empty((0, B, self.action_dim), dtype=torch.float32, device=dev)
+        if single:
+            states, rewards, actions, seq, key = states[:, 0], rewards[:, 0], actions[:, 0], seq[0], key[0]
+        return states, rewards, actions, opt_state.replace(key=key, best_sequence=seq)
 
 
 class iCEMOptimizer(BaseOptimizer):

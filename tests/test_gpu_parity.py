@@ -187,6 +187,146 @@ def test_sample_actions(mb, cuda_device, prng_mode, horizon, action_dim):
 
 
 # ---------------------------------------------------------------------------------------------
+# any horizon: iCemTO(horizon=h) is a free int in the reference (icem_optimizer.py:94-96)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("horizon", [2, 3, 4, 6, 7, 10, 11, 13, 21, 25, 33, 40, 47, 64, 77, 128])
+def test_any_horizon_noise_vs_oracle(mb, cuda_device, prng_mode, horizon, budget_report):
+    """Horizons without an unrolled instance run the rolled-loop kernel: words bit-exact, floats to tolerance and
+    inside the float64 budget, for even / odd / prime / maximal sizes."""
+    L = mb._lib
+    exponent = 1.0 if horizon % 3 else 0.0
+    _, cfg = _cfg(mb, horizon, dict(exponent=exponent))
+    M = 200
+    keys = _keys(M, seed=100 + horizon)
+    F = horizon // 2 + 1
+    dkeys = _dev(keys, cuda_device)
+    out = torch.empty((M, horizon), dtype=torch.float32, device=cuda_device)
+    bits = torch.empty((M, 2, F), dtype=torch.uint32, device=cuda_device)
+    L.check(L.lib.mbpo_powerlaw_noise(L.C.byref(cfg), L.ptr(dkeys), M, L.ptr(out), L.ptr(bits),
+                                      L.stream_ptr(cuda_device)))
+    want, br, bi = orc.powerlaw_psd_gaussian_keys(exponent, horizon, keys, prng_mode, return_bits=True)
+    got_bits = bits.cpu().numpy()
+    assert np.array_equal(got_bits[:, 0], br) and np.array_equal(got_bits[:, 1], bi)
+    np.testing.assert_allclose(out.cpu().numpy(), want, rtol=RTOL, atol=5e-6)
+    truth = ft.powerlaw_truth(exponent, horizon, br, bi)
+    f_gpu = float(np.abs(out.cpu().numpy() - truth).max() / ft.noise_budget(horizon))
+    budget_report("gpu/noise_rolled_H%d_%s" % (horizon, "part" if prng_mode else "legacy"), noise_frac=f_gpu)
+    assert f_gpu <= 1.0, f_gpu
+
+
+@pytest.mark.parametrize("horizon", [5, 8, 15, 20, 30, 50])
+@pytest.mark.parametrize("exponent", [0.0, 2.0])
+def test_rolled_noise_kernel_bit_identical_to_unrolled(mb, cuda_device, prng_mode, horizon, exponent):
+    """Same key tree, same words, same operation order: at the six unrolled horizons the any-horizon kernel gives
+    the unrolled instances' bits (so a plan's results do not depend on which one sampled it)."""
+    L = mb._lib
+    _, cfg = _cfg(mb, horizon, dict(exponent=exponent))
+    M = 1000
+    dkeys = _dev(_keys(M, seed=7 * horizon), cuda_device)
+    a, b = (torch.empty((M, horizon), dtype=torch.float32, device=cuda_device) for _ in range(2))
+    ba, bb = (torch.empty((M, 2, horizon // 2 + 1), dtype=torch.uint32, device=cuda_device) for _ in range(2))
+    L.check(L.lib.mbpo_powerlaw_noise(L.C.byref(cfg), L.ptr(dkeys), M, L.ptr(a), L.ptr(ba), L.stream_ptr(cuda_device)))
+    L.check(L.lib.mbpo_powerlaw_noise_rolled(L.C.byref(cfg), L.ptr(dkeys), M, L.ptr(b), L.ptr(bb),
+                                             L.stream_ptr(cuda_device)))
+    assert torch.equal(ba.view(torch.int32), bb.view(torch.int32))
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("horizon,action_dim", [(10, 1), (25, 1), (7, 2)])
+def test_any_horizon_sample_actions(mb, cuda_device, prng_mode, horizon, action_dim):
+    L = mb._lib
+    params = dict(num_samples=64, num_elites=10, exponent=1.0)
+    _, cfg = _cfg(mb, horizon, params, action_dim)
+    B, N, Np = 4, 64, cfg.num_prev_elites
+    rng = np.random.default_rng(1)
+    keys = _keys(B, seed=9)
+    mean = rng.uniform(-0.5, 0.5, (B, horizon, action_dim)).astype(np.float32)
+    std = rng.uniform(0.1, 0.8, (B, horizon, action_dim)).astype(np.float32)
+    acts = torch.empty((B, N + Np, horizon, action_dim), dtype=torch.float32, device=cuda_device)
+    nk = torch.empty((B, 2), dtype=torch.uint32, device=cuda_device)
+    pk = torch.empty((B, N + Np, 2), dtype=torch.uint32, device=cuda_device)
+    dk, dm, ds = _dev(keys, cuda_device), _dev(mean, cuda_device), _dev(std, cuda_device)
+    L.check(L.lib.mbpo_icem_sample_actions(L.C.byref(cfg), L.ptr(dk), L.ptr(dm), L.ptr(ds), B, L.ptr(acts), L.ptr(nk),
+                                           L.ptr(pk), L.stream_ptr(cuda_device)))
+    p = orc.ICemParams(**params)
+    for b in range(B):
+        want_key, want_acts, want_pk = orc.icem_sample_actions(keys[b], mean[b], std[b], p, horizon, action_dim,
+                                                               prng_mode)
+        assert np.array_equal(nk[b].cpu().numpy(), want_key) and np.array_equal(pk[b].cpu().numpy(), want_pk)
+        np.testing.assert_allclose(acts[b].cpu().numpy(), want_acts, rtol=RTOL, atol=5e-6)
+        assert np.all(acts[b, N:].cpu().numpy() == 0.0)
+
+
+@pytest.mark.parametrize("horizon", [10, 25, 40])
+def test_any_horizon_plan_vs_oracle(mb, cuda_device, horizon, budget_report):
+    """iCemTO(horizon=h) for horizons without a fused kernel: the staged plan (same per-stage kernels) against the
+    oracle, free-running with the explanation walk; act() (the C staged plan) gives the traced composition's bits;
+    the closed loop runs as plan -> System.step launches and reaches the reference test's threshold scaled to its
+    length."""
+    from mbpo_b200.optimizers import iCemTO, iCemParams
+    from mbpo_b200.systems import PendulumSystem
+    B = 5
+    params = dict(num_samples=150, num_elites=15, num_particles=1, num_steps=3)
+    opt = iCemTO(horizon=horizon, action_dim=1, opt_params=iCemParams(**params))
+    system = PendulumSystem()
+    opt.set_system(system)
+    assert mb._lib.lib.mbpo_icem_plan_is_fused(mb._lib.C.byref(opt._cfg())) == 0
+    keys = _keys(B, seed=200 + horizon)
+    x0 = _random_states(B, 201 + horizon)
+    st, seq, val = _free_running_vs_oracle("any_horizon_H%d" % horizon, opt, mb, cuda_device, x0, keys, params,
+                                           horizon, budget_report)
+    action, new = opt.act(_dev(x0, cuda_device), st)
+    assert torch.equal(new.best_sequence, seq) and torch.equal(new.best_reward, val)
+    states, rewards, actions, fin = opt.closed_loop(_dev(x0, cuda_device), st, 3)
+    assert states.shape == (3, B, 3) and rewards.shape == (3, B) and actions.shape == (3, B, 1)
+    assert torch.equal(actions[0], action)
+    one = system.step(_dev(x0, cuda_device), action, st.system_params)
+    assert torch.equal(states[0], one.x_next) and torch.equal(rewards[0], one.reward)
+
+
+@pytest.mark.parametrize("target", [0.0, 3.0, -6.0, 7.5, 40.0])
+def test_plan_target_angle_inside_and_outside_the_fused_range(mb, cuda_device, target):
+    """The fused kernel's reward wrap assumes |target_angle| <= 6 rad (no fmod slow path in its instruction stream);
+    beyond that the same plan runs staged.  Either way the returns match the oracle's floored mod
+    (pendulum_reward.py:34-35) and best_reward is the return of best_sequence."""
+    from mbpo_b200.optimizers import iCemTO, iCemParams
+    from mbpo_b200.systems import PendulumSystem, PendulumRewardParams, SystemParams, PendulumDynamicsParams
+    from mbpo_b200.utils import rollout_returns
+    H, B = 20, 6
+    opt = iCemTO(horizon=H, action_dim=1, opt_params=iCemParams(num_samples=128, num_elites=16, num_particles=1,
+                                                                 num_steps=3))
+    system = PendulumSystem()
+    opt.set_system(system)
+    sp = SystemParams(dynamics_params=PendulumDynamicsParams(), reward_params=PendulumRewardParams(target_angle=target))
+    st = opt.init(_dev(_keys(B, seed=61), cuda_device)).replace(system_params=sp)
+    x0 = _random_states(B, 62)
+    assert opt._fused(opt._cfg(), system.pack_params(sp)) == (abs(target) <= 6.0)
+    action, new = opt.act(_dev(x0, cuda_device), st)
+    ret = rollout_returns(system, sp, _dev(x0, cuda_device), new.best_sequence.reshape(B, 1, H, 1))[:, 0]
+    assert torch.equal(ret, new.best_reward)                      # fused and staged rollouts: the same bits
+    p = orc.PendulumParams(target_angle=target)
+    want = orc.rollout_actions(x0, new.best_sequence.cpu().numpy().reshape(B, H), p)
+    r64 = orc.rollout_actions(x0.astype(np.float64), new.best_sequence.cpu().numpy().reshape(B, H).astype(np.float64),
+                              p, dtype=np.float64)
+    np.testing.assert_allclose(ret.cpu().numpy(), r64, rtol=RTOL, atol=2e-6)
+    np.testing.assert_allclose(want, r64, rtol=RTOL, atol=2e-6)
+
+
+def test_icemopt_reference_test_at_an_uncompiled_horizon(mb, cuda_device):
+    """tests/test_icemopt.py with horizon=25 (no unrolled kernel): the closed loop still swings the pendulum up."""
+    from mbpo_b200.optimizers import iCemTO, iCemParams
+    from mbpo_b200.systems import PendulumSystem
+    jr = mb.random
+    ks = jr.split(jr.PRNGKey(0, cuda_device), 3)
+    system = PendulumSystem()
+    system_state = system.reset(ks[2])
+    cem = iCemTO(horizon=25, action_dim=1, system=None, opt_params=iCemParams(num_particles=1), key=ks[0])
+    cem.set_system(system)
+    states, rewards, actions, _ = cem.closed_loop(system_state.x_next, cem.init(ks[1]), 200)
+    assert float(rewards.sum()) >= -400, float(rewards.sum())
+
+
+# ---------------------------------------------------------------------------------------------
 # stage 2: System.step and rollouts
 # ---------------------------------------------------------------------------------------------
 def _random_states(n, seed):
@@ -495,8 +635,13 @@ def test_plan_with_cost_fn_vs_oracle(mb, cuda_device, use_pessimism, budget_repo
     np.testing.assert_allclose(new.best_reward.cpu().numpy(), want, rtol=1e-6, atol=1e-6)
     # the constraint binds for fast initial states: penalised value below the plain return there
     assert np.all(new.best_reward.cpu().numpy() <= p3(rew) + 1e-6)
-    with pytest.raises(mb.MbpoUnsupported):                                       # closed loop is the fused kernel only
-        opt.closed_loop(_dev(x0, cuda_device), st, 2)
+    # the closed loop of a configuration without a fused kernel: plan -> System.step launches, same bits as act()
+    states, rewards, actions, _ = opt.closed_loop(_dev(x0, cuda_device), st, 2)
+    assert torch.equal(actions[0], action)
+    one = system.step(_dev(x0, cuda_device), action, st.system_params)
+    assert torch.equal(states[0], one.x_next) and torch.equal(rewards[0], one.reward)
+    a2, _ = opt.act(one.x_next, new)
+    assert torch.equal(actions[1], a2)
 
 
 def test_plan_with_array_bounds_vs_oracle(mb, cuda_device, budget_report):
@@ -1134,10 +1279,10 @@ def test_errors(mb, cuda_device):
     oc.set_system(PendulumSystem())
     with pytest.raises(NotImplementedError):
         oc.act(torch.tensor([-1.0, 0.0, 0.0], device=cuda_device), oc.init(mb.random.PRNGKey(0, cuda_device)))
-    opt = iCemTO(horizon=21, action_dim=1, opt_params=iCemParams(num_particles=1))   # no compiled kernel for H=21
+    opt = iCemTO(horizon=200, action_dim=1, opt_params=iCemParams(num_particles=1))  # beyond MBPO_MAX_HORIZON = 128
     opt.set_system(PendulumSystem())
     st = opt.init(mb.random.PRNGKey(0, cuda_device))
-    with pytest.raises(mb.MbpoUnsupported):
+    with pytest.raises(mb.MbpoError):
         opt.act(torch.tensor([-1.0, 0.0, 0.0], device=cuda_device), st)
     with pytest.raises(mb.MbpoError):                                                # CPU tensors are refused
         PendulumSystem().step(torch.zeros(3), torch.zeros(1), st.system_params)
@@ -1188,10 +1333,12 @@ def test_full_size_config2_properties(mb, cuda_device, budget_report):
     # return inside its float64 amplification bound, refit bit-exact given the kernel's own actions and values.
     pick = np.sort(np.random.default_rng(5).choice(B, 32, replace=False))
     pk = torch.from_numpy(pick).to(cuda_device)
-    xs, ks, bs = x0[pk].contiguous(), st.key[pk].contiguous(), st.best_sequence[pk].contiguous()
+    # (torch has no CUDA index kernel for uint32: index the int32 view of the keys)
+    xs, bs = x0[pk].contiguous(), st.best_sequence[pk].contiguous()
+    ks = st.key.view(torch.int32)[pk].contiguous().view(torch.uint32)
     seq_s, val_s, key_s, tr = opt._plan_raw(xs, ks, bs, st.system_params, trace=True)
     assert torch.equal(seq_s, n1.best_sequence[pk]) and torch.equal(val_s, n1.best_reward[pk])
-    assert torch.equal(key_s, n1.key[pk])
+    assert torch.equal(key_s.view(torch.int32), n1.key.view(torch.int32)[pk])
     tr = {k: v.cpu().numpy() for k, v in tr.items()}
     p = orc.ICemParams(num_samples=512, num_particles=1)
     x0n, kn = xs.cpu().numpy(), ks.cpu().numpy()
