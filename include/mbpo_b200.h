@@ -177,6 +177,18 @@ int mbpo_icem_plan(const MbpoIcemCfg* cfg_host, const void* sys_params_host,
                    const float* best_seq_in /*[B,H,A]*/, int B, float* best_seq_out /*[B,H,A]*/,
                    float* best_value_out /*[B]*/, uint32_t* key_out /*[B,2]*/,
                    const MbpoIcemTrace* trace_host /*NULL = no dumps*/, void* stream);
+/* The same plan with an explicit thread-block-cluster size: few problems leave most of the 148 SMs idle when each
+ * gets one CTA, so a problem can be spread over a cluster of 2, 4 or 8 CTAs whose elite exchange runs through
+ * distributed shared memory (csrc/icem_cluster_kernels.cuh).  Results are bit-identical for every cluster size.
+ * cluster_size: -1 = the library's choice for (B, num_samples) -- what mbpo_icem_plan uses; 1 = one CTA per
+ * problem; 2, 4, 8.  mbpo_icem_plan_cluster_size returns that choice (0 or 1: no cluster).
+ * Reference: icem_optimizer.py:134-252 at B = 1 is tests/test_icemopt.py's shape. */
+int mbpo_icem_plan_clustered(const MbpoIcemCfg* cfg_host, const void* sys_params_host, const float* x0,
+                             const uint32_t* key_in, const float* best_seq_in, int B, float* best_seq_out,
+                             float* best_value_out, uint32_t* key_out, const MbpoIcemTrace* trace_host,
+                             int cluster_size, void* stream);
+int mbpo_icem_plan_cluster_size(const MbpoIcemCfg* cfg_host, int B);
+
 /* 1 if mbpo_icem_plan runs this configuration as the single fused kernel, 0 if it composes
  * the staged kernels through `workspace`. */
 int mbpo_icem_plan_is_fused(const MbpoIcemCfg* cfg_host);
@@ -206,6 +218,11 @@ int mbpo_icem_mpc_closed_loop(const MbpoIcemCfg* cfg_host, const void* sys_param
                               float* states_out /*[T,B,X]*/, float* rewards_out /*[T,B]*/,
                               float* actions_out /*[T,B,A]*/, float* best_seq_out /*[B,H,A]*/,
                               uint32_t* key_out /*[B,2]*/, void* stream);
+int mbpo_icem_mpc_closed_loop_clustered(const MbpoIcemCfg* cfg_host, const void* sys_params_host, const float* x0,
+                                        const uint32_t* key_in, const float* best_seq_in, int B, int num_mpc_steps,
+                                        float* states_out, float* rewards_out, float* actions_out,
+                                        float* best_seq_out, uint32_t* key_out, int cluster_size, void* stream);
+
 
 /* ---- vmapped env rollouts for SAC/PPO collection ---------------------------------------- */
 /* brax_wrapper.py:40-50 + brax_utils/training.py:71-74,91-107,119-137 + sac/acting.py:35-55.

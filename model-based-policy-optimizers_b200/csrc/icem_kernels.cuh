@@ -17,11 +17,11 @@ namespace mbpo {
 // (icem_optimizer.py:160 inner jnp.mean over rollout_actions(...).reward).
 // ------------------------------------------------------------------------------------------
 // SMALL: the host checked |target_angle| <= 6, so the reward's floored mod needs no fmod slow path.
+// th0 = atan2_bounded(s0, c0) of the initial state.
 template <int MATH, bool SMALL = false, typename ActFn>
-__device__ __forceinline__ float rollout_return(const PendulumConsts& pc, float c0, float s0, float w0, int H,
-                                                ActFn act) {
+__device__ __forceinline__ float rollout_return_th(const PendulumConsts& pc, float th0, float w0, int H, ActFn act) {
   float acc = 0.0f;
-  float th = atan2_bounded(s0, c0), w = w0;
+  float th = th0, w = w0;
 #pragma unroll 2
   for (int t = 0; t < H; ++t) {
     float r;
@@ -30,6 +30,12 @@ __device__ __forceinline__ float rollout_return(const PendulumConsts& pc, float 
     acc = __fadd_rn(acc, r);
   }
   return __fdiv_rn(acc, static_cast<float>(H));
+}
+
+template <int MATH, bool SMALL = false, typename ActFn>
+__device__ __forceinline__ float rollout_return(const PendulumConsts& pc, float c0, float s0, float w0, int H,
+                                                ActFn act) {
+  return rollout_return_th<MATH, SMALL>(pc, atan2_bounded(s0, c0), w0, H, act);
 }
 
 // Two independent rollouts from the same initial state (th0 = atan2(s0, c0), computed once per problem by the

@@ -167,7 +167,7 @@ int plan_fusable(const MbpoIcemCfg* c, bool set_error) {
 
 int run_plan(const MbpoIcemCfg* c, const void* sys_params_host, const float* x0, const uint32_t* key_in,
              const float* best_seq_in, int B, float* best_seq_out, float* best_value_out, uint32_t* key_out,
-             const MbpoIcemTrace* trace, const MpcArgs* mpc, void* stream) {
+             const MbpoIcemTrace* trace, const MpcArgs* mpc, int cluster_size, void* stream) {
   int rc = validate_cfg(c);
   if (rc != MBPO_OK) return rc;
   MBPO_REQUIRE(B >= 0, "plan: B < 0");
@@ -181,10 +181,19 @@ int run_plan(const MbpoIcemCfg* c, const void* sys_params_host, const float* x0,
   PlanArgs a;
   fill_plan_args(a, c, static_cast<const MbpoPendulumParams*>(sys_params_host), x0, key_in, best_seq_in, B,
                  best_seq_out, best_value_out, key_out, trace);
+  // few problems: spread each over a thread-block cluster (same bits; icem_cluster_kernels.cuh)
+  int cluster = cluster_size;
+  if (cluster < 0) cluster = plan_cluster_size(B, a.N);
+  if (cluster > 1) {
+    MBPO_REQUIRE(cluster == 2 || cluster == 4 || cluster == 8 || cluster == 16,
+                 "plan: cluster_size %d (use -1, 1, 2, 4, 8 or 16)", cluster);
+    const int R = (a.N + cluster - 1) / cluster;
+    if (R > 256) return fail(MBPO_EUNSUPPORTED, "plan: %d candidates per CTA of a %d-cluster (at most 256)", R, cluster);
+  }
   switch (c->horizon) {
 #define X(h) \
   case h:    \
-    return plan_entry<h>(c->prng_mode, c->math_mode, a, mpc, as_stream(stream));
+    return plan_entry<h>(c->prng_mode, c->math_mode, a, mpc, as_stream(stream), cluster);
     MBPO_FOR_EACH_H(X)
 #undef X
     default:
@@ -470,7 +479,20 @@ int mbpo_icem_plan(const MbpoIcemCfg* cfg, const void* sys_params_host, const fl
                    const float* best_seq_in, int B, float* best_seq_out, float* best_value_out, uint32_t* key_out,
                    const MbpoIcemTrace* trace_host, void* stream) {
   return run_plan(cfg, sys_params_host, x0, key_in, best_seq_in, B, best_seq_out, best_value_out, key_out,
-                  trace_host, nullptr, stream);
+                  trace_host, nullptr, -1, stream);
+}
+
+int mbpo_icem_plan_clustered(const MbpoIcemCfg* cfg, const void* sys_params_host, const float* x0,
+                             const uint32_t* key_in, const float* best_seq_in, int B, float* best_seq_out,
+                             float* best_value_out, uint32_t* key_out, const MbpoIcemTrace* trace_host,
+                             int cluster_size, void* stream) {
+  return run_plan(cfg, sys_params_host, x0, key_in, best_seq_in, B, best_seq_out, best_value_out, key_out,
+                  trace_host, nullptr, cluster_size, stream);
+}
+
+int mbpo_icem_plan_cluster_size(const MbpoIcemCfg* cfg, int B) {
+  if (validate_cfg(cfg) != MBPO_OK || !plan_fusable(cfg, false)) return 0;
+  return plan_cluster_size(B, cfg->num_samples);
 }
 
 // Staged plan workspace layout (floats unless noted), all [B, ...]:
@@ -601,6 +623,14 @@ int mbpo_icem_mpc_closed_loop(const MbpoIcemCfg* cfg, const void* sys_params_hos
                               const uint32_t* key_in, const float* best_seq_in, int B, int num_mpc_steps,
                               float* states_out, float* rewards_out, float* actions_out, float* best_seq_out,
                               uint32_t* key_out, void* stream) {
+  return mbpo_icem_mpc_closed_loop_clustered(cfg, sys_params_host, x0, key_in, best_seq_in, B, num_mpc_steps,
+                                             states_out, rewards_out, actions_out, best_seq_out, key_out, -1, stream);
+}
+
+int mbpo_icem_mpc_closed_loop_clustered(const MbpoIcemCfg* cfg, const void* sys_params_host, const float* x0,
+                                        const uint32_t* key_in, const float* best_seq_in, int B, int num_mpc_steps,
+                                        float* states_out, float* rewards_out, float* actions_out,
+                                        float* best_seq_out, uint32_t* key_out, int cluster_size, void* stream) {
   MBPO_REQUIRE(num_mpc_steps >= 0, "mpc_closed_loop: num_mpc_steps < 0");
   MpcArgs m;
   m.T = num_mpc_steps;
@@ -608,7 +638,7 @@ int mbpo_icem_mpc_closed_loop(const MbpoIcemCfg* cfg, const void* sys_params_hos
   m.rewards_out = rewards_out;
   m.actions_out = actions_out;
   return run_plan(cfg, sys_params_host, x0, key_in, best_seq_in, B, best_seq_out, nullptr, key_out, nullptr, &m,
-                  stream);
+                  cluster_size, stream);
 }
 
 // ---- env rollouts ----------------------------------------------------------------------------------

@@ -63,9 +63,13 @@ struct NoiseShape {
 // so the H needed values fill exactly the H floats of the caller's row.  The threefry blocks run
 // in a rolled loop (small code: the instruction cache matters more than the last bit of ILP);
 // `scale` is indexed dynamically (constant bank / shared memory).
+// One unit of that work: in the legacy layout threefry block j, whose two words are normals j and HALF + j; in the
+// partitionable layout the block of word j.  NoiseShape<H>::tasks(MODE) units make one half spectrum; they are
+// independent, so one thread may run them in a loop (stage_normals) or several threads may share them (the
+// cluster plan, icem_cluster_kernels.cuh) with the same results.
 template <int H, int MODE, bool IMAG>
-__device__ __forceinline__ void stage_normals(Key2 key, const float* __restrict__ scale, float* stage,
-                                              uint32_t* bits_out) {
+__device__ __forceinline__ void stage_normals_task(Key2 key, const float* __restrict__ scale, float* stage,
+                                                   uint32_t* bits_out, int j) {
   using S = NoiseShape<H>;
   constexpr int LASTK = S::EVEN ? S::F - 1 : S::F;
   auto put = [&](int k, uint32_t word) {
@@ -77,55 +81,57 @@ __device__ __forceinline__ void stage_normals(Key2 key, const float* __restrict_
     }
   };
   if (MODE == 1) {
-#pragma unroll 2
-    for (int f = 0; f < S::F; ++f) {
-      uint32_t x0 = 0u, x1 = static_cast<uint32_t>(f);
-      threefry2x32(key.k0, key.k1, x0, x1);
-      put(f, x0 ^ x1);
-    }
+    uint32_t x0 = 0u, x1 = static_cast<uint32_t>(j);
+    threefry2x32(key.k0, key.k1, x0, x1);
+    put(j, x0 ^ x1);
   } else {
-#pragma unroll 2
-    for (int j = 0; j < S::HALF; ++j) {
-      uint32_t x0 = static_cast<uint32_t>(j);
-      uint32_t x1 = (S::HALF + j < S::F) ? static_cast<uint32_t>(S::HALF + j) : 0u;
-      threefry2x32(key.k0, key.k1, x0, x1);
-      put(j, x0);
-      if (S::HALF + j < S::F) put(S::HALF + j, x1);
-    }
+    uint32_t x0 = static_cast<uint32_t>(j);
+    uint32_t x1 = (S::HALF + j < S::F) ? static_cast<uint32_t>(S::HALF + j) : 0u;
+    threefry2x32(key.k0, key.k1, x0, x1);
+    put(j, x0);
+    if (S::HALF + j < S::F) put(S::HALF + j, x1);
   }
 }
 
-// Emits y[t] for every t in [0, H) through emit(t, value).  `stage` is H floats private to the
-// calling thread (its own shared-memory action row: emit may overwrite it, every staged value is
-// in a register by then).  `scale` may live in shared or constant memory (F floats).
-template <int H, int MODE, typename Emit>
-__device__ __forceinline__ void colored_noise_row(Key2 rng, const float* __restrict__ scale, float* stage,
-                                                  uint32_t* bits_out, Emit emit) {
+template <int H, int MODE>
+__host__ __device__ constexpr int noise_tasks() { return MODE == 1 ? NoiseShape<H>::F : NoiseShape<H>::HALF; }
+
+template <int H, int MODE, bool IMAG>
+__device__ __forceinline__ void stage_normals(Key2 key, const float* __restrict__ scale, float* stage,
+                                              uint32_t* bits_out) {
+#pragma unroll 2
+  for (int j = 0; j < noise_tasks<H, MODE>(); ++j) stage_normals_task<H, MODE, IMAG>(key, scale, stage, bits_out, j);
+}
+
+// The inverse real DFT as independent GROUPS of outputs (each output is one thread's multiply-add chain in a fixed
+// order, so the groups may run in one thread one after the other or in different threads):
+//   odd H :  group 0 = {y[0]};  group t = {y[t], y[H - t]}, t = 1 .. (H - 1) / 2   (shared cosine sum, opposite sine sums)
+//   even H:  one more split.  With h = H/2, cos(2 pi k (t + h) / H) = (-1)^k cos(2 pi k t / H) (sin likewise), so the
+//            even-k and odd-k partial sums ae, ao (cosine) and be, bo (sine) of one t give FOUR outputs:
+//              y[t]     = (ae + ao) - (be + bo) + n        y[H - t] = (ae + ao) + (be + bo) + n
+//              y[h + t] = (ae - ao) - (be - bo) + nh       y[h - t] = (ae - ao) + (be - bo) + nh
+//            (n, nh: the Nyquist bin with the sign of (-1)^t, (-1)^(t + h)) -- half the multiply-adds of the t / H - t
+//            pairing alone.  group 0 = {y[0], y[h]};  group t = those four (two when 2 t == h), t = 1 .. h / 2.
+// colored_noise_row_rt evaluates the same expressions in the same order.  __fmul_rn / __fadd_rn where a plain
+// product feeds a sum: such a pair is a candidate for FMA contraction, which the compiler applies differently in
+// differently shaped code (1 ulp apart); these are not.
+template <int H>
+__host__ __device__ constexpr int dft_groups() { return (H % 2 == 0) ? 1 + (H / 2) / 2 : 1 + (H - 1) / 2; }
+
+template <int H, int G, typename Emit>
+__device__ __forceinline__ void dft_group(const float (&sr)[NoiseShape<H>::F], const float (&si)[NoiseShape<H>::F],
+                                          Emit emit) {
   using S = NoiseShape<H>;
   constexpr detail::Twiddle<H> tw{};
   constexpr int LASTK = S::EVEN ? S::F - 1 : S::F;  // bins [1, LASTK) have weight 2
-  Key2 key_sr, key_si;
-  split3_first2<MODE>(rng, key_sr, key_si);
-  stage_normals<H, MODE, false>(key_sr, scale, stage, bits_out);
-  stage_normals<H, MODE, true>(key_si, scale, stage, bits_out ? bits_out + S::F : nullptr);
-
-  float sr[S::F], si[S::F];
-#pragma unroll
-  for (int k = 0; k < S::F; ++k) sr[k] = stage[k];
-  si[0] = 0.0f;
-#pragma unroll
-  for (int k = 1; k < S::F; ++k) si[k] = (k < LASTK) ? stage[S::F + k - 1] : 0.0f;
-
+  constexpr int t = G;
   if constexpr (!S::EVEN) {
-    // odd H: outputs t and H - t share the cosine sum and have opposite sine sums
-    {
+    if constexpr (G == 0) {
       float a = __fmul_rn(sr[0], tw.c[0]);
 #pragma unroll
       for (int k = 1; k < LASTK; ++k) a = fmaf(sr[k], 2.0f * tw.c[0], a);
       emit(0, a);
-    }
-#pragma unroll
-    for (int t = 1; 2 * t < H; ++t) {
+    } else {
       float a = __fmul_rn(sr[0], tw.c[0]);
       float b = 0.0f;
 #pragma unroll
@@ -137,18 +143,10 @@ __device__ __forceinline__ void colored_noise_row(Key2 rng, const float* __restr
       emit(H - t, __fadd_rn(a, b));
     }
   } else {
-    // even H: one more split.  With h = H/2, cos(2 pi k (t + h) / H) = (-1)^k cos(2 pi k t / H) (sin likewise), so
-    // the even-k and odd-k partial sums ae, ao (cosine) and be, bo (sine) of one t give FOUR outputs:
-    //   y[t]     = (ae + ao) - (be + bo) + n        y[H - t] = (ae + ao) + (be + bo) + n
-    //   y[h + t] = (ae - ao) - (be - bo) + nh       y[h - t] = (ae - ao) + (be - bo) + nh
-    // (n, nh: the Nyquist bin with the sign of (-1)^t, (-1)^(t + h)) -- half the multiply-adds of the t / H - t
-    // pairing alone.  colored_noise_row_rt evaluates the same expressions in the same order.
     constexpr int h = H / 2;
-    // __fmul_rn / __fadd_rn: a plain product feeding a sum is a candidate for FMA contraction, which the
-    // compiler applies differently in the unrolled and the rolled routine (1 ulp apart); these are not.
     const float d = __fmul_rn(sr[0], tw.c[0]);
     const float nq = __fmul_rn(sr[h], tw.c[0]);
-    {
+    if constexpr (G == 0) {
       float ae = d, ao = 0.0f;
 #pragma unroll
       for (int k = 1; k < h; ++k) {
@@ -157,9 +155,7 @@ __device__ __forceinline__ void colored_noise_row(Key2 rng, const float* __restr
       }
       emit(0, __fadd_rn(__fadd_rn(ae, ao), nq));
       emit(h, __fadd_rn(__fsub_rn(ae, ao), (h & 1) ? -nq : nq));
-    }
-#pragma unroll
-    for (int t = 1; 2 * t <= h; ++t) {
+    } else {
       float ae = d, ao = 0.0f, be = 0.0f, bo = 0.0f;
 #pragma unroll
       for (int k = 1; k < h; ++k) {
@@ -175,7 +171,7 @@ __device__ __forceinline__ void colored_noise_row(Key2 rng, const float* __restr
       const float p = __fadd_rn(ae, ao), r = __fadd_rn(be, bo);
       emit(t, __fadd_rn(__fsub_rn(p, r), n));
       emit(H - t, __fadd_rn(__fadd_rn(p, r), n));
-      if (2 * t < h) {
+      if constexpr (2 * t < h) {
         const float nh = ((t + h) & 1) ? -nq : nq;
         const float q = __fsub_rn(ae, ao), v = __fsub_rn(be, bo);
         emit(h + t, __fadd_rn(__fsub_rn(q, v), nh));
@@ -183,6 +179,55 @@ __device__ __forceinline__ void colored_noise_row(Key2 rng, const float* __restr
       }
     }
   }
+}
+
+// Loads the staged half spectra of one row into registers.
+template <int H>
+__device__ __forceinline__ void load_staged(const float* stage, float (&sr)[NoiseShape<H>::F],
+                                            float (&si)[NoiseShape<H>::F]) {
+  using S = NoiseShape<H>;
+  constexpr int LASTK = S::EVEN ? S::F - 1 : S::F;
+#pragma unroll
+  for (int k = 0; k < S::F; ++k) sr[k] = stage[k];
+  si[0] = 0.0f;
+#pragma unroll
+  for (int k = 1; k < S::F; ++k) si[k] = (k < LASTK) ? stage[S::F + k - 1] : 0.0f;
+}
+
+namespace detail {
+template <int H, int G, typename Emit>
+__device__ __forceinline__ void dft_all_groups(const float (&sr)[NoiseShape<H>::F],
+                                               const float (&si)[NoiseShape<H>::F], Emit emit) {
+  if constexpr (G < dft_groups<H>()) {
+    dft_group<H, G>(sr, si, emit);
+    dft_all_groups<H, G + 1>(sr, si, emit);
+  }
+}
+// group g (runtime, uniform across the caller's warp) of the row
+template <int H, int G, typename Emit>
+__device__ __forceinline__ void dft_one_group(int g, const float (&sr)[NoiseShape<H>::F],
+                                              const float (&si)[NoiseShape<H>::F], Emit emit) {
+  if constexpr (G < dft_groups<H>()) {
+    if (g == G) dft_group<H, G>(sr, si, emit);
+    else dft_one_group<H, G + 1>(g, sr, si, emit);
+  }
+}
+}  // namespace detail
+
+// Emits y[t] for every t in [0, H) through emit(t, value).  `stage` is H floats private to the
+// calling thread (its own shared-memory action row: emit may overwrite it, every staged value is
+// in a register by then).  `scale` may live in shared or constant memory (F floats).
+template <int H, int MODE, typename Emit>
+__device__ __forceinline__ void colored_noise_row(Key2 rng, const float* __restrict__ scale, float* stage,
+                                                  uint32_t* bits_out, Emit emit) {
+  using S = NoiseShape<H>;
+  Key2 key_sr, key_si;
+  split3_first2<MODE>(rng, key_sr, key_si);
+  stage_normals<H, MODE, false>(key_sr, scale, stage, bits_out);
+  stage_normals<H, MODE, true>(key_si, scale, stage, bits_out ? bits_out + S::F : nullptr);
+  float sr[S::F], si[S::F];
+  load_staged<H>(stage, sr, si);
+  detail::dft_all_groups<H, 0>(sr, si, emit);
 }
 
 // ------------------------------------------------------------------------------------------

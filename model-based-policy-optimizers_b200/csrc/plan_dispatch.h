@@ -3,14 +3,26 @@
 // declares what those units define.
 #pragma once
 #include "host_util.h"
+#include "icem_cluster_kernels.cuh"
 #include "icem_kernels.cuh"
 
 namespace mbpo {
 
 // Fused plan (mpc == nullptr) or closed-loop MPC (mpc != nullptr); selects PRNG / MATH
-// template variants from prng_mode / math_mode.
+// template variants from prng_mode / math_mode.  cluster > 1: every problem is spread over a thread-block cluster
+// of that many CTAs (icem_cluster_kernels.cuh; same bits, for few problems); 0 / 1: one CTA per problem.
 template <int H>
-int plan_entry(int prng_mode, int math_mode, const PlanArgs& a, const MpcArgs* mpc, cudaStream_t st);
+int plan_entry(int prng_mode, int math_mode, const PlanArgs& a, const MpcArgs* mpc, cudaStream_t st, int cluster);
+
+// Cluster size the library picks for B problems of N candidates (0: one CTA per problem).
+inline int plan_cluster_size(int B, int N) {
+  const int sms = device_sm_count();
+  if (B <= 0 || B >= sms) return 0;
+  int c = 8;    // the portable maximum; 16 (non-portable) is available on request
+  while (c > 1 && (B * c > sms || (N + c - 1) / c < 32)) c >>= 1;
+  if (c <= 1 || (N + c - 1) / c > 256) return 0;
+  return c;
+}
 
 // vmap(powerlaw_psd_gaussian) over M keys.
 template <int H>

@@ -26,6 +26,60 @@ int prepare_plan_kernel(Kernel kernel, size_t smem, int B, int* grid_out) {
   return MBPO_OK;
 }
 
+// One problem per cluster of `cluster` CTAs (icem_cluster_kernels.cuh).
+template <int PRNG, int MATH>
+int launch_cluster(const PlanArgs& a, const MpcArgs* mpc, cudaStream_t st, int cluster) {
+  const int R = (a.N + cluster - 1) / cluster;               // candidates per CTA, one per thread
+  // one rollout thread per candidate; a CTA with few rows still gets 8 warps: they share the sampling of every
+  // row (coop_sample_chunk) and speed up the selection
+  int threads = (R + 31) / 32 * 32;
+  if (R <= COOP_MAX_ROWS) threads = 256;
+  if (threads < 64) threads = 64;                            // the prologue wants a thread per horizon step
+  const size_t smem = ClusterSmem<kH>::bytes(R, a.N, a.Np, a.K);
+  const int sms = device_sm_count();
+  long long clusters = sms / cluster;
+  if (clusters > a.B) clusters = a.B;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(clusters * cluster), 1, 1);
+  cfg.blockDim = dim3(static_cast<unsigned>(threads), 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(cluster);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e;
+  if (mpc == nullptr) {
+    auto kernel = icem_plan_cluster_kernel<kH, PRNG, MATH>;
+    if (cluster > 8) {
+      e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      if (e != cudaSuccess) return fail(MBPO_ECUDA, "cluster plan: non-portable cluster size: %s", cudaGetErrorString(e));
+    }
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return fail(MBPO_ECUDA, "cluster plan smem attr (%zu): %s", smem, cudaGetErrorString(e));
+    zero_row_value_kernel<MATH><<<(a.B + 127) / 128, 128, 0, st>>>(a.sys, kH, a.P, a.summarize, a.x0, a.B,
+                                                                  a.best_value_out);
+    const int rc = check_launch("zero_row_value_kernel");
+    if (rc != MBPO_OK) return rc;
+    e = cudaLaunchKernelEx(&cfg, kernel, a, R);
+    if (e != cudaSuccess) return fail(MBPO_ECUDA, "icem_plan_cluster_kernel launch: %s", cudaGetErrorString(e));
+    return check_launch("icem_plan_cluster_kernel");
+  }
+  auto kernel = icem_mpc_cluster_kernel<kH, PRNG, MATH>;
+  if (cluster > 8) {
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return fail(MBPO_ECUDA, "cluster mpc: non-portable cluster size: %s", cudaGetErrorString(e));
+  }
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return fail(MBPO_ECUDA, "cluster mpc smem attr (%zu): %s", smem, cudaGetErrorString(e));
+  e = cudaLaunchKernelEx(&cfg, kernel, a, *mpc, R);
+  if (e != cudaSuccess) return fail(MBPO_ECUDA, "icem_mpc_cluster_kernel launch: %s", cudaGetErrorString(e));
+  return check_launch("icem_mpc_cluster_kernel");
+}
+
 template <int PRNG, int MATH>
 int launch(const PlanArgs& a, const MpcArgs* mpc, cudaStream_t st) {
   const size_t smem = PlanSmem<kH>::bytes(a.N, a.Np, a.K);
@@ -53,7 +107,16 @@ int launch(const PlanArgs& a, const MpcArgs* mpc, cudaStream_t st) {
 }  // namespace
 
 template <>
-int plan_entry<MBPO_INST_H>(int prng_mode, int math_mode, const PlanArgs& a, const MpcArgs* mpc, cudaStream_t st) {
+int plan_entry<MBPO_INST_H>(int prng_mode, int math_mode, const PlanArgs& a, const MpcArgs* mpc, cudaStream_t st,
+                            int cluster) {
+  if (cluster > 1) {
+    switch (prng_mode * 2 + math_mode) {
+      case 0: return launch_cluster<0, 0>(a, mpc, st, cluster);
+      case 1: return launch_cluster<0, 1>(a, mpc, st, cluster);
+      case 2: return launch_cluster<1, 0>(a, mpc, st, cluster);
+      default: return launch_cluster<1, 1>(a, mpc, st, cluster);
+    }
+  }
   switch (prng_mode * 2 + math_mode) {
     case 0: return launch<0, 0>(a, mpc, st);
     case 1: return launch<0, 1>(a, mpc, st);
@@ -86,5 +149,14 @@ int sample_entry<MBPO_INST_H>(int prng_mode, const ScaleTable& tbl, const uint32
                                                            actions, next_key, particle_keys);
   return check_launch("sample_actions_kernel");
 }
+
+#ifdef MBPO_CLUSTER_CLOCKS
+extern "C" int mbpo_debug_cluster_clocks(long long* out_host) {
+  return cudaMemcpyFromSymbol(out_host, g_cluster_clocks, sizeof(long long) * 64) == cudaSuccess ? 0 : -3;
+}
+extern "C" int mbpo_debug_select_clocks(long long* out_host) {
+  return cudaMemcpyFromSymbol(out_host, g_select_clocks, sizeof(long long) * 16) == cudaSuccess ? 0 : -3;
+}
+#endif
 
 }  // namespace mbpo

@@ -156,8 +156,10 @@ class iCemTO(BaseOptimizer):
         )
 
     def _plan_raw(self, x0: torch.Tensor, key: torch.Tensor, best_seq: torch.Tensor, system_params,
-                  trace: bool = False):
-        """x0 [B,X], key [B,2], best_seq [B,H,A] -> (best_seq', best_value, key', trace dict|None)."""
+                  trace: bool = False, cluster: int = -1):
+        """x0 [B,X], key [B,2], best_seq [B,H,A] -> (best_seq', best_value, key', trace dict|None).
+        cluster: thread-block-cluster size of the fused plan (-1: the library's choice for B; 1, 2, 4, 8: forced --
+        every choice gives the same bits)."""
         if self.cost_fn is not None or self._array_bounds():
             return self._plan_general(x0, key, best_seq, system_params, trace=trace)
         cfg = self._cfg()
@@ -182,11 +184,10 @@ class iCemTO(BaseOptimizer):
                               best_value=torch.empty((S, B), dtype=torch.float32, device=dev))
                     tr_c = _lib.IcemTraceC(*(_lib.ptr(tr[n]) for n in ("actions", "values", "elite_idx", "mean",
                                                                         "std", "best_value")))
-                _lib.check(_lib.lib.mbpo_icem_plan(_lib.C.byref(cfg), _lib.C.addressof(params), _lib.ptr(x0),
-                                                   _lib.ptr(key), _lib.ptr(best_seq), B, _lib.ptr(out_seq),
-                                                   _lib.ptr(out_val), _lib.ptr(out_key),
-                                                   _lib.C.byref(tr_c) if tr_c is not None else None,
-                                                   _lib.stream_ptr(dev)))
+                _lib.check(_lib.lib.mbpo_icem_plan_clustered(
+                    _lib.C.byref(cfg), _lib.C.addressof(params), _lib.ptr(x0), _lib.ptr(key), _lib.ptr(best_seq), B,
+                    _lib.ptr(out_seq), _lib.ptr(out_val), _lib.ptr(out_key),
+                    _lib.C.byref(tr_c) if tr_c is not None else None, int(cluster), _lib.stream_ptr(dev)))
             elif trace:
                 # the per-stage kernels composed from Python dump the same per-iteration arrays (and give the
                 # same bits as mbpo_icem_plan_staged: the same kernels in the same order)
@@ -302,8 +303,10 @@ class iCemTO(BaseOptimizer):
         return new_opt_state.action, new_opt_state
 
     # ---- additive: closed loop in one launch (tests/test_icemopt.py:19-32) ---------------------
-    def closed_loop(self, initial_state: torch.Tensor, opt_state: iCemOptimizerState, num_steps: int):
-        """Returns (states [T, (B,) X], rewards [T, (B)], actions [T, (B,) A], new opt_state)."""
+    def closed_loop(self, initial_state: torch.Tensor, opt_state: iCemOptimizerState, num_steps: int,
+                    cluster: int = -1):
+        """Returns (states [T, (B,) X], rewards [T, (B)], actions [T, (B,) A], new opt_state).  cluster: as in
+        ``_plan_raw`` (a single problem is spread over 8 SMs by default)."""
         assert self.system is not None, "iCem optimizer requires system to be defined."
         single, x0, key, seq = self._canon(initial_state, opt_state)
         cfg = self._cfg()
@@ -318,10 +321,10 @@ class iCemTO(BaseOptimizer):
         out_seq = torch.empty((B, H, A), dtype=torch.float32, device=dev)
         out_key = torch.empty((B, 2), dtype=torch.uint32, device=dev)
         with _lib.cuda_guard(x0):
-            _lib.check(_lib.lib.mbpo_icem_mpc_closed_loop(
+            _lib.check(_lib.lib.mbpo_icem_mpc_closed_loop_clustered(
                 _lib.C.byref(cfg), _lib.C.addressof(params), _lib.ptr(x0), _lib.ptr(key), _lib.ptr(seq), B, num_steps,
                 _lib.ptr(states), _lib.ptr(rewards), _lib.ptr(actions), _lib.ptr(out_seq), _lib.ptr(out_key),
-                _lib.stream_ptr(dev)))
+                int(cluster), _lib.stream_ptr(dev)))
         if single:
             states, rewards, actions, out_seq, out_key = states[:, 0], rewards[:, 0], actions[:, 0], out_seq[0], out_key[0]
         return states, rewards, actions, opt_state.replace(key=out_key, best_sequence=out_seq)

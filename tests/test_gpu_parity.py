@@ -765,6 +765,67 @@ def test_icemopt_closed_loop_kernel_matches_python_loop(mb, cuda_device, prng_mo
 
 
 # ---------------------------------------------------------------------------------------------
+# few problems: one problem per thread-block cluster (csrc/icem_cluster_kernels.cuh) -- same bits
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("horizon,params,B", [
+    (20, dict(), 1),                                                             # tests/test_icemopt.py's shape
+    (30, dict(num_samples=512, num_particles=1), 3),                             # config 2's problem
+    (30, dict(num_samples=512, num_particles=1, exponent=2.0, alpha=0.1), 2),
+    (8, dict(num_samples=40, num_elites=7, num_steps=3, warm_start=False), 5),   # 5 candidates per CTA of 8
+    (15, dict(num_samples=100, num_elites=20, num_steps=2, exponent=1.0), 2),    # ragged split, odd horizon
+    (50, dict(num_samples=1024, num_particles=1, num_steps=2), 1),               # 256 candidates per CTA at C = 4
+])
+def test_cluster_plan_bit_identical(mb, cuda_device, prng_mode, horizon, params, B):
+    """A problem spread over a cluster of 2 / 4 / 8 / 16 CTAs (keys, elite rows and refit columns exchanged through
+    distributed shared memory; few rows per CTA: the sampling of a row shared by several warps) gives the one-CTA
+    kernel's bits: final state and every per-iteration dump (actions, values, elite indices, mean, std, best value)."""
+    from mbpo_b200.systems import PendulumSystem
+    opt, cfg = _cfg(mb, horizon, params)
+    sp = PendulumSystem().reset(device=cuda_device).system_params
+    x0 = _dev(_random_states(B, 301), cuda_device)
+    keys = _dev(_keys(B, seed=302), cuda_device)
+    seq = _dev(np.random.default_rng(303).uniform(-1, 1, (B, horizon, 1)).astype(np.float32), cuda_device)
+    ref = opt._plan_raw(x0, keys, seq, sp, trace=True, cluster=1)
+    N = cfg.num_samples
+    for c in (2, 4, 8, 16):
+        if (N + c - 1) // c > 256:
+            with pytest.raises(mb.MbpoUnsupported):
+                opt._plan_raw(x0, keys, seq, sp, cluster=c)
+            continue
+        got = opt._plan_raw(x0, keys, seq, sp, trace=True, cluster=c)
+        assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]), "cluster %d" % c
+        assert torch.equal(got[2].view(torch.int32), ref[2].view(torch.int32))
+        for name in ("actions", "values", "elite_idx", "mean", "std", "best_value"):
+            assert torch.equal(got[3][name], ref[3][name]), "cluster %d: %s" % (c, name)
+    auto = opt._plan_raw(x0, keys, seq, sp)                                       # the library's own choice
+    assert torch.equal(auto[0], ref[0]) and torch.equal(auto[1], ref[1])
+
+
+def test_cluster_choice_and_closed_loop(mb, cuda_device, prng_mode):
+    """The library spreads few problems over clusters by itself (B = 1 -> 8 CTAs) and the closed loop
+    (tests/test_icemopt.py:19-32) on a cluster reproduces the one-CTA closed loop bit for bit."""
+    L = mb._lib
+    system, system_state, cem, st = _icemopt_setup(mb, cuda_device)
+    cfg = cem._cfg()
+    sizes = {B: L.lib.mbpo_icem_plan_cluster_size(L.C.byref(cfg), B) for B in (1, 8, 18, 19, 37, 64, 74, 75, 148, 4096)}
+    assert sizes[1] == 8 and sizes[8] == 8 and sizes[18] == 8 and sizes[19] == 4 and sizes[37] == 4
+    assert sizes[64] == 2 and sizes[74] == 2 and sizes[75] in (0, 1) and sizes[4096] in (0, 1)
+    one = cem.closed_loop(system_state.x_next, st, 40, cluster=1)
+    for c in (2, 8, 16, -1):
+        got = cem.closed_loop(system_state.x_next, st, 40, cluster=c)
+        for a, b in zip(one[:3], got[:3]):
+            assert torch.equal(a, b), "cluster %d" % c
+        assert torch.equal(one[3].best_sequence, got[3].best_sequence)
+        assert torch.equal(one[3].key.view(torch.int32), got[3].key.view(torch.int32))
+    # a batch of closed loops on clusters (B = 3 -> 8 CTAs each)
+    x3 = _dev(_random_states(3, 311), cuda_device)
+    st3 = cem.init(_dev(_keys(3, seed=312), cuda_device))
+    a = cem.closed_loop(x3, st3, 5, cluster=1)
+    b = cem.closed_loop(x3, st3, 5, cluster=4)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+
+
+# ---------------------------------------------------------------------------------------------
 # config 3: vmapped env rollouts with Episode / AutoReset bookkeeping
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("E,T,episode_length,action_repeat", [(1000, 57, 20, 1), (77, 40, 7, 2), (4096, 16, 200, 1)])
