@@ -40,7 +40,10 @@ enum {
 
 enum { MBPO_PRNG_LEGACY = 0, MBPO_PRNG_PARTITIONABLE = 1 }; /* jax_threefry_partitionable */
 enum { MBPO_SUMMARIZE_MEAN = 0, MBPO_SUMMARIZE_MAX = 1 };   /* icem_optimizer.py:112-115 */
-enum { MBPO_SYSTEM_PENDULUM = 0, MBPO_SYSTEM_MLP_ENSEMBLE = 1 };
+/* 2, 3: the general Systems (csrc/systems.cuh) -- a pendulum whose transition is SAMPLED with the System's own key
+ * (the per-particle key of icem_optimizer.py:146-156) and a two-action point mass (action_dim > 1, :180). */
+enum { MBPO_SYSTEM_PENDULUM = 0, MBPO_SYSTEM_MLP_ENSEMBLE = 1, MBPO_SYSTEM_NOISY_PENDULUM = 2,
+       MBPO_SYSTEM_POINT_MASS = 3 };
 /* MBPO_MATH_REFERENCE follows pendulum_dynamics.py:35,43 literally (theta re-derived with
  * atan2 from [cos, sin] every step).  MBPO_MATH_THETA_CARRY keeps theta in a register and
  * wraps it to (-pi, pi]; mathematically identical, rounding differs. */
@@ -52,6 +55,18 @@ typedef struct MbpoPendulumParams {
   float max_speed, max_torque, dt, g, m, l;
   float control_cost, angle_cost, target_angle;
 } MbpoPendulumParams;
+
+/* Parameters of the general Systems: MBPO_SYSTEM_NOISY_PENDULUM reads `pendulum` and `noise_std` (the scale of the
+ * Normal that PendulumDynamics.next_state returns, pendulum_dynamics.py:45-46 -- 0 in the reference);
+ * MBPO_SYSTEM_POINT_MASS reads `point_mass` (state [px, py, vx, vy], action [ax, ay]). */
+typedef struct MbpoPointMassParams {
+  float dt, max_accel, max_speed, target_x, target_y, speed_cost, control_cost;
+} MbpoPointMassParams;
+typedef struct MbpoGeneralSystemParams {
+  MbpoPendulumParams pendulum;
+  float noise_std;
+  MbpoPointMassParams point_mass;
+} MbpoGeneralSystemParams;
 
 /* Learned MLP-ensemble System (template: mbpo/utils/network_utils.py:5-17, swish).
  * E members of [x_dim+u_dim -> hidden -> hidden -> hidden -> x_dim], predicting delta-x.
@@ -112,7 +127,7 @@ int mbpo_abi_version(void);
 const char* mbpo_last_error(void);
 /* sizeof() of the ABI structs, so that a foreign binding can verify its own layout:
  * which = 0 MbpoIcemCfg, 1 MbpoPendulumParams, 2 MbpoMlpEnsembleParams, 3 MbpoIcemTrace,
- * 4 MbpoPolicyParams, 5 MbpoReplayState, 6 MbpoReplayFields;
+ * 4 MbpoPolicyParams, 5 MbpoReplayState, 6 MbpoReplayFields, 7 MbpoGeneralSystemParams;
  * anything else returns 0. */
 size_t mbpo_struct_size(int which);
 
@@ -162,6 +177,24 @@ int mbpo_rollout_actions(int system_kind, const void* sys_params_host, int math_
                          int horizon, int action_dim, int x_dim, const float* x0,
                          const float* actions, int B, int M, float* returns_out, float* obs_out,
                          float* reward_out, float* next_obs_out, void* stream);
+
+/* ---- general Systems: any action_dim, key-consuming transitions ------------------------ */
+/* vmap(System.step) for MBPO_SYSTEM_PENDULUM / _NOISY_PENDULUM / _POINT_MASS: x [R,X], u [R,A]; keys_in / keys_out
+ * uint32 [R,2] are system_params.key before / after the step (NULL for a System that draws nothing). */
+int mbpo_system_step_general(int system_kind, const MbpoGeneralSystemParams* params_host, int prng_mode,
+                             const float* x, const float* u, const uint32_t* keys_in, int R, float* x_next,
+                             float* reward, uint32_t* keys_out, void* stream);
+/* vmap(vmap(objective)) (icem_optimizer.py:144-160,195) over B problems x M candidates: actions [B,M,H,A],
+ * keys [B,M,2] = split(particles_rng, N+Np) (:177; NULL for a System that draws nothing).
+ * num_particles >= 1: split(key, P) (:155), one rollout per particle key, horizon mean, then the left-to-right mean
+ * (MBPO_SUMMARIZE_MEAN) or the max over particles -> values_out [B,M].
+ * num_particles == 0: vmap(rollout_actions) (optimizer_utils.py:11-59) -- ONE rollout per row with keys[b,m] as
+ * system_params.key; values_out (horizon mean) and the Transition buffers obs_out [B,M,H,X], reward_out [B,M,H],
+ * next_obs_out [B,M,H,X] are each optional. */
+int mbpo_system_objective(int system_kind, const MbpoGeneralSystemParams* params_host, int prng_mode, int horizon,
+                          const float* x0 /*[B,X]*/, const float* actions, const uint32_t* keys, int B, int M,
+                          int num_particles, int summarize, float* values_out, float* obs_out, float* reward_out,
+                          float* next_obs_out, void* stream);
 
 /* ---- stage 3: elite selection + refit + best tracking (icem_optimizer.py:199-226) ------- */
 int mbpo_icem_elite_refit(const MbpoIcemCfg* cfg_host, const float* actions /*[B,M,H*A]*/,

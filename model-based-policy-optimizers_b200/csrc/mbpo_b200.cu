@@ -20,6 +20,7 @@
 #include "ensemble_pp_kernels.cuh"
 #include "plan_dispatch.h"
 #include "staged_kernels.cuh"
+#include "systems.cuh"
 
 namespace mbpo {
 thread_local char g_err[512] = "";
@@ -221,6 +222,7 @@ size_t mbpo_struct_size(int which) {
     case 4: return sizeof(MbpoPolicyParams);
     case 5: return sizeof(MbpoReplayState);
     case 6: return sizeof(MbpoReplayFields);
+    case 7: return sizeof(MbpoGeneralSystemParams);
     default: return 0;
   }
 }
@@ -440,6 +442,87 @@ int mbpo_rollout_actions(int system_kind, const void* sys_params_host, int math_
   return check_launch("rollout_actions_pendulum_kernel");
 }
 
+// ---- general Systems (any action_dim, key-consuming) ---------------------------------------------
+extern "C++" {
+namespace {
+bool general_kind(int k) {
+  return k == MBPO_SYSTEM_PENDULUM || k == MBPO_SYSTEM_NOISY_PENDULUM || k == MBPO_SYSTEM_POINT_MASS;
+}
+int general_dims(int kind, int* X, int* A, bool* keyed) {
+  switch (kind) {
+    case MBPO_SYSTEM_PENDULUM: *X = 3; *A = 1; *keyed = false; return MBPO_OK;
+    case MBPO_SYSTEM_NOISY_PENDULUM: *X = 3; *A = 1; *keyed = true; return MBPO_OK;
+    case MBPO_SYSTEM_POINT_MASS: *X = 4; *A = 2; *keyed = false; return MBPO_OK;
+    default: return mbpo::fail(MBPO_EUNSUPPORTED, "system_kind %d is not one of the general Systems", kind);
+  }
+}
+}  // namespace
+}  // extern "C++"
+
+int mbpo_system_step_general(int system_kind, const MbpoGeneralSystemParams* params_host, int prng_mode,
+                             const float* x, const float* u, const uint32_t* keys_in, int R, float* x_next,
+                             float* reward, uint32_t* keys_out, void* stream) {
+  int X, A; bool keyed;
+  const int rc = general_dims(system_kind, &X, &A, &keyed);
+  if (rc != MBPO_OK) return rc;
+  MBPO_REQUIRE(prng_mode == 0 || prng_mode == 1, "system_step_general: bad prng_mode %d", prng_mode);
+  MBPO_REQUIRE(R >= 0, "system_step_general: R < 0");
+  if (R == 0) return MBPO_OK;
+  MBPO_REQUIRE(params_host && x && u && x_next && reward, "system_step_general: null pointer");
+  MBPO_REQUIRE(!keyed || keys_in, "system_step_general: this System draws from system_params.key: keys_in is null");
+  const unsigned blocks = static_cast<unsigned>((R + 127) / 128);
+  cudaStream_t st = as_stream(stream);
+#define MBPO_LAUNCH_STEP(SYS)                                                                                     \
+  do {                                                                                                            \
+    if (prng_mode == 0) system_step_general_kernel<SYS, 0><<<blocks, 128, 0, st>>>(*params_host, x, u, keys_in, R, \
+                                                                                   x_next, reward, keys_out);     \
+    else system_step_general_kernel<SYS, 1><<<blocks, 128, 0, st>>>(*params_host, x, u, keys_in, R, x_next,       \
+                                                                    reward, keys_out);                            \
+  } while (0)
+  if (system_kind == MBPO_SYSTEM_PENDULUM) MBPO_LAUNCH_STEP(PendulumSys);
+  else if (system_kind == MBPO_SYSTEM_NOISY_PENDULUM) MBPO_LAUNCH_STEP(NoisyPendulumSys);
+  else MBPO_LAUNCH_STEP(PointMassSys);
+#undef MBPO_LAUNCH_STEP
+  return check_launch("system_step_general_kernel");
+}
+
+int mbpo_system_objective(int system_kind, const MbpoGeneralSystemParams* params_host, int prng_mode, int horizon,
+                          const float* x0, const float* actions, const uint32_t* keys, int B, int M,
+                          int num_particles, int summarize, float* values_out, float* obs_out, float* reward_out,
+                          float* next_obs_out, void* stream) {
+  int X, A; bool keyed;
+  const int rc = general_dims(system_kind, &X, &A, &keyed);
+  if (rc != MBPO_OK) return rc;
+  MBPO_REQUIRE(prng_mode == 0 || prng_mode == 1, "system_objective: bad prng_mode %d", prng_mode);
+  MBPO_REQUIRE(horizon >= 1 && B >= 0 && M >= 0 && num_particles >= 0, "system_objective: bad sizes");
+  MBPO_REQUIRE(summarize == 0 || summarize == 1, "system_objective: bad summarize %d", summarize);
+  const long long total = static_cast<long long>(B) * M;
+  if (total == 0) return MBPO_OK;
+  MBPO_REQUIRE(params_host && x0 && actions, "system_objective: null pointer");
+  MBPO_REQUIRE(!keyed || keys, "system_objective: this System draws from system_params.key: keys is null");
+  MBPO_REQUIRE(num_particles == 0 || values_out, "system_objective: values_out is null");
+  MBPO_REQUIRE(num_particles == 0 || !(obs_out || reward_out || next_obs_out),
+               "system_objective: Transition buffers exist for single rollouts (num_particles == 0) only");
+  const unsigned blocks = static_cast<unsigned>((total + 127) / 128);
+  cudaStream_t st = as_stream(stream);
+#define MBPO_LAUNCH_OBJ(SYS)                                                                                        \
+  do {                                                                                                              \
+    if (prng_mode == 0)                                                                                             \
+      general_objective_kernel<SYS, 0><<<blocks, 128, 0, st>>>(*params_host, horizon, x0, actions, keys, B, M,     \
+                                                               num_particles, summarize, values_out, obs_out,       \
+                                                               reward_out, next_obs_out);                           \
+    else                                                                                                            \
+      general_objective_kernel<SYS, 1><<<blocks, 128, 0, st>>>(*params_host, horizon, x0, actions, keys, B, M,     \
+                                                               num_particles, summarize, values_out, obs_out,       \
+                                                               reward_out, next_obs_out);                           \
+  } while (0)
+  if (system_kind == MBPO_SYSTEM_PENDULUM) MBPO_LAUNCH_OBJ(PendulumSys);
+  else if (system_kind == MBPO_SYSTEM_NOISY_PENDULUM) MBPO_LAUNCH_OBJ(NoisyPendulumSys);
+  else MBPO_LAUNCH_OBJ(PointMassSys);
+#undef MBPO_LAUNCH_OBJ
+  return check_launch("general_objective_kernel");
+}
+
 // ---- stage 3 -----------------------------------------------------------------------------------
 int mbpo_icem_elite_refit(const MbpoIcemCfg* cfg, const float* actions, const float* values, const float* mean_in,
                           const float* std_in, const float* best_value_in, const float* best_seq_in, int B,
@@ -503,7 +586,7 @@ size_t mbpo_icem_workspace_bytes(const MbpoIcemCfg* cfg, int B) {
   const size_t M = static_cast<size_t>(cfg->num_samples) + cfg->num_prev_elites;
   const size_t D = static_cast<size_t>(cfg->horizon) * cfg->action_dim;
   const size_t b = static_cast<size_t>(B);
-  const size_t words = b * M * D + b * M + 5 * b * D + 2 * b + 4 * b;
+  const size_t words = b * M * D + b * M + 5 * b * D + 2 * b + 4 * b + 2 * b * M /* particle keys */;
   return words * 4 + 256;
 }
 
@@ -515,8 +598,15 @@ int mbpo_icem_plan_staged(const MbpoIcemCfg* cfg, const void* sys_params_host, c
   if (rc != MBPO_OK) return rc;
   MBPO_REQUIRE(sys_params_host, "plan_staged: null pointer");
   MBPO_REQUIRE(B >= 0 && B <= 65535, "plan_staged: B %d outside [0, 65535]", B);
-  if (cfg->system_kind != MBPO_SYSTEM_PENDULUM && cfg->system_kind != MBPO_SYSTEM_MLP_ENSEMBLE)
+  const bool general = cfg->system_kind == MBPO_SYSTEM_NOISY_PENDULUM || cfg->system_kind == MBPO_SYSTEM_POINT_MASS;
+  if (cfg->system_kind != MBPO_SYSTEM_PENDULUM && cfg->system_kind != MBPO_SYSTEM_MLP_ENSEMBLE && !general)
     return fail(MBPO_EUNSUPPORTED, "plan_staged: unknown system_kind %d", cfg->system_kind);
+  if (general) {
+    int X, A; bool keyed;
+    general_dims(cfg->system_kind, &X, &A, &keyed);
+    MBPO_REQUIRE(cfg->action_dim == A && cfg->x_dim == X, "plan_staged: system_kind %d has x_dim %d, action_dim %d "
+                 "(cfg says %d, %d)", cfg->system_kind, X, A, cfg->x_dim, cfg->action_dim);
+  }
   if (cfg->system_kind == MBPO_SYSTEM_MLP_ENSEMBLE) {
     const MbpoMlpEnsembleParams* ep = static_cast<const MbpoMlpEnsembleParams*>(sys_params_host);
     if (cfg->num_particles != ep->num_members)
@@ -546,6 +636,7 @@ int mbpo_icem_plan_staged(const MbpoIcemCfg* cfg, const void* sys_params_host, c
   uint32_t* ckey[2];
   ckey[0] = reinterpret_cast<uint32_t*>(w); w += 2 * b;
   ckey[1] = reinterpret_cast<uint32_t*>(w); w += 2 * b;
+  uint32_t* pkeys = reinterpret_cast<uint32_t*>(w); w += 2 * b * M;      // split(particles_rng, N + Np)  (:177)
   cudaStream_t st = as_stream(stream);
 
   // ping-pong so that after S iterations the results land in slot 0 (= the caller's buffers)
@@ -562,9 +653,16 @@ int mbpo_icem_plan_staged(const MbpoIcemCfg* cfg, const void* sys_params_host, c
   if (rc != MBPO_OK) return rc;
   for (int it = 0; it < cfg->num_steps; ++it) {
     const int nxt = cur ^ 1;
-    rc = mbpo_icem_sample_actions(cfg, ckey[cur], mean[cur], std_[cur], B, actions, ckey[nxt], nullptr, stream);
+    rc = mbpo_icem_sample_actions(cfg, ckey[cur], mean[cur], std_[cur], B, actions, ckey[nxt],
+                                  general ? pkeys : nullptr, stream);
     if (rc != MBPO_OK) return rc;
-    if (cfg->system_kind == MBPO_SYSTEM_MLP_ENSEMBLE) {
+    if (general) {
+      // one rollout per particle key, horizon mean, mean / max over the particles (:144-160)
+      rc = mbpo_system_objective(cfg->system_kind, static_cast<const MbpoGeneralSystemParams*>(sys_params_host),
+                                 cfg->prng_mode, cfg->horizon, x0, actions, pkeys, B, static_cast<int>(M),
+                                 cfg->num_particles, cfg->summarize, values, nullptr, nullptr, nullptr, stream);
+      if (rc != MBPO_OK) return rc;
+    } else if (cfg->system_kind == MBPO_SYSTEM_MLP_ENSEMBLE) {
       // particles = ensemble members; the kernel summarises over them itself (:160)
       rc = mbpo_ensemble_rollout(static_cast<const MbpoMlpEnsembleParams*>(sys_params_host), cfg->horizon, x0, actions,
                                  B, static_cast<int>(M), cfg->summarize, values, stream);

@@ -22,7 +22,7 @@ MBPO_EWORKSPACE = -4
 
 PRNG_LEGACY, PRNG_PARTITIONABLE = 0, 1
 SUMMARIZE_MEAN, SUMMARIZE_MAX = 0, 1
-SYSTEM_PENDULUM, SYSTEM_MLP_ENSEMBLE = 0, 1
+SYSTEM_PENDULUM, SYSTEM_MLP_ENSEMBLE, SYSTEM_NOISY_PENDULUM, SYSTEM_POINT_MASS = 0, 1, 2, 3
 MATH_REFERENCE, MATH_THETA_CARRY = 0, 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -45,6 +45,15 @@ class MbpoUnsupported(MbpoError, NotImplementedError):
 class PendulumParamsC(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("max_speed", "max_torque", "dt", "g", "m", "l",
                                          "control_cost", "angle_cost", "target_angle")]
+
+
+class PointMassParamsC(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("dt", "max_accel", "max_speed", "target_x", "target_y", "speed_cost",
+                                         "control_cost")]
+
+
+class GeneralSystemParamsC(C.Structure):
+    _fields_ = [("pendulum", PendulumParamsC), ("noise_std", C.c_float), ("point_mass", PointMassParamsC)]
 
 
 class MlpEnsembleParamsC(C.Structure):
@@ -112,6 +121,9 @@ SIGNATURES = {
     "mbpo_icem_sample_actions": (_I, [C.POINTER(IcemCfgC), _P, _P, _P, _I, _P, _P, _P, _P]),
     "mbpo_system_step": (_I, [_I, _P, _I, _P, _P, _I, _P, _P, _P]),
     "mbpo_rollout_actions": (_I, [_I, _P, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P]),
+    "mbpo_system_step_general": (_I, [_I, C.POINTER(GeneralSystemParamsC), _I, _P, _P, _P, _I, _P, _P, _P, _P]),
+    "mbpo_system_objective": (_I, [_I, C.POINTER(GeneralSystemParamsC), _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P,
+                                   _P, _P]),
     "mbpo_icem_elite_refit": (_I, [C.POINTER(IcemCfgC), _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P]),
     "mbpo_icem_plan": (_I, [C.POINTER(IcemCfgC), _P, _P, _P, _P, _I, _P, _P, _P, C.POINTER(IcemTraceC), _P]),
     "mbpo_icem_plan_clustered": (_I, [C.POINTER(IcemCfgC), _P, _P, _P, _P, _I, _P, _P, _P, C.POINTER(IcemTraceC), _I,

@@ -243,11 +243,18 @@ class iCemTO(BaseOptimizer):
         with L.cuda_guard(x0):
             for _ in range(S):
                 nxt_carry = torch.empty_like(carry)
+                general = self.system.system_kind in (L.SYSTEM_NOISY_PENDULUM, L.SYSTEM_POINT_MASS)
+                pkeys = torch.empty((B, M, 2), dtype=torch.uint32, device=dev) if general else None
                 L.check(L.lib.mbpo_icem_sample_actions(L.C.byref(cfg), L.ptr(carry), L.ptr(mean), L.ptr(std), B,
-                                                       L.ptr(actions), L.ptr(nxt_carry), None, st))
+                                                       L.ptr(actions), L.ptr(nxt_carry), L.ptr(pkeys), st))
                 if lo is not None:
                     L.check(L.lib.mbpo_icem_clip_actions(L.ptr(actions), L.ptr(lo), L.ptr(hi), B, M, N, D, st))
-                if self.system.system_kind == L.SYSTEM_MLP_ENSEMBLE:
+                if general:
+                    # one rollout per particle key, horizon mean, mean / max over the particles (:144-160)
+                    L.check(L.lib.mbpo_system_objective(self.system.system_kind, L.C.byref(params), config.prng_mode, H,
+                                                        L.ptr(x0), L.ptr(actions), L.ptr(pkeys), B, M,
+                                                        cfg.num_particles, s_rew, L.ptr(values), None, None, None, st))
+                elif self.system.system_kind == L.SYSTEM_MLP_ENSEMBLE:
                     # particles = members; the rollout kernel summarises over them itself (:160)
                     L.check(L.lib.mbpo_ensemble_rollout(L.C.addressof(params), H, L.ptr(x0), L.ptr(actions), B, M,
                                                         s_rew, L.ptr(values), st))
@@ -341,6 +348,8 @@ class iCemTO(BaseOptimizer):
             seq, _, key, _ = self._plan_raw(x, key, seq, sp)
             u = seq[:, 0, :].contiguous()
             nxt = self.system.step(x, u, sp)
+            if nxt.system_params is not None and nxt.system_params.key is not None:
+                sp = nxt.system_params                      # a System that draws carries its key on (tests/test_icemopt.py:24)
             x = nxt.x_next
             states.append(x); rewards.append(nxt.reward); actions.append(u)
         B, dev = x0.shape[0], x0.device

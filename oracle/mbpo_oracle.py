@@ -877,3 +877,141 @@ def lambda_return_vjp(g_returns, discount: float, lambda_: float, dtype=F32):
     g_nv = (dn * g_inp).astype(dtype)
     g_nv[..., -1] += dl * g_inp[..., -1]
     return g_inp, g_nv
+
+
+# ----------------------------------------------------------------------------------
+# iCEM generality: Systems that consume the per-particle key and A > 1.
+# The reference ships neither (its only System is the deterministic pendulum, whose
+# PendulumDynamics.next_state already returns distrax.Normal(mean, std = 0),
+# pendulum_dynamics.py:45-46); these two are the smallest Systems that exercise
+# iCemTO's own code for them:
+#   icem_optimizer.py:146-147  system_params.replace(key=rng)      one key per particle
+#   icem_optimizer.py:155-156  split(key, num_particles) + vmap     P distinct rollouts
+#   icem_optimizer.py:160      mean over the horizon, mean / max over particles
+#   icem_optimizer.py:180      vmap(split(x, action_dim))           one noise key per action dim
+#   optimizer_utils.py:28-46   the scan carries [obs, system_params]: the key threads through
+# ----------------------------------------------------------------------------------
+class NoisyPendulumOracle:
+    """PendulumSystem whose transition is SAMPLED: next_state returns Normal(mean, noise_std) and step draws from it
+    with the System's own key -- ``key, sub = split(system_params.key)``; ``x_next = mean + noise_std *
+    normal(sub, (3,))`` (distrax Normal.sample: loc + scale * jax.random.normal) -- and carries ``key`` on in the
+    returned SystemParams.  The reward is the pendulum reward on the current (noisy) state."""
+    x_dim, u_dim, keyed = 3, 1, True
+
+    def __init__(self, noise_std: float = 0.05, p: PendulumParams = PendulumParams()):
+        self.noise_std, self.p = noise_std, p
+
+    def step(self, x, u, keys, partitionable=False, dtype=F32):
+        """x [R,3], u [R,1], keys uint32 [R,2] -> (x_next [R,3], reward [R], keys_next [R,2])."""
+        mean, reward = pendulum_step(x, u[:, 0], self.p, dtype)
+        ks = split_keys(keys, 2, partitionable)
+        z = jr.bits_to_normal(random_bits_keys(ks[:, 1], 3, partitionable)).astype(dtype)
+        x_next = (mean + (dtype(self.noise_std) * z).astype(dtype)).astype(dtype)
+        return x_next, reward, ks[:, 0]
+
+
+@dataclass(frozen=True)
+class PointMassParams:
+    dt: float = 0.1
+    max_accel: float = 1.0
+    max_speed: float = 2.0
+    target_x: float = 1.0
+    target_y: float = -0.5
+    speed_cost: float = 0.1
+    control_cost: float = 0.02
+
+    def packed(self) -> np.ndarray:
+        return np.array([self.dt, self.max_accel, self.max_speed, self.target_x, self.target_y, self.speed_cost,
+                         self.control_cost], dtype=F32)
+
+
+class PointMassOracle:
+    """A planar double integrator with TWO action dimensions: state [px, py, vx, vy], action [ax, ay].
+        a = clip(u, -1, 1) * max_accel;  v' = clip(v + a * dt, +-max_speed);  p' = p + v' * dt
+        reward = -(|p - target|^2 + speed_cost * |v|^2) - control_cost * |u|^2     (on the current state, raw action)
+    Deterministic; every float operation is a separate float32 rounding in the order written."""
+    x_dim, u_dim, keyed = 4, 2, False
+
+    def __init__(self, p: PointMassParams = PointMassParams()):
+        self.p = p
+
+    def step(self, x, u, keys=None, partitionable=False, dtype=F32):
+        d, p = dtype, self.p
+        x, u = np.asarray(x, d), np.asarray(u, d)
+        pos, vel = x[:, 0:2], x[:, 2:4]
+        tgt = np.array([p.target_x, p.target_y], d)
+        dp = (pos - tgt).astype(d)
+        dist2 = ((dp[:, 0] * dp[:, 0]).astype(d) + (dp[:, 1] * dp[:, 1]).astype(d)).astype(d)
+        spd2 = ((vel[:, 0] * vel[:, 0]).astype(d) + (vel[:, 1] * vel[:, 1]).astype(d)).astype(d)
+        u2 = ((u[:, 0] * u[:, 0]).astype(d) + (u[:, 1] * u[:, 1]).astype(d)).astype(d)
+        reward = ((-(dist2 + (d(p.speed_cost) * spd2).astype(d)).astype(d)) - (d(p.control_cost) * u2).astype(d)).astype(d)
+        a = (np.clip(u, d(-1), d(1)) * d(p.max_accel)).astype(d)
+        nv = np.clip((vel + (a * d(p.dt)).astype(d)).astype(d), d(-p.max_speed), d(p.max_speed)).astype(d)
+        npos = (pos + (nv * d(p.dt)).astype(d)).astype(d)
+        return np.concatenate([npos, nv], axis=1).astype(d), reward, keys
+
+
+class PendulumOracle:
+    """The reference's deterministic pendulum behind the same interface (the key is dropped: pendulum_system.py:38)."""
+    x_dim, u_dim, keyed = 3, 1, False
+
+    def __init__(self, p: PendulumParams = PendulumParams()):
+        self.p = p
+
+    def step(self, x, u, keys=None, partitionable=False, dtype=F32):
+        xn, r = pendulum_step(x, u[:, 0], self.p, dtype)
+        return xn, r, keys
+
+
+def system_rollout_actions(system, x0, actions, keys=None, partitionable=False, dtype=F32, full=False):
+    """vmap(rollout_actions) (optimizer_utils.py:11-59) for any oracle System: x0 [R,X], actions [R,H,A], keys
+    uint32 [R,2] (keyed Systems) -> horizon-mean reward [R] (+ obs [R,H,X], reward [R,H], next_obs [R,H,X])."""
+    actions = np.asarray(actions, dtype)
+    r, h, _ = actions.shape
+    x = np.broadcast_to(np.asarray(x0, dtype), (r, system.x_dim)).copy()
+    k = None if keys is None else np.asarray(keys, U32).reshape(r, 2).copy()
+    acc = np.zeros(r, dtype)
+    obs = np.empty((r, h, system.x_dim), dtype); nxt = np.empty_like(obs); rew = np.empty((r, h), dtype)
+    for t in range(h):
+        xn, rw, k = system.step(x, actions[:, t], k, partitionable, dtype)
+        obs[:, t], nxt[:, t], rew[:, t] = x, xn, rw
+        acc = (acc + rw).astype(dtype)
+        x = xn
+    ret = (acc / dtype(h)).astype(dtype)
+    return (ret, obs, rew, nxt) if full else ret
+
+
+def system_objective(system, x0, acts, particle_keys, params: ICemParams, use_optimism=False, partitionable=False,
+                     dtype=F32):
+    """vmap(objective) (icem_optimizer.py:144-160,195) for any oracle System: acts [M,H,A], particle_keys [M,2].
+    Per candidate ``split(key, P)``, one rollout per particle key, mean over the horizon, then mean (left-to-right)
+    or max over the particles."""
+    m, P = acts.shape[0], params.num_particles
+    if not system.keyed:
+        ret = system_rollout_actions(system, x0, acts, None, partitionable, dtype)
+        return ret if (use_optimism or P == 1) else particle_mean(np.repeat(ret[:, None], P, axis=1), dtype)
+    pk = split_keys(particle_keys, P, partitionable)                              # :155  [M, P, 2]
+    per = np.stack([system_rollout_actions(system, x0, acts, pk[:, p], partitionable, dtype) for p in range(P)], axis=1)
+    return per.max(axis=1) if use_optimism else particle_mean(per, dtype)
+
+
+def system_icem_optimize(system, x0, state: ICemState, params: ICemParams, horizon: int, use_optimism=False,
+                         partitionable=False, dtype=F32, trace: Optional[list] = None) -> ICemState:
+    """iCemTO.optimize (icem_optimizer.py:134-252) over any oracle System (action_dim = system.u_dim)."""
+    A = system.u_dim
+    mean = np.zeros((horizon, A), dtype)
+    if params.warm_start:
+        mean[:-1] = state.best_sequence[1:]
+        mean[-1] = state.best_sequence[-1]
+    std = np.full((horizon, A), params.init_std, dtype)
+    best_seq, best_value = mean.copy(), dtype(-np.inf)
+    ks = jr.split(state.key, 2, partitionable)
+    carry_key, new_state_key = ks[0], ks[1]
+    for _ in range(params.num_steps):
+        carry_key, acts, pkeys = icem_sample_actions(carry_key, mean, std, params, horizon, A, partitionable, dtype)
+        values = system_objective(system, x0, acts, pkeys, params, use_optimism, partitionable, dtype)
+        mean, std, best_value, best_seq, idx = icem_refit(acts, values, mean, std, best_value, best_seq, params, dtype)
+        if trace is not None:
+            trace.append(dict(actions=acts, values=values, elite_idx=idx, mean=mean, std=std, best_value=best_value,
+                              particle_keys=pkeys))
+    return ICemState(key=new_state_key, best_sequence=np.asarray(best_seq, F32), best_reward=F32(best_value))

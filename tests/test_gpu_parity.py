@@ -1857,3 +1857,133 @@ def test_dummy_true_buffer_state_feeds_brax_wrapper(mb, cuda_device, prng_mode):
     # batched init (additive vmap): the vmapped pytree
     stb = opt.init(mb.random.split(_dev(ojr.PRNGKey(5), dev), 4))
     assert tuple(stb.true_buffer_state.ring.shape) == (4, 10, 9) and tuple(stb.true_buffer_state.key.shape) == (4, 2)
+
+
+# ---------------------------------------------------------------------------------------------
+# iCEM generality: a System that consumes the per-particle key, and action_dim > 1
+# ---------------------------------------------------------------------------------------------
+def _general_systems(mb):
+    from mbpo_b200.systems import NoisyPendulumSystem, PointMassSystem
+    return {"noisy_pendulum": (NoisyPendulumSystem(0.05), orc.NoisyPendulumOracle(0.05)),
+            "point_mass": (PointMassSystem(), orc.PointMassOracle())}
+
+
+def _general_states(kind, n, seed):
+    if kind == "noisy_pendulum":
+        return _random_states(n, seed)
+    return np.random.default_rng(seed).uniform(-1.5, 1.5, (n, 4)).astype(np.float32)
+
+
+@pytest.mark.parametrize("kind", ["noisy_pendulum", "point_mass"])
+def test_general_system_step(mb, cuda_device, prng_mode, kind):
+    """System.step of the key-consuming pendulum (key, sub = split(key); x' = mean + std * normal(sub, (3,)); the key
+    is carried on) and of the two-action point mass, against the oracle: keys bit-exact, the point mass bit-exact
+    (single-rounded arithmetic in the oracle's order), the pendulum's floats to the north star's tolerance."""
+    system, osys = _general_systems(mb)[kind]
+    R = 1000
+    x = _general_states(kind, R, 401)
+    u = np.random.default_rng(402).uniform(-1.3, 1.3, (R, system.u_dim)).astype(np.float32)
+    keys = _keys(R, seed=403)
+    sp = system.init_params(mb.random.PRNGKey(0, cuda_device)).replace(key=_dev(keys, cuda_device))
+    out = system.step(_dev(x, cuda_device), _dev(u, cuda_device), sp)
+    xn, r, kn = osys.step(x, u, keys, prng_mode)
+    if kind == "point_mass":
+        assert np.array_equal(out.x_next.cpu().numpy(), xn) and np.array_equal(out.reward.cpu().numpy(), r)
+        assert out.system_params.key is None
+    else:
+        assert np.array_equal(out.system_params.key.cpu().numpy(), kn)           # the key is carried on
+        np.testing.assert_allclose(out.x_next.cpu().numpy(), xn, rtol=RTOL, atol=2e-6)
+        np.testing.assert_allclose(out.reward.cpu().numpy(), r, rtol=RTOL, atol=2e-6)
+        det = orc.pendulum_step(x, u[:, 0])[0]
+        assert np.abs(out.x_next.cpu().numpy() - det).std() > 0.03                 # the draw is really there
+        # a second step continues the stream: different noise
+        out2 = system.step(out.x_next, _dev(u, cuda_device), out.system_params)
+        xn2, _, kn2 = osys.step(out.x_next.cpu().numpy(), u, kn, prng_mode)
+        assert np.array_equal(out2.system_params.key.cpu().numpy(), kn2)
+        np.testing.assert_allclose(out2.x_next.cpu().numpy(), xn2, rtol=RTOL, atol=2e-6)
+
+
+@pytest.mark.parametrize("kind", ["noisy_pendulum", "point_mass"])
+def test_general_objective_vs_oracle(mb, cuda_device, prng_mode, kind):
+    """vmap(vmap(objective)) (icem_optimizer.py:144-160): split(key, P), one rollout per particle key, horizon mean,
+    mean / max over particles; and vmap(rollout_actions) with the key threaded through the scan, step by step."""
+    system, osys = _general_systems(mb)[kind]
+    B, M, H, P = 3, 37, 12, 4
+    A = system.u_dim
+    x0 = _general_states(kind, B, 411)
+    acts = np.clip(np.random.default_rng(412).normal(0, 0.5, (B, M, H, A)), -1, 1).astype(np.float32)
+    keys = _keys(B * M, seed=413).reshape(B, M, 2)
+    sp = system.init_params(mb.random.PRNGKey(0, cuda_device))
+    d = lambda a: _dev(a, cuda_device)
+    p = orc.ICemParams(num_particles=P)
+    for use_max in (False, True):
+        got = system.objective(sp, d(x0), d(acts), d(keys), num_particles=P, use_optimism=use_max).cpu().numpy()
+        for b in range(B):
+            want = orc.system_objective(osys, x0[b], acts[b], keys[b], p, use_max, prng_mode)
+            if kind == "point_mass":
+                assert np.array_equal(got[b], want)
+            else:
+                np.testing.assert_allclose(got[b], want, rtol=2e-5, atol=2e-6)
+    # single rollouts with the Transition buffers, teacher-forced: every step from the kernel's own observation and key
+    vals, obs, rew, nxt = system.objective(sp, d(x0), d(acts), d(keys), num_particles=0, full=True)
+    obs, rew, nxt = obs.cpu().numpy(), rew.cpu().numpy(), nxt.cpu().numpy()
+    assert np.array_equal(obs[:, :, 1:], nxt[:, :, :-1])
+    assert np.array_equal(obs[:, :, 0], np.broadcast_to(x0[:, None], (B, M, system.x_dim)))
+    k = keys.reshape(-1, 2)
+    for t in range(H):
+        xn, r, k = osys.step(obs[:, :, t].reshape(B * M, -1), acts[:, :, t].reshape(B * M, A), k, prng_mode)
+        np.testing.assert_allclose(nxt[:, :, t].reshape(B * M, -1), xn, rtol=RTOL, atol=2e-6)
+        np.testing.assert_allclose(rew[:, :, t].reshape(-1), r, rtol=RTOL, atol=3e-6)
+    np.testing.assert_allclose(vals.cpu().numpy(), rew.astype(np.float64).mean(-1), rtol=2e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("kind,use_optimism", [("noisy_pendulum", False), ("noisy_pendulum", True), ("point_mass", False)])
+def test_icem_plan_over_general_systems(mb, cuda_device, prng_mode, kind, use_optimism):
+    """iCemTO through its unchanged API over a key-consuming System (P distinct particles per candidate, mean and max
+    summaries) and over a System with two action dimensions: teacher-forced against the oracle iteration by iteration
+    (keys and elite indices exact, sampled actions and objectives to tolerance, the refit bit-exact given the
+    kernel's own actions and values); act() -- the C staged plan -- gives the traced composition's bits."""
+    from mbpo_b200.optimizers import iCemTO, iCemParams
+    system, osys = _general_systems(mb)[kind]
+    H, B, A = 10, 4, system.u_dim
+    params = dict(num_samples=96, num_elites=12, num_particles=3, num_steps=3, alpha=0.1, exponent=1.0)
+    opt = iCemTO(horizon=H, action_dim=A, opt_params=iCemParams(**params), use_optimism=use_optimism)
+    opt.set_system(system)
+    keys = _keys(B, seed=421)
+    st = opt.init(_dev(keys, cuda_device))
+    assert st.best_sequence.shape == (B, H, A)
+    x0 = _general_states(kind, B, 422)
+    seq_t, val_t, key_t, tr = opt._plan_raw(_dev(x0, cuda_device), st.key, st.best_sequence, st.system_params, trace=True)
+    action, new = opt.act(_dev(x0, cuda_device), st)
+    assert action.shape == (B, A)
+    assert torch.equal(new.best_sequence, seq_t) and torch.equal(new.best_reward, val_t)
+    assert torch.equal(new.key.view(torch.int32), key_t.view(torch.int32))
+    tr = {k: v.cpu().numpy() for k, v in tr.items()}
+    p = orc.ICemParams(**params)
+    M = p.num_samples + p.num_prev_elites
+    k_np = st.key.cpu().numpy()
+    for b in range(B):
+        ks = ojr.split(k_np[b], 2, prng_mode)
+        assert np.array_equal(new.key[b].cpu().numpy(), ks[1])
+        carry = ks[0]
+        mean, std = np.zeros((H, A), np.float32), np.full((H, A), p.init_std, np.float32)
+        bval, bseq = np.float32(-np.inf), mean.copy()
+        for it in range(p.num_steps):
+            carry, acts, pkeys = orc.icem_sample_actions(carry, mean, std, p, H, A, prng_mode)
+            g_acts = tr["actions"][it, b].reshape(M, H, A)
+            np.testing.assert_allclose(g_acts, acts, rtol=RTOL, atol=5e-6)
+            vals = orc.system_objective(osys, x0[b], g_acts, pkeys, p, use_optimism, prng_mode)
+            g_vals = tr["values"][it, b]
+            np.testing.assert_allclose(g_vals, vals, rtol=2e-5, atol=2e-6)
+            if kind == "noisy_pendulum":                       # the kept-elite zero rows are distinct rollouts now
+                assert len(np.unique(g_vals[p.num_samples:])) > 1
+            mean, std, bval, bseq, idx = orc.icem_refit(g_acts, g_vals, mean, std, bval, bseq, p)
+            assert np.array_equal(tr["elite_idx"][it, b], idx)
+            assert np.array_equal(tr["mean"][it, b].reshape(H, A), mean)
+            assert np.array_equal(tr["std"][it, b].reshape(H, A), std)
+            assert tr["best_value"][it, b] == bval
+        assert np.array_equal(seq_t[b].cpu().numpy(), np.asarray(bseq)) and float(val_t[b]) == float(bval)
+    # closed loop through plan -> System.step launches (the key of the true System threads through as well)
+    states, rewards, actions, _ = opt.closed_loop(_dev(x0, cuda_device), st, 3)
+    assert states.shape == (3, B, system.x_dim) and actions.shape == (3, B, A)
+    assert torch.equal(actions[0], action)
