@@ -9,6 +9,7 @@
 #include "noise.cuh"
 #include "pendulum.cuh"
 #include "select.cuh"
+#include "systems.cuh"
 
 namespace mbpo {
 
@@ -81,6 +82,7 @@ struct PlanArgs {
   int warm_start, summarize;
   float init_std, alpha, one_minus_alpha, u_min, u_max;
   MbpoPendulumParams sys;
+  MbpoGeneralSystemParams gsys;  // the general Systems (systems.cuh): fused general plan only
   float scale[MBPO_MAX_FREQ];  // fill_noise_scale()
   // I/O
   const float* x0;           // [B,3]
@@ -375,6 +377,171 @@ __global__ void __launch_bounds__(THREADS, MINB)
       a.best_value_out ? (void)(a.best_value_out[b] = *sm.best_value) : (void)0;
       a.key_out[2 * b] = sm.state_key[0];
       a.key_out[2 * b + 1] = sm.state_key[1];
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused plan over the general Systems (systems.cuh): any action_dim, P distinct particles per candidate when the
+// System consumes its key (icem_optimizer.py:146-160,180).  One CTA per problem like the pendulum kernel, one
+// candidate at a time per thread.  A candidate's actions live in shared memory DIMENSION-MAJOR ([A][H]): the H
+// floats of a dimension double as the staging area of its noise row, and System.step reads u[t] with stride H.
+// The Np kept-elite rows (the closure's zeros, :192,:245) are candidates N .. N+Np-1 with their own particle keys:
+// for a System that draws they are distinct rollouts every iteration.  Same device functions as the staged path
+// (sample_actions_kernel, general_objective_kernel, elite_refit_kernel): same bits.
+// ------------------------------------------------------------------------------------------
+template <int H, int A>
+struct GenPlanSmem {
+  static constexpr int RS = (H * A) | 1;   // odd row stride
+  static size_t bytes(int N, int Np, int K) {
+    const size_t words = static_cast<size_t>(N + 1) * RS + (N + Np) + 3 * H * A + 2 * K +
+                         select_scratch_words(K, N + Np) + 8;
+    return words * 4;
+  }
+};
+
+template <class Sys, int H, int PRNG>
+__global__ void __launch_bounds__(256, 1) icem_plan_general_kernel(const __grid_constant__ PlanArgs a) {
+  constexpr int A = Sys::A, X = Sys::X, D = H * A, RS = GenPlanSmem<H, A>::RS, THREADS = 256;
+  extern __shared__ __align__(16) uint32_t smem_u32[];
+  const int N = a.N, M = a.N + a.Np, K = a.K;
+  float* act = reinterpret_cast<float*>(smem_u32);               // [N + 1][RS], row N all zeros
+  uint32_t* skey = smem_u32 + static_cast<size_t>(N + 1) * RS;   // [M]
+  float* mean = reinterpret_cast<float*>(skey + M);              // [H*A] in the ABI's (t, a) order
+  float* std_ = mean + D;
+  float* best_seq = std_ + D;
+  int* elite_idx = reinterpret_cast<int*>(best_seq + D);
+  int* sel_idx = elite_idx + K;
+  uint32_t* scratch = reinterpret_cast<uint32_t*>(sel_idx + K);
+  float* best_value = reinterpret_cast<float*>(scratch + select_scratch_words(K, M));
+  uint32_t* carry = reinterpret_cast<uint32_t*>(best_value + 1);
+  const int tid = threadIdx.x;
+  const Sys sys(a.gsys);
+  RefitScalars rs;
+  rs.M = M; rs.K = K; rs.D = D; rs.alpha = a.alpha; rs.one_minus_alpha = a.one_minus_alpha;
+  // element d = t * A + ad of candidate i (ABI order) in the dimension-major shared row
+  auto elem = [&](int i, int d) { return i < N ? act[static_cast<size_t>(i) * RS + (d % A) * H + d / A] : 0.0f; };
+
+  for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+    float s0[X];
+#pragma unroll
+    for (int k = 0; k < X; ++k) s0[k] = a.x0[static_cast<size_t>(b) * X + k];
+    // ---- prologue (:235-249): warm start shifts by one step = A elements --------------------------------
+    const float* prev = a.best_seq_in + static_cast<size_t>(b) * D;
+    for (int d = tid; d < D; d += THREADS) {
+      float m = 0.0f;
+      if (a.warm_start) m = prev[(d + A < D) ? d + A : (D - A + d % A)];
+      mean[d] = m;
+      std_[d] = a.init_std;
+      best_seq[d] = m;
+    }
+    for (int d = tid; d < RS; d += THREADS) act[static_cast<size_t>(N) * RS + d] = 0.0f;
+    Key2 k_new{0u, 0u};
+    if (tid == 0) {
+      *best_value = __int_as_float(0xFF800000);
+      Key2 k_opt;
+      split2<PRNG>(Key2{a.key_in[2 * b], a.key_in[2 * b + 1]}, k_opt, k_new);
+      carry[0] = k_opt.k0;
+      carry[1] = k_opt.k1;
+    }
+    __syncthreads();
+    float zero_value = 0.0f;   // deterministic System: the objective of the all-zero row, computed once (thread 0)
+
+    for (int it = 0; it < a.S; ++it) {
+      const size_t tslot = static_cast<size_t>(it) * a.B + b;
+      Key2 ck{carry[0], carry[1]}, sampling_rng, particles_rng;
+      split2<PRNG>(ck, sampling_rng, particles_rng);                                            // :174
+      __syncthreads();  // every thread has read carry
+      if (tid == 0) {
+        const Key2 nk = split_at<PRNG>(sampling_rng, static_cast<uint32_t>(N + 1), 0u);         // :176
+        carry[0] = nk.k0;
+        carry[1] = nk.k1;
+      }
+      // candidates 0 .. N-1 are sampled; N .. M-1 are the zero rows (rolled out only if the System draws, or once)
+      const int jobs = Sys::KEYED ? M : ((it == 0) ? N + 1 : N);
+      for (int n = tid; n < jobs; n += THREADS) {
+        float* row = act + static_cast<size_t>(n < N ? n : N) * RS;
+        if (n < N) {
+          const Key2 sk = split_at<PRNG>(sampling_rng, static_cast<uint32_t>(N + 1), static_cast<uint32_t>(n + 1));
+#pragma unroll 1
+          for (int ad = 0; ad < A; ++ad) {
+            const Key2 dk = split_at<PRNG>(sk, static_cast<uint32_t>(A), static_cast<uint32_t>(ad));   // :180
+            float* dim = row + ad * H;
+            colored_noise_row<H, PRNG>(dk, a.scale, dim, nullptr, [&](int t, float y) {
+              const float v = __fadd_rn(mean[t * A + ad], __fmul_rn(y, std_[t * A + ad]));              // :190
+              dim[t] = fminf(fmaxf(v, a.u_min), a.u_max);                                               // :191
+            });
+          }
+        }
+        // ---- objective (:144-160) ----------------------------------------------------------------------
+        float val;
+        auto roll = [&](Key2 key) {
+          float s[X];
+#pragma unroll
+          for (int k = 0; k < X; ++k) s[k] = s0[k];
+          float acc = 0.0f;
+          for (int t = 0; t < H; ++t) acc = __fadd_rn(acc, sys.template step<PRNG>(s, row + t, H, key));
+          return __fdiv_rn(acc, static_cast<float>(H));
+        };
+        if (!Sys::KEYED) {
+          const float ret = roll(Key2{0u, 0u});
+          if (a.summarize == MBPO_SUMMARIZE_MAX || a.P == 1) {
+            val = ret;
+          } else {
+            float acc = 0.0f;
+            for (int p = 0; p < a.P; ++p) acc = __fadd_rn(acc, ret);
+            val = __fdiv_rn(acc, static_cast<float>(a.P));
+          }
+        } else {
+          const Key2 pkey = split_at<PRNG>(particles_rng, static_cast<uint32_t>(M), static_cast<uint32_t>(n));   // :177
+          float acc = 0.0f, mx = 0.0f;
+          for (int p = 0; p < a.P; ++p) {
+            const float ret = roll(split_at<PRNG>(pkey, static_cast<uint32_t>(a.P), static_cast<uint32_t>(p)));  // :155
+            acc = __fadd_rn(acc, ret);
+            mx = (p == 0) ? ret : fmaxf(mx, ret);
+          }
+          val = (a.summarize == MBPO_SUMMARIZE_MAX) ? mx : __fdiv_rn(acc, static_cast<float>(a.P));
+        }
+        if (n < N || Sys::KEYED) {
+          skey[n] = total_order_key(val);
+          if (a.trace.values) a.trace.values[tslot * M + n] = val;
+        } else {
+          zero_value = val;                                   // n == N, deterministic System, iteration 0: thread N % THREADS
+          for (int j = N; j < M; ++j) skey[j] = total_order_key(val);
+        }
+        if (a.trace.actions) {
+          float* dst = a.trace.actions + (tslot * M + n) * D;
+          for (int d = 0; d < D; ++d) dst[d] = (n < N) ? row[(d % A) * H + d / A] : 0.0f;
+        }
+      }
+      __syncthreads();
+      if (!Sys::KEYED && (a.trace.values || a.trace.actions)) {   // the zero rows' dumps (one value serves them all)
+        const float zv = value_of_key(skey[N]);
+        for (int j = N + tid; j < M; j += THREADS) {
+          if (a.trace.values) a.trace.values[tslot * M + j] = zv;
+          if (a.trace.actions && !(j == N && it == 0)) {
+            float* dst = a.trace.actions + (tslot * M + j) * D;
+            for (int d = 0; d < D; ++d) dst[d] = 0.0f;
+          }
+        }
+      }
+      (void)zero_value;
+      cta_select_refit<THREADS>(rs, skey, elite_idx, sel_idx, scratch, elem, mean, std_, best_seq, best_value);
+      if (a.trace.elite_idx)
+        for (int e = tid; e < K; e += THREADS) a.trace.elite_idx[tslot * K + e] = elite_idx[e];
+      for (int d = tid; d < D; d += THREADS) {
+        if (a.trace.mean) a.trace.mean[tslot * D + d] = mean[d];
+        if (a.trace.std) a.trace.std[tslot * D + d] = std_[d];
+      }
+      if (a.trace.best_value && tid == 0) a.trace.best_value[tslot] = *best_value;
+      __syncthreads();
+    }
+    for (int d = tid; d < D; d += THREADS) a.best_seq_out[static_cast<size_t>(b) * D + d] = best_seq[d];
+    if (tid == 0) {
+      a.best_value_out[b] = *best_value;
+      a.key_out[2 * b] = k_new.k0;
+      a.key_out[2 * b + 1] = k_new.k1;
     }
     __syncthreads();
   }

@@ -143,16 +143,30 @@ void fill_plan_args(PlanArgs& a, const MbpoIcemCfg* c, const MbpoPendulumParams*
   a.S = c->num_steps; a.warm_start = c->warm_start; a.summarize = c->summarize;
   a.init_std = c->init_std; a.alpha = c->alpha; a.one_minus_alpha = static_cast<float>(1.0 - static_cast<double>(c->alpha));
   a.u_min = c->u_min; a.u_max = c->u_max;
-  a.sys = *sys;
+  if (sys) a.sys = *sys;
   fill_noise_scale(c->s_scale, c->sigma, c->horizon, a.scale);
   a.x0 = x0; a.key_in = key_in; a.best_seq_in = best_seq_in; a.best_seq_out = best_seq_out;
   a.best_value_out = best_value_out; a.key_out = key_out;
   if (trace) a.trace = *trace;
 }
 
+bool general_system_kind(int k) { return k == MBPO_SYSTEM_NOISY_PENDULUM || k == MBPO_SYSTEM_POINT_MASS; }
+
 int plan_fusable(const MbpoIcemCfg* c, bool set_error) {
   const char* why = nullptr;
-  if (c->system_kind != MBPO_SYSTEM_PENDULUM) why = "fused plan supports system_kind == MBPO_SYSTEM_PENDULUM only";
+  if (general_system_kind(c->system_kind)) {
+    const int A = c->system_kind == MBPO_SYSTEM_POINT_MASS ? 2 : 1, X = c->system_kind == MBPO_SYSTEM_POINT_MASS ? 4 : 3;
+    const size_t RS = static_cast<size_t>(c->horizon * A) | 1;
+    const size_t words = static_cast<size_t>(c->num_samples + 1) * RS + (c->num_samples + c->num_prev_elites) +
+                         3 * c->horizon * A + 2 * c->num_elites +
+                         select_scratch_words(c->num_elites, c->num_samples + c->num_prev_elites) + 8;
+    if (c->action_dim != A || c->x_dim != X) why = "fused plan: action_dim / x_dim do not match the System";
+    else if (!horizon_supported(c->horizon)) why = "fused plan: horizon has no compiled kernel (" MBPO_H_LIST_STR ")";
+    else if (words * 4 > 227 * 1024) why = "fused plan: population does not fit 227 KB of shared memory";
+    if (why && set_error) fail(MBPO_EUNSUPPORTED, "%s", why);
+    return why == nullptr;
+  }
+  if (c->system_kind != MBPO_SYSTEM_PENDULUM) why = "fused plan supports the pendulum and the general Systems only";
   else if (c->action_dim != 1 || c->x_dim != 3) why = "fused plan requires action_dim == 1 and x_dim == 3";
   else if (!horizon_supported(c->horizon)) why = "fused plan: horizon has no compiled kernel (" MBPO_H_LIST_STR ")";
   else {
@@ -176,6 +190,22 @@ int run_plan(const MbpoIcemCfg* c, const void* sys_params_host, const float* x0,
   if (B == 0) return MBPO_OK;
   MBPO_REQUIRE(sys_params_host && x0 && key_in && best_seq_in && best_seq_out && key_out, "plan: null pointer");
   MBPO_REQUIRE(mpc != nullptr || best_value_out != nullptr, "plan: best_value_out is null");
+  if (general_system_kind(c->system_kind)) {
+    if (mpc != nullptr)
+      return fail(MBPO_EUNSUPPORTED, "closed loop in one launch exists for the pendulum System only");
+    PlanArgs g;
+    fill_plan_args(g, c, nullptr, x0, key_in, best_seq_in, B, best_seq_out, best_value_out, key_out, trace);
+    g.gsys = *static_cast<const MbpoGeneralSystemParams*>(sys_params_host);
+    switch (c->horizon) {
+#define X(h) \
+  case h:    \
+    return general_plan_entry<h>(c->system_kind, c->prng_mode, g, as_stream(stream));
+      MBPO_FOR_EACH_H(X)
+#undef X
+      default:
+        return fail(MBPO_EUNSUPPORTED, "horizon %d has no compiled kernel", c->horizon);
+    }
+  }
   // the fused kernel's reward wrap has no fmod slow path (pendulum.cuh wrap_diff<true>): |theta - target + pi| < 4 pi
   if (!(std::fabs(static_cast<const MbpoPendulumParams*>(sys_params_host)->target_angle) <= 6.0f))
     return fail(MBPO_EUNSUPPORTED, "fused plan: |target_angle| > 6 rad; use mbpo_icem_plan_staged");

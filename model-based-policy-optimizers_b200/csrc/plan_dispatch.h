@@ -14,6 +14,10 @@ namespace mbpo {
 template <int H>
 int plan_entry(int prng_mode, int math_mode, const PlanArgs& a, const MpcArgs* mpc, cudaStream_t st, int cluster);
 
+// Fused plan over the general Systems (MBPO_SYSTEM_NOISY_PENDULUM, MBPO_SYSTEM_POINT_MASS): icem_plan_general_kernel.
+template <int H>
+int general_plan_entry(int system_kind, int prng_mode, const PlanArgs& a, cudaStream_t st);
+
 // Cluster size the library picks for B problems of N candidates (0: one CTA per problem).
 inline int plan_cluster_size(int B, int N) {
   const int sms = device_sm_count();

@@ -125,6 +125,32 @@ int plan_entry<MBPO_INST_H>(int prng_mode, int math_mode, const PlanArgs& a, con
   }
 }
 
+namespace {
+template <class Sys, int PRNG>
+int launch_general(const PlanArgs& a, cudaStream_t st) {
+  const size_t smem = GenPlanSmem<kH, Sys::A>::bytes(a.N, a.Np, a.K);
+  auto kernel = icem_plan_general_kernel<Sys, kH, PRNG>;
+  if (smem > 227 * 1024) return fail(MBPO_EUNSUPPORTED, "general fused plan: %zu B of shared memory", smem);
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return fail(MBPO_ECUDA, "general plan smem attr (%zu): %s", smem, cudaGetErrorString(e));
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const long long resident = static_cast<long long>(per_sm) * device_sm_count();
+  const int grid = static_cast<int>(a.B < resident ? a.B : resident);
+  kernel<<<grid, 256, smem, st>>>(a);
+  return check_launch("icem_plan_general_kernel");
+}
+}  // namespace
+
+template <>
+int general_plan_entry<MBPO_INST_H>(int system_kind, int prng_mode, const PlanArgs& a, cudaStream_t st) {
+  if (system_kind == MBPO_SYSTEM_NOISY_PENDULUM)
+    return prng_mode == 0 ? launch_general<NoisyPendulumSys, 0>(a, st) : launch_general<NoisyPendulumSys, 1>(a, st);
+  if (system_kind == MBPO_SYSTEM_POINT_MASS)
+    return prng_mode == 0 ? launch_general<PointMassSys, 0>(a, st) : launch_general<PointMassSys, 1>(a, st);
+  return fail(MBPO_EUNSUPPORTED, "general fused plan: system_kind %d", system_kind);
+}
+
 template <>
 int noise_entry<MBPO_INST_H>(int prng_mode, const ScaleTable& tbl, const uint32_t* keys, int M, float* noise_out,
                              uint32_t* bits_out, cudaStream_t st) {

@@ -156,7 +156,7 @@ class iCemTO(BaseOptimizer):
         )
 
     def _plan_raw(self, x0: torch.Tensor, key: torch.Tensor, best_seq: torch.Tensor, system_params,
-                  trace: bool = False, cluster: int = -1):
+                  trace: bool = False, cluster: int = -1, staged: bool = False):
         """x0 [B,X], key [B,2], best_seq [B,H,A] -> (best_seq', best_value, key', trace dict|None).
         cluster: thread-block-cluster size of the fused plan (-1: the library's choice for B; 1, 2, 4, 8: forced --
         every choice gives the same bits)."""
@@ -171,7 +171,7 @@ class iCemTO(BaseOptimizer):
         out_key = torch.empty((B, 2), dtype=torch.uint32, device=dev)
         params = self.system.pack_params(system_params)
         tr_c, tr = None, None
-        fused = self._fused(cfg, params)
+        fused = self._fused(cfg, params) and not staged     # staged=True: the per-stage kernels even where a fused one exists
         with _lib.cuda_guard(x0):
             if fused:
                 if trace:
@@ -318,7 +318,8 @@ class iCemTO(BaseOptimizer):
         single, x0, key, seq = self._canon(initial_state, opt_state)
         cfg = self._cfg()
         params = self.system.pack_params(opt_state.system_params)
-        if self.cost_fn is not None or self._array_bounds() or not self._fused(cfg, params):
+        if (self.cost_fn is not None or self._array_bounds() or not self._fused(cfg, params)
+                or self.system.system_kind != _lib.SYSTEM_PENDULUM):      # the one-launch loop is the pendulum's
             return self._closed_loop_staged(single, x0, key, seq, opt_state, num_steps)
         B, dev = x0.shape[0], x0.device
         H, A = self.opt_dim

@@ -1937,15 +1937,16 @@ def test_general_objective_vs_oracle(mb, cuda_device, prng_mode, kind):
     np.testing.assert_allclose(vals.cpu().numpy(), rew.astype(np.float64).mean(-1), rtol=2e-6, atol=1e-6)
 
 
+@pytest.mark.parametrize("horizon", [10, 20])        # 10: no unrolled instance -> the staged plan; 20: the fused kernel
 @pytest.mark.parametrize("kind,use_optimism", [("noisy_pendulum", False), ("noisy_pendulum", True), ("point_mass", False)])
-def test_icem_plan_over_general_systems(mb, cuda_device, prng_mode, kind, use_optimism):
+def test_icem_plan_over_general_systems(mb, cuda_device, prng_mode, kind, use_optimism, horizon):
     """iCemTO through its unchanged API over a key-consuming System (P distinct particles per candidate, mean and max
     summaries) and over a System with two action dimensions: teacher-forced against the oracle iteration by iteration
     (keys and elite indices exact, sampled actions and objectives to tolerance, the refit bit-exact given the
     kernel's own actions and values); act() -- the C staged plan -- gives the traced composition's bits."""
     from mbpo_b200.optimizers import iCemTO, iCemParams
     system, osys = _general_systems(mb)[kind]
-    H, B, A = 10, 4, system.u_dim
+    H, B, A = horizon, 4, system.u_dim
     params = dict(num_samples=96, num_elites=12, num_particles=3, num_steps=3, alpha=0.1, exponent=1.0)
     opt = iCemTO(horizon=H, action_dim=A, opt_params=iCemParams(**params), use_optimism=use_optimism)
     opt.set_system(system)
@@ -1958,6 +1959,15 @@ def test_icem_plan_over_general_systems(mb, cuda_device, prng_mode, kind, use_op
     assert action.shape == (B, A)
     assert torch.equal(new.best_sequence, seq_t) and torch.equal(new.best_reward, val_t)
     assert torch.equal(new.key.view(torch.int32), key_t.view(torch.int32))
+    # act() ran the FUSED general kernel (one launch); the staged plan (one launch per stage) gives the same bits,
+    # and so does its traced composition, dump by dump
+    assert mb._lib.lib.mbpo_icem_plan_is_fused(mb._lib.C.byref(opt._cfg())) == (1 if horizon == 20 else 0)
+    s_seq, s_val, s_key, _ = opt._plan_raw(_dev(x0, cuda_device), st.key, st.best_sequence, st.system_params, staged=True)
+    assert torch.equal(s_seq, seq_t) and torch.equal(s_val, val_t)
+    _, _, _, tr_s = opt._plan_raw(_dev(x0, cuda_device), st.key, st.best_sequence, st.system_params, trace=True,
+                                  staged=True)
+    for name in ("actions", "values", "elite_idx", "mean", "std", "best_value"):
+        assert torch.equal(tr[name], tr_s[name]), name
     tr = {k: v.cpu().numpy() for k, v in tr.items()}
     p = orc.ICemParams(**params)
     M = p.num_samples + p.num_prev_elites
