@@ -447,13 +447,16 @@ def run_env(args):
     from mbpo_b200.parallel import shard_bounds
     from mbpo_b200.systems import PendulumSystem
     mbpo_b200.config.math_mode = args.math
-    lo, hi = shard_bounds(ENV_E, rank, world)
+    weak = args.scaling == "weak"
+    total_E = ENV_E * world if weak else ENV_E
+    lo, hi = shard_bounds(total_E, rank, world)
     E, T = hi - lo, ENV_T
     system = PendulumSystem()
     sp = system.reset(device=dev).system_params
     env = wrap(system, sp, episode_length=ENV_EPISODE)
-    x0 = torch.from_numpy(random_states(ENV_E, 1)[lo:hi].copy()).to(dev)
-    acts_host = torch.from_numpy(np.random.default_rng(2).uniform(-1, 1, (T, ENV_E, 1)).astype(np.float32)[:, lo:hi].copy())
+    x0 = torch.from_numpy(random_states(total_E, 1)[lo:hi].copy()).to(dev)
+    acts_host = torch.from_numpy(np.random.default_rng(2 + (rank if weak else 0)).uniform(-1, 1, (T, ENV_E if not weak else E, 1))
+                                 .astype(np.float32)[:, (lo if not weak else 0):(hi if not weak else E)].copy())
     acts_host = acts_host.pin_memory()
     acts = acts_host.to(dev)
     st = env.reset(x0)
@@ -505,7 +508,7 @@ def run_env(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    value = ENV_E * T / (ms * 1e-3)
+    value = total_E * T / (ms * 1e-3)
     # end to end: actions from pinned host memory, rewards back to the host
     rew_host = torch.empty((T, E), dtype=torch.float32).pin_memory()
     for _ in range(3):                                               # untimed: the allocator's first blocks, the streams
@@ -533,13 +536,13 @@ def run_env(args):
         emit_json({
             "metric": "vmapped System.step env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "config3_env_rollouts", "envs": ENV_E, "steps_per_call": T,
+            "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config3_env_rollouts", "envs": total_E, "envs_per_gpu": E, "steps_per_call": T,
                        "episode_length": ENV_EPISODE, "action_repeat": 1, "parallelism": "envs sharded x%d" % world,
                        "kernel": "sequential scan per env" if args.env_sequential else "episode pieces rolled concurrently",
                        "l2": "inputs+outputs %.2f GB per call >> 126 MB L2" % (E * T * ENV_BYTES_PER_TRANSITION / 1e9)},
             "math_mode": args.math, "clocks": clk.summary(),
-            "e2e": {"value": ENV_E * T / e2e_s, "unit": "env-steps/s", "ms_per_step": e2e_s * 1e3,
+            "e2e": {"value": total_E * T / e2e_s, "unit": "env-steps/s", "ms_per_step": e2e_s * 1e3,
                     "h2d_bytes_per_step": int(acts_host.numel() * 4), "d2h_bytes_per_step": int(rew_host.numel() * 4),
                     "api": "VmappedSystemEnv.unroll_streamed(actions[T,E,1] in pinned host memory, rewards to pinned host): "
                            "H2D, rollout and D2H of 64-step chunks overlapped on three streams"},
@@ -713,7 +716,8 @@ MPC_T, MPC_H = 200, 20
 
 def run_closed_loop(args):
     """A "step" is one 200-step closed-loop MPC episode from x0 = [-1, 0, 0] with iCemParams() defaults
-    (P = 10, N = 500, H = 20): plan -> true System.step -> warm start, 200 times, in ONE kernel launch."""
+    (P = 10, N = 500, H = 20): plan -> true System.step -> warm start, 200 times, in ONE kernel launch (one
+    8-CTA cluster)."""
     import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -810,8 +814,8 @@ def run_closed_loop(args):
         "gpu_launches": steps,
         "roofline": {"bound": "issue", "kernel": "icem_mpc_pendulum_kernel", "achieved": None,
                      "peak": 148 * 4 * 32 * sm_max * 1e6 / 1e12, "unit": "T lane-instr/s", "frac": None, "traffic": None,
-                     "note": "one problem occupies one CTA of one SM: the episode is latency-bound by construction "
-                             "(1/148 of the chip); throughput configurations are config 2 / config 5"},
+                     "note": "one problem = one 8-CTA thread-block cluster (8 of 148 SMs): the episode is latency-bound "
+                             "by construction; throughput configurations are config 2 / config 5"},
         "cpu_baseline": None}, GUARD)
 
 
@@ -895,12 +899,69 @@ def run_sweep(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-        rows.append({"problems": B, "ms_per_plan_call": ms, "transitions_per_s": transitions_per_step(B, H, p) / (ms * 1e-3)})
+        row = {"problems": B, "ms_per_plan_call": ms, "transitions_per_s": transitions_per_step(B, H, p) / (ms * 1e-3)}
+        # end to end through iCemTO.act with host buffers (states from pinned memory, first actions back) at this B
+        e2e_steps = max(steps // 2, 1)
+        if n > 0:
+            xh = x0.cpu().pin_memory()
+            ah = torch.empty((n, 1), dtype=torch.float32).pin_memory()
+            opt.act(xh.to(dev, non_blocking=True), state)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            if n > 0:
+                a_, _ = opt.act(xh.to(dev, non_blocking=True), state)
+                ah.copy_(a_, non_blocking=True)
+            torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        te = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        row["e2e_ms_per_plan_call"] = float(te.item()) * 1e3
+        row["e2e_transitions_per_s"] = transitions_per_step(B, H, p) / float(te.item())
+        rows.append(row)
         clocks = clk.summary()
         if n > 0:
             del state, x0, keys
     if rank == 0:
         top = rows[-1]
+        # CPU column: the C restatement + OpenMP on this host, measured up to 512 problems; beyond that one plan call
+        # is B independent problems over a fixed number of cores, so the rate of the largest measured point stands
+        cpu = None
+        if not args.no_cpu_baseline:
+            cpu_rows = {}
+            for Bc in (1, 8, 64, 512):
+                r = cpu_reference_step(dict(wl, B=Bc), steps=1, warmup=1, sample_B=Bc)
+                cpu_rows[Bc] = r
+            last = cpu_rows[512]
+            for row in rows:
+                Bc = row["problems"]
+                if Bc in cpu_rows:
+                    row["cpu_transitions_per_s"] = cpu_rows[Bc]["value"]
+                    row["cpu_ms_per_plan_call"] = cpu_rows[Bc]["ms_per_step"]
+                    row["cpu_measured"] = True
+                else:
+                    row["cpu_transitions_per_s"] = last["value"]
+                    row["cpu_ms_per_plan_call"] = last["ms_per_step"] * Bc / 512.0
+                    row["cpu_measured"] = False
+                row["gpu_over_cpu"] = row["transitions_per_s"] / row["cpu_transitions_per_s"]
+            ncores, model = host_info()
+            cpu = {"value": last["value"], "unit": UNIT, "cores": last["cores"], "kind": "port",
+                   "sample": "B in {1, 8, 64, 512} measured per point (C restatement + OpenMP); larger B carry the "
+                             "512-problem rate (independent problems over a fixed number of cores)",
+                   "host_cpu": model, "host_logical_cpus": ncores}
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        issue_peak = 148 * 4 * 32 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12 * world
+        best = max(rows, key=lambda r: r["transitions_per_s"])
+        for row in rows:
+            row["frac_algorithmic"] = row["transitions_per_s"] * ALGORITHMIC_LANE_INSTR_PER_TRANSITION / 1e12 / issue_peak
         emit_json({"metric": METRIC, "value": top["transitions_per_s"], "unit": UNIT, "n_gpus": world, "steps": 2,
                    "warmup": 3, "ms_per_step": top["ms_per_plan_call"], "higher_is_better": True, "scaling": "strong",
                    "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -910,8 +971,19 @@ def run_sweep(args):
                               "l2": "back-to-back launches; per-problem state is ~0.4 KB and the kernel works out of shared memory"},
                    "math_mode": args.math, "sweep": rows, "clocks": clocks,
                    "gpu_launches": sum((20 if r["problems"] <= 4096 else (5 if r["problems"] <= 32768 else 2)) * 2 for r in rows),
-                   "roofline": None, "cpu_baseline": None,
-                   "e2e": None}, GUARD)
+                   "roofline": {"bound": "issue", "kernel": "icem_plan_pendulum_kernel (clusters below 148 problems)",
+                                "achieved": best["transitions_per_s"] * ALGORITHMIC_LANE_INSTR_PER_TRANSITION / 1e12,
+                                "peak": issue_peak, "unit": "T lane-instr/s", "frac": best["frac_algorithmic"],
+                                "at_problems": best["problems"], "traffic": None,
+                                "note": "per-point frac_algorithmic in `sweep`; the left end is latency-bound (one "
+                                        "problem = one 8-CTA cluster of 148 SMs)"},
+                   "cpu_baseline": cpu,
+                   "e2e": {"value": top["e2e_transitions_per_s"], "unit": UNIT,
+                           "ms_per_step": top["e2e_ms_per_plan_call"],
+                           "h2d_bytes_per_step": int(top["problems"] // world * 12),
+                           "d2h_bytes_per_step": int(top["problems"] // world * 4),
+                           "api": "iCemTO.act(obs[B,3] from pinned host) -> first actions[B,1] to pinned host, per sweep "
+                                  "point in `sweep`"}}, GUARD)
     if world > 1:
         dist.destroy_process_group()
 
@@ -980,14 +1052,16 @@ def run_actor(args):
     from mbpo_b200.parallel import shard_bounds
     from mbpo_b200.systems import PendulumSystem
     mbpo_b200.config.math_mode = args.math
-    lo, hi = shard_bounds(ENV_E, rank, world)
+    weak = args.scaling == "weak"
+    total_E = ENV_E * world if weak else ENV_E
+    lo, hi = shard_bounds(total_E, rank, world)
     E = hi - lo
     system = PendulumSystem()
     env = wrap(system, system.reset(device=dev).system_params, episode_length=ENV_EPISODE)
     policy = acting.Policy(acting.PolicyParams([torch.from_numpy(w).to(dev) for w in pol_w],
                                                [torch.from_numpy(b).to(dev) for b in pol_b]),
                            kernel=args.actor_kernel)
-    x0_host = torch.from_numpy(random_states(ENV_E, 1)[lo:hi].copy()).pin_memory()
+    x0_host = torch.from_numpy(random_states(total_E, 1)[lo:hi].copy()).pin_memory()
     key = mbpo_b200.random.PRNGKey(0, dev)              # one key for all ranks: a shard draws its slice of the stream
     st = env.reset(x0_host.to(dev))
 
@@ -996,7 +1070,7 @@ def run_actor(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
     for _ in range(max(args.warmup, 3)):
-        acting.get_experience(env, st, policy, key, T, env_offset=lo, total_envs=ENV_E)
+        acting.get_experience(env, st, policy, key, T, env_offset=lo, total_envs=total_E)
     steps = min(args.steps, 10)
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
@@ -1004,7 +1078,7 @@ def run_actor(args):
         barrier()
         for k in range(steps):
             starts[k].record()
-            acting.get_experience(env, st, policy, key, T, env_offset=lo, total_envs=ENV_E)
+            acting.get_experience(env, st, policy, key, T, env_offset=lo, total_envs=total_E)
             ends[k].record()
         barrier()
     ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends)) / steps
@@ -1016,7 +1090,7 @@ def run_actor(args):
 
     def e2e_step():
         st_k = env.reset(x0_host.to(dev, non_blocking=True))
-        _, _, trn = acting.get_experience(env, st_k, policy, key, T, env_offset=lo, total_envs=ENV_E)
+        _, _, trn = acting.get_experience(env, st_k, policy, key, T, env_offset=lo, total_envs=total_E)
         rew_host.copy_(trn.reward, non_blocking=True)
         torch.cuda.synchronize(dev)
         return trn
@@ -1049,16 +1123,17 @@ def run_actor(args):
             roof = {"bound": "fma", "kernel": "actor_rollout_pendulum_kernel", "achieved": achieved, "peak": peak,
                     "unit": "T FMA/s", "frac": achieved / peak, "traffic": None, "note": ACT_INSTR_NOTE}
         emit_json({
-            "metric": "policy-in-the-loop env-steps/sec", "value": ENV_E * T / (ms * 1e-3), "unit": "env-steps/s",
+            "metric": "policy-in-the-loop env-steps/sec", "value": total_E * T / (ms * 1e-3), "unit": "env-steps/s",
             "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic (random-init policy)",
-            "config": {"workload": "config3_actor_rollouts", "envs": ENV_E, "steps_per_call": T,
+            "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (random-init policy)",
+            "config": {"workload": "config3_actor_rollouts", "envs": total_E, "envs_per_gpu": E, "steps_per_call": T,
                        "policy": "3-64-64-64-2 swish, NormalTanh", "episode_length": ENV_EPISODE,
                        "policy_kernel": "tcgen05 (TF32 x 3 split precision)" if tc else "CUDA cores (float32 FFMA2)",
                        "parallelism": "envs sharded x%d" % world,
                        "l2": "per-call outputs %.0f MB > 126 MB L2; the kernel is compute bound" % (E * T * 28 / 1e6)},
             "math_mode": args.math, "clocks": clk.summary(),
-            "e2e": {"value": ENV_E * T / e2e_s, "unit": "env-steps/s", "ms_per_step": e2e_s * 1e3,
+            "e2e": {"value": total_E * T / e2e_s, "unit": "env-steps/s", "ms_per_step": e2e_s * 1e3,
                     "h2d_bytes_per_step": int(x0_host.numel() * 4), "d2h_bytes_per_step": int(rew_host.numel() * 4),
                     "api": "acting.get_experience(env, reset(x0 from pinned host), policy, key, T) -> rewards to host"},
             "gpu_launches": steps,
@@ -1535,6 +1610,9 @@ def main():
                     default="config2_batched_icem")
     ap.add_argument("--math", choices=["reference", "theta_carry"], default="reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default=None,
+                    help="config3_* workloads: strong = 65,536 envs split over the ranks (default, BASELINE.json's "
+                         "wording); weak = 65,536 envs PER GPU")
     ap.add_argument("--no-others", action="store_true",
                     help="default workload: skip the compact measurements of configs 1, 3 and 4 (the `others` key)")
     ap.add_argument("--actor-kernel", choices=["auto", "cuda_cores", "tcgen05", "tcgen05_wide"], default="auto",
