@@ -8,7 +8,8 @@
 //
 //   1. every thread pushes the total-order key of its row's objective into ALL C copies of skey[]  (C remote stores)
 //   2. cluster.sync()
-//   3. every CTA runs the selection on its own full copy of the keys -- redundantly, identical results
+//   3. every CTA ranks ITS candidates against its full copy of the keys (rank = number of larger (key, index)
+//      pairs; rank < K = elite): exactly the stable argsort's top K, without a sort
 //   4. the owner of an elite row sends its element d to the CTA that refits column d (d mod C): rank-ordered ebuf[K][H]
 //   5. cluster.sync()
 //   6. every CTA refits its columns (the reference's rank-ordered sums) and pushes the new mean / std / best_seq of
@@ -49,7 +50,7 @@ struct ClusterSmem {
                          + 3 * H                               // mean, std, best_seq
                          + 2 * K                               // elite_idx, sel_idx
                          + select_scratch_words(K, N + Np)
-                         + 12;                                 // best_value, carry key, state key, true state, pad
+                         + 12;                                 // best_value, carry key + best key, state key, true state, pad
     return words * 4;
   }
 };
@@ -66,7 +67,7 @@ struct ClusterCtaSmem {
   int* sel_idx;
   uint32_t* sel_scratch;
   float* best_value;     // [1]
-  uint32_t* carry;       // [2]
+  uint32_t* carry;       // [3]
   uint32_t* state_key;   // [2]
   float* xs;             // [4] true state of the closed loop
   __device__ __forceinline__ ClusterCtaSmem(uint32_t* base, int R, int N, int Np, int K) {
@@ -81,8 +82,8 @@ struct ClusterCtaSmem {
     sel_idx = elite_idx + K;
     sel_scratch = reinterpret_cast<uint32_t*>(sel_idx + K);
     best_value = reinterpret_cast<float*>(sel_scratch + select_scratch_words(K, N + Np));
-    carry = reinterpret_cast<uint32_t*>(best_value + 1);
-    state_key = carry + 2;
+    carry = reinterpret_cast<uint32_t*>(best_value + 1);   // [0..1] carry key, [2] key of the best elite of the iteration
+    state_key = carry + 3;
     xs = reinterpret_cast<float*>(state_key + 2);
   }
 };
@@ -229,27 +230,94 @@ __device__ __forceinline__ void plan_problem_cluster(const PlanArgs& a, const Cl
         }
       }
     }
-    // ---- selection, redundantly (:199-203) --------------------------------------------------------------
-    cta_select<0, true>(rs, sm.skey, sm.elite_idx, sm.sel_idx, sm.sel_scratch);
-    const float best_elite = value_of_key(sm.skey[sm.elite_idx[K - 1]]);   // read before the next keys may arrive
-    const bool take = (*sm.best_value <= best_elite);
+    // ---- selection, distributed (:199-203): every CTA ranks ITS candidates against all keys ------------------
+    // rank(i) = number of candidates whose (key, index) pair is larger; the K elites are rank < K and the elite of
+    // ascending position e has rank K - 1 - e.  The pairs are distinct, so this is exactly argsort(values)[-K:]
+    // (stable, ascending) -- without the histogram passes of cta_select, whose barrier phases cost 6,300 cycles.
+    // The Np kept-elite rows N .. M-1 are dealt round-robin to the CTAs as virtual candidates (all-zero actions).
+    int* mine_row = sm.sel_idx;                                  // compact list of this CTA's elites: local row ...
+    const int V = (a.Np + C - 1 - rank) / C;                     // virtual rows of this CTA: j = N + rank + v * C
+    const int rows_here = R + V;                                 // local candidate slots [0, R) real, [R, R + V) virtual
+    // With many rows per CTA the all-pairs count costs more than cta_select's passes: then every CTA selects on its
+    // full copy of the keys (redundantly, identical results) and picks its own elites out of the list.
+    const bool ranked = 2 * rows_here <= NT;
+    uint32_t* cnt = sm.sel_scratch;                              // ranked: [rows_here] rank counters
+    uint32_t* n_mine = sm.sel_scratch + 299;                     // (the selection's scratch is dead once it returns)
+    int* mine_pos = reinterpret_cast<int*>(sm.sel_scratch) + 300; // ... and ascending position e   (<= K entries each)
+    if (ranked) {
+      for (int i = tid; i < rows_here; i += NT) cnt[i] = 0u;
+      if (tid == 0) *n_mine = 0u;
+      __syncthreads();
+      const int parts = NT / rows_here;                          // >= 2
+      const int chunk = (M + parts - 1) / parts;
+      for (int w = tid; w < rows_here * parts; w += NT) {
+        const int r = w / parts, part = w - r * parts;
+        const int i = r < R ? rank * R + r : N + rank + (r - R) * C;
+        if (r < R && i >= N) continue;                           // beyond the last real candidate
+        const uint32_t ki = sm.skey[i];
+        const int j1 = (part + 1) * chunk < M ? (part + 1) * chunk : M;
+        uint32_t larger = 0u;
+#pragma unroll 8
+        for (int j = part * chunk; j < j1; ++j) {
+          const uint32_t kj = sm.skey[j];
+          larger += (kj > ki || (kj == ki && j > i)) ? 1u : 0u;
+        }
+        if (larger) atomicAdd(&cnt[r], larger);
+      }
+      __syncthreads();
+      for (int r = tid; r < rows_here; r += NT) {
+        const int i = r < R ? rank * R + r : N + rank + (r - R) * C;
+        if ((r < R && i >= N) || static_cast<int>(cnt[r]) >= K) continue;
+        const int e = K - 1 - static_cast<int>(cnt[r]);
+        const uint32_t slot = atomicAdd(n_mine, 1u);
+        mine_row[slot] = r;
+        mine_pos[slot] = e;
+        cluster.map_shared_rank(sm.elite_idx, 0)[e] = i;         // CTA 0 keeps the index list (trace dumps)
+        if (e == K - 1)                                          // the best elite's key goes to everybody (:217-226)
+          for (int c = 0; c < C; ++c) cluster.map_shared_rank(sm.carry, c)[2] = sm.skey[i];
+      }
+    } else {
+      cta_select<0>(rs, sm.skey, sm.elite_idx, sm.sel_idx, sm.sel_scratch);   // sel_idx is free again afterwards
+      if (tid == 0) {
+        *n_mine = 0u;
+        sm.carry[2] = sm.skey[sm.elite_idx[K - 1]];
+      }
+      __syncthreads();
+      const uint32_t inv_r = ((1u << 20) + R - 1) / R;           // src / R == (src * inv_r) >> 20 (src < 2^11, R <= 2^8)
+      for (int e = tid; e < K; e += NT) {
+        const int src = sm.elite_idx[e];
+        int r = -1;
+        if (src >= N) {
+          if (((src - N) & (C - 1)) == rank) r = R + (src - N - rank) / C;
+        } else if (static_cast<int>((static_cast<uint32_t>(src) * inv_r) >> 20) == rank) {
+          r = src - rank * R;
+        }
+        if (r >= 0) {
+          const uint32_t slot = atomicAdd(n_mine, 1u);
+          mine_row[slot] = r;
+          mine_pos[slot] = e;
+        }
+      }
+    }
+    __syncthreads();
     MBPO_CLK(6);
     // ---- elite element (e, d) goes to the CTA that refits column d ---------------------------------------
-    const uint32_t inv_r = ((1u << 20) + R - 1) / R;           // src / R == (src * inv_r) >> 20 for src < 2^10 * ... (N <= 2048)
-    for (int i = tid; i < K * H; i += NT) {
-      const int e = i / H, d = i - e * H;
-      const int src = sm.elite_idx[e];
-      const int dst = d & (C - 1);                             // C is a power of two
-      if (src >= N) {
-        if (dst == rank) sm.ebuf[i] = 0.0f;                    // a kept-elite row: zeros (:192,:245)
-      } else if (static_cast<int>((static_cast<uint32_t>(src) * inv_r) >> 20) == rank) {
-        cluster.map_shared_rank(sm.ebuf, dst)[i] = sm.act[static_cast<size_t>(src - rank * R) * HS + d];
+    {
+      const int n_el = static_cast<int>(*n_mine);
+      for (int w = tid; w < n_el * H; w += NT) {
+        const int q = w / H, d = w - q * H;
+        const int r = mine_row[q], e = mine_pos[q];
+        const float v = r < R ? sm.act[static_cast<size_t>(r) * HS + d] : 0.0f;   // a kept-elite row: zeros (:192,:245)
+        cluster.map_shared_rank(sm.ebuf, d & (C - 1))[e * H + d] = v;          // C is a power of two
       }
     }
     MBPO_CLK(7);
     cluster.sync();   // this CTA's columns of the elite rows are complete; action rows are free again
     MBPO_CLK(8);
     // ---- refit + best tracking of this CTA's columns (:206-226); results to every CTA ----------------------
+    const float best_elite = value_of_key(sm.carry[2]);
+    const bool take = (*sm.best_value <= best_elite);
+    __syncthreads();   // every thread has read *best_value
     if (tid < H && (tid & (C - 1)) == rank) {
       const int d = tid;
       auto elite = [&](int e, int dd) { return sm.ebuf[e * H + dd]; };

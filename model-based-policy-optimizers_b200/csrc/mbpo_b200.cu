@@ -220,16 +220,26 @@ int run_plan(const MbpoIcemCfg* c, const void* sys_params_host, const float* x0,
                  "plan: cluster_size %d (use -1, 1, 2, 4, 8 or 16)", cluster);
     const int R = (a.N + cluster - 1) / cluster;
     if (R > 256) return fail(MBPO_EUNSUPPORTED, "plan: %d candidates per CTA of a %d-cluster (at most 256)", R, cluster);
+    if (R + (a.Np + cluster - 1) / cluster > 298 || a.N + a.Np < 36)   // the cluster kernel's use of the selection scratch
+      return fail(MBPO_EUNSUPPORTED, "plan: population (%d + %d) outside what a %d-cluster handles", a.N, a.Np, cluster);
   }
-  switch (c->horizon) {
+  const auto dispatch = [&](int cl) -> int {
+    switch (c->horizon) {
 #define X(h) \
   case h:    \
-    return plan_entry<h>(c->prng_mode, c->math_mode, a, mpc, as_stream(stream), cluster);
-    MBPO_FOR_EACH_H(X)
+    return plan_entry<h>(c->prng_mode, c->math_mode, a, mpc, as_stream(stream), cl);
+      MBPO_FOR_EACH_H(X)
 #undef X
-    default:
-      return fail(MBPO_EUNSUPPORTED, "horizon %d has no compiled kernel", c->horizon);
+      default:
+        return fail(MBPO_EUNSUPPORTED, "horizon %d has no compiled kernel", c->horizon);
+    }
+  };
+  int rc2 = dispatch(cluster);
+  if (rc2 == MBPO_ECUDA && cluster_size < 0 && cluster == 16) {
+    cudaGetLastError();                 // the device refused the non-portable size the library picked: use 8
+    rc2 = dispatch(8);
   }
+  return rc2;
 }
 
 }  // namespace

@@ -22,7 +22,9 @@ int general_plan_entry(int system_kind, int prng_mode, const PlanArgs& a, cudaSt
 inline int plan_cluster_size(int B, int N) {
   const int sms = device_sm_count();
   if (B <= 0 || B >= sms) return 0;
-  int c = 8;    // the portable maximum; 16 (non-portable) is available on request
+  // one or two problems: the non-portable 16 (32 candidates per CTA at N = 512: one cooperative sampling chunk);
+  // otherwise the largest portable size that still gives every cluster its own SMs
+  int c = (B <= 2 && (N + 15) / 16 >= 32) ? 16 : 8;
   while (c > 1 && (B * c > sms || (N + c - 1) / c < 32)) c >>= 1;
   if (c <= 1 || (N + c - 1) / c > 256) return 0;
   return c;

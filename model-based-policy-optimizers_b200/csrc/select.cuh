@@ -22,7 +22,7 @@ namespace mbpo {
 
 #ifdef MBPO_CLUSTER_CLOCKS
 __device__ long long g_select_clocks[16];
-#define MBPO_SEL_CLK(i) do { if (LATENCY && threadIdx.x == 0 && blockIdx.x == 0) g_select_clocks[i] = clock64(); } while (0)
+#define MBPO_SEL_CLK(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_select_clocks[i] = clock64(); } while (0)
 #else
 #define MBPO_SEL_CLK(i) do {} while (0)
 #endif
@@ -53,11 +53,7 @@ template <int THREADS>
 __device__ __forceinline__ int cta_threads() { return THREADS ? THREADS : static_cast<int>(blockDim.x); }
 
 // Steps 0-5: elite_idx[K] = argsort(values)[-K:] in ascending rank.  On return elite_idx is visible to every thread.
-// LATENCY = false (the throughput kernels): step 5 costs the fewest instructions -- one thread per elite walks the
-// whole list.  LATENCY = true (one problem per cluster, idle issue slots): the all-pairs comparison is spread over
-// every thread of the CTA (NT / K threads per elite, partial counts combined with shared-memory atomics) -- more
-// instructions, half the time (measured: 3,700 -> 1,950 cycles at K = 50).  Same result.
-template <int THREADS, bool LATENCY = false>
+template <int THREADS>
 __device__ __forceinline__ void cta_select(const RefitScalars rs, const uint32_t* keys, int* elite_idx, int* sel_idx,
                                            uint32_t* scratch) {
   const int NT = cta_threads<THREADS>();
@@ -173,37 +169,16 @@ __device__ __forceinline__ void cta_select(const RefitScalars rs, const uint32_t
 
   MBPO_SEL_CLK(5);
   // ---- 5. rank the K elites by (key, index) ascending --------------------------------------
-  if (LATENCY) {
-    uint32_t* cnt = hist;
-    for (int i = tid; i < K; i += NT) cnt[i] = 0u;
-    __syncthreads();
-    const int parts = (NT / K) > 0 ? (NT / K) : 1;
-    for (int w = tid; w < K * parts; w += NT) {
-      const int e = w / parts, part = w - e * parts;
-      const int ie = sel_idx[e];
-      const uint32_t ke = sel_key[e];
-      int rank = 0;
-      for (int f = part; f < K; f += parts) {
-        const int jf = sel_idx[f];
-        const uint32_t kf = sel_key[f];
-        rank += (kf < ke || (kf == ke && jf < ie)) ? 1 : 0;
-      }
-      if (rank) atomicAdd(&cnt[e], static_cast<uint32_t>(rank));
+  for (int e = tid; e < K; e += NT) {
+    const int ie = sel_idx[e];
+    const uint32_t ke = sel_key[e];
+    int rank = 0;
+    for (int f = 0; f < K; ++f) {
+      const int jf = sel_idx[f];
+      const uint32_t kf = sel_key[f];
+      rank += (kf < ke || (kf == ke && jf < ie)) ? 1 : 0;
     }
-    __syncthreads();
-    for (int e = tid; e < K; e += NT) elite_idx[cnt[e]] = sel_idx[e];
-  } else {
-    for (int e = tid; e < K; e += NT) {
-      const int ie = sel_idx[e];
-      const uint32_t ke = sel_key[e];
-      int rank = 0;
-      for (int f = 0; f < K; ++f) {
-        const int jf = sel_idx[f];
-        const uint32_t kf = sel_key[f];
-        rank += (kf < ke || (kf == ke && jf < ie)) ? 1 : 0;
-      }
-      elite_idx[rank] = ie;
-    }
+    elite_idx[rank] = ie;
   }
   __syncthreads();
   MBPO_SEL_CLK(6);

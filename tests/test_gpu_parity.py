@@ -802,13 +802,13 @@ def test_cluster_plan_bit_identical(mb, cuda_device, prng_mode, horizon, params,
 
 
 def test_cluster_choice_and_closed_loop(mb, cuda_device, prng_mode):
-    """The library spreads few problems over clusters by itself (B = 1 -> 8 CTAs) and the closed loop
+    """The library spreads few problems over clusters by itself (B = 1 -> 16 CTAs, B = 8 -> 8) and the closed loop
     (tests/test_icemopt.py:19-32) on a cluster reproduces the one-CTA closed loop bit for bit."""
     L = mb._lib
     system, system_state, cem, st = _icemopt_setup(mb, cuda_device)
     cfg = cem._cfg()
     sizes = {B: L.lib.mbpo_icem_plan_cluster_size(L.C.byref(cfg), B) for B in (1, 8, 18, 19, 37, 64, 74, 75, 148, 4096)}
-    assert sizes[1] == 8 and sizes[8] == 8 and sizes[18] == 8 and sizes[19] == 4 and sizes[37] == 4
+    assert sizes[1] == 16 and sizes[8] == 8 and sizes[18] == 8 and sizes[19] == 4 and sizes[37] == 4
     assert sizes[64] == 2 and sizes[74] == 2 and sizes[75] in (0, 1) and sizes[4096] in (0, 1)
     one = cem.closed_loop(system_state.x_next, st, 40, cluster=1)
     for c in (2, 8, 16, -1):
