@@ -77,8 +77,8 @@ __device__ __forceinline__ float summarize_particles(float ret, int P, int summa
 // Fused plan kernel
 // ------------------------------------------------------------------------------------------
 struct PlanArgs {
-  // shapes / hyper-parameters
-  int B, N, Np, K, P, S;
+  // shapes / hyper-parameters (H: the horizon, read by the any-horizon kernels only; the others have it as a template argument)
+  int B, N, Np, K, P, S, H;
   int warm_start, summarize;
   float init_std, alpha, one_minus_alpha, u_min, u_max;
   MbpoPendulumParams sys;
@@ -97,23 +97,30 @@ struct PlanArgs {
   int zero_value_precomputed;
 };
 
-template <int H>
+// HT: the horizon as a template argument (unrolled sampling, immediate twiddles) or 0 = any horizon, read from
+// PlanArgs::H at run time (rolled sampling; needs a staging row per thread besides the action rows).
+constexpr int PLAN_THREADS = 256;
+
+template <int HT>
 struct PlanSmem {
-  static constexpr int HS = H | 1;  // odd row stride: conflict-free per-thread rows
-  static size_t bytes(int N, int Np, int K) {
-    size_t words = static_cast<size_t>(N + 1) * HS  // action rows + one all-zero row
+  static constexpr int HS = HT | 1;  // odd row stride: conflict-free per-thread rows (HT != 0)
+  static size_t bytes(int N, int Np, int K, int H_rt = 0) {
+    const int H = HT ? HT : H_rt;
+    const int hs = H | 1;
+    size_t words = static_cast<size_t>(N + 1) * hs  // action rows + one all-zero row
                    + (N + Np)                   // sort keys
                    + 2 * (N + 1)                // legacy split words
                    + 3 * H                      // mean, std, best_seq
                    + 2 * K                      // elite_idx, sel_idx
                    + select_scratch_words(K, N + Np)  // selection histogram + lists
-                   + 8;                         // best_value, carry key, state key, pad
+                   + 8                          // best_value, carry key, state key, pad
+                   + (HT ? 0 : static_cast<size_t>(PLAN_THREADS) * hs);  // any horizon: staged normals of the row in flight
     return words * 4;
   }
 };
 
 // Shared-memory carve-up of one planning CTA.
-template <int H>
+template <int HT>
 struct PlanCtaSmem {
   float* act;          // [N + 1][HS] action rows of the sampled candidates; row N is all zeros
   uint32_t* skey;      // [M]     total-order keys of the objective values
@@ -127,8 +134,10 @@ struct PlanCtaSmem {
   float* best_value;   // [1]
   uint32_t* carry;     // [2] carry.key
   uint32_t* state_key; // [2] opt_state.key (closed loop)
-  __device__ __forceinline__ PlanCtaSmem(uint32_t* base, int N, int Np, int K) {
-    constexpr int HS = PlanSmem<H>::HS;
+  float* stage;        // [THREADS][HS] (HT == 0 only)
+  __device__ __forceinline__ PlanCtaSmem(uint32_t* base, int N, int Np, int K, int H_rt = 0) {
+    const int H = HT ? HT : H_rt;
+    const int HS = H | 1;
     act = reinterpret_cast<float*>(base);
     skey = base + static_cast<size_t>(N + 1) * HS;
     flat = skey + (N + Np);
@@ -141,6 +150,7 @@ struct PlanCtaSmem {
     best_value = reinterpret_cast<float*>(sel_scratch + select_scratch_words(K, N + Np));
     carry = reinterpret_cast<uint32_t*>(best_value + 1);
     state_key = carry + 2;
+    stage = reinterpret_cast<float*>(state_key + 5);
   }
 };
 
@@ -152,11 +162,13 @@ struct PlanCtaSmem {
 // best sequence for the warm start; `key_in` is opt_state.key; the new opt_state.key is
 // returned through key_new (valid in thread 0 only).  `slot` indexes the optional trace
 // dumps ([S, B, ...] with problem slot `slot` of `slots`).
-template <int H, int PRNG, int MATH, int THREADS>
-__device__ __forceinline__ void plan_problem(const PlanArgs& a, const PlanCtaSmem<H>& sm, const PendulumConsts& pc,
+template <int HT, int PRNG, int MATH, int THREADS>
+__device__ __forceinline__ void plan_problem(const PlanArgs& a, const PlanCtaSmem<HT>& sm, const PendulumConsts& pc,
                                              const RefitScalars& rs, const float* prev_best, Key2 key_in,
-                                             Key2& key_new, float x_th, float x_w, int slot, int slots) {
-  constexpr int HS = PlanSmem<H>::HS;
+                                             Key2& key_new, float x_th, float x_w, int slot, int slots,
+                                             const TwiddleTable* tw = nullptr) {
+  const int H = HT ? HT : a.H;
+  const int HS = H | 1;
   const int N = a.N, M = a.N + a.Np, K = a.K;
   const int tid = threadIdx.x;
   float* act = sm.act;
@@ -228,10 +240,12 @@ __device__ __forceinline__ void plan_problem(const PlanArgs& a, const PlanCtaSme
         else skey_n = split_at<1>(sampling_rng, static_cast<uint32_t>(N + 1), static_cast<uint32_t>(n + 1));
         const Key2 dim_key = split1<PRNG>(skey_n);             // vmap(split(x, action_dim)), A == 1  (:180)
         float* row = act + static_cast<size_t>(n) * HS;
-        colored_noise_row<H, PRNG>(dim_key, a.scale, row, nullptr, [&](int t, float y) {
+        auto emit = [&](int t, float y) {
           const float v = __fadd_rn(mean[t], __fmul_rn(y, std_[t]));           // :190
           row[t] = fminf(fmaxf(v, a.u_min), a.u_max);                          // :191
-        });
+        };
+        if constexpr (HT != 0) colored_noise_row<HT, PRNG>(dim_key, a.scale, row, nullptr, emit);
+        else colored_noise_row_rt<PRNG>(H, dim_key, a.scale, *tw, sm.stage + static_cast<size_t>(tid) * HS, nullptr, emit);
       }
       const int r0 = n0 < N ? n0 : N, r1 = n1 < N ? n1 : N;   // idle slots roll out the zero row
       float ret0, ret1;
@@ -297,10 +311,11 @@ __global__ void zero_row_value_kernel(const MbpoPendulumParams sys, int H, int P
 }
 
 // Fused plan: one CTA plans one problem at a time (grid-stride over problems).
-template <int H, int PRNG, int MATH, int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) icem_plan_pendulum_kernel(const __grid_constant__ PlanArgs a) {
+template <int HT, int PRNG, int MATH, int THREADS>
+__device__ __forceinline__ void plan_kernel_body(const PlanArgs& a, const TwiddleTable* tw) {
   extern __shared__ __align__(16) uint32_t smem_u32[];
-  const PlanCtaSmem<H> sm(smem_u32, a.N, a.Np, a.K);
+  const int H = HT ? HT : a.H;
+  const PlanCtaSmem<HT> sm(smem_u32, a.N, a.Np, a.K, H);
   const int tid = threadIdx.x;
   const PendulumConsts pc(a.sys);
   RefitScalars rs;
@@ -309,8 +324,8 @@ __global__ void __launch_bounds__(THREADS, MINB) icem_plan_pendulum_kernel(const
   for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
     const float x_c = a.x0[3 * b], x_s = a.x0[3 * b + 1], x_w = a.x0[3 * b + 2];
     Key2 k_in{a.key_in[2 * b], a.key_in[2 * b + 1]}, k_new;
-    plan_problem<H, PRNG, MATH, THREADS>(a, sm, pc, rs, a.best_seq_in + static_cast<size_t>(b) * H, k_in, k_new,
-                                         atan2_bounded(x_s, x_c), x_w, b, a.B);
+    plan_problem<HT, PRNG, MATH, THREADS>(a, sm, pc, rs, a.best_seq_in + static_cast<size_t>(b) * H, k_in, k_new,
+                                          atan2_bounded(x_s, x_c), x_w, b, a.B, tw);
     // ---- epilogue (:251) -----------------------------------------------------------------
     if (tid < H) a.best_seq_out[static_cast<size_t>(b) * H + tid] = sm.best_seq[tid];
     if (tid == 0) {
@@ -320,6 +335,18 @@ __global__ void __launch_bounds__(THREADS, MINB) icem_plan_pendulum_kernel(const
     }
     __syncthreads();
   }
+}
+
+template <int H, int PRNG, int MATH, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) icem_plan_pendulum_kernel(const __grid_constant__ PlanArgs a) {
+  plan_kernel_body<H, PRNG, MATH, THREADS>(a, nullptr);
+}
+
+// The same for ANY horizon in [2, MBPO_MAX_HORIZON] (PlanArgs::H): rolled sampling, twiddle table in the constant bank.
+template <int PRNG, int MATH>
+__global__ void __launch_bounds__(PLAN_THREADS, 1)
+    icem_plan_pendulum_rt_kernel(const __grid_constant__ PlanArgs a, const __grid_constant__ TwiddleTable tw) {
+  plan_kernel_body<0, PRNG, MATH, PLAN_THREADS>(a, &tw);
 }
 
 // Closed-loop MPC (tests/test_icemopt.py:19-32): T times { act = optimize(x)[0]; x = true
@@ -332,11 +359,11 @@ struct MpcArgs {
   float* actions_out;  // [T,B,1]
 };
 
-template <int H, int PRNG, int MATH, int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB)
-    icem_mpc_pendulum_kernel(const __grid_constant__ PlanArgs a, const __grid_constant__ MpcArgs m) {
+template <int HT, int PRNG, int MATH, int THREADS>
+__device__ __forceinline__ void mpc_kernel_body(const PlanArgs& a, const MpcArgs& m, const TwiddleTable* tw) {
   extern __shared__ __align__(16) uint32_t smem_u32[];
-  const PlanCtaSmem<H> sm(smem_u32, a.N, a.Np, a.K);
+  const int H = HT ? HT : a.H;
+  const PlanCtaSmem<HT> sm(smem_u32, a.N, a.Np, a.K, H);
   __shared__ float xs[4];
   const int tid = threadIdx.x;
   const PendulumConsts pc(a.sys);
@@ -351,8 +378,8 @@ __global__ void __launch_bounds__(THREADS, MINB)
     for (int t = 0; t < m.T; ++t) {
       const float x_c = xs[0], x_s = xs[1], x_w = xs[2];
       Key2 k_in{sm.state_key[0], sm.state_key[1]}, k_new;
-      plan_problem<H, PRNG, MATH, THREADS>(a, sm, pc, rs, sm.best_seq, k_in, k_new, atan2_bounded(x_s, x_c), x_w, 0,
-                                           1);
+      plan_problem<HT, PRNG, MATH, THREADS>(a, sm, pc, rs, sm.best_seq, k_in, k_new, atan2_bounded(x_s, x_c), x_w, 0,
+                                            1, tw);
       if (tid == 0) {
         sm.state_key[0] = k_new.k0; sm.state_key[1] = k_new.k1;
         const float u = sm.best_seq[0];                       // opt_state.action (:67-69)
@@ -380,6 +407,19 @@ __global__ void __launch_bounds__(THREADS, MINB)
     }
     __syncthreads();
   }
+}
+
+template <int H, int PRNG, int MATH, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+    icem_mpc_pendulum_kernel(const __grid_constant__ PlanArgs a, const __grid_constant__ MpcArgs m) {
+  mpc_kernel_body<H, PRNG, MATH, THREADS>(a, m, nullptr);
+}
+
+template <int PRNG, int MATH>
+__global__ void __launch_bounds__(PLAN_THREADS, 1)
+    icem_mpc_pendulum_rt_kernel(const __grid_constant__ PlanArgs a, const __grid_constant__ MpcArgs m,
+                                const __grid_constant__ TwiddleTable tw) {
+  mpc_kernel_body<0, PRNG, MATH, PLAN_THREADS>(a, m, &tw);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -140,6 +140,7 @@ void fill_plan_args(PlanArgs& a, const MbpoIcemCfg* c, const MbpoPendulumParams*
                     float* best_value_out, uint32_t* key_out, const MbpoIcemTrace* trace) {
   std::memset(&a, 0, sizeof(a));
   a.B = B; a.N = c->num_samples; a.Np = c->num_prev_elites; a.K = c->num_elites; a.P = c->num_particles;
+  a.H = c->horizon;
   a.S = c->num_steps; a.warm_start = c->warm_start; a.summarize = c->summarize;
   a.init_std = c->init_std; a.alpha = c->alpha; a.one_minus_alpha = static_cast<float>(1.0 - static_cast<double>(c->alpha));
   a.u_min = c->u_min; a.u_max = c->u_max;
@@ -168,12 +169,12 @@ int plan_fusable(const MbpoIcemCfg* c, bool set_error) {
   }
   if (c->system_kind != MBPO_SYSTEM_PENDULUM) why = "fused plan supports the pendulum and the general Systems only";
   else if (c->action_dim != 1 || c->x_dim != 3) why = "fused plan requires action_dim == 1 and x_dim == 3";
-  else if (!horizon_supported(c->horizon)) why = "fused plan: horizon has no compiled kernel (" MBPO_H_LIST_STR ")";
   else {
     const int HS = c->horizon | 1;
-    const size_t words = static_cast<size_t>(c->num_samples + 1) * HS + (c->num_samples + c->num_prev_elites) +
-                         2 * (c->num_samples + 1) + 3 * c->horizon + 2 * c->num_elites +
-                         select_scratch_words(c->num_elites, c->num_samples + c->num_prev_elites) + 8;
+    size_t words = static_cast<size_t>(c->num_samples + 1) * HS + (c->num_samples + c->num_prev_elites) +
+                   2 * (c->num_samples + 1) + 3 * c->horizon + 2 * c->num_elites +
+                   select_scratch_words(c->num_elites, c->num_samples + c->num_prev_elites) + 8;
+    if (!horizon_supported(c->horizon)) words += static_cast<size_t>(PLAN_THREADS) * HS;   // the any-horizon kernel's staging rows
     if (words * 4 > 227 * 1024) why = "fused plan: population does not fit 227 KB of shared memory";
   }
   if (why && set_error) fail(MBPO_EUNSUPPORTED, "%s", why);
@@ -215,6 +216,10 @@ int run_plan(const MbpoIcemCfg* c, const void* sys_params_host, const float* x0,
   // few problems: spread each over a thread-block cluster (same bits; icem_cluster_kernels.cuh)
   int cluster = cluster_size;
   if (cluster < 0) cluster = plan_cluster_size(B, a.N);
+  if (!horizon_supported(c->horizon)) {
+    if (cluster_size > 1) return fail(MBPO_EUNSUPPORTED, "plan: clusters exist for the unrolled horizons (" MBPO_H_LIST_STR ")");
+    return plan_entry_rt(c->prng_mode, c->math_mode, a, mpc, as_stream(stream));
+  }
   if (cluster > 1) {
     MBPO_REQUIRE(cluster == 2 || cluster == 4 || cluster == 8 || cluster == 16,
                  "plan: cluster_size %d (use -1, 1, 2, 4, 8 or 16)", cluster);
@@ -614,7 +619,9 @@ int mbpo_icem_plan_clustered(const MbpoIcemCfg* cfg, const void* sys_params_host
 }
 
 int mbpo_icem_plan_cluster_size(const MbpoIcemCfg* cfg, int B) {
-  if (validate_cfg(cfg) != MBPO_OK || !plan_fusable(cfg, false)) return 0;
+  if (validate_cfg(cfg) != MBPO_OK || !plan_fusable(cfg, false) || !horizon_supported(cfg->horizon) ||
+      general_system_kind(cfg->system_kind))
+    return 0;
   return plan_cluster_size(B, cfg->num_samples);
 }
 

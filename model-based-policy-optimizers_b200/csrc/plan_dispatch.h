@@ -14,6 +14,9 @@ namespace mbpo {
 template <int H>
 int plan_entry(int prng_mode, int math_mode, const PlanArgs& a, const MpcArgs* mpc, cudaStream_t st, int cluster);
 
+// The same for a horizon without an unrolled instance (plan_rt.cu; PlanArgs::H).
+int plan_entry_rt(int prng_mode, int math_mode, const PlanArgs& a, const MpcArgs* mpc, cudaStream_t st);
+
 // Fused plan over the general Systems (MBPO_SYSTEM_NOISY_PENDULUM, MBPO_SYSTEM_POINT_MASS): icem_plan_general_kernel.
 template <int H>
 int general_plan_entry(int system_kind, int prng_mode, const PlanArgs& a, cudaStream_t st);

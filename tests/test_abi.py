@@ -74,7 +74,9 @@ def test_error_codes_without_gpu(mb):
     L.check(L.lib.mbpo_icem_cfg_init(C.byref(cfg), 30, 1, 3, 1, 512, 50, 0.5, 0.0, 5, 0.0, 0.3, -1.0, 1.0, 1, 1e4))
     assert L.lib.mbpo_icem_plan_is_fused(C.byref(cfg)) == 1
     assert L.lib.mbpo_icem_workspace_bytes(C.byref(cfg), 16) > 16 * 527 * 30 * 4
-    cfg.horizon = 21                                   # no unrolled instance for H=21: the staged plan runs it
+    cfg.horizon = 21                                   # no unrolled instance for H=21: the any-horizon fused kernel
+    assert L.lib.mbpo_icem_plan_is_fused(C.byref(cfg)) == 1 and L.lib.mbpo_icem_plan_cluster_size(C.byref(cfg), 1) == 0
+    cfg.horizon = 128                                  # 513 x 129 floats + 256 staging rows do not fit: staged
     assert L.lib.mbpo_icem_plan_is_fused(C.byref(cfg)) == 0
     cfg.horizon = 30
     cfg.num_samples = 4000                             # 4000 x 31 floats do not fit 227 KB of shared memory

@@ -259,10 +259,9 @@ def test_any_horizon_sample_actions(mb, cuda_device, prng_mode, horizon, action_
 
 @pytest.mark.parametrize("horizon", [10, 25, 40])
 def test_any_horizon_plan_vs_oracle(mb, cuda_device, horizon, budget_report):
-    """iCemTO(horizon=h) for horizons without a fused kernel: the staged plan (same per-stage kernels) against the
-    oracle, free-running with the explanation walk; act() (the C staged plan) gives the traced composition's bits;
-    the closed loop runs as plan -> System.step launches and reaches the reference test's threshold scaled to its
-    length."""
+    """iCemTO(horizon=h) for horizons without an unrolled instance: the any-horizon FUSED kernel (rolled sampling
+    loops, one launch) against the oracle, free-running with the explanation walk; it gives the staged plan's bits
+    (the same per-stage device functions); the closed loop runs in one launch too and equals plan -> System.step."""
     from mbpo_b200.optimizers import iCemTO, iCemParams
     from mbpo_b200.systems import PendulumSystem
     B = 5
@@ -270,18 +269,24 @@ def test_any_horizon_plan_vs_oracle(mb, cuda_device, horizon, budget_report):
     opt = iCemTO(horizon=horizon, action_dim=1, opt_params=iCemParams(**params))
     system = PendulumSystem()
     opt.set_system(system)
-    assert mb._lib.lib.mbpo_icem_plan_is_fused(mb._lib.C.byref(opt._cfg())) == 0
+    assert mb._lib.lib.mbpo_icem_plan_is_fused(mb._lib.C.byref(opt._cfg())) == 1
     keys = _keys(B, seed=200 + horizon)
     x0 = _random_states(B, 201 + horizon)
     st, seq, val = _free_running_vs_oracle("any_horizon_H%d" % horizon, opt, mb, cuda_device, x0, keys, params,
                                            horizon, budget_report)
     action, new = opt.act(_dev(x0, cuda_device), st)
     assert torch.equal(new.best_sequence, seq) and torch.equal(new.best_reward, val)
-    states, rewards, actions, fin = opt.closed_loop(_dev(x0, cuda_device), st, 3)
-    assert states.shape == (3, B, 3) and rewards.shape == (3, B) and actions.shape == (3, B, 1)
+    s_seq, s_val, s_key, _ = opt._plan_raw(_dev(x0, cuda_device), st.key, st.best_sequence, st.system_params, staged=True)
+    assert torch.equal(s_seq, seq) and torch.equal(s_val, val) and torch.equal(s_key.view(torch.int32), new.key.view(torch.int32))
+    states, rewards, actions, fin = opt.closed_loop(_dev(x0, cuda_device), st, 4)          # one launch
+    assert states.shape == (4, B, 3) and rewards.shape == (4, B) and actions.shape == (4, B, 1)
     assert torch.equal(actions[0], action)
     one = system.step(_dev(x0, cuda_device), action, st.system_params)
     assert torch.equal(states[0], one.x_next) and torch.equal(rewards[0], one.reward)
+    single, x0c, keyc, seqc = opt._canon(_dev(x0, cuda_device), st)
+    s2, r2, a2, fin2 = opt._closed_loop_staged(single, x0c, keyc, seqc, st, 4)           # plan -> step launches
+    assert torch.equal(states, s2) and torch.equal(rewards, r2) and torch.equal(actions, a2)
+    assert torch.equal(fin.best_sequence, fin2.best_sequence)
 
 
 @pytest.mark.parametrize("target", [0.0, 3.0, -6.0, 7.5, 40.0])
