@@ -117,9 +117,12 @@ __global__ void __launch_bounds__(ENV_THREADS, 18) env_rollout_pendulum_kernel(c
   const float ep_len = static_cast<float>(a.episode_length);
   const float rep = static_cast<float>(a.action_repeat);
   const size_t E = static_cast<size_t>(a.E);
-  // theta-carry: the angle lives in a register across steps; [cos, sin] are only outputs
-  float th = (MATH == MBPO_MATH_REFERENCE) ? 0.0f : atan2_bounded(s, c);
-  const float f_th = (MATH == MBPO_MATH_REFERENCE) ? 0.0f : atan2_bounded(f_s, f_c);
+  // theta-carry: the angle lives in a register across steps; [cos, sin] are only outputs.  Reference math in the
+  // uniform-warp loop carries it too -- theta = atan2(sin, cos) of the CURRENT state, re-derived after every step
+  // from the fresh unit [cos, sin] (pendulum_step_ref_thcs: the guard-free atan2; same bits) -- so the guarded atan2
+  // runs only here, on the caller's arbitrary states.
+  float th = (MATH == MBPO_MATH_REFERENCE && !FAST) ? 0.0f : atan2_bounded(s, c);
+  const float f_th = (MATH == MBPO_MATH_REFERENCE && !FAST) ? 0.0f : atan2_bounded(f_s, f_c);
   if (FAST) {
     const bool uniform = __all_sync(0xffffffffu, live && t_beg == w_beg && t_end == w_end);
     if (uniform) {
@@ -152,7 +155,7 @@ __global__ void __launch_bounds__(ENV_THREADS, 18) env_rollout_pendulum_kernel(c
               if (row_lane) *reinterpret_cast<float4*>(a.observation_out + off3) = v;
             }
             float rew;
-            if (MATH == MBPO_MATH_REFERENCE) pendulum_step_ref<true>(pc, c, s, w, u_cur[k], rew);
+            if (MATH == MBPO_MATH_REFERENCE) pendulum_step_ref_thcs<true>(pc, th, c, s, w, u_cur[k], rew);
             else { pendulum_step_theta<true>(pc, th, w, u_cur[k], rew); sincos_bounded(th, s, c); }
             rew = __fadd_rn(0.0f, rew);                          // the wrapper's reward sum starts at 0
             steps = __fadd_rn(steps, 1.0f);

@@ -98,6 +98,19 @@ __device__ __forceinline__ void pendulum_step_ref_th(const PendulumConsts& p, fl
   w = nw;
 }
 
+// The same step for a loop that also needs [cos, sin] of every state (the env kernels stream them out): theta of the
+// current state in, the next state's [cos, sin] and its theta out.  Same bits as pendulum_step_ref.
+template <bool SMALL = false>
+__device__ __forceinline__ void pendulum_step_ref_thcs(const PendulumConsts& p, float& th, float& c, float& s,
+                                                       float& w, float u, float& reward) {
+  reward = reward_from<SMALL>(p, th, w, u);
+  const float nw = pendulum_next_thdot(p, sin_bounded(th), w, u);
+  const float nth = fmaf(nw, p.dt, th);
+  sincos_bounded(nth, s, c);
+  th = atan2_bounded<true>(s, c);
+  w = nw;
+}
+
 // Theta-carry variant: the state is (theta, thdot) with theta kept in (-pi, pi], which is
 // what atan2(sin(newth), cos(newth)) returns up to rounding.
 template <bool SMALL = false>
