@@ -2,19 +2,22 @@
 //
 // The fused plan (icem_kernels.cuh) gives a problem one CTA = one SM: at B = 1 (the reference's own test,
 // tests/test_icemopt.py) 147 of 148 SMs idle and the plan takes as long as one thread needs for its two rows.
-// Here a cluster of C CTAs (C = 2, 4, 8, or the non-portable 16) owns the problem; CTA r samples and rolls out
-// candidates [r R, (r + 1) R), R = ceil(N / C), and the elite exchange runs through
-// distributed shared memory:
+// Here a cluster of C CTAs (C = 2, 4, 8, or the non-portable 16) owns the problem; CTA r owns candidates
+// [r R, (r + 1) R), R = ceil(N / C), and the elite exchange runs through distributed shared memory.  Inside a CTA
+// the warps are split: the first ceil(R / 32) warps roll out one candidate per thread, the others sample the colored
+// noise of the NEXT iteration meanwhile (neither the noise nor the key chain depends on data; only
+// clip(mean + noise * std) waits for the refit).  One iteration:
 //
-//   1. every thread pushes the total-order key of its row's objective into ALL C copies of skey[]  (C remote stores)
+//   1. rollout warps: objective of the row -> total-order key into ALL C copies of skey[]  (C remote stores);
+//      sampling warps: noise rows of iteration it + 1 into nz[]
 //   2. cluster.sync()
 //   3. every CTA ranks ITS candidates against its full copy of the keys (rank = number of larger (key, index)
-//      pairs; rank < K = elite): exactly the stable argsort's top K, without a sort
-//   4. the owner of an elite row sends its element d to the CTA that refits column d (d mod C): rank-ordered ebuf[K][H]
+//      pairs; rank < K = elite): exactly the stable argsort's top K, without a sort  (many rows per CTA: every CTA
+//      runs the one-CTA selection on its copy instead and picks out its own elites)
+//   4. the owner of an elite row sends it to every CTA: rank-ordered ebuf[K][H]
 //   5. cluster.sync()
-//   6. every CTA refits its columns (the reference's rank-ordered sums) and pushes the new mean / std / best_seq of
-//      those columns into all C copies
-//   7. cluster.sync()
+//   6. every CTA refits all columns for itself (the reference's rank-ordered sums on identical inputs: identical
+//      mean / std / best everywhere, no third exchange) and applies them to the presampled noise
 //
 // Every number is produced by the device functions of the one-CTA kernel in the same order (same key tree, same
 // noise row, same rollout step, same selection, same rank-ordered refit sums): the results are the one-CTA kernel's
@@ -30,6 +33,10 @@ namespace mbpo {
 
 namespace cg = cooperative_groups;
 
+#ifndef MBPO_QUIET_SCHED
+#define MBPO_QUIET_SCHED 1
+#endif
+
 constexpr int CLUSTER_MAX = 16;   // 16 is a non-portable size (cudaFuncAttributeNonPortableClusterSizeAllowed)
 
 #ifdef MBPO_CLUSTER_CLOCKS
@@ -39,12 +46,21 @@ __device__ long long g_cluster_clocks[64];
 #define MBPO_CLK(i) do {} while (0)
 #endif
 
+// A CTA that owns at most this many rows samples them cooperatively (coop_sample_rows) and overlaps the sampling of
+// the next iteration's noise with the rollouts of this one.
+constexpr int COOP_MAX_ROWS = 96;
+// Threads of a cooperative CTA: per chunk of 32 rows one rollout warp and seven sampling warps, at most 512 threads
+// (128 registers each: the kernel holds a sampling and a rollout instance and spills below that).
+constexpr int COOP_WARPS_PER_CHUNK = 8;
+constexpr int CLUSTER_MAX_THREADS = 512;
+
 // Shared memory of one CTA of the cluster (words).
 template <int H>
 struct ClusterSmem {
   static constexpr int HS = H | 1;
   static size_t bytes(int R, int N, int Np, int K) {
     const size_t words = static_cast<size_t>(R) * HS          // this CTA's action rows
+                         + static_cast<size_t>(R) * HS          // next iteration's noise rows
                          + static_cast<size_t>(K) * H          // rank-ordered elite rows (filled by their owners)
                          + (N + Np)                            // sort keys of ALL candidates (filled by their owners)
                          + 3 * H                               // mean, std, best_seq
@@ -70,6 +86,7 @@ struct ClusterCtaSmem {
   uint32_t* carry;       // [3]
   uint32_t* state_key;   // [2]
   float* xs;             // [4] true state of the closed loop
+  float* nz;             // [R][HS] colored noise of the NEXT iteration
   __device__ __forceinline__ ClusterCtaSmem(uint32_t* base, int R, int N, int Np, int K) {
     constexpr int HS = ClusterSmem<H>::HS;
     act = reinterpret_cast<float*>(base);
@@ -85,6 +102,7 @@ struct ClusterCtaSmem {
     carry = reinterpret_cast<uint32_t*>(best_value + 1);   // [0..1] carry key, [2] key of the best elite of the iteration
     state_key = carry + 3;
     xs = reinterpret_cast<float*>(state_key + 2);
+    nz = best_value + 12;
   }
 };
 
@@ -94,13 +112,13 @@ struct ClusterCtaSmem {
 // idle anyway), then the 2 x tasks threefry-block + normal units of the two half spectra are dealt round-robin to
 // the warps, and after a barrier each warp evaluates its share of the DFT output groups.  Same device functions and
 // per-output operation order as colored_noise_row: same bits.
-constexpr int COOP_MAX_ROWS = 96;
-
+//
 // `parts` warps share one chunk of 32 rows (this warp is share `part` of them); warps of different chunks run side
 // by side.  Called by every thread of the CTA (barriers inside); `valid` marks the lanes that own a row.
-template <int H, int PRNG, typename Emit>
+// `bar` is a barrier over exactly the threads that make the call (all of the CTA, or the sampling warps alone).
+template <int H, int PRNG, typename Emit, typename Bar>
 __device__ __forceinline__ void coop_sample_rows(Key2 sampling_rng, int N, int n, bool valid, int part, int parts,
-                                                 const float* __restrict__ scale, float* row, Emit emit) {
+                                                 const float* __restrict__ scale, float* row, Emit emit, Bar bar) {
   using S = NoiseShape<H>;
   constexpr int TASKS = noise_tasks<H, PRNG>();
   if (valid) {
@@ -113,27 +131,22 @@ __device__ __forceinline__ void coop_sample_rows(Key2 sampling_rng, int N, int n
       else stage_normals_task<H, PRNG, true>(key_si, scale, row, nullptr, task - TASKS);
     }
   }
-  __syncthreads();   // the rows' staged half spectra are complete
+  bar();   // the rows' staged half spectra are complete
   float sr[S::F], si[S::F];
   if (valid) load_staged<H>(row, sr, si);
-  __syncthreads();   // every warp holds them in registers: the outputs may overwrite the rows
+  bar();   // every warp holds them in registers: the outputs may overwrite the rows
   if (valid)
     for (int g = part; g < dft_groups<H>(); g += parts) detail::dft_one_group<H, 0>(g, sr, si, emit);
 }
 
-// iCemTO.optimize for ONE problem, executed by the whole cluster.  Same contract as plan_problem(); zero_value is
-// the objective of the all-zero kept-elite row (zero_row_value_kernel or, in the closed loop, the caller's own
-// rollout).  Trace dumps are written by the owners (values, actions) and by CTA 0 (the rest).
-//
-// Per iteration: sample + roll out the CTA's rows -> push the keys to every CTA -> cluster.sync -> selection
-// (every CTA, redundantly) -> the owner of an elite row sends element d to the CTA that refits column d
-// (d mod C) -> cluster.sync -> each CTA refits its columns and pushes mean / std / best_seq of those columns to
-// every CTA -> cluster.sync.
+// iCemTO.optimize for ONE problem, executed by the whole cluster.  Same contract as plan_problem(); the objective
+// of the all-zero kept-elite rows (:192,:245) is rolled out here by one thread, beside the sampling of iteration 0.
+// Trace dumps are written by the owners (values, actions) and by CTA 0 (the rest).
 template <int H, int PRNG, int MATH>
 __device__ __forceinline__ void plan_problem_cluster(const PlanArgs& a, const ClusterCtaSmem<H>& sm,
                                                      const PendulumConsts& pc, const RefitScalars& rs,
                                                      const float* prev_best, Key2 key_in, Key2& key_new, float x_th,
-                                                     float x_w, float zero_value, int slot, int slots, int R) {
+                                                     float x_w, int slot, int slots, int R) {
   constexpr int HS = ClusterSmem<H>::HS;
   cg::cluster_group cluster = cg::this_cluster();
   const int C = static_cast<int>(cluster.num_blocks());
@@ -152,71 +165,104 @@ __device__ __forceinline__ void plan_problem_cluster(const PlanArgs& a, const Cl
     mean[tid] = m0;
     std_[tid] = a.init_std;
     best_seq[tid] = m0;
+    sm.act[tid] = 0.0f;                             // row 0 = the all-zero kept-elite row, rolled out by thread 0 below
   }
   if (tid == 0) {
     *sm.best_value = __int_as_float(0xFF800000);  // -inf
-    Key2 k_opt;
-    split2<PRNG>(key_in, k_opt, key_new);
-    sm.carry[0] = k_opt.k0;
-    sm.carry[1] = k_opt.k1;
+    sm.sel_scratch[299] = 0u;                       // the elite list cursor of the selection
   }
-  for (int j = N + tid; j < M; j += NT) sm.skey[j] = total_order_key(zero_value);   // kept-elite rows (:192,:245)
+  // The carry key (:174-180) does not depend on data: every thread advances its own copy in registers.
+  Key2 chain;
+  split2<PRNG>(key_in, chain, key_new);
+  auto next_sampling_rng = [&]() {
+    Key2 srng, particles_rng;
+    split2<PRNG>(chain, srng, particles_rng);
+    chain = split_at<PRNG>(srng, static_cast<uint32_t>(N + 1), 0u);   // key = sampling_rng[0]  (:176)
+    return srng;
+  };
   __syncthreads();
 
+  // ---- who does what.  The colored noise does not depend on mean / std either, so the CTA is split: the first
+  // `chunks` warps own one candidate per thread and roll it out; the other warps sample the noise of iteration
+  // it + 1 meanwhile (into nz); only  clip(mean + noise * std)  (:190-191) waits for the refit.  Few rows
+  // (R <= COOP_MAX_ROWS): `sparts` sampling warps share each chunk of 32 rows (coop_sample_rows); more rows: one
+  // sampling thread per row.  Pass it = -1 samples iteration 0 and rolls out the all-zero row.
+  const int warp = tid >> 5, lane = tid & 31;
+  const int chunks = (R + 31) >> 5;                        // rollout warps (32 rows each)
+  const int warps = NT >> 5;
+  const bool coop = R <= COOP_MAX_ROWS;
+  // One rollout warp (R <= 32): the warp that shares its scheduler (warp & 3 == 0) stays idle in the loop, so the
+  // rollout chain -- the critical path -- issues alone.
+  const bool quiet = MBPO_QUIET_SCHED && chunks == 1 && warps == 8;
+  const int sparts = quiet ? 6 : (warps - chunks) / chunks;   // coop: sampling warps per chunk (host: >= 1)
+  const int swarps = chunks * sparts;
   const int n = rank * R + tid;             // the candidate this thread rolls out
   const bool mine = tid < R && n < N;
   float* row = sm.act + static_cast<size_t>(tid < R ? tid : 0) * HS;
-  const bool coop = R <= COOP_MAX_ROWS;
+  float zero_value = 0.0f;
 
-  for (int it = 0; it < a.S; ++it) {
-    const size_t tslot = static_cast<size_t>(it) * slots + slot;
-    // ---- key plumbing (:174-180) ---------------------------------------------------------------------
+  for (int it = -1; it < a.S; ++it) {
+    const size_t tslot = static_cast<size_t>(it < 0 ? 0 : it) * slots + slot;
     MBPO_CLK(0);
-    Key2 ck{sm.carry[0], sm.carry[1]}, sampling_rng, particles_rng;
-    split2<PRNG>(ck, sampling_rng, particles_rng);
-    __syncthreads();  // every thread has read carry
     MBPO_CLK(1);
-    if (tid == NT - 1) {
-      const Key2 nk = split_at<PRNG>(sampling_rng, static_cast<uint32_t>(N + 1), 0u);   // key = sampling_rng[0]  (:176)
-      sm.carry[0] = nk.k0;
-      sm.carry[1] = nk.k1;
-    }
-    // ---- sampling -----------------------------------------------------------------------------------------
-    if (coop) {
-      // chunks of 32 rows side by side, warps / chunks warps on each
-      const int chunks = (R + 31) >> 5, warps = NT >> 5;
-      const int parts = warps / chunks;
-      const int chunk = (tid >> 5) / parts, part = (tid >> 5) - chunk * parts;
-      const int r = (chunk << 5) + (tid & 31);
-      const int nn = rank * R + r;
-      float* rw = sm.act + static_cast<size_t>(r < R ? r : 0) * HS;
-      coop_sample_rows<H, PRNG>(sampling_rng, N, nn, chunk < chunks && r < R && nn < N, part, parts, a.scale, rw,
-                                [&](int t, float y) {
-        const float v = __fadd_rn(mean[t], __fmul_rn(y, std_[t]));           // :190
-        rw[t] = fminf(fmaxf(v, a.u_min), a.u_max);                           // :191
-      });
-      __syncthreads();   // the rows are complete before their rollout threads read them
-    } else if (mine) {
-      const Key2 skey_n = split_at<PRNG>(sampling_rng, static_cast<uint32_t>(N + 1), static_cast<uint32_t>(n + 1));
-      const Key2 dim_key = split1<PRNG>(skey_n);
-      colored_noise_row<H, PRNG>(dim_key, a.scale, row, nullptr, [&](int t, float y) {
-        const float v = __fadd_rn(mean[t], __fmul_rn(y, std_[t]));
-        row[t] = fminf(fmaxf(v, a.u_min), a.u_max);
-      });
-    }
-    MBPO_CLK(2);
-    // ---- rollout of this thread's row; the key goes to every CTA of the cluster -----------------------------
-    if (mine) {
+    if (warp >= chunks) {
+      // ---- sampling warps: the noise of iteration it + 1 -----------------------------------------------------
+      if (it + 1 < a.S) {
+        if (coop) {
+          const int sw = quiet ? ((warp & 3) == 0 ? swarps : warp - 1 - (warp >> 2)) : warp - chunks;
+          if (sw < swarps) {
+            const Key2 srng = next_sampling_rng();
+            const int chunk = sw / sparts;
+            const int count = swarps << 5;
+            const int r = (chunk << 5) + lane;
+            const int nn = rank * R + r;
+            float* nrow = sm.nz + static_cast<size_t>(r < R ? r : 0) * HS;
+            coop_sample_rows<H, PRNG>(srng, N, nn, r < R && nn < N, sw - chunk * sparts, sparts, a.scale, nrow,
+                                      [&](int t, float y) { nrow[t] = y; },
+                                      [count] { asm volatile("bar.sync 1, %0;" ::"r"(count) : "memory"); });
+          }
+        } else {
+          const int r = tid - (chunks << 5);
+          const int nn = rank * R + r;
+          if (r < R && nn < N) {
+            const Key2 srng = next_sampling_rng();
+            const Key2 skey_n = split_at<PRNG>(srng, static_cast<uint32_t>(N + 1), static_cast<uint32_t>(nn + 1));
+            const Key2 dim_key = split1<PRNG>(skey_n);
+            float* nrow = sm.nz + static_cast<size_t>(r) * HS;
+            colored_noise_row<H, PRNG>(dim_key, a.scale, nrow, nullptr, [&](int t, float y) { nrow[t] = y; });
+          }
+        }
+      }
+      MBPO_CLK(2);
+    } else if (it < 0 ? tid == 0 : mine) {
+      // ---- rollout of this thread's row; the key goes to every CTA of the cluster -----------------------------
       const float ret = rollout_return_th<MATH, true>(pc, x_th, x_w, H, [&](int t) { return row[t]; });
       MBPO_CLK(3);
       const float val = summarize_particles(ret, a.P, a.summarize);
-      const uint32_t key = total_order_key(val);
-      for (int c = 0; c < C; ++c) cluster.map_shared_rank(sm.skey, c)[n] = key;
-      if (a.trace.values) a.trace.values[tslot * M + n] = val;
-      if (a.trace.actions) {
-        float* dst = a.trace.actions + (tslot * M + n) * H;
-        for (int t = 0; t < H; ++t) dst[t] = row[t];
+      if (it < 0) {
+        sm.xs[3] = val;                     // the objective of the kept-elite rows (:192,:245)
+      } else {
+        const uint32_t key = total_order_key(val);
+        for (int c = 0; c < C; ++c) cluster.map_shared_rank(sm.skey, c)[n] = key;
+        if (a.trace.values) a.trace.values[tslot * M + n] = val;
+        if (a.trace.actions) {
+          float* dst = a.trace.actions + (tslot * M + n) * H;
+          for (int t = 0; t < H; ++t) dst[t] = row[t];
+        }
       }
+    }
+    if (it < 0) {
+      __syncthreads();
+      zero_value = sm.xs[3];
+      for (int j = N + tid; j < M; j += NT) sm.skey[j] = total_order_key(zero_value);
+      // :190-191 on the presampled noise (ends with a barrier)
+      for (int w = tid; w < R * H; w += NT) {
+        const int r = w / H, t = w - r * H;
+        const float v = __fadd_rn(mean[t], __fmul_rn(sm.nz[static_cast<size_t>(r) * HS + t], std_[t]));
+        sm.act[static_cast<size_t>(r) * HS + t] = fminf(fmaxf(v, a.u_min), a.u_max);
+      }
+      __syncthreads();
+      continue;
     }
     MBPO_CLK(4);
     cluster.sync();   // all keys are in every copy
@@ -240,42 +286,60 @@ __device__ __forceinline__ void plan_problem_cluster(const PlanArgs& a, const Cl
     const int rows_here = R + V;                                 // local candidate slots [0, R) real, [R, R + V) virtual
     // With many rows per CTA the all-pairs count costs more than cta_select's passes: then every CTA selects on its
     // full copy of the keys (redundantly, identical results) and picks its own elites out of the list.
-    const bool ranked = 2 * rows_here <= NT;
-    uint32_t* cnt = sm.sel_scratch;                              // ranked: [rows_here] rank counters
+    // Ranked: a warp takes RB rows at a time (independent compare chains); its lanes stride over the keys and one
+    // __reduce_add per row counts the larger pairs -- no shared counters, no barrier inside.  The loops stay rolled:
+    // this code runs once per iteration on a few warps, so every instruction is an instruction-cache miss and a
+    // compact loop beats its unrolled form (measured: 3,400 cycles unrolled over 20 keys per lane).
+    // (the choice must be the same in every CTA of the cluster -- the ranked CTAs send the best elite's key to all,
+    // the others read it from their own list -- so it is made on the largest row count, rank 0's)
+    const bool ranked = 2 * (R + (a.Np + C - 1) / C) <= NT;
     uint32_t* n_mine = sm.sel_scratch + 299;                     // (the selection's scratch is dead once it returns)
     int* mine_pos = reinterpret_cast<int*>(sm.sel_scratch) + 300; // ... and ascending position e   (<= K entries each)
     if (ranked) {
-      for (int i = tid; i < rows_here; i += NT) cnt[i] = 0u;
-      if (tid == 0) *n_mine = 0u;
-      __syncthreads();
-      const int parts = NT / rows_here;                          // >= 2
-      const int chunk = (M + parts - 1) / parts;
-      for (int w = tid; w < rows_here * parts; w += NT) {
-        const int r = w / parts, part = w - r * parts;
-        const int i = r < R ? rank * R + r : N + rank + (r - R) * C;
-        if (r < R && i >= N) continue;                           // beyond the last real candidate
-        const uint32_t ki = sm.skey[i];
-        const int j1 = (part + 1) * chunk < M ? (part + 1) * chunk : M;
-        uint32_t larger = 0u;
-#pragma unroll 8
-        for (int j = part * chunk; j < j1; ++j) {
-          const uint32_t kj = sm.skey[j];
-          larger += (kj > ki || (kj == ki && j > i)) ? 1u : 0u;
+      MBPO_CLK(10);
+      constexpr int RB = 6;
+#pragma unroll 1
+      for (int r0 = warp; r0 < rows_here; r0 += RB * warps) {
+        unsigned long long pi[RB];
+        uint32_t larger[RB];
+#pragma unroll
+        for (int b = 0; b < RB; ++b) {
+          const int r = r0 + b * warps;
+          const int i = r < R ? rank * R + r : N + rank + (r - R) * C;
+          const bool ok = r < rows_here && !(r < R && i >= N);   // warp-uniform
+          // (key, index) pairs compared as one 64-bit integer: branch-free, two compares per pair
+          pi[b] = ok ? (static_cast<unsigned long long>(sm.skey[i]) << 32) | static_cast<uint32_t>(i) : ~0ull;
+          larger[b] = 0u;
         }
-        if (larger) atomicAdd(&cnt[r], larger);
+#pragma unroll 4
+        for (int j = lane; j < M; j += 32) {
+          const unsigned long long pj = (static_cast<unsigned long long>(sm.skey[j]) << 32) | static_cast<uint32_t>(j);
+#pragma unroll
+          for (int b = 0; b < RB; ++b) larger[b] += pj > pi[b] ? 1u : 0u;
+        }
+        MBPO_CLK(11);
+        // lane b finishes row b of the batch
+        unsigned long long my_pi = ~0ull;
+        uint32_t my_cnt = 0u;
+#pragma unroll
+        for (int b = 0; b < RB; ++b) {
+          const uint32_t cnt = __reduce_add_sync(0xFFFFFFFFu, larger[b]);
+          if (lane == b) { my_cnt = cnt; my_pi = pi[b]; }
+        }
+        if (my_pi != ~0ull && static_cast<int>(my_cnt) < K) {    // (a real pair never has index 2^32 - 1)
+          const int r = r0 + lane * warps;
+          const uint32_t ki = static_cast<uint32_t>(my_pi >> 32);
+          const int i = static_cast<int>(static_cast<uint32_t>(my_pi));
+          const int e = K - 1 - static_cast<int>(my_cnt);
+          const uint32_t slot = atomicAdd(n_mine, 1u);
+          mine_row[slot] = r;
+          mine_pos[slot] = e;
+          cluster.map_shared_rank(sm.elite_idx, 0)[e] = i;       // CTA 0 keeps the index list (trace dumps)
+          if (e == K - 1)                                        // the best elite's key goes to everybody (:217-226)
+            for (int c = 0; c < C; ++c) cluster.map_shared_rank(sm.carry, c)[2] = ki;
+        }
       }
-      __syncthreads();
-      for (int r = tid; r < rows_here; r += NT) {
-        const int i = r < R ? rank * R + r : N + rank + (r - R) * C;
-        if ((r < R && i >= N) || static_cast<int>(cnt[r]) >= K) continue;
-        const int e = K - 1 - static_cast<int>(cnt[r]);
-        const uint32_t slot = atomicAdd(n_mine, 1u);
-        mine_row[slot] = r;
-        mine_pos[slot] = e;
-        cluster.map_shared_rank(sm.elite_idx, 0)[e] = i;         // CTA 0 keeps the index list (trace dumps)
-        if (e == K - 1)                                          // the best elite's key goes to everybody (:217-226)
-          for (int c = 0; c < C; ++c) cluster.map_shared_rank(sm.carry, c)[2] = sm.skey[i];
-      }
+      MBPO_CLK(12);
     } else {
       cta_select<0>(rs, sm.skey, sm.elite_idx, sm.sel_idx, sm.sel_scratch);   // sel_idx is free again afterwards
       if (tid == 0) {
@@ -301,37 +365,24 @@ __device__ __forceinline__ void plan_problem_cluster(const PlanArgs& a, const Cl
     }
     __syncthreads();
     MBPO_CLK(6);
-    // ---- elite element (e, d) goes to the CTA that refits column d ---------------------------------------
+    // ---- every elite row goes to every CTA (rank-ordered ebuf) ------------------------------------------------
     {
       const int n_el = static_cast<int>(*n_mine);
       for (int w = tid; w < n_el * H; w += NT) {
         const int q = w / H, d = w - q * H;
         const int r = mine_row[q], e = mine_pos[q];
         const float v = r < R ? sm.act[static_cast<size_t>(r) * HS + d] : 0.0f;   // a kept-elite row: zeros (:192,:245)
-        cluster.map_shared_rank(sm.ebuf, d & (C - 1))[e * H + d] = v;          // C is a power of two
+        for (int c = 0; c < C; ++c) cluster.map_shared_rank(sm.ebuf, c)[e * H + d] = v;
       }
     }
     MBPO_CLK(7);
-    cluster.sync();   // this CTA's columns of the elite rows are complete; action rows are free again
+    cluster.sync();   // the elite rows are complete in every CTA; action rows are free again
     MBPO_CLK(8);
-    // ---- refit + best tracking of this CTA's columns (:206-226); results to every CTA ----------------------
-    const float best_elite = value_of_key(sm.carry[2]);
-    const bool take = (*sm.best_value <= best_elite);
-    __syncthreads();   // every thread has read *best_value
-    if (tid < H && (tid & (C - 1)) == rank) {
-      const int d = tid;
-      auto elite = [&](int e, int dd) { return sm.ebuf[e * H + dd]; };
-      float m_new, s_new;
-      refit_column(rs, elite, d, mean[d], std_[d], m_new, s_new);
-      const float b_new = elite(K - 1, d);
-      for (int c = 0; c < C; ++c) {
-        cluster.map_shared_rank(mean, c)[d] = m_new;
-        cluster.map_shared_rank(std_, c)[d] = s_new;
-        if (take) cluster.map_shared_rank(best_seq, c)[d] = b_new;
-      }
-    }
-    if (tid == 0 && take) *sm.best_value = best_elite;
-    cluster.sync();   // mean / std / best_seq are complete everywhere
+    // ---- refit + best tracking (:206-226), every CTA for itself: identical inputs, identical results, and no
+    // third exchange.  (A CTA that runs ahead cannot disturb a slower one: it writes skey / ebuf / carry[2] of the
+    // next iteration only after that iteration's first cluster.sync, which the slower CTA reaches after this refit.)
+    cta_refit<0>(rs, value_of_key(sm.carry[2]), [&](int e, int d) { return sm.ebuf[e * H + d]; }, mean, std_,
+                 best_seq, sm.best_value);
     MBPO_CLK(9);
     if (rank == 0) {
       if (a.trace.elite_idx)
@@ -342,15 +393,23 @@ __device__ __forceinline__ void plan_problem_cluster(const PlanArgs& a, const Cl
       }
       if (a.trace.best_value && tid == 0) a.trace.best_value[tslot] = *sm.best_value;
     }
+    if (tid == 0) *n_mine = 0u;
+    if (it + 1 < a.S) {   // the next iteration's rows (their noise was sampled under the rollouts), :190-191
+      for (int w = tid; w < R * H; w += NT) {
+        const int r = w / H, t = w - r * H;
+        const float v = __fadd_rn(mean[t], __fmul_rn(sm.nz[static_cast<size_t>(r) * HS + t], std_[t]));
+        sm.act[static_cast<size_t>(r) * HS + t] = fminf(fmaxf(v, a.u_min), a.u_max);
+      }
+    }
     __syncthreads();
   }
 }
 
 // One cluster plans one problem at a time (cluster-stride over problems).  Launched with cluster dimension C along
-// x and R = ceil(N / C) rounded up to a warp as the block size; best_value_out holds the zero-row objectives on entry
-// (zero_row_value_kernel), like the one-CTA kernel.
+// x; best_value_out holds the zero-row objectives on entry (zero_row_value_kernel) when the CTAs own more than
+// COOP_MAX_ROWS rows, like the one-CTA kernel.
 template <int H, int PRNG, int MATH>
-__global__ void __launch_bounds__(256, 1) icem_plan_cluster_kernel(const __grid_constant__ PlanArgs a, int R) {
+__global__ void __launch_bounds__(CLUSTER_MAX_THREADS, 1) icem_plan_cluster_kernel(const __grid_constant__ PlanArgs a, int R) {
   extern __shared__ __align__(16) uint32_t smem_u32[];
   cg::cluster_group cluster = cg::this_cluster();
   const int C = static_cast<int>(cluster.num_blocks());
@@ -364,9 +423,8 @@ __global__ void __launch_bounds__(256, 1) icem_plan_cluster_kernel(const __grid_
   for (int b = static_cast<int>(blockIdx.x) / C; b < a.B; b += clusters) {
     const float x_c = a.x0[3 * b], x_s = a.x0[3 * b + 1], x_w = a.x0[3 * b + 2];
     Key2 k_in{a.key_in[2 * b], a.key_in[2 * b + 1]}, k_new;
-    const float zero_value = a.best_value_out[b];
     plan_problem_cluster<H, PRNG, MATH>(a, sm, pc, rs, a.best_seq_in + static_cast<size_t>(b) * H, k_in, k_new,
-                                        atan2_bounded(x_s, x_c), x_w, zero_value, b, a.B, R);
+                                        atan2_bounded(x_s, x_c), x_w, b, a.B, R);
     cluster.sync();   // every CTA has read the zero-row value; no CTA runs ahead into a lagging CTA's buffers
     if (rank == 0) {
       if (tid < H) a.best_seq_out[static_cast<size_t>(b) * H + tid] = sm.best_seq[tid];
@@ -384,7 +442,7 @@ __global__ void __launch_bounds__(256, 1) icem_plan_cluster_kernel(const __grid_
 // keeps its own copy of the true state, the planner key and the best sequence (identical by construction); CTA 0
 // writes the outputs.  The zero-row objective of every step is one rollout by one thread per CTA.
 template <int H, int PRNG, int MATH>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(CLUSTER_MAX_THREADS, 1)
     icem_mpc_cluster_kernel(const __grid_constant__ PlanArgs a, const __grid_constant__ MpcArgs m, int R) {
   extern __shared__ __align__(16) uint32_t smem_u32[];
   cg::cluster_group cluster = cg::this_cluster();
@@ -404,15 +462,8 @@ __global__ void __launch_bounds__(256, 1)
     for (int t = 0; t < m.T; ++t) {
       const float x_c = sm.xs[0], x_s = sm.xs[1], x_w = sm.xs[2];
       Key2 k_in{sm.state_key[0], sm.state_key[1]}, k_new;
-      // the objective of the all-zero row from this state: the same rollout zero_row_value_kernel runs
-      if (tid == 0) {
-        const float ret = rollout_return<MATH, true>(pc, x_c, x_s, x_w, H, [](int) { return 0.0f; });
-        sm.xs[3] = summarize_particles(ret, a.P, a.summarize);
-      }
-      __syncthreads();
-      const float zero_value = sm.xs[3];
       plan_problem_cluster<H, PRNG, MATH>(a, sm, pc, rs, sm.best_seq, k_in, k_new, atan2_bounded(x_s, x_c), x_w,
-                                          zero_value, 0, 1, R);
+                                          0, 1, R);
       if (tid == 0) {
         sm.state_key[0] = k_new.k0; sm.state_key[1] = k_new.k1;
         const float u = sm.best_seq[0];                       // opt_state.action (:67-69)

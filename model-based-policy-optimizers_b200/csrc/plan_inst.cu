@@ -30,11 +30,15 @@ int prepare_plan_kernel(Kernel kernel, size_t smem, int B, int* grid_out) {
 template <int PRNG, int MATH>
 int launch_cluster(const PlanArgs& a, const MpcArgs* mpc, cudaStream_t st, int cluster) {
   const int R = (a.N + cluster - 1) / cluster;               // candidates per CTA, one per thread
-  // one rollout thread per candidate; a CTA with few rows still gets 8 warps: they share the sampling of every
-  // row (coop_sample_chunk) and speed up the selection
-  int threads = (R + 31) / 32 * 32;
-  if (R <= COOP_MAX_ROWS) threads = 256;
-  if (threads < 64) threads = 64;                            // the prologue wants a thread per horizon step
+  // One rollout thread per candidate, and as many sampling threads again (they sample the next iteration's noise
+  // under the rollouts); a CTA with few rows gets 8 warps per 32 rows: one rolls out, the others share the sampling
+  // of its rows (coop_sample_rows), and all of them share the selection.
+  const int chunks = (R + 31) / 32;
+  int threads = 2 * 32 * chunks;
+  if (R <= COOP_MAX_ROWS) threads = 32 * COOP_WARPS_PER_CHUNK * chunks;
+  if (threads > CLUSTER_MAX_THREADS) threads = CLUSTER_MAX_THREADS;
+  if (threads < 64 * chunks)
+    return fail(MBPO_EUNSUPPORTED, "cluster plan: %d candidates per CTA (max %d)", R, CLUSTER_MAX_THREADS / 2);
   const size_t smem = ClusterSmem<kH>::bytes(R, a.N, a.Np, a.K);
   const int sms = device_sm_count();
   long long clusters = sms / cluster;
@@ -60,11 +64,7 @@ int launch_cluster(const PlanArgs& a, const MpcArgs* mpc, cudaStream_t st, int c
     }
     e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return fail(MBPO_ECUDA, "cluster plan smem attr (%zu): %s", smem, cudaGetErrorString(e));
-    zero_row_value_kernel<MATH><<<(a.B + 127) / 128, 128, 0, st>>>(a.sys, kH, a.P, a.summarize, a.x0, a.B,
-                                                                  a.best_value_out);
-    const int rc = check_launch("zero_row_value_kernel");
-    if (rc != MBPO_OK) return rc;
-    e = cudaLaunchKernelEx(&cfg, kernel, a, R);
+    e = cudaLaunchKernelEx(&cfg, kernel, a, R);   // (the all-zero row is rolled out inside, beside iteration 0's sampling)
     if (e != cudaSuccess) return fail(MBPO_ECUDA, "icem_plan_cluster_kernel launch: %s", cudaGetErrorString(e));
     return check_launch("icem_plan_cluster_kernel");
   }

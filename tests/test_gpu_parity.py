@@ -772,6 +772,25 @@ def test_icemopt_closed_loop_kernel_matches_python_loop(mb, cuda_device, prng_mo
 # ---------------------------------------------------------------------------------------------
 # few problems: one problem per thread-block cluster (csrc/icem_cluster_kernels.cuh) -- same bits
 # ---------------------------------------------------------------------------------------------
+_SCRIBBLER = {}
+
+
+def _scribble_shared_memory(mb, cuda_device):
+    """Run an unrelated kernel that fills the shared memory of every SM (a fused plan over 444 problems).  A cluster
+    kernel launched right after one of its own launches finds its previous contents at the same offsets, which hides
+    a read of a stale or never-written location; after this call it does not."""
+    from mbpo_b200.systems import PendulumSystem
+    if "opt" not in _SCRIBBLER:
+        opt, _ = _cfg(mb, 30, dict(num_samples=512, num_particles=1, num_steps=1))
+        _SCRIBBLER["opt"] = opt
+        _SCRIBBLER["sp"] = PendulumSystem().reset(device=cuda_device).system_params
+        _SCRIBBLER["x0"] = _dev(_random_states(444, 77), cuda_device)
+        _SCRIBBLER["keys"] = _dev(_keys(444, seed=78), cuda_device)
+        _SCRIBBLER["seq"] = torch.zeros((444, 30, 1), device=cuda_device)
+    k = _SCRIBBLER
+    k["opt"]._plan_raw(k["x0"], k["keys"], k["seq"], k["sp"], cluster=1)
+
+
 @pytest.mark.parametrize("horizon,params,B", [
     (20, dict(), 1),                                                             # tests/test_icemopt.py's shape
     (30, dict(num_samples=512, num_particles=1), 3),                             # config 2's problem
@@ -779,6 +798,9 @@ def test_icemopt_closed_loop_kernel_matches_python_loop(mb, cuda_device, prng_mo
     (8, dict(num_samples=40, num_elites=7, num_steps=3, warm_start=False), 5),   # 5 candidates per CTA of 8
     (15, dict(num_samples=100, num_elites=20, num_steps=2, exponent=1.0), 2),    # ragged split, odd horizon
     (50, dict(num_samples=1024, num_particles=1, num_steps=2), 1),               # 256 candidates per CTA at C = 4
+    (20, dict(), 3),                 # config 1's problem: 500 + 15 candidates; at C = 4 the CTAs own 129 or 128 rows
+    (20, dict(num_samples=250, num_elites=25, elite_set_fraction=0.5, num_steps=4), 2),   # 13 kept elites: ragged virtual rows
+    (20, dict(num_samples=333, num_elites=40, num_particles=3, num_steps=3), 2),          # C * R > N at every C
 ])
 def test_cluster_plan_bit_identical(mb, cuda_device, prng_mode, horizon, params, B):
     """A problem spread over a cluster of 2 / 4 / 8 / 16 CTAs (keys, elite rows and refit columns exchanged through
@@ -797,11 +819,13 @@ def test_cluster_plan_bit_identical(mb, cuda_device, prng_mode, horizon, params,
             with pytest.raises(mb.MbpoUnsupported):
                 opt._plan_raw(x0, keys, seq, sp, cluster=c)
             continue
+        _scribble_shared_memory(mb, cuda_device)
         got = opt._plan_raw(x0, keys, seq, sp, trace=True, cluster=c)
         assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]), "cluster %d" % c
         assert torch.equal(got[2].view(torch.int32), ref[2].view(torch.int32))
         for name in ("actions", "values", "elite_idx", "mean", "std", "best_value"):
             assert torch.equal(got[3][name], ref[3][name]), "cluster %d: %s" % (c, name)
+    _scribble_shared_memory(mb, cuda_device)
     auto = opt._plan_raw(x0, keys, seq, sp)                                       # the library's own choice
     assert torch.equal(auto[0], ref[0]) and torch.equal(auto[1], ref[1])
 
@@ -816,7 +840,8 @@ def test_cluster_choice_and_closed_loop(mb, cuda_device, prng_mode):
     assert sizes[1] == 16 and sizes[8] == 8 and sizes[18] == 8 and sizes[19] == 4 and sizes[37] == 4
     assert sizes[64] == 2 and sizes[74] == 2 and sizes[75] in (0, 1) and sizes[4096] in (0, 1)
     one = cem.closed_loop(system_state.x_next, st, 40, cluster=1)
-    for c in (2, 8, 16, -1):
+    for c in (2, 4, 8, 16, -1):
+        _scribble_shared_memory(mb, cuda_device)
         got = cem.closed_loop(system_state.x_next, st, 40, cluster=c)
         for a, b in zip(one[:3], got[:3]):
             assert torch.equal(a, b), "cluster %d" % c
@@ -826,8 +851,10 @@ def test_cluster_choice_and_closed_loop(mb, cuda_device, prng_mode):
     x3 = _dev(_random_states(3, 311), cuda_device)
     st3 = cem.init(_dev(_keys(3, seed=312), cuda_device))
     a = cem.closed_loop(x3, st3, 5, cluster=1)
-    b = cem.closed_loop(x3, st3, 5, cluster=4)
-    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    for c in (2, 4, 8, 16):
+        _scribble_shared_memory(mb, cuda_device)
+        b = cem.closed_loop(x3, st3, 5, cluster=c)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]), "cluster %d" % c
 
 
 # ---------------------------------------------------------------------------------------------
