@@ -46,11 +46,8 @@ __device__ long long g_cluster_clocks[64];
 #define MBPO_CLK(i) do {} while (0)
 #endif
 
-// A CTA that owns at most this many rows samples them cooperatively (coop_sample_rows) and overlaps the sampling of
-// the next iteration's noise with the rollouts of this one.
-constexpr int COOP_MAX_ROWS = 96;
-// Threads of a cooperative CTA: per chunk of 32 rows one rollout warp and seven sampling warps, at most 512 threads
-// (128 registers each: the kernel holds a sampling and a rollout instance and spills below that).
+// Threads of a CTA: per chunk of 32 rows one rollout warp and up to seven sampling warps, at most 512 threads (128
+// registers each: the kernel holds a sampling and a rollout instance and spills below that).
 constexpr int COOP_WARPS_PER_CHUNK = 8;
 constexpr int CLUSTER_MAX_THREADS = 512;
 
@@ -106,9 +103,8 @@ struct ClusterCtaSmem {
   }
 };
 
-// Cooperative sampling of 32 rows by the whole CTA (lane = row, warp = share of the work): used when a CTA owns few
-// rows (R <= COOP_MAX_ROWS), where one thread per row would leave the plan waiting on a single thread's ~3,000
-// dependent instructions.  Every warp derives the row's keys (6 threefry blocks, redundantly -- the issue slots are
+// Cooperative sampling of 32 rows by several warps (lane = row, warp = share of the work): one thread per row would
+// leave the plan waiting on a single thread's ~3,000 dependent instructions.  Every warp derives the row's keys (6 threefry blocks, redundantly -- the issue slots are
 // idle anyway), then the 2 x tasks threefry-block + normal units of the two half spectra are dealt round-robin to
 // the warps, and after a barrier each warp evaluates its share of the DFT output groups.  Same device functions and
 // per-output operation order as colored_noise_row: same bits.
@@ -184,17 +180,16 @@ __device__ __forceinline__ void plan_problem_cluster(const PlanArgs& a, const Cl
 
   // ---- who does what.  The colored noise does not depend on mean / std either, so the CTA is split: the first
   // `chunks` warps own one candidate per thread and roll it out; the other warps sample the noise of iteration
-  // it + 1 meanwhile (into nz); only  clip(mean + noise * std)  (:190-191) waits for the refit.  Few rows
-  // (R <= COOP_MAX_ROWS): `sparts` sampling warps share each chunk of 32 rows (coop_sample_rows); more rows: one
-  // sampling thread per row.  Pass it = -1 samples iteration 0 and rolls out the all-zero row.
+  // it + 1 meanwhile (into nz); only  clip(mean + noise * std)  (:190-191) waits for the refit.  `sparts` sampling
+  // warps share each chunk of 32 rows (coop_sample_rows; with many rows per CTA sparts is 1: a sampling thread per
+  // row).  Pass it = -1 samples iteration 0 and rolls out the all-zero row.
   const int warp = tid >> 5, lane = tid & 31;
   const int chunks = (R + 31) >> 5;                        // rollout warps (32 rows each)
   const int warps = NT >> 5;
-  const bool coop = R <= COOP_MAX_ROWS;
   // One rollout warp (R <= 32): the warp that shares its scheduler (warp & 3 == 0) stays idle in the loop, so the
   // rollout chain -- the critical path -- issues alone.
   const bool quiet = MBPO_QUIET_SCHED && chunks == 1 && warps == 8;
-  const int sparts = quiet ? 6 : (warps - chunks) / chunks;   // coop: sampling warps per chunk (host: >= 1)
+  const int sparts = quiet ? 6 : (warps - chunks) / chunks;   // sampling warps per chunk of 32 rows (host: >= 1)
   const int swarps = chunks * sparts;
   const int n = rank * R + tid;             // the candidate this thread rolls out
   const bool mine = tid < R && n < N;
@@ -208,27 +203,22 @@ __device__ __forceinline__ void plan_problem_cluster(const PlanArgs& a, const Cl
     if (warp >= chunks) {
       // ---- sampling warps: the noise of iteration it + 1 -----------------------------------------------------
       if (it + 1 < a.S) {
-        if (coop) {
-          const int sw = quiet ? ((warp & 3) == 0 ? swarps : warp - 1 - (warp >> 2)) : warp - chunks;
-          if (sw < swarps) {
-            const Key2 srng = next_sampling_rng();
-            const int chunk = sw / sparts;
+        const int sw = quiet ? ((warp & 3) == 0 ? swarps : warp - 1 - (warp >> 2)) : warp - chunks;
+        if (sw < swarps) {
+          const Key2 srng = next_sampling_rng();
+          const int chunk = sw / sparts;
+          const int r = (chunk << 5) + lane;
+          const int nn = rank * R + r;
+          float* nrow = sm.nz + static_cast<size_t>(r < R ? r : 0) * HS;
+          if (sparts > 1) {
             const int count = swarps << 5;
-            const int r = (chunk << 5) + lane;
-            const int nn = rank * R + r;
-            float* nrow = sm.nz + static_cast<size_t>(r < R ? r : 0) * HS;
             coop_sample_rows<H, PRNG>(srng, N, nn, r < R && nn < N, sw - chunk * sparts, sparts, a.scale, nrow,
                                       [&](int t, float y) { nrow[t] = y; },
                                       [count] { asm volatile("bar.sync 1, %0;" ::"r"(count) : "memory"); });
-          }
-        } else {
-          const int r = tid - (chunks << 5);
-          const int nn = rank * R + r;
-          if (r < R && nn < N) {
-            const Key2 srng = next_sampling_rng();
+          } else if (r < R && nn < N) {
+            // a sampling thread per row: the unrolled single-thread routine beats the shared one run by one share
             const Key2 skey_n = split_at<PRNG>(srng, static_cast<uint32_t>(N + 1), static_cast<uint32_t>(nn + 1));
             const Key2 dim_key = split1<PRNG>(skey_n);
-            float* nrow = sm.nz + static_cast<size_t>(r) * HS;
             colored_noise_row<H, PRNG>(dim_key, a.scale, nrow, nullptr, [&](int t, float y) { nrow[t] = y; });
           }
         }
@@ -406,8 +396,7 @@ __device__ __forceinline__ void plan_problem_cluster(const PlanArgs& a, const Cl
 }
 
 // One cluster plans one problem at a time (cluster-stride over problems).  Launched with cluster dimension C along
-// x; best_value_out holds the zero-row objectives on entry (zero_row_value_kernel) when the CTAs own more than
-// COOP_MAX_ROWS rows, like the one-CTA kernel.
+// x (the all-zero row's objective is rolled out inside; best_value_out is output only).
 template <int H, int PRNG, int MATH>
 __global__ void __launch_bounds__(CLUSTER_MAX_THREADS, 1) icem_plan_cluster_kernel(const __grid_constant__ PlanArgs a, int R) {
   extern __shared__ __align__(16) uint32_t smem_u32[];

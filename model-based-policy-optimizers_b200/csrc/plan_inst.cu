@@ -30,12 +30,11 @@ int prepare_plan_kernel(Kernel kernel, size_t smem, int B, int* grid_out) {
 template <int PRNG, int MATH>
 int launch_cluster(const PlanArgs& a, const MpcArgs* mpc, cudaStream_t st, int cluster) {
   const int R = (a.N + cluster - 1) / cluster;               // candidates per CTA, one per thread
-  // One rollout thread per candidate, and as many sampling threads again (they sample the next iteration's noise
-  // under the rollouts); a CTA with few rows gets 8 warps per 32 rows: one rolls out, the others share the sampling
-  // of its rows (coop_sample_rows), and all of them share the selection.
+  // Per chunk of 32 candidates one rollout warp (a thread per candidate) and up to seven sampling warps, which share
+  // the sampling of the chunk's rows for the next iteration under the rollouts (coop_sample_rows); all warps share the
+  // selection.  At least one sampling warp per chunk.
   const int chunks = (R + 31) / 32;
-  int threads = 2 * 32 * chunks;
-  if (R <= COOP_MAX_ROWS) threads = 32 * COOP_WARPS_PER_CHUNK * chunks;
+  int threads = 32 * COOP_WARPS_PER_CHUNK * chunks;
   if (threads > CLUSTER_MAX_THREADS) threads = CLUSTER_MAX_THREADS;
   if (threads < 64 * chunks)
     return fail(MBPO_EUNSUPPORTED, "cluster plan: %d candidates per CTA (max %d)", R, CLUSTER_MAX_THREADS / 2);
