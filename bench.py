@@ -698,7 +698,9 @@ def run_ensemble(args):
                     "h2d_bytes_per_step": int(x0_host.numel() * 4), "d2h_bytes_per_step": int(act_host.numel() * 4),
                     "api": "iCemTO.act with MLPEnsembleSystem (staged plan: sample -> ensemble rollout -> refit)"},
             "gpu_launches": steps * (1 + 3 * ENS_S + 1),
-            "roofline": {"bound": "tensor", "kernel": "ensemble_rollout_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "tensor",
+                         "kernel": "ensemble_rollout_pp_kernel" if rows > 18944 else "ensemble_rollout_kernel",
+                         "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": ncu_traffic("config4_ensemble_icem") if world == 1 else None,
                          "kernel_ms": k_ms, "flops_per_launch": flops,
@@ -812,10 +814,16 @@ def run_closed_loop(args):
                 "h2d_bytes_per_step": 12, "d2h_bytes_per_step": 4 * MPC_T,
                 "api": "iCemTO.closed_loop(x0 from pinned host, 200 steps) -> rewards[200] to pinned host"},
         "gpu_launches": steps,
-        "roofline": {"bound": "issue", "kernel": "icem_mpc_pendulum_kernel", "achieved": None,
-                     "peak": 148 * 4 * 32 * sm_max * 1e6 / 1e12, "unit": "T lane-instr/s", "frac": None, "traffic": None,
-                     "note": "one problem = one 8-CTA thread-block cluster (8 of 148 SMs): the episode is latency-bound "
-                             "by construction; throughput configurations are config 2 / config 5"},
+        "roofline": {"bound": "issue", "kernel": "icem_mpc_cluster_kernel",
+                     "achieved": MPC_T * tr_plan_written / 10.0 / (ms * 1e-3) * ALGORITHMIC_LANE_INSTR_PER_TRANSITION / 1e12,
+                     "peak": 148 * 4 * 32 * sm_max * 1e6 / 1e12, "unit": "T lane-instr/s",
+                     "frac": MPC_T * tr_plan_written / 10.0 / (ms * 1e-3) * ALGORITHMIC_LANE_INSTR_PER_TRANSITION / 1e12
+                             / (148 * 4 * 32 * sm_max * 1e6 / 1e12),
+                     "traffic": None,
+                     "note": "one problem = one 16-CTA thread-block cluster (16 of 148 SMs) and a chain of 200 x 5 "
+                             "dependent iterations: the episode is latency-bound by construction (distinct "
+                             "transitions counted: the 10 particles of the deterministic pendulum are one rollout); "
+                             "throughput configurations are config 2 / config 5"},
         "cpu_baseline": None}, GUARD)
 
 
