@@ -211,10 +211,13 @@ int mbpo_icem_plan(const MbpoIcemCfg* cfg_host, const void* sys_params_host,
                    float* best_value_out /*[B]*/, uint32_t* key_out /*[B,2]*/,
                    const MbpoIcemTrace* trace_host /*NULL = no dumps*/, void* stream);
 /* The same plan with an explicit thread-block-cluster size: few problems leave most of the 148 SMs idle when each
- * gets one CTA, so a problem can be spread over a cluster of 2, 4 or 8 CTAs whose elite exchange runs through
- * distributed shared memory (csrc/icem_cluster_kernels.cuh).  Results are bit-identical for every cluster size.
- * cluster_size: -1 = the library's choice for (B, num_samples) -- what mbpo_icem_plan uses; 1 = one CTA per
- * problem; 2, 4, 8.  mbpo_icem_plan_cluster_size returns that choice (0 or 1: no cluster).
+ * gets one CTA, so a problem can be spread over a cluster of 2, 4, 8 or 16 CTAs (16 is a non-portable size: devices
+ * that refuse it return MBPO_ECUDA for an explicit 16; the library's own choice falls back to 8, then to one CTA)
+ * whose key / elite exchange runs through distributed shared memory and whose spare warps sample the next
+ * iteration's noise under the rollouts (csrc/icem_cluster_kernels.cuh).  Results are bit-identical for every
+ * cluster size.  cluster_size: -1 = the library's choice for (B, num_samples) -- what mbpo_icem_plan uses; 1 = one
+ * CTA per problem; 2, 4, 8, 16 (at most 256 candidates per CTA).  mbpo_icem_plan_cluster_size returns that choice
+ * (0 or 1: no cluster).
  * Reference: icem_optimizer.py:134-252 at B = 1 is tests/test_icemopt.py's shape. */
 int mbpo_icem_plan_clustered(const MbpoIcemCfg* cfg_host, const void* sys_params_host, const float* x0,
                              const uint32_t* key_in, const float* best_seq_in, int B, float* best_seq_out,

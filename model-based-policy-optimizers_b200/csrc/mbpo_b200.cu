@@ -242,7 +242,12 @@ int run_plan(const MbpoIcemCfg* c, const void* sys_params_host, const float* x0,
   int rc2 = dispatch(cluster);
   if (rc2 == MBPO_ECUDA && cluster_size < 0 && cluster == 16) {
     cudaGetLastError();                 // the device refused the non-portable size the library picked: use 8
+    cluster = 8;
     rc2 = dispatch(8);
+  }
+  if (rc2 == MBPO_ECUDA && cluster_size < 0 && cluster > 1) {
+    cudaGetLastError();                 // no cluster of the library's own choice can be placed (e.g. a partitioned
+    rc2 = dispatch(1);                  // device): the one-CTA kernel gives the same bits
   }
   return rc2;
 }
