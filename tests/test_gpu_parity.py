@@ -830,6 +830,42 @@ def test_cluster_plan_bit_identical(mb, cuda_device, prng_mode, horizon, params,
     assert torch.equal(auto[0], ref[0]) and torch.equal(auto[1], ref[1])
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_cluster_plan_random_shapes(mb, cuda_device, prng_mode, seed):
+    """Random populations / elite counts / horizons / batch sizes: every cluster size the library accepts gives the
+    one-CTA kernel's final state and per-iteration dumps (ragged row counts, partial warps, kept elites that do not
+    divide by the cluster size, C x R > N)."""
+    from mbpo_b200.systems import PendulumSystem
+    rng = np.random.default_rng(9000 + seed)
+    horizon = int(rng.choice([5, 8, 15, 20, 30, 50]))
+    N = int(rng.integers(64, 900))
+    K = int(rng.integers(4, max(5, N // 6)))
+    params = dict(num_samples=N, num_elites=K, num_steps=int(rng.integers(1, 5)),
+                  elite_set_fraction=float(rng.choice([0.0, 0.1, 0.3, 0.5])), alpha=float(rng.choice([0.0, 0.2])),
+                  exponent=float(rng.choice([0.0, 1.0, 2.0])), num_particles=int(rng.choice([1, 4])),
+                  warm_start=bool(rng.integers(0, 2)))
+    B = int(rng.integers(1, 5))
+    opt, cfg = _cfg(mb, horizon, params)
+    sp = PendulumSystem().reset(device=cuda_device).system_params
+    x0 = _dev(_random_states(B, 9100 + seed), cuda_device)
+    keys = _dev(_keys(B, seed=9200 + seed), cuda_device)
+    seq = _dev(rng.uniform(-1, 1, (B, horizon, 1)).astype(np.float32), cuda_device)
+    ref = opt._plan_raw(x0, keys, seq, sp, trace=True, cluster=1)
+    ran = 0
+    for c in (2, 4, 8, 16):
+        _scribble_shared_memory(mb, cuda_device)
+        try:
+            got = opt._plan_raw(x0, keys, seq, sp, trace=True, cluster=c)
+        except mb.MbpoUnsupported:
+            continue                                    # more than 256 candidates per CTA, or too few candidates
+        ran += 1
+        assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]), "cluster %d %r" % (c, params)
+        assert torch.equal(got[2].view(torch.int32), ref[2].view(torch.int32))
+        for name in ("actions", "values", "elite_idx", "mean", "std", "best_value"):
+            assert torch.equal(got[3][name], ref[3][name]), "cluster %d: %s %r" % (c, name, params)
+    assert ran >= 2
+
+
 def test_cluster_choice_and_closed_loop(mb, cuda_device, prng_mode):
     """The library spreads few problems over clusters by itself (B = 1 -> 16 CTAs, B = 8 -> 8) and the closed loop
     (tests/test_icemopt.py:19-32) on a cluster reproduces the one-CTA closed loop bit for bit."""
