@@ -225,7 +225,7 @@ int run_plan(const MbpoIcemCfg* c, const void* sys_params_host, const float* x0,
                  "plan: cluster_size %d (use -1, 1, 2, 4, 8 or 16)", cluster);
     const int R = (a.N + cluster - 1) / cluster;
     if (R > 256) return fail(MBPO_EUNSUPPORTED, "plan: %d candidates per CTA of a %d-cluster (at most 256)", R, cluster);
-    if (R + (a.Np + cluster - 1) / cluster > 298 || a.N + a.Np < 36)   // the cluster kernel's use of the selection scratch
+    if (a.N + a.Np < 36)   // the cluster kernel keeps its elite list in the selection scratch (words 299 .. 300 + K)
       return fail(MBPO_EUNSUPPORTED, "plan: population (%d + %d) outside what a %d-cluster handles", a.N, a.Np, cluster);
   }
   const auto dispatch = [&](int cl) -> int {

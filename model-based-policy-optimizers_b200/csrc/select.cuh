@@ -36,8 +36,12 @@ struct RefitScalars {
 };
 
 // Scratch words the selection needs besides keys / elite_idx / sel_idx:
-// histogram [256] + misc [8] + selected keys [K] + boundary-bin candidates [M].
-__host__ __device__ constexpr int select_scratch_words(int K, int M) { return 264 + K + M; }
+// histogram [256 bins, one pad word per 8 bins = 288] + misc [8] + selected keys [K] + boundary-bin candidates [M].
+// The pad makes "lane l reads bins 8 l .. 8 l + 7" (step 2) hit 32 different banks instead of 4.
+constexpr int SELECT_HIST_WORDS = 288;
+constexpr int SELECT_HEAD_WORDS = SELECT_HIST_WORDS + 8;
+__host__ __device__ constexpr int select_scratch_words(int K, int M) { return SELECT_HEAD_WORDS + K + M; }
+__device__ __forceinline__ uint32_t select_hist_slot(uint32_t bin) { return bin + (bin >> 3); }
 
 // keys      : shared, uint32[M]  total-order keys of the objective values
 // elite_idx : shared, int32[K]   out: argsort(values)[-K:]  (ascending rank)
@@ -61,14 +65,14 @@ __device__ __forceinline__ void cta_select(const RefitScalars rs, const uint32_t
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int M = rs.M, K = rs.K;
-  uint32_t* hist = scratch;              // [256]
-  uint32_t* misc = scratch + 256;        // [0] or, [1] and, [2] selection cursor, [3] candidate cursor
-  uint32_t* sel_key = scratch + 264;     // [K]
-  int* cand = reinterpret_cast<int*>(scratch + 264 + K);  // [M]
+  uint32_t* hist = scratch;                           // [288] padded bins (select_hist_slot)
+  uint32_t* misc = scratch + SELECT_HIST_WORDS;       // [0] or, [1] and, [2] selection cursor, [3] candidate cursor
+  uint32_t* sel_key = scratch + SELECT_HEAD_WORDS;    // [K]
+  int* cand = reinterpret_cast<int*>(scratch + SELECT_HEAD_WORDS + K);  // [M]
 
   MBPO_SEL_CLK(0);
   // ---- 0. reset; OR / AND of all keys (which bits differ at all) -----------------------------
-  for (int i = tid; i < 264; i += NT) scratch[i] = (i == 257) ? 0xFFFFFFFFu : 0u;
+  for (int i = tid; i < SELECT_HEAD_WORDS; i += NT) scratch[i] = (i == SELECT_HIST_WORDS + 1) ? 0xFFFFFFFFu : 0u;
   __syncthreads();
   {
     uint32_t o = 0u, a = 0xFFFFFFFFu;
@@ -91,7 +95,7 @@ __device__ __forceinline__ void cta_select(const RefitScalars rs, const uint32_t
 
   MBPO_SEL_CLK(1);
   // ---- 1. histogram of the leading digit ---------------------------------------------------
-  for (int i = tid; i < M; i += NT) atomicAdd(&hist[(keys[i] >> shift) & 255u], 1u);
+  for (int i = tid; i < M; i += NT) atomicAdd(&hist[select_hist_slot((keys[i] >> shift) & 255u)], 1u);
   __syncthreads();
 
   MBPO_SEL_CLK(2);
@@ -102,7 +106,7 @@ __device__ __forceinline__ void cta_select(const RefitScalars rs, const uint32_t
     uint32_t s = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      h8[j] = hist[lane * 8 + j];
+      h8[j] = hist[lane * 9 + j];                    // bins 8 lane .. 8 lane + 7 in the padded layout
       s += h8[j];
     }
     uint32_t suf = s;  // inclusive suffix sum over lanes (lanes >= mine)
@@ -149,17 +153,25 @@ __device__ __forceinline__ void cta_select(const RefitScalars rs, const uint32_t
 
   MBPO_SEL_CLK(4);
   // ---- 4. exact choice inside the boundary bin: the `need` largest (key, index) pairs ---------
+  // (four lanes share a candidate's comparisons; the trip counts are uniform so that every lane reaches the shuffles)
   const int nc = static_cast<int>(misc[3]);
-  for (int e = tid; e < nc; e += NT) {
-    const int ie = cand[e];
-    const uint32_t ke = keys[ie];
-    int larger = 0;
-    for (int f = 0; f < nc; ++f) {
-      const int jf = cand[f];
-      const uint32_t kf = keys[jf];
-      larger += (kf > ke || (kf == ke && jf > ie)) ? 1 : 0;
+  for (int base = 0; base < 4 * nc; base += NT) {
+    const int w = base + tid;
+    const int e = w >> 2, g = w & 3;
+    int larger = 0, ie = 0;
+    uint32_t ke = 0u;
+    if (e < nc) {
+      ie = cand[e];
+      ke = keys[ie];
+      for (int f = g; f < nc; f += 4) {
+        const int jf = cand[f];
+        const uint32_t kf = keys[jf];
+        larger += (kf > ke || (kf == ke && jf > ie)) ? 1 : 0;
+      }
     }
-    if (larger < need) {
+    larger += __shfl_xor_sync(full, larger, 1);
+    larger += __shfl_xor_sync(full, larger, 2);
+    if (e < nc && g == 0 && larger < need) {
       const uint32_t pos = atomicAdd(&misc[2], 1u);
       sel_idx[pos] = ie;
       sel_key[pos] = ke;
@@ -168,17 +180,23 @@ __device__ __forceinline__ void cta_select(const RefitScalars rs, const uint32_t
   __syncthreads();
 
   MBPO_SEL_CLK(5);
-  // ---- 5. rank the K elites by (key, index) ascending --------------------------------------
-  for (int e = tid; e < K; e += NT) {
-    const int ie = sel_idx[e];
-    const uint32_t ke = sel_key[e];
-    int rank = 0;
-    for (int f = 0; f < K; ++f) {
-      const int jf = sel_idx[f];
-      const uint32_t kf = sel_key[f];
-      rank += (kf < ke || (kf == ke && jf < ie)) ? 1 : 0;
+  // ---- 5. rank the K elites by (key, index) ascending (four lanes per elite) ------------------
+  for (int base = 0; base < 4 * K; base += NT) {
+    const int w = base + tid;
+    const int e = w >> 2, g = w & 3;
+    int rank = 0, ie = 0;
+    if (e < K) {
+      ie = sel_idx[e];
+      const uint32_t ke = sel_key[e];
+      for (int f = g; f < K; f += 4) {
+        const int jf = sel_idx[f];
+        const uint32_t kf = sel_key[f];
+        rank += (kf < ke || (kf == ke && jf < ie)) ? 1 : 0;
+      }
     }
-    elite_idx[rank] = ie;
+    rank += __shfl_xor_sync(full, rank, 1);
+    rank += __shfl_xor_sync(full, rank, 2);
+    if (e < K && g == 0) elite_idx[rank] = ie;
   }
   __syncthreads();
   MBPO_SEL_CLK(6);

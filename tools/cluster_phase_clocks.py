@@ -24,3 +24,9 @@ print("selection detail: entry", x[0] - c[5], "compare", x[1] - x[0], "finalize"
 names = ["0 key split", "1 sampling (thread 0's share)", "2 rollout", "3 push keys", "4 cluster.sync", "5 selection",
          "6 push elites", "7 cluster.sync", "8 refit"]
 print(json.dumps({"cluster": C, "cycles": {names[i]: c[i + 1] - c[i] for i in range(9)}, "iteration": c[9] - c[0]}))
+sbuf = (ctypes.c_longlong * 16)()
+lib.mbpo_debug_select_clocks.argtypes = [ctypes.c_void_p]; lib.mbpo_debug_select_clocks(sbuf)
+sc = list(sbuf)[:7]
+if sc[6] > sc[0] > 0:
+    print(json.dumps({"cta_select phases (last call)": {n: sc[i + 1] - sc[i] for i, n in enumerate(
+        ["0 reset + or/and", "1 histogram", "2 boundary bin", "3 classify", "4 boundary exact", "5 rank elites"])}}))
