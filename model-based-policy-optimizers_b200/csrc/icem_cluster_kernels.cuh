@@ -223,9 +223,9 @@ __device__ __forceinline__ void plan_problem_cluster(const PlanArgs& a, const Cl
           }
         }
       }
-      MBPO_CLK(2);
     } else if (it < 0 ? tid == 0 : mine) {
       // ---- rollout of this thread's row; the key goes to every CTA of the cluster -----------------------------
+      MBPO_CLK(2);
       const float ret = rollout_return_th<MATH, true>(pc, x_th, x_w, H, [&](int t) { return row[t]; });
       MBPO_CLK(3);
       const float val = summarize_particles(ret, a.P, a.summarize);

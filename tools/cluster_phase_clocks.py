@@ -20,9 +20,9 @@ lib = _lib.lib
 buf = (ctypes.c_longlong * 64)()
 lib.mbpo_debug_cluster_clocks.argtypes = [ctypes.c_void_p]; lib.mbpo_debug_cluster_clocks(buf)
 c = list(buf)[:10]; x = list(buf)[10:13]
-print("selection detail: entry", x[0] - c[5], "compare", x[1] - x[0], "finalize", x[2] - x[1], "barrier", c[6] - x[2])
-names = ["0 key split", "1 sampling (thread 0's share)", "2 rollout", "3 push keys", "4 cluster.sync", "5 selection",
-         "6 push elites", "7 cluster.sync", "8 refit"]
+if x[2] > x[0] > c[5]: print("ranked selection detail: entry", x[0] - c[5], "compare", x[1] - x[0], "finalize", x[2] - x[1], "barrier", c[6] - x[2])
+names = ["0 -", "1 -", "2 rollout", "3 push keys", "4 cluster.sync", "5 selection",
+         "6 push elites", "7 cluster.sync", "8 refit + apply"]
 print(json.dumps({"cluster": C, "cycles": {names[i]: c[i + 1] - c[i] for i in range(9)}, "iteration": c[9] - c[0]}))
 sbuf = (ctypes.c_longlong * 16)()
 lib.mbpo_debug_select_clocks.argtypes = [ctypes.c_void_p]; lib.mbpo_debug_select_clocks(sbuf)
