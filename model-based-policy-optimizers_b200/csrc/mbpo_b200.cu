@@ -8,6 +8,9 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <tuple>
 
 #include "../../include/mbpo_b200.h"
 #include "env_kernels.cuh"
@@ -181,6 +184,38 @@ int plan_fusable(const MbpoIcemCfg* c, bool set_error) {
   return why == nullptr;
 }
 
+// Capacities of cluster sizes 16, 8, 4, 2 for a configuration on the current device, cached: the occupancy queries
+// cost more than a plan at B = 1.
+struct ClusterCaps { int cap[4]; };
+ClusterCaps cluster_caps(const MbpoIcemCfg* c, bool mpc) {
+  static std::mutex mu;
+  static std::map<std::tuple<int, int, int, int, int, int, int, int>, ClusterCaps> cache;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const auto key = std::make_tuple(dev, c->horizon, c->prng_mode, c->math_mode, mpc ? 1 : 0, c->num_samples,
+                                   c->num_prev_elites, c->num_elites);
+  std::lock_guard<std::mutex> lock(mu);
+  const auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  ClusterCaps caps = {{0, 0, 0, 0}};
+  for (int i = 0, cl = 16; i < 4; ++i, cl >>= 1) {
+    const int R = (c->num_samples + cl - 1) / cl;
+    if (R < 32 || R > 256) continue;
+    switch (c->horizon) {
+#define X(h)                                                                                                      \
+  case h:                                                                                                         \
+    caps.cap[i] = plan_cluster_capacity<h>(c->prng_mode, c->math_mode, mpc, c->num_samples, c->num_prev_elites, \
+                                           c->num_elites, cl);                                                    \
+    break;
+      MBPO_FOR_EACH_H(X)
+#undef X
+      default: break;
+    }
+  }
+  cache[key] = caps;
+  return caps;
+}
+
 int run_plan(const MbpoIcemCfg* c, const void* sys_params_host, const float* x0, const uint32_t* key_in,
              const float* best_seq_in, int B, float* best_seq_out, float* best_value_out, uint32_t* key_out,
              const MbpoIcemTrace* trace, const MpcArgs* mpc, int cluster_size, void* stream) {
@@ -215,7 +250,13 @@ int run_plan(const MbpoIcemCfg* c, const void* sys_params_host, const float* x0,
                  best_seq_out, best_value_out, key_out, trace);
   // few problems: spread each over a thread-block cluster (same bits; icem_cluster_kernels.cuh)
   int cluster = cluster_size;
-  if (cluster < 0) cluster = plan_cluster_size(B, a.N);
+  if (cluster < 0) {
+    cluster = 0;
+    if (horizon_supported(c->horizon) && a.N + a.Np >= 36) {
+      const ClusterCaps caps = cluster_caps(c, mpc != nullptr);
+      cluster = plan_cluster_choice(B, a.N, caps.cap);
+    }
+  }
   if (!horizon_supported(c->horizon)) {
     if (cluster_size > 1) return fail(MBPO_EUNSUPPORTED, "plan: clusters exist for the unrolled horizons (" MBPO_H_LIST_STR ")");
     return plan_entry_rt(c->prng_mode, c->math_mode, a, mpc, as_stream(stream));
@@ -625,9 +666,24 @@ int mbpo_icem_plan_clustered(const MbpoIcemCfg* cfg, const void* sys_params_host
 
 int mbpo_icem_plan_cluster_size(const MbpoIcemCfg* cfg, int B) {
   if (validate_cfg(cfg) != MBPO_OK || !plan_fusable(cfg, false) || !horizon_supported(cfg->horizon) ||
+      general_system_kind(cfg->system_kind) || cfg->num_samples + cfg->num_prev_elites < 36)
+    return 0;
+  const ClusterCaps caps = cluster_caps(cfg, false);
+  return plan_cluster_choice(B, cfg->num_samples, caps.cap);
+}
+
+int mbpo_icem_plan_cluster_capacity(const MbpoIcemCfg* cfg, int cluster_size) {
+  if (validate_cfg(cfg) != MBPO_OK || !plan_fusable(cfg, false) || !horizon_supported(cfg->horizon) ||
       general_system_kind(cfg->system_kind))
     return 0;
-  return plan_cluster_size(B, cfg->num_samples);
+  const ClusterCaps caps = cluster_caps(cfg, false);
+  switch (cluster_size) {
+    case 16: return caps.cap[0];
+    case 8: return caps.cap[1];
+    case 4: return caps.cap[2];
+    case 2: return caps.cap[3];
+    default: return 0;
+  }
 }
 
 // Staged plan workspace layout (floats unless noted), all [B, ...]:

@@ -21,16 +21,22 @@ int plan_entry_rt(int prng_mode, int math_mode, const PlanArgs& a, const MpcArgs
 template <int H>
 int general_plan_entry(int system_kind, int prng_mode, const PlanArgs& a, cudaStream_t st);
 
-// Cluster size the library picks for B problems of N candidates (0: one CTA per problem).
-inline int plan_cluster_size(int B, int N) {
-  const int sms = device_sm_count();
-  if (B <= 0 || B >= sms) return 0;
-  // one or two problems: the non-portable 16 (32 candidates per CTA at N = 512: one cooperative sampling chunk);
-  // otherwise the largest portable size that still gives every cluster its own SMs
-  int c = (B <= 2 && (N + 15) / 16 >= 32) ? 16 : 8;
-  while (c > 1 && (B * c > sms || (N + c - 1) / c < 32)) c >>= 1;
-  if (c <= 1 || (N + c - 1) / c > 256) return 0;
-  return c;
+// How many clusters of `cluster` CTAs of the cluster plan (mpc: of the closed loop) run at once on the current device
+// (cudaOccupancyMaxActiveClusters: the GPCs, not the SM count, decide -- 7 of 16, 15 of 8, 32 of 4, 74 of 2 on a
+// B200); 0 if the size cannot be launched.
+template <int H>
+int plan_cluster_capacity(int prng_mode, int math_mode, bool mpc, int N, int Np, int K, int cluster);
+
+// Cluster size for B problems given the capacities of sizes 16, 8, 4, 2 (cap[0..3]): the largest size whose clusters
+// all run at once (a second round of clusters costs a whole plan) with 32 .. 256 candidates per CTA; 0: one CTA per
+// problem.
+inline int plan_cluster_choice(int B, int N, const int cap[4]) {
+  if (B <= 0) return 0;
+  for (int i = 0, c = 16; i < 4; ++i, c >>= 1) {
+    const int R = (N + c - 1) / c;
+    if (R >= 32 && R <= 256 && B <= cap[i]) return c;
+  }
+  return 0;
 }
 
 // vmap(powerlaw_psd_gaussian) over M keys.

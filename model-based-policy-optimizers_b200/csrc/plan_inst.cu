@@ -26,19 +26,77 @@ int prepare_plan_kernel(Kernel kernel, size_t smem, int B, int* grid_out) {
   return MBPO_OK;
 }
 
-// One problem per cluster of `cluster` CTAs (icem_cluster_kernels.cuh).
-template <int PRNG, int MATH>
-int launch_cluster(const PlanArgs& a, const MpcArgs* mpc, cudaStream_t st, int cluster) {
-  const int R = (a.N + cluster - 1) / cluster;               // candidates per CTA, one per thread
+// Block size of a cluster CTA that owns R candidates (0: more than the kernel takes).
+int cluster_threads(int R) {
   // Per chunk of 32 candidates one rollout warp (a thread per candidate) and up to seven sampling warps, which share
   // the sampling of the chunk's rows for the next iteration under the rollouts (coop_sample_rows); all warps share the
   // selection.  At least one sampling warp per chunk.
   const int chunks = (R + 31) / 32;
   int threads = 32 * COOP_WARPS_PER_CHUNK * chunks;
   if (threads > CLUSTER_MAX_THREADS) threads = CLUSTER_MAX_THREADS;
-  if (threads < 64 * chunks)
+  return threads < 64 * chunks ? 0 : threads;
+}
+
+// A cluster plan is a latency path: two of its CTAs on one SM would share the issue slots of the rollout chain
+// (measured at 16 CTAs per cluster: 48 -> 59 us).  Asking for more than half an SM's shared memory keeps every CTA
+// on an SM of its own, and makes the occupancy answer (cluster_capacity) count exactly those placements.
+size_t cluster_smem_alloc(size_t smem) {
+  const size_t half_sm = 117 * 1024;
+  return smem > half_sm ? smem : half_sm;
+}
+
+template <typename Kernel>
+cudaError_t prepare_cluster_kernel(Kernel kernel, int cluster, size_t smem) {
+  if (cluster > 8) {
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+}
+
+template <int PRNG, int MATH>
+int cluster_capacity(bool mpc, int N, int Np, int K, int cluster) {
+  const int R = (N + cluster - 1) / cluster;
+  const int threads = cluster_threads(R);
+  if (threads == 0) return 0;
+  const size_t smem = cluster_smem_alloc(ClusterSmem<kH>::bytes(R, N, Np, K));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(cluster), 1, 1);
+  cfg.blockDim = dim3(static_cast<unsigned>(threads), 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(cluster);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  cudaError_t e;
+  if (mpc) {
+    auto kernel = icem_mpc_cluster_kernel<kH, PRNG, MATH>;
+    e = prepare_cluster_kernel(kernel, cluster, smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, kernel, &cfg);
+  } else {
+    auto kernel = icem_plan_cluster_kernel<kH, PRNG, MATH>;
+    e = prepare_cluster_kernel(kernel, cluster, smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, kernel, &cfg);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+// One problem per cluster of `cluster` CTAs (icem_cluster_kernels.cuh).
+template <int PRNG, int MATH>
+int launch_cluster(const PlanArgs& a, const MpcArgs* mpc, cudaStream_t st, int cluster) {
+  const int R = (a.N + cluster - 1) / cluster;               // candidates per CTA, one per thread
+  const int threads = cluster_threads(R);
+  if (threads == 0)
     return fail(MBPO_EUNSUPPORTED, "cluster plan: %d candidates per CTA (max %d)", R, CLUSTER_MAX_THREADS / 2);
-  const size_t smem = ClusterSmem<kH>::bytes(R, a.N, a.Np, a.K);
+  const size_t smem = cluster_smem_alloc(ClusterSmem<kH>::bytes(R, a.N, a.Np, a.K));
   const int sms = device_sm_count();
   long long clusters = sms / cluster;
   if (clusters > a.B) clusters = a.B;
@@ -57,23 +115,17 @@ int launch_cluster(const PlanArgs& a, const MpcArgs* mpc, cudaStream_t st, int c
   cudaError_t e;
   if (mpc == nullptr) {
     auto kernel = icem_plan_cluster_kernel<kH, PRNG, MATH>;
-    if (cluster > 8) {
-      e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-      if (e != cudaSuccess) return fail(MBPO_ECUDA, "cluster plan: non-portable cluster size: %s", cudaGetErrorString(e));
-    }
-    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return fail(MBPO_ECUDA, "cluster plan smem attr (%zu): %s", smem, cudaGetErrorString(e));
+    e = prepare_cluster_kernel(kernel, cluster, smem);
+    if (e != cudaSuccess)
+      return fail(MBPO_ECUDA, "cluster plan attributes (cluster %d, smem %zu): %s", cluster, smem, cudaGetErrorString(e));
     e = cudaLaunchKernelEx(&cfg, kernel, a, R);   // (the all-zero row is rolled out inside, beside iteration 0's sampling)
     if (e != cudaSuccess) return fail(MBPO_ECUDA, "icem_plan_cluster_kernel launch: %s", cudaGetErrorString(e));
     return check_launch("icem_plan_cluster_kernel");
   }
   auto kernel = icem_mpc_cluster_kernel<kH, PRNG, MATH>;
-  if (cluster > 8) {
-    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (e != cudaSuccess) return fail(MBPO_ECUDA, "cluster mpc: non-portable cluster size: %s", cudaGetErrorString(e));
-  }
-  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  if (e != cudaSuccess) return fail(MBPO_ECUDA, "cluster mpc smem attr (%zu): %s", smem, cudaGetErrorString(e));
+  e = prepare_cluster_kernel(kernel, cluster, smem);
+  if (e != cudaSuccess)
+    return fail(MBPO_ECUDA, "cluster mpc attributes (cluster %d, smem %zu): %s", cluster, smem, cudaGetErrorString(e));
   e = cudaLaunchKernelEx(&cfg, kernel, a, *mpc, R);
   if (e != cudaSuccess) return fail(MBPO_ECUDA, "icem_mpc_cluster_kernel launch: %s", cudaGetErrorString(e));
   return check_launch("icem_mpc_cluster_kernel");
@@ -121,6 +173,16 @@ int plan_entry<MBPO_INST_H>(int prng_mode, int math_mode, const PlanArgs& a, con
     case 1: return launch<0, 1>(a, mpc, st);
     case 2: return launch<1, 0>(a, mpc, st);
     default: return launch<1, 1>(a, mpc, st);
+  }
+}
+
+template <>
+int plan_cluster_capacity<MBPO_INST_H>(int prng_mode, int math_mode, bool mpc, int N, int Np, int K, int cluster) {
+  switch (prng_mode * 2 + math_mode) {
+    case 0: return cluster_capacity<0, 0>(mpc, N, Np, K, cluster);
+    case 1: return cluster_capacity<0, 1>(mpc, N, Np, K, cluster);
+    case 2: return cluster_capacity<1, 0>(mpc, N, Np, K, cluster);
+    default: return cluster_capacity<1, 1>(mpc, N, Np, K, cluster);
   }
 }
 

@@ -129,6 +129,7 @@ SIGNATURES = {
     "mbpo_icem_plan_clustered": (_I, [C.POINTER(IcemCfgC), _P, _P, _P, _P, _I, _P, _P, _P, C.POINTER(IcemTraceC), _I,
                                       _P]),
     "mbpo_icem_plan_cluster_size": (_I, [C.POINTER(IcemCfgC), _I]),
+    "mbpo_icem_plan_cluster_capacity": (_I, [C.POINTER(IcemCfgC), _I]),
     "mbpo_icem_plan_is_fused": (_I, [C.POINTER(IcemCfgC)]),
     "mbpo_icem_workspace_bytes": (_SZ, [C.POINTER(IcemCfgC), _I]),
     "mbpo_icem_plan_staged": (_I, [C.POINTER(IcemCfgC), _P, _P, _P, _P, _I, _P, _P, _P, _P, _SZ, _P]),

@@ -867,14 +867,25 @@ def test_cluster_plan_random_shapes(mb, cuda_device, prng_mode, seed):
 
 
 def test_cluster_choice_and_closed_loop(mb, cuda_device, prng_mode):
-    """The library spreads few problems over clusters by itself (B = 1 -> 16 CTAs, B = 8 -> 8) and the closed loop
+    """The library spreads few problems over clusters by itself (B = 1 -> 16 CTAs, ...) and the closed loop
     (tests/test_icemopt.py:19-32) on a cluster reproduces the one-CTA closed loop bit for bit."""
     L = mb._lib
     system, system_state, cem, st = _icemopt_setup(mb, cuda_device)
     cfg = cem._cfg()
-    sizes = {B: L.lib.mbpo_icem_plan_cluster_size(L.C.byref(cfg), B) for B in (1, 8, 18, 19, 37, 64, 74, 75, 148, 4096)}
-    assert sizes[1] == 16 and sizes[8] == 8 and sizes[18] == 8 and sizes[19] == 4 and sizes[37] == 4
-    assert sizes[64] == 2 and sizes[74] == 2 and sizes[75] in (0, 1) and sizes[4096] in (0, 1)
+    # the choice: the largest cluster size whose clusters all run at once (the device's own occupancy answer: the GPCs
+    # decide, not the SM count) with 32 .. 256 candidates per CTA
+    cap = {c: L.lib.mbpo_icem_plan_cluster_capacity(L.C.byref(cfg), c) for c in (16, 8, 4, 2)}
+    assert cap[16] >= 1 and cap[2] >= cap[4] >= cap[8] >= cap[16], cap
+    N = cfg.num_samples
+    for B in (1, 2, cap[16], cap[16] + 1, cap[8], cap[8] + 1, cap[4], cap[4] + 1, cap[2], cap[2] + 1, 148, 4096):
+        want = 0
+        for c in (16, 8, 4, 2):
+            if 32 <= -(-N // c) <= 256 and B <= cap[c]:
+                want = c
+                break
+        assert L.lib.mbpo_icem_plan_cluster_size(L.C.byref(cfg), B) == want, (B, want, cap)
+    assert L.lib.mbpo_icem_plan_cluster_size(L.C.byref(cfg), 1) == 16
+    assert L.lib.mbpo_icem_plan_cluster_size(L.C.byref(cfg), 4096) == 0
     one = cem.closed_loop(system_state.x_next, st, 40, cluster=1)
     for c in (2, 4, 8, 16, -1):
         _scribble_shared_memory(mb, cuda_device)
