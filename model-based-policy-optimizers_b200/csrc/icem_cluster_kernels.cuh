@@ -33,6 +33,11 @@ namespace mbpo {
 
 namespace cg = cooperative_groups;
 
+// Ranked selection up to this many candidate rows per warp (measured at 8.25 rows per warp, C = 4: 70 us against 80 us
+// with the one-CTA selection; at 16.5, C = 2, the all-pairs count loses).
+#ifndef MBPO_RANKED_ROWS_PER_WARP
+#define MBPO_RANKED_ROWS_PER_WARP 9
+#endif
 #ifndef MBPO_QUIET_SCHED
 #define MBPO_QUIET_SCHED 1
 #endif
@@ -282,7 +287,7 @@ __device__ __forceinline__ void plan_problem_cluster(const PlanArgs& a, const Cl
     // compact loop beats its unrolled form (measured: 3,400 cycles unrolled over 20 keys per lane).
     // (the choice must be the same in every CTA of the cluster -- the ranked CTAs send the best elite's key to all,
     // the others read it from their own list -- so it is made on the largest row count, rank 0's)
-    const bool ranked = 2 * (R + (a.Np + C - 1) / C) <= NT;
+    const bool ranked = (R + (a.Np + C - 1) / C) <= MBPO_RANKED_ROWS_PER_WARP * warps;
     uint32_t* n_mine = sm.sel_scratch + 299;                     // (the selection's scratch is dead once it returns)
     int* mine_pos = reinterpret_cast<int*>(sm.sel_scratch) + 300; // ... and ascending position e   (<= K entries each)
     if (ranked) {
