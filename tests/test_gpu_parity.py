@@ -866,6 +866,62 @@ def test_cluster_plan_random_shapes(mb, cuda_device, prng_mode, seed):
     assert ran >= 2
 
 
+@pytest.mark.parametrize("bad", ["nan", "inf"])
+def test_plan_with_all_equal_objectives(mb, cuda_device, prng_mode, bad):
+    """An initial state that is NaN (or has an infinite speed: every reward is -inf) makes EVERY candidate's objective
+    equal: jnp.argsort is stable, so the elites are the last K rows in index order (the kept-elite rows among them),
+    `best_value <= elite_value` is False for NaN and True for -inf.  The one-CTA kernel, every cluster size (ranked
+    selection: ties broken by index; redundant selection: every key in one histogram bin) and the staged plan agree
+    with each other and with the oracle's refit of the kernel's own actions; a normal problem runs beside it."""
+    from mbpo_b200.systems import PendulumSystem
+    horizon, params = 20, dict(num_steps=3)
+    opt, cfg = _cfg(mb, horizon, params)
+    p = orc.ICemParams(**params)
+    N, K, Np = p.num_samples, p.num_elites, cfg.num_prev_elites
+    M = N + Np
+    sp = PendulumSystem().reset(device=cuda_device).system_params
+    x0 = _random_states(2, 71)
+    x0[1] = [np.nan, np.nan, np.nan] if bad == "nan" else [1.0, 0.0, np.inf]
+    keys = _keys(2, seed=72)
+    seq = np.random.default_rng(73).uniform(-1, 1, (2, horizon, 1)).astype(np.float32)
+    args = (_dev(x0, cuda_device), _dev(keys, cuda_device), _dev(seq, cuda_device), sp)
+    ref = opt._plan_raw(*args, trace=True, cluster=1)
+    tr = {k: v.cpu().numpy() for k, v in ref[3].items()}
+    vals = tr["values"][:, 1]
+    assert np.all(np.isnan(vals)) if bad == "nan" else np.all(np.isneginf(vals))
+    for it in range(p.num_steps):
+        assert np.array_equal(tr["elite_idx"][it, 1], np.arange(M - K, M)), "stable argsort of equal keys"
+    # the oracle's refit of the kernel's own actions and values, iteration by iteration
+    mean = np.zeros((horizon, 1), np.float32)
+    mean[:-1] = seq[1, 1:]
+    mean[-1] = seq[1, -1]
+    std = np.full((horizon, 1), p.init_std, np.float32)
+    bval, bseq = np.float32(-np.inf), mean.copy()
+    for it in range(p.num_steps):
+        acts = tr["actions"][it, 1].reshape(M, horizon, 1)
+        mean, std, bval, bseq, idx = orc.icem_refit(acts, tr["values"][it, 1], mean, std, bval, bseq, p)
+        assert np.array_equal(tr["elite_idx"][it, 1], idx)
+        assert np.array_equal(tr["mean"][it, 1], mean[:, 0]) and np.array_equal(tr["std"][it, 1], std[:, 0])
+    assert np.array_equal(ref[0][1].cpu().numpy(), bseq)
+    got_val = ref[1][1].item()
+    assert np.isneginf(got_val) and np.isneginf(bval)       # NaN never replaces -inf; -inf <= -inf takes the elite
+    if bad == "inf":
+        assert np.array_equal(bseq, tr["actions"][p.num_steps - 1, 1].reshape(M, horizon, 1)[M - 1])
+    for c in (2, 4, 8, 16):
+        _scribble_shared_memory(mb, cuda_device)
+        got = opt._plan_raw(*args, trace=True, cluster=c)
+        assert torch.equal(got[0], ref[0]), "cluster %d" % c
+        assert torch.equal(got[1].view(torch.int32), ref[1].view(torch.int32))
+        for name in ("actions", "values", "elite_idx", "mean", "std", "best_value"):
+            a_, b_ = got[3][name], ref[3][name]
+            if a_.dtype.is_floating_point:               # NaN == NaN here (the payload of a dumped NaN is not specified)
+                assert torch.equal(torch.isnan(a_), torch.isnan(b_)), "cluster %d: %s" % (c, name)
+                a_, b_ = torch.nan_to_num(a_, nan=0.0), torch.nan_to_num(b_, nan=0.0)
+            assert torch.equal(a_, b_), "cluster %d: %s" % (c, name)
+    staged = opt._plan_raw(*args, staged=True)
+    assert torch.equal(staged[0], ref[0]) and torch.equal(staged[1].view(torch.int32), ref[1].view(torch.int32))
+
+
 def test_cluster_choice_and_closed_loop(mb, cuda_device, prng_mode):
     """The library spreads few problems over clusters by itself (B = 1 -> 16 CTAs, ...) and the closed loop
     (tests/test_icemopt.py:19-32) on a cluster reproduces the one-CTA closed loop bit for bit."""
