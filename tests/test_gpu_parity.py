@@ -922,6 +922,40 @@ def test_plan_with_all_equal_objectives(mb, cuda_device, prng_mode, bad):
     assert torch.equal(staged[0], ref[0]) and torch.equal(staged[1].view(torch.int32), ref[1].view(torch.int32))
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_cluster_closed_loop_random_shapes(mb, cuda_device, prng_mode, seed):
+    """The one-launch closed loop on clusters against the one-CTA closed loop for random populations, bounds,
+    momentum, noise colours and batch sizes (states, rewards, actions, final sequence and key: bit-identical)."""
+    from mbpo_b200.optimizers import iCemTO, iCemParams
+    from mbpo_b200.systems import PendulumSystem
+    rng = np.random.default_rng(9500 + seed)
+    horizon = int(rng.choice([8, 15, 20, 30]))
+    N = int(rng.integers(64, 700))
+    params = dict(num_samples=N, num_elites=int(rng.integers(4, max(5, N // 6))), num_steps=int(rng.integers(1, 4)),
+                  elite_set_fraction=float(rng.choice([0.0, 0.3, 0.5])), alpha=float(rng.choice([0.0, 0.2])),
+                  exponent=float(rng.choice([0.0, 2.0])), num_particles=int(rng.choice([1, 3])),
+                  u_min=float(rng.choice([-1.0, -0.5])), u_max=float(rng.choice([1.0, 0.7])))
+    B = int(rng.integers(1, 4))
+    cem = iCemTO(horizon=horizon, action_dim=1, opt_params=iCemParams(**params))
+    cem.set_system(PendulumSystem())
+    x = _dev(_random_states(B, 9600 + seed), cuda_device)
+    st = cem.init(_dev(_keys(B, seed=9700 + seed), cuda_device))
+    one = cem.closed_loop(x, st, 6, cluster=1)
+    ran = 0
+    for c in (2, 4, 8, 16):
+        _scribble_shared_memory(mb, cuda_device)
+        try:
+            got = cem.closed_loop(x, st, 6, cluster=c)
+        except mb.MbpoUnsupported:
+            continue
+        ran += 1
+        for a, b in zip(one[:3], got[:3]):
+            assert torch.equal(a, b), "cluster %d %r" % (c, params)
+        assert torch.equal(one[3].best_sequence, got[3].best_sequence)
+        assert torch.equal(one[3].key.view(torch.int32), got[3].key.view(torch.int32))
+    assert ran >= 2
+
+
 def test_cluster_choice_and_closed_loop(mb, cuda_device, prng_mode):
     """The library spreads few problems over clusters by itself (B = 1 -> 16 CTAs, ...) and the closed loop
     (tests/test_icemopt.py:19-32) on a cluster reproduces the one-CTA closed loop bit for bit."""
