@@ -12,8 +12,8 @@
 // radix pass: a 256-bin shared-memory histogram over the 8 most significant bits in which the
 // keys differ locates the bin holding the K-th largest key; everything in higher bins is an
 // elite, and the (few) candidates inside the boundary bin are ranked exactly by brute force.
-// The K elites are then ranked among themselves (K compares each) so that every float sum
-// below runs in the reference's rank order with unfused float32 operations: given identical
+// The elites' positions in the ascending order come out of the same comparisons, so every float
+// sum below runs in the reference's rank order with unfused float32 operations: given identical
 // inputs the refit is bit-identical to the NumPy oracle.
 #pragma once
 #include "mathx.cuh"
@@ -45,7 +45,7 @@ __device__ __forceinline__ uint32_t select_hist_slot(uint32_t bin) { return bin 
 
 // keys      : shared, uint32[M]  total-order keys of the objective values
 // elite_idx : shared, int32[K]   out: argsort(values)[-K:]  (ascending rank)
-// sel_idx   : shared, int32[K]   temporary (unordered selection)
+// sel_idx   : shared, int32[K]   temporary (the keys above the boundary bin)
 // scratch   : shared, uint32[select_scratch_words(K, M)]  temporary
 // row(i, d) : action element d of candidate i
 // mean/std/best_seq : shared float[D], updated in place; best_value: shared float*
@@ -134,7 +134,6 @@ __device__ __forceinline__ void cta_select(const RefitScalars rs, const uint32_t
     bb = __shfl_sync(full, my_bb, L);
     n_above = __shfl_sync(full, my_above, L);
   }
-  const int need = K - n_above;  // elites still to be taken from the boundary bin (>= 1)
 
   MBPO_SEL_CLK(3);
   // ---- 3. classify: above the boundary bin -> elite; inside it -> candidate ------------------
@@ -152,17 +151,27 @@ __device__ __forceinline__ void cta_select(const RefitScalars rs, const uint32_t
   __syncthreads();
 
   MBPO_SEL_CLK(4);
-  // ---- 4. exact choice inside the boundary bin: the `need` largest (key, index) pairs ---------
-  // (four lanes share a candidate's comparisons; the trip counts are uniform so that every lane reaches the shuffles)
+  // ---- 4. ranks.  Every key above the boundary bin outranks every key inside it, so a key above is ranked among the
+  // n_above keys above, a key inside among the nc candidates (+ n_above): rank = number of larger (key, index) pairs;
+  // rank < K is the elite of ascending position K - 1 - rank.  One pass, four lanes per item (the trip counts are
+  // uniform so that every lane reaches the shuffles).
   const int nc = static_cast<int>(misc[3]);
-  for (int base = 0; base < 4 * nc; base += NT) {
+  for (int base = 0; base < 4 * (n_above + nc); base += NT) {
     const int w = base + tid;
-    const int e = w >> 2, g = w & 3;
+    const int item = w >> 2, g = w & 3;
     int larger = 0, ie = 0;
-    uint32_t ke = 0u;
-    if (e < nc) {
-      ie = cand[e];
-      ke = keys[ie];
+    if (item < n_above) {
+      ie = sel_idx[item];
+      const uint32_t ke = sel_key[item];
+      for (int f = g; f < n_above; f += 4) {
+        const int jf = sel_idx[f];
+        const uint32_t kf = sel_key[f];
+        larger += (kf > ke || (kf == ke && jf > ie)) ? 1 : 0;
+      }
+    } else if (item < n_above + nc) {
+      ie = cand[item - n_above];
+      const uint32_t ke = keys[ie];
+      larger = (g == 0) ? n_above : 0;
       for (int f = g; f < nc; f += 4) {
         const int jf = cand[f];
         const uint32_t kf = keys[jf];
@@ -171,34 +180,10 @@ __device__ __forceinline__ void cta_select(const RefitScalars rs, const uint32_t
     }
     larger += __shfl_xor_sync(full, larger, 1);
     larger += __shfl_xor_sync(full, larger, 2);
-    if (e < nc && g == 0 && larger < need) {
-      const uint32_t pos = atomicAdd(&misc[2], 1u);
-      sel_idx[pos] = ie;
-      sel_key[pos] = ke;
-    }
+    if (item < n_above + nc && g == 0 && larger < K) elite_idx[K - 1 - larger] = ie;
   }
   __syncthreads();
-
   MBPO_SEL_CLK(5);
-  // ---- 5. rank the K elites by (key, index) ascending (four lanes per elite) ------------------
-  for (int base = 0; base < 4 * K; base += NT) {
-    const int w = base + tid;
-    const int e = w >> 2, g = w & 3;
-    int rank = 0, ie = 0;
-    if (e < K) {
-      ie = sel_idx[e];
-      const uint32_t ke = sel_key[e];
-      for (int f = g; f < K; f += 4) {
-        const int jf = sel_idx[f];
-        const uint32_t kf = sel_key[f];
-        rank += (kf < ke || (kf == ke && jf < ie)) ? 1 : 0;
-      }
-    }
-    rank += __shfl_xor_sync(full, rank, 1);
-    rank += __shfl_xor_sync(full, rank, 2);
-    if (e < K && g == 0) elite_idx[rank] = ie;
-  }
-  __syncthreads();
   MBPO_SEL_CLK(6);
 
 }

@@ -29,4 +29,4 @@ lib.mbpo_debug_select_clocks.argtypes = [ctypes.c_void_p]; lib.mbpo_debug_select
 sc = list(sbuf)[:7]
 if sc[6] > sc[0] > 0:
     print(json.dumps({"cta_select phases (last call)": {n: sc[i + 1] - sc[i] for i, n in enumerate(
-        ["0 reset + or/and", "1 histogram", "2 boundary bin", "3 classify", "4 boundary exact", "5 rank elites"])}}))
+        ["0 reset + or/and", "1 histogram", "2 boundary bin", "3 classify", "4 ranks", "5 -"])}}))

@@ -20,4 +20,4 @@ sbuf = (ctypes.c_longlong * 16)()
 _lib.lib.mbpo_debug_select_clocks.argtypes = [ctypes.c_void_p]; _lib.lib.mbpo_debug_select_clocks(sbuf)
 sc = list(sbuf)[:7]
 print(json.dumps({"problems": B, "cta_select phases": {n: sc[i + 1] - sc[i] for i, n in enumerate(
-    ["0 reset + or/and", "1 histogram", "2 boundary bin", "3 classify", "4 boundary exact", "5 rank elites"])}, "total": sc[6] - sc[0]}))
+    ["0 reset + or/and", "1 histogram", "2 boundary bin", "3 classify", "4 ranks", "5 -"])}, "total": sc[6] - sc[0]}))
