@@ -137,15 +137,31 @@ __device__ __forceinline__ void cta_select(const RefitScalars rs, const uint32_t
 
   MBPO_SEL_CLK(3);
   // ---- 3. classify: above the boundary bin -> elite; inside it -> candidate ------------------
-  for (int i = tid; i < M; i += NT) {
-    const uint32_t k = keys[i];
-    const int d = static_cast<int>((k >> shift) & 255u);
+  // (a warp reserves its slots of either list with one atomic: the two cursors are the only contended words)
+  for (int base = 0; base < M; base += NT) {
+    const int i = base + tid;
+    uint32_t k = 0u;
+    int d = -1;
+    if (i < M) {
+      k = keys[i];
+      d = static_cast<int>((k >> shift) & 255u);
+    }
+    const unsigned above = __ballot_sync(full, d > bb);
+    const unsigned inside = __ballot_sync(full, d == bb);
+    uint32_t pos_a = 0u, pos_c = 0u;
+    if (lane == 0) {
+      if (above) pos_a = atomicAdd(&misc[2], static_cast<uint32_t>(__popc(above)));
+      if (inside) pos_c = atomicAdd(&misc[3], static_cast<uint32_t>(__popc(inside)));
+    }
+    pos_a = __shfl_sync(full, pos_a, 0);
+    pos_c = __shfl_sync(full, pos_c, 0);
+    const unsigned lt = (1u << lane) - 1u;
     if (d > bb) {
-      const uint32_t pos = atomicAdd(&misc[2], 1u);
+      const uint32_t pos = pos_a + static_cast<uint32_t>(__popc(above & lt));
       sel_idx[pos] = i;
       sel_key[pos] = k;
     } else if (d == bb) {
-      cand[atomicAdd(&misc[3], 1u)] = i;
+      cand[pos_c + static_cast<uint32_t>(__popc(inside & lt))] = i;
     }
   }
   __syncthreads();
