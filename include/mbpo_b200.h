@@ -225,7 +225,7 @@ int mbpo_icem_plan_clustered(const MbpoIcemCfg* cfg_host, const void* sys_params
                              int cluster_size, void* stream);
 int mbpo_icem_plan_cluster_size(const MbpoIcemCfg* cfg_host, int B);
 /* How many clusters of that size run at once on the current device (the GPCs decide, not the SM count: 7 of 16, 15 of
- * 8, 32 of 4, 74 of 2 on a B200); the library's choice is the largest size with B <= capacity, since a second round
+ * 8, 33 of 4, 74 of 2 on a B200); the library's choice is the largest size with B <= capacity, since a second round
  * of clusters costs a whole plan.  0: the size is not available for this configuration. */
 int mbpo_icem_plan_cluster_capacity(const MbpoIcemCfg* cfg_host, int cluster_size);
 

@@ -22,7 +22,7 @@ template <int H>
 int general_plan_entry(int system_kind, int prng_mode, const PlanArgs& a, cudaStream_t st);
 
 // How many clusters of `cluster` CTAs of the cluster plan (mpc: of the closed loop) run at once on the current device
-// (cudaOccupancyMaxActiveClusters: the GPCs, not the SM count, decide -- 7 of 16, 15 of 8, 32 of 4, 74 of 2 on a
+// (cudaOccupancyMaxActiveClusters: the GPCs, not the SM count, decide -- 7 of 16, 15 of 8, 33 of 4, 74 of 2 on a
 // B200); 0 if the size cannot be launched.
 template <int H>
 int plan_cluster_capacity(int prng_mode, int math_mode, bool mpc, int N, int Np, int K, int cluster);
