@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(CLUSTER_MAX_THREADS, 1) icem_plan_cluster_kern
     Key2 k_in{a.key_in[2 * b], a.key_in[2 * b + 1]}, k_new;
     plan_problem_cluster<H, PRNG, MATH>(a, sm, pc, rs, a.best_seq_in + static_cast<size_t>(b) * H, k_in, k_new,
                                         atan2_bounded(x_s, x_c), x_w, b, a.B, R);
-    cluster.sync();   // every CTA has read the zero-row value; no CTA runs ahead into a lagging CTA's buffers
+    cluster.sync();   // no CTA runs ahead into the next problem while a lagging CTA still reads this one's buffers
     if (rank == 0) {
       if (tid < H) a.best_seq_out[static_cast<size_t>(b) * H + tid] = sm.best_seq[tid];
       if (tid == 0) {
