@@ -191,10 +191,11 @@ __device__ __forceinline__ void plan_problem_cluster(const PlanArgs& a, const Cl
   const int warp = tid >> 5, lane = tid & 31;
   const int chunks = (R + 31) >> 5;                        // rollout warps (32 rows each)
   const int warps = NT >> 5;
-  // One rollout warp (R <= 32): the warp that shares its scheduler (warp & 3 == 0) stays idle in the loop, so the
-  // rollout chain -- the critical path -- issues alone.
-  const bool quiet = MBPO_QUIET_SCHED && chunks == 1 && warps == 8;
-  const int sparts = quiet ? 6 : (warps - chunks) / chunks;   // sampling warps per chunk of 32 rows (host: >= 1)
+  // One or two rollout warps (R <= 64): the warps that share a scheduler with them (warp & 3 < chunks) stay idle in
+  // the loop, so the rollout chains -- the critical path -- issue alone; the other 6 (of 8) / 8 (of 16) warps sample.
+  const bool quiet = MBPO_QUIET_SCHED && chunks <= 2 && warps == 8 * chunks;
+  const int sparts = quiet ? ((warps >> 2) * (4 - chunks)) / chunks   // sampling warps per chunk of 32 rows (>= 1)
+                           : (warps - chunks) / chunks;
   const int swarps = chunks * sparts;
   const int n = rank * R + tid;             // the candidate this thread rolls out
   const bool mine = tid < R && n < N;
@@ -208,7 +209,8 @@ __device__ __forceinline__ void plan_problem_cluster(const PlanArgs& a, const Cl
     if (warp >= chunks) {
       // ---- sampling warps: the noise of iteration it + 1 -----------------------------------------------------
       if (it + 1 < a.S) {
-        const int sw = quiet ? ((warp & 3) == 0 ? swarps : warp - 1 - (warp >> 2)) : warp - chunks;
+        const int sw = quiet ? ((warp & 3) < chunks ? swarps : (warp >> 2) * (4 - chunks) + (warp & 3) - chunks)
+                             : warp - chunks;
         if (sw < swarps) {
           const Key2 srng = next_sampling_rng();
           const int chunk = sw / sparts;
