@@ -192,10 +192,22 @@ __device__ __forceinline__ void plan_problem_cluster(const PlanArgs& a, const Cl
   const int chunks = (R + 31) >> 5;                        // rollout warps (32 rows each)
   const int warps = NT >> 5;
   // One or two rollout warps (R <= 64): the warps that share a scheduler with them (warp & 3 < chunks) stay idle in
-  // the loop, so the rollout chains -- the critical path -- issue alone; the other 6 (of 8) / 8 (of 16) warps sample.
+  // the loop -- all of them with one rollout warp, all but one per scheduler with two (warps 4 and 5) -- so that the
+  // rollout chains, the critical path, issue (almost) alone while enough warps remain to hide the sampling under them.
   const bool quiet = MBPO_QUIET_SCHED && chunks <= 2 && warps == 8 * chunks;
-  const int sparts = quiet ? ((warps >> 2) * (4 - chunks)) / chunks   // sampling warps per chunk of 32 rows (>= 1)
-                           : (warps - chunks) / chunks;
+  auto samples = [&](int w) {
+    if (w < chunks) return false;
+    if (!quiet || (w & 3) >= chunks) return true;
+    return chunks == 2 && (w >> 2) == 1;
+  };
+  int n_samplers = 0, sw_mine = 0;
+  for (int w = chunks; w < warps; ++w) {
+    if (samples(w)) {
+      if (w < warp) ++sw_mine;
+      ++n_samplers;
+    }
+  }
+  const int sparts = n_samplers / chunks;                  // sampling warps per chunk of 32 rows (host: >= 1)
   const int swarps = chunks * sparts;
   const int n = rank * R + tid;             // the candidate this thread rolls out
   const bool mine = tid < R && n < N;
@@ -209,8 +221,7 @@ __device__ __forceinline__ void plan_problem_cluster(const PlanArgs& a, const Cl
     if (warp >= chunks) {
       // ---- sampling warps: the noise of iteration it + 1 -----------------------------------------------------
       if (it + 1 < a.S) {
-        const int sw = quiet ? ((warp & 3) < chunks ? swarps : (warp >> 2) * (4 - chunks) + (warp & 3) - chunks)
-                             : warp - chunks;
+        const int sw = samples(warp) ? sw_mine : swarps;
         if (sw < swarps) {
           const Key2 srng = next_sampling_rng();
           const int chunk = sw / sparts;
