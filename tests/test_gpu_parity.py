@@ -956,6 +956,39 @@ def test_cluster_closed_loop_random_shapes(mb, cuda_device, prng_mode, seed):
     assert ran >= 2
 
 
+@pytest.mark.parametrize("B", [1, 40, 600])
+def test_plan_under_cuda_graph_capture(mb, cuda_device, B):
+    """The plan is one launch on the caller's stream with no allocation or synchronisation of its own, so a caller can
+    capture `iCemTO.optimize` in a CUDA graph (cluster launches included) and replay it: same bits as the eager call."""
+    from mbpo_b200.optimizers import iCemTO, iCemParams
+    from mbpo_b200.systems import PendulumSystem
+    cem = iCemTO(horizon=20, action_dim=1, opt_params=iCemParams(num_steps=3))
+    cem.set_system(PendulumSystem())
+    x = _dev(_random_states(B, 41), cuda_device)
+    st = cem.init(_dev(_keys(B, seed=42), cuda_device))
+    eager = cem.optimize(x, st)
+    side = torch.cuda.Stream(device=cuda_device)
+    side.wait_stream(torch.cuda.current_stream(cuda_device))
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            cem.optimize(x, st)                      # warm-up on the side stream (first-use attribute / occupancy calls)
+    torch.cuda.current_stream(cuda_device).wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        captured = cem.optimize(x, st)
+    captured.best_sequence.zero_()
+    graph.replay()
+    torch.cuda.synchronize(cuda_device)
+    assert torch.equal(captured.best_sequence, eager.best_sequence)
+    assert torch.equal(captured.key.view(torch.int32), eager.key.view(torch.int32))
+    # new inputs through the captured buffers
+    x.copy_(_dev(_random_states(B, 43), cuda_device))
+    graph.replay()
+    torch.cuda.synchronize(cuda_device)
+    again = cem.optimize(x, st)
+    assert torch.equal(captured.best_sequence, again.best_sequence)
+
+
 def test_cluster_choice_and_closed_loop(mb, cuda_device, prng_mode):
     """The library spreads few problems over clusters by itself (B = 1 -> 16 CTAs, ...) and the closed loop
     (tests/test_icemopt.py:19-32) on a cluster reproduces the one-CTA closed loop bit for bit."""
